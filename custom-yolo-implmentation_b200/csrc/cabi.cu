@@ -1,0 +1,26 @@
+// C-ABI plumbing shared by every entry point: version, thread-local error text.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace yb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return YB_ERR_CUDA;
+}
+
+}  // namespace yb
+
+extern "C" int yb_abi_version(void) { return YB_ABI_VERSION; }
+extern "C" const char *yb_last_error(void) { return yb::g_err; }

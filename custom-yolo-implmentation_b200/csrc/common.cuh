@@ -1,0 +1,184 @@
+// Shared device/host helpers for the box-path kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/yolo_boxpath.h"
+
+namespace yb {
+
+// ---- host-side error plumbing (cabi.cu) -------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define YB_CUDA(call)                                            \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return ::yb::cuda_fail(e__, #call); \
+    } while (0)
+
+#define YB_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::yb::set_error(__VA_ARGS__); \
+            return YB_ERR_ARG;           \
+        }                                \
+    } while (0)
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+constexpr int kRegMax = 16;        // bins per box side; the only value the kernels are built for
+constexpr float kEpsIou = 1e-6f;   // src/model/losses.py:40
+constexpr float kEpsLog = 1e-12f;  // src/model/losses.py:53-54
+
+// ---- 128-bit streaming access --------------------------------------------------------------
+// Head outputs and gradients are touched exactly once per step: keep them out of L1 and mark them
+// evict-first in L2 so the small reused tables (GT, match table, anchors) stay resident.
+__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream16(void *p, const uint4 &v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+template <typename T>
+struct ElemsPer16;
+template <>
+struct ElemsPer16<float> {
+    static constexpr int value = 4;
+};
+template <>
+struct ElemsPer16<__nv_bfloat16> {
+    static constexpr int value = 8;
+};
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // round-to-nearest-even, as Tensor.to(bfloat16)
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// A "group" is the VW consecutive anchors one thread owns: VW = 16 B worth of elements on the
+// vector path, 1 on the scalar fall-back (row pitch or base pointer not 16-byte aligned).
+template <typename T, int VW>
+struct Group;
+
+template <>
+struct Group<float, 4> {
+    uint4 raw;
+    __device__ __forceinline__ void load(const float *p) { raw = ldg_stream16(p); }
+    __device__ __forceinline__ float get(int v) const {
+        return __uint_as_float(v == 0 ? raw.x : v == 1 ? raw.y : v == 2 ? raw.z : raw.w);
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&f)[4]) {
+        stg_stream16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                                   __float_as_uint(f[3])));
+    }
+    static __device__ __forceinline__ void store_zero(float *p) { stg_stream16(p, make_uint4(0, 0, 0, 0)); }
+};
+
+template <>
+struct Group<__nv_bfloat16, 8> {
+    uint4 raw;
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { raw = ldg_stream16(p); }
+    __device__ __forceinline__ float get(int v) const {
+        uint32_t w = (v >> 1) == 0 ? raw.x : (v >> 1) == 1 ? raw.y : (v >> 1) == 2 ? raw.z : raw.w;
+        return (v & 1) ? bf16_hi(w) : bf16_lo(w);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[8]) {
+        stg_stream16(p, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                   pack_bf16x2(f[6], f[7])));
+    }
+    static __device__ __forceinline__ void store_zero(__nv_bfloat16 *p) { stg_stream16(p, make_uint4(0, 0, 0, 0)); }
+};
+
+template <>
+struct Group<float, 1> {
+    float raw;
+    __device__ __forceinline__ void load(const float *p) { raw = __ldg(p); }
+    __device__ __forceinline__ float get(int) const { return raw; }
+    static __device__ __forceinline__ void store(float *p, const float (&f)[1]) { *p = f[0]; }
+    static __device__ __forceinline__ void store_zero(float *p) { *p = 0.f; }
+};
+
+template <>
+struct Group<__nv_bfloat16, 1> {
+    __nv_bfloat16 raw;
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { raw = *p; }
+    __device__ __forceinline__ float get(int) const { return __bfloat162float(raw); }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[1]) { *p = __float2bfloat16_rn(f[0]); }
+    static __device__ __forceinline__ void store_zero(__nv_bfloat16 *p) { *p = __float2bfloat16_rn(0.f); }
+};
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T *p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void store_from_float(T *p, float v);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float *p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- DFL softmax-expectation of one box side ------------------------------------------------
+// Mirrors Tensor.softmax(16 bins) followed by sum(p * [0..15]) (src/model/losses.py:157-159):
+// max-subtracted exp, the bin sum taken in the butterfly order of ATen's 16-lane warp softmax
+// (offsets 8,4,2,1), each probability an IEEE division, products rounded before they are added.
+__device__ __forceinline__ float dfl_expectation16(const float (&x)[16], float (&prob)[16]) {
+    float m = x[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) m = fmaxf(m, x[j]);
+    float e[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j] = expf(x[j] - m);
+    float s8[8], s4[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s8[j] = __fadd_rn(e[j], e[j + 8]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s4[j] = __fadd_rn(s8[j], s8[j + 4]);
+    const float sum = __fadd_rn(__fadd_rn(s4[0], s4[2]), __fadd_rn(s4[1], s4[3]));
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        prob[j] = __fdiv_rn(e[j], sum);
+        acc = __fadd_rn(acc, __fmul_rn(prob[j], (float)j));
+    }
+    return acc;
+}
+
+// Pixel-space box of one anchor from its four expected distances (src/model/losses.py:178-186).
+struct PredBox {
+    float x1, y1, x2, y2, cx, cy, w, h;
+};
+__device__ __forceinline__ PredBox decode_box(float ax, float ay, float s, float dl, float dt, float dr, float db) {
+    PredBox b;
+    b.x1 = __fmul_rn(__fsub_rn(ax, dl), s);
+    b.y1 = __fmul_rn(__fsub_rn(ay, dt), s);
+    b.x2 = __fmul_rn(__fadd_rn(ax, dr), s);
+    b.y2 = __fmul_rn(__fadd_rn(ay, db), s);
+    b.w = __fsub_rn(b.x2, b.x1);
+    b.h = __fsub_rn(b.y2, b.y1);
+    b.cx = __fmul_rn(__fadd_rn(b.x1, b.x2), 0.5f);
+    b.cy = __fmul_rn(__fadd_rn(b.y1, b.y2), 0.5f);
+    return b;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace yb

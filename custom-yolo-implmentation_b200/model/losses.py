@@ -1,0 +1,289 @@
+"""Drop-in for the reference's ``src/model/losses.py`` on CUDA devices.
+
+Same public names, arguments and return values:
+
+  YoloDFLQFLoss(num_classes=171, lambda_box=1.5, lambda_cls=1.0, lambda_dfl=1.5, reg_max=16)
+      .forward(preds, gt_boxes_list, anchors, strides) -> (loss, {"total_loss","box_loss","cls_loss"})
+  bbox_iou(box1, box2)                                  (reference :9-40)
+  quality_focal_loss(pred_scores, target_scores, beta)  (reference :46-57)
+  distribution_focal_loss(pred_dist, target_val)        (reference :63-78)
+
+``forward`` runs the whole of reference lines 140-281 *and* the backward of it in three CUDA
+launches (``csrc/loss.cu``): the gradient w.r.t. ``preds`` is produced during the forward call and
+handed to autograd by ``_FusedLoss.backward``.  The reference's behaviours that decide results are
+kept — see SURVEY.md §0.2 (Q1-Q7, Q16) and DESIGN.md.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi
+
+__all__ = ["YoloDFLQFLoss", "bbox_iou", "quality_focal_loss", "distribution_focal_loss", "pack_gt", "fused_loss"]
+
+
+# ----------------------------------------------------------------------------------------------
+# host logic: GT list -> one concatenated tensor + offsets (no per-image device work, no sync)
+# ----------------------------------------------------------------------------------------------
+def pack_gt(gt_boxes_list: Sequence[torch.Tensor], device) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
+    """``list[(Mi, 5)]`` -> ``(gt (sum Mi, 5) fp32, offsets (N+1,) int32, counts)`` on ``device``.
+
+    The counts come from tensor *shapes*, so nothing here waits for the GPU.  Boxes are cast to
+    fp32 as the reference does (``gt_boxes[:, 0:4].to(preds.dtype)`` with preds already float,
+    losses.py:208); the class column is truncated toward zero inside the kernel (``.long()``, :257).
+    """
+    counts = []
+    parts = []
+    for i, g in enumerate(gt_boxes_list):
+        if not isinstance(g, torch.Tensor):
+            raise TypeError(f"gt_boxes_list[{i}] must be a tensor, got {type(g).__name__}")
+        if g.numel() == 0:
+            counts.append(0)
+            continue
+        if g.dim() != 2 or g.shape[1] < 5:
+            raise ValueError(f"gt_boxes_list[{i}] must have shape (Mi, 5), got {tuple(g.shape)}")
+        counts.append(int(g.shape[0]))
+        parts.append(g[:, :5].to(device=device, dtype=torch.float32))
+    offsets = [0]
+    for c in counts:
+        offsets.append(offsets[-1] + c)
+    if parts:
+        gt = torch.cat(parts, 0).contiguous() if len(parts) > 1 else parts[0].contiguous()
+    else:
+        gt = torch.zeros(0, 5, dtype=torch.float32, device=device)
+    off = torch.tensor(offsets, dtype=torch.int32).to(device, non_blocking=True)
+    return gt, off, counts
+
+
+def _workspace(n_bytes: int, device) -> torch.Tensor:
+    return torch.empty(max(n_bytes, 16), dtype=torch.uint8, device=device)
+
+
+def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, gmax: int, anchors: torch.Tensor,
+               strides: torch.Tensor, num_classes: int, lambda_cls: float, lambda_dfl: float, reg_max: int = 16,
+               want_grad: bool = True, want_trace: bool = False):
+    """One call of ``yb_loss_fwd_bwd``.  Returns ``(out_loss (8,), grad or None, trace dict)``.
+
+    ``out_loss`` = [total, mean DFL, mean QFL, #matched anchors, 0...] on the device.
+    ``trace`` (``want_trace``) holds the per-GT matched anchor / IoU and per-image loss terms the
+    parity tests compare against the oracle.
+    """
+    _cabi.require_cuda(preds, "preds")
+    if preds.dim() != 3:
+        raise ValueError(f"preds must be (N, 4*reg_max + nc, A), got {tuple(preds.shape)}")
+    n, c, a = preds.shape
+    if c != 4 * reg_max + num_classes:
+        raise ValueError(f"preds has {c} channels, expected 4*{reg_max} + {num_classes}")
+    dev = preds.device
+    dt = _cabi.dtype_code(preds.dtype)
+    x = preds.detach()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    anc = anchors.detach().to(device=dev, dtype=torch.float32).contiguous()
+    st = strides.detach().to(device=dev, dtype=torch.float32).contiguous()
+    if anc.shape != (2, a) or st.numel() != a:
+        raise ValueError(f"anchors must be (2, {a}) and strides (1, {a}); got {tuple(anc.shape)}, {tuple(st.shape)}")
+    gt_total = int(gt.shape[0])
+    lib = _cabi.lib()
+    ws_bytes = lib.yb_loss_workspace_bytes(n, a, gt_total, dt)
+    ws = _workspace(ws_bytes, dev)
+    grad = torch.empty_like(x) if want_grad else None
+    out = torch.empty(8, dtype=torch.float32, device=dev)
+    trace = {}
+    idx = iou = per_image = None
+    if want_trace:
+        idx = torch.empty(max(gt_total, 1), dtype=torch.int32, device=dev)
+        iou = torch.empty(max(gt_total, 1), dtype=torch.float32, device=dev)
+        per_image = torch.empty(2, n, dtype=torch.float32, device=dev)
+        trace = {"idx": idx[:gt_total], "iou": iou[:gt_total], "dfl_per_image": per_image[0], "cls_per_image": per_image[1]}
+    with torch.cuda.device(dev):
+        rc = lib.yb_loss_fwd_bwd(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st),
+                                 _cabi.ptr(gt) if gt_total else None, _cabi.ptr(gt_offsets), gt_total, gmax,
+                                 float(lambda_cls), float(lambda_dfl), _cabi.ptr(grad), _cabi.ptr(out),
+                                 _cabi.ptr(idx), _cabi.ptr(iou), _cabi.ptr(per_image), _cabi.ptr(ws), ws.numel(),
+                                 _cabi.stream_ptr(dev))
+    _cabi.check(rc, "yb_loss_fwd_bwd")
+    _cabi.count_launches(3 if gt_total else 2)
+    return out, grad, trace
+
+
+class _FusedLoss(torch.autograd.Function):
+    """Autograd bridge: forward launches the fused fwd+bwd kernels, backward hands the stored
+    gradient over (scaled in place by ``grad_output`` only when that is not exactly 1)."""
+
+    @staticmethod
+    def forward(ctx, preds, gt, gt_offsets, gmax, anchors, strides, num_classes, lambda_cls, lambda_dfl, reg_max, need,
+                holder):
+        out, grad, _ = fused_loss(preds, gt, gt_offsets, gmax, anchors, strides, num_classes, lambda_cls, lambda_dfl,
+                                  reg_max, want_grad=need)
+        ctx.grad = grad
+        holder.append(out)              # the 8-float stats vector; the loss itself is its element 0
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_total):
+        g = ctx.grad
+        ctx.grad = None
+        if g is None:
+            return (None,) * 12
+        scale = grad_total.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(g.device):
+            rc = _cabi.lib().yb_scale_grad(_cabi.ptr(g), _cabi.dtype_code(g.dtype), g.numel(), _cabi.ptr(scale),
+                                           _cabi.stream_ptr(g.device))
+        _cabi.check(rc, "yb_scale_grad")
+        _cabi.count_launches(1)
+        return (g,) + (None,) * 11
+
+
+class YoloDFLQFLoss(nn.Module):
+    """Same constructor and ``forward`` contract as the reference class (losses.py:84-281).
+
+    ``lambda_box`` is accepted and, as in the reference, never used (losses.py:88, :275).
+    ``forward`` returns ``(total_loss, {"total_loss", "box_loss", "cls_loss"})`` with the dict holding
+    Python floats; they are fetched with ONE device-to-host copy instead of three ``.item()`` syncs.
+    ``last_stats`` keeps the 8-float device vector [total, dfl, cls, #matched, ...] of the last call
+    for ``training.distributed_setup.reduce_loss_stats``.
+    """
+
+    def __init__(self, num_classes=171, lambda_box=1.5, lambda_cls=1.0, lambda_dfl=1.5, reg_max=16):
+        super().__init__()
+        self.num_classes = num_classes
+        self.lambda_box = lambda_box
+        self.lambda_cls = lambda_cls
+        self.lambda_dfl = lambda_dfl
+        self.reg_max = reg_max
+        self.last_stats = None
+
+    def forward(self, preds, gt_boxes_list, anchors, strides):
+        n = preds.shape[0]
+        if len(gt_boxes_list) != n:
+            raise IndexError(f"gt_boxes_list has {len(gt_boxes_list)} entries for a batch of {n}")
+        gt, off, counts = pack_gt(gt_boxes_list, preds.device)
+        if n > 0 and sum(counts) == 0:
+            # the reference fails here: total_dfl is still the python float 0.0 (losses.py:271-279)
+            raise AttributeError("'float' object has no attribute 'detach'")
+        need_grad = torch.is_grad_enabled() and preds.requires_grad     # validation runs under no_grad: forward only
+        holder = []
+        total = _FusedLoss.apply(preds, gt, off, max(counts), anchors, strides, self.num_classes,
+                                 self.lambda_cls, self.lambda_dfl, self.reg_max, need_grad, holder)
+        stats = self.last_stats = holder[0]
+        host = stats[:3].tolist()                       # one D2H copy (the reference does three .item())
+        return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2]}
+
+
+# ----------------------------------------------------------------------------------------------
+# public helpers of the reference module
+# ----------------------------------------------------------------------------------------------
+class _BboxIou(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, box1, box2):
+        _cabi.require_cuda(box1, "box1")
+        _cabi.require_cuda(box2, "box2")
+        b1 = box1.detach().float().contiguous()
+        b2 = box2.detach().float().contiguous()
+        if b1.dim() != 2 or b1.shape[1] != 4 or b1.shape != b2.shape:
+            raise ValueError(f"bbox_iou expects two (M, 4) tensors, got {tuple(box1.shape)} and {tuple(box2.shape)}")
+        out = torch.empty(b1.shape[0], dtype=torch.float32, device=b1.device)
+        if b1.shape[0]:
+            with torch.cuda.device(b1.device):
+                rc = _cabi.lib().yb_bbox_iou(_cabi.ptr(b1), _cabi.ptr(b2), b1.shape[0], _cabi.ptr(out), None, None,
+                                             _cabi.stream_ptr(b1.device))
+            _cabi.check(rc, "yb_bbox_iou")
+            _cabi.count_launches(1)
+        ctx.save_for_backward(b1, b2)
+        ctx.in_dtype = box1.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        b1, b2 = ctx.saved_tensors
+        g1 = torch.zeros_like(b1)
+        if b1.shape[0]:
+            go = go.detach().float().contiguous()
+            scratch = torch.empty(b1.shape[0], dtype=torch.float32, device=b1.device)
+            with torch.cuda.device(b1.device):
+                rc = _cabi.lib().yb_bbox_iou(_cabi.ptr(b1), _cabi.ptr(b2), b1.shape[0], _cabi.ptr(scratch),
+                                             _cabi.ptr(go), _cabi.ptr(g1), _cabi.stream_ptr(b1.device))
+            _cabi.check(rc, "yb_bbox_iou")
+            _cabi.count_launches(1)
+        return g1.to(ctx.in_dtype), None
+
+
+def bbox_iou(box1, box2):
+    """Element-wise IoU of (M, 4) xywh pairs -> (M,), eps 1e-6; differentiable w.r.t. ``box1``.
+
+    Reference ``bbox_iou`` (losses.py:9-40) including its ``b1_y2 = h + cy/2`` (line 20)."""
+    return _BboxIou.apply(box1, box2)
+
+
+class _Qfl(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_scores, target_scores, beta):
+        _cabi.require_cuda(pred_scores, "pred_scores")
+        _cabi.require_cuda(target_scores, "target_scores")
+        if beta != 2.0:
+            raise NotImplementedError("quality_focal_loss: the CUDA kernel implements beta == 2.0 (the reference's only use)")
+        if pred_scores.dim() != 2 or pred_scores.shape != target_scores.shape:
+            raise ValueError("quality_focal_loss expects two (M, C) tensors of the same shape")
+        x = pred_scores.detach().float().contiguous()
+        t = target_scores.detach().float().contiguous()
+        m, c = x.shape
+        lib = _cabi.lib()
+        ws = _workspace(lib.yb_qfl_workspace_bytes(x.numel()), x.device)
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if pred_scores.requires_grad else None
+        with torch.cuda.device(x.device):
+            rc = lib.yb_quality_focal_loss(_cabi.ptr(x), _cabi.ptr(t), m, c, float(beta), _cabi.ptr(out),
+                                           _cabi.ptr(grad), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(x.device))
+        _cabi.check(rc, "yb_quality_focal_loss")
+        _cabi.count_launches(2)
+        ctx.grad = grad
+        ctx.in_dtype = pred_scores.dtype
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, go):
+        g = ctx.grad
+        ctx.grad = None
+        return (None if g is None else (g * go).to(ctx.in_dtype)), None, None
+
+
+def quality_focal_loss(pred_scores, target_scores, beta=2.0):
+    """Reference ``quality_focal_loss`` (losses.py:46-57): -sum(...)/M over dense (M, C) tensors."""
+    return _Qfl.apply(pred_scores, target_scores, beta)
+
+
+class _Dfl(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_dist, target_val):
+        _cabi.require_cuda(pred_dist, "pred_dist")
+        _cabi.require_cuda(target_val, "target_val")
+        if pred_dist.dim() != 2 or target_val.dim() != 1 or pred_dist.shape[0] != target_val.shape[0]:
+            raise ValueError("distribution_focal_loss expects pred_dist (M, R) and target_val (M,)")
+        x = pred_dist.detach().float().contiguous()
+        t = target_val.detach().float().contiguous()
+        m, r = x.shape
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if pred_dist.requires_grad else None
+        with torch.cuda.device(x.device):
+            rc = _cabi.lib().yb_distribution_focal_loss(_cabi.ptr(x), _cabi.ptr(t), m, r, _cabi.ptr(out),
+                                                        _cabi.ptr(grad), _cabi.stream_ptr(x.device))
+        _cabi.check(rc, "yb_distribution_focal_loss")
+        _cabi.count_launches(1)
+        ctx.grad = grad
+        ctx.in_dtype = pred_dist.dtype
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, go):
+        g = ctx.grad
+        ctx.grad = None
+        return (None if g is None else (g * go).to(ctx.in_dtype)), None
+
+
+def distribution_focal_loss(pred_dist, target_val):
+    """Reference ``distribution_focal_loss`` (losses.py:63-78): mean over M of the left/right CE."""
+    return _Dfl.apply(pred_dist, target_val)

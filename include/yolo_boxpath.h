@@ -1,0 +1,176 @@
+/* yolo_boxpath.h — C ABI of the B200-native box-geometry hot path.
+ *
+ * The reference (DarylFernandes99/custom-yolo-implmentation) is pure Python and has no plugin /
+ * FFI surface; its boundary for this path is a handful of Python call
+ * signatures.  Each entry point below names the reference function(s) it replaces; the Python
+ * mirror of those signatures (custom-yolo-implmentation_b200/{model,utils,training}/) binds
+ * them through ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises the host except
+ *     the *_host entry points, which say so.
+ *   - return 0 on success, negative yb_status on error; yb_last_error() gives the text
+ *     (thread-local).  No exceptions cross the ABI, no hidden allocations: the caller owns
+ *     every buffer, including the workspace whose size a *_workspace_bytes() query returns.
+ *   - tensors use the reference's layouts: head output (N, 4*reg_max + nc, A) channel-major with
+ *     the anchor axis contiguous (src/model/head.py:119); anchors (2, A); strides (1, A).
+ *   - dtype: YB_F32 or YB_BF16 for the head output and its gradient; all arithmetic is fp32
+ *     (the reference upcasts at src/model/losses.py:142).
+ */
+#ifndef YOLO_BOXPATH_H
+#define YOLO_BOXPATH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_ABI_VERSION 1
+
+typedef enum { YB_F32 = 0, YB_BF16 = 1 } yb_dtype;
+
+typedef enum {
+    YB_OK = 0,
+    YB_ERR_ARG = -1,        /* bad argument (null pointer, non-positive size, unsupported value) */
+    YB_ERR_WORKSPACE = -2,  /* workspace too small */
+    YB_ERR_CUDA = -3,       /* a CUDA runtime call failed; see yb_last_error() */
+    YB_ERR_ALIGN = -4       /* pointer not aligned as documented */
+} yb_status;
+
+int yb_abi_version(void);
+const char *yb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Training: fused decode + nearest-centre assignment + DFL/QFL loss + backward.
+ * Replaces YoloDFLQFLoss.forward and the autograd backward of it
+ * (src/model/losses.py:93-281; invoked at src/training/train_model.py:245, :248/:252).
+ *
+ *   preds        (N, 4*reg_max + nc, A)  dtype            head output
+ *   anchors      (2, A) fp32, strides (1, A) fp32         (src/model/head.py:112-114)
+ *   gt           (gt_total, 5) fp32 [cx, cy, w, h, cls]   all images' boxes concatenated
+ *   gt_offsets   (N + 1) int32                            image b owns rows [off[b], off[b+1])
+ *   gmax         max boxes of any one image (host-known from the list shapes)
+ *   grad_preds   (N, C, A) dtype or NULL                  d total_loss / d preds (NULL: forward only)
+ *   out_loss     8 floats: [0] total  [1] mean DFL ("box_loss")  [2] mean QFL ("cls_loss")
+ *                          [3] number of distinct matched anchors  [4..7] reserved (zero)
+ *   out_idx      (gt_total) int32 or NULL                 matched anchor per GT  (losses.py:215)
+ *   out_iou      (gt_total) fp32  or NULL                 IoU soft target per GT (losses.py:256)
+ *   out_per_image (2, N) fp32 or NULL                     per-image DFL and QFL terms
+ *
+ * The quirks of the reference that decide results are kept (Q1-Q6, Q16).
+ * Images with no boxes contribute their QFL term and count in the mean (Q6).  The all-empty
+ * batch, on which the reference raises, is the caller's to reject (gt_total == 0 is accepted
+ * here and yields the QFL-only loss).
+ * ---------------------------------------------------------------------------------------- */
+size_t yb_loss_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype);
+
+int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                    const float *anchors, const float *strides,
+                    const float *gt, const int32_t *gt_offsets, int gt_total, int gmax,
+                    float lambda_cls, float lambda_dfl,
+                    void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou, float *out_per_image,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* grad *= *scale (device scalar), in place; returns without touching memory when *scale == 1.
+ * Used by the autograd bridge for `loss.backward()` under a GradScaler
+ * (src/training/train_model.py:247-253). */
+int yb_scale_grad(void *grad, int dtype, size_t n_elements, const float *scale, void *stream);
+
+/* Same as yb_loss_fwd_bwd but with HOST buffers (pinned for full speed): copies preds / gt to the
+ * device buffers the caller provides, runs the fused path, copies out_loss (and grad, if
+ * grad_host != NULL) back, and waits for the stream.  This is the end-to-end entry point that
+ * bench.py's `e2e` leg times. */
+int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                         const float *anchors, const float *strides,
+                         const float *gt_host, const int32_t *gt_offsets_host, int gt_total, int gmax,
+                         float lambda_cls, float lambda_dfl,
+                         void *preds_dev, float *gt_dev, int32_t *gt_offsets_dev, void *grad_dev,
+                         float *out_loss_dev, float *out_loss_host, void *grad_host,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decode.  Replaces DFL.forward (src/model/model_blocks.py:278-280), dist2bbox
+ * (src/utils/model_utils.py:120-129) and the decode block of decode_predictions
+ * (src/training/train_model.py:36-109) / Model.inference (src/model/model_builder.py:123-133).
+ *
+ *   box_logits  (N, 4*reg_max, A) rows of a tensor whose image stride is `image_stride` elements
+ *   out_ltrb    (N, 4, A) fp32 or NULL    expected bin per side, grid units
+ *   out_box     (N, 4, A) fp32 or NULL    xywh (box_format 0) or xyxy (1), times stride if scale_by_stride
+ * ---------------------------------------------------------------------------------------- */
+int yb_dfl_decode(const void *box_logits, int dtype, int n_images, int reg_max, int n_anchors, size_t image_stride,
+                  const float *anchors, const float *strides, float *out_ltrb, float *out_box,
+                  int box_format, int scale_by_stride, void *stream);
+
+/* make_anchors (src/utils/model_utils.py:18-70; called at src/model/head.py:94, :112): integer cell
+ * indices, x fastest within a level, levels concatenated, plus the per-anchor stride.
+ *   shapes_host  n_levels x (h, w) int32 on the HOST     strides_host  n_levels floats on the HOST
+ *   out_grid (A, 2) fp32 = (col, row) WITHOUT the offset (the caller adds it in the target dtype so
+ *   that the reference's rounding sequence is kept)       out_strides (A, 1) fp32 */
+int yb_make_anchors(const int32_t *shapes_host, const float *strides_host, int n_levels, float *out_grid,
+                    float *out_strides, void *stream);
+
+/* ltrb (N, 4, A) fp32 + anchors (2, A) -> box (N, 4, A); dist2bbox with dim=1. */
+int yb_dist2bbox(const float *ltrb, const float *anchors, int n_images, int n_anchors, int xywh, float *out_box,
+                 void *stream);
+
+/* Validation decode: decode + sigmoid + best class + `>= conf` + top-k by score, per image.
+ * Replaces decode_predictions (src/training/train_model.py:14-142).
+ *   out_rows  (N, top_k, 5) fp32 [cx, cy, w, h, cls]   out_count (N) int32   out_anchor (N, top_k) int32 or NULL
+ * Row order: anchor order when at most top_k candidates pass, else score descending (ties: lowest anchor). */
+size_t yb_val_decode_workspace_bytes(int n_images, int n_anchors);
+int yb_val_decode(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                  const float *anchors, const float *strides, float conf_thres, int top_k,
+                  float *out_rows, int32_t *out_count, int32_t *out_anchor,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Eval: batched class-aware NMS.  Replaces non_max_suppression (src/utils/model_utils.py:174-279)
+ * including the torchvision.ops.nms call inside it (:264), for multi_label=False, labels=().
+ *
+ *   prediction (N, 4 + nc, A) fp32: xywh pixels + per-class scores
+ *   iou_thres is a double so that "IoU > thr" is decided exactly as torchvision's CPU kernel does
+ *   class_filter: NULL or n_class_filter int32 class ids to keep (the `classes` argument)
+ *   out_rows  (N, max_det, 6) fp32 [x1, y1, x2, y2, conf, cls]  score descending
+ *   out_count (N) int32        out_anchor (N, max_det) int32 or NULL (anchor index of each row)
+ * The reference's wall-clock abort (:212, :275-277) is not reproduced.
+ * ---------------------------------------------------------------------------------------- */
+size_t yb_nms_workspace_bytes(int n_images, int n_anchors);
+int yb_nms(const float *prediction, int n_images, int nc, int n_anchors,
+           float conf_thres, double iou_thres, int max_det, int agnostic,
+           const int32_t *class_filter, int n_class_filter,
+           float *out_rows, int32_t *out_count, int32_t *out_anchor,
+           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * IoU / box utilities (fp32).
+ *   yb_xywh2xyxy      src/utils/model_utils.py:153-172
+ *   yb_bbox_iou       src/model/losses.py:9-40   element-wise, xywh, eps 1e-6, b1_y2 slip kept;
+ *                     grad_box1 (M,4) or NULL receives d(sum_i go[i]*iou[i]) / d box1
+ *   yb_box_iou        src/utils/model_utils.py:131-151  pairwise xyxy, eps argument
+ *   yb_box_iou_batch  src/training/metrics.py:6-41      pairwise xywh, eps 1e-6
+ * ---------------------------------------------------------------------------------------- */
+int yb_xywh2xyxy(const float *in, size_t n_boxes, float *out, void *stream);
+int yb_bbox_iou(const float *box1, const float *box2, int m, float *out_iou,
+                const float *grad_out, float *grad_box1, void *stream);
+int yb_box_iou(const float *box1, int n, const float *box2, int m, float eps, float *out, void *stream);
+int yb_box_iou_batch(const float *box1, int n, const float *box2, int m, float *out, void *stream);
+
+/* quality_focal_loss (src/model/losses.py:46-57) on dense (M, C) logits/targets, fp32:
+ * out_loss[0] = -sum(...)/M; grad_scores (M, C) or NULL = d out_loss / d pred_scores (times *grad_out if given). */
+size_t yb_qfl_workspace_bytes(size_t n_elements);
+int yb_quality_focal_loss(const float *pred_scores, const float *target_scores, int m, int c, float beta,
+                          float *out_loss, float *grad_scores, void *workspace, size_t workspace_bytes, void *stream);
+
+/* distribution_focal_loss (src/model/losses.py:63-78): pred_dist (M, R) logits, target (M,) in [0, R-1):
+ * out_loss[0] = mean over M; grad_dist (M, R) or NULL = d out_loss / d pred_dist. */
+int yb_distribution_focal_loss(const float *pred_dist, const float *target, int m, int r,
+                               float *out_loss, float *grad_dist, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_BOXPATH_H */

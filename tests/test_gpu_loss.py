@@ -1,0 +1,232 @@
+"""Parity of the fused CUDA loss path (through the C ABI) against the golden vectors of the
+unmodified reference and against the CPU oracle.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (north_star): matched anchor indices bit-exact; fp32 loss values and gradients within
+1e-5 relative (gradients: relative to the largest |gradient| of the tensor, plus an element-wise
+check at 1e-4 on the elements that carry 99.9 % of the gradient mass); bf16 inputs within 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_loss_inputs, load_golden
+from oracle import loss_oracle as L
+from custom_yolo_implmentation_b200.model import losses as P
+from custom_yolo_implmentation_b200.utils import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+F32_RTOL, BF16_RTOL = 1e-5, 1e-2
+
+
+def run_cuda(preds, gts, anchors, strides, nc, dev, **kw):
+    x = preds.to(dev).requires_grad_(True)
+    crit = P.YoloDFLQFLoss(num_classes=nc, **kw)
+    loss, parts = crit(x, [g.to(dev) for g in gts], anchors.to(dev), strides.to(dev))
+    loss.backward()
+    return loss.detach().cpu(), parts, x.grad.detach().cpu(), crit
+
+
+def run_cuda_trace(preds, gts, anchors, strides, nc, dev, want_grad=True, lambda_cls=1.0, lambda_dfl=1.5):
+    gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
+    out, grad, tr = P.fused_loss(preds.to(dev), gt, off, max(counts), anchors.to(dev), strides.to(dev), nc,
+                                 lambda_cls, lambda_dfl, want_grad=want_grad, want_trace=True)
+    idx = tr["idx"].cpu().long()
+    split = lambda t: list(torch.split(t, counts))
+    return out.cpu(), (grad.cpu() if grad is not None else None), split(idx), split(tr["iou"].cpu()), \
+        tr["dfl_per_image"].cpu(), tr["cls_per_image"].cpu()
+
+
+def assert_grad_close(got, ref, rtol):
+    got, ref = got.float(), ref.float()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs()
+    assert err.max().item() <= rtol * scale, f"max |dgrad| {err.max().item():.3e} vs {rtol} * {scale:.3e}"
+    big = ref.abs() > 1e-3 * scale          # elements that matter, checked element-wise
+    if big.any():
+        rel = (err[big] / ref.abs()[big]).max().item()
+        assert rel <= 10 * rtol, f"element-wise relative error {rel:.3e}"
+
+
+def idx_agreement(gpu_idx, ora: L.LossTrace):
+    tot = sum(len(i) for i in ora.idx)
+    bad = []
+    for b, (gi, oi) in enumerate(zip(gpu_idx, ora.idx)):
+        for m in (gi != oi).nonzero()[:, 0].tolist():
+            bad.append((b, m, float(ora.margin[b][m])))
+    return tot, bad
+
+
+@pytest.mark.parametrize("name", ["loss_small_fp32", "loss_conflict_fp32", "loss_nc171_fp32", "loss_small_bf16"])
+def test_loss_matches_reference_golden(name, cuda_device):
+    z, preds, gts, anchors, strides, grad_ref = golden_loss_inputs(name)
+    nc = int(z["meta"][1])
+    rtol = BF16_RTOL if z["meta"][5] else F32_RTOL
+    loss, parts, grad, crit = run_cuda(preds, gts, anchors, strides, nc, cuda_device)
+    assert abs(parts["total_loss"] - float(z["total_loss"])) <= rtol * abs(float(z["total_loss"]))
+    assert abs(parts["box_loss"] - float(z["box_loss"])) <= rtol * abs(float(z["box_loss"]))
+    assert abs(parts["cls_loss"] - float(z["cls_loss"])) <= rtol * abs(float(z["cls_loss"]))
+    assert abs(loss.item() - parts["total_loss"]) == 0.0
+    assert grad.dtype == preds.dtype and grad.shape == preds.shape
+    _, _, idx, iou, _, _ = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    for b in range(len(gts)):
+        m = int(z["gt_count"][b])
+        assert idx[b].tolist() == z["idx"][b, :m].tolist()               # bit-exact matched anchors
+        assert torch.allclose(iou[b], torch.from_numpy(z["iou"][b, :m]), rtol=1e-5, atol=1e-6)
+    assert_grad_close(grad, grad_ref, rtol)
+    # number of distinct matched anchors
+    distinct = sum(len(set(i.tolist())) for i in idx)
+    assert int(crit.last_stats[3].item()) == distinct
+
+
+@pytest.mark.parametrize("n,nc,imgsz,gmax,seed,conflict", [
+    (4, 80, 640, 50, 1235, 0.0),        # cfg1 shape, 4 of its images
+    (3, 80, 640, 100, 1236, 0.05),      # cfg2 GT density, with forced duplicate anchors
+    (2, 20, 320, 300, 1238, 0.0),       # more than 128 GT per image: multi-chunk scan
+    (2, 3, 96, 7, 1239, 0.0),           # A = 189: scalar (unaligned) path
+])
+def test_loss_matches_oracle(n, nc, imgsz, gmax, seed, conflict, cuda_device):
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed, conflict_frac=conflict)
+    out, grad, idx, iou, dfl_img, cls_img = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    ora = L.loss_forward_backward(preds, gts, anchors, strides, nc)
+    tot, bad = idx_agreement(idx, ora)
+    # a mismatch is only acceptable on a numerical near-tie of the distance matrix
+    assert len(bad) <= max(1, tot // 200), f"{len(bad)} of {tot} matched anchors differ: {bad[:5]}"
+    for b, m, margin in bad:
+        assert margin < 5e-3, f"image {b} GT {m}: anchors differ with a runner-up margin of {margin}"
+    if bad:     # compare the remaining stages on the GPU's own matching
+        ora = L.loss_forward_backward(preds, gts, anchors, strides, nc, forced_idx=idx)
+    assert abs(out[0].item() - ora.total.item()) <= F32_RTOL * abs(ora.total.item())
+    assert torch.allclose(dfl_img, ora.dfl_per_image, rtol=F32_RTOL, atol=1e-7)
+    assert torch.allclose(cls_img, ora.cls_per_image, rtol=F32_RTOL, atol=1e-9)
+    for b in range(n):
+        assert torch.allclose(iou[b], ora.iou[b], rtol=1e-4, atol=1e-6)
+    assert_grad_close(grad, ora.grad, F32_RTOL)
+    # box-channel gradient is non-zero only at matched anchors
+    fg = torch.zeros(n, preds.shape[2], dtype=torch.bool)
+    for b in range(n):
+        fg[b, idx[b]] = True
+    assert (grad[:, :64].abs().sum(1) > 0).le(fg).all()
+
+
+def test_bf16_inputs_match_oracle(cuda_device):
+    preds, gts, anchors, strides = syn.make_loss_inputs(3, 80, 640, 60, 1240, dtype=torch.bfloat16)
+    out, grad, idx, iou, _, _ = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
+    ora = L.loss_forward_backward(preds, gts, anchors, strides, 80)
+    tot, bad = idx_agreement(idx, ora)
+    assert len(bad) <= max(1, tot // 200)
+    if bad:
+        ora = L.loss_forward_backward(preds, gts, anchors, strides, 80, forced_idx=idx)
+    assert grad.dtype == torch.bfloat16
+    assert abs(out[0].item() - ora.total.item()) <= BF16_RTOL * abs(ora.total.item())
+    assert_grad_close(grad, ora.grad, BF16_RTOL)
+
+
+def test_cfg1_summary_against_reference(cuda_device):
+    """cfg1 (N=16, 640x640, nc=80, <=50 GT): the reference's own outputs, stored as a summary."""
+    z = load_golden("loss_cfg1_summary")
+    n, nc, imgsz, gmax, seed = (int(v) for v in z["meta"][:5])
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed)
+    out, grad, idx, _, _, _ = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    assert abs(out[0].item() - float(z["total_loss"])) <= F32_RTOL * float(z["total_loss"])
+    assert abs(out[1].item() - float(z["box_loss"])) <= F32_RTOL * float(z["box_loss"])
+    assert abs(out[2].item() - float(z["cls_loss"])) <= F32_RTOL * float(z["cls_loss"])
+    agree = sum(int((idx[b].numpy() == z["idx"][b, : len(idx[b])]).sum()) for b in range(n))
+    assert agree == int(z["gt_count"].sum())                              # 335 of 335 matched anchors
+    g = grad.flatten()
+    samp = g[:: int(z["grad_sample_stride"])]
+    assert (samp - torch.from_numpy(z["grad_sample"])).abs().max().item() <= F32_RTOL * float(z["grad_absmax"])
+    assert abs(g.double().abs().sum().item() - float(z["grad_abs_sum"])) <= 1e-5 * float(z["grad_abs_sum"])
+
+
+def test_full_size_properties_cfg2(cuda_device):
+    """cfg2 (N=128, 640x640, nc=80, <=100 GT): size-independent properties + oracle on a slice."""
+    n, nc = 128, 80
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, 640, 100, 1236)
+    out, grad, idx, iou, dfl_img, cls_img = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    # (1) the total is the weighted mean of the per-image terms
+    total = 1.5 * dfl_img.double().sum() / n + 1.0 * cls_img.double().sum() / n
+    assert abs(out[0].item() - total.item()) <= 2e-6 * abs(total.item())
+    # (2) images are independent: the second half alone gives the same per-image terms bit for bit and,
+    #     1/N being a power of two, exactly twice the gradient
+    h = n // 2
+    out2, grad2, idx2, _, dfl2, cls2 = run_cuda_trace(preds[h:], gts[h:], anchors, strides, nc, cuda_device)
+    assert torch.equal(dfl2, dfl_img[h:]) and torch.equal(cls2, cls_img[h:])
+    assert all(torch.equal(a, b) for a, b in zip(idx2, idx[h:]))
+    assert torch.equal(grad2, grad[h:] * 2)
+    # (3) linearity in the loss weights
+    out3, grad3, _, _, _, _ = run_cuda_trace(preds[:8], gts[:8], anchors, strides, nc, cuda_device, lambda_cls=2.0, lambda_dfl=3.0)
+    out4, grad4, _, _, _, _ = run_cuda_trace(preds[:8], gts[:8], anchors, strides, nc, cuda_device)
+    assert torch.allclose(grad3, 2 * grad4, rtol=1e-6, atol=0)
+    assert abs(out3[0].item() - 2 * out4[0].item()) <= 1e-6 * abs(out3[0].item())
+    # (4) repeatability: the whole path is deterministic
+    out5, grad5, idx5, _, _, _ = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    assert torch.equal(out5, out) and torch.equal(grad5, grad)
+    # (5) oracle on 6 of the 128 images (per-image terms do not depend on the rest of the batch)
+    sel = [0, 1, 2, 50, 100, 127]
+    ora = L.loss_forward_backward(preds[sel], [gts[i] for i in sel], anchors, strides, nc)
+    for k, i in enumerate(sel):
+        if not torch.equal(idx[i], ora.idx[k]):
+            bad = (idx[i] != ora.idx[k]).nonzero()[:, 0]
+            assert float(ora.margin[k][bad].max()) < 5e-3
+            continue
+        assert abs(dfl_img[i].item() - ora.dfl_per_image[k].item()) <= F32_RTOL * max(abs(ora.dfl_per_image[k].item()), 1e-6)
+        assert abs(cls_img[i].item() - ora.cls_per_image[k].item()) <= F32_RTOL * abs(ora.cls_per_image[k].item())
+        assert_grad_close(grad[i] * (n / len(sel)), ora.grad[k], F32_RTOL)
+
+
+def test_forward_only_under_no_grad_and_empty_batch(cuda_device):
+    preds, gts, anchors, strides = syn.make_loss_inputs(3, 6, 128, 10, 101)
+    crit = P.YoloDFLQFLoss(num_classes=6)
+    x = preds.to(cuda_device).requires_grad_(True)
+    g = [t.to(cuda_device) for t in gts]
+    with torch.no_grad():
+        loss, parts = crit(x, g, anchors.to(cuda_device), strides.to(cuda_device))
+    assert not loss.requires_grad
+    loss2, parts2 = crit(x, g, anchors.to(cuda_device), strides.to(cuda_device))
+    assert parts == parts2 and loss2.requires_grad
+    with pytest.raises(AttributeError):        # the reference fails the same way
+        crit(x, [torch.zeros(0, 5, device=cuda_device)] * 3, anchors.to(cuda_device), strides.to(cuda_device))
+
+
+def test_grad_output_scaling_and_noncontiguous_input(cuda_device):
+    preds, gts, anchors, strides = syn.make_loss_inputs(2, 6, 128, 10, 55)
+    _, _, g1, _ = run_cuda(preds, gts, anchors, strides, 6, cuda_device)
+    x = preds.to(cuda_device).requires_grad_(True)
+    crit = P.YoloDFLQFLoss(num_classes=6)
+    loss, _ = crit(x, [g.to(cuda_device) for g in gts], anchors.to(cuda_device), strides.to(cuda_device))
+    (loss * 1024.0).backward()                   # GradScaler-style scaled backward
+    assert torch.equal(x.grad.cpu(), g1 * 1024.0)
+    # a transposed (non-contiguous) view of the same values, and a non-leaf input
+    xt = preds.transpose(1, 2).contiguous().to(cuda_device).requires_grad_(True)
+    loss_t, _ = crit((xt * 1.0).transpose(1, 2), [g.to(cuda_device) for g in gts], anchors.to(cuda_device), strides.to(cuda_device))
+    loss_t.backward()
+    assert torch.equal(xt.grad.transpose(1, 2).cpu(), g1)
+
+
+def test_host_entry_point_matches_device_entry_point(cuda_device):
+    """yb_loss_fwd_bwd_host (pinned host buffers in, loss and gradient out)."""
+    from custom_yolo_implmentation_b200 import _cabi
+    n, nc = 4, 80
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, 640, 50, 99)
+    out, grad, _, _, _, _ = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    a = preds.shape[2]
+    counts = [g.shape[0] for g in gts]
+    gt_host = torch.cat(gts).contiguous().pin_memory()
+    off_host = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32).pin_memory()
+    preds_host = preds.pin_memory()
+    grad_host = torch.empty_like(preds).pin_memory()
+    loss_host = torch.zeros(8).pin_memory()
+    dev = cuda_device
+    preds_dev = torch.empty_like(preds, device=dev); grad_dev = torch.empty_like(preds, device=dev)
+    gt_dev = torch.empty(sum(counts), 5, device=dev); off_dev = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    loss_dev = torch.empty(8, device=dev)
+    lib = _cabi.lib()
+    ws = torch.empty(lib.yb_loss_workspace_bytes(n, a, sum(counts), 0), dtype=torch.uint8, device=dev)
+    anc, st = anchors.to(dev), strides.to(dev)
+    rc = lib.yb_loss_fwd_bwd_host(_cabi.ptr(preds_host), 0, n, nc, 16, a, _cabi.ptr(anc), _cabi.ptr(st), _cabi.ptr(gt_host),
+                                  _cabi.ptr(off_host), sum(counts), max(counts), 1.0, 1.5, _cabi.ptr(preds_dev),
+                                  _cabi.ptr(gt_dev), _cabi.ptr(off_dev), _cabi.ptr(grad_dev), _cabi.ptr(loss_dev),
+                                  _cabi.ptr(loss_host), _cabi.ptr(grad_host), _cabi.ptr(ws), ws.numel(),
+                                  _cabi.stream_ptr(dev))
+    _cabi.check(rc, "yb_loss_fwd_bwd_host")
+    assert torch.equal(loss_host[:4], out[:4]) and torch.equal(grad_host, grad)

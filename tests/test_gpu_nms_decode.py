@@ -1,0 +1,200 @@
+"""Parity of the CUDA decode / NMS / IoU-utility kernels (through the C ABI) against the reference's
+golden vectors and the CPU oracle.  Needs a B200: run with ``-m gpu``.
+
+Integer results (keep lists, class ids, anchor indices, row order) are compared bit-exactly; the NMS
+output rows are compared bit-exactly too (they are copies / exact fp32 arithmetic of the input)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import decode_oracle as D
+from oracle import loss_oracle as L
+from oracle import nms_oracle as N
+from custom_yolo_implmentation_b200.model import losses as PL
+from custom_yolo_implmentation_b200.model.model_blocks import DFL, dfl_decode
+from custom_yolo_implmentation_b200.training.metrics import box_iou_batch
+from custom_yolo_implmentation_b200.training.train_model import decode_predictions, decode_predictions_raw
+from custom_yolo_implmentation_b200.utils import model_utils as U
+from custom_yolo_implmentation_b200.utils import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("name", ["nms_small", "nms_dense_maxdet", "nms_agnostic", "nms_classes", "nms_few"])
+def test_nms_matches_reference_golden(name, cuda_device):
+    z = load_golden(name)
+    n, nc, _, _, max_det, agnostic, _ = (int(v) for v in z["meta"])
+    classes = z["classes"].tolist() or None
+    out = U.non_max_suppression(torch.from_numpy(z["prediction"]).to(cuda_device), float(z["conf"]), float(z["iou"]),
+                                classes=classes, agnostic=bool(agnostic), max_det=max_det, nc=nc)
+    assert len(out) == n
+    for b in range(n):
+        k = int(z["count"][b])
+        assert out[b].shape == (k, 6)
+        assert np.array_equal(out[b].cpu().numpy(), z["rows"][b, :k])          # bit-exact rows, same order
+
+
+def _check_against_oracle(x, conf, iou, max_det, nc, dev, agnostic=False, classes=None):
+    rows, count, anchor = U.batched_nms_raw(x.to(dev), conf, iou, max_det, nc, agnostic, classes, want_anchor=True)
+    ora = N.nms_forward(x, conf, iou, classes=classes, agnostic=agnostic, max_det=max_det, nc=nc)
+    count = count.cpu()
+    for b in range(x.shape[0]):
+        k = int(count[b])
+        assert k == ora.rows[b].shape[0], f"image {b}: kept {k} vs oracle {ora.rows[b].shape[0]}"
+        assert torch.equal(anchor[b, :k].cpu().long(), ora.keep_anchor[b])   # keep list, bit-exact, in order
+        assert torch.equal(rows[b, :k].cpu(), ora.rows[b])
+    return count
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_nms_cfg4_shape_against_oracle(dense, cuda_device):
+    """cfg4 shape (8400 candidates, nc=80, conf 0.001, IoU 0.7, max_det 300) on 4 images."""
+    x = syn.make_nms_input(4, 80, 640, 4321 + dense, dense_uniform=dense)
+    cnt = _check_against_oracle(x, 0.001, 0.7, 300, 80, cuda_device)
+    assert int(cnt.min()) == 300
+
+
+def test_nms_edge_cases(cuda_device):
+    x = syn.make_nms_input(3, 5, 160, 77)
+    x[1, 4:] = 0.0005                                   # image with no candidate at all
+    x[2, 4:, 10:] = 0.0                                 # image with exactly 10 candidates
+    _check_against_oracle(x, 0.001, 0.5, 300, 5, cuda_device)
+    _check_against_oracle(x, 0.001, 0.5, 7, 5, cuda_device)               # max_det cap
+    _check_against_oracle(x, 0.001, 0.0, 300, 5, cuda_device)             # IoU threshold 0
+    _check_against_oracle(x, 0.001, 1.0, 300, 5, cuda_device)             # IoU threshold 1: nothing suppressed
+    _check_against_oracle(x, 0.001, 0.6, 300, 5, cuda_device, agnostic=True)
+    _check_against_oracle(x, 0.001, 0.6, 300, 5, cuda_device, classes=[0, 3])
+    out = U.non_max_suppression(x.to(cuda_device), 0.001, 0.5, nc=5)
+    assert out[1].shape == (0, 6)
+    # scalar path: anchor count not a multiple of 4 / unaligned rows
+    y = syn.make_nms_input(2, 3, 96, 78)
+    assert y.shape[2] % 4 != 0
+    _check_against_oracle(y, 0.01, 0.45, 300, 3, cuda_device)
+    # tuple input, nc inferred, argument errors as in the reference
+    out2 = U.non_max_suppression((x.to(cuda_device), None), 0.001, 0.5)
+    assert all(torch.equal(a, b) for a, b in zip(out, out2))
+    with pytest.raises(AssertionError):
+        U.non_max_suppression(x.to(cuda_device), conf_thres=1.5)
+    with pytest.raises(RuntimeError):                   # mask channels: the reference fails in split()
+        U.non_max_suppression(x.to(cuda_device), 0.1, 0.5, nc=3)
+
+
+def test_nms_more_candidates_than_register_columns(cuda_device):
+    """1280x1280 grid (33600 anchors): > 9216 candidates -> the global-scratch sweep, and the 30000 cap."""
+    x = syn.make_nms_input(2, 4, 1280, 91)
+    _check_against_oracle(x, 0.001, 0.6, 300, 4, cuda_device)
+    x[:, 4:] = x[:, 4:] * 0.9 + 0.05                  # every anchor is a candidate: 33600 > max_nms
+    _check_against_oracle(x, 0.001, 0.6, 300, 4, cuda_device)
+
+
+def test_nms_full_cfg4_properties(cuda_device):
+    """cfg4 at full size (N=64): structural properties on all images, oracle on 3 of them."""
+    n, nc, thr = 64, 80, 0.7
+    x = syn.make_nms_input(n, nc, 640, 2024)
+    rows, count, anchor = U.batched_nms_raw(x.to(cuda_device), 0.001, thr, 300, nc, want_anchor=True)
+    count = count.cpu()
+    assert int(count.min()) > 0
+    for b in range(n):
+        r = rows[b, : int(count[b])]
+        assert bool((r[1:, 4] <= r[:-1, 4]).all())                         # score descending
+        a = anchor[b, : int(count[b])].long()
+        assert a.unique().numel() == a.numel()
+        # no kept pair of one class overlaps above the threshold (IoU on the class-offset boxes)
+        off = r[:, :4] + r[:, 5:6] * 7680.0
+        iou = U.box_iou(off, off, eps=0.0)
+        iou.fill_diagonal_(0)
+        assert float(iou.max()) <= thr
+    sel = [0, 31, 63]
+    ora = N.nms_forward(x[sel], 0.001, thr, max_det=300, nc=nc)
+    for k, b in enumerate(sel):
+        assert torch.equal(anchor[b, : int(count[b])].cpu().long(), ora.keep_anchor[k])
+
+
+# --------------------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("name", ["decode_topk", "decode_sparse"])
+def test_decode_matches_reference_golden(name, cuda_device):
+    z = load_golden(name)
+    n, nc, _, _, top_k = (int(v) for v in z["meta"])
+    dev = cuda_device
+    preds, anchors, strides = (torch.from_numpy(z[k]).to(dev) for k in ("preds", "anchors", "strides"))
+    out = decode_predictions(preds, anchors, strides, float(z["conf"]), top_k, nc)
+    for b in range(n):
+        k = int(z["count"][b])
+        assert out[b].shape == (k, 5)
+        ref = torch.from_numpy(z["rows"][b, :k])
+        assert torch.equal(out[b][:, 4].cpu(), ref[:, 4])                 # class ids and row order exact
+        assert torch.allclose(out[b][:, :4].cpu(), ref[:, :4], rtol=1e-5, atol=1e-4)
+    # DFL module + dist2bbox + stride (src/model/model_builder.py:123-133)
+    ltrb = DFL(16).to(dev)(preds[:, :64, :])
+    assert torch.allclose(ltrb.cpu(), torch.from_numpy(z["dfl_ltrb"]), rtol=1e-5, atol=1e-5)
+    box = U.dist2bbox(ltrb, anchors.unsqueeze(0), xywh=True, dim=1) * strides
+    assert torch.allclose(box.cpu(), torch.from_numpy(z["box_xywh"]), rtol=1e-5, atol=1e-4)
+    xyxy = U.dist2bbox(ltrb, anchors.unsqueeze(0), xywh=False, dim=1)
+    assert torch.allclose(xyxy.cpu(), torch.from_numpy(z["box_xyxy_grid"]), rtol=1e-5, atol=1e-4)
+    # fused decode in one launch
+    _, fused = dfl_decode(preds, anchors, strides, box_format="xywh")
+    assert torch.allclose(fused.cpu(), torch.from_numpy(z["box_xywh"]), rtol=1e-5, atol=1e-4)
+
+
+def test_val_decode_against_oracle_full_grid(cuda_device):
+    anchors, strides = syn.anchor_grid(640)
+    for seed, conf, top_k, mean, dt in [(5, 0.25, 100, -1.0, torch.float32), (6, 0.5, 100, -6.0, torch.float32),
+                                        (7, 0.25, 17, -2.0, torch.float32), (8, 0.25, 100, -1.0, torch.bfloat16)]:
+        preds = syn.make_preds(3, 80, anchors.shape[1], seed, cls_mean=mean, cls_std=1.5, dtype=dt)
+        rows, count, anchor = decode_predictions_raw(preds.to(cuda_device), anchors.to(cuda_device), strides.to(cuda_device),
+                                                     conf, top_k, 80, want_anchor=True)
+        ora = D.val_decode(preds.float(), anchors, strides, conf, top_k, 80)
+        for b in range(3):
+            k = int(count[b])
+            assert k == ora.rows[b].shape[0]
+            if dt == torch.float32:
+                # bit-exact rows order unless two scores tie to the last ulp between CPU and GPU sigmoid
+                same = anchor[b, :k].cpu().long() == ora.anchor[b]
+                assert same.float().mean().item() >= 0.97
+                sel = same.nonzero()[:, 0]
+                assert torch.allclose(rows[b, :k].cpu()[sel], ora.rows[b][sel], rtol=1e-5, atol=1e-4)
+            else:
+                assert set(anchor[b, :k].cpu().tolist()) & set(ora.anchor[b].tolist())
+
+
+def test_make_anchors_and_helpers_match_reference(cuda_device):
+    z = load_golden("helpers")
+    dev = cuda_device
+    t = lambda k: torch.from_numpy(z[k]).to(dev)
+    lv = [torch.zeros(1, 1, 6, 5, device=dev), torch.zeros(1, 1, 3, 3, device=dev), torch.zeros(1, 1, 2, 1, device=dev)]
+    anc, st = U.make_anchors(lv, [8, 16, 32], 0.5)
+    assert torch.equal(anc.cpu(), torch.from_numpy(z["anchors"])) and torch.equal(st.cpu(), torch.from_numpy(z["strides"]))
+    ancb, _ = U.make_anchors([l.bfloat16() for l in lv], [8, 16, 32], 0.5)
+    assert ancb.dtype == torch.bfloat16 and torch.equal(ancb.float().cpu(), torch.from_numpy(z["anchors"]))
+    assert torch.equal(U.xywh2xyxy(t("b1")).cpu(), torch.from_numpy(z["xyxy"]))
+    assert torch.allclose(U.box_iou(t("xyxy"), U.xywh2xyxy(t("q"))).cpu(), torch.from_numpy(z["box_iou"]), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(box_iou_batch(t("b1"), t("q")).cpu(), torch.from_numpy(z["box_iou_batch"]), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(PL.bbox_iou(t("b1"), t("b2")).cpu(), torch.from_numpy(z["bbox_iou"]), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(PL.quality_focal_loss(t("scores"), t("target")).cpu(), torch.from_numpy(z["qfl"]), rtol=1e-5)
+    assert torch.allclose(PL.distribution_focal_loss(t("dist"), t("tval")).cpu(), torch.from_numpy(z["dfl"]), rtol=1e-5)
+
+
+def test_helper_gradients_match_oracle_autograd(cuda_device):
+    z = load_golden("helpers")
+    dev = cuda_device
+    # bbox_iou: d sum(w * iou) / d box1
+    b1 = torch.from_numpy(z["b1"]).clone().requires_grad_(True)
+    w = torch.linspace(0.5, 2.0, b1.shape[0])
+    (L.iou_xywh_reference(b1, torch.from_numpy(z["b2"])) * w).sum().backward()
+    g1 = torch.from_numpy(z["b1"]).to(dev).requires_grad_(True)
+    (PL.bbox_iou(g1, torch.from_numpy(z["b2"]).to(dev)) * w.to(dev)).sum().backward()
+    assert torch.allclose(g1.grad.cpu(), b1.grad, rtol=1e-4, atol=1e-7)
+    # quality_focal_loss
+    s = torch.from_numpy(z["scores"]).clone().requires_grad_(True)
+    (L.qfl_sum(s, torch.from_numpy(z["target"])) * 3.0).backward()
+    gs = torch.from_numpy(z["scores"]).to(dev).requires_grad_(True)
+    (PL.quality_focal_loss(gs, torch.from_numpy(z["target"]).to(dev)) * 3.0).backward()
+    assert torch.allclose(gs.grad.cpu(), s.grad, rtol=1e-4, atol=1e-7)
+    # distribution_focal_loss
+    d = torch.from_numpy(z["dist"]).clone().requires_grad_(True)
+    L.dfl_loss_rows(d, torch.from_numpy(z["tval"])).mean().backward()
+    gd = torch.from_numpy(z["dist"]).to(dev).requires_grad_(True)
+    PL.distribution_focal_loss(gd, torch.from_numpy(z["tval"]).to(dev)).backward()
+    assert torch.allclose(gd.grad.cpu(), d.grad, rtol=1e-4, atol=1e-7)

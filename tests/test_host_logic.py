@@ -1,0 +1,116 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, the host
+logic (GT packing, argument checking, sharding) behaves, and nothing silently falls back to the CPU."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from custom_yolo_implmentation_b200 import _cabi
+from custom_yolo_implmentation_b200.model import losses as P
+from custom_yolo_implmentation_b200.training import distributed_setup as DS
+from custom_yolo_implmentation_b200.training.train_model import decode_predictions
+from custom_yolo_implmentation_b200.utils import model_utils as U
+from custom_yolo_implmentation_b200.utils import synthetic as syn
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "yolo_boxpath.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(yb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.lib()                      # raises if the extension was not built
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/yolo_boxpath.h but not exported"
+    assert sorted(_cabi.EXPORTS) == declared, "the ctypes binding and the header disagree"
+    assert lib.yb_abi_version() == _cabi.ABI_VERSION
+    # size queries are pure host code and safe without a GPU
+    assert lib.yb_loss_workspace_bytes(128, 8400, 6400, 0) > 6400 * 8
+    assert lib.yb_nms_workspace_bytes(64, 8400) >= 64 * 16384 * 8
+    assert lib.yb_loss_workspace_bytes(0, 8400, 0, 0) == 0
+
+
+def test_argument_errors_come_back_through_the_abi():
+    lib = _cabi.lib()
+    rc = lib.yb_loss_fwd_bwd(None, 0, 1, 1, 16, 4, None, None, None, None, 0, 0, 1.0, 1.5, None, None, None, None, None,
+                             None, 0, None)
+    assert rc == -1 and b"null pointer" in lib.yb_last_error()
+    rc = lib.yb_nms(None, 1, 1, 4, 0.1, 0.5, 300, 0, None, 0, None, None, None, None, 0, None)
+    assert rc == -1
+    with pytest.raises(RuntimeError, match="yb_nms failed"):
+        _cabi.check(rc, "yb_nms")
+
+
+def test_no_cpu_fallback():
+    preds, gts, anchors, strides = syn.make_loss_inputs(2, 4, 64, 3, 1)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        P.YoloDFLQFLoss(num_classes=4)(preds, gts, anchors, strides)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        U.non_max_suppression(syn.make_nms_input(1, 4, 64, 1), nc=4)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        decode_predictions(preds, anchors, strides, num_classes=4)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        P.bbox_iou(torch.zeros(2, 4), torch.zeros(2, 4))
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libyolo_boxpath.so")
+    with pytest.raises(_cabi.ExtensionMissing, match="no CPU fallback"):
+        _cabi.lib()
+
+
+def test_pack_gt_layout():
+    gts = [torch.arange(10.).view(2, 5), torch.zeros(0, 5), torch.ones(3, 5, dtype=torch.float64), torch.zeros(0)]
+    gt, off, counts = P.pack_gt(gts, "cpu")
+    assert counts == [2, 0, 3, 0] and off.tolist() == [0, 2, 2, 5, 5] and off.dtype == torch.int32
+    assert gt.shape == (5, 5) and gt.dtype == torch.float32 and gt.is_contiguous()
+    assert torch.equal(gt[:2], gts[0]) and torch.equal(gt[2:], torch.ones(3, 5))
+    gt0, off0, c0 = P.pack_gt([torch.zeros(0, 5)] * 2, "cpu")
+    assert gt0.shape == (0, 5) and off0.tolist() == [0, 0, 0] and c0 == [0, 0]
+    with pytest.raises(ValueError):
+        P.pack_gt([torch.zeros(3, 4)], "cpu")
+    with pytest.raises(TypeError):
+        P.pack_gt([[1, 2, 3, 4, 5]], "cpu")
+
+
+def test_loss_module_contract():
+    crit = P.YoloDFLQFLoss()
+    assert (crit.num_classes, crit.lambda_box, crit.lambda_cls, crit.lambda_dfl, crit.reg_max) == (171, 1.5, 1.0, 1.5, 16)
+    assert list(crit.parameters()) == [] and list(crit.buffers()) == []      # stateless, DDP/FSDP safe
+    with pytest.raises(IndexError):
+        crit(torch.zeros(2, 64 + 171, 8), [torch.zeros(0, 5)], torch.zeros(2, 8), torch.zeros(1, 8))
+
+
+def test_nms_argument_checks_happen_before_any_device_work():
+    x = syn.make_nms_input(1, 4, 64, 1)
+    with pytest.raises(AssertionError, match="Invalid Confidence"):
+        U.non_max_suppression(x, conf_thres=-0.1)
+    with pytest.raises(AssertionError, match="Invalid IoU"):
+        U.non_max_suppression(x, iou_thres=1.1)
+    with pytest.raises(NotImplementedError):
+        U.non_max_suppression(x, multi_label=True, nc=4)
+
+
+def test_synthetic_generators_are_seeded_and_shaped():
+    a, s = syn.anchor_grid(640)
+    assert a.shape == (2, 8400) and s.shape == (1, 8400) and syn.num_anchors(1280) == 33600
+    assert a[:, 0].tolist() == [0.5, 0.5] and s[0, -1].item() == 32 and a[:, 6400].tolist() == [0.5, 0.5]
+    p1, g1, _, _ = syn.make_loss_inputs(4, 80, 640, 50, 7)
+    p2, g2, _, _ = syn.make_loss_inputs(4, 80, 640, 50, 7)
+    assert torch.equal(p1, p2) and all(torch.equal(x, y) for x, y in zip(g1, g2))
+    assert g1[0].shape[0] == 50 and g1[1].shape[0] == 0 and p1.shape == (4, 144, 8400)
+    gc = syn.make_gt(4, 80, 640, 50, 9, conflict_frac=0.1)
+    assert all(g.shape[0] <= 50 for g in gc)
+    x = syn.make_nms_input(2, 80, 640, 3)
+    assert x.shape == (2, 84, 8400) and float(x[:, 4:].min()) > 0 and float(x[:, 4:].max()) < 1
+
+
+def test_shard_batch():
+    assert [DS.shard_batch(1024, r, 8) for r in (0, 7)] == [(0, 128), (896, 1024)]
+    assert DS.reduce_value(3.5) == 3.5                  # not distributed: identity
