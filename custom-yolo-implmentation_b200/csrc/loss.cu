@@ -538,6 +538,18 @@ static bool vector_ok(const void *preds, const void *grad, int n_anchors) {
     return n_anchors % VW == 0 && aligned16(preds) && (grad == nullptr || aligned16(grad));
 }
 
+// Optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching
+// stream around each of the three kernels.  Off by default; never on during a timed benchmark step.
+static bool g_stage_timing = false;
+static cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+static int stage_mark(int i, cudaStream_t st) {
+    if (!g_stage_timing) return YB_OK;
+    if (g_stage_ev[i] == nullptr) YB_CUDA(cudaEventCreate(&g_stage_ev[i]));
+    YB_CUDA(cudaEventRecord(g_stage_ev[i], st));
+    return YB_OK;
+}
+
 template <typename T, int VW>
 static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, const float *anchors, const float *strides,
                        const float *gt, const int32_t *gt_off, int gt_total, int gmax, float lambda_cls,
@@ -547,6 +559,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
     const float k_dfl_num = lambda_dfl / ((float)n_images * 4.f);
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
+    if (int rc = stage_mark(0, st)) return rc;
     {
         constexpr int TILE = kAssignThreads * VW;
         dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
@@ -554,6 +567,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
                                                               w.best, grad);
         YB_CUDA(cudaGetLastError());
     }
+    if (int rc = stage_mark(1, st)) return rc;
     if (gt_total > 0 && gmax > 0) {
         dim3 grid((gmax + 3) / 4, n_images);
         match_kernel<T><<<grid, 128, 0, st>>>(preds, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.best,
@@ -561,6 +575,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
                                               out_iou);
         YB_CUDA(cudaGetLastError());
     }
+    if (int rc = stage_mark(2, st)) return rc;
     {
         constexpr int TILE = kClsThreads * VW;
         dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
@@ -576,6 +591,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
                                                                         out_per_image);
         YB_CUDA(cudaGetLastError());
     }
+    if (int rc = stage_mark(3, st)) return rc;
     return YB_OK;
 }
 
@@ -637,6 +653,19 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
     return launch_loss<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
                                          gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl,
                                          (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w, st);
+}
+
+extern "C" int yb_stage_timing(int enable) {
+    g_stage_timing = enable != 0;
+    return YB_OK;
+}
+
+extern "C" int yb_loss_last_stage_ms(float *out_ms_host) {
+    YB_REQUIRE(out_ms_host != nullptr, "yb_loss_last_stage_ms: null pointer");
+    for (int i = 0; i < 4; ++i) YB_REQUIRE(g_stage_ev[i] != nullptr, "yb_loss_last_stage_ms: no timed call has run");
+    YB_CUDA(cudaEventSynchronize(g_stage_ev[3]));
+    for (int i = 0; i < 3; ++i) YB_CUDA(cudaEventElapsedTime(out_ms_host + i, g_stage_ev[i], g_stage_ev[i + 1]));
+    return YB_OK;
 }
 
 extern "C" int yb_scale_grad(void *grad, int dtype, size_t n_elements, const float *scale, void *stream) {

@@ -75,6 +75,12 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
                     void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou, float *out_per_image,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* Measurement aid: when enabled, yb_loss_fwd_bwd records CUDA events on its stream around each of its
+ * three kernels (assign, match, cls_loss); yb_loss_last_stage_ms waits for the last timed call and
+ * returns the three durations in milliseconds (host array of 3).  Off by default. */
+int yb_stage_timing(int enable);
+int yb_loss_last_stage_ms(float *out_ms_host);
+
 /* grad *= *scale (device scalar), in place; returns without touching memory when *scale == 1.
  * Used by the autograd bridge for `loss.backward()` under a GradScaler
  * (src/training/train_model.py:247-253). */

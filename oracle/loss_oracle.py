@@ -225,7 +225,12 @@ def loss_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torc
             iou = iou_xywh_reference(xywh[b, idx], g)            #                      :256
             rows_t = torch.zeros(g.shape[0], num_classes)
             rows_t.scatter_(1, gt[:, 4].long()[:, None], iou[:, None])
-            target[idx] = rows_t                                 # last GT wins on duplicates :261
+            # `target_scores[idx] = matched_targets` (:261).  With duplicate anchors index_put_ is
+            # order-undefined in torch (multi-threaded CPU and CUDA runs really do differ); the oracle
+            # fixes the sequential meaning: the LAST GT's whole row wins (what one thread produces).
+            later_same = (idx[None, :] == idx[:, None]).triu(1).any(1)      # a later GT shares my anchor
+            win = ~later_same
+            target[idx[win]] = rows_t[win]                                  # unique indices: deterministic
             dfl_img.append(rows)
             tr.idx.append(idx); tr.margin.append(margin); tr.iou.append(iou.detach())
             tr.bins_left.append(t.long())
@@ -234,7 +239,15 @@ def loss_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torc
             dfl_img.append(torch.zeros(()))
             tr.idx.append(torch.zeros(0, dtype=torch.long)); tr.margin.append(torch.zeros(0))
             tr.iou.append(torch.zeros(0)); tr.bins_left.append(torch.zeros(0, 4, dtype=torch.long))
-        cls_img.append(qfl_sum(cls[b], target))                  #                      :264
+        q = qfl_sum(cls[b], target)                              #                      :264
+        if gt.numel() > 0 and bool(later_same.any()):
+            # Q16: index_put_'s backward hands EVERY source row the gradient of its destination row,
+            # overwritten or not.  A zero-valued term reproduces that gradient for the losing GTs.
+            lose = later_same
+            p = cls[b][idx[lose]].detach().sigmoid()
+            dq_dt = -((1 - p).pow(2) * torch.log(p + EPS_LOG) - p.pow(2) * torch.log(1 - p + EPS_LOG)) / cls[b].shape[0]
+            q = q + (dq_dt * (rows_t[lose] - rows_t[lose].detach())).sum()
+        cls_img.append(q)
     if not any_gt:
         # the reference dies here with AttributeError on a python float
         raise AttributeError("'float' object has no attribute 'detach'")
