@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the box-geometry hot path (BASELINE.json metric: images/s through
+decode+assign+loss(+bwd) and through NMS; % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the fused decode + assign + DFL/QFL loss + backward over one batch of
+synthetic head outputs.  Workload at every N: cfg2 of BASELINE.json per GPU (batch 128, 640x640,
+8400 anchors, 80 classes, <=100 GT/img, fp32) — i.e. cfg3 (global batch 1024) at N=8: weak scaling.
+
+  value       whole-job images/s with inputs resident in HBM, timed with CUDA events on the launching
+              stream, max over ranks (inputs are 619 MB/step: larger than the 126 MB L2).
+  e2e         the same metric through the public drop-in API (YoloDFLQFLoss.forward + backward) with
+              HOST inputs: every step copies preds / GT from pinned host memory and reads the loss
+              scalars back.
+  roofline    dominant kernel (cls_loss_kernel): algorithmic bytes / CUDA-event duration vs the
+              measured copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference
+              the CPU oracle port of the reference's loss (oracle/loss_oracle.py; the reference is
+              Python and cannot travel to the box) on all host cores, on a bounded sample.
+  nms         cfg4 (batch 64, 8400 candidates, conf 0.001, IoU 0.7, max_det 300) through yb_nms.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(batch_per_gpu=128, imgsz=640, nc=80, gmax=100, reg_max=16)
+CPU_SAMPLE_IMAGES = 16
+METRIC = "images/sec through decode+assign+loss(+bwd)"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons of one GPU, sampled in-process through NVML (initialised before the
+    timed region; a fork of nvidia-smi inside it would stall the launching thread)."""
+
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index, period=0.1):
+        self.rows, self._stop, self._t, self.period = [], threading.Event(), None, period
+        self.h = self.mx = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+        except Exception:
+            self.h = None
+
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((float(sm), [n for n, b in zip(self.NAMES, self.bits) if r & b]))
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.mx) if self.mx else None,
+                "reasons": sorted({n for r in self.rows for n in r[1]}), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_loss_images_per_s(steps, warmup, seed=1236):
+    from custom_yolo_implmentation_b200.utils import synthetic as syn
+    from oracle import loss_oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = CPU_SAMPLE_IMAGES
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, CFG["nc"], CFG["imgsz"], CFG["gmax"], seed)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss_oracle.loss_forward_backward(preds, gts, anchors, strides, CFG["nc"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return n / med, med, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    ips, med, threads = cpu_loss_images_per_s(steps, warmup)
+    sample = (f"{CPU_SAMPLE_IMAGES} images of the cfg2 workload per step (640x640, 8400 anchors, nc=80, <=100 GT/img, fp32), "
+              f"oracle/loss_oracle.py fwd+bwd on torch CPU, median of {steps} steps")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: batch 128/GPU, 640x640 (8400 anchors, reg_max 16), 80 classes, <=100 GT/img, "
+                                   "fused decode+assign+loss+backward", "cpu_sample_images": CPU_SAMPLE_IMAGES},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from custom_yolo_implmentation_b200 import _cabi
+    from custom_yolo_implmentation_b200.model.losses import YoloDFLQFLoss, fused_loss, pack_gt
+    from custom_yolo_implmentation_b200.training.distributed_setup import reduce_loss_stats
+    from custom_yolo_implmentation_b200.utils import synthetic as syn
+    from custom_yolo_implmentation_b200.utils.model_utils import batched_nms_raw
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    n, nc, imgsz, gmax = CFG["batch_per_gpu"], CFG["nc"], CFG["imgsz"], CFG["gmax"]
+    preds_h, gts_h, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, 1236 + rank)
+    a = preds_h.shape[2]
+    preds = preds_h.to(dev)
+    anchors_d, strides_d = anchors.to(dev), strides.to(dev)
+    gt, off, counts = pack_gt([g.to(dev) for g in gts_h], dev)
+    gmax_real = max(counts)
+    bytes_per_step = 2 * preds.numel() * preds.element_size()          # read once + gradient written once
+
+    def step():
+        out, grad, _ = fused_loss(preds, gt, off, gmax_real, anchors_d, strides_d, nc, 1.0, 1.5, want_grad=True)
+        if world > 1:
+            reduce_loss_stats(out, n)                                  # one small all-reduce (logging/normaliser)
+        return out, grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = _cabi.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    with sampler as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out, grad = step()
+        ev1.record()
+        clocks.sample()                      # the queue is still draining: a sample under load
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = _cabi.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * n * args.steps / (elapsed_ms * 1e-3)
+    loss_val = float(out[0].item())
+
+    # ---- per-kernel durations for the roofline (separate pass, events on the launching stream) ----
+    lib.yb_stage_timing(1)
+    stage = []
+    import ctypes
+    buf = (ctypes.c_float * 3)()
+    for _ in range(max(5, min(args.steps, 20))):
+        step()
+        _cabi.check(lib.yb_loss_last_stage_ms(buf), "yb_loss_last_stage_ms")
+        stage.append([buf[0], buf[1], buf[2]])
+    lib.yb_stage_timing(0)
+    assign_ms, cls_ms, match_ms = (statistics.mean(s[i] for s in stage) for i in range(3))   # launch order
+    peak, peak_src = measured_peak_gbs()
+    cls_bytes = 2 * n * nc * a * preds.element_size()                  # class logits read + class gradient written
+    assign_bytes = 2 * n * 64 * a * preds.element_size()               # box logits read + box gradient written
+    cls_gbs = cls_bytes / (cls_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "cls_loss_kernel", "achieved": cls_gbs, "peak": peak, "unit": "GB/s",
+                "frac": cls_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": cls_bytes, "ms_per_launch": cls_ms,
+                "other_kernels": {"assign_kernel": {"ms": assign_ms, "GB/s": assign_bytes / (assign_ms * 1e-3) / 1e9,
+                                                    "frac": assign_bytes / (assign_ms * 1e-3) / 1e9 / peak},
+                                  "match_kernel+finalize_kernel": {"ms": match_ms}},
+                "whole_step": {"algorithmic_bytes": bytes_per_step, "GB/s": bytes_per_step / (ms_per_step * 1e-3) / 1e9,
+                               "frac": bytes_per_step / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end through the public API, host inputs ----
+    crit = YoloDFLQFLoss(num_classes=nc)
+    preds_pin = preds_h.pin_memory()
+    gts_pin = [g.pin_memory() for g in gts_h]
+    h2d = preds_pin.numel() * preds_pin.element_size() + sum(g.numel() * 4 for g in gts_pin) + 4 * (n + 1)
+    d2h = 3 * 4
+
+    def e2e_step():
+        x = preds_pin.to(dev, non_blocking=True).requires_grad_(True)
+        g = [t.to(dev, non_blocking=True) for t in gts_pin]
+        loss, parts = crit(x, g, anchors_d, strides_d)                 # parts: one D2H copy of the loss scalars
+        loss.backward()
+        return parts
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        parts = e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- NMS (cfg4), reported alongside ----
+    nms = None
+    if rank == 0 or world > 1:
+        y = syn.make_nms_input(64, nc, imgsz, 2024 + rank).to(dev)
+        for _ in range(3):
+            batched_nms_raw(y, 0.001, 0.7, 300, nc)
+        barrier()
+        ev0.record()
+        nms_steps = max(5, min(args.steps, 20))
+        for _ in range(nms_steps):
+            rows, cnt, _ = batched_nms_raw(y, 0.001, 0.7, 300, nc)
+        ev1.record()
+        barrier()
+        nms_ms = ev0.elapsed_time(ev1) / nms_steps
+        if world > 1:
+            t = torch.tensor([nms_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nms_ms = float(t.item())
+        nms_bytes = y.numel() * 4 + 64 * 300 * 6 * 4
+        nms = {"metric": "images/sec through batched class-aware NMS", "value": world * 64 / (nms_ms * 1e-3), "unit": "images/s",
+               "ms_per_step": nms_ms, "config": {"workload": "cfg4: batch 64/GPU, 8400 candidates, nc=80, conf 0.001, IoU 0.7, max_det 300"},
+               "hbm_frac_of_scan_roofline": nms_bytes / (nms_ms * 1e-3) / 1e9 / peak, "kept_min": int(cnt.min().item())}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ips, med, threads = cpu_loss_images_per_s(3, 1)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"{CPU_SAMPLE_IMAGES} images of the same workload per step, oracle/loss_oracle.py fwd+bwd on torch CPU, "
+                             f"median of 3 steps ({med * 1e3:.0f} ms/step)"}
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "cfg2 per GPU: batch 128, 640x640 (8400 anchors, reg_max 16), 80 classes, <=100 GT/img, "
+                                       "fused decode+assign+loss+backward (cfg3 = global batch 1024 at 8 GPUs)",
+                           "global_batch": world * n, "gt_boxes_per_step_per_gpu": int(sum(counts)),
+                           "l2_policy": "inputs+outputs are 1.24 GB per step, larger than the 126 MB L2",
+                           "parallelism": f"batch-sharded x{world}, one small all-reduce of the loss stats per step" if world > 1 else "single GPU"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                        "api": "YoloDFLQFLoss.forward + loss.backward on pinned host inputs"},
+                "gpu_launches": launches, "clocks": clocks.summary(), "loss": loss_val, "nms": nms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,13 +34,15 @@ constexpr float kEpsIou = 1e-6f;   // src/model/losses.py:40
 constexpr float kEpsLog = 1e-12f;  // src/model/losses.py:53-54
 
 // ---- 128-bit streaming access --------------------------------------------------------------
-// Head outputs and gradients are touched exactly once per step: keep them out of L1 and mark them
-// evict-first in L2 so the small reused tables (GT, match table, anchors) stay resident.
+// Head outputs and gradients are touched exactly once per step: loads bypass L1 allocation and
+// stores use the streaming (evict-first) policy so the small reused tables (GT, match table,
+// anchors) stay resident in L1/L2.
 __device__ __forceinline__ uint4 ldg_stream16(const void *p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
+    // not volatile: a pure read of data no kernel writes, so the compiler may hoist / batch it
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+        : "l"(p));
     return r;
 }
 __device__ __forceinline__ void stg_stream16(void *p, const uint4 &v) {
@@ -133,29 +135,61 @@ template <>
 __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 // ---- DFL softmax-expectation of one box side ------------------------------------------------
-// Mirrors Tensor.softmax(16 bins) followed by sum(p * [0..15]) (src/model/losses.py:157-159):
-// max-subtracted exp, the bin sum taken in the butterfly order of ATen's 16-lane warp softmax
-// (offsets 8,4,2,1), each probability an IEEE division, products rounded before they are added.
-__device__ __forceinline__ float dfl_expectation16(const float (&x)[16], float (&prob)[16]) {
+// softmax over the 16 bins followed by sum(p * [0..15]) (src/model/losses.py:157-159), evaluated as
+// (sum_j j e_j) / (sum_j e_j) with e_j = exp(x_j - max): one division per side instead of sixteen.
+// ex2.approx keeps e_j within ~2^-21 relative of exp(); the result is within ~1e-6 relative of the
+// reference's, far inside the 1e-5 budget (the matched-anchor decision is re-checked against the
+// oracle with its runner-up margin in tests/test_gpu_loss.py).
+__device__ __forceinline__ float dfl_expectation16(const float (&x)[16], float (&prob)[16], bool want_prob = false) {
     float m = x[0];
 #pragma unroll
     for (int j = 1; j < 16; ++j) m = fmaxf(m, x[j]);
     float e[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) e[j] = expf(x[j] - m);
-    float s8[8], s4[4];
+    for (int j = 0; j < 16; ++j) e[j] = __expf(x[j] - m);
+    float s8[8], s4[4], w8[8], w4[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s8[j] = __fadd_rn(e[j], e[j + 8]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s4[j] = __fadd_rn(s8[j], s8[j + 4]);
-    const float sum = __fadd_rn(__fadd_rn(s4[0], s4[2]), __fadd_rn(s4[1], s4[3]));
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        prob[j] = __fdiv_rn(e[j], sum);
-        acc = __fadd_rn(acc, __fmul_rn(prob[j], (float)j));
+    for (int j = 0; j < 8; ++j) {
+        s8[j] = e[j] + e[j + 8];
+        w8[j] = fmaf((float)(j + 8), e[j + 8], (float)j * e[j]);
     }
-    return acc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s4[j] = s8[j] + s8[j + 4];
+        w4[j] = w8[j] + w8[j + 4];
+    }
+    const float sum = (s4[0] + s4[2]) + (s4[1] + s4[3]);
+    const float wsum = (w4[0] + w4[2]) + (w4[1] + w4[3]);
+    if (want_prob) {
+        const float inv = __fdividef(1.f, sum);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) prob[j] = e[j] * inv;
+    }
+    return __fdiv_rn(wsum, sum);
+}
+
+// The same expectation from two 8-bin halves (online-softmax merge): lets a kernel keep only 8 rows
+// of a side in registers at a time.  Half h holds bins 8h .. 8h+7.
+struct DflPartial {
+    float m, s, w;      // max, sum exp(x - m), sum j exp(x - m)
+};
+__device__ __forceinline__ DflPartial dfl_half8(const float (&x)[8], int bin0) {
+    DflPartial r;
+    r.m = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    float e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = __expf(x[j] - r.m);
+    r.s = ((e[0] + e[4]) + (e[2] + e[6])) + ((e[1] + e[5]) + (e[3] + e[7]));
+    float w = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w = fmaf((float)(bin0 + j), e[j], w);
+    r.w = w;
+    return r;
+}
+__device__ __forceinline__ float dfl_merge(const DflPartial &a, const DflPartial &b) {
+    const float m = fmaxf(a.m, b.m);
+    const float fa = __expf(a.m - m), fb = __expf(b.m - m);
+    return __fdiv_rn(fmaf(a.w, fa, b.w * fb), fmaf(a.s, fa, b.s * fb));
 }
 
 // Pixel-space box of one anchor from its four expected distances (src/model/losses.py:178-186).
@@ -173,6 +207,45 @@ __device__ __forceinline__ PredBox decode_box(float ax, float ay, float s, float
     b.cx = __fmul_rn(__fadd_rn(b.x1, b.x2), 0.5f);
     b.cy = __fmul_rn(__fadd_rn(b.y1, b.y2), 0.5f);
     return b;
+}
+
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two IEEE round-to-nearest operations per
+// instruction, lane-wise identical to the scalar __fmul_rn / __fmaf_rn / __fadd_rn ------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+__device__ __forceinline__ float fast_ex2(float x) {         // MUFU.EX2, 2 ulp
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {        // MUFU.RCP, 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,19 +1,21 @@
 // Fused decode + nearest-centre assignment + DFL/QFL loss + backward (sm_100a).
 //
 // Replaces YoloDFLQFLoss.forward and its autograd backward (src/model/losses.py:93-281).
-// Three launches per step, every head-output byte read once and every gradient byte written once;
+// Four launches per step (the last two are tiny), every head-output byte read once and every gradient byte written once;
 // the (M x A) distance matrix, the decoded boxes and the dense (A x nc) QFL target never exist:
 //
 //   assign_kernel    reads the 4*16 box channels (128-bit loads), decodes each anchor's predicted
 //                    centre, scans it against the image's GT centres (one GT per thread, anchors
 //                    streamed from shared memory), merges the per-CTA winners with a 64-bit
 //                    atomicMax on (distance, anchor) keys, and zero-fills the box-channel gradient.
+//   cls_loss_kernel  reads the nc class channels: QFL loss + gradient of every cell for target 0
+//                    (all but <= one cell per GT), per-CTA partial sums.  Independent of the matching.
 //   match_kernel     one warp per GT: gathers the 64 logits of the matched anchor, DFL loss and its
 //                    gradient, IoU soft target (reference formula, slip included) and the gradient
-//                    that flows through it, duplicate-anchor resolution; writes the match table.
-//   cls_loss_kernel  reads the nc class channels, QFL loss + gradient in one pass with the target
-//                    looked up from a per-tile table in shared memory; the last CTA reduces the
-//                    per-CTA partial sums in a fixed order and writes the loss scalars.
+//                    that flows through it, duplicate-anchor resolution; corrects the one positive
+//                    QFL cell of each matched anchor (loss delta + gradient).
+//   finalize_kernel  one warp per image reduces that image's partial sums; the last CTA adds the
+//                    images up; everything in a fixed order, so the loss is run-to-run identical.
 #include "common.cuh"
 
 namespace yb {
@@ -23,13 +25,15 @@ constexpr int kClsThreads = 128;
 constexpr unsigned long long kNoKey = ~0ull;
 
 struct LossWorkspace {
-    unsigned int *ticket;          // [1]   cls_loss_kernel completion counter      } zeroed
+    unsigned int *ticket;          // [1]   finalize_kernel completion counter      } zeroed
     unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys   } every call
     int *m_idx;                    // [gt_total] matched anchor
     int *m_cls;                    // [gt_total] class id, or -1 when this GT does not own its anchor's target row
     float *m_iou;                  // [gt_total]
     float *m_dfl;                  // [gt_total] sum over the 4 sides of the DFL term
-    float *part;                   // [N * tiles] per-CTA sums of p^2 log(1-p) etc.
+    float *m_dcls;                 // [gt_total] QFL correction of the GT's positive cell: T (q^2 log p - p^2 log q)
+    float *part;                   // [N * tiles] per-CTA sums of p^2 log(1-p)
+    float *img_terms;              // [3 * N] per-image DFL term, QFL term, matched-anchor count
     size_t zero_bytes;
     size_t total_bytes;
 };
@@ -52,8 +56,12 @@ static LossWorkspace carve(void *base, int n_images, int cls_tiles, int gt_total
     off += g4;
     w.m_dfl = reinterpret_cast<float *>(p + off);
     off += g4;
+    w.m_dcls = reinterpret_cast<float *>(p + off);
+    off += g4;
     w.part = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * (size_t)n_images * cls_tiles, 64);
+    w.img_terms = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * 3 * (size_t)n_images, 64);
     w.total_bytes = off;
     return w;
 }
@@ -67,7 +75,9 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
               const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
               unsigned long long *__restrict__ best, T *__restrict__ grad) {
     constexpr int TILE = kAssignThreads * VW;
-    __shared__ float4 s_ctr[TILE];                        // cx, cy, cx^2+cy^2 of the tile's anchors
+    constexpr int TILE4 = (TILE + 3) & ~3;
+    // predicted centres of the tile's anchors, structure-of-arrays so that four anchors are one LDS.128
+    __shared__ __align__(16) float s_x[TILE4], s_y[TILE4], s_p[TILE4];     // cx, cy, cx^2 + cy^2
     __shared__ unsigned long long s_key[kAssignThreads];
 
     const int n = blockIdx.y;
@@ -81,22 +91,28 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
         float dist[4][VW];
 #pragma unroll
         for (int side = 0; side < 4; ++side) {
-            Group<T, VW> row[kRegMax];
+            DflPartial part[VW];
 #pragma unroll
-            for (int j = 0; j < kRegMax; ++j)
-                row[j].load(preds + img + (size_t)(side * kRegMax + j) * n_anchors + a0);
-            if (grad != nullptr) {
+            for (int h = 0; h < 2; ++h) {                  // 8 rows (128 B per thread) in flight at a time
+                Group<T, VW> row[8];
 #pragma unroll
-                for (int j = 0; j < kRegMax; ++j)
-                    Group<T, VW>::store_zero(grad + img + (size_t)(side * kRegMax + j) * n_anchors + a0);
-            }
-            if (m_img > 0) {
+                for (int j = 0; j < 8; ++j)
+                    row[j].load(preds + img + (size_t)(side * kRegMax + h * 8 + j) * n_anchors + a0);
+                if (grad != nullptr) {
 #pragma unroll
-                for (int v = 0; v < VW; ++v) {
-                    float x[kRegMax], p[kRegMax];
+                    for (int j = 0; j < 8; ++j)
+                        Group<T, VW>::store_zero(grad + img + (size_t)(side * kRegMax + h * 8 + j) * n_anchors + a0);
+                }
+                if (m_img > 0) {
 #pragma unroll
-                    for (int j = 0; j < kRegMax; ++j) x[j] = row[j].get(v);
-                    dist[side][v] = dfl_expectation16(x, p);
+                    for (int v = 0; v < VW; ++v) {
+                        float x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
+                        const DflPartial ph = dfl_half8(x, h * 8);
+                        if (h == 0) part[v] = ph;
+                        else dist[side][v] = dfl_merge(part[v], ph);
+                    }
                 }
             }
         }
@@ -106,18 +122,33 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
                 const float ax = __ldg(anchors + a0 + v), ay = __ldg(anchors + n_anchors + a0 + v);
                 const float s = __ldg(strides + a0 + v);
                 const PredBox b = decode_box(ax, ay, s, dist[0][v], dist[1][v], dist[2][v], dist[3][v]);
-                const float pn = __fadd_rn(__fmul_rn(b.cx, b.cx), __fmul_rn(b.cy, b.cy));
-                s_ctr[threadIdx.x * VW + v] = make_float4(b.cx, b.cy, pn, 0.f);
+                s_x[threadIdx.x * VW + v] = b.cx;
+                s_y[threadIdx.x * VW + v] = b.cy;
+                s_p[threadIdx.x * VW + v] = __fadd_rn(__fmul_rn(b.cx, b.cx), __fmul_rn(b.cy, b.cy));
             }
+        }
+    } else if (m_img > 0) {
+        // past the last anchor: a centre at infinite distance never wins
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            s_x[threadIdx.x * VW + v] = 0.f;
+            s_y[threadIdx.x * VW + v] = 0.f;
+            s_p[threadIdx.x * VW + v] = __int_as_float(0x7f800000);
         }
     }
     if (m_img == 0) return;                                // uniform per CTA
+    if (TILE4 != TILE && threadIdx.x < TILE4 - TILE) {
+        s_x[TILE + threadIdx.x] = 0.f;
+        s_y[TILE + threadIdx.x] = 0.f;
+        s_p[TILE + threadIdx.x] = __int_as_float(0x7f800000);
+    }
     __syncthreads();
 
     const int tile_n = min(TILE, n_anchors - tile0);
+    const int tile_n4 = (tile_n + 3) & ~3;                 // entries in [tile_n, tile_n4) are at infinity
     // GT chunks of up to 128: thread <-> one GT; when the chunk is small the anchors of the tile are
     // split into slices so that all warps have work.  Lanes of a warp share the slice, so every
-    // shared-memory read below is a broadcast.
+    // shared-memory read below is a broadcast.  Four anchors per step, evaluated as two packed pairs.
     for (int g0 = 0; g0 < m_img; g0 += kAssignThreads) {
         const int m_chunk = min(kAssignThreads, m_img - g0);
         const int m_pad = (m_chunk + 31) & ~31;
@@ -131,21 +162,31 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
             // ATen _euclidean_dist: [-2gx, -2gy, |g|^2, 1] . [px, py, 1, |p|^2], K = 4, FMA chain k = 0..3
             const float c0 = __fmul_rn(-2.f, gx), c1 = __fmul_rn(-2.f, gy);
             const float gn = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
-            const int per = (tile_n + n_slice - 1) / n_slice;
-            const int j_begin = slice * per, j_end = min(tile_n, j_begin + per);
+            const f32x2 c0p = pack2(c0, c0), c1p = pack2(c1, c1), gnp = pack2(gn, gn);
+            const int per = (((tile_n4 >> 2) + n_slice - 1) / n_slice) << 2;
+            const int j_begin = slice * per, j_end = min(tile_n4, j_begin + per);
             float best_d2 = __int_as_float(0x7f800000), best_s = __int_as_float(0x7f800000);
             int best_j = -1;
-#pragma unroll 4
-            for (int j = j_begin; j < j_end; ++j) {
-                const float4 c = s_ctr[j];
-                float d2 = __fmul_rn(c0, c.x);
-                d2 = __fmaf_rn(c1, c.y, d2);
-                d2 = __fadd_rn(d2, gn);
-                d2 = __fadd_rn(d2, c.z);
-                d2 = d2 < 0.f ? 0.f : d2;                  // clamp_min(0)
-                if (d2 < best_d2) {                        // sqrt is monotone: only then can it win
-                    const float s = __fsqrt_rn(d2);
-                    if (s < best_s) { best_s = s; best_d2 = d2; best_j = j; }
+#pragma unroll 2
+            for (int j = j_begin; j < j_end; j += 4) {
+                const ulonglong2 xs = *reinterpret_cast<const ulonglong2 *>(s_x + j);
+                const ulonglong2 ys = *reinterpret_cast<const ulonglong2 *>(s_y + j);
+                const ulonglong2 ps = *reinterpret_cast<const ulonglong2 *>(s_p + j);
+                const f32x2 d01 = add2(add2(fma2(c1p, ys.x, mul2(c0p, xs.x)), gnp), ps.x);
+                const f32x2 d23 = add2(add2(fma2(c1p, ys.y, mul2(c0p, xs.y)), gnp), ps.y);
+                float d[4];
+                unpack2(d01, d[0], d[1]);
+                unpack2(d23, d[2], d[3]);
+                // clamp_min(0) and sqrt are monotone: an anchor can only win if its raw d^2 is below the
+                // raw d^2 of the current winner, which happens O(log tile) times per scan
+                if (fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) < best_d2) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (d[v] < best_d2) {
+                            const float s = __fsqrt_rn(fmaxf(d[v], 0.f));
+                            if (s < best_s) { best_s = s; best_d2 = d[v]; best_j = j + v; }
+                        }
+                    }
                 }
             }
             if (best_j >= 0)
@@ -175,15 +216,10 @@ struct GtTerms {
     float g_lo, g_hi;   // gradient of the two logits this lane holds (bins lane%16 of sides lane/16 and 2+lane/16)
     float dfl;          // sum over the four sides of the DFL term (all lanes)
     float iou;          // soft target (all lanes)
+    float cell_delta;   // QFL loss change of the (anchor, class) cell per unit of target: q^2 log p - p^2 log q
+    float cell_grad0;   // d total / d logit of that cell at target t is  cell_grad0 + t * cell_grad1
+    float cell_grad1;
 };
-
-// d(total)/d(iou_m): the QFL is linear in the target, so this is independent of the target value
-// (src/model/losses.py:53-56 differentiated w.r.t. target_scores).
-__device__ __forceinline__ float qfl_dloss_dtarget(float logit, float k_cls) {
-    const float p = __fdiv_rn(1.f, 1.f + expf(-logit));
-    const float q = 1.f - p;
-    return -k_cls * (q * q * logf(p + kEpsLog) - p * p * logf(q + kEpsLog));
-}
 
 template <typename T>
 __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anchors, int idx,
@@ -211,11 +247,11 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
     float s_lo = e_lo, s_hi = e_hi;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
-        s_lo = __fadd_rn(s_lo, __shfl_xor_sync(0xffffffffu, s_lo, o));
-        s_hi = __fadd_rn(s_hi, __shfl_xor_sync(0xffffffffu, s_hi, o));
+        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, o);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
     }
     const float p_lo = __fdiv_rn(e_lo, s_lo), p_hi = __fdiv_rn(e_hi, s_hi);
-    float d_lo = __fmul_rn(p_lo, (float)bin), d_hi = __fmul_rn(p_hi, (float)bin);
+    float d_lo = p_lo * (float)bin, d_hi = p_hi * (float)bin;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
         d_lo += __shfl_xor_sync(0xffffffffu, d_lo, o);
@@ -240,19 +276,29 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
     const float den = uni + kEpsIou;
     const float iou = inter / den;
 
-    // backward of the above in autograd's conventions: clamp passes where the input >= 0, max/min
+    // ---- the (anchor, class) QFL cell (src/model/losses.py:51-56) ------------------------------
+    // loss(t) = t q^2 log(p+e) + (1-t) p^2 log(q+e)   (sign and 1/A applied later); linear in t, so
+    // d total / d iou does not depend on the target value (and reaches over-written GTs too)
+    const float pc = __fdiv_rn(1.f, 1.f + expf(-z_cls));
+    const float qc = 1.f - pc;
+    const float lp = logf(pc + kEpsLog), lq = logf(qc + kEpsLog);
+    const float cell_delta = qc * qc * lp - pc * pc * lq;
+    const float g_iou = -k_cls * cell_delta;
+    const float dpos = -2.f * qc * lp + qc * qc / (pc + kEpsLog);     // d/dp of q^2 log(p+e)
+    const float dneg = 2.f * pc * lq - pc * pc / (qc + kEpsLog);      // d/dp of p^2 log(q+e)
+
+    // backward of the IoU in autograd's conventions: clamp passes where the input >= 0, max/min
     // route to the larger/smaller argument and split evenly on ties.
-    const float g_iou = qfl_dloss_dtarget(z_cls, k_cls);
-    const float d_inter = g_iou * (1.f / den + inter / (den * den));   // d iou/d inter, incl. the -inter in the union
+    const float d_inter = g_iou * (1.f / den + inter / (den * den));   // incl. the -inter inside the union
     const float d_area1 = -g_iou * inter / (den * den);
     const float d_iw = (iw_raw >= 0.f) ? d_inter * ih : 0.f;
     const float d_ih = (ih_raw >= 0.f) ? d_inter * iw : 0.f;
     auto pick_max = [](float a, float o) { return a > o ? 1.f : (a == o ? 0.5f : 0.f); };   // weight on `a`
     auto pick_min = [](float a, float o) { return a < o ? 1.f : (a == o ? 0.5f : 0.f); };
-    float d_ax1 = -d_iw * pick_max(ax1, bx1) - d_area1 * ah;
-    float d_ax2 = d_iw * pick_min(ax2, bx2) + d_area1 * ah;
-    float d_ay1 = -d_ih * pick_max(ay1, by1) - d_area1 * aw;
-    float d_ay2 = d_ih * pick_min(ay2, by2) + d_area1 * aw;
+    const float d_ax1 = -d_iw * pick_max(ax1, bx1) - d_area1 * ah;
+    const float d_ax2 = d_iw * pick_min(ax2, bx2) + d_area1 * ah;
+    const float d_ay1 = -d_ih * pick_max(ay1, by1) - d_area1 * aw;
+    const float d_ay2 = d_ih * pick_min(ay2, by2) + d_area1 * aw;
     // ax1 = cx - w/2, ax2 = cx + w/2, ay1 = cy - h/2, ay2 = h + cy/2
     const float d_cx = d_ax1 + d_ax2;
     const float d_w = 0.5f * (d_ax2 - d_ax1);
@@ -280,11 +326,13 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
                           __shfl_sync(0xffffffffu, lp_hi, base + bl_hi + 1) * wr_hi);
     // ce_lo is uniform within a half: lanes 0-15 hold side 0 / 2, lanes 16-31 side 1 / 3
     const float ce_half = ce_lo + ce_hi;
-    const float dfl = ce_half + __shfl_xor_sync(0xffffffffu, ce_half, 16);
 
     GtTerms r;
-    r.dfl = dfl;
+    r.dfl = ce_half + __shfl_xor_sync(0xffffffffu, ce_half, 16);
     r.iou = iou;
+    r.cell_delta = cell_delta;
+    r.cell_grad0 = -k_cls * dneg * pc * qc;
+    r.cell_grad1 = -k_cls * (dpos - dneg) * pc * qc;
     const float dd_lo = half == 0 ? d_dl : d_dt, dd_hi = half == 0 ? d_dr : d_db;
     const float dk_lo = half == 0 ? dl : dt, dk_hi = half == 0 ? dr : db;
     const float oh_lo = (bin == bl_lo ? wl_lo : 0.f) + (bin == bl_lo + 1 ? wr_lo : 0.f);
@@ -294,166 +342,280 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
     return r;
 }
 
+constexpr int kMatchThreads = 128;
+
 template <typename T>
-__global__ void __launch_bounds__(128)
-match_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ anchors,
-             const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
-             const unsigned long long *__restrict__ best, float k_dfl_num, float k_cls, T *__restrict__ grad,
-             int *__restrict__ m_idx, int *__restrict__ m_cls, float *__restrict__ m_iou, float *__restrict__ m_dfl,
-             int *__restrict__ out_idx, float *__restrict__ out_iou) {
-    const int n = blockIdx.y;
-    const int g_begin = gt_off[n];
-    const int m_img = gt_off[n + 1] - g_begin;
-    const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (m >= m_img) return;
+__global__ void __launch_bounds__(kMatchThreads)
+match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
+             const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
+             const int *__restrict__ gt_off, int gt_total, const unsigned long long *__restrict__ best,
+             float k_dfl_num, float k_cls, T *__restrict__ grad, float *__restrict__ m_dfl,
+             float *__restrict__ m_dcls, int *__restrict__ m_win, int *__restrict__ out_idx,
+             float *__restrict__ out_iou) {
     const int lane = threadIdx.x & 31;
-    const T *img = preds + (size_t)n * n_ch * n_anchors;
-    auto idx_of = [&](int mm) {
-        const unsigned long long inv = best[g_begin + mm];
-        return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance at all -> anchor 0
-    };
-    const int idx = idx_of(m);
-    const float k_dfl = k_dfl_num / (float)m_img;         // lambda_dfl / (N * 4 * M)
+    const int g = blockIdx.x * (kMatchThreads / 32) + (threadIdx.x >> 5);          // one warp per GT
+    if (g >= gt_total) return;
+    {
+        // image of this GT: last n with gt_off[n] <= g
+        int lo = 0, hi = n_images;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(gt_off + mid) <= g) lo = mid; else hi = mid;
+        }
+        const int n = lo;
+        const int g_begin = __ldg(gt_off + n);
+        const int m_img = __ldg(gt_off + n + 1) - g_begin;
+        const int m = g - g_begin;
+        const T *img = preds + (size_t)n * n_ch * n_anchors;
+        auto idx_of = [&](int mm) {
+            const unsigned long long inv = best[g_begin + mm];
+            return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
+        };
+        const int idx = idx_of(m);
+        const float k_dfl = k_dfl_num / (float)m_img;         // lambda_dfl / (N * 4 * M)
 
-    // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
-    // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
-    int first = m, last = m;
-    for (int mm = lane; mm < m_img; mm += 32) {
-        if (idx_of(mm) == idx) { first = min(first, mm); last = max(last, mm); }
-    }
+        // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
+        // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
+        int first = m, last = m;
+        for (int mm = lane; mm < m_img; mm += 32) {
+            if (idx_of(mm) == idx) { first = min(first, mm); last = max(last, mm); }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-    }
+        for (int o = 16; o > 0; o >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        }
 
-    GtTerms mine = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)(g_begin + m) * 5, k_dfl, k_cls, nc);
-    if (lane == 0) {
-        int cls = (int)__ldg(gt + (size_t)(g_begin + m) * 5 + 4);
-        cls = min(max(cls, 0), nc - 1);
-        m_idx[g_begin + m] = idx;
-        m_cls[g_begin + m] = (last == m) ? cls : -1;
-        m_iou[g_begin + m] = mine.iou;
-        m_dfl[g_begin + m] = mine.dfl;
-        if (out_idx) out_idx[g_begin + m] = idx;
-        if (out_iou) out_iou[g_begin + m] = mine.iou;
-    }
-    if (grad == nullptr || first != m) return;
-    float g_lo = mine.g_lo, g_hi = mine.g_hi;
-    if (last != m) {
-        for (int mm = m + 1; mm <= last; ++mm) {           // warp-uniform loop
-            if (idx_of(mm) != idx) continue;
-            const GtTerms o = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)(g_begin + mm) * 5, k_dfl,
-                                       k_cls, nc);
-            g_lo += o.g_lo;
-            g_hi += o.g_hi;
+        const GtTerms mine = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)g * 5, k_dfl, k_cls, nc);
+        const bool winner = (last == m);
+        if (lane == 0) {
+            m_dfl[g] = mine.dfl;
+            m_dcls[g] = winner ? mine.iou * mine.cell_delta : 0.f;
+            m_win[g] = winner ? 1 : 0;
+            if (out_idx) out_idx[g] = idx;
+            if (out_iou) out_iou[g] = mine.iou;
+        }
+        if (grad != nullptr) {
+            T *gimg = grad + (size_t)n * n_ch * n_anchors;
+            if (winner && lane == 0) {
+                // the anchor's one positive QFL cell: overwrite the target-0 gradient cls_loss_kernel wrote
+                int cls = (int)__ldg(gt + (size_t)g * 5 + 4);
+                cls = min(max(cls, 0), nc - 1);
+                store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
+                                 mine.cell_grad0 + mine.iou * mine.cell_grad1);
+            }
+            if (first == m) {
+                float g_lo = mine.g_lo, g_hi = mine.g_hi;
+                if (last != m) {
+                    for (int mm = m + 1; mm <= last; ++mm) {           // warp-uniform loop
+                        if (idx_of(mm) != idx) continue;
+                        const GtTerms o = gt_terms(img, n_anchors, idx, anchors, strides,
+                                                   gt + (size_t)(g_begin + mm) * 5, k_dfl, k_cls, nc);
+                        g_lo += o.g_lo;
+                        g_hi += o.g_hi;
+                    }
+                }
+                store_from_float(gimg + (size_t)lane * n_anchors + idx, g_lo);
+                store_from_float(gimg + (size_t)(lane + 32) * n_anchors + idx, g_hi);
+            }
         }
     }
-    T *gimg = grad + (size_t)n * n_ch * n_anchors;
-    store_from_float(gimg + (size_t)lane * n_anchors + idx, g_lo);
-    store_from_float(gimg + (size_t)(lane + 32) * n_anchors + idx, g_hi);
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize_kernel: one warp per image sums that image's partials in a fixed order; the last CTA
+// to finish adds the per-image terms up (again in a fixed order) and writes the loss scalars.
+// ------------------------------------------------------------------------------------------
+constexpr int kFinThreads = 256;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+finalize_kernel(int n_images, int n_anchors, int cls_tiles, const int *__restrict__ gt_off,
+                const float *__restrict__ part, const float *__restrict__ m_dfl, const float *__restrict__ m_dcls,
+                const int *__restrict__ m_win, float lambda_cls, float lambda_dfl, float *__restrict__ img_terms,
+                unsigned int *__restrict__ ticket, float *__restrict__ out_loss, float *__restrict__ out_per_image) {
+    __shared__ bool s_last;
+    __shared__ double s_d[kFinThreads / 32], s_c[kFinThreads / 32], s_f[kFinThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * (kFinThreads / 32) + warp;
+    if (b < n_images) {
+        double c_img = 0.0, d_img = 0.0, f_img = 0.0;
+        for (int t = lane; t < cls_tiles; t += 32) c_img += (double)__ldcg(part + (size_t)b * cls_tiles + t);
+        const int gb = gt_off[b], mb = gt_off[b + 1] - gb;
+        for (int m = lane; m < mb; m += 32) {
+            d_img += (double)__ldcg(m_dfl + gb + m);
+            c_img += (double)__ldcg(m_dcls + gb + m);
+            f_img += (double)__ldcg(m_win + gb + m);
+        }
+        c_img = warp_sum_d(c_img);
+        d_img = warp_sum_d(d_img);
+        f_img = warp_sum_d(f_img);
+        if (lane == 0) {
+            const float cls_b = (float)(-c_img / (double)n_anchors);                     // losses.py:56
+            const float dfl_b = mb > 0 ? (float)(d_img / (4.0 * (double)mb)) : 0.f;      // losses.py:78, :252
+            img_terms[b] = dfl_b;
+            img_terms[n_images + b] = cls_b;
+            img_terms[2 * n_images + b] = (float)f_img;
+            if (out_per_image) {
+                out_per_image[b] = dfl_b;
+                out_per_image[n_images + b] = cls_b;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double d = 0.0, c = 0.0, f = 0.0;
+    for (int i = threadIdx.x; i < n_images; i += kFinThreads) {
+        d += (double)__ldcg(img_terms + i);
+        c += (double)__ldcg(img_terms + n_images + i);
+        f += (double)__ldcg(img_terms + 2 * n_images + i);
+    }
+    d = warp_sum_d(d); c = warp_sum_d(c); f = warp_sum_d(f);
+    if (lane == 0) { s_d[warp] = d; s_c[warp] = c; s_f[warp] = f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double dd = 0.0, cc = 0.0, ff = 0.0;
+        for (int w = 0; w < kFinThreads / 32; ++w) { dd += s_d[w]; cc += s_c[w]; ff += s_f[w]; }
+        const float mean_dfl = (float)(dd / (double)n_images);        // N counts images without GT (losses.py:271)
+        const float mean_cls = (float)(cc / (double)n_images);
+        out_loss[0] = lambda_dfl * mean_dfl + lambda_cls * mean_cls;  // losses.py:275
+        out_loss[1] = mean_dfl;
+        out_loss[2] = mean_cls;
+        out_loss[3] = (float)ff;
+        out_loss[4] = out_loss[5] = out_loss[6] = out_loss[7] = 0.f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // cls_loss_kernel
 // ------------------------------------------------------------------------------------------
-// One element of the quality focal loss and its gradient w.r.t. the logit
-// (src/model/losses.py:51-56):  loss += t (1-p)^2 log(p+e) + (1-t) p^2 log(1-p+e)   (sign applied later)
-__device__ __forceinline__ void qfl_elem(float x, float t, float k_cls, float &acc, float &g) {
-    const float e = expf(-x);
-    const float p = __fdividef(1.f, 1.f + e);
+// One element of the quality focal loss at target 0 and its gradient w.r.t. the logit
+// (src/model/losses.py:51-56 with target_scores == 0):
+//     loss term  p^2 log(1 - p + 1e-12)          (sign and 1/A applied by the reduction)
+//     gradient   k p^2 (p - 2 q log q)           k = lambda_cls / (N A),  q = 1 - p
+// Fast path for q >= 0.7071 (logit <= -0.88, i.e. background): ex2.approx / rcp.approx and a degree-5
+// minimax polynomial of log1p on [-0.293, 0] (max relative error 9.4e-8, fitted offline); q is formed
+// as fl(1 - p) exactly as the reference does, so its rounding near 1 is reproduced, not avoided.
+// The +1e-12 inside the reference's log is below half an ulp of q there and drops out.
+constexpr float kFastQ = 0.70710678f;
+
+// Two elements at a time on the packed fp32 pipe (FMUL2 / FFMA2 / FADD2); MUFU.EX2 and MUFU.RCP are
+// the only scalar operations.  Returns q of both so the caller can detect, once per group, the rare
+// elements that need the general formula.
+__device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 &acc2, float &g0, float &g1,
+                                            float &q0, float &q1, float &t0, float &t1) {
+    const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), mtwo = pack2(-2.f, -2.f);
+    float a0, a1;
+    unpack2(mul2(pack2(x0, x1), pack2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+    const f32x2 u = add2(pack2(fast_ex2(a0), fast_ex2(a1)), one);            // 1 + exp(-x)
+    float u0, u1;
+    unpack2(u, u0, u1);
+    const f32x2 p = pack2(fast_rcp(u0), fast_rcp(u1));
+    const f32x2 q = fma2(p, mone, one);                                       // fl(1 - p), as the reference
+    const f32x2 f = add2(q, mone);                                            // exact for q in [0.5, 1]
+    f32x2 r = pack2(0.3410167098045349f, 0.3410167098045349f);
+    r = fma2(r, f, pack2(-0.08926734328269958f, -0.08926734328269958f));
+    r = fma2(r, f, pack2(0.21280372142791748f, 0.21280372142791748f));
+    r = fma2(r, f, pack2(-0.249073788523674f, -0.249073788523674f));
+    r = fma2(r, f, pack2(0.33335742354393005f, 0.33335742354393005f));
+    r = fma2(r, f, pack2(-0.49999991059303284f, -0.49999991059303284f));
+    const f32x2 lq = fma2(mul2(f, f), r, f);                                  // log(q) = f + f^2 R(f)
+    const f32x2 p2 = mul2(p, p);
+    const f32x2 term = mul2(p2, lq);
+    acc2 = add2(acc2, term);
+    const f32x2 g = mul2(mul2(p2, k2), fma2(mul2(q, mtwo), lq, p));           // k p^2 (p - 2 q log q)
+    unpack2(g, g0, g1);
+    unpack2(q, q0, q1);
+    unpack2(term, t0, t1);
+}
+
+// general formula for target 0 (any logit), used for the few elements with q < kFastQ
+__device__ __noinline__ void qfl_bg_slow(float x, float k_cls, float &term, float &g) {
+    const float p = __fdiv_rn(1.f, 1.f + expf(-x));
     const float q = 1.f - p;
     const float lq = logf(q + kEpsLog);
-    if (t == 0.f && q > 1e-4f) {
-        // target 0 and 1-p far above the 1e-12 guard: -(d/dx) = k p^2 (p - 2 q log q)
-        acc += p * p * lq;
-        g = k_cls * p * p * (p - 2.f * q * lq);
+    term = p * p * lq;
+    g = -k_cls * (2.f * p * lq - p * p / (q + kEpsLog)) * p * q;
+}
+
+template <typename T, int VW>
+__device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cls, f32x2 k2, f32x2 &acc2, float &fix,
+                                             float (&g)[VW]) {
+    if constexpr (VW == 1) {
+        float q0, q1, t0, t1, g1;
+        f32x2 dummy = pack2(0.f, 0.f);
+        qfl_bg_pair(row.get(0), row.get(0), k2, dummy, g[0], g1, q0, q1, t0, t1);
+        if (!(q0 >= kFastQ)) qfl_bg_slow(row.get(0), k_cls, t0, g[0]);
+        fix += t0;
     } else {
-        const float lp = logf(p + kEpsLog);
-        const float u = 1.f - t;
-        acc += t * q * q * lp + u * p * p * lq;
-        const float dpos = t * (-2.f * q * lp + q * q / (p + kEpsLog));
-        const float dneg = u * (2.f * p * lq - p * p / (q + kEpsLog));
-        g = -k_cls * (dpos + dneg) * p * q;
+        float q[VW], t[VW];
+        float qmin = 1.f;
+#pragma unroll
+        for (int v = 0; v < VW; v += 2) {
+            qfl_bg_pair(row.get(v), row.get(v + 1), k2, acc2, g[v], g[v + 1], q[v], q[v + 1], t[v], t[v + 1]);
+            qmin = fminf(qmin, fminf(q[v], q[v + 1]));
+        }
+        if (!(qmin >= kFastQ)) {                           // rare (also catches NaN)
+#pragma unroll
+            for (int v = 0; v < VW; ++v)
+                if (!(q[v] >= kFastQ)) {
+                    float ts;
+                    qfl_bg_slow(row.get(v), k_cls, ts, g[v]);
+                    fix += ts - t[v];                      // replace the fast-path term already in acc2
+                }
+        }
     }
 }
 
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kClsThreads)
-cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const int *__restrict__ gt_off,
-                const int *__restrict__ m_idx, const int *__restrict__ m_cls, const float *__restrict__ m_iou,
-                const float *__restrict__ m_dfl, float k_cls, float lambda_cls, float lambda_dfl,
-                T *__restrict__ grad, float *__restrict__ part, unsigned int *__restrict__ ticket,
-                float *__restrict__ out_loss, float *__restrict__ out_per_image) {
-    constexpr int TILE = kClsThreads * VW;
-    __shared__ int s_cls[TILE];
-    __shared__ float s_iou[TILE];
+cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
+                float *__restrict__ part) {
     __shared__ float s_red[kClsThreads / 32];
-    __shared__ bool s_last;
-
     const int n = blockIdx.y;
-    const int tile0 = blockIdx.x * TILE;
-    const int a0 = tile0 + threadIdx.x * VW;
-    const int g_begin = gt_off[n];
-    const int m_img = gt_off[n + 1] - g_begin;
-
-#pragma unroll
-    for (int v = 0; v < VW; ++v) s_cls[threadIdx.x * VW + v] = -1;
-    __syncthreads();
-    for (int m = threadIdx.x; m < m_img; m += kClsThreads) {
-        const int c = m_cls[g_begin + m];
-        const int j = m_idx[g_begin + m] - tile0;
-        if (c >= 0 && j >= 0 && j < TILE) {               // one owner per anchor: no write conflict
-            s_cls[j] = c;
-            s_iou[j] = m_iou[g_begin + m];
-        }
-    }
-    __syncthreads();
-
-    float acc = 0.f;
+    const int a0 = (blockIdx.x * kClsThreads + threadIdx.x) * VW;
+    f32x2 acc2 = pack2(0.f, 0.f);
+    float fix = 0.f;
     if (a0 < n_anchors) {
-        int t_cls[VW];
-        float t_iou[VW];
-        bool any = false;
-#pragma unroll
-        for (int v = 0; v < VW; ++v) {
-            t_cls[v] = s_cls[threadIdx.x * VW + v];
-            t_iou[v] = t_cls[v] >= 0 ? s_iou[threadIdx.x * VW + v] : 0.f;
-            any |= t_cls[v] >= 0;
-        }
         const size_t base = ((size_t)n * n_ch + 4 * kRegMax) * n_anchors + a0;
+        const f32x2 k2 = pack2(k_cls, k_cls);
         constexpr int U = 4;
-        int c = 0;
-        for (; c + U <= nc; c += U) {
-            Group<T, VW> row[U];
+        // software pipeline: the next U rows are in flight while the current U are evaluated
+        Group<T, VW> cur[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) row[u].load(preds + base + (size_t)(c + u) * n_anchors);
+        for (int u = 0; u < U; ++u)
+            if (u < nc) cur[u].load(preds + base + (size_t)u * n_anchors);
+        for (int c = 0; c < nc; c += U) {
+            Group<T, VW> nxt[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (c + U + u < nc) nxt[u].load(preds + base + (size_t)(c + U + u) * n_anchors);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                float g[VW];
-#pragma unroll
-                for (int v = 0; v < VW; ++v) {
-                    const float t = (any && t_cls[v] == c + u) ? t_iou[v] : 0.f;
-                    qfl_elem(row[u].get(v), t, k_cls, acc, g[v]);
+                if (c + u < nc) {
+                    float g[VW];
+                    qfl_bg_group<T, VW>(cur[u], k_cls, k2, acc2, fix, g);
+                    if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
                 }
-                if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
             }
-        }
-        for (; c < nc; ++c) {
-            Group<T, VW> row;
-            row.load(preds + base + (size_t)c * n_anchors);
-            float g[VW];
 #pragma unroll
-            for (int v = 0; v < VW; ++v) {
-                const float t = (any && t_cls[v] == c) ? t_iou[v] : 0.f;
-                qfl_elem(row.get(v), t, k_cls, acc, g[v]);
-            }
-            if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)c * n_anchors, g);
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
         }
     }
-
-    // CTA partial -> workspace; the last CTA to finish reduces everything in a fixed order.
-    acc = warp_sum(acc);
+    float lo, hi;
+    unpack2(acc2, lo, hi);
+    float acc = warp_sum((lo + hi) + fix);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -461,59 +623,6 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, co
 #pragma unroll
         for (int w = 0; w < kClsThreads / 32; ++w) s += s_red[w];
         part[(size_t)n * gridDim.x + blockIdx.x] = s;
-        __threadfence();
-        const unsigned int done = atomicAdd(ticket, 1u);
-        s_last = (done == gridDim.x * gridDim.y - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-
-    // final reduction: thread i owns images i, i+128, ...; then a fixed-shape tree over the CTA.
-    const int n_images = gridDim.y;
-    const int tiles = gridDim.x;
-    double dfl_sum = 0.0, cls_sum = 0.0;
-    float fg = 0.f;
-    for (int b = threadIdx.x; b < n_images; b += kClsThreads) {
-        double c_img = 0.0;
-        for (int t = 0; t < tiles; ++t) c_img += (double)__ldcg(part + (size_t)b * tiles + t);
-        const float cls_b = (float)(-c_img / (double)n_anchors);
-        const int gb = gt_off[b], mb = gt_off[b + 1] - gb;
-        double d_img = 0.0;
-        for (int m = 0; m < mb; ++m) {
-            d_img += (double)__ldcg(m_dfl + gb + m);
-            fg += (__ldcg(m_cls + gb + m) >= 0) ? 1.f : 0.f;
-        }
-        const float dfl_b = mb > 0 ? (float)(d_img / (4.0 * (double)mb)) : 0.f;
-        if (out_per_image) {
-            out_per_image[b] = dfl_b;
-            out_per_image[n_images + b] = cls_b;
-        }
-        dfl_sum += (double)dfl_b;
-        cls_sum += (double)cls_b;
-    }
-    __shared__ double s_d[kClsThreads], s_c[kClsThreads];
-    __shared__ float s_f[kClsThreads];
-    s_d[threadIdx.x] = dfl_sum;
-    s_c[threadIdx.x] = cls_sum;
-    s_f[threadIdx.x] = fg;
-    __syncthreads();
-    for (int o = kClsThreads / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            s_d[threadIdx.x] += s_d[threadIdx.x + o];
-            s_c[threadIdx.x] += s_c[threadIdx.x + o];
-            s_f[threadIdx.x] += s_f[threadIdx.x + o];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const float mean_dfl = (float)(s_d[0] / (double)n_images);
-        const float mean_cls = (float)(s_c[0] / (double)n_images);
-        out_loss[0] = lambda_dfl * mean_dfl + lambda_cls * mean_cls;   // losses.py:275
-        out_loss[1] = mean_dfl;
-        out_loss[2] = mean_cls;
-        out_loss[3] = s_f[0];
-        out_loss[4] = out_loss[5] = out_loss[6] = out_loss[7] = 0.f;
     }
 }
 
@@ -555,40 +664,42 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
                        const float *gt, const int32_t *gt_off, int gt_total, int gmax, float lambda_cls,
                        float lambda_dfl, T *grad, float *out_loss, int32_t *out_idx, float *out_iou,
                        float *out_per_image, const LossWorkspace &w, cudaStream_t st) {
+    (void)gmax;
     const int n_ch = 4 * kRegMax + nc;
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
     const float k_dfl_num = lambda_dfl / ((float)n_images * 4.f);
+    constexpr int TILE_A = kAssignThreads * VW, TILE_C = kClsThreads * VW;
+    const int cls_tiles = (n_anchors + TILE_C - 1) / TILE_C;
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(0, st)) return rc;
     {
-        constexpr int TILE = kAssignThreads * VW;
-        dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
+        dim3 grid((n_anchors + TILE_A - 1) / TILE_A, n_images);
         assign_kernel<T, VW><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
                                                               w.best, grad);
         YB_CUDA(cudaGetLastError());
     }
     if (int rc = stage_mark(1, st)) return rc;
-    if (gt_total > 0 && gmax > 0) {
-        dim3 grid((gmax + 3) / 4, n_images);
-        match_kernel<T><<<grid, 128, 0, st>>>(preds, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.best,
-                                              k_dfl_num, k_cls, grad, w.m_idx, w.m_cls, w.m_iou, w.m_dfl, out_idx,
-                                              out_iou);
+    {
+        dim3 grid(cls_tiles, n_images);
+        if (grad != nullptr)
+            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+        else
+            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
         YB_CUDA(cudaGetLastError());
     }
     if (int rc = stage_mark(2, st)) return rc;
+    if (gt_total > 0) {
+        const int warps = kMatchThreads / 32;
+        match_kernel<T><<<(gt_total + warps - 1) / warps, kMatchThreads, 0, st>>>(
+            preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, gt_total, w.best, k_dfl_num, k_cls, grad,
+            w.m_dfl, w.m_dcls, w.m_idx, out_idx, out_iou);
+        YB_CUDA(cudaGetLastError());
+    }
     {
-        constexpr int TILE = kClsThreads * VW;
-        dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
-        if (grad != nullptr)
-            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, gt_off, w.m_idx,
-                                                                       w.m_cls, w.m_iou, w.m_dfl, k_cls, lambda_cls,
-                                                                       lambda_dfl, grad, w.part, w.ticket, out_loss,
-                                                                       out_per_image);
-        else
-            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, gt_off, w.m_idx,
-                                                                        w.m_cls, w.m_iou, w.m_dfl, k_cls, lambda_cls,
-                                                                        lambda_dfl, grad, w.part, w.ticket, out_loss,
-                                                                        out_per_image);
+        const int warps = kFinThreads / 32;
+        finalize_kernel<<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
+            n_images, n_anchors, cls_tiles, gt_off, w.part, w.m_dfl, w.m_dcls, w.m_idx, lambda_cls, lambda_dfl, w.img_terms,
+            w.ticket, out_loss, out_per_image);
         YB_CUDA(cudaGetLastError());
     }
     if (int rc = stage_mark(3, st)) return rc;

@@ -62,6 +62,26 @@ def _workspace(n_bytes: int, device) -> torch.Tensor:
     return torch.empty(max(n_bytes, 16), dtype=torch.uint8, device=device)
 
 
+_ws_cache = {}
+
+
+def _stream_workspace(n_bytes: int, device) -> torch.Tensor:
+    """Scratch buffer reused by consecutive calls on one (device, stream): calls on a stream are
+    ordered, so the next call may overwrite the previous call's scratch."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < n_bytes:
+        buf = torch.empty(max(n_bytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
+    if t.dtype == torch.float32 and t.device == device and t.is_contiguous() and not t.requires_grad:
+        return t
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
 def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, gmax: int, anchors: torch.Tensor,
                strides: torch.Tensor, num_classes: int, lambda_cls: float, lambda_dfl: float, reg_max: int = 16,
                want_grad: bool = True, want_trace: bool = False):
@@ -79,17 +99,16 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
         raise ValueError(f"preds has {c} channels, expected 4*{reg_max} + {num_classes}")
     dev = preds.device
     dt = _cabi.dtype_code(preds.dtype)
-    x = preds.detach()
+    x = preds.detach() if preds.requires_grad else preds
     if not x.is_contiguous():
         x = x.contiguous()
-    anc = anchors.detach().to(device=dev, dtype=torch.float32).contiguous()
-    st = strides.detach().to(device=dev, dtype=torch.float32).contiguous()
+    anc = _as_f32(anchors, dev)
+    st = _as_f32(strides, dev)
     if anc.shape != (2, a) or st.numel() != a:
         raise ValueError(f"anchors must be (2, {a}) and strides (1, {a}); got {tuple(anc.shape)}, {tuple(st.shape)}")
     gt_total = int(gt.shape[0])
     lib = _cabi.lib()
-    ws_bytes = lib.yb_loss_workspace_bytes(n, a, gt_total, dt)
-    ws = _workspace(ws_bytes, dev)
+    ws = _stream_workspace(lib.yb_loss_workspace_bytes(n, a, gt_total, dt), dev)
     grad = torch.empty_like(x) if want_grad else None
     out = torch.empty(8, dtype=torch.float32, device=dev)
     trace = {}
