@@ -20,8 +20,30 @@
 
 namespace yb {
 
-constexpr int kAssignThreads = 128;
-constexpr int kClsThreads = 128;
+#ifndef YB_ASSIGN_THREADS
+#define YB_ASSIGN_THREADS 128
+#endif
+#ifndef YB_CLS_THREADS
+#define YB_CLS_THREADS 128
+#endif
+#ifndef YB_CLS_UNROLL
+#define YB_CLS_UNROLL 4
+#endif
+#ifndef YB_CLS_CSPLIT
+#define YB_CLS_CSPLIT 4
+#endif
+#ifndef YB_CLS_MINBLOCKS
+#define YB_CLS_MINBLOCKS 1
+#endif
+#ifndef YB_ASSIGN_MINBLOCKS          // resident CTAs/SM the register allocator must allow (measured: 4 best
+#define YB_ASSIGN_MINBLOCKS 0       // for fp32 rows, 6 for bf16 rows; 0 = pick by row type)
+#endif
+#ifndef YB_SCAN_UNROLL
+#define YB_SCAN_UNROLL 4
+#endif
+constexpr int kScanUnroll = YB_SCAN_UNROLL;
+constexpr int kAssignThreads = YB_ASSIGN_THREADS;
+constexpr int kClsThreads = YB_CLS_THREADS;
 constexpr unsigned long long kNoKey = ~0ull;
 
 struct LossWorkspace {
@@ -70,7 +92,7 @@ static LossWorkspace carve(void *base, int n_images, int cls_tiles, int gt_total
 // assign_kernel
 // ------------------------------------------------------------------------------------------
 template <typename T, int VW>
-__global__ void __launch_bounds__(kAssignThreads)
+__global__ void __launch_bounds__(kAssignThreads, YB_ASSIGN_MINBLOCKS ? YB_ASSIGN_MINBLOCKS : (VW == 8 ? 6 : 4))
 assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
               const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
               unsigned long long *__restrict__ best, T *__restrict__ grad) {
@@ -109,7 +131,11 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
                         float x[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
+#ifdef YB_ASSIGN_NODECODE
+                        DflPartial ph; ph.m = x[0] + x[7]; ph.s = x[1] + x[2] + x[3]; ph.w = x[4] + x[5] + x[6];
+#else
                         const DflPartial ph = dfl_half8(x, h * 8);
+#endif
                         if (h == 0) part[v] = ph;
                         else dist[side][v] = dfl_merge(part[v], ph);
                     }
@@ -137,6 +163,11 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
         }
     }
     if (m_img == 0) return;                                // uniform per CTA
+#ifdef YB_ASSIGN_NOSCAN
+    __syncthreads();
+    if (threadIdx.x == 0 && s_x[5] + s_y[77] + s_p[300] == 12345.f) best[0] = 1;   // keep the decode alive
+    return;
+#endif
     if (TILE4 != TILE && threadIdx.x < TILE4 - TILE) {
         s_x[TILE + threadIdx.x] = 0.f;
         s_y[TILE + threadIdx.x] = 0.f;
@@ -165,27 +196,44 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
             const f32x2 c0p = pack2(c0, c0), c1p = pack2(c1, c1), gnp = pack2(gn, gn);
             const int per = (((tile_n4 >> 2) + n_slice - 1) / n_slice) << 2;
             const int j_begin = slice * per, j_end = min(tile_n4, j_begin + per);
-            float best_d2 = __int_as_float(0x7f800000), best_s = __int_as_float(0x7f800000);
-            int best_j = -1;
-#pragma unroll 2
-            for (int j = j_begin; j < j_end; j += 4) {
+            // The reference takes argmin of sqrt(clamp_min(d^2, 0)) with the first index winning ties.
+            // Both maps are monotone, so the winner is the FIRST anchor whose clamped d^2 is at most
+            // hi(m) = the largest float with the same rounded sqrt as the minimum m.  Two cheap passes
+            // over the slice instead of index bookkeeping in a divergent loop:
+            //   pass 1: m = min d^2 (packed FMA chain + FMNMX only);
+            //   pass 2: first j with d^2 <= hi(m) (one compare per four anchors, branch taken once).
+            auto d2_of4 = [&](int j, float (&d)[4]) {
                 const ulonglong2 xs = *reinterpret_cast<const ulonglong2 *>(s_x + j);
                 const ulonglong2 ys = *reinterpret_cast<const ulonglong2 *>(s_y + j);
                 const ulonglong2 ps = *reinterpret_cast<const ulonglong2 *>(s_p + j);
-                const f32x2 d01 = add2(add2(fma2(c1p, ys.x, mul2(c0p, xs.x)), gnp), ps.x);
-                const f32x2 d23 = add2(add2(fma2(c1p, ys.y, mul2(c0p, xs.y)), gnp), ps.y);
+                unpack2(add2(add2(fma2(c1p, ys.x, mul2(c0p, xs.x)), gnp), ps.x), d[0], d[1]);
+                unpack2(add2(add2(fma2(c1p, ys.y, mul2(c0p, xs.y)), gnp), ps.y), d[2], d[3]);
+            };
+            float m_raw = __int_as_float(0x7f800000);
+#pragma unroll kScanUnroll
+            for (int j = j_begin; j < j_end; j += 4) {
                 float d[4];
-                unpack2(d01, d[0], d[1]);
-                unpack2(d23, d[2], d[3]);
-                // clamp_min(0) and sqrt are monotone: an anchor can only win if its raw d^2 is below the
-                // raw d^2 of the current winner, which happens O(log tile) times per scan
-                if (fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) < best_d2) {
+                d2_of4(j, d);
+                m_raw = fminf(m_raw, fminf(fminf(d[0], d[1]), fminf(d[2], d[3])));
+            }
+            int best_j = -1;
+            float best_s = __int_as_float(0x7f800000);
+            if (m_raw < __int_as_float(0x7f800000)) {
+                const float m = fmaxf(m_raw, 0.f);
+                best_s = __fsqrt_rn(m);
+                float hi = m;                              // at most three floats share a rounded sqrt
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        if (d[v] < best_d2) {
-                            const float s = __fsqrt_rn(fmaxf(d[v], 0.f));
-                            if (s < best_s) { best_s = s; best_d2 = d[v]; best_j = j + v; }
-                        }
+                for (int k = 0; k < 3; ++k) {
+                    const float nx = __uint_as_float(__float_as_uint(hi) + 1u);
+                    if (__fsqrt_rn(nx) == best_s) hi = nx;
+                }
+                for (int j = j_begin; j < j_end && best_j < 0; j += 4) {
+                    float d[4];
+                    d2_of4(j, d);
+                    if (fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) <= hi) {
+#pragma unroll
+                        for (int v = 3; v >= 0; --v)
+                            if (d[v] <= hi) best_j = j + v;  // descending v: the lowest index sticks
                     }
                 }
             }
@@ -552,6 +600,10 @@ __device__ __noinline__ void qfl_bg_slow(float x, float k_cls, float &term, floa
 template <typename T, int VW>
 __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cls, f32x2 k2, f32x2 &acc2, float &fix,
                                              float (&g)[VW]) {
+#ifdef YB_CLS_NOMATH
+    for (int v = 0; v < VW; ++v) g[v] = row.get(v) * k_cls;
+    return;
+#endif
     if constexpr (VW == 1) {
         float q0, q1, t0, t1, g1;
         f32x2 dummy = pack2(0.f, 0.f);
@@ -579,18 +631,22 @@ __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cl
 }
 
 template <typename T, int VW, bool WRITE_GRAD>
-__global__ void __launch_bounds__(kClsThreads)
+__global__ void __launch_bounds__(kClsThreads, YB_CLS_MINBLOCKS)
 cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
                 float *__restrict__ part) {
     __shared__ float s_red[kClsThreads / 32];
     const int n = blockIdx.y;
     const int a0 = (blockIdx.x * kClsThreads + threadIdx.x) * VW;
+    // the class channels of a tile are split over gridDim.z CTAs: short-lived CTAs, small tail
+    const int c_per = (nc + gridDim.z - 1) / gridDim.z;
+    const int c_lo = blockIdx.z * c_per;
+    nc = min(nc, c_lo + c_per) - c_lo;
     f32x2 acc2 = pack2(0.f, 0.f);
     float fix = 0.f;
-    if (a0 < n_anchors) {
-        const size_t base = ((size_t)n * n_ch + 4 * kRegMax) * n_anchors + a0;
+    if (a0 < n_anchors && nc > 0) {
+        const size_t base = ((size_t)n * n_ch + 4 * kRegMax + c_lo) * n_anchors + a0;
         const f32x2 k2 = pack2(k_cls, k_cls);
-        constexpr int U = 4;
+        constexpr int U = YB_CLS_UNROLL;
         // software pipeline: the next U rows are in flight while the current U are evaluated
         Group<T, VW> cur[U];
 #pragma unroll
@@ -622,7 +678,7 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kClsThreads / 32; ++w) s += s_red[w];
-        part[(size_t)n * gridDim.x + blockIdx.x] = s;
+        part[((size_t)n * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x] = s;
     }
 }
 
@@ -669,7 +725,8 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
     const float k_dfl_num = lambda_dfl / ((float)n_images * 4.f);
     constexpr int TILE_A = kAssignThreads * VW, TILE_C = kClsThreads * VW;
-    const int cls_tiles = (n_anchors + TILE_C - 1) / TILE_C;
+    const int cls_split = YB_CLS_CSPLIT;
+    const int cls_tiles = ((n_anchors + TILE_C - 1) / TILE_C) * cls_split;     // partial sums per image
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(0, st)) return rc;
     {
@@ -680,7 +737,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     }
     if (int rc = stage_mark(1, st)) return rc;
     {
-        dim3 grid(cls_tiles, n_images);
+        dim3 grid(cls_tiles / cls_split, n_images, cls_split);
         if (grad != nullptr)
             cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
         else
@@ -709,7 +766,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
 static int cls_tiles_for(int n_anchors, int dtype, bool vec) {
     const int vw = vec ? (dtype == YB_BF16 ? 8 : 4) : 1;
     const int tile = kClsThreads * vw;
-    return (n_anchors + tile - 1) / tile;
+    return ((n_anchors + tile - 1) / tile) * YB_CLS_CSPLIT;
 }
 
 }  // namespace yb
