@@ -30,6 +30,11 @@ struct NmsWorkspace {
     int *cls;                     // [N * A]
     unsigned long long *keys;     // [N * Apad]
     float4 *sbox;                 // [N * A] sorted offset boxes (only used beyond kRegCols * 1024 candidates)
+    unsigned long long *keys2;    // [N * Apad] class-segmented sorted keys of the class-parallel path
+    int *mode;                    // [N] 1 = image finished by the class-parallel kernel (zeroed every call)
+    unsigned *tick;               // [N] CTAs of the image that finished their classes (zeroed every call)
+    unsigned *range;              // [N][2] encoded min x1 / max x2 of the image's candidates (zeroed every call)
+    unsigned char *alive_g;       // [N * Apad] survivor flag per class-sorted position
     int a_pad;
     size_t zero_bytes, total_bytes;
 };
@@ -40,12 +45,22 @@ static NmsWorkspace carve_nms(void *base, int n_images, int n_anchors) {
     size_t off = 0;
     w.count = reinterpret_cast<int *>(p + off);
     off += round_up(sizeof(int) * (size_t)n_images, 64);
+    w.mode = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * (size_t)n_images, 64);
+    w.tick = reinterpret_cast<unsigned *>(p + off);
+    off += round_up(sizeof(unsigned) * (size_t)n_images, 64);
+    w.range = reinterpret_cast<unsigned *>(p + off);
+    off += round_up(sizeof(unsigned) * 2 * (size_t)n_images, 64);
     w.zero_bytes = off;
     w.cls = reinterpret_cast<int *>(p + off);
     off += round_up(sizeof(int) * (size_t)n_images * n_anchors, 64);
     w.a_pad = next_pow2(n_anchors);
     w.keys = reinterpret_cast<unsigned long long *>(p + off);
     off += sizeof(unsigned long long) * (size_t)n_images * w.a_pad;
+    w.keys2 = reinterpret_cast<unsigned long long *>(p + off);
+    off += sizeof(unsigned long long) * (size_t)n_images * w.a_pad;
+    w.alive_g = reinterpret_cast<unsigned char *>(p + off);
+    off += round_up((size_t)n_images * w.a_pad, 64);
     w.sbox = reinterpret_cast<float4 *>(p + off);
     off += (n_anchors > kRegCols * kSortThreads) ? sizeof(float4) * (size_t)n_images * n_anchors : 0;
     w.total_bytes = off;
@@ -126,11 +141,12 @@ nms_scan_kernel(const float *__restrict__ pred, int nc, int n_anchors, float con
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-nms_sort_kernel(const int *__restrict__ count, unsigned long long *__restrict__ keys, int a_pad) {
+nms_sort_kernel(const int *__restrict__ count, const int *__restrict__ mode, unsigned long long *__restrict__ keys,
+                int a_pad) {
     extern __shared__ unsigned long long s_keys[];
     const int n = blockIdx.x;
     const int cnt = count[n];
-    if (cnt <= 1) return;
+    if (cnt <= 1 || mode[n] != 0) return;
     unsigned long long *k = keys + (size_t)n * a_pad;
     const int n_pad = next_pow2(cnt);
     for (int t = cnt + threadIdx.x; t < n_pad; t += blockDim.x) k[t] = kSentinel;
@@ -138,14 +154,20 @@ nms_sort_kernel(const int *__restrict__ count, unsigned long long *__restrict__ 
     cta_bitonic_sort(k, n_pad, s_keys);
 }
 
-// torchvision's IoU test on two xyxy boxes; thr is the largest float <= the double threshold
+// torchvision's IoU test on two xyxy boxes, bit-exact:  fl(inter / (area_a + area_b - inter)) > thr
+// with thr the largest float <= the double threshold.  Boxes that do not intersect give IoU 0 (or
+// NaN), never above thr >= 0; otherwise a MUFU.RCP estimate decides unless it lands within 1e-6
+// (relative) of the threshold, where the IEEE division is taken.
 __device__ __forceinline__ bool iou_exceeds(const float4 &a, float area_a, const float4 &b, float thr) {
-    const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
-    const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (!(w > 0.f && h > 0.f)) return false;
     const float inter = __fmul_rn(w, h);
     const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-    return ovr > thr;
+    const float den = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float est = inter * fast_rcp(den);
+    if (fabsf(est - thr) > fmaf(1e-6f, thr, 1e-35f)) return est > thr;
+    return __fdiv_rn(inter, den) > thr;
 }
 __device__ __forceinline__ float box_area(const float4 &b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
 
@@ -174,7 +196,10 @@ __device__ __forceinline__ unsigned resolve_block(const float4 &bx, bool alive, 
         o.y = __shfl_sync(0xffffffffu, bx.y, r2);
         o.z = __shfl_sync(0xffffffffu, bx.z, r2);
         o.w = __shfl_sync(0xffffffffu, bx.w, r2);
-        if (r2 > lane && iou_exceeds(bx, my_area, o, thr)) sup |= 1u << r2;
+        const bool touch = r2 > lane && fminf(bx.z, o.z) > fmaxf(bx.x, o.x) && fminf(bx.w, o.w) > fmaxf(bx.y, o.y);
+        if (__any_sync(0xffffffffu, touch)) {
+            if (touch && iou_exceeds(bx, my_area, o, thr)) sup |= 1u << r2;
+        }
     }
     unsigned kept = 0;
 #pragma unroll
@@ -211,7 +236,7 @@ __device__ __forceinline__ void emit_row(float *__restrict__ out_rows, int *__re
 template <bool REG>
 __global__ void __launch_bounds__(kSortThreads, 1)
 nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const int *__restrict__ count,
-                 const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
+                 const int *__restrict__ mode, const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
                  float4 *__restrict__ sbox, float thr, int max_det, int agnostic, float *__restrict__ out_rows,
                  int *__restrict__ out_count, int *__restrict__ out_anchor) {
     __shared__ float4 s_row[32];
@@ -221,6 +246,7 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
 
     const int n = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (mode[n] != 0) return;                              // finished by the class-parallel kernel
     const int n_cand = min(count[n], kMaxNms);
     if (n_cand == 0 || max_det <= 0) {
         if (tid == 0) out_count[n] = 0;
@@ -310,6 +336,350 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     if (tid == 0) out_count[n] = min(kept_total, max_det);
 }
 
+// ------------------------------------------------------------------------------------------
+// Class-parallel path.  With the reference's class offset (cls * 7680) boxes of different classes
+// cannot intersect as long as all candidate boxes of the image span less than 7680 px in x, so greedy
+// NMS decomposes into one independent problem per class.  One CTA per image:
+//   1. class histogram + exclusive scan (shared-memory atomics)  -> one segment per class
+//   2. scatter the (score, anchor) keys into their segments, rank-sort every segment by one warp
+//   3. gather the class-offset boxes into shared memory (score order inside each segment)
+//   4. greedy NMS per class: one warp per class walks its rows, lanes test the later columns and
+//      clear their alive bits with warp ballots
+//   5. 5-pass radix select (11-bit digits) of the max_det best survivors, bitonic sort, emit
+// Images the path cannot take (too many candidates for shared memory, one class larger than
+// kClassSegCap, boxes spanning more than 7680 px) are left to the generic sort + sweep kernels,
+// which run afterwards and skip every image whose mode flag is set.  Both paths give the same rows.
+// ------------------------------------------------------------------------------------------
+#ifdef YB_NMS_PROFILE
+__device__ long long g_nms_clk[16];
+__device__ long long g_nms_warp[32][4];
+#define YB_MARK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_nms_clk[i] = clock64(); } while (0)
+#else
+#define YB_MARK(i)
+#endif
+constexpr int kClassThreads = 1024;
+constexpr int kClassCap = 10240;       // candidates per image held in shared memory (16 B each)
+constexpr int kClassSegCap = 512;      // largest class segment the warp-per-class sweep accepts
+constexpr int kClassMaxNc = 1023;      // 10 class bits in the key
+constexpr int kClassMaxDet = 1024;
+constexpr int kAnchorBits = 22;
+constexpr int kSelBits = 11;
+
+__global__ void __launch_bounds__(kClassThreads, 1)
+nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const int *__restrict__ count,
+                 const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
+                 unsigned long long *__restrict__ keys2, unsigned char *__restrict__ alive_g,
+                 unsigned *__restrict__ tick, unsigned *__restrict__ range, float thr, int max_det,
+                 int *__restrict__ mode, float *__restrict__ out_rows, int *__restrict__ out_count,
+                 int *__restrict__ out_anchor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_start[kClassMaxNc + 2];
+    __shared__ int s_cursor[kClassMaxNc + 1];
+    __shared__ unsigned s_alive[kClassCap / 4];           // used as one byte per sorted position
+    __shared__ int s_flag, s_total;
+    __shared__ unsigned s_minx, s_maxx;
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_k;
+
+    // gridDim.x CTAs share an image: CTA `part` owns the classes c with c % gridDim.x == part
+    const int img = blockIdx.y, part = blockIdx.x, n_part = gridDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = count[img];
+    if (n == 0) {
+        if (tid == 0 && part == 0) { out_count[img] = 0; mode[img] = 1; }
+        return;
+    }
+    if (n > kClassCap) return;                             // generic path (same decision in every CTA)
+    const float *img_pred = pred + (size_t)img * (4 + nc) * n_anchors;
+    const unsigned long long *k_in = keys + (size_t)img * a_pad;
+    unsigned long long *k2 = keys2 + (size_t)img * a_pad;
+    const int *cls_n = cls + (size_t)img * n_anchors;
+    unsigned long long *K = reinterpret_cast<unsigned long long *>(smem_raw);
+
+    YB_MARK(0);
+    // ---- 1. histogram of classes, exclusive scan ------------------------------------------------
+    for (int c = tid; c < nc; c += kClassThreads) s_cursor[c] = 0;
+    if (tid == 0) { s_flag = 0; s_minx = 0u; s_maxx = 0u; s_total = 0; }
+    __syncthreads();
+    for (int r = tid; r < n; r += kClassThreads) atomicAdd(&s_cursor[cls_n[key_anchor(k_in[r])]], 1);
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0, big = 0;
+        for (int base = 0; base < nc; base += 32) {
+            const int c = base + lane;
+            const int v = c < nc ? s_cursor[c] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (c < nc) s_start[c] = run + incl - v;
+            big |= v > kClassSegCap;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        big = __any_sync(0xffffffffu, big);
+        if (lane == 0) { s_start[nc] = run; s_flag = big; }
+    }
+    __syncthreads();
+    if (s_flag) return;                                    // a class too large for one warp: generic path
+    for (int c = tid; c < nc; c += kClassThreads) s_cursor[c] = s_start[c];
+    __syncthreads();
+
+    YB_MARK(1);
+    // ---- 2. scatter into class segments, rank-sort each segment (score desc, ties -> lowest anchor)
+    for (int r = tid; r < n; r += kClassThreads) {
+        const unsigned long long key = k_in[r];
+        const unsigned a = key_anchor(key);
+        const int c = cls_n[a];
+        if (c % n_part != part) continue;
+        const int slot = atomicAdd(&s_cursor[c], 1);
+        K[slot] = ((key >> 32) << kAnchorBits) | a;        // 32-bit inverted score | 22-bit anchor
+    }
+    __syncthreads();
+    YB_MARK(2);
+    for (int c = part + warp * n_part; c < nc; c += (kClassThreads / 32) * n_part) {
+        const int seg0 = s_start[c], n_c = s_start[c + 1] - seg0;
+        for (int e0 = 0; e0 < n_c; e0 += 128) {            // four elements per lane per sweep of the segment
+            unsigned long long ke[4];
+            int rank[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ke[u] = (e0 + u * 32 + lane < n_c) ? K[seg0 + e0 + u * 32 + lane] : kSentinel;
+#pragma unroll 4
+            for (int i = 0; i < n_c; ++i) {
+                const unsigned long long ki = K[seg0 + i];  // broadcast
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rank[u] += (ki < ke[u]) ? 1 : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * 32 + lane < n_c) k2[seg0 + rank[u]] = ((unsigned long long)c << 54) | ke[u];
+        }
+    }
+    __syncthreads();
+
+    YB_MARK(3);
+    float4 *B = reinterpret_cast<float4 *>(smem_raw) + 0;  // boxes overwrite the unsorted keys: see the barrier above
+    float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+    YB_MARK(4);
+    // ---- 4. greedy NMS, one warp per class, 32 boxes at a time ---------------------------------
+    // Lane l owns column l of every 32-box block of the segment; bit b of `alive_bits` says whether
+    // its column in block b is still alive.  Per row block: resolve the 32x32 diagonal block with
+    // shuffles (resolve_block), then let the kept rows clear later columns.  All in registers.
+    unsigned char *alive_img = alive_g + (size_t)img * a_pad;                // one byte per sorted position
+    for (int c = part + warp * n_part; c < nc; c += (kClassThreads / 32) * n_part) {
+        const int seg0 = s_start[c], n_c = s_start[c + 1] - seg0;
+        if (n_c == 0) continue;
+        const int nb = (n_c + 31) >> 5;                    // <= 16 (kClassSegCap)
+        // class-offset boxes of the segment into shared memory, in score order (model_utils.py:239, :262-263)
+        for (int m0 = 0; m0 < n_c; m0 += 128) {
+            float bx[4], by[4], bw[4], bh[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int m = m0 + u * 32 + lane;
+                const int a = m < n_c ? (int)(k2[seg0 + m] & ((1u << kAnchorBits) - 1u)) : 0;
+                bx[u] = __ldg(img_pred + a);
+                by[u] = __ldg(img_pred + n_anchors + a);
+                bw[u] = __ldg(img_pred + 2 * (size_t)n_anchors + a);
+                bh[u] = __ldg(img_pred + 3 * (size_t)n_anchors + a);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int m = m0 + u * 32 + lane;
+                if (m >= n_c) continue;
+                const float dw = __fmul_rn(bw[u], 0.5f), dh = __fmul_rn(bh[u], 0.5f);
+                const float off = __fmul_rn((float)c, kMaxWh);
+                const float x1 = __fsub_rn(bx[u], dw), x2 = __fadd_rn(bx[u], dw);
+                B[seg0 + m] = make_float4(__fadd_rn(x1, off), __fadd_rn(__fsub_rn(by[u], dh), off), __fadd_rn(x2, off),
+                                          __fadd_rn(__fadd_rn(by[u], dh), off));
+                lo = fminf(lo, fminf(x1, x2));
+                hi = fmaxf(hi, fmaxf(x1, x2));
+            }
+        }
+        __syncwarp();
+#ifdef YB_NMS_PROFILE
+        long long t_res = 0, t_cross = 0, t0c = clock64();
+#endif
+        unsigned alive_bits = 0;
+        for (int b = 0; b < nb; ++b) alive_bits |= (b * 32 + lane < n_c ? 1u : 0u) << b;
+        for (int rb = 0; rb < nb; ++rb) {
+            const int my = rb * 32 + lane;
+            const float4 rbox = my < n_c ? B[seg0 + my] : make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef YB_NMS_PROFILE
+            long long ta = clock64();
+#endif
+            const unsigned kept = resolve_block(rbox, (alive_bits >> rb) & 1u, thr, 32);
+#ifdef YB_NMS_PROFILE
+            long long tb = clock64(); t_res += tb - ta;
+#endif
+            alive_bits = (alive_bits & ~(1u << rb)) | (((kept >> lane) & 1u) << rb);
+            for (int cb = rb + 1; cb < nb; ++cb) {
+                const int col = cb * 32 + lane;
+                bool live = (alive_bits >> cb) & 1u;
+                const float4 cbox = live ? B[seg0 + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned todo = kept;
+                bool sup = false;
+                while (todo) {                             // warp-uniform walk over the kept rows of block rb
+                    const int r = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float4 row = B[seg0 + rb * 32 + r];                 // broadcast read
+                    // most same-class pairs do not even touch: one vote skips the IoU arithmetic
+                    const bool touch = live && fminf(row.z, cbox.z) > fmaxf(row.x, cbox.x) &&
+                                       fminf(row.w, cbox.w) > fmaxf(row.y, cbox.y);
+                    if (__any_sync(0xffffffffu, touch)) {
+                        if (touch) sup |= iou_exceeds(row, box_area(row), cbox, thr);
+                    }
+                }
+                live = live && !sup;
+                if (!live) alive_bits &= ~(1u << cb);
+            }
+        }
+        for (int b = 0; b < nb; ++b)
+            if (b * 32 + lane < n_c) alive_img[seg0 + b * 32 + lane] = (alive_bits >> b) & 1u;
+#ifdef YB_NMS_PROFILE
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) { g_nms_warp[warp][0] += t_res; g_nms_warp[warp][1] += clock64() - t0c; g_nms_warp[warp][2] += n_c; g_nms_warp[warp][3] += 1; }
+#endif
+    }
+    // x extent of this CTA's candidates -> global, encoded so that atomicMax on zeroed words works
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    auto enc = [](float x) { const unsigned u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+    auto dec = [](unsigned e) { return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e); };
+    if (lane == 0 && lo <= hi) {
+        atomicMax(&s_minx, ~enc(lo));
+        atomicMax(&s_maxx, enc(hi));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_maxx != 0u) {
+            atomicMax(range + 2 * img, s_minx);
+            atomicMax(range + 2 * img + 1, s_maxx);
+        }
+        __threadfence();                                   // this CTA's keys2 / alive flags / range are published
+        s_flag = (atomicAdd(tick + img, 1u) == (unsigned)n_part - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_flag) return;                                   // the last CTA of the image finishes it
+    __threadfence();
+    {
+        const unsigned e_lo = ~__ldcg(range + 2 * img), e_hi = __ldcg(range + 2 * img + 1);
+        // classes stay disjoint only while every box fits in one 7680-px slot (2 px of rounding slack);
+        // infinite coordinates fail the test and go to the generic path
+        if (!(dec(e_hi) - dec(e_lo) <= kMaxWh - 2.f)) return;
+    }
+
+    YB_MARK(5);
+    // ---- 5. the max_det best survivors (smallest 54-bit keys) -------------------------------------
+    // all keys and survivor flags of the image into shared memory, then an 11-bit radix select
+    unsigned char *alive8 = reinterpret_cast<unsigned char *>(s_alive);
+    unsigned long long *KS = reinterpret_cast<unsigned long long *>(smem_raw);
+    int *hist = reinterpret_cast<int *>(smem_raw + sizeof(unsigned long long) * (size_t)kClassCap);
+    unsigned long long *L = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(unsigned long long) * (size_t)kClassCap +
+                                                                  sizeof(int) * (1 << kSelBits));
+    int my_alive = 0;
+    for (int q = tid; q < n; q += kClassThreads) {
+        KS[q] = __ldcg(k2 + q);
+        const unsigned char al = __ldcg(alive_img + q);
+        alive8[q] = al;
+        my_alive += al;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_alive += __shfl_xor_sync(0xffffffffu, my_alive, o);
+    if (lane == 0 && my_alive) atomicAdd(&s_total, my_alive);
+    __syncthreads();
+    const int n_surv = s_total;
+    const int n_sel = min(n_surv, max_det);
+    const unsigned long long key_mask = (1ull << 54) - 1ull;
+    unsigned long long limit = key_mask;                   // select every survivor whose key54 <= limit
+    if (n_surv > max_det) {
+        if (tid == 0) { s_prefix = 0ull; s_k = max_det; }
+        int shift = 54;
+        for (int pass = 0; pass < 5; ++pass) {
+            const int bits = pass < 4 ? kSelBits : 54 - 4 * kSelBits;
+            const int hi_shift = shift;                    // bits above hi_shift are fixed by s_prefix
+            shift -= bits;
+            for (int b = tid; b < (1 << kSelBits); b += kClassThreads) hist[b] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (int q = tid; q < n; q += kClassThreads) {
+                if (!alive8[q]) continue;
+                const unsigned long long k54 = KS[q] & key_mask;
+                if (hi_shift < 54 && (k54 >> hi_shift) != prefix) continue;
+                // lanes with the same digit share one shared-memory atomic
+                const int digit = (int)((k54 >> shift) & ((1u << bits) - 1u));
+                const unsigned peers = __match_any_sync(__activemask(), digit);
+                if ((__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], __popc(peers));
+            }
+            __syncthreads();
+            if (warp == 0) {                               // find the digit where the running count reaches k
+                const int per = (1 << kSelBits) / 32;
+                int local = 0;
+                for (int b = 0; b < per; ++b) local += hist[lane * per + b];
+                int incl = local;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const int excl = incl - local;
+                const int k = s_k;
+                if (excl < k && k <= incl) {               // exactly one lane
+                    int run = excl;
+                    for (int b = 0; b < per; ++b) {
+                        const int h = hist[lane * per + b];
+                        if (run + h >= k) {
+                            s_prefix = (prefix << bits) | (unsigned long long)(lane * per + b);
+                            s_k = k - run;
+                            break;
+                        }
+                        run += h;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        limit = s_prefix;                                  // the max_det-th smallest key
+    }
+    YB_MARK(6);
+    // collect, sort (ascending key = descending score), emit
+    const int n_pad = next_pow2(max(n_sel, 1));
+    if (tid == 0) s_total = 0;
+    for (int t = tid; t < n_pad; t += kClassThreads) L[t] = kSentinel;
+    __syncthreads();
+    for (int q = tid; q < n; q += kClassThreads) {
+        if (!alive8[q]) continue;
+        const unsigned long long e = KS[q];
+        if ((e & key_mask) <= limit) L[atomicAdd(&s_total, 1)] = ((e & key_mask) << 10) | (e >> 54);
+    }
+    __syncthreads();
+    YB_MARK(7);
+    for (int k = 2; k <= n_pad; k <<= 1) bitonic_tile_steps(L, n_pad, 0, k, k >> 1);
+    YB_MARK(8);
+    for (int r = tid; r < n_sel; r += kClassThreads) {
+        const unsigned long long e = L[r];
+        const int c = (int)(e & 1023u);
+        const unsigned long long k54 = e >> 10;
+        const unsigned a = (unsigned)(k54 & ((1u << kAnchorBits) - 1u));
+        const unsigned inv = (unsigned)(k54 >> kAnchorBits);
+        emit_row(out_rows, out_anchor, img, max_det, r, img_pred, n_anchors, ((unsigned long long)inv << 32) | a, c);
+    }
+    YB_MARK(9);
+    if (tid == 0) { out_count[img] = n_sel; mode[img] = 1; }
+}
+#ifdef YB_NMS_PROFILE
+extern "C" int yb_nms_profile_read(long long *out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, g_nms_clk, sizeof(long long) * 16);
+}
+extern "C" int yb_nms_profile_read_warps(long long *out_host) {
+    long long z[128] = {0};
+    cudaMemcpyFromSymbol(out_host, g_nms_warp, sizeof(long long) * 128);
+    return (int)cudaMemcpyToSymbol(g_nms_warp, z, sizeof(z));
+}
+#endif
+
 }  // namespace yb
 
 using namespace yb;
@@ -351,16 +721,27 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
                                                           n_class_filter, w.count, w.cls, w.keys, w.a_pad);
     }
     YB_CUDA(cudaGetLastError());
+    if (!agnostic && nc <= kClassMaxNc && n_anchors < (1 << kAnchorBits) && max_det <= kClassMaxDet) {
+        const size_t csmem = sizeof(float4) * (size_t)kClassCap;      // boxes; later keys + histogram + selection
+        YB_CUDA(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        // CTAs per image: enough to put every SM to work on small batches
+        const int split = n_images >= 96 ? 1 : (n_images >= 48 ? 2 : 4);
+        nms_class_kernel<<<dim3(split, n_images), kClassThreads, csmem, st>>>(
+            prediction, nc, n_anchors, w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det,
+            w.mode, out_rows, out_count, out_anchor);
+        YB_CUDA(cudaGetLastError());
+    }
+    // generic path for whatever the class-parallel kernel left (mode == 0)
     const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
     YB_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_sort_kernel<<<n_images, kSortThreads, smem, st>>>(w.count, w.keys, w.a_pad);
+    nms_sort_kernel<<<n_images, kSortThreads, smem, st>>>(w.count, w.mode, w.keys, w.a_pad);
     YB_CUDA(cudaGetLastError());
     if (n_anchors <= kRegCols * kSortThreads)
-        nms_sweep_kernel<true><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.cls, w.keys,
+        nms_sweep_kernel<true><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
                                                                   w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
                                                                   out_count, out_anchor);
     else
-        nms_sweep_kernel<false><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.cls, w.keys,
+        nms_sweep_kernel<false><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
                                                                    w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
                                                                    out_count, out_anchor);
     YB_CUDA(cudaGetLastError());
