@@ -33,20 +33,33 @@ def reduce_value(value: Union[float, torch.Tensor], average: bool = True):
         return t.item() if was_float else t
 
 
-def reduce_loss_stats(stats: torch.Tensor, n_local: int, group=None) -> torch.Tensor:
-    """All-reduce of ``[total, dfl_mean, cls_mean, num_matched, ...]`` weighted by the local batch
-    size, in a single message.  Returns ``[total, dfl_mean, cls_mean, num_matched_sum, n_global, 0..]``:
-    the first three are global per-image means, i.e. what the reference's three
+def reduce_loss_stats(stats: torch.Tensor, n_local: int, group=None, async_op: bool = False):
+    """All-reduce of the loss kernel's 8-float vector ``[total, dfl_mean, cls_mean, num_matched, ...]``
+    in a single message.  Returns ``[total, dfl_mean, cls_mean, num_matched_sum, n_global, 0..]``: the
+    first three are global per-image means, i.e. what the reference's three
     ``reduce_value(..., average=True)`` calls give when every rank holds the same number of images
-    (DistributedSampler with drop_last, src/data/data_loader.py:19-36)."""
+    (DistributedSampler with drop_last, src/data/data_loader.py:19-36).
+
+    ``async_op=True`` returns ``(tensor, finish)``: the collective runs on NCCL's stream while the next
+    step's kernels run on the caller's; call ``finish()`` before reading the tensor (it waits for
+    the collective and turns the weighted sums into means).
+    """
     v = stats.detach().clone().float()
     v[:3] *= float(n_local)
     v[4] = float(n_local)
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(v, group=group)
-    out = v.clone()
-    out[:3] = v[:3] / v[4]
-    return out
+        work = dist.all_reduce(v, group=group, async_op=async_op)
+
+    def finish():
+        if async_op and work is not None:
+            work.wait()
+        v[:3] /= v[4]
+        return v
+
+    if async_op:
+        return v, finish
+    return finish()
 
 
 def shard_batch(n_global: int, rank: int, world: int):
