@@ -30,6 +30,11 @@ _SIGNATURES = {
     "yb_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
+    "yb_tal_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "yb_tal_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_tal_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                            c_int, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_stage_timing": (c_int, [c_int]),
     "yb_loss_last_stage_ms": (c_int, [c_void_p]),
     "yb_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),

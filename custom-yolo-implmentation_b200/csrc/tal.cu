@@ -1,0 +1,810 @@
+// Task-aligned variant of the training path (sm_100a): DFL decode -> task-aligned assignment
+// (pairwise CIoU over anchors x GT, metric = score^alpha * IoU^beta, per-GT top-k, conflicts to the
+// larger IoU) -> CIoU + DFL + BCE loss and its backward.
+//
+// The reference has NO counterpart for this tier: the specification is the in-repo
+// oracle `oracle/tal_oracle.py` (SURVEY.md §8(a')); results are "parity vs the in-repo oracle".
+//
+// Two ABI calls so that the normaliser can be all-reduced between them (the one real exchange step):
+//   yb_tal_assign   tal_candidates_kernel  per (image, anchor tile): decode the tile into shared memory;
+//                                          one warp per GT enqueues the anchors whose centre lies inside
+//                                          the GT (ballot compaction), evaluates CIoU / metric for the
+//                                          queue and keeps the tile's k best -> per-GT candidate list
+//                   tal_select_kernel      one warp per GT: global top-k (metric desc, anchor asc),
+//                                          64-bit atomicMax (overlap, ~gt) per anchor resolves conflicts
+//                   tal_resolve_kernel     one warp per GT: which of its k anchors it kept, max metric /
+//                                          overlap, normalised target scores, per-GT score sum
+//                   tal_stats_kernel       fixed-order sum -> [sum of target scores, #foreground]
+//   yb_tal_loss     tal_cls_kernel         dense BCE-with-logits at target 0 + gradient, zero box gradient
+//                   tal_fg_kernel          one warp per foreground anchor: CIoU and DFL loss + gradient into
+//                                          its 64 box logits, correction of its one positive class cell
+//                   tal_finalize_kernel    fixed-order reduction -> loss scalars
+// The anchors x GT overlap / metric matrices never exist; only <= k candidates per (GT, tile) leave a CTA.
+#include "common.cuh"
+
+namespace yb {
+
+constexpr int kTalThreads = 128;
+constexpr int kTalMaxK = 16;
+constexpr float kEpsCiou = 1e-7f;
+constexpr float kEpsIn = 1e-9f;
+constexpr float kEpsNorm = 1e-9f;
+constexpr float kFourOverPi2 = 0.40528473456935109f;
+constexpr int kTalFinThreadsDecl = 256;
+
+struct TalWorkspace {
+    // zeroed by yb_tal_assign
+    unsigned int *ticket;               // [2]
+    int *cand_count;                    // [gt_total]
+    unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
+    // plain scratch
+    float4 *cand;                       // [gt_total * cand_cap]  metric, overlap, anchor (as int bits), -
+    float4 *sel;                        // [gt_total * kTalMaxK]  anchor bits, metric, overlap, target score
+    int *sel_count;                     // [gt_total]
+    float *g_tsum;                      // [gt_total]
+    int *g_npos;                        // [gt_total]
+    float *fg_box, *fg_dfl, *fg_cls;    // [gt_total * kTalMaxK] per-foreground loss terms
+    float *part;                        // [N * cls_tiles]
+    double *cta_sums;                   // [4 * finalize CTAs]
+    int cand_cap, cls_tiles;
+    size_t zero_bytes, total_bytes;
+};
+
+static int tal_tile(int dtype, bool vec) { return kTalThreads * (vec ? (dtype == YB_BF16 ? 8 : 4) : 1); }
+
+static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_total, int topk, int tile) {
+    TalWorkspace w;
+    char *p = static_cast<char *>(base);
+    const size_t g = (size_t)(gt_total > 0 ? gt_total : 1);
+    const int tiles = (n_anchors + tile - 1) / tile;
+    size_t off = 0;
+    w.ticket = reinterpret_cast<unsigned int *>(p + off);
+    off += 64;
+    w.cand_count = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * g, 64);
+    w.akey = reinterpret_cast<unsigned long long *>(p + off);
+    off += round_up(sizeof(unsigned long long) * (size_t)n_images * n_anchors, 64);
+    w.zero_bytes = off;
+    w.cand_cap = topk * tiles;
+    w.cls_tiles = tiles;
+    w.cand = reinterpret_cast<float4 *>(p + off);
+    off += round_up(sizeof(float4) * g * (size_t)w.cand_cap, 64);
+    w.sel = reinterpret_cast<float4 *>(p + off);
+    off += round_up(sizeof(float4) * g * kTalMaxK, 64);
+    w.sel_count = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * g, 64);
+    w.g_tsum = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * g, 64);
+    w.g_npos = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * g, 64);
+    w.fg_box = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * g * kTalMaxK, 64);
+    w.fg_dfl = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * g * kTalMaxK, 64);
+    w.fg_cls = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * g * kTalMaxK, 64);
+    w.part = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * (size_t)n_images * tiles, 64);
+    w.cta_sums = reinterpret_cast<double *>(p + off);
+    off += round_up(sizeof(double) * 4 * (((size_t)n_images * tiles + g * kTalMaxK) / kTalFinThreadsDecl + 2), 64);
+    w.total_bytes = off;
+    return w;
+}
+
+// Complete-IoU of a GT box g and a predicted box p (xyxy), spec: oracle/tal_oracle.py::ciou
+struct Ciou {
+    float value, iou, v, alpha, inter, uni, c2, rho2, cw, ch, w1, h1, iw_raw, ih_raw, dxs, dys, at;
+};
+__device__ __forceinline__ float gt_atan(const float4 &g) { return atanf((g.z - g.x) / (g.w - g.y + kEpsCiou)); }
+
+__device__ __forceinline__ Ciou ciou_eval(const float4 &p, const float4 &g, float atan_g) {
+    Ciou r;
+    r.w1 = p.z - p.x;
+    r.h1 = p.w - p.y + kEpsCiou;
+    const float w2 = g.z - g.x, h2 = g.w - g.y + kEpsCiou;
+    r.iw_raw = fminf(p.z, g.z) - fmaxf(p.x, g.x);
+    r.ih_raw = fminf(p.w, g.w) - fmaxf(p.y, g.y);
+    r.inter = fmaxf(r.iw_raw, 0.f) * fmaxf(r.ih_raw, 0.f);
+    r.uni = r.w1 * r.h1 + w2 * h2 - r.inter + kEpsCiou;
+    r.iou = r.inter / r.uni;
+    r.cw = fmaxf(p.z, g.z) - fminf(p.x, g.x);
+    r.ch = fmaxf(p.w, g.w) - fminf(p.y, g.y);
+    r.c2 = r.cw * r.cw + r.ch * r.ch + kEpsCiou;
+    r.dxs = g.x + g.z - p.x - p.z;
+    r.dys = g.y + g.w - p.y - p.w;
+    r.rho2 = (r.dxs * r.dxs + r.dys * r.dys) * 0.25f;
+    r.at = atan_g - atanf(r.w1 / r.h1);
+    r.v = kFourOverPi2 * r.at * r.at;
+    r.alpha = r.v / (r.v - r.iou + (1.f + kEpsCiou));
+    r.value = r.iou - (r.rho2 / r.c2 + r.v * r.alpha);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// tal_candidates_kernel
+// ------------------------------------------------------------------------------------------
+template <typename T, int VW>
+__global__ void __launch_bounds__(kTalThreads)
+tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
+                      const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
+                      int topk, float alpha, float beta, int *__restrict__ cand_count, float4 *__restrict__ cand,
+                      int cand_cap) {
+    constexpr int TILE = kTalThreads * VW;
+    constexpr int NW = kTalThreads / 32;
+    // dynamic shared memory (64 B per anchor of the tile: 32 KB for fp32 rows, 64 KB for bf16 rows)
+    extern __shared__ __align__(16) unsigned char tal_smem[];
+    float4 *s_box = reinterpret_cast<float4 *>(tal_smem);                         // decoded xyxy (pixels)
+    float2 *s_ctr = reinterpret_cast<float2 *>(s_box + TILE);                     // anchor centres (pixels)
+    float (*s_qm)[TILE] = reinterpret_cast<float (*)[TILE]>(s_ctr + TILE);        // per-warp queue: metric
+    float (*s_qo)[TILE] = reinterpret_cast<float (*)[TILE]>(&s_qm[NW][0]);        //                 overlap
+    unsigned short (*s_q)[TILE] = reinterpret_cast<unsigned short (*)[TILE]>(&s_qo[NW][0]);   //     anchor
+    __shared__ float s_bb[4][NW];                        // tile extent of the anchor centres
+
+    const int n = blockIdx.y;
+    const int tile0 = blockIdx.x * TILE;
+    const int a0 = tile0 + threadIdx.x * VW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t img = (size_t)n * n_ch * n_anchors;
+    const int g_begin = gt_off[n];
+    const int m_img = gt_off[n + 1] - g_begin;
+    if (m_img == 0) return;                               // uniform per CTA
+
+    float lo_x = __int_as_float(0x7f800000), lo_y = lo_x, hi_x = -lo_x, hi_y = -lo_x;
+    if (a0 < n_anchors) {
+        float dist[4][VW];
+#pragma unroll
+        for (int side = 0; side < 4; ++side) {
+            DflPartial part[VW];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                Group<T, VW> row[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) row[j].load(preds + img + (size_t)(side * kRegMax + h * 8 + j) * n_anchors + a0);
+#pragma unroll
+                for (int v = 0; v < VW; ++v) {
+                    float x[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
+                    const DflPartial ph = dfl_half8(x, h * 8);
+                    if (h == 0) part[v] = ph;
+                    else dist[side][v] = dfl_merge(part[v], ph);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            const float ax = __ldg(anchors + a0 + v), ay = __ldg(anchors + n_anchors + a0 + v), s = __ldg(strides + a0 + v);
+            const PredBox b = decode_box(ax, ay, s, dist[0][v], dist[1][v], dist[2][v], dist[3][v]);
+            s_box[threadIdx.x * VW + v] = make_float4(b.x1, b.y1, b.x2, b.y2);
+            const float cx = ax * s, cy = ay * s;
+            s_ctr[threadIdx.x * VW + v] = make_float2(cx, cy);
+            lo_x = fminf(lo_x, cx); hi_x = fmaxf(hi_x, cx);
+            lo_y = fminf(lo_y, cy); hi_y = fmaxf(hi_y, cy);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
+        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+        hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+        hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    if (lane == 0) { s_bb[0][warp] = lo_x; s_bb[1][warp] = lo_y; s_bb[2][warp] = hi_x; s_bb[3][warp] = hi_y; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        lo_x = fminf(lo_x, s_bb[0][w]); lo_y = fminf(lo_y, s_bb[1][w]);
+        hi_x = fmaxf(hi_x, s_bb[2][w]); hi_y = fmaxf(hi_y, s_bb[3][w]);
+    }
+    const int tile_n = min(TILE, n_anchors - tile0);
+
+    for (int g = warp; g < m_img; g += NW) {                              // one warp per GT
+        const float *g5 = gt + (size_t)(g_begin + g) * 5;
+        const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
+        const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
+        if (!(gb.x < hi_x && gb.z > lo_x && gb.y < hi_y && gb.w > lo_y)) continue;   // no centre of this tile inside
+        int cls = (int)__ldg(g5 + 4);
+        cls = min(max(cls, 0), n_ch - 4 * kRegMax - 1);
+        const float at_g = gt_atan(gb);
+        // 1. queue the anchors whose centre is strictly inside the GT (ascending anchor order)
+        int nq = 0;
+        for (int base = 0; base < tile_n; base += 32) {
+            const int a = base + lane;
+            bool in = false;
+            if (a < tile_n) {
+                const float2 c = s_ctr[a];
+                in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, in);
+            if (in) s_q[warp][nq + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)a;
+            nq += __popc(mask);
+        }
+        if (nq == 0) continue;
+        __syncwarp();
+        // 2. overlap and alignment metric of the queue
+        for (int q = lane; q < nq; q += 32) {
+            const int a = s_q[warp][q];
+            const float ov = fmaxf(ciou_eval(s_box[a], gb, at_g).value, 0.f);
+            const float logit = load_as_float(preds + img + (size_t)(4 * kRegMax + cls) * n_anchors + tile0 + a);
+            const float sc = __fdiv_rn(1.f, 1.f + expf(-logit));
+            s_qo[warp][q] = ov;
+            float m;
+            if (alpha == 0.5f && beta == 6.f) {             // the defaults: sqrt and three multiplications
+                const float o2 = ov * ov;
+                m = sqrtf(sc) * (o2 * o2 * o2);
+            } else {
+                m = powf(sc, alpha) * powf(ov, beta);
+            }
+            s_qm[warp][q] = m;
+        }
+        __syncwarp();
+        // 3. the tile's k best (metric descending, ties -> lowest anchor = lowest queue position)
+        const int n_sel = min(nq, topk);
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(cand_count + g_begin + g, n_sel);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        float4 *out = cand + (size_t)(g_begin + g) * cand_cap + slot;
+        if (nq <= topk) {
+            for (int q = lane; q < nq; q += 32)
+                out[q] = make_float4(s_qm[warp][q], s_qo[warp][q], __int_as_float(tile0 + (int)s_q[warp][q]), 0.f);
+        } else {
+            for (int r = 0; r < n_sel; ++r) {
+                float bm = -1.f;
+                int bq = 0x7fffffff;
+                for (int q = lane; q < nq; q += 32) {
+                    const float m = s_qm[warp][q];
+                    if (m > bm) { bm = m; bq = q; }               // strict: first (lowest q) maximum per lane
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+                    const int oq = __shfl_xor_sync(0xffffffffu, bq, o);
+                    if (om > bm || (om == bm && oq < bq)) { bm = om; bq = oq; }
+                }
+                if (lane == 0) {
+                    out[r] = make_float4(bm, s_qo[warp][bq], __int_as_float(tile0 + (int)s_q[warp][bq]), 0.f);
+                    s_qm[warp][bq] = -2.f;                        // taken (metrics are >= 0)
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tal_select_kernel: one warp per GT, global top-k of its candidates
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_images, int g) {
+    int lo = 0, hi = n_images;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(gt_off + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128)
+tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total, int topk,
+                  const int *__restrict__ cand_count, const float4 *__restrict__ cand, int cand_cap,
+                  float4 *__restrict__ sel, int *__restrict__ sel_count, unsigned long long *__restrict__ akey) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (g >= gt_total) return;
+    const int n = gt_image(gt_off, n_images, g);
+    const int g_local = g - __ldg(gt_off + n);
+    const int nc = min(cand_count[g], cand_cap);
+    const float4 *c = cand + (size_t)g * cand_cap;
+    const int n_sel = min(nc, topk);
+    unsigned taken = 0;                                    // bit t: my t-th strided entry is already selected
+    for (int r = 0; r < n_sel; ++r) {
+        float bm = -1.f;
+        int ba = 0x7fffffff, bt = -1;
+        float bo = 0.f;
+        for (int q = lane, t = 0; q < nc; q += 32, ++t) {
+            if ((taken >> t) & 1u) continue;
+            const float4 e = c[q];
+            const int a = __float_as_int(e.z);
+            if (e.x > bm || (e.x == bm && a < ba)) { bm = e.x; ba = a; bo = e.y; bt = t; }
+        }
+        float wm = bm; int wa = ba; float wo = bo; int wl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, wm, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, wa, o);
+            const float oo = __shfl_xor_sync(0xffffffffu, wo, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+            if (om > wm || (om == wm && oa < wa)) { wm = om; wa = oa; wo = oo; wl = ol; }
+        }
+        if (lane == wl && bt >= 0) taken |= 1u << bt;
+        if (lane == 0) {
+            sel[(size_t)g * kTalMaxK + r] = make_float4(__int_as_float(wa), wm, wo, 0.f);
+            // conflict resolution: the anchor goes to the GT with the largest overlap, ties -> lowest GT
+            atomicMax(akey + (size_t)n * n_anchors + wa,
+                      ((unsigned long long)__float_as_uint(wo) << 32) | (unsigned int)(~(unsigned int)g_local));
+        }
+    }
+    if (lane == 0) sel_count[g] = n_sel;
+}
+
+// one warp per GT: keep the anchors this GT won, normalise their target scores
+__global__ void __launch_bounds__(128)
+tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total,
+                   const unsigned long long *__restrict__ akey, float4 *__restrict__ sel, const int *__restrict__ sel_count,
+                   float *__restrict__ g_tsum, int *__restrict__ g_npos, int *__restrict__ out_assigned,
+                   float *__restrict__ out_tscore) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (g >= gt_total) return;
+    const int n = gt_image(gt_off, n_images, g);
+    const int g_local = g - __ldg(gt_off + n);
+    const int ns = sel_count[g];
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool pos = false;
+    if (lane < ns) {
+        e = sel[(size_t)g * kTalMaxK + lane];
+        const unsigned long long k = akey[(size_t)n * n_anchors + __float_as_int(e.x)];
+        pos = (unsigned int)(k & 0xffffffffull) == (unsigned int)(~(unsigned int)g_local);
+    }
+    float mm = pos ? e.y : 0.f, mo = pos ? e.z : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    }
+    const float t = pos ? e.y * (mo / (mm + kEpsNorm)) : 0.f;
+    float ts = t;
+    int np = pos ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        np += __shfl_xor_sync(0xffffffffu, np, o);
+    }
+    if (lane < ns) {
+        sel[(size_t)g * kTalMaxK + lane].w = pos ? t : -1.f;      // -1: lost the anchor to another GT
+        if (pos && out_assigned) out_assigned[(size_t)n * n_anchors + __float_as_int(e.x)] = g_local;
+        if (pos && out_tscore) out_tscore[(size_t)n * n_anchors + __float_as_int(e.x)] = t;
+    }
+    if (lane == 0) { g_tsum[g] = ts; g_npos[g] = np; }
+}
+
+__global__ void __launch_bounds__(256)
+tal_stats_kernel(int gt_total, const float *__restrict__ g_tsum, const int *__restrict__ g_npos, float *__restrict__ out_stats) {
+    __shared__ double s_t[256];
+    __shared__ double s_n[256];
+    double t = 0.0, np = 0.0;
+    for (int g = threadIdx.x; g < gt_total; g += 256) { t += (double)g_tsum[g]; np += (double)g_npos[g]; }
+    s_t[threadIdx.x] = t; s_n[threadIdx.x] = np;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_t[threadIdx.x] += s_t[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out_stats[0] = (float)s_t[0];      // local sum of target scores (un-clamped)
+        out_stats[1] = (float)s_n[0];      // foreground anchors
+#pragma unroll
+        for (int i = 2; i < 8; ++i) out_stats[i] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 2: dense BCE-with-logits at target 0 (+ zero box gradient), foreground terms, finalize
+// ------------------------------------------------------------------------------------------
+// softplus(x) = max(x,0) + log1p(exp(-|x|));  d/dx = sigmoid(x)
+__device__ __forceinline__ void bce_bg_elem(float x, float kc, float &acc, float &g) {
+    const float e = __expf(-fabsf(x));
+    acc += fmaxf(x, 0.f) + log1pf(e);
+    const float r = fast_rcp(1.f + e);
+    g = kc * (x >= 0.f ? r : e * r);
+}
+
+template <typename T, int VW, bool WRITE_GRAD>
+__global__ void __launch_bounds__(kTalThreads)
+tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ tss_dev,
+               float lambda_cls, T *__restrict__ grad, float *__restrict__ part) {
+    __shared__ float s_red[kTalThreads / 32];
+    const int n = blockIdx.y;
+    const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
+    const float kc = lambda_cls / fmaxf(__ldg(tss_dev), 1.f);
+    float acc = 0.f;
+    if (a0 < n_anchors) {
+        const size_t img = (size_t)n * n_ch * n_anchors + a0;
+        if (WRITE_GRAD) {
+            for (int c = 0; c < 4 * kRegMax; ++c) Group<T, VW>::store_zero(grad + img + (size_t)c * n_anchors);
+        }
+        const size_t base = img + (size_t)4 * kRegMax * n_anchors;
+        constexpr int U = 4;
+        Group<T, VW> cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (u < nc) cur[u].load(preds + base + (size_t)u * n_anchors);
+        for (int c = 0; c < nc; c += U) {
+            Group<T, VW> nxt[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (c + U + u < nc) nxt[u].load(preds + base + (size_t)(c + U + u) * n_anchors);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (c + u < nc) {
+                    float g[VW];
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) bce_bg_elem(cur[u].get(v), kc, acc, g[v]);
+                    if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kTalThreads / 32; ++w) s += s_red[w];
+        part[(size_t)n * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// one warp per (GT, selected anchor) slot
+template <typename T>
+__global__ void __launch_bounds__(128)
+tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
+              const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
+              const int *__restrict__ gt_off, int gt_total, int topk, const float4 *__restrict__ sel,
+              const int *__restrict__ sel_count, const float *__restrict__ tss_dev, float lambda_box, float lambda_cls,
+              float lambda_dfl, T *__restrict__ grad, float *__restrict__ fg_box, float *__restrict__ fg_dfl,
+              float *__restrict__ fg_cls) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);          // slot = g * topk + r
+    const int g = slot / topk, r = slot % topk;
+    if (g >= gt_total) return;
+    float4 e = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (r < sel_count[g]) e = sel[(size_t)g * kTalMaxK + r];
+    if (!(e.w >= 0.f)) {                                   // unused slot or anchor lost to another GT
+        if (lane == 0) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; }
+        return;
+    }
+    const int idx = __float_as_int(e.x);
+    const float t = e.w;
+    const int n = gt_image(gt_off, n_images, g);
+    const T *img = preds + (size_t)n * n_ch * n_anchors;
+    const float inv_tss = 1.f / fmaxf(__ldg(tss_dev), 1.f);
+    const float wgt = t * inv_tss;
+
+    const int bin = lane & 15, half = lane >> 4;
+    const float z_lo = load_as_float(img + (size_t)lane * n_anchors + idx);
+    const float z_hi = load_as_float(img + (size_t)(lane + 32) * n_anchors + idx);
+    const float *g5 = gt + (size_t)g * 5;
+    const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
+    int cls = (int)__ldg(g5 + 4);
+    cls = min(max(cls, 0), nc - 1);
+    const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
+    const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
+
+    float m_lo = z_lo, m_hi = z_hi;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, o));
+        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, o));
+    }
+    const float e_lo = expf(z_lo - m_lo), e_hi = expf(z_hi - m_hi);
+    float s_lo = e_lo, s_hi = e_hi;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, o);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
+    }
+    const float p_lo = __fdiv_rn(e_lo, s_lo), p_hi = __fdiv_rn(e_hi, s_hi);
+    float d_lo = p_lo * (float)bin, d_hi = p_hi * (float)bin;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        d_lo += __shfl_xor_sync(0xffffffffu, d_lo, o);
+        d_hi += __shfl_xor_sync(0xffffffffu, d_hi, o);
+    }
+    const float dl = __shfl_sync(0xffffffffu, d_lo, 0), dt = __shfl_sync(0xffffffffu, d_lo, 16);
+    const float dr = __shfl_sync(0xffffffffu, d_hi, 0), db = __shfl_sync(0xffffffffu, d_hi, 16);
+    const PredBox b = decode_box(ax, ay, s, dl, dt, dr, db);
+    const float4 pb = make_float4(b.x1, b.y1, b.x2, b.y2);
+    const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
+
+    // ---- CIoU and its gradient w.r.t. the predicted corners (alpha_v constant) --------------------
+    const Ciou c = ciou_eval(pb, gb, gt_atan(gb));
+    auto w_gt = [](float a, float o) { return a > o ? 1.f : (a == o ? 0.5f : 0.f); };     // d max(a,o)/da
+    auto w_lt = [](float a, float o) { return a < o ? 1.f : (a == o ? 0.5f : 0.f); };     // d min(a,o)/da
+    const float iw = fmaxf(c.iw_raw, 0.f), ih = fmaxf(c.ih_raw, 0.f);
+    const float d_inter = (c.uni + c.inter) / (c.uni * c.uni);       // d iou / d inter (union contains -inter)
+    const float d_area1 = -c.inter / (c.uni * c.uni);
+    const float d_iw = c.iw_raw >= 0.f ? d_inter * ih : 0.f;
+    const float d_ih = c.ih_raw >= 0.f ? d_inter * iw : 0.f;
+    // iou part
+    float gx1 = -d_iw * w_gt(pb.x, gb.x) - d_area1 * c.h1;
+    float gx2 = d_iw * w_lt(pb.z, gb.z) + d_area1 * c.h1;
+    float gy1 = -d_ih * w_gt(pb.y, gb.y) - d_area1 * c.w1;
+    float gy2 = d_ih * w_lt(pb.w, gb.w) + d_area1 * c.w1;
+    // - rho2 / c2
+    const float inv_c2 = 1.f / c.c2;
+    const float k_r = c.rho2 * inv_c2 * inv_c2;                      // rho2 / c2^2
+    // d rho2/dx1 = d rho2/dx2 = -dxs/2 ;  d c2/dx2 = 2 cw [x2 > u2], d c2/dx1 = -2 cw [x1 < u1]
+    gx1 -= (-0.5f * c.dxs) * inv_c2 - k_r * (-2.f * c.cw * w_lt(pb.x, gb.x));
+    gx2 -= (-0.5f * c.dxs) * inv_c2 - k_r * (2.f * c.cw * w_gt(pb.z, gb.z));
+    gy1 -= (-0.5f * c.dys) * inv_c2 - k_r * (-2.f * c.ch * w_lt(pb.y, gb.y));
+    gy2 -= (-0.5f * c.dys) * inv_c2 - k_r * (2.f * c.ch * w_gt(pb.w, gb.w));
+    // - alpha v :  v = k at^2, at = atan(w2/h2) - atan(w1/h1)
+    const float dv_dA1 = -2.f * kFourOverPi2 * c.at;
+    const float hyp = c.h1 * c.h1 + c.w1 * c.w1;
+    const float dv_dw1 = dv_dA1 * (c.h1 / hyp), dv_dh1 = dv_dA1 * (-c.w1 / hyp);
+    gx1 -= c.alpha * (-dv_dw1);
+    gx2 -= c.alpha * dv_dw1;
+    gy1 -= c.alpha * (-dv_dh1);
+    gy2 -= c.alpha * dv_dh1;
+    // L_box = (1 - ciou) * t / tss * lambda_box
+    const float kb = -lambda_box * wgt;
+    const float d_dl = kb * gx1 * (-s), d_dt = kb * gy1 * (-s), d_dr = kb * gx2 * s, d_db = kb * gy2 * s;
+
+    // ---- DFL rows (same target rule as the reference, src/model/losses.py:226-246, :63-78) -------
+    const float t_l = ax - gb.x / s, t_t = ay - gb.y / s, t_r = gb.z / s - ax, t_b = gb.w / s - ay;
+    const float hi_clamp = (float)(kRegMax - 1 - 0.01);
+    const float t_lo = fminf(fmaxf(half == 0 ? t_l : t_t, 0.f), hi_clamp);
+    const float t_hi = fminf(fmaxf(half == 0 ? t_r : t_b, 0.f), hi_clamp);
+    const int bl_lo = (int)t_lo, bl_hi = (int)t_hi;
+    const float wl_lo = (float)(bl_lo + 1) - t_lo, wr_lo = t_lo - (float)bl_lo;
+    const float wl_hi = (float)(bl_hi + 1) - t_hi, wr_hi = t_hi - (float)bl_hi;
+    const float lp_lo = (z_lo - m_lo) - logf(s_lo), lp_hi = (z_hi - m_hi) - logf(s_hi);
+    const int base = lane & 16;
+    const float ce_lo = -(__shfl_sync(0xffffffffu, lp_lo, base + bl_lo) * wl_lo +
+                          __shfl_sync(0xffffffffu, lp_lo, base + bl_lo + 1) * wr_lo);
+    const float ce_hi = -(__shfl_sync(0xffffffffu, lp_hi, base + bl_hi) * wl_hi +
+                          __shfl_sync(0xffffffffu, lp_hi, base + bl_hi + 1) * wr_hi);
+    const float ce_half = ce_lo + ce_hi;
+    const float dfl4 = ce_half + __shfl_xor_sync(0xffffffffu, ce_half, 16);      // sum over the four sides
+    const float kd = lambda_dfl * wgt * 0.25f;
+
+    if (grad != nullptr) {
+        const float dd_lo = half == 0 ? d_dl : d_dt, dd_hi = half == 0 ? d_dr : d_db;
+        const float dk_lo = half == 0 ? dl : dt, dk_hi = half == 0 ? dr : db;
+        const float oh_lo = (bin == bl_lo ? wl_lo : 0.f) + (bin == bl_lo + 1 ? wr_lo : 0.f);
+        const float oh_hi = (bin == bl_hi ? wl_hi : 0.f) + (bin == bl_hi + 1 ? wr_hi : 0.f);
+        const float g_lo = kd * ((wl_lo + wr_lo) * p_lo - oh_lo) + dd_lo * p_lo * ((float)bin - dk_lo);
+        const float g_hi = kd * ((wl_hi + wr_hi) * p_hi - oh_hi) + dd_hi * p_hi * ((float)bin - dk_hi);
+        T *gimg = grad + (size_t)n * n_ch * n_anchors;
+        store_from_float(gimg + (size_t)lane * n_anchors + idx, g_lo);
+        store_from_float(gimg + (size_t)(lane + 32) * n_anchors + idx, g_hi);
+        if (lane == 0) {
+            // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / tss
+            const float sg = __fdiv_rn(1.f, 1.f + expf(-z_cls));
+            store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx, lambda_cls * inv_tss * (sg - t));
+        }
+    }
+    if (lane == 0) {
+        fg_box[slot] = (1.f - c.value) * t;
+        fg_dfl[slot] = dfl4 * 0.25f * t;
+        fg_cls[slot] = -t * z_cls;
+    }
+}
+
+// fixed-order reduction in two levels: CTA b sums its slice of every array (tree of fixed shape) and
+// publishes 4 partials; the last CTA to finish adds the partials up in index order.
+constexpr int kTalFinThreads = 256;
+__global__ void __launch_bounds__(kTalFinThreads)
+tal_finalize_kernel(int n_part, int n_slots, int gt_total, const float *__restrict__ part,
+                    const float *__restrict__ fg_box, const float *__restrict__ fg_dfl, const float *__restrict__ fg_cls,
+                    const int *__restrict__ g_npos, const float *__restrict__ tss_dev, float lambda_box, float lambda_cls,
+                    float lambda_dfl, double *__restrict__ cta_sums, unsigned int *__restrict__ ticket,
+                    float *__restrict__ out_loss) {
+    __shared__ double s[4][kTalFinThreads];
+    __shared__ bool s_last;
+    const size_t i = (size_t)blockIdx.x * kTalFinThreads + threadIdx.x;
+    s[0][threadIdx.x] = (i < (size_t)n_part ? (double)part[i] : 0.0) + (i < (size_t)n_slots ? (double)fg_cls[i] : 0.0);
+    s[1][threadIdx.x] = i < (size_t)n_slots ? (double)fg_box[i] : 0.0;
+    s[2][threadIdx.x] = i < (size_t)n_slots ? (double)fg_dfl[i] : 0.0;
+    s[3][threadIdx.x] = i < (size_t)gt_total ? (double)g_npos[i] : 0.0;
+    __syncthreads();
+    for (int o = kTalFinThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int k = 0; k < 4; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 4; ++k) cta_sums[(size_t)blockIdx.x * 4 + k] = s[k][0];
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kTalFinThreads)
+        for (int k = 0; k < 4; ++k) acc[k] += __ldcg(cta_sums + (size_t)b * 4 + k);
+    for (int k = 0; k < 4; ++k) s[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int o = kTalFinThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int k = 0; k < 4; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double tss = fmax((double)tss_dev[0], 1.0);
+        const float l_cls = (float)(s[0][0] / tss), l_box = (float)(s[1][0] / tss), l_dfl = (float)(s[2][0] / tss);
+        out_loss[0] = lambda_box * l_box + lambda_cls * l_cls + lambda_dfl * l_dfl;
+        out_loss[1] = l_box;
+        out_loss[2] = l_cls;
+        out_loss[3] = l_dfl;
+        out_loss[4] = (float)tss;
+        out_loss[5] = (float)s[3][0];
+        out_loss[6] = out_loss[7] = 0.f;
+        *ticket = 0u;                                      // re-armed for the next yb_tal_loss on this workspace
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static bool tal_vec_ok(const void *preds, const void *grad, int n_anchors) {
+    constexpr int VW = ElemsPer16<T>::value;
+    return n_anchors % VW == 0 && aligned16(preds) && (grad == nullptr || aligned16(grad));
+}
+
+template <typename T, int VW>
+static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors, const float *anchors,
+                             const float *strides, const float *gt, const int32_t *gt_off, int gt_total, int topk,
+                             float alpha, float beta, float *out_stats, int32_t *out_assigned, float *out_tscore,
+                             const TalWorkspace &w, cudaStream_t st) {
+    const int n_ch = 4 * kRegMax + nc;
+    YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
+    if (out_assigned) YB_CUDA(cudaMemsetAsync(out_assigned, 0xff, sizeof(int32_t) * (size_t)n_images * n_anchors, st));
+    if (out_tscore) YB_CUDA(cudaMemsetAsync(out_tscore, 0, sizeof(float) * (size_t)n_images * n_anchors, st));
+    if (gt_total > 0) {
+        constexpr int TILE = kTalThreads * VW;
+        dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
+        const size_t smem = (size_t)TILE * (16 + 8 + (kTalThreads / 32) * (4 + 4 + 2));
+        YB_CUDA(cudaFuncSetAttribute(tal_candidates_kernel<T, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tal_candidates_kernel<T, VW><<<grid, kTalThreads, smem, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
+                                                                     topk, alpha, beta, w.cand_count, w.cand, w.cand_cap);
+        YB_CUDA(cudaGetLastError());
+        const int blocks = (gt_total + 3) / 4;
+        tal_select_kernel<<<blocks, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, topk, w.cand_count, w.cand,
+                                                  w.cand_cap, w.sel, w.sel_count, w.akey);
+        YB_CUDA(cudaGetLastError());
+        tal_resolve_kernel<<<blocks, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, w.akey, w.sel, w.sel_count,
+                                                   w.g_tsum, w.g_npos, out_assigned, out_tscore);
+        YB_CUDA(cudaGetLastError());
+    }
+    tal_stats_kernel<<<1, 256, 0, st>>>(gt_total, w.g_tsum, w.g_npos, out_stats);
+    YB_CUDA(cudaGetLastError());
+    return YB_OK;
+}
+
+template <typename T, int VW>
+static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, const float *anchors,
+                           const float *strides, const float *gt, const int32_t *gt_off, int gt_total,
+                           int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl, T *grad,
+                           float *out_loss, const TalWorkspace &w, cudaStream_t st) {
+    const int n_ch = 4 * kRegMax + nc;
+    {
+        constexpr int TILE = kTalThreads * VW;
+        dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
+        if (grad != nullptr)
+            tal_cls_kernel<T, VW, true><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, grad, w.part);
+        else
+            tal_cls_kernel<T, VW, false><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, grad, w.part);
+        YB_CUDA(cudaGetLastError());
+    }
+    if (gt_total > 0) {
+        const int slots = gt_total * topk;
+        tal_fg_kernel<T><<<(slots + 3) / 4, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
+                                                         gt_total, topk, w.sel, w.sel_count, tss_dev, lambda_box, lambda_cls,
+                                                         lambda_dfl, grad, w.fg_box, w.fg_dfl, w.fg_cls);
+        YB_CUDA(cudaGetLastError());
+    }
+    {
+        const int n_part = n_images * w.cls_tiles, n_slots = gt_total * topk;
+        const int n_max = max(max(n_part, n_slots), gt_total);
+        const int blocks = (n_max + kTalFinThreads - 1) / kTalFinThreads;
+        tal_finalize_kernel<<<blocks, kTalFinThreads, 0, st>>>(n_part, n_slots, gt_total, w.part, w.fg_box, w.fg_dfl, w.fg_cls,
+                                                               w.g_npos, tss_dev, lambda_box, lambda_cls, lambda_dfl,
+                                                               w.cta_sums, w.ticket, out_loss);
+    }
+    YB_CUDA(cudaGetLastError());
+    return YB_OK;
+}
+
+static int tal_check(const void *preds, const float *anchors, const float *strides, const int32_t *gt_off,
+                     const float *gt, void *workspace, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                     int gt_total, int topk, const char *who) {
+    YB_REQUIRE(preds && anchors && strides && gt_off && workspace, "%s: null pointer", who);
+    YB_REQUIRE(gt_total == 0 || gt != nullptr, "%s: gt is null but gt_total > 0", who);
+    YB_REQUIRE(n_images > 0 && n_images <= 65535 && nc > 0 && n_anchors > 0 && gt_total >= 0, "%s: bad sizes", who);
+    YB_REQUIRE(reg_max == kRegMax, "%s: reg_max must be %d (got %d)", who, kRegMax, reg_max);
+    YB_REQUIRE(dtype == YB_F32 || dtype == YB_BF16, "%s: dtype must be YB_F32 or YB_BF16", who);
+    YB_REQUIRE(topk >= 1 && topk <= kTalMaxK, "%s: topk must be in [1, %d]", who, kTalMaxK);
+    YB_REQUIRE(n_anchors <= 65535 * 8, "%s: too many anchors", who);
+    if (!aligned16(workspace)) {
+        set_error("%s: workspace must be 16-byte aligned", who);
+        return YB_ERR_ALIGN;
+    }
+    return YB_OK;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype, int topk) {
+    if (n_images <= 0 || n_anchors <= 0 || gt_total < 0 || topk < 1 || topk > kTalMaxK) return 0;
+    // sized for the scalar fall-back (smallest tile -> most tiles)
+    return carve_tal(nullptr, n_images, n_anchors, gt_total, topk, tal_tile(dtype, false)).total_bytes;
+}
+
+extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                             const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                             int gt_total, int topk, float alpha, float beta, float *out_stats,
+                             int32_t *out_assigned_gt, float *out_target_score, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    if (int rc = tal_check(preds, anchors, strides, gt_offsets, gt, workspace, dtype, n_images, nc, reg_max, n_anchors,
+                           gt_total, topk, "yb_tal_assign"))
+        return rc;
+    YB_REQUIRE(out_stats != nullptr, "yb_tal_assign: out_stats is null");
+    if (workspace_bytes < yb_tal_workspace_bytes(n_images, n_anchors, gt_total, dtype, topk)) {
+        set_error("yb_tal_assign: workspace too small");
+        return YB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == YB_F32) {
+        const bool vec = tal_vec_ok<float>(preds, nullptr, n_anchors);
+        const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, topk, tal_tile(dtype, vec));
+        if (vec)
+            return launch_tal_assign<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
+                                               gt_total, topk, alpha, beta, out_stats, out_assigned_gt, out_target_score, w, st);
+        return launch_tal_assign<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
+                                           gt_total, topk, alpha, beta, out_stats, out_assigned_gt, out_target_score, w, st);
+    }
+    const bool vec = tal_vec_ok<__nv_bfloat16>(preds, nullptr, n_anchors);
+    const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, topk, tal_tile(dtype, vec));
+    if (vec)
+        return launch_tal_assign<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
+                                                   gt_offsets, gt_total, topk, alpha, beta, out_stats, out_assigned_gt,
+                                                   out_target_score, w, st);
+    return launch_tal_assign<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
+                                               gt_offsets, gt_total, topk, alpha, beta, out_stats, out_assigned_gt,
+                                               out_target_score, w, st);
+}
+
+extern "C" int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                           const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                           int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls,
+                           float lambda_dfl, void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes,
+                           void *stream) {
+    if (int rc = tal_check(preds, anchors, strides, gt_offsets, gt, workspace, dtype, n_images, nc, reg_max, n_anchors,
+                           gt_total, topk, "yb_tal_loss"))
+        return rc;
+    YB_REQUIRE(tss_dev && out_loss, "yb_tal_loss: null pointer");
+    if (workspace_bytes < yb_tal_workspace_bytes(n_images, n_anchors, gt_total, dtype, topk)) {
+        set_error("yb_tal_loss: workspace too small");
+        return YB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the tile (hence the workspace carving) must be the one yb_tal_assign used: decided by preds only
+    if (dtype == YB_F32) {
+        const bool vec_a = tal_vec_ok<float>(preds, nullptr, n_anchors);
+        const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, topk, tal_tile(dtype, vec_a));
+        if (vec_a && tal_vec_ok<float>(preds, grad_preds, n_anchors))
+            return launch_tal_loss<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
+                                             gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, (float *)grad_preds, out_loss, w, st);
+        YB_REQUIRE(!vec_a, "yb_tal_loss: grad_preds must be 16-byte aligned when preds is");
+        return launch_tal_loss<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
+                                         gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, (float *)grad_preds, out_loss, w, st);
+    }
+    const bool vec_a = tal_vec_ok<__nv_bfloat16>(preds, nullptr, n_anchors);
+    const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, topk, tal_tile(dtype, vec_a));
+    if (vec_a && tal_vec_ok<__nv_bfloat16>(preds, grad_preds, n_anchors))
+        return launch_tal_loss<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
+                                                 gt_offsets, gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl,
+                                                 (__nv_bfloat16 *)grad_preds, out_loss, w, st);
+    YB_REQUIRE(!vec_a, "yb_tal_loss: grad_preds must be 16-byte aligned when preds is");
+    return launch_tal_loss<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
+                                             gt_offsets, gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl,
+                                             (__nv_bfloat16 *)grad_preds, out_loss, w, st);
+}

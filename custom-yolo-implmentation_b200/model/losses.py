@@ -22,7 +22,8 @@ import torch.nn as nn
 
 from .. import _cabi
 
-__all__ = ["YoloDFLQFLoss", "bbox_iou", "quality_focal_loss", "distribution_focal_loss", "pack_gt", "fused_loss"]
+__all__ = ["YoloDFLQFLoss", "bbox_iou", "quality_focal_loss", "distribution_focal_loss", "pack_gt", "fused_loss",
+           "fused_tal_loss"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -157,6 +158,86 @@ class _FusedLoss(torch.autograd.Function):
         return (g,) + (None,) * 11
 
 
+def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, anchors: torch.Tensor,
+                   strides: torch.Tensor, num_classes: int, lambda_box: float, lambda_cls: float, lambda_dfl: float,
+                   reg_max: int = 16, topk: int = 10, alpha: float = 0.5, beta: float = 6.0, want_grad: bool = True,
+                   want_trace: bool = False, sync_normalizer: bool = True):
+    """Task-aligned variant (``yb_tal_assign`` + ``yb_tal_loss``).  Not in the reference: specified by
+    ``oracle/tal_oracle.py`` (SURVEY.md §8(a')).
+
+    Between the two calls the normaliser ``sum(target scores)`` is all-reduced (SUM / world) when a
+    process group is initialised and ``sync_normalizer`` is set — the path's one real exchange step.
+    Returns ``(out_loss (8,) [total, box, cls, dfl, normaliser, #fg, ..], grad or None, trace)``.
+    """
+    _cabi.require_cuda(preds, "preds")
+    n, c, a = preds.shape
+    if c != 4 * reg_max + num_classes:
+        raise ValueError(f"preds has {c} channels, expected 4*{reg_max} + {num_classes}")
+    dev = preds.device
+    dt = _cabi.dtype_code(preds.dtype)
+    x = preds.detach() if preds.requires_grad else preds
+    if not x.is_contiguous():
+        x = x.contiguous()
+    anc, st = _as_f32(anchors, dev), _as_f32(strides, dev)
+    gt_total = int(gt.shape[0])
+    lib = _cabi.lib()
+    ws = _stream_workspace(lib.yb_tal_workspace_bytes(n, a, gt_total, dt, topk), dev)
+    stats = torch.empty(8, dtype=torch.float32, device=dev)
+    asg = tsc = None
+    if want_trace:
+        asg = torch.empty(n, a, dtype=torch.int32, device=dev)
+        tsc = torch.empty(n, a, dtype=torch.float32, device=dev)
+    gt_ptr = _cabi.ptr(gt) if gt_total else None
+    with torch.cuda.device(dev):
+        rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
+                               _cabi.ptr(gt_offsets), gt_total, int(topk), float(alpha), float(beta), _cabi.ptr(stats),
+                               _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "yb_tal_assign")
+    _cabi.count_launches(4 if gt_total else 1)
+    tss = stats[:1]
+    if sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1:
+        tss = stats[:2].clone()
+        torch.distributed.all_reduce(tss)                       # [sum of target scores, #foreground]
+        tss = (tss / torch.distributed.get_world_size())[:1].contiguous()
+    grad = torch.empty_like(x) if want_grad else None
+    out = torch.empty(8, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.yb_tal_loss(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
+                             _cabi.ptr(gt_offsets), gt_total, int(topk), _cabi.ptr(tss), float(lambda_box), float(lambda_cls),
+                             float(lambda_dfl), _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(),
+                             _cabi.stream_ptr(dev))
+    _cabi.check(rc, "yb_tal_loss")
+    _cabi.count_launches(3 if gt_total else 2)
+    trace = {"assigned_gt": asg, "target_score": tsc, "stats": stats} if want_trace else {}
+    return out, grad, trace
+
+
+class _FusedTalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, gt, gt_offsets, anchors, strides, num_classes, lambdas, reg_max, tal, need, holder):
+        out, grad, _ = fused_tal_loss(preds, gt, gt_offsets, anchors, strides, num_classes, lambdas[0], lambdas[1],
+                                      lambdas[2], reg_max, tal["topk"], tal["alpha"], tal["beta"], want_grad=need,
+                                      sync_normalizer=tal["sync_normalizer"])
+        ctx.grad = grad
+        holder.append(out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_total):
+        g = ctx.grad
+        ctx.grad = None
+        if g is None:
+            return (None,) * 11
+        scale = grad_total.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(g.device):
+            rc = _cabi.lib().yb_scale_grad(_cabi.ptr(g), _cabi.dtype_code(g.dtype), g.numel(), _cabi.ptr(scale),
+                                           _cabi.stream_ptr(g.device))
+        _cabi.check(rc, "yb_scale_grad")
+        _cabi.count_launches(1)
+        return (g,) + (None,) * 10
+
+
 class YoloDFLQFLoss(nn.Module):
     """Same constructor and ``forward`` contract as the reference class (losses.py:84-281).
 
@@ -165,15 +246,24 @@ class YoloDFLQFLoss(nn.Module):
     Python floats; they are fetched with ONE device-to-host copy instead of three ``.item()`` syncs.
     ``last_stats`` keeps the 8-float device vector [total, dfl, cls, #matched, ...] of the last call
     for ``training.distributed_setup.reduce_loss_stats``.
+
+    ``assigner="tal"`` (not in the reference; BASELINE.json's north_star) switches to the task-aligned
+    assigner with CIoU + DFL + BCE losses (``topk``, ``alpha``, ``beta``); the dict then also carries
+    ``"dfl_loss"`` and ``"box_loss"`` is the CIoU term.  Under DDP the normaliser is all-reduced.
     """
 
-    def __init__(self, num_classes=171, lambda_box=1.5, lambda_cls=1.0, lambda_dfl=1.5, reg_max=16):
+    def __init__(self, num_classes=171, lambda_box=1.5, lambda_cls=1.0, lambda_dfl=1.5, reg_max=16,
+                 assigner="nearest_center", topk=10, alpha=0.5, beta=6.0, sync_normalizer=True):
         super().__init__()
+        if assigner not in ("nearest_center", "tal"):
+            raise ValueError(f"assigner must be 'nearest_center' (the reference's behaviour) or 'tal', got {assigner!r}")
         self.num_classes = num_classes
         self.lambda_box = lambda_box
         self.lambda_cls = lambda_cls
         self.lambda_dfl = lambda_dfl
         self.reg_max = reg_max
+        self.assigner = assigner
+        self.tal = {"topk": topk, "alpha": alpha, "beta": beta, "sync_normalizer": sync_normalizer}
         self.last_stats = None
 
     def forward(self, preds, gt_boxes_list, anchors, strides):
@@ -181,6 +271,16 @@ class YoloDFLQFLoss(nn.Module):
         if len(gt_boxes_list) != n:
             raise IndexError(f"gt_boxes_list has {len(gt_boxes_list)} entries for a batch of {n}")
         gt, off, counts = pack_gt(gt_boxes_list, preds.device)
+        if self.assigner == "tal":
+            # not in the reference: task-aligned assigner + CIoU / DFL / BCE, here lambda_box IS used
+            need_grad = torch.is_grad_enabled() and preds.requires_grad
+            holder = []
+            total = _FusedTalLoss.apply(preds, gt, off, anchors, strides, self.num_classes,
+                                        (self.lambda_box, self.lambda_cls, self.lambda_dfl), self.reg_max, self.tal,
+                                        need_grad, holder)
+            stats = self.last_stats = holder[0]
+            host = stats[:4].tolist()
+            return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2], "dfl_loss": host[3]}
         if n > 0 and sum(counts) == 0:
             # the reference fails here: total_dfl is still the python float 0.0 (losses.py:271-279)
             raise AttributeError("'float' object has no attribute 'detach'")

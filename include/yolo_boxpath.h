@@ -99,6 +99,33 @@ int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_images, int nc
                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training, task-aligned variant (BASELINE.json north_star; NO counterpart in the reference — see
+ * SURVEY.md §0.1 / §8(a'); specified by oracle/tal_oracle.py):  pairwise CIoU over anchors x GT,
+ * metric = sigmoid(cls)^alpha * CIoU^beta, per-GT top-k (ties -> lowest anchor), conflicts to the larger
+ * CIoU (ties -> lowest GT), normalised target scores; CIoU + DFL + BCE-with-logits loss and backward.
+ * Two calls with the normaliser in between, so the caller can all-reduce it (SUM / world) under DDP:
+ *
+ *   yb_tal_assign  -> out_stats[0] = sum of target scores of this rank (un-clamped), [1] = #foreground;
+ *                     out_assigned_gt (N, A) int32 (-1 background) / out_target_score (N, A) fp32: optional
+ *   yb_tal_loss    <- tss_dev: device scalar, the normaliser to use (clamped at 1 inside);
+ *                  -> grad_preds (or NULL), out_loss: [0] total [1] box (CIoU) [2] cls (BCE) [3] dfl
+ *                     [4] normaliser used [5] #foreground
+ * The same workspace must be passed to both calls (it carries the assignment).
+ * ---------------------------------------------------------------------------------------- */
+size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype, int topk);
+
+int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                  const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                  int gt_total, int topk, float alpha, float beta, float *out_stats,
+                  int32_t *out_assigned_gt, float *out_target_score,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl,
+                void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Decode.  Replaces DFL.forward (src/model/model_blocks.py:278-280), dist2bbox
  * (src/utils/model_utils.py:120-129) and the decode block of decode_predictions
  * (src/training/train_model.py:36-109) / Model.inference (src/model/model_builder.py:123-133).
