@@ -55,6 +55,9 @@ _SIGNATURES = {
     "yb_bbox_iou": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yb_box_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "yb_box_iou_batch": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "yb_detection_counters_bytes": (c_size_t, [c_int]),
+    "yb_detection_match": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   c_float, c_void_p, c_void_p]),
     "yb_qfl_workspace_bytes": (c_size_t, [c_size_t]),
     "yb_quality_focal_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),

@@ -16,6 +16,8 @@
 //                    QFL cell of each matched anchor (loss delta + gradient).
 //   finalize_kernel  one warp per image reduces that image's partial sums; the last CTA adds the
 //                    images up; everything in a fixed order, so the loss is run-to-run identical.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace yb {
@@ -49,11 +51,12 @@ constexpr unsigned long long kNoKey = ~0ull;
 struct LossWorkspace {
     unsigned int *ticket;          // [1]   finalize_kernel completion counter      } zeroed
     unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys   } every call
-    int *m_idx;                    // [gt_total] matched anchor
-    int *m_cls;                    // [gt_total] class id, or -1 when this GT does not own its anchor's target row
+    int *m_idx;                    // [gt_total] 1 if this GT owns its anchor's QFL target row (last of its duplicates)
+    int *m_cls;                    // [gt_total] matched anchor (for finalize_kernel's positive-cell write)
     float *m_iou;                  // [gt_total]
     float *m_dfl;                  // [gt_total] sum over the 4 sides of the DFL term
     float *m_dcls;                 // [gt_total] QFL correction of the GT's positive cell: T (q^2 log p - p^2 log q)
+    float *m_cellg;                // [gt_total] gradient of that cell (applied by finalize_kernel, after the class pass)
     float *part;                   // [N * tiles] per-CTA sums of p^2 log(1-p)
     float *img_terms;              // [3 * N] per-image DFL term, QFL term, matched-anchor count
     size_t zero_bytes;
@@ -79,6 +82,8 @@ static LossWorkspace carve(void *base, int n_images, int cls_tiles, int gt_total
     w.m_dfl = reinterpret_cast<float *>(p + off);
     off += g4;
     w.m_dcls = reinterpret_cast<float *>(p + off);
+    off += g4;
+    w.m_cellg = reinterpret_cast<float *>(p + off);
     off += g4;
     w.part = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * (size_t)n_images * cls_tiles, 64);
@@ -398,8 +403,8 @@ match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors,
              const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
              const int *__restrict__ gt_off, int gt_total, const unsigned long long *__restrict__ best,
              float k_dfl_num, float k_cls, T *__restrict__ grad, float *__restrict__ m_dfl,
-             float *__restrict__ m_dcls, int *__restrict__ m_win, int *__restrict__ out_idx,
-             float *__restrict__ out_iou) {
+             float *__restrict__ m_dcls, int *__restrict__ m_win, int *__restrict__ m_anchor,
+             float *__restrict__ m_cellg, int *__restrict__ out_idx, float *__restrict__ out_iou) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (kMatchThreads / 32) + (threadIdx.x >> 5);          // one warp per GT
     if (g >= gt_total) return;
@@ -440,18 +445,15 @@ match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors,
             m_dfl[g] = mine.dfl;
             m_dcls[g] = winner ? mine.iou * mine.cell_delta : 0.f;
             m_win[g] = winner ? 1 : 0;
+            m_anchor[g] = idx;
+            // the anchor's one positive QFL cell: finalize_kernel overwrites the target-0 gradient that
+            // cls_loss_kernel (which may run concurrently with this kernel) writes there
+            m_cellg[g] = mine.cell_grad0 + mine.iou * mine.cell_grad1;
             if (out_idx) out_idx[g] = idx;
             if (out_iou) out_iou[g] = mine.iou;
         }
         if (grad != nullptr) {
             T *gimg = grad + (size_t)n * n_ch * n_anchors;
-            if (winner && lane == 0) {
-                // the anchor's one positive QFL cell: overwrite the target-0 gradient cls_loss_kernel wrote
-                int cls = (int)__ldg(gt + (size_t)g * 5 + 4);
-                cls = min(max(cls, 0), nc - 1);
-                store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
-                                 mine.cell_grad0 + mine.iou * mine.cell_grad1);
-            }
             if (first == m) {
                 float g_lo = mine.g_lo, g_hi = mine.g_hi;
                 if (last != m) {
@@ -482,11 +484,14 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kFinThreads)
-finalize_kernel(int n_images, int n_anchors, int cls_tiles, const int *__restrict__ gt_off,
-                const float *__restrict__ part, const float *__restrict__ m_dfl, const float *__restrict__ m_dcls,
-                const int *__restrict__ m_win, float lambda_cls, float lambda_dfl, float *__restrict__ img_terms,
-                unsigned int *__restrict__ ticket, float *__restrict__ out_loss, float *__restrict__ out_per_image) {
+finalize_kernel(int n_images, int n_ch, int nc, int n_anchors, int cls_tiles, const int *__restrict__ gt_off,
+                const float *__restrict__ gt, const float *__restrict__ part, const float *__restrict__ m_dfl,
+                const float *__restrict__ m_dcls, const int *__restrict__ m_win, const int *__restrict__ m_anchor,
+                const float *__restrict__ m_cellg, T *__restrict__ grad, float lambda_cls, float lambda_dfl,
+                float *__restrict__ img_terms, unsigned int *__restrict__ ticket, float *__restrict__ out_loss,
+                float *__restrict__ out_per_image) {
     __shared__ bool s_last;
     __shared__ double s_d[kFinThreads / 32], s_c[kFinThreads / 32], s_f[kFinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -498,7 +503,14 @@ finalize_kernel(int n_images, int n_anchors, int cls_tiles, const int *__restric
         for (int m = lane; m < mb; m += 32) {
             d_img += (double)__ldcg(m_dfl + gb + m);
             c_img += (double)__ldcg(m_dcls + gb + m);
-            f_img += (double)__ldcg(m_win + gb + m);
+            const int win = __ldcg(m_win + gb + m);
+            f_img += (double)win;
+            if (win && grad != nullptr) {                  // the positive cell of a matched anchor
+                int cls = (int)__ldg(gt + (size_t)(gb + m) * 5 + 4);
+                cls = min(max(cls, 0), nc - 1);
+                store_from_float(grad + ((size_t)b * n_ch + 4 * kRegMax + cls) * n_anchors + __ldcg(m_anchor + gb + m),
+                                 __ldcg(m_cellg + gb + m));
+            }
         }
         c_img = warp_sum_d(c_img);
         d_img = warp_sum_d(d_img);
@@ -715,6 +727,44 @@ static int stage_mark(int i, cudaStream_t st) {
     return YB_OK;
 }
 
+// The class pass does not depend on the matching, so it runs on a side stream while
+// assign -> match run on the caller's stream; finalize joins both.  One side stream + two events per
+// device, created on first use (fork/join through events is also legal inside CUDA-graph capture).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream g_side[64];
+
+// YB_OVERLAP (environment, read once): 0 = one stream, 1 = class pass on a side stream (default),
+// 2 = side stream at the lowest priority, 3 = like 1 but the class pass is launched before assign
+static int overlap_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("YB_OVERLAP");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+static int side_for_current_device(SideStream **out) {
+    int dev = 0;
+    YB_CUDA(cudaGetDevice(&dev));
+    YB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    SideStream &sd = g_side[dev];
+    if (sd.stream == nullptr) {
+        // lowest priority: when both streams have CTAs pending, the short latency-bound kernels of the
+        // caller's stream (match, finalize) are dispatched first and hide under the class pass
+        int prio_lo = 0, prio_hi = 0;
+        YB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        YB_CUDA(cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, overlap_mode() == 2 ? prio_lo : prio_hi));
+        YB_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
+        YB_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
+    }
+    *out = &sd;
+    return YB_OK;
+}
+
 template <typename T, int VW>
 static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, const float *anchors, const float *strides,
                        const float *gt, const int32_t *gt_off, int gt_total, int gmax, float lambda_cls,
@@ -727,36 +777,54 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     constexpr int TILE_A = kAssignThreads * VW, TILE_C = kClsThreads * VW;
     const int cls_split = YB_CLS_CSPLIT;
     const int cls_tiles = ((n_anchors + TILE_C - 1) / TILE_C) * cls_split;     // partial sums per image
+    // stage timing serialises the kernels on one stream so that each can be bracketed by events
+    const bool overlap = !g_stage_timing && gt_total > 0 && overlap_mode() != 0;
+    SideStream *sd = nullptr;
+    cudaStream_t st_cls = st;
+    if (overlap) {
+        if (int rc = side_for_current_device(&sd)) return rc;
+        st_cls = sd->stream;
+        YB_CUDA(cudaEventRecord(sd->fork, st));            // everything the caller queued (preds ready, buffers free)
+        YB_CUDA(cudaStreamWaitEvent(st_cls, sd->fork, 0));
+    }
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(0, st)) return rc;
-    {
+    auto launch_assign = [&]() -> int {
         dim3 grid((n_anchors + TILE_A - 1) / TILE_A, n_images);
         assign_kernel<T, VW><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
                                                               w.best, grad);
         YB_CUDA(cudaGetLastError());
-    }
+        return YB_OK;
+    };
+    const bool cls_first = overlap && overlap_mode() == 3;
+    if (!cls_first)
+        if (int rc = launch_assign()) return rc;
     if (int rc = stage_mark(1, st)) return rc;
     {
         dim3 grid(cls_tiles / cls_split, n_images, cls_split);
         if (grad != nullptr)
-            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st_cls>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
         else
-            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st_cls>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
         YB_CUDA(cudaGetLastError());
+        if (overlap) YB_CUDA(cudaEventRecord(sd->join, st_cls));
     }
+    if (cls_first)
+        if (int rc = launch_assign()) return rc;
     if (int rc = stage_mark(2, st)) return rc;
     if (gt_total > 0) {
         const int warps = kMatchThreads / 32;
         match_kernel<T><<<(gt_total + warps - 1) / warps, kMatchThreads, 0, st>>>(
             preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, gt_total, w.best, k_dfl_num, k_cls, grad,
-            w.m_dfl, w.m_dcls, w.m_idx, out_idx, out_iou);
+            w.m_dfl, w.m_dcls, w.m_idx, w.m_cls, w.m_cellg, out_idx, out_iou);
         YB_CUDA(cudaGetLastError());
     }
+    if (overlap) YB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));      // join: the class pass has written its gradients
     {
         const int warps = kFinThreads / 32;
-        finalize_kernel<<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
-            n_images, n_anchors, cls_tiles, gt_off, w.part, w.m_dfl, w.m_dcls, w.m_idx, lambda_cls, lambda_dfl, w.img_terms,
-            w.ticket, out_loss, out_per_image);
+        finalize_kernel<T><<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
+            n_images, n_ch, nc, n_anchors, cls_tiles, gt_off, gt, w.part, w.m_dfl, w.m_dcls, w.m_idx, w.m_cls, w.m_cellg, grad,
+            lambda_cls, lambda_dfl, w.img_terms, w.ticket, out_loss, out_per_image);
         YB_CUDA(cudaGetLastError());
     }
     if (int rc = stage_mark(3, st)) return rc;

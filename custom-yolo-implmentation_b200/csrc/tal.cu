@@ -285,7 +285,7 @@ __device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_im
 
 __global__ void __launch_bounds__(128)
 tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total, int topk,
-                  const int *__restrict__ cand_count, const float4 *__restrict__ cand, int cand_cap,
+                  const int *__restrict__ cand_count, float4 *__restrict__ cand, int cand_cap,
                   float4 *__restrict__ sel, int *__restrict__ sel_count, unsigned long long *__restrict__ akey) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -293,18 +293,16 @@ tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, i
     const int n = gt_image(gt_off, n_images, g);
     const int g_local = g - __ldg(gt_off + n);
     const int nc = min(cand_count[g], cand_cap);
-    const float4 *c = cand + (size_t)g * cand_cap;
+    float4 *c = cand + (size_t)g * cand_cap;               // scratch list: a selected entry gets metric -2
     const int n_sel = min(nc, topk);
-    unsigned taken = 0;                                    // bit t: my t-th strided entry is already selected
     for (int r = 0; r < n_sel; ++r) {
         float bm = -1.f;
         int ba = 0x7fffffff, bt = -1;
         float bo = 0.f;
-        for (int q = lane, t = 0; q < nc; q += 32, ++t) {
-            if ((taken >> t) & 1u) continue;
+        for (int q = lane; q < nc; q += 32) {
             const float4 e = c[q];
             const int a = __float_as_int(e.z);
-            if (e.x > bm || (e.x == bm && a < ba)) { bm = e.x; ba = a; bo = e.y; bt = t; }
+            if (e.x > bm || (e.x == bm && a < ba)) { bm = e.x; ba = a; bo = e.y; bt = q; }
         }
         float wm = bm; int wa = ba; float wo = bo; int wl = lane;
 #pragma unroll
@@ -315,7 +313,8 @@ tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, i
             const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
             if (om > wm || (om == wm && oa < wa)) { wm = om; wa = oa; wo = oo; wl = ol; }
         }
-        if (lane == wl && bt >= 0) taken |= 1u << bt;
+        if (lane == wl && bt >= 0) c[bt].x = -2.f;         // taken (metrics are >= 0)
+        __syncwarp();
         if (lane == 0) {
             sel[(size_t)g * kTalMaxK + r] = make_float4(__int_as_float(wa), wm, wo, 0.f);
             // conflict resolution: the anchor goes to the GT with the largest overlap, ties -> lowest GT

@@ -192,6 +192,21 @@ int yb_bbox_iou(const float *box1, const float *box2, int m, float *out_iou,
 int yb_box_iou(const float *box1, int n, const float *box2, int m, float eps, float *out, void *stream);
 int yb_box_iou_batch(const float *box1, int n, const float *box2, int m, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Validation bookkeeping.  Replaces DetectionMetrics.update (src/training/metrics.py:68-160; called per
+ * image at src/training/train_model.py:326-328) for a whole batch: greedy class-matched TP/FP/FN.
+ *   pred_rows   (N, row_stride, 5) fp32 [cx, cy, w, h, cls] (the layout yb_val_decode writes), pred_count (N)
+ *   pred_scores (N, row_stride) or NULL; rows with score < score_threshold are ignored (:82-86)
+ *   gt / gt_offsets as in yb_loss_fwd_bwd; gmax = most targets of one image (<= 1024)
+ *   counters    uint64[8 + 4*nc], ACCUMULATED (zero them to reset):
+ *               [0] tp [1] fp [2] fn [3] total_predictions [4] total_ground_truths
+ *               [8..] class_tp, then class_fp, class_fn, class_gt_count (nc each)
+ * ---------------------------------------------------------------------------------------- */
+size_t yb_detection_counters_bytes(int nc);
+int yb_detection_match(const float *pred_rows, int row_stride, const int32_t *pred_count, const float *pred_scores,
+                       float score_threshold, const float *gt, const int32_t *gt_offsets, int gmax, int n_images,
+                       int nc, float iou_threshold, uint64_t *counters, void *stream);
+
 /* quality_focal_loss (src/model/losses.py:46-57) on dense (M, C) logits/targets, fp32:
  * out_loss[0] = -sum(...)/M; grad_scores (M, C) or NULL = d out_loss / d pred_scores (times *grad_out if given). */
 size_t yb_qfl_workspace_bytes(size_t n_elements);

@@ -162,6 +162,46 @@ def decode_case(name, n, nc, imgsz, seed, conf, top_k, cls_mean):
     print(f"{name}: rows per image {cnt.tolist()}")
 
 
+def metrics_case(name, seed, n_images, nc, thr):
+    """DetectionMetrics of the reference on seeded predictions/targets (incl. empty images, score filter)."""
+    g = torch.Generator().manual_seed(seed)
+    mt = ref_metrics.DetectionMetrics(nc, iou_threshold=thr)
+    preds, tgts, scores = [], [], []
+    for i in range(n_images):
+        m = int(torch.randint(0, 9, (1,), generator=g))
+        p = int(torch.randint(0, 14, (1,), generator=g))
+        if i == 1: m = 0
+        if i == 2: p = 0
+        t = torch.cat((torch.rand(m, 2, generator=g) * 200, 10 + torch.rand(m, 2, generator=g) * 60,
+                       torch.randint(0, nc, (m, 1), generator=g).float()), 1)
+        # predictions: jittered copies of targets (some right class, some wrong) + random boxes
+        k = min(p, m)
+        src = torch.randperm(m, generator=g)[:k] if m else torch.zeros(0, dtype=torch.long)
+        near = t[src].clone()
+        near[:, :4] += (torch.rand(k, 4, generator=g) - 0.5) * 12
+        flip = torch.rand(k, generator=g) < 0.25
+        near[flip, 4] = torch.randint(0, nc, (int(flip.sum()),), generator=g).float()
+        rnd = torch.cat((torch.rand(p - k, 2, generator=g) * 200, 10 + torch.rand(p - k, 2, generator=g) * 60,
+                         torch.randint(0, nc, (p - k, 1), generator=g).float()), 1)
+        pr = torch.cat((near, rnd), 0)[torch.randperm(p, generator=g)] if p else torch.zeros(0, 5)
+        sc = torch.rand(p, generator=g)
+        mt.update(pr, t, pred_scores=sc if i % 2 == 0 else None, score_threshold=0.3)
+        preds.append(pr); tgts.append(t); scores.append(sc if i % 2 == 0 else torch.ones(p))
+    out = mt.compute()
+    pp, pc = pack_ragged(preds, 5, np.float32)
+    tt, tc = pack_ragged(tgts, 5, np.float32)
+    ss, _ = pack_ragged(scores, 0, np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), preds=pp, pred_count=pc, targets=tt, target_count=tc, scores=ss,
+                        use_scores=np.array([i % 2 == 0 for i in range(n_images)]), meta=np.array([n_images, nc], np.int64),
+                        thr=np.float64(thr),
+                        totals=np.array([mt.true_positives, mt.false_positives, mt.false_negatives, mt.total_predictions,
+                                         mt.total_ground_truths], np.int64),
+                        class_tp=mt.class_tp.numpy(), class_fp=mt.class_fp.numpy(), class_fn=mt.class_fn.numpy(),
+                        class_gt=mt.class_gt_count.numpy(),
+                        compute=np.array([out["precision"], out["recall"], out["f1_score"], out["mAP"]], np.float64))
+    print(f"{name}: TP {mt.true_positives} FP {mt.false_positives} FN {mt.false_negatives}")
+
+
 def helper_case(name, seed):
     g = torch.Generator().manual_seed(seed)
     m, c = 37, 11
@@ -202,3 +242,5 @@ if __name__ == "__main__":
     decode_case("decode_topk", 3, 6, 160, 21, conf=0.25, top_k=100, cls_mean=-1.0)
     decode_case("decode_sparse", 3, 6, 160, 22, conf=0.6, top_k=100, cls_mean=-4.0)
     helper_case("helpers", 31)
+    metrics_case("metrics_a", 41, 12, 5, 0.5)
+    metrics_case("metrics_b", 42, 9, 3, 0.3)
