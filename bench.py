@@ -13,7 +13,7 @@ synthetic head outputs.  Workload at every N: cfg2 of BASELINE.json per GPU (bat
   e2e         the same metric through the public drop-in API (YoloDFLQFLoss.forward + backward) with
               HOST inputs: every step copies preds / GT from pinned host memory and reads the loss
               scalars back.
-  roofline    dominant kernel (cls_loss_kernel): algorithmic bytes / CUDA-event duration vs the
+  roofline    dominant kernel (fused_main_kernel): algorithmic bytes / CUDA-event duration vs the
               measured copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline / --impl reference
               the CPU oracle port of the reference's loss (oracle/loss_oracle.py; the reference is
@@ -226,21 +226,20 @@ def run_ours(args):
         _cabi.check(lib.yb_loss_last_stage_ms(buf), "yb_loss_last_stage_ms")
         stage.append([buf[0], buf[1], buf[2]])
     lib.yb_stage_timing(0)
-    assign_ms, cls_ms, match_ms = (statistics.mean(s[i] for s in stage) for i in range(3))   # launch order
+    main_ms, match_ms, fin_ms = (statistics.mean(s[i] for s in stage) for i in range(3))   # launch order
     peak, peak_src = measured_peak_gbs()
-    cls_bytes = 2 * n * nc * a * preds.element_size()                  # class logits read + class gradient written
-    assign_bytes = 2 * n * 64 * a * preds.element_size()               # box logits read + box gradient written
-    cls_gbs = cls_bytes / (cls_ms * 1e-3) / 1e9
+    # fused_main_kernel = box role (reads the 64 box channels, writes their gradient) + class role (reads the nc
+    # class channels, writes their gradient): every byte of preds read once, every byte of grad written once
+    main_bytes = bytes_per_step
+    main_gbs = main_bytes / (main_ms * 1e-3) / 1e9
     traffic = None                                   # dram read+write per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath) and (n, nc, a, preds.element_size()) == (128, 80, 8400, 4):
-        traffic = json.load(open(tpath)).get("cls_loss_kernel")
-    roofline = {"bound": "hbm", "kernel": "cls_loss_kernel", "achieved": cls_gbs, "peak": peak, "unit": "GB/s",
-                "frac": cls_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": cls_bytes, "ms_per_launch": cls_ms,
-                "other_kernels": {"assign_kernel": {"ms": assign_ms, "GB/s": assign_bytes / (assign_ms * 1e-3) / 1e9,
-                                                    "frac": assign_bytes / (assign_ms * 1e-3) / 1e9 / peak},
-                                  "match_kernel+finalize_kernel": {"ms": match_ms}},
+        traffic = json.load(open(tpath)).get("fused_main_kernel")
+    roofline = {"bound": "hbm", "kernel": "fused_main_kernel", "achieved": main_gbs, "peak": peak, "unit": "GB/s",
+                "frac": main_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": main_bytes, "ms_per_launch": main_ms,
+                "other_kernels": {"match_kernel": {"ms": match_ms}, "finalize_kernel": {"ms": fin_ms}},
                 "whole_step": {"algorithmic_bytes": bytes_per_step, "GB/s": bytes_per_step / (ms_per_step * 1e-3) / 1e9,
                                "frac": bytes_per_step / (ms_per_step * 1e-3) / 1e9 / peak}}
 

@@ -1,7 +1,7 @@
 // Fused decode + nearest-centre assignment + DFL/QFL loss + backward (sm_100a).
 //
 // Replaces YoloDFLQFLoss.forward and its autograd backward (src/model/losses.py:93-281).
-// Four launches per step (the last two are tiny), every head-output byte read once and every gradient byte written once;
+// Three launches per step (the last two are tiny; assign + class pass share one launch, see fused_main_kernel), every head-output byte read once and every gradient byte written once;
 // the (M x A) distance matrix, the decoded boxes and the dense (A x nc) QFL target never exist:
 //
 //   assign_kernel    reads the 4*16 box channels (128-bit loads), decodes each anchor's predicted
@@ -10,7 +10,7 @@
 //                    atomicMax on (distance, anchor) keys, and zero-fills the box-channel gradient.
 //   cls_loss_kernel  reads the nc class channels: QFL loss + gradient of every cell for target 0
 //                    (all but <= one cell per GT), per-CTA partial sums.  Independent of the matching.
-//   match_kernel     one warp per GT: gathers the 64 logits of the matched anchor, DFL loss and its
+//   match_kernel     one half-warp per GT: gathers the 64 logits of the matched anchor, DFL loss and its
 //                    gradient, IoU soft target (reference formula, slip included) and the gradient
 //                    that flows through it, duplicate-anchor resolution; corrects the one positive
 //                    QFL cell of each matched anchor (loss delta + gradient).
@@ -52,11 +52,10 @@ struct LossWorkspace {
     unsigned int *ticket;          // [1]   finalize_kernel completion counter      } zeroed
     unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys   } every call
     int *m_idx;                    // [gt_total] 1 if this GT owns its anchor's QFL target row (last of its duplicates)
-    int *m_cls;                    // [gt_total] matched anchor (for finalize_kernel's positive-cell write)
+    int *gt_img;                   // [gt_total] image of each GT (written by the box role, read by match_kernel)
     float *m_iou;                  // [gt_total]
     float *m_dfl;                  // [gt_total] sum over the 4 sides of the DFL term
     float *m_dcls;                 // [gt_total] QFL correction of the GT's positive cell: T (q^2 log p - p^2 log q)
-    float *m_cellg;                // [gt_total] gradient of that cell (applied by finalize_kernel, after the class pass)
     float *part;                   // [N * tiles] per-CTA sums of p^2 log(1-p)
     float *img_terms;              // [3 * N] per-image DFL term, QFL term, matched-anchor count
     size_t zero_bytes;
@@ -75,15 +74,13 @@ static LossWorkspace carve(void *base, int n_images, int cls_tiles, int gt_total
     const size_t g4 = round_up(sizeof(int) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
     w.m_idx = reinterpret_cast<int *>(p + off);
     off += g4;
-    w.m_cls = reinterpret_cast<int *>(p + off);
+    w.gt_img = reinterpret_cast<int *>(p + off);
     off += g4;
     w.m_iou = reinterpret_cast<float *>(p + off);
     off += g4;
     w.m_dfl = reinterpret_cast<float *>(p + off);
     off += g4;
     w.m_dcls = reinterpret_cast<float *>(p + off);
-    off += g4;
-    w.m_cellg = reinterpret_cast<float *>(p + off);
     off += g4;
     w.part = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * (size_t)n_images * cls_tiles, 64);
@@ -97,22 +94,24 @@ static LossWorkspace carve(void *base, int n_images, int cls_tiles, int gt_total
 // assign_kernel
 // ------------------------------------------------------------------------------------------
 template <typename T, int VW>
-__global__ void __launch_bounds__(kAssignThreads, YB_ASSIGN_MINBLOCKS ? YB_ASSIGN_MINBLOCKS : (VW == 8 ? 6 : 4))
-assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
-              const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
-              unsigned long long *__restrict__ best, T *__restrict__ grad) {
+__device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict__ preds, int n_ch, int n_anchors,
+                                            const float *__restrict__ anchors, const float *__restrict__ strides,
+                                            const float *__restrict__ gt, const int *__restrict__ gt_off,
+                                            unsigned long long *__restrict__ best, int *__restrict__ gt_img,
+                                            T *__restrict__ grad) {
     constexpr int TILE = kAssignThreads * VW;
     constexpr int TILE4 = (TILE + 3) & ~3;
     // predicted centres of the tile's anchors, structure-of-arrays so that four anchors are one LDS.128
     __shared__ __align__(16) float s_x[TILE4], s_y[TILE4], s_p[TILE4];     // cx, cy, cx^2 + cy^2
     __shared__ unsigned long long s_key[kAssignThreads];
 
-    const int n = blockIdx.y;
-    const int tile0 = blockIdx.x * TILE;
+    const int tile0 = tile * TILE;
     const int a0 = tile0 + threadIdx.x * VW;
     const size_t img = (size_t)n * n_ch * n_anchors;
     const int g_begin = gt_off[n];
     const int m_img = gt_off[n + 1] - g_begin;
+    if (tile == 0)                                         // GT -> image table for match_kernel
+        for (int m = threadIdx.x; m < m_img; m += kAssignThreads) gt_img[g_begin + m] = n;
 
     if (a0 < n_anchors) {
         float dist[4][VW];
@@ -262,11 +261,20 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
     }
 }
 
+template <typename T, int VW>
+__global__ void __launch_bounds__(kAssignThreads, YB_ASSIGN_MINBLOCKS ? YB_ASSIGN_MINBLOCKS : (VW == 8 ? 6 : 4))
+assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
+              const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
+              unsigned long long *__restrict__ best, int *__restrict__ gt_img, T *__restrict__ grad) {
+    assign_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img, grad);
+}
+
 // ------------------------------------------------------------------------------------------
 // match_kernel: one warp per GT
 // ------------------------------------------------------------------------------------------
+// Sixteen lanes per GT: lane l of a half-warp holds bin l of all four box sides of the matched anchor.
 struct GtTerms {
-    float g_lo, g_hi;   // gradient of the two logits this lane holds (bins lane%16 of sides lane/16 and 2+lane/16)
+    float g[4];         // gradient of this lane's bin on sides l, t, r, b
     float dfl;          // sum over the four sides of the DFL term (all lanes)
     float iou;          // soft target (all lanes)
     float cell_delta;   // QFL loss change of the (anchor, class) cell per unit of target: q^2 log p - p^2 log q
@@ -274,45 +282,41 @@ struct GtTerms {
     float cell_grad1;
 };
 
+// All 32 lanes of the warp must call this together (full-mask shuffles; xor offsets <= 8 stay in a half).
 template <typename T>
 __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anchors, int idx,
                                             const float *__restrict__ anchors, const float *__restrict__ strides,
                                             const float *__restrict__ g5, float k_dfl, float k_cls, int nc) {
     const int lane = threadIdx.x & 31;
     const int bin = lane & 15;
-    const int half = lane >> 4;
-    const float z_lo = load_as_float(img + (size_t)lane * n_anchors + idx);          // sides 0,1
-    const float z_hi = load_as_float(img + (size_t)(lane + 32) * n_anchors + idx);   // sides 2,3
+    const int base = lane & 16;
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
     const float gcx = __ldg(g5 + 0), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
     int cls = (int)__ldg(g5 + 4);                                                     // .long(): truncation
     cls = min(max(cls, 0), nc - 1);
     const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
     const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
 
-    // softmax over each 16-lane half (xor offsets 8,4,2,1 stay inside a half)
-    float m_lo = z_lo, m_hi = z_hi;
+    // softmax + expectation of each side over the 16 lanes of the half
+    float mx[4], sm[4], pr[4], ds[4];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, o));
-        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, o));
-    }
-    const float e_lo = expf(z_lo - m_lo), e_hi = expf(z_hi - m_hi);
-    float s_lo = e_lo, s_hi = e_hi;
+    for (int k = 0; k < 4; ++k) {
+        float m = z[k];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, o);
-        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
-    }
-    const float p_lo = __fdiv_rn(e_lo, s_lo), p_hi = __fdiv_rn(e_hi, s_hi);
-    float d_lo = p_lo * (float)bin, d_hi = p_hi * (float)bin;
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float e = expf(z[k] - m);
+        float sum = e;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        d_lo += __shfl_xor_sync(0xffffffffu, d_lo, o);
-        d_hi += __shfl_xor_sync(0xffffffffu, d_hi, o);
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float p = __fdiv_rn(e, sum);
+        float d = p * (float)bin;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        mx[k] = m; sm[k] = sum; pr[k] = p; ds[k] = d;
     }
-    const float dl = __shfl_sync(0xffffffffu, d_lo, 0), dt = __shfl_sync(0xffffffffu, d_lo, 16);
-    const float dr = __shfl_sync(0xffffffffu, d_hi, 0), db = __shfl_sync(0xffffffffu, d_hi, 16);
-    const PredBox b = decode_box(ax, ay, s, dl, dt, dr, db);
+    const PredBox b = decode_box(ax, ay, s, ds[0], ds[1], ds[2], ds[3]);
 
     // ---- IoU soft target, reference formula (src/model/losses.py:17-40) and its gradient ------
     const float hw = b.w * 0.5f, hh = b.h * 0.5f;
@@ -360,115 +364,120 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
     // cx = (x1+x2)/2, w = x2-x1 ;  x1 = (ax-dl)*s, x2 = (ax+dr)*s
     const float d_x1 = 0.5f * d_cx - d_w, d_x2 = 0.5f * d_cx + d_w;
     const float d_y1 = 0.5f * d_cy - d_h, d_y2 = 0.5f * d_cy + d_h;
-    const float d_dl = -d_x1 * s, d_dt = -d_y1 * s, d_dr = d_x2 * s, d_db = d_y2 * s;
+    const float dd[4] = {-d_x1 * s, -d_y1 * s, d_x2 * s, d_y2 * s};   // d total / d (dl, dt, dr, db) through the IoU
 
     // ---- DFL target bins (src/model/losses.py:226-246) and loss rows (:63-78) -----------------
-    const float t_l = ax - bx1 / s, t_t = ay - by1 / s, t_r = bx2 / s - ax, t_b = by2 / s - ay;
+    const float tgt[4] = {ax - bx1 / s, ay - by1 / s, bx2 / s - ax, by2 / s - ay};
     const float hi_clamp = (float)(kRegMax - 1 - 0.01);
-    const float t_lo = fminf(fmaxf(half == 0 ? t_l : t_t, 0.f), hi_clamp);   // this lane's side in the low register
-    const float t_hi = fminf(fmaxf(half == 0 ? t_r : t_b, 0.f), hi_clamp);   // ... and in the high register
-    const int bl_lo = (int)t_lo, bl_hi = (int)t_hi;
-    const float wl_lo = (float)(bl_lo + 1) - t_lo, wr_lo = t_lo - (float)bl_lo;
-    const float wl_hi = (float)(bl_hi + 1) - t_hi, wr_hi = t_hi - (float)bl_hi;
-    // log-softmax value of this lane's bin
-    const float lp_lo = (z_lo - m_lo) - logf(s_lo), lp_hi = (z_hi - m_hi) - logf(s_hi);
-    const int base = lane & 16;
-    const float ce_lo = -(__shfl_sync(0xffffffffu, lp_lo, base + bl_lo) * wl_lo +
-                          __shfl_sync(0xffffffffu, lp_lo, base + bl_lo + 1) * wr_lo);
-    const float ce_hi = -(__shfl_sync(0xffffffffu, lp_hi, base + bl_hi) * wl_hi +
-                          __shfl_sync(0xffffffffu, lp_hi, base + bl_hi + 1) * wr_hi);
-    // ce_lo is uniform within a half: lanes 0-15 hold side 0 / 2, lanes 16-31 side 1 / 3
-    const float ce_half = ce_lo + ce_hi;
-
     GtTerms r;
-    r.dfl = ce_half + __shfl_xor_sync(0xffffffffu, ce_half, 16);
+    float dfl = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float t = fminf(fmaxf(tgt[k], 0.f), hi_clamp);
+        const int bl = (int)t;
+        const float wl = (float)(bl + 1) - t, wr = t - (float)bl;
+        const float lpk = (z[k] - mx[k]) - logf(sm[k]);               // log-softmax of this lane's bin
+        dfl -= __shfl_sync(0xffffffffu, lpk, base + bl) * wl + __shfl_sync(0xffffffffu, lpk, base + bl + 1) * wr;
+        const float oh = (bin == bl ? wl : 0.f) + (bin == bl + 1 ? wr : 0.f);
+        r.g[k] = k_dfl * ((wl + wr) * pr[k] - oh) + dd[k] * pr[k] * ((float)bin - ds[k]);
+    }
+    r.dfl = dfl;
     r.iou = iou;
     r.cell_delta = cell_delta;
     r.cell_grad0 = -k_cls * dneg * pc * qc;
     r.cell_grad1 = -k_cls * (dpos - dneg) * pc * qc;
-    const float dd_lo = half == 0 ? d_dl : d_dt, dd_hi = half == 0 ? d_dr : d_db;
-    const float dk_lo = half == 0 ? dl : dt, dk_hi = half == 0 ? dr : db;
-    const float oh_lo = (bin == bl_lo ? wl_lo : 0.f) + (bin == bl_lo + 1 ? wr_lo : 0.f);
-    const float oh_hi = (bin == bl_hi ? wl_hi : 0.f) + (bin == bl_hi + 1 ? wr_hi : 0.f);
-    r.g_lo = k_dfl * ((wl_lo + wr_lo) * p_lo - oh_lo) + dd_lo * p_lo * ((float)bin - dk_lo);
-    r.g_hi = k_dfl * ((wl_hi + wr_hi) * p_hi - oh_hi) + dd_hi * p_hi * ((float)bin - dk_hi);
     return r;
 }
 
 constexpr int kMatchThreads = 128;
 
+// one HALF-warp per GT (8 GTs per CTA)
 template <typename T>
-__global__ void __launch_bounds__(kMatchThreads)
+__global__ void __launch_bounds__(kMatchThreads, 6)
 match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
              const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
-             const int *__restrict__ gt_off, int gt_total, const unsigned long long *__restrict__ best,
-             float k_dfl_num, float k_cls, T *__restrict__ grad, float *__restrict__ m_dfl,
-             float *__restrict__ m_dcls, int *__restrict__ m_win, int *__restrict__ m_anchor,
-             float *__restrict__ m_cellg, int *__restrict__ out_idx, float *__restrict__ out_iou) {
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (kMatchThreads / 32) + (threadIdx.x >> 5);          // one warp per GT
-    if (g >= gt_total) return;
-    {
-        // image of this GT: last n with gt_off[n] <= g
-        int lo = 0, hi = n_images;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(gt_off + mid) <= g) lo = mid; else hi = mid;
-        }
-        const int n = lo;
-        const int g_begin = __ldg(gt_off + n);
-        const int m_img = __ldg(gt_off + n + 1) - g_begin;
-        const int m = g - g_begin;
-        const T *img = preds + (size_t)n * n_ch * n_anchors;
-        auto idx_of = [&](int mm) {
-            const unsigned long long inv = best[g_begin + mm];
-            return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
-        };
-        const int idx = idx_of(m);
-        const float k_dfl = k_dfl_num / (float)m_img;         // lambda_dfl / (N * 4 * M)
+             const int *__restrict__ gt_off, const int *__restrict__ gt_img, int gt_total,
+             const unsigned long long *__restrict__ best, float k_dfl_num, float k_cls, T *__restrict__ grad,
+             float *__restrict__ m_dfl, float *__restrict__ m_dcls, int *__restrict__ m_win, int *__restrict__ out_idx,
+             float *__restrict__ out_iou) {
+    (void)n_images;
+    const int bin = threadIdx.x & 15;
+    const int g_raw = (blockIdx.x * kMatchThreads + threadIdx.x) >> 4;
+    if ((blockIdx.x * kMatchThreads + (threadIdx.x & ~31)) >> 4 >= gt_total) return;      // whole warp past the end
+    const bool live = g_raw < gt_total;                    // the second half of the last warp may be idle
+    const int g = live ? g_raw : gt_total - 1;             // ... but must walk through the same shuffles
+    const int n = __ldg(gt_img + g);
+    const int g_begin = __ldg(gt_off + n);
+    const int m_img = __ldg(gt_off + n + 1) - g_begin;
+    const int m = g - g_begin;
+    const T *img = preds + (size_t)n * n_ch * n_anchors;
+    auto idx_of = [&](int mm) {
+        const unsigned long long inv = best[g_begin + mm];
+        return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
+    };
+    const int idx = idx_of(m);
+    const float k_dfl = k_dfl_num / (float)m_img;          // lambda_dfl / (N * 4 * M)
 
-        // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
-        // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
-        int first = m, last = m;
-        for (int mm = lane; mm < m_img; mm += 32) {
-            if (idx_of(mm) == idx) { first = min(first, mm); last = max(last, mm); }
+    // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
+    // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
+    int first = m, last = m, n_later = 0;
+    for (int mm = bin; mm < m_img; mm += 16) {
+        if (idx_of(mm) == idx) {
+            first = min(first, mm);
+            last = max(last, mm);
+            n_later += mm > m ? 1 : 0;
         }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-        }
+    for (int o = 8; o > 0; o >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        n_later += __shfl_xor_sync(0xffffffffu, n_later, o);
+    }
 
-        const GtTerms mine = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)g * 5, k_dfl, k_cls, nc);
-        const bool winner = (last == m);
-        if (lane == 0) {
-            m_dfl[g] = mine.dfl;
-            m_dcls[g] = winner ? mine.iou * mine.cell_delta : 0.f;
-            m_win[g] = winner ? 1 : 0;
-            m_anchor[g] = idx;
-            // the anchor's one positive QFL cell: finalize_kernel overwrites the target-0 gradient that
-            // cls_loss_kernel (which may run concurrently with this kernel) writes there
-            m_cellg[g] = mine.cell_grad0 + mine.iou * mine.cell_grad1;
-            if (out_idx) out_idx[g] = idx;
-            if (out_iou) out_iou[g] = mine.iou;
+    const GtTerms mine = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)g * 5, k_dfl, k_cls, nc);
+    const bool winner = (last == m);
+    T *gimg = grad ? grad + (size_t)n * n_ch * n_anchors : nullptr;
+    if (live && bin == 0) {
+        m_dfl[g] = mine.dfl;
+        m_dcls[g] = winner ? mine.iou * mine.cell_delta : 0.f;
+        m_win[g] = winner ? 1 : 0;
+        if (out_idx) out_idx[g] = idx;
+        if (out_iou) out_iou[g] = mine.iou;
+        if (winner && gimg) {
+            // the anchor's one positive QFL cell: overwrite the target-0 gradient the class pass wrote
+            int cls = (int)__ldg(gt + (size_t)g * 5 + 4);
+            cls = min(max(cls, 0), nc - 1);
+            store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
+                             mine.cell_grad0 + mine.iou * mine.cell_grad1);
         }
-        if (grad != nullptr) {
-            T *gimg = grad + (size_t)n * n_ch * n_anchors;
-            if (first == m) {
-                float g_lo = mine.g_lo, g_hi = mine.g_hi;
-                if (last != m) {
-                    for (int mm = m + 1; mm <= last; ++mm) {           // warp-uniform loop
-                        if (idx_of(mm) != idx) continue;
-                        const GtTerms o = gt_terms(img, n_anchors, idx, anchors, strides,
-                                                   gt + (size_t)(g_begin + mm) * 5, k_dfl, k_cls, nc);
-                        g_lo += o.g_lo;
-                        g_hi += o.g_hi;
-                    }
-                }
-                store_from_float(gimg + (size_t)lane * n_anchors + idx, g_lo);
-                store_from_float(gimg + (size_t)(lane + 32) * n_anchors + idx, g_hi);
-            }
+    }
+    // the owner adds the terms of the later GTs that share its anchor (rare); the trip count is made
+    // warp-uniform because gt_terms shuffles across the whole warp
+    float acc[4] = {mine.g[0], mine.g[1], mine.g[2], mine.g[3]};
+    const bool owner = live && first == m && gimg != nullptr;
+    int todo = owner ? n_later : 0;
+    const int trips = max(todo, __shfl_xor_sync(0xffffffffu, todo, 16));
+    int cur = m;
+    for (int it = 0; it < trips; ++it) {
+        int nxt = 0x7fffffff;
+        if (it < todo)
+            for (int mm = bin; mm < m_img; mm += 16)
+                if (mm > cur && idx_of(mm) == idx) nxt = min(nxt, mm);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+        const bool has = nxt != 0x7fffffff;
+        const GtTerms o = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)(g_begin + (has ? nxt : m)) * 5, k_dfl,
+                                   k_cls, nc);
+        if (has) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += o.g[k];
+            cur = nxt;
         }
+    }
+    if (owner) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) store_from_float(gimg + (size_t)(k * kRegMax + bin) * n_anchors + idx, acc[k]);
     }
 }
 
@@ -484,14 +493,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-template <typename T>
 __global__ void __launch_bounds__(kFinThreads)
-finalize_kernel(int n_images, int n_ch, int nc, int n_anchors, int cls_tiles, const int *__restrict__ gt_off,
-                const float *__restrict__ gt, const float *__restrict__ part, const float *__restrict__ m_dfl,
-                const float *__restrict__ m_dcls, const int *__restrict__ m_win, const int *__restrict__ m_anchor,
-                const float *__restrict__ m_cellg, T *__restrict__ grad, float lambda_cls, float lambda_dfl,
-                float *__restrict__ img_terms, unsigned int *__restrict__ ticket, float *__restrict__ out_loss,
-                float *__restrict__ out_per_image) {
+finalize_kernel(int n_images, int n_anchors, int cls_tiles, const int *__restrict__ gt_off,
+                const float *__restrict__ part, const float *__restrict__ m_dfl, const float *__restrict__ m_dcls,
+                const int *__restrict__ m_win, float lambda_cls, float lambda_dfl, float *__restrict__ img_terms,
+                unsigned int *__restrict__ ticket, float *__restrict__ out_loss, float *__restrict__ out_per_image) {
     __shared__ bool s_last;
     __shared__ double s_d[kFinThreads / 32], s_c[kFinThreads / 32], s_f[kFinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -503,14 +509,7 @@ finalize_kernel(int n_images, int n_ch, int nc, int n_anchors, int cls_tiles, co
         for (int m = lane; m < mb; m += 32) {
             d_img += (double)__ldcg(m_dfl + gb + m);
             c_img += (double)__ldcg(m_dcls + gb + m);
-            const int win = __ldcg(m_win + gb + m);
-            f_img += (double)win;
-            if (win && grad != nullptr) {                  // the positive cell of a matched anchor
-                int cls = (int)__ldg(gt + (size_t)(gb + m) * 5 + 4);
-                cls = min(max(cls, 0), nc - 1);
-                store_from_float(grad + ((size_t)b * n_ch + 4 * kRegMax + cls) * n_anchors + __ldcg(m_anchor + gb + m),
-                                 __ldcg(m_cellg + gb + m));
-            }
+            f_img += (double)__ldcg(m_win + gb + m);
         }
         c_img = warp_sum_d(c_img);
         d_img = warp_sum_d(d_img);
@@ -642,16 +641,15 @@ __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cl
     }
 }
 
+// the class channels of a tile are split over n_split CTAs: short-lived CTAs, small tail
 template <typename T, int VW, bool WRITE_GRAD>
-__global__ void __launch_bounds__(kClsThreads, YB_CLS_MINBLOCKS)
-cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
-                float *__restrict__ part) {
+__device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split, int n_split, const T *__restrict__ preds,
+                                         int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
+                                         float *__restrict__ part) {
     __shared__ float s_red[kClsThreads / 32];
-    const int n = blockIdx.y;
-    const int a0 = (blockIdx.x * kClsThreads + threadIdx.x) * VW;
-    // the class channels of a tile are split over gridDim.z CTAs: short-lived CTAs, small tail
-    const int c_per = (nc + gridDim.z - 1) / gridDim.z;
-    const int c_lo = blockIdx.z * c_per;
+    const int a0 = (tile * kClsThreads + threadIdx.x) * VW;
+    const int c_per = (nc + n_split - 1) / n_split;
+    const int c_lo = split * c_per;
     nc = min(nc, c_lo + c_per) - c_lo;
     f32x2 acc2 = pack2(0.f, 0.f);
     float fix = 0.f;
@@ -690,8 +688,39 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kClsThreads / 32; ++w) s += s_red[w];
-        part[((size_t)n * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x] = s;
+        part[((size_t)n * n_split + split) * n_tiles + tile] = s;
     }
+}
+
+template <typename T, int VW, bool WRITE_GRAD>
+__global__ void __launch_bounds__(kClsThreads, YB_CLS_MINBLOCKS)
+cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
+                float *__restrict__ part) {
+    cls_body<T, VW, WRITE_GRAD>(blockIdx.y, blockIdx.x, gridDim.x, blockIdx.z, gridDim.z, preds, n_ch, n_anchors, nc, k_cls,
+                                grad, part);
+}
+
+// One launch for both big passes: CTAs alternate between the box role (assign_body) and the class role
+// (cls_body, YB_CLS_CSPLIT CTAs per tile), so every SM holds a mix of the latency-bound decode/scan
+// CTAs and the streaming class CTAs and the two underused halves of the machine fill each other.
+#ifndef YB_FUSED_MINBLOCKS           // measured on B200: 6 resident CTAs/SM is best for fp32 rows, 5 for bf16 rows
+#define YB_FUSED_MINBLOCKS 0
+#endif
+template <typename T, int VW, bool WRITE_GRAD>
+__global__ void __launch_bounds__(kAssignThreads, YB_FUSED_MINBLOCKS ? YB_FUSED_MINBLOCKS : (VW == 8 ? 5 : 6))
+fused_main_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, int n_tiles, const float *__restrict__ anchors,
+                  const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
+                  unsigned long long *__restrict__ best, int *__restrict__ gt_img, float k_cls, T *__restrict__ grad,
+                  float *__restrict__ part) {
+    static_assert(kAssignThreads == kClsThreads, "roles share one block shape");
+    constexpr int ROLES = 1 + YB_CLS_CSPLIT;
+    const int tile = blockIdx.x / ROLES, role = blockIdx.x % ROLES;
+    if (role == 0)
+        assign_body<T, VW>(blockIdx.y, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
+                           WRITE_GRAD ? grad : nullptr);
+    else
+        cls_body<T, VW, WRITE_GRAD>(blockIdx.y, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
+                                    part);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -727,42 +756,17 @@ static int stage_mark(int i, cudaStream_t st) {
     return YB_OK;
 }
 
-// The class pass does not depend on the matching, so it runs on a side stream while
-// assign -> match run on the caller's stream; finalize joins both.  One side stream + two events per
-// device, created on first use (fork/join through events is also legal inside CUDA-graph capture).
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-static SideStream g_side[64];
-
-// YB_OVERLAP (environment, read once): 0 = one stream, 1 = class pass on a side stream (default),
-// 2 = side stream at the lowest priority, 3 = like 1 but the class pass is launched before assign
-static int overlap_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char *e = getenv("YB_OVERLAP");
-        mode = e ? atoi(e) : 1;
+// YB_LAYOUT (environment, read once): "fused" (default) = assign + class pass in ONE launch
+// (fused_main_kernel), "split" = two launches (assign_kernel, cls_loss_kernel) — kept for profiling the
+// two roles separately.  Stream-level overlap of the two big kernels was measured and does not help:
+// the first kernel's CTAs fill every SM, so the second only starts as the first drains.
+static bool fused_layout() {
+    static int fused = -1;
+    if (fused < 0) {
+        const char *e = getenv("YB_LAYOUT");
+        fused = (e && e[0] == 's') ? 0 : 1;
     }
-    return mode;
-}
-
-static int side_for_current_device(SideStream **out) {
-    int dev = 0;
-    YB_CUDA(cudaGetDevice(&dev));
-    YB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
-    SideStream &sd = g_side[dev];
-    if (sd.stream == nullptr) {
-        // lowest priority: when both streams have CTAs pending, the short latency-bound kernels of the
-        // caller's stream (match, finalize) are dispatched first and hide under the class pass
-        int prio_lo = 0, prio_hi = 0;
-        YB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        YB_CUDA(cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, overlap_mode() == 2 ? prio_lo : prio_hi));
-        YB_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
-        YB_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
-    }
-    *out = &sd;
-    return YB_OK;
+    return fused != 0;
 }
 
 template <typename T, int VW>
@@ -775,56 +779,47 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
     const float k_dfl_num = lambda_dfl / ((float)n_images * 4.f);
     constexpr int TILE_A = kAssignThreads * VW, TILE_C = kClsThreads * VW;
+    static_assert(TILE_A == TILE_C, "both roles tile the anchors identically");
     const int cls_split = YB_CLS_CSPLIT;
-    const int cls_tiles = ((n_anchors + TILE_C - 1) / TILE_C) * cls_split;     // partial sums per image
-    // stage timing serialises the kernels on one stream so that each can be bracketed by events
-    const bool overlap = !g_stage_timing && gt_total > 0 && overlap_mode() != 0;
-    SideStream *sd = nullptr;
-    cudaStream_t st_cls = st;
-    if (overlap) {
-        if (int rc = side_for_current_device(&sd)) return rc;
-        st_cls = sd->stream;
-        YB_CUDA(cudaEventRecord(sd->fork, st));            // everything the caller queued (preds ready, buffers free)
-        YB_CUDA(cudaStreamWaitEvent(st_cls, sd->fork, 0));
-    }
+    const int n_tiles = (n_anchors + TILE_C - 1) / TILE_C;
+    const int cls_tiles = n_tiles * cls_split;                                  // partial sums per image
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(0, st)) return rc;
-    auto launch_assign = [&]() -> int {
-        dim3 grid((n_anchors + TILE_A - 1) / TILE_A, n_images);
-        assign_kernel<T, VW><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
-                                                              w.best, grad);
-        YB_CUDA(cudaGetLastError());
-        return YB_OK;
-    };
-    const bool cls_first = overlap && overlap_mode() == 3;
-    if (!cls_first)
-        if (int rc = launch_assign()) return rc;
-    if (int rc = stage_mark(1, st)) return rc;
-    {
-        dim3 grid(cls_tiles / cls_split, n_images, cls_split);
+    if (fused_layout()) {
+        dim3 grid(n_tiles * (1 + cls_split), n_images);
         if (grad != nullptr)
-            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st_cls>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+            fused_main_kernel<T, VW, true><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, nc, n_tiles, anchors, strides,
+                                                                            gt, gt_off, w.best, w.gt_img, k_cls, grad, w.part);
         else
-            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st_cls>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+            fused_main_kernel<T, VW, false><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, nc, n_tiles, anchors,
+                                                                             strides, gt, gt_off, w.best, w.gt_img, k_cls, grad,
+                                                                             w.part);
         YB_CUDA(cudaGetLastError());
-        if (overlap) YB_CUDA(cudaEventRecord(sd->join, st_cls));
+    } else {
+        assign_kernel<T, VW><<<dim3(n_tiles, n_images), kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt,
+                                                                                 gt_off, w.best, w.gt_img, grad);
+        YB_CUDA(cudaGetLastError());
+        dim3 grid(n_tiles, n_images, cls_split);
+        if (grad != nullptr)
+            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+        else
+            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+        YB_CUDA(cudaGetLastError());
     }
-    if (cls_first)
-        if (int rc = launch_assign()) return rc;
-    if (int rc = stage_mark(2, st)) return rc;
+    if (int rc = stage_mark(1, st)) return rc;
     if (gt_total > 0) {
-        const int warps = kMatchThreads / 32;
-        match_kernel<T><<<(gt_total + warps - 1) / warps, kMatchThreads, 0, st>>>(
-            preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, gt_total, w.best, k_dfl_num, k_cls, grad,
-            w.m_dfl, w.m_dcls, w.m_idx, w.m_cls, w.m_cellg, out_idx, out_iou);
+        const int per_cta = kMatchThreads / 16;                                  // one half-warp per GT
+        match_kernel<T><<<(gt_total + per_cta - 1) / per_cta, kMatchThreads, 0, st>>>(
+            preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.gt_img, gt_total, w.best, k_dfl_num, k_cls,
+            grad, w.m_dfl, w.m_dcls, w.m_idx, out_idx, out_iou);
         YB_CUDA(cudaGetLastError());
     }
-    if (overlap) YB_CUDA(cudaStreamWaitEvent(st, sd->join, 0));      // join: the class pass has written its gradients
+    if (int rc = stage_mark(2, st)) return rc;
     {
         const int warps = kFinThreads / 32;
-        finalize_kernel<T><<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
-            n_images, n_ch, nc, n_anchors, cls_tiles, gt_off, gt, w.part, w.m_dfl, w.m_dcls, w.m_idx, w.m_cls, w.m_cellg, grad,
-            lambda_cls, lambda_dfl, w.img_terms, w.ticket, out_loss, out_per_image);
+        finalize_kernel<<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
+            n_images, n_anchors, cls_tiles, gt_off, w.part, w.m_dfl, w.m_dcls, w.m_idx, lambda_cls, lambda_dfl, w.img_terms,
+            w.ticket, out_loss, out_per_image);
         YB_CUDA(cudaGetLastError());
     }
     if (int rc = stage_mark(3, st)) return rc;
