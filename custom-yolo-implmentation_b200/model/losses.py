@@ -22,8 +22,8 @@ import torch.nn as nn
 
 from .. import _cabi
 
-__all__ = ["YoloDFLQFLoss", "bbox_iou", "quality_focal_loss", "distribution_focal_loss", "pack_gt", "fused_loss",
-           "fused_tal_loss"]
+__all__ = ["YoloDFLQFLoss", "bbox_iou", "quality_focal_loss", "distribution_focal_loss", "pack_gt", "pack_gt_host",
+           "PackedGT", "fused_loss", "fused_tal_loss"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -57,6 +57,45 @@ def pack_gt(gt_boxes_list: Sequence[torch.Tensor], device) -> Tuple[torch.Tensor
         gt = torch.zeros(0, 5, dtype=torch.float32, device=device)
     off = torch.tensor(offsets, dtype=torch.int32).to(device, non_blocking=True)
     return gt, off, counts
+
+
+class PackedGT:
+    """The GT wire format of the kernels: ``gt (sum Mi, 5)`` fp32, ``offsets (N+1,)`` int32, per-image counts.
+    ``YoloDFLQFLoss.forward`` accepts it in place of the per-image list (one pinned
+    staging buffer and ONE host-to-device copy per batch instead of N small ones)."""
+
+    __slots__ = ("gt", "offsets", "counts")
+
+    def __init__(self, gt, offsets, counts):
+        self.gt, self.offsets, self.counts = gt, offsets, list(counts)
+
+    def __len__(self):
+        return len(self.counts)
+
+    def to(self, device, non_blocking=True):
+        return PackedGT(self.gt.to(device, non_blocking=non_blocking), self.offsets.to(device, non_blocking=non_blocking),
+                        self.counts)
+
+
+def pack_gt_host(gt_boxes_list: Sequence[torch.Tensor], pin_memory: bool = True) -> PackedGT:
+    """Collate-side packing: CPU ``list[(Mi, 5)]`` -> one (pinned) ``(sum Mi, 5)`` buffer + offsets.
+    Use in a ``collate_fn`` and move the result with ``.to(device)``: two async copies per batch,
+    independent of the batch size (the reference does N copies, src/training/train_model.py:236)."""
+    counts = [0 if (g is None or g.numel() == 0) else int(g.shape[0]) for g in gt_boxes_list]
+    total = sum(counts)
+    gt = torch.empty(total, 5, dtype=torch.float32)
+    off = torch.zeros(len(counts) + 1, dtype=torch.int32)
+    pos = 0
+    for i, (g, c) in enumerate(zip(gt_boxes_list, counts)):
+        if c:
+            if g.dim() != 2 or g.shape[1] < 5:
+                raise ValueError(f"gt_boxes_list[{i}] must have shape (Mi, 5), got {tuple(g.shape)}")
+            gt[pos:pos + c] = g[:, :5].to(torch.float32)
+        pos += c
+        off[i + 1] = pos
+    if pin_memory and torch.cuda.is_available():
+        gt, off = gt.pin_memory(), off.pin_memory()
+    return PackedGT(gt, off, counts)
 
 
 def _workspace(n_bytes: int, device) -> torch.Tensor:
@@ -270,7 +309,11 @@ class YoloDFLQFLoss(nn.Module):
         n = preds.shape[0]
         if len(gt_boxes_list) != n:
             raise IndexError(f"gt_boxes_list has {len(gt_boxes_list)} entries for a batch of {n}")
-        gt, off, counts = pack_gt(gt_boxes_list, preds.device)
+        if isinstance(gt_boxes_list, PackedGT):
+            packed = gt_boxes_list if gt_boxes_list.gt.device == preds.device else gt_boxes_list.to(preds.device)
+            gt, off, counts = packed.gt, packed.offsets, packed.counts
+        else:
+            gt, off, counts = pack_gt(gt_boxes_list, preds.device)
         if self.assigner == "tal":
             # not in the reference: task-aligned assigner + CIoU / DFL / BCE, here lambda_box IS used
             need_grad = torch.is_grad_enabled() and preds.requires_grad

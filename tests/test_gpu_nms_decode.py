@@ -198,3 +198,30 @@ def test_helper_gradients_match_oracle_autograd(cuda_device):
     gd = torch.from_numpy(z["dist"]).to(dev).requires_grad_(True)
     PL.distribution_focal_loss(gd, torch.from_numpy(z["tval"]).to(dev)).backward()
     assert torch.allclose(gd.grad.cpu(), d.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_packed_gt_and_inference_postprocess(cuda_device):
+    """§8(f).3/.4: the packed GT wire format gives the same loss; fused inference post-processing equals the
+    reference's sequence DFL -> dist2bbox -> *stride -> cat -> NMS (golden decode fixture + NMS oracle)."""
+    from custom_yolo_implmentation_b200.model.losses import YoloDFLQFLoss, pack_gt_host
+    from custom_yolo_implmentation_b200.utils.postprocess import postprocess_inference
+    dev = cuda_device
+    preds, gts, anchors, strides = syn.make_loss_inputs(3, 6, 128, 10, 101)
+    crit = YoloDFLQFLoss(num_classes=6)
+    l1, d1 = crit(preds.to(dev), [g.to(dev) for g in gts], anchors.to(dev), strides.to(dev))
+    l2, d2 = crit(preds.to(dev), pack_gt_host(gts).to(dev), anchors.to(dev), strides.to(dev))
+    assert d1 == d2 and torch.equal(l1, l2)
+    z = load_golden("decode_topk")
+    x = torch.from_numpy(z["preds"]).to(dev)
+    anc, st = torch.from_numpy(z["anchors"]).to(dev), torch.from_numpy(z["strides"]).to(dev)
+    out = postprocess_inference(x, anc, st, 6, conf_thres=0.25, iou_thres=0.45, apply_sigmoid=True)
+    # the decode itself is pinned to the reference above (test_decode_matches_reference_golden); here the NMS oracle
+    # runs on the SAME decoded boxes so that a 1e-6 difference cannot flip an IoU decision
+    _, box = dfl_decode(x, anc, st, want_ltrb=False, box_format="xywh")
+    assert torch.allclose(box.cpu(), torch.from_numpy(z["box_xywh"]), rtol=1e-5, atol=1e-4)
+    y = torch.cat((box.cpu(), torch.from_numpy(z["preds"])[:, 64:].sigmoid()), 1)
+    ora = N.nms_forward(y, 0.25, 0.45, max_det=300, nc=6)
+    for b in range(x.shape[0]):
+        assert out[b].shape == ora.rows[b].shape and out[b].shape[0] > 0
+        assert torch.equal(out[b][:, 5].cpu(), ora.rows[b][:, 5])
+        assert torch.allclose(out[b].cpu(), ora.rows[b], rtol=1e-6, atol=1e-6)

@@ -114,3 +114,16 @@ def test_synthetic_generators_are_seeded_and_shaped():
 def test_shard_batch():
     assert [DS.shard_batch(1024, r, 8) for r in (0, 7)] == [(0, 128), (896, 1024)]
     assert DS.reduce_value(3.5) == 3.5                  # not distributed: identity
+
+
+def test_packed_gt_host_and_collate():
+    from custom_yolo_implmentation_b200.data.collate import collate_fn, collate_fn_packed
+    gts = [torch.arange(10.).view(2, 5), torch.zeros(0, 5), torch.ones(3, 5)]
+    pk = P.pack_gt_host(gts, pin_memory=False)
+    assert len(pk) == 3 and pk.counts == [2, 0, 3] and pk.offsets.tolist() == [0, 2, 2, 5] and pk.gt.shape == (5, 5)
+    assert torch.equal(pk.gt[2:], torch.ones(3, 5))
+    batch = [(torch.zeros(3, 4, 4), {"boxes": g}) for g in gts]
+    images, targets, packed = collate_fn_packed(batch)
+    assert images.shape == (3, 3, 4, 4) and len(targets) == 3 and packed.counts == [2, 0, 3]
+    images2, targets2 = collate_fn(batch)
+    assert torch.equal(images, images2) and targets2[2]["boxes"] is gts[2]
