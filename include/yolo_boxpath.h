@@ -76,8 +76,8 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* Measurement aid: when enabled, yb_loss_fwd_bwd records CUDA events on its stream around each of its
- * three kernels (assign, match, cls_loss); yb_loss_last_stage_ms waits for the last timed call and
- * returns the three durations in milliseconds (host array of 3).  Off by default. */
+ * three launches (fused main pass, match, finalize); yb_loss_last_stage_ms waits for the last timed
+ * call and returns the three durations in milliseconds (host array of 3).  Off by default. */
 int yb_stage_timing(int enable);
 int yb_loss_last_stage_ms(float *out_ms_host);
 
