@@ -51,14 +51,17 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons of one GPU, sampled in-process through NVML (initialised before the
-    timed region; a fork of nvidia-smi inside it would stall the launching thread)."""
+    """SM clock / throttle reasons of one GPU through NVML, in-process.
+
+    NVML queries take the driver lock for milliseconds and stall kernel launches, so nothing is
+    sampled while the timed loop is ENQUEUEING; the samples are taken right after the last launch of
+    the timed region, while the GPU is still draining the queued steps (i.e. under load, inside the
+    timed region, before the closing synchronize)."""
 
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index, period=0.1):
-        self.rows, self._stop, self._t, self.period = [], threading.Event(), None, period
-        self.h = self.mx = None
+    def __init__(self, index):
+        self.rows, self.h, self.mx, self.sample_ms = [], None, None, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -70,34 +73,26 @@ class ClockSampler:
         except Exception:
             self.h = None
 
-    def sample(self):
+    def sample(self, n=1, gap=0.002):
         if self.h is None:
             return
-        try:
-            sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
-            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            self.rows.append((float(sm), [n for n, b in zip(self.NAMES, self.bits) if r & b]))
-        except Exception:
-            pass
-
-    def _run(self):
-        while not self._stop.is_set():
-            self.sample()
-            self._stop.wait(self.period)
-
-    def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=2)
+        for i in range(n):
+            t0 = time.perf_counter()
+            try:
+                sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(sm), [nm for nm, b in zip(self.NAMES, self.bits) if r & b]))
+            except Exception:
+                pass
+            self.sample_ms.append((time.perf_counter() - t0) * 1e3)
+            if i + 1 < n:
+                time.sleep(gap)
 
     def summary(self):
         sm = [r[0] for r in self.rows]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.mx) if self.mx else None,
-                "reasons": sorted({n for r in self.rows for n in r[1]}), "samples": len(sm)}
+                "reasons": sorted({n for r in self.rows for n in r[1]}), "samples": len(sm),
+                "nvml_ms_per_sample": round(statistics.mean(self.sample_ms), 3) if self.sample_ms else None}
 
 
 def dist_env():
@@ -187,13 +182,13 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(max(args.warmup, 3)):             # results bound exactly as in the timed loop, so the caching
+        out, grad = step()                           # allocator already owns both 619 MB gradient blocks
     barrier()
     launches0 = _cabi.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
-    with sampler as clocks:
+    clocks = ClockSampler(local)
+    if True:
         barrier()
         ev0.record()
         for _ in range(args.steps):
@@ -204,7 +199,7 @@ def run_ours(args):
             # loss statistics are reduced once per run — one 8-float message, inside the timed region
             reduced = reduce_loss_stats(out, n)
         ev1.record()
-        clocks.sample()                      # the queue is still draining: a sample under load
+        clocks.sample(3)                     # the GPU is still draining the queued steps: samples under load
         barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = _cabi.launch_count - launches0
@@ -259,7 +254,7 @@ def run_ours(args):
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        e2e_step()
+        parts = e2e_step()
     barrier()
     ev0.record()
     for _ in range(e2e_steps):
@@ -278,7 +273,7 @@ def run_ours(args):
     if rank == 0 or world > 1:
         y = syn.make_nms_input(64, nc, imgsz, 2024 + rank).to(dev)
         for _ in range(3):
-            batched_nms_raw(y, 0.001, 0.7, 300, nc)
+            rows, cnt, _ = batched_nms_raw(y, 0.001, 0.7, 300, nc)
         barrier()
         ev0.record()
         nms_steps = max(5, min(args.steps, 20))
@@ -299,11 +294,11 @@ def run_ours(args):
     # ---- extra lines (not the headline): the task-aligned variant and the dense bf16 config ----
     def time_steps(fn, k):
         for _ in range(3):
-            fn()
+            keep = fn()
         barrier()
         ev0.record()
         for _ in range(k):
-            fn()
+            keep = fn()
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1) / k
@@ -358,7 +353,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
