@@ -230,3 +230,30 @@ def test_host_entry_point_matches_device_entry_point(cuda_device):
                                   _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_loss_fwd_bwd_host")
     assert torch.equal(loss_host[:4], out[:4]) and torch.equal(grad_host, grad)
+
+
+def test_fused_loss_is_cuda_graph_capturable(cuda_device):
+    """No host sync, no hidden allocation inside the ABI call: the step can be captured and replayed."""
+    dev = cuda_device
+    preds, gts, anchors, strides = syn.make_loss_inputs(4, 80, 640, 50, 321)
+    x = preds.to(dev)
+    gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
+    a, s = anchors.to(dev), strides.to(dev)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            ref_out, ref_grad, _ = P.fused_loss(x, gt, off, max(counts), a, s, 80, 1.0, 1.5)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            out, grad, _ = P.fused_loss(x, gt, off, max(counts), a, s, 80, 1.0, 1.5)
+    torch.cuda.synchronize()
+    out.zero_(); grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out) and torch.equal(grad, ref_grad)
+    x.add_(0.25)                                           # new head output in the captured buffer
+    graph.replay()
+    torch.cuda.synchronize()
+    chk_out, chk_grad, _ = P.fused_loss(x, gt, off, max(counts), a, s, 80, 1.0, 1.5)
+    assert torch.equal(out, chk_out) and torch.equal(grad, chk_grad)
