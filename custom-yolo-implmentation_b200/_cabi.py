@@ -44,6 +44,8 @@ _SIGNATURES = {
     "yb_dfl_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_void_p]),
     "yb_make_anchors": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "yb_head_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "yb_head_scatter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "yb_dist2bbox": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "yb_val_decode_workspace_bytes": (c_size_t, [c_int, c_int]),
     "yb_val_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,

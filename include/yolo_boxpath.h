@@ -146,6 +146,19 @@ int yb_dfl_decode(const void *box_logits, int dtype, int n_images, int reg_max, 
 int yb_make_anchors(const int32_t *shapes_host, const float *strides_host, int n_levels, float *out_grid,
                     float *out_strides, void *stream);
 
+/* Tail of Head.forward (src/model/head.py:86-121): `cat((box_l, cls_l), 1)` per level, flatten H x W,
+ * `cat(..., 2)` over the levels -- one launch, each element moved once (the reference moves it twice).
+ *   box_levels / cls_levels   HOST arrays of n_levels DEVICE pointers: (N, box_ch, H_l*W_l) / (N, nc, H_l*W_l),
+ *                             contiguous, dtype YB_F32 or YB_BF16 (the outputs of the last 1x1 convs, head.py:52, :60)
+ *   hw_host                   n_levels int32 on the HOST: H_l * W_l          (n_levels <= 8)
+ *   out                       (N, box_ch + nc, sum H_l*W_l)
+ * yb_head_scatter is the adjoint (the backward of the two cats): grad (N, C, A) -> the 2 * n_levels
+ * contiguous conv-output gradients. */
+int yb_head_gather(const void *const *box_levels, const void *const *cls_levels, const int32_t *hw_host, int n_levels,
+                   int dtype, int n_images, int box_ch, int nc, void *out, void *stream);
+int yb_head_scatter(const void *grad, const int32_t *hw_host, int n_levels, int dtype, int n_images, int box_ch, int nc,
+                    void *const *box_grads, void *const *cls_grads, void *stream);
+
 /* ltrb (N, 4, A) fp32 + anchors (2, A) -> box (N, 4, A); dist2bbox with dim=1. */
 int yb_dist2bbox(const float *ltrb, const float *anchors, int n_images, int n_anchors, int xywh, float *out_box,
                  void *stream);

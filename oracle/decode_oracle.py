@@ -31,6 +31,14 @@ def make_anchor_grid(shapes: Sequence[Tuple[int, int]], strides: Sequence[float]
     return torch.cat(pts), torch.cat(sts)
 
 
+def head_tail(box_outs: Sequence[torch.Tensor], cls_outs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Tail of Head.forward: per level ``cat((box, cls), 1)`` (src/model/head.py:86-87), then
+    ``cat([i.view(N, no, -1) for i in x], 2)`` (:119).  Returns (N, box_ch + nc, sum H*W)."""
+    n = box_outs[0].shape[0]
+    levels = [torch.cat((b, c), dim=1) for b, c in zip(box_outs, cls_outs)]
+    return torch.cat([lv.reshape(n, lv.shape[1], -1) for lv in levels], dim=2)
+
+
 def dfl_expectation(box_logits: torch.Tensor, reg_max: int = 16) -> torch.Tensor:
     """(b, 4R, a) -> (b, 4, a) expected bin per side, computed in the input dtype."""
     b, _, a = box_logits.shape

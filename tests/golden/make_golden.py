@@ -14,6 +14,7 @@ What is called, unmodified, from /root/reference:
   src.model.model_blocks.DFL
   src.training.train_model.decode_predictions
   src.training.metrics.box_iou_batch
+  src.model.head.Head  (forward; the six conv-tower outputs it concatenates are captured with hooks)
 The only intervention is freezing ``src.utils.model_utils.time`` so the reference's wall-clock
 NMS abort (model_utils.py:212, :275-277) cannot drop images on a slow machine.  The matched
 anchor indices, which the reference computes but does not return, are recovered by re-running
@@ -47,6 +48,7 @@ import src.utils.model_utils as ref_utils        # noqa: E402
 import src.model.model_blocks as ref_blocks      # noqa: E402
 import src.training.train_model as ref_train     # noqa: E402
 import src.training.metrics as ref_metrics       # noqa: E402
+import src.model.head as ref_head                # noqa: E402
 
 ref_utils.time = types.SimpleNamespace(time=lambda: 0.0)     # freeze the NMS abort clock (Q8)
 
@@ -227,6 +229,29 @@ def helper_case(name, seed):
     print(f"{name}: helpers written")
 
 
+def head_case(name, seed, n, nc, shapes, dtype=torch.float32):
+    """Head.forward of the reference (head.py:77-121) on random feature maps; the outputs of its box / cls
+    towers (what the tail concatenates) are captured with forward hooks."""
+    torch.manual_seed(seed)
+    filters = [8, 16, 32][: len(shapes)]
+    head = ref_head.Head(nc=nc, filters=filters).eval()
+    head.stride = torch.tensor([8.0, 16.0, 32.0][: len(shapes)])
+    cap = {}
+    for i in range(len(shapes)):
+        head.box[i].register_forward_hook(lambda m, a, out, i=i: cap.__setitem__(("box", i), out.detach().clone()))
+        head.cls[i].register_forward_hook(lambda m, a, out, i=i: cap.__setitem__(("cls", i), out.detach().clone()))
+    feats = [torch.randn(n, f, h, w) for f, (h, w) in zip(filters, shapes)]
+    with torch.no_grad():
+        x, anchors, strides = head(list(feats))
+    d = {"x": x.to(dtype).float().numpy(), "anchors": anchors.numpy(), "strides": strides.numpy(),
+         "meta": np.array([n, nc, len(shapes)], np.int64), "shapes": np.array(shapes, np.int64)}
+    for i in range(len(shapes)):
+        d[f"box{i}"] = cap[("box", i)].to(dtype).float().numpy()
+        d[f"cls{i}"] = cap[("cls", i)].to(dtype).float().numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(f"{name}: x {tuple(x.shape)}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)         # fixed reduction order for the stored reference sums
     loss_case("loss_small_fp32", 3, 6, 128, 10, 101)
@@ -244,3 +269,5 @@ if __name__ == "__main__":
     helper_case("helpers", 31)
     metrics_case("metrics_a", 41, 12, 5, 0.5)
     metrics_case("metrics_b", 42, 9, 3, 0.3)
+    head_case("head_aligned", 51, 2, 5, [(8, 8), (4, 4), (2, 4)])
+    head_case("head_ragged", 52, 3, 3, [(7, 5), (3, 3), (2, 1)])

@@ -225,3 +225,53 @@ def test_packed_gt_and_inference_postprocess(cuda_device):
         assert out[b].shape == ora.rows[b].shape and out[b].shape[0] > 0
         assert torch.equal(out[b][:, 5].cpu(), ora.rows[b][:, 5])
         assert torch.allclose(out[b].cpu(), ora.rows[b], rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ head tail
+@pytest.mark.parametrize("name", ["head_aligned", "head_ragged"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_head_tail_matches_reference_golden(name, dtype, cuda_device):
+    from custom_yolo_implmentation_b200.model.head import head_tail
+    z = load_golden(name)
+    n, nc, nl = (int(v) for v in z["meta"])
+    box = [torch.from_numpy(z[f"box{i}"]).to(cuda_device, dtype).requires_grad_(True) for i in range(nl)]
+    cls = [torch.from_numpy(z[f"cls{i}"]).to(cuda_device, dtype).requires_grad_(True) for i in range(nl)]
+    x, anchors, strides = head_tail(box, cls, torch.tensor([8.0, 16.0, 32.0][:nl]))
+    want = torch.from_numpy(z["x"]).to(dtype)
+    assert torch.equal(x.cpu(), want)                                           # a copy: bit-exact in either dtype
+    assert anchors.shape == (2, x.shape[2]) and strides.shape == (1, x.shape[2])
+    assert np.array_equal(anchors.float().cpu().numpy(), z["anchors"])
+    assert np.array_equal(strides.float().cpu().numpy(), z["strides"])
+    # adjoint: the backward of the two cats hands every level its slice of the gradient, bit-exactly
+    g = torch.randn(x.shape, device=cuda_device).to(dtype)
+    x.backward(g)
+    ref_in = [t.detach().cpu().float().requires_grad_(True) for t in box + cls]
+    D.head_tail(ref_in[:nl], ref_in[nl:]).backward(g.cpu().float())
+    for got, ref in zip(box + cls, ref_in):
+        assert torch.equal(got.grad.cpu().float(), ref.grad)
+
+
+def test_head_tail_full_size_round_trip(cuda_device):
+    """640 px, nc=80, N=16: gather equals torch's own cats, and scatter(gather(levels)) == levels."""
+    from custom_yolo_implmentation_b200.model.head import gather_levels
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    shapes = [(80, 80), (40, 40), (20, 20)]
+    box = [torch.randn(16, 64, h, w, device=cuda_device, generator=g).requires_grad_(True) for h, w in shapes]
+    cls = [torch.randn(16, 80, h, w, device=cuda_device, generator=g).requires_grad_(True) for h, w in shapes]
+    x = gather_levels(box, cls)
+    assert x.shape == (16, 144, 8400)
+    assert torch.equal(x, D.head_tail([b.detach() for b in box], [c.detach() for c in cls]))
+    x.backward(x.detach())
+    for t in box + cls:
+        assert torch.equal(t.grad, t.detach())
+
+
+def test_head_tail_rejects_bad_input(cuda_device):
+    from custom_yolo_implmentation_b200.model.head import head_tail
+    b = [torch.zeros(1, 64, 2, 2, device=cuda_device)]
+    with pytest.raises(ValueError):
+        head_tail(b, [torch.zeros(1, 3, 2, 3, device=cuda_device)], [8.0])
+    with pytest.raises(RuntimeError):
+        head_tail([torch.zeros(1, 64, 2, 2)], [torch.zeros(1, 3, 2, 2)], [8.0])
+    with pytest.raises(TypeError):
+        head_tail([t.half() for t in b], [torch.zeros(1, 3, 2, 2, device=cuda_device).half()], [8.0])

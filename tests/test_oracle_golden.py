@@ -153,3 +153,16 @@ def test_helper_oracles_match_reference():
     a2, s2 = syn.anchor_grid(64)
     ar, sr = D.make_anchor_grid([(8, 8), (4, 4), (2, 2)], [8, 16, 32])
     assert torch.equal(a2, ar.t()) and torch.equal(s2, sr.t())
+
+
+@pytest.mark.parametrize("name", ["head_aligned", "head_ragged"])
+def test_head_tail_oracle_matches_reference(name):
+    z = load_golden(name)
+    n, nc, nl = (int(v) for v in z["meta"])
+    box = [torch.from_numpy(z[f"box{i}"]) for i in range(nl)]
+    cls = [torch.from_numpy(z[f"cls{i}"]) for i in range(nl)]
+    x = D.head_tail(box, cls)
+    assert x.shape == (n, 64 + nc, sum(int(h) * int(w) for h, w in z["shapes"]))
+    assert np.array_equal(x.numpy(), z["x"])                                   # a copy: bit-exact
+    grid, st = D.make_anchor_grid([tuple(int(v) for v in s) for s in z["shapes"]], [8.0, 16.0, 32.0][:nl])
+    assert np.array_equal(grid.t().numpy(), z["anchors"]) and np.array_equal(st.t().numpy(), z["strides"])
