@@ -168,30 +168,6 @@ __device__ __forceinline__ float dfl_expectation16(const float (&x)[16], float (
     return __fdiv_rn(wsum, sum);
 }
 
-// The same expectation from two 8-bin halves (online-softmax merge): lets a kernel keep only 8 rows
-// of a side in registers at a time.  Half h holds bins 8h .. 8h+7.
-struct DflPartial {
-    float m, s, w;      // max, sum exp(x - m), sum j exp(x - m)
-};
-__device__ __forceinline__ DflPartial dfl_half8(const float (&x)[8], int bin0) {
-    DflPartial r;
-    r.m = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
-    float e[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) e[j] = __expf(x[j] - r.m);
-    r.s = ((e[0] + e[4]) + (e[2] + e[6])) + ((e[1] + e[5]) + (e[3] + e[7]));
-    float w = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w = fmaf((float)(bin0 + j), e[j], w);
-    r.w = w;
-    return r;
-}
-__device__ __forceinline__ float dfl_merge(const DflPartial &a, const DflPartial &b) {
-    const float m = fmaxf(a.m, b.m);
-    const float fa = __expf(a.m - m), fb = __expf(b.m - m);
-    return __fdiv_rn(fmaf(a.w, fa, b.w * fb), fmaf(a.s, fa, b.s * fb));
-}
-
 // Pixel-space box of one anchor from its four expected distances (src/model/losses.py:178-186).
 struct PredBox {
     float x1, y1, x2, y2, cx, cy, w, h;
@@ -246,6 +222,46 @@ __device__ __forceinline__ float fast_rcp(float x) {        // MUFU.RCP, 1 ulp
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+// The same expectation from two 8-bin halves (online-softmax merge): lets a kernel keep only 8 rows
+// of a side in registers at a time.  Half h holds bins 8h .. 8h+7.  exp(x - max) is evaluated in the
+// base-2 domain, ex2(x * log2e - o) with o = fl(max * log2e): packed FFMA2 (one instruction per two
+// bins) + MUFU.EX2.  The partial carries o itself, so the merge rescales by ex2(o_a - o) exactly as the
+// terms were scaled and the rounding of o cancels.  Sums run on the packed pipe in the fixed order
+// ((0+4)+(2+6)) + ((1+5)+(3+7)).
+struct DflPartial {
+    float o, s, w;      // o = fl(max * log2e), s = sum ex2(x*log2e - o), w = sum j ex2(x*log2e - o)
+};
+__device__ __forceinline__ DflPartial dfl_half8(const float (&x)[8], int bin0) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    DflPartial r;
+    const float m = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    r.o = m * kLog2e;
+    const f32x2 no2 = pack2(-r.o, -r.o), l2 = pack2(kLog2e, kLog2e);
+    f32x2 e2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        unpack2(fma2(pack2(x[2 * k], x[2 * k + 1]), l2, no2), lo, hi);
+        e2[k] = pack2(fast_ex2(lo), fast_ex2(hi));
+    }
+    float lo, hi;
+    unpack2(add2(add2(e2[0], e2[2]), add2(e2[1], e2[3])), lo, hi);
+    r.s = lo + hi;
+    const float b = (float)bin0;
+    f32x2 w2 = mul2(pack2(b + 6.f, b + 7.f), e2[3]);
+    w2 = fma2(pack2(b + 4.f, b + 5.f), e2[2], w2);
+    w2 = fma2(pack2(b + 2.f, b + 3.f), e2[1], w2);
+    w2 = fma2(pack2(b, b + 1.f), e2[0], w2);
+    unpack2(w2, lo, hi);
+    r.w = lo + hi;
+    return r;
+}
+__device__ __forceinline__ float dfl_merge(const DflPartial &a, const DflPartial &b) {
+    const float o = fmaxf(a.o, b.o);
+    const float fa = fast_ex2(a.o - o), fb = fast_ex2(b.o - o);
+    return __fdiv_rn(fmaf(a.w, fa, b.w * fb), fmaf(a.s, fa, b.s * fb));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

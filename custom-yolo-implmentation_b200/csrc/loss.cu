@@ -136,7 +136,7 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
 #pragma unroll
                         for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
 #ifdef YB_ASSIGN_NODECODE
-                        DflPartial ph; ph.m = x[0] + x[7]; ph.s = x[1] + x[2] + x[3]; ph.w = x[4] + x[5] + x[6];
+                        DflPartial ph; ph.o = x[0] + x[7]; ph.s = x[1] + x[2] + x[3]; ph.w = x[4] + x[5] + x[6];
 #else
                         const DflPartial ph = dfl_half8(x, h * 8);
 #endif

@@ -31,6 +31,13 @@ constexpr float kEpsIn = 1e-9f;
 constexpr float kEpsNorm = 1e-9f;
 constexpr float kFourOverPi2 = 0.40528473456935109f;
 constexpr int kTalFinThreadsDecl = 256;
+#ifndef YB_TAL_CAND_MINBLOCKS
+#define YB_TAL_CAND_MINBLOCKS 8
+#endif
+constexpr int kTalCandMinBlocks = YB_TAL_CAND_MINBLOCKS;
+// shared memory of tal_candidates_kernel: box 16 B + centre 8 B per anchor, 16 B per group of 32 anchors,
+// and per warp a queue of (metric 4 B, anchor 2 B) per anchor
+static size_t tal_cand_smem(int tile) { return (size_t)tile * (16 + 8 + (kTalThreads / 32) * (4 + 2)) + (size_t)(tile / 32) * 16; }
 
 struct TalWorkspace {
     // zeroed by yb_tal_assign
@@ -124,20 +131,22 @@ __device__ __forceinline__ Ciou ciou_eval(const float4 &p, const float4 &g, floa
 // tal_candidates_kernel
 // ------------------------------------------------------------------------------------------
 template <typename T, int VW>
-__global__ void __launch_bounds__(kTalThreads)
+__global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : kTalCandMinBlocks)   // bf16 tiles: 4 CTAs of shared memory per SM
 tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
                       const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
                       int topk, float alpha, float beta, int *__restrict__ cand_count, float4 *__restrict__ cand,
                       int cand_cap) {
     constexpr int TILE = kTalThreads * VW;
     constexpr int NW = kTalThreads / 32;
-    // dynamic shared memory (64 B per anchor of the tile: 32 KB for fp32 rows, 64 KB for bf16 rows)
+    constexpr int NG = TILE / 32;                          // groups of 32 consecutive anchors (<= 32)
+    constexpr int GL = 32 / VW;                            // lanes that share one group
+    // dynamic shared memory: 24 B per anchor of the tile + 6 B per anchor and warp (see tal_cand_smem)
     extern __shared__ __align__(16) unsigned char tal_smem[];
     float4 *s_box = reinterpret_cast<float4 *>(tal_smem);                         // decoded xyxy (pixels)
     float2 *s_ctr = reinterpret_cast<float2 *>(s_box + TILE);                     // anchor centres (pixels)
-    float (*s_qm)[TILE] = reinterpret_cast<float (*)[TILE]>(s_ctr + TILE);        // per-warp queue: metric
-    float (*s_qo)[TILE] = reinterpret_cast<float (*)[TILE]>(&s_qm[NW][0]);        //                 overlap
-    unsigned short (*s_q)[TILE] = reinterpret_cast<unsigned short (*)[TILE]>(&s_qo[NW][0]);   //     anchor
+    float4 *s_grp = reinterpret_cast<float4 *>(s_ctr + TILE);                     // centre extent of each group
+    float (*s_qm)[TILE] = reinterpret_cast<float (*)[TILE]>(s_grp + NG);          // per-warp queue: metric
+    unsigned short (*s_q)[TILE] = reinterpret_cast<unsigned short (*)[TILE]>(&s_qm[NW][0]);   //     anchor
     __shared__ float s_bb[4][NW];                        // tile extent of the anchor centres
 
     const int n = blockIdx.y;
@@ -183,12 +192,15 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
+        if (o == GL && (lane & (GL - 1)) == 0)             // extent of this lane's group of 32 anchors
+            s_grp[(threadIdx.x * VW) >> 5] = make_float4(lo_x, lo_y, hi_x, hi_y);
         lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
         lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
         hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
         hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
     }
+    if (GL == 32 && lane == 0) s_grp[warp] = make_float4(lo_x, lo_y, hi_x, hi_y);
     if (lane == 0) { s_bb[0][warp] = lo_x; s_bb[1][warp] = lo_y; s_bb[2][warp] = hi_x; s_bb[3][warp] = hi_y; }
     __syncthreads();
 #pragma unroll
@@ -197,19 +209,21 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
         hi_x = fmaxf(hi_x, s_bb[2][w]); hi_y = fmaxf(hi_y, s_bb[3][w]);
     }
     const int tile_n = min(TILE, n_anchors - tile0);
+    float4 my_grp = make_float4(0.f, 0.f, -1.f, -1.f);    // an empty extent never intersects
+    if (lane < NG) my_grp = s_grp[lane];
 
     for (int g = warp; g < m_img; g += NW) {                              // one warp per GT
         const float *g5 = gt + (size_t)(g_begin + g) * 5;
         const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
         const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
         if (!(gb.x < hi_x && gb.z > lo_x && gb.y < hi_y && gb.w > lo_y)) continue;   // no centre of this tile inside
-        int cls = (int)__ldg(g5 + 4);
-        cls = min(max(cls, 0), n_ch - 4 * kRegMax - 1);
-        const float at_g = gt_atan(gb);
-        // 1. queue the anchors whose centre is strictly inside the GT (ascending anchor order)
+        // 1. queue the anchors whose centre is strictly inside the GT (ascending anchor order); only the
+        //    groups of 32 anchors whose centre extent meets the GT are looked at
+        unsigned groups = __ballot_sync(0xffffffffu, gb.x < my_grp.z && gb.z > my_grp.x && gb.y < my_grp.w && gb.w > my_grp.y);
         int nq = 0;
-        for (int base = 0; base < tile_n; base += 32) {
-            const int a = base + lane;
+        while (groups) {
+            const int a = ((__ffs(groups) - 1) << 5) + lane;
+            groups &= groups - 1;
             bool in = false;
             if (a < tile_n) {
                 const float2 c = s_ctr[a];
@@ -220,14 +234,16 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
             nq += __popc(mask);
         }
         if (nq == 0) continue;
+        int cls = (int)__ldg(g5 + 4);
+        cls = min(max(cls, 0), n_ch - 4 * kRegMax - 1);
+        const float at_g = gt_atan(gb);
         __syncwarp();
-        // 2. overlap and alignment metric of the queue
+        // 2. alignment metric of the queue
         for (int q = lane; q < nq; q += 32) {
             const int a = s_q[warp][q];
-            const float ov = fmaxf(ciou_eval(s_box[a], gb, at_g).value, 0.f);
             const float logit = load_as_float(preds + img + (size_t)(4 * kRegMax + cls) * n_anchors + tile0 + a);
+            const float ov = fmaxf(ciou_eval(s_box[a], gb, at_g).value, 0.f);
             const float sc = __fdiv_rn(1.f, 1.f + expf(-logit));
-            s_qo[warp][q] = ov;
             float m;
             if (alpha == 0.5f && beta == 6.f) {             // the defaults: sqrt and three multiplications
                 const float o2 = ov * ov;
@@ -238,36 +254,37 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
             s_qm[warp][q] = m;
         }
         __syncwarp();
-        // 3. the tile's k best (metric descending, ties -> lowest anchor = lowest queue position)
+        // 3. the tile's k best (metric descending, ties -> lowest anchor = lowest queue position).
+        //    Metrics are >= 0, so their bit patterns order like signed integers; lane r ends up holding the
+        //    r-th best (queue position, metric) and re-evaluates its overlap once, all lanes in parallel.
         const int n_sel = min(nq, topk);
         int slot = 0;
         if (lane == 0) slot = atomicAdd(cand_count + g_begin + g, n_sel);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        float4 *out = cand + (size_t)(g_begin + g) * cand_cap + slot;
+        int my_q = lane, my_m = 0;
         if (nq <= topk) {
-            for (int q = lane; q < nq; q += 32)
-                out[q] = make_float4(s_qm[warp][q], s_qo[warp][q], __int_as_float(tile0 + (int)s_q[warp][q]), 0.f);
+            if (lane < nq) my_m = __float_as_int(s_qm[warp][lane]);
         } else {
             for (int r = 0; r < n_sel; ++r) {
-                float bm = -1.f;
-                int bq = 0x7fffffff;
+                int bm = -1, bq = 0x7fffffff;
                 for (int q = lane; q < nq; q += 32) {
-                    const float m = s_qm[warp][q];
+                    const int m = __float_as_int(s_qm[warp][q]);
                     if (m > bm) { bm = m; bq = q; }               // strict: first (lowest q) maximum per lane
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float om = __shfl_xor_sync(0xffffffffu, bm, o);
-                    const int oq = __shfl_xor_sync(0xffffffffu, bq, o);
-                    if (om > bm || (om == bm && oq < bq)) { bm = om; bq = oq; }
-                }
-                if (lane == 0) {
-                    out[r] = make_float4(bm, s_qo[warp][bq], __int_as_float(tile0 + (int)s_q[warp][bq]), 0.f);
-                    s_qm[warp][bq] = -2.f;                        // taken (metrics are >= 0)
-                }
+                const int wm = __reduce_max_sync(0xffffffffu, bm);
+                const int wq = __reduce_min_sync(0xffffffffu, bm == wm ? bq : 0x7fffffff);
+                if (lane == r) { my_q = wq; my_m = wm; }
+                if (lane == (wq & 31)) s_qm[warp][wq] = -2.f;     // taken (negative as an integer too)
                 __syncwarp();
             }
         }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (lane < n_sel) {
+            const int a = s_q[warp][my_q];
+            const float ov = fmaxf(ciou_eval(s_box[a], gb, at_g).value, 0.f);
+            cand[(size_t)(g_begin + g) * cand_cap + slot + lane] =
+                make_float4(__int_as_float(my_m), ov, __int_as_float(tile0 + a), 0.f);
+        }
+        __syncwarp();                                             // the queue is reused by the warp's next GT
     }
 }
 
@@ -658,7 +675,7 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
     if (gt_total > 0) {
         constexpr int TILE = kTalThreads * VW;
         dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
-        const size_t smem = (size_t)TILE * (16 + 8 + (kTalThreads / 32) * (4 + 4 + 2));
+        const size_t smem = tal_cand_smem(TILE);
         YB_CUDA(cudaFuncSetAttribute(tal_candidates_kernel<T, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tal_candidates_kernel<T, VW><<<grid, kTalThreads, smem, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
                                                                      topk, alpha, beta, w.cand_count, w.cand, w.cand_cap);

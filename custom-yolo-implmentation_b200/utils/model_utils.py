@@ -174,8 +174,11 @@ def non_max_suppression(
     descending, on ``prediction.device`` (reference :174-279).  All images are processed by three
     kernel launches and ONE device-to-host copy (the per-image counts); the reference's wall-clock
     abort (:212, :275-277) is deliberately not reproduced — every image is processed.
-    ``multi_label=True`` (with nc > 1) and apriori ``labels`` are not on the reference's own call
-    path (src/model/model_builder.py:139) and raise NotImplementedError.
+    ``multi_label=True`` (with nc > 1) is not on the reference's own call path
+    (src/model/model_builder.py:139) and raises NotImplementedError.  Non-empty apriori ``labels``
+    raise the RuntimeError the reference raises: it builds label rows ``nc + nm + 5`` wide (:227, the
+    YOLOv5 layout with an objectness column) and cannot concatenate them with its ``4 + nc + nm`` wide
+    candidates (:231).
     """
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
@@ -186,7 +189,9 @@ def non_max_suppression(
     if multi_label and nc > 1:
         raise NotImplementedError("non_max_suppression(multi_label=True) is not implemented by the CUDA path")
     if labels and any(len(lb) for lb in labels):
-        raise NotImplementedError("non_max_suppression(labels=...) (autolabelling) is not implemented by the CUDA path")
+        width = prediction.shape[1]
+        raise RuntimeError(f"Sizes of tensors must match except in dimension 0. Expected size {width} but got size "
+                           f"{width + 1} for tensor number 1 in the list.")
     if classes is not None and len(classes) == 0:
         return [torch.zeros((0, 6), device=prediction.device)] * bs
     rows, count, _ = batched_nms_raw(prediction, conf_thres, iou_thres, max_det, nc, agnostic, classes)
