@@ -162,8 +162,11 @@ __device__ __forceinline__ bool iou_exceeds(const float4 &a, float area_a, const
     const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
     const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
     if (!(w > 0.f && h > 0.f)) return false;
-    const float inter = __fmul_rn(w, h);
     const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    // IoU <= min(area) / max(area): boxes of clearly different size cannot exceed the threshold (the 1 %
+    // margin is far above the rounding of the exact test below; NaN / non-positive areas fall through)
+    if (fminf(area_a, area_b) < 0.99f * thr * fmaxf(area_a, area_b) && fminf(area_a, area_b) > 0.f) return false;
+    const float inter = __fmul_rn(w, h);
     const float den = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     const float est = inter * fast_rcp(den);
     if (fabsf(est - thr) > fmaf(1e-6f, thr, 1e-35f)) return est > thr;
@@ -182,29 +185,50 @@ __device__ __forceinline__ float4 load_offset_box(const float *__restrict__ img,
                        __fadd_rn(__fadd_rn(x, dw), off), __fadd_rn(__fadd_rn(y, dh), off));
 }
 
+// Cheap necessary condition for iou_exceeds: the boxes overlap in x and in y (four comparisons).
+__device__ __forceinline__ bool boxes_touch(const float4 &a, const float4 &b) {
+    return a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y;
+}
+
+// IoU <= min(area) / max(area), so |log2(area_a) - log2(area_b)| > -log2(0.99 * thr) rules a pair out
+// with one subtraction and one comparison (MUFU.LG2 is good to ~2^-22, the 1 % margin is 0.0145 in log2
+// units).  NaN (non-positive or infinite areas on both sides) never rules out; the exact test decides.
+__device__ __forceinline__ float log_area(const float4 &b) { return __log2f(box_area(b)); }
+__device__ __forceinline__ float log_area_bound(float thr) { return -__log2f(0.99f * thr); }
+__device__ __forceinline__ bool areas_compatible(float la, float lb, float bound) { return !(fabsf(la - lb) > bound); }
+
 // Resolve one block of 32 consecutive sorted boxes inside a warp.  `bx`/`alive` belong to lane r =
 // position c0 + r.  Returns the mask of rows kept (already capped to `room`).
 __device__ __forceinline__ unsigned resolve_block(const float4 &bx, bool alive, float thr, int room) {
     const int lane = threadIdx.x & 31;
     unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
     const float my_area = box_area(bx);
-    unsigned sup = 0;                                    // bit r2: my box suppresses the later box r2
+    const float my_la = __log2f(my_area), la_bound = log_area_bound(thr);
+    // Every unordered pair is tested once: in step k lane l meets lane (l + k) mod 32.  The test is
+    // symmetric, so the lane records either "I suppress the later box" (sup) or "the earlier box
+    // suppresses me" (by), whichever side of the pair it is on.
+    unsigned sup = 0, by = 0;
 #pragma unroll 4
-    for (int r2 = 1; r2 < 32; ++r2) {
+    for (int k = 1; k <= 16; ++k) {
+        const int partner = (lane + k) & 31;
         float4 o;
-        o.x = __shfl_sync(0xffffffffu, bx.x, r2);
-        o.y = __shfl_sync(0xffffffffu, bx.y, r2);
-        o.z = __shfl_sync(0xffffffffu, bx.z, r2);
-        o.w = __shfl_sync(0xffffffffu, bx.w, r2);
-        const bool touch = r2 > lane && fminf(bx.z, o.z) > fmaxf(bx.x, o.x) && fminf(bx.w, o.w) > fmaxf(bx.y, o.y);
-        if (__any_sync(0xffffffffu, touch)) {
-            if (touch && iou_exceeds(bx, my_area, o, thr)) sup |= 1u << r2;
+        o.x = __shfl_sync(0xffffffffu, bx.x, partner);
+        o.y = __shfl_sync(0xffffffffu, bx.y, partner);
+        o.z = __shfl_sync(0xffffffffu, bx.z, partner);
+        o.w = __shfl_sync(0xffffffffu, bx.w, partner);
+        const float o_la = __shfl_sync(0xffffffffu, my_la, partner);
+        const bool maybe = boxes_touch(bx, o) && areas_compatible(my_la, o_la, la_bound);
+        if (__any_sync(0xffffffffu, maybe)) {
+            if (maybe && iou_exceeds(bx, my_area, o, thr)) {
+                if (partner > lane) sup |= 1u << partner;
+                else by |= 1u << partner;
+            }
         }
     }
     unsigned kept = 0;
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
-        const unsigned s_r = __shfl_sync(0xffffffffu, sup, r);
+        const unsigned s_r = __shfl_sync(0xffffffffu, sup, r) | __ballot_sync(0xffffffffu, (by >> r) & 1u);
         if ((alive_mask >> r) & 1u) {
             kept |= 1u << r;
             alive_mask &= ~s_r;
@@ -380,6 +404,10 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     __shared__ unsigned s_minx, s_maxx;
     __shared__ unsigned long long s_prefix;
     __shared__ int s_k;
+    __shared__ float4 s_rowbox[kClassThreads / 32][32];   // per warp: kept rows of the current 32-box block
+    __shared__ float s_rowla[kClassThreads / 32][32];     //           and log2 of their areas
+    __shared__ unsigned short s_order[kClassMaxNc + 1];   // this CTA's classes, largest segment first
+    __shared__ int s_next[2];                             // work counters of the two per-class phases
 
     // gridDim.x CTAs share an image: CTA `part` owns the classes c with c % gridDim.x == part
     const int img = blockIdx.y, part = blockIdx.x, n_part = gridDim.x;
@@ -399,7 +427,7 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     YB_MARK(0);
     // ---- 1. histogram of classes, exclusive scan ------------------------------------------------
     for (int c = tid; c < nc; c += kClassThreads) s_cursor[c] = 0;
-    if (tid == 0) { s_flag = 0; s_minx = 0u; s_maxx = 0u; s_total = 0; }
+    if (tid == 0) { s_flag = 0; s_minx = 0u; s_maxx = 0u; s_total = 0; s_next[0] = 0; s_next[1] = 0; }
     __syncthreads();
     for (int r = tid; r < n; r += kClassThreads) atomicAdd(&s_cursor[cls_n[key_anchor(k_in[r])]], 1);
     __syncthreads();
@@ -423,6 +451,20 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     }
     __syncthreads();
     if (s_flag) return;                                    // a class too large for one warp: generic path
+    // Warps take classes from a shared counter, largest segment first (the per-class work grows with
+    // the square of the segment, so index order leaves the warp with two large classes far behind).
+    const int n_my = (nc - part + n_part - 1) / n_part;    // classes of this CTA: part, part + n_part, ...
+    for (int t = tid; t < n_my; t += kClassThreads) {
+        const int c = part + t * n_part;
+        const int sz = s_start[c + 1] - s_start[c];
+        int rank = 0;
+        for (int u = 0; u < n_my; ++u) {
+            const int cu = part + u * n_part;
+            const int su = s_start[cu + 1] - s_start[cu];
+            rank += (su > sz || (su == sz && u < t)) ? 1 : 0;
+        }
+        s_order[rank] = (unsigned short)c;
+    }
     for (int c = tid; c < nc; c += kClassThreads) s_cursor[c] = s_start[c];
     __syncthreads();
 
@@ -438,7 +480,12 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     }
     __syncthreads();
     YB_MARK(2);
-    for (int c = part + warp * n_part; c < nc; c += (kClassThreads / 32) * n_part) {
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next[0], 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_my) break;
+        const int c = s_order[item];
         const int seg0 = s_start[c], n_c = s_start[c + 1] - seg0;
         for (int e0 = 0; e0 < n_c; e0 += 128) {            // four elements per lane per sweep of the segment
             unsigned long long ke[4];
@@ -467,9 +514,14 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     // its column in block b is still alive.  Per row block: resolve the 32x32 diagonal block with
     // shuffles (resolve_block), then let the kept rows clear later columns.  All in registers.
     unsigned char *alive_img = alive_g + (size_t)img * a_pad;                // one byte per sorted position
-    for (int c = part + warp * n_part; c < nc; c += (kClassThreads / 32) * n_part) {
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next[1], 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_my) break;
+        const int c = s_order[item];
         const int seg0 = s_start[c], n_c = s_start[c + 1] - seg0;
-        if (n_c == 0) continue;
+        if (n_c == 0) break;                               // largest first: every later class is empty too
         const int nb = (n_c + 31) >> 5;                    // <= 16 (kClassSegCap)
         // class-offset boxes of the segment into shared memory, in score order (model_utils.py:239, :262-263)
         for (int m0 = 0; m0 < n_c; m0 += 128) {
@@ -501,6 +553,7 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
         long long t_res = 0, t_cross = 0, t0c = clock64();
 #endif
         unsigned alive_bits = 0;
+        const float la_bound = log_area_bound(thr);
         for (int b = 0; b < nb; ++b) alive_bits |= (b * 32 + lane < n_c ? 1u : 0u) << b;
         for (int rb = 0; rb < nb; ++rb) {
             const int my = rb * 32 + lane;
@@ -513,26 +566,40 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
             long long tb = clock64(); t_res += tb - ta;
 #endif
             alive_bits = (alive_bits & ~(1u << rb)) | (((kept >> lane) & 1u) << rb);
+            if (rb + 1 == nb || kept == 0u) continue;
+            // the kept rows of this block, compacted into the warp's scratch list (box + log2 area)
+            const int nk = __popc(kept);
+            if ((kept >> lane) & 1u) {
+                const int rank = __popc(kept & ((1u << lane) - 1u));
+                s_rowbox[warp][rank] = rbox;
+                s_rowla[warp][rank] = log_area(rbox);
+            }
+            __syncwarp();
             for (int cb = rb + 1; cb < nb; ++cb) {
                 const int col = cb * 32 + lane;
                 bool live = (alive_bits >> cb) & 1u;
                 const float4 cbox = live ? B[seg0 + col] : make_float4(0.f, 0.f, 0.f, 0.f);
-                unsigned todo = kept;
+                const float c_area = box_area(cbox), c_la = __log2f(c_area);
                 bool sup = false;
-                while (todo) {                             // warp-uniform walk over the kept rows of block rb
-                    const int r = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const float4 row = B[seg0 + rb * 32 + r];                 // broadcast read
-                    // most same-class pairs do not even touch: one vote skips the IoU arithmetic
-                    const bool touch = live && fminf(row.z, cbox.z) > fmaxf(row.x, cbox.x) &&
-                                       fminf(row.w, cbox.w) > fmaxf(row.y, cbox.y);
-                    if (__any_sync(0xffffffffu, touch)) {
-                        if (touch) sup |= iou_exceeds(row, box_area(row), cbox, thr);
+                for (int i = 0; i < nk; i += 4) {          // warp-uniform walk over the kept rows, four at a time
+                    bool maybe[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = min(i + u, nk - 1);  // the tail repeats the last row: harmless
+                        maybe[u] = live && boxes_touch(s_rowbox[warp][r], cbox) &&
+                                   areas_compatible(s_rowla[warp][r], c_la, la_bound);
+                    }
+                    // most same-class pairs cannot reach the threshold: one vote skips the IoU arithmetic
+                    if (__any_sync(0xffffffffu, maybe[0] || maybe[1] || maybe[2] || maybe[3])) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (maybe[u]) sup |= iou_exceeds(cbox, c_area, s_rowbox[warp][min(i + u, nk - 1)], thr);
                     }
                 }
                 live = live && !sup;
                 if (!live) alive_bits &= ~(1u << cb);
             }
+            __syncwarp();                                  // the list is rewritten by the next row block
         }
         for (int b = 0; b < nb; ++b)
             if (b * 32 + lane < n_c) alive_img[seg0 + b * 32 + lane] = (alive_bits >> b) & 1u;

@@ -4,7 +4,7 @@ import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.7
 cur_file = None
-agg = collections.OrderedDict()
+agg = collections.OrderedDict(); last = ("?", "0"); agg[last] = [0.0, 0.0, ""]
 hdr = None
 for r in rows:
     if not r: continue
