@@ -8,17 +8,21 @@
 // Two ABI calls so that the normaliser can be all-reduced between them (the one real exchange step):
 //   yb_tal_assign   tal_candidates_kernel  per (image, anchor tile): decode the tile into shared memory;
 //                                          one warp per GT enqueues the anchors whose centre lies inside
-//                                          the GT (ballot compaction), evaluates CIoU / metric for the
-//                                          queue and keeps the tile's k best -> per-GT candidate list
+//                                          the GT (group-extent skip + ballot compaction), evaluates the
+//                                          metric for the queue and keeps the tile's k best (REDUX rounds)
+//                                          -> per-GT candidate list
 //                   tal_select_kernel      one warp per GT: global top-k (metric desc, anchor asc),
 //                                          64-bit atomicMax (overlap, ~gt) per anchor resolves conflicts
 //                   tal_resolve_kernel     one warp per GT: which of its k anchors it kept, max metric /
-//                                          overlap, normalised target scores, per-GT score sum
+//                                          overlap, normalised target scores, per-GT score sum, anchor -> slot map
 //                   tal_stats_kernel       fixed-order sum -> [sum of target scores, #foreground]
-//   yb_tal_loss     tal_cls_kernel         dense BCE-with-logits at target 0 + gradient, zero box gradient
-//                   tal_fg_kernel          one warp per foreground anchor: CIoU and DFL loss + gradient into
-//                                          its 64 box logits, correction of its one positive class cell
-//                   tal_finalize_kernel    fixed-order reduction -> loss scalars
+//   yb_tal_loss     tal_fg_kernel          one warp per foreground anchor: CIoU and DFL loss, and the gradient of
+//                                          its 64 box logits into a compact, coalesced buffer
+//                   tal_cls_kernel         dense BCE-with-logits at target 0 + gradient; writes the box rows of the
+//                                          gradient too: zero, or the foreground anchor's 64 values (predicated
+//                                          loads through the anchor -> slot map, no scattered stores)
+//                   tal_finalize_kernel    patches the one positive class cell of every foreground anchor, then
+//                                          fixed-order reduction -> loss scalars
 // The anchors x GT overlap / metric matrices never exist; only <= k candidates per (GT, tile) leave a CTA.
 #include "common.cuh"
 
@@ -44,6 +48,7 @@ struct TalWorkspace {
     unsigned int *ticket;               // [2]
     int *cand_count;                    // [gt_total]
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
+    int *aslot;                         // [N * A]  1 + (g * topk + r) of the GT slot that owns the anchor (0 = background)
     // plain scratch
     float4 *cand;                       // [gt_total * cand_cap]  metric, overlap, anchor (as int bits), -
     float4 *sel;                        // [gt_total * kTalMaxK]  anchor bits, metric, overlap, target score
@@ -51,6 +56,9 @@ struct TalWorkspace {
     float *g_tsum;                      // [gt_total]
     int *g_npos;                        // [gt_total]
     float *fg_box, *fg_dfl, *fg_cls;    // [gt_total * kTalMaxK] per-foreground loss terms
+    float *fgrad;                       // [gt_total * kTalMaxK * 64] box-logit gradient of every foreground anchor
+    long long *fcell_off;               // [gt_total * kTalMaxK] element offset of the anchor's positive class cell (-1 = none)
+    float *fcell_val;                   // [gt_total * kTalMaxK] its gradient
     float *part;                        // [N * cls_tiles]
     double *cta_sums;                   // [4 * finalize CTAs]
     int cand_cap, cls_tiles;
@@ -71,6 +79,8 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     off += round_up(sizeof(int) * g, 64);
     w.akey = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)n_images * n_anchors, 64);
+    w.aslot = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * (size_t)n_images * n_anchors, 64);
     w.zero_bytes = off;
     w.cand_cap = topk * tiles;
     w.cls_tiles = tiles;
@@ -89,6 +99,12 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     w.fg_dfl = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * g * kTalMaxK, 64);
     w.fg_cls = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * g * kTalMaxK, 64);
+    w.fgrad = reinterpret_cast<float *>(p + off);
+    off += round_up(sizeof(float) * g * kTalMaxK * 4 * kRegMax, 64);
+    w.fcell_off = reinterpret_cast<long long *>(p + off);
+    off += round_up(sizeof(long long) * g * kTalMaxK, 64);
+    w.fcell_val = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * g * kTalMaxK, 64);
     w.part = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * (size_t)n_images * tiles, 64);
@@ -346,8 +362,8 @@ tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, i
 __global__ void __launch_bounds__(128)
 tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total,
                    const unsigned long long *__restrict__ akey, float4 *__restrict__ sel, const int *__restrict__ sel_count,
-                   float *__restrict__ g_tsum, int *__restrict__ g_npos, int *__restrict__ out_assigned,
-                   float *__restrict__ out_tscore) {
+                   float *__restrict__ g_tsum, int *__restrict__ g_npos, int *__restrict__ aslot, int topk,
+                   int *__restrict__ out_assigned, float *__restrict__ out_tscore) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (g >= gt_total) return;
@@ -377,6 +393,7 @@ tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, 
     }
     if (lane < ns) {
         sel[(size_t)g * kTalMaxK + lane].w = pos ? t : -1.f;      // -1: lost the anchor to another GT
+        if (pos) aslot[(size_t)n * n_anchors + __float_as_int(e.x)] = g * topk + lane + 1;
         if (pos && out_assigned) out_assigned[(size_t)n * n_anchors + __float_as_int(e.x)] = g_local;
         if (pos && out_tscore) out_tscore[(size_t)n * n_anchors + __float_as_int(e.x)] = t;
     }
@@ -417,7 +434,8 @@ __device__ __forceinline__ void bce_bg_elem(float x, float kc, float &acc, float
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kTalThreads)
 tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ tss_dev,
-               float lambda_cls, T *__restrict__ grad, float *__restrict__ part) {
+               float lambda_cls, const int *__restrict__ aslot, const float *__restrict__ fgrad, T *__restrict__ grad,
+               float *__restrict__ part) {
     __shared__ float s_red[kTalThreads / 32];
     const int n = blockIdx.y;
     const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
@@ -426,7 +444,17 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     if (a0 < n_anchors) {
         const size_t img = (size_t)n * n_ch * n_anchors + a0;
         if (WRITE_GRAD) {
-            for (int c = 0; c < 4 * kRegMax; ++c) Group<T, VW>::store_zero(grad + img + (size_t)c * n_anchors);
+            // box rows: zero, except the foreground anchors, whose 64 values tal_fg_kernel left in fgrad
+            int fo[VW];                                    // offset of the anchor's 64 values in fgrad, -1 = background
+#pragma unroll
+            for (int v = 0; v < VW; ++v) fo[v] = (__ldg(aslot + (size_t)n * n_anchors + a0 + v) - 1) * (4 * kRegMax);
+#pragma unroll 8
+            for (int c = 0; c < 4 * kRegMax; ++c) {        // predicated loads, no divergence; rows are independent
+                float vals[VW];
+#pragma unroll
+                for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? __ldg(fgrad + fo[v] + c) : 0.f;
+                Group<T, VW>::store(grad + img + (size_t)c * n_anchors, vals);
+            }
         }
         const size_t base = img + (size_t)4 * kRegMax * n_anchors;
         constexpr int U = 4;
@@ -470,7 +498,8 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
               const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
               const int *__restrict__ gt_off, int gt_total, int topk, const float4 *__restrict__ sel,
               const int *__restrict__ sel_count, const float *__restrict__ tss_dev, float lambda_box, float lambda_cls,
-              float lambda_dfl, T *__restrict__ grad, float *__restrict__ fg_box, float *__restrict__ fg_dfl,
+              float lambda_dfl, bool want_grad, float *__restrict__ fgrad, long long *__restrict__ fcell_off,
+              float *__restrict__ fcell_val, float *__restrict__ fg_box, float *__restrict__ fg_dfl,
               float *__restrict__ fg_cls) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);          // slot = g * topk + r
@@ -479,7 +508,7 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
     float4 e = make_float4(0.f, 0.f, 0.f, -1.f);
     if (r < sel_count[g]) e = sel[(size_t)g * kTalMaxK + r];
     if (!(e.w >= 0.f)) {                                   // unused slot or anchor lost to another GT
-        if (lane == 0) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; }
+        if (lane == 0) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; fcell_off[slot] = -1; }
         return;
     }
     const int idx = __float_as_int(e.x);
@@ -577,21 +606,25 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
     const float dfl4 = ce_half + __shfl_xor_sync(0xffffffffu, ce_half, 16);      // sum over the four sides
     const float kd = lambda_dfl * wgt * 0.25f;
 
-    if (grad != nullptr) {
+    if (want_grad) {
         const float dd_lo = half == 0 ? d_dl : d_dt, dd_hi = half == 0 ? d_dr : d_db;
         const float dk_lo = half == 0 ? dl : dt, dk_hi = half == 0 ? dr : db;
         const float oh_lo = (bin == bl_lo ? wl_lo : 0.f) + (bin == bl_lo + 1 ? wr_lo : 0.f);
         const float oh_hi = (bin == bl_hi ? wl_hi : 0.f) + (bin == bl_hi + 1 ? wr_hi : 0.f);
         const float g_lo = kd * ((wl_lo + wr_lo) * p_lo - oh_lo) + dd_lo * p_lo * ((float)bin - dk_lo);
         const float g_hi = kd * ((wl_hi + wr_hi) * p_hi - oh_hi) + dd_hi * p_hi * ((float)bin - dk_hi);
-        T *gimg = grad + (size_t)n * n_ch * n_anchors;
-        store_from_float(gimg + (size_t)lane * n_anchors + idx, g_lo);
-        store_from_float(gimg + (size_t)(lane + 32) * n_anchors + idx, g_hi);
+        // compact, coalesced: the dense kernel merges these 64 values into the anchor's box rows
+        fgrad[(size_t)slot * (4 * kRegMax) + lane] = g_lo;
+        fgrad[(size_t)slot * (4 * kRegMax) + 32 + lane] = g_hi;
         if (lane == 0) {
-            // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / tss
+            // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / tss;
+            // patched in by tal_finalize_kernel after the dense kernel has written the background value
             const float sg = __fdiv_rn(1.f, 1.f + expf(-z_cls));
-            store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx, lambda_cls * inv_tss * (sg - t));
+            fcell_off[slot] = (long long)((size_t)n * n_ch * n_anchors + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
+            fcell_val[slot] = lambda_cls * inv_tss * (sg - t);
         }
+    } else if (lane == 0) {
+        fcell_off[slot] = -1;
     }
     if (lane == 0) {
         fg_box[slot] = (1.f - c.value) * t;
@@ -603,8 +636,10 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
 // fixed-order reduction in two levels: CTA b sums its slice of every array (tree of fixed shape) and
 // publishes 4 partials; the last CTA to finish adds the partials up in index order.
 constexpr int kTalFinThreads = 256;
+template <typename T>
 __global__ void __launch_bounds__(kTalFinThreads)
-tal_finalize_kernel(int n_part, int n_slots, int gt_total, const float *__restrict__ part,
+tal_finalize_kernel(T *__restrict__ grad, const long long *__restrict__ fcell_off, const float *__restrict__ fcell_val,
+                    int n_part, int n_slots, int gt_total, const float *__restrict__ part,
                     const float *__restrict__ fg_box, const float *__restrict__ fg_dfl, const float *__restrict__ fg_cls,
                     const int *__restrict__ g_npos, const float *__restrict__ tss_dev, float lambda_box, float lambda_cls,
                     float lambda_dfl, double *__restrict__ cta_sums, unsigned int *__restrict__ ticket,
@@ -612,6 +647,10 @@ tal_finalize_kernel(int n_part, int n_slots, int gt_total, const float *__restri
     __shared__ double s[4][kTalFinThreads];
     __shared__ bool s_last;
     const size_t i = (size_t)blockIdx.x * kTalFinThreads + threadIdx.x;
+    if (grad != nullptr && i < (size_t)n_slots) {          // positive class cell of every foreground anchor
+        const long long cell = fcell_off[i];
+        if (cell >= 0) store_from_float(grad + cell, fcell_val[i]);
+    }
     s[0][threadIdx.x] = (i < (size_t)n_part ? (double)part[i] : 0.0) + (i < (size_t)n_slots ? (double)fg_cls[i] : 0.0);
     s[1][threadIdx.x] = i < (size_t)n_slots ? (double)fg_box[i] : 0.0;
     s[2][threadIdx.x] = i < (size_t)n_slots ? (double)fg_dfl[i] : 0.0;
@@ -685,7 +724,7 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
                                                   w.cand_cap, w.sel, w.sel_count, w.akey);
         YB_CUDA(cudaGetLastError());
         tal_resolve_kernel<<<blocks, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, w.akey, w.sel, w.sel_count,
-                                                   w.g_tsum, w.g_npos, out_assigned, out_tscore);
+                                                   w.g_tsum, w.g_npos, w.aslot, topk, out_assigned, out_tscore);
         YB_CUDA(cudaGetLastError());
     }
     tal_stats_kernel<<<1, 256, 0, st>>>(gt_total, w.g_tsum, w.g_npos, out_stats);
@@ -699,29 +738,33 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
                            int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl, T *grad,
                            float *out_loss, const TalWorkspace &w, cudaStream_t st) {
     const int n_ch = 4 * kRegMax + nc;
+    if (gt_total > 0) {                                    // foreground terms first: the dense kernel merges their gradient
+        const int slots = gt_total * topk;
+        tal_fg_kernel<T><<<(slots + 3) / 4, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
+                                                         gt_total, topk, w.sel, w.sel_count, tss_dev, lambda_box, lambda_cls,
+                                                         lambda_dfl, grad != nullptr, w.fgrad, w.fcell_off, w.fcell_val,
+                                                         w.fg_box, w.fg_dfl, w.fg_cls);
+        YB_CUDA(cudaGetLastError());
+    }
     {
         constexpr int TILE = kTalThreads * VW;
         dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
         if (grad != nullptr)
-            tal_cls_kernel<T, VW, true><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, grad, w.part);
+            tal_cls_kernel<T, VW, true><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, w.aslot,
+                                                                      w.fgrad, grad, w.part);
         else
-            tal_cls_kernel<T, VW, false><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, grad, w.part);
-        YB_CUDA(cudaGetLastError());
-    }
-    if (gt_total > 0) {
-        const int slots = gt_total * topk;
-        tal_fg_kernel<T><<<(slots + 3) / 4, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
-                                                         gt_total, topk, w.sel, w.sel_count, tss_dev, lambda_box, lambda_cls,
-                                                         lambda_dfl, grad, w.fg_box, w.fg_dfl, w.fg_cls);
+            tal_cls_kernel<T, VW, false><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, w.aslot,
+                                                                       w.fgrad, grad, w.part);
         YB_CUDA(cudaGetLastError());
     }
     {
         const int n_part = n_images * w.cls_tiles, n_slots = gt_total * topk;
         const int n_max = max(max(n_part, n_slots), gt_total);
         const int blocks = (n_max + kTalFinThreads - 1) / kTalFinThreads;
-        tal_finalize_kernel<<<blocks, kTalFinThreads, 0, st>>>(n_part, n_slots, gt_total, w.part, w.fg_box, w.fg_dfl, w.fg_cls,
-                                                               w.g_npos, tss_dev, lambda_box, lambda_cls, lambda_dfl,
-                                                               w.cta_sums, w.ticket, out_loss);
+        tal_finalize_kernel<T><<<blocks, kTalFinThreads, 0, st>>>(grad, w.fcell_off, w.fcell_val, n_part, n_slots, gt_total,
+                                                                  w.part, w.fg_box, w.fg_dfl, w.fg_cls, w.g_npos, tss_dev,
+                                                                  lambda_box, lambda_cls, lambda_dfl, w.cta_sums, w.ticket,
+                                                                  out_loss);
     }
     YB_CUDA(cudaGetLastError());
     return YB_OK;
