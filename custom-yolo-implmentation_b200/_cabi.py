@@ -35,6 +35,9 @@ _SIGNATURES = {
                               c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_tal_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                             c_int, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_tal_loss_vfl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                c_size_t, c_void_p]),
     "yb_stage_timing": (c_int, [c_int]),
     "yb_loss_last_stage_ms": (c_int, [c_void_p]),
     "yb_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),

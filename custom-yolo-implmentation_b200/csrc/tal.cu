@@ -431,11 +431,29 @@ __device__ __forceinline__ void bce_bg_elem(float x, float kc, float &acc, float
     g = kc * (x >= 0.f ? r : e * r);
 }
 
-template <typename T, int VW, bool WRITE_GRAD>
+// Varifocal weighting of the background cells (label 0, target 0): w = va * sigmoid(x)^vg, loss = w * softplus(x);
+// the weight is differentiated too:  d/dx = w * (vg * (1 - sigmoid) * softplus + sigmoid).
+struct VflParams {
+    float alpha, gamma;
+};
+__device__ __forceinline__ float vfl_bg_weight(float sg, const VflParams &vp) {
+    return vp.alpha * (vp.gamma == 2.f ? sg * sg : exp2f(vp.gamma * __log2f(sg)));
+}
+__device__ __forceinline__ void vfl_bg_elem(float x, float kc, const VflParams &vp, float &acc, float &g) {
+    const float e = __expf(-fabsf(x));
+    const float r = fast_rcp(1.f + e);
+    const float sg = x >= 0.f ? r : e * r;
+    const float sp = fmaxf(x, 0.f) + log1pf(e);
+    const float w = vfl_bg_weight(sg, vp);
+    acc += w * sp;
+    g = kc * w * fmaf(vp.gamma * (1.f - sg), sp, sg);
+}
+
+template <typename T, int VW, bool WRITE_GRAD, bool VFL>
 __global__ void __launch_bounds__(kTalThreads)
 tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ tss_dev,
-               float lambda_cls, const int *__restrict__ aslot, const float *__restrict__ fgrad, T *__restrict__ grad,
-               float *__restrict__ part) {
+               float lambda_cls, VflParams vp, const int *__restrict__ aslot, const float *__restrict__ fgrad,
+               T *__restrict__ grad, float *__restrict__ part) {
     __shared__ float s_red[kTalThreads / 32];
     const int n = blockIdx.y;
     const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
@@ -472,7 +490,10 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
                 if (c + u < nc) {
                     float g[VW];
 #pragma unroll
-                    for (int v = 0; v < VW; ++v) bce_bg_elem(cur[u].get(v), kc, acc, g[v]);
+                    for (int v = 0; v < VW; ++v) {
+                        if (VFL) vfl_bg_elem(cur[u].get(v), kc, vp, acc, g[v]);
+                        else bce_bg_elem(cur[u].get(v), kc, acc, g[v]);
+                    }
                     if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
                 }
             }
@@ -498,7 +519,8 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
               const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
               const int *__restrict__ gt_off, int gt_total, int topk, const float4 *__restrict__ sel,
               const int *__restrict__ sel_count, const float *__restrict__ tss_dev, float lambda_box, float lambda_cls,
-              float lambda_dfl, bool want_grad, float *__restrict__ fgrad, long long *__restrict__ fcell_off,
+              float lambda_dfl, int vfl, VflParams vp, bool want_grad, float *__restrict__ fgrad,
+              long long *__restrict__ fcell_off,
               float *__restrict__ fcell_val, float *__restrict__ fg_box, float *__restrict__ fg_dfl,
               float *__restrict__ fg_cls) {
     const int lane = threadIdx.x & 31;
@@ -621,7 +643,8 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
             // patched in by tal_finalize_kernel after the dense kernel has written the background value
             const float sg = __fdiv_rn(1.f, 1.f + expf(-z_cls));
             fcell_off[slot] = (long long)((size_t)n * n_ch * n_anchors + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
-            fcell_val[slot] = lambda_cls * inv_tss * (sg - t);
+            // varifocal: the positive cell is weighted by its own target score, a constant
+            fcell_val[slot] = lambda_cls * inv_tss * (sg - t) * (vfl ? t : 1.f);
         }
     } else if (lane == 0) {
         fcell_off[slot] = -1;
@@ -629,7 +652,14 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
     if (lane == 0) {
         fg_box[slot] = (1.f - c.value) * t;
         fg_dfl[slot] = dfl4 * 0.25f * t;
-        fg_cls[slot] = -t * z_cls;
+        if (vfl) {
+            // the dense pass counted this cell as background (w_bg * softplus); it is t * BCE(x, t) instead
+            const float sp = fmaxf(z_cls, 0.f) + log1pf(expf(-fabsf(z_cls)));
+            const float sg = __fdiv_rn(1.f, 1.f + expf(-z_cls));
+            fg_cls[slot] = t * (sp - t * z_cls) - vfl_bg_weight(sg, vp) * sp;
+        } else {
+            fg_cls[slot] = -t * z_cls;                       // BCE(x, t) - BCE(x, 0)
+        }
     }
 }
 
@@ -735,26 +765,26 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
 template <typename T, int VW>
 static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, const float *anchors,
                            const float *strides, const float *gt, const int32_t *gt_off, int gt_total,
-                           int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl, T *grad,
-                           float *out_loss, const TalWorkspace &w, cudaStream_t st) {
+                           int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl, int vfl,
+                           VflParams vp, T *grad, float *out_loss, const TalWorkspace &w, cudaStream_t st) {
     const int n_ch = 4 * kRegMax + nc;
     if (gt_total > 0) {                                    // foreground terms first: the dense kernel merges their gradient
         const int slots = gt_total * topk;
         tal_fg_kernel<T><<<(slots + 3) / 4, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
                                                          gt_total, topk, w.sel, w.sel_count, tss_dev, lambda_box, lambda_cls,
-                                                         lambda_dfl, grad != nullptr, w.fgrad, w.fcell_off, w.fcell_val,
+                                                         lambda_dfl, vfl, vp, grad != nullptr, w.fgrad, w.fcell_off, w.fcell_val,
                                                          w.fg_box, w.fg_dfl, w.fg_cls);
         YB_CUDA(cudaGetLastError());
     }
     {
         constexpr int TILE = kTalThreads * VW;
         dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
-        if (grad != nullptr)
-            tal_cls_kernel<T, VW, true><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, w.aslot,
-                                                                      w.fgrad, grad, w.part);
-        else
-            tal_cls_kernel<T, VW, false><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, w.aslot,
-                                                                       w.fgrad, grad, w.part);
+#define YB_TAL_CLS(WG, VF)                                                                                           \
+    tal_cls_kernel<T, VW, WG, VF><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, vp, w.aslot, \
+                                                                w.fgrad, grad, w.part)
+        if (grad != nullptr) { if (vfl) YB_TAL_CLS(true, true); else YB_TAL_CLS(true, false); }
+        else { if (vfl) YB_TAL_CLS(false, true); else YB_TAL_CLS(false, false); }
+#undef YB_TAL_CLS
         YB_CUDA(cudaGetLastError());
     }
     {
@@ -831,11 +861,11 @@ extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc,
                                                out_target_score, w, st);
 }
 
-extern "C" int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
-                           const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                           int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls,
-                           float lambda_dfl, void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes,
-                           void *stream) {
+static int tal_loss_entry(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                          const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                          int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls,
+                          float lambda_dfl, int vfl, VflParams vp, void *grad_preds, float *out_loss, void *workspace,
+                          size_t workspace_bytes, void *stream) {
     if (int rc = tal_check(preds, anchors, strides, gt_offsets, gt, workspace, dtype, n_images, nc, reg_max, n_anchors,
                            gt_total, topk, "yb_tal_loss"))
         return rc;
@@ -851,19 +881,40 @@ extern "C" int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, i
         const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, topk, tal_tile(dtype, vec_a));
         if (vec_a && tal_vec_ok<float>(preds, grad_preds, n_anchors))
             return launch_tal_loss<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
-                                             gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, (float *)grad_preds, out_loss, w, st);
+                                             gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, vfl, vp, (float *)grad_preds, out_loss, w, st);
         YB_REQUIRE(!vec_a, "yb_tal_loss: grad_preds must be 16-byte aligned when preds is");
         return launch_tal_loss<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
-                                         gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, (float *)grad_preds, out_loss, w, st);
+                                         gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, vfl, vp, (float *)grad_preds, out_loss, w, st);
     }
     const bool vec_a = tal_vec_ok<__nv_bfloat16>(preds, nullptr, n_anchors);
     const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, topk, tal_tile(dtype, vec_a));
     if (vec_a && tal_vec_ok<__nv_bfloat16>(preds, grad_preds, n_anchors))
         return launch_tal_loss<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
-                                                 gt_offsets, gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl,
+                                                 gt_offsets, gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, vfl, vp,
                                                  (__nv_bfloat16 *)grad_preds, out_loss, w, st);
     YB_REQUIRE(!vec_a, "yb_tal_loss: grad_preds must be 16-byte aligned when preds is");
     return launch_tal_loss<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
-                                             gt_offsets, gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl,
+                                             gt_offsets, gt_total, topk, tss_dev, lambda_box, lambda_cls, lambda_dfl, vfl, vp,
                                              (__nv_bfloat16 *)grad_preds, out_loss, w, st);
+}
+
+extern "C" int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                           const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                           int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls,
+                           float lambda_dfl, void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes,
+                           void *stream) {
+    return tal_loss_entry(preds, dtype, n_images, nc, reg_max, n_anchors, anchors, strides, gt, gt_offsets, gt_total, topk,
+                          tss_dev, lambda_box, lambda_cls, lambda_dfl, 0, VflParams{0.f, 0.f}, grad_preds, out_loss, workspace,
+                          workspace_bytes, stream);
+}
+
+extern "C" int yb_tal_loss_vfl(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                               const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                               int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls,
+                               float lambda_dfl, float vfl_alpha, float vfl_gamma, void *grad_preds, float *out_loss,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    YB_REQUIRE(vfl_alpha >= 0.f && vfl_gamma >= 0.f, "yb_tal_loss_vfl: vfl_alpha and vfl_gamma must be non-negative");
+    return tal_loss_entry(preds, dtype, n_images, nc, reg_max, n_anchors, anchors, strides, gt, gt_offsets, gt_total, topk,
+                          tss_dev, lambda_box, lambda_cls, lambda_dfl, 1, VflParams{vfl_alpha, vfl_gamma}, grad_preds, out_loss,
+                          workspace, workspace_bytes, stream);
 }

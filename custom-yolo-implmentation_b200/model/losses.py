@@ -200,15 +200,20 @@ class _FusedLoss(torch.autograd.Function):
 def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, anchors: torch.Tensor,
                    strides: torch.Tensor, num_classes: int, lambda_box: float, lambda_cls: float, lambda_dfl: float,
                    reg_max: int = 16, topk: int = 10, alpha: float = 0.5, beta: float = 6.0, want_grad: bool = True,
-                   want_trace: bool = False, sync_normalizer: bool = True):
+                   want_trace: bool = False, sync_normalizer: bool = True, cls_loss: str = "bce",
+                   vfl_alpha: float = 0.75, vfl_gamma: float = 2.0):
     """Task-aligned variant (``yb_tal_assign`` + ``yb_tal_loss``).  Not in the reference: specified by
     ``oracle/tal_oracle.py`` (SURVEY.md §8(a')).
 
     Between the two calls the normaliser ``sum(target scores)`` is all-reduced (SUM / world) when a
     process group is initialised and ``sync_normalizer`` is set — the path's one real exchange step.
+    ``cls_loss="vfl"`` weights the class term varifocally (``yb_tal_loss_vfl``): background cells by
+    ``vfl_alpha * sigmoid(x) ** vfl_gamma``, the positive cell of a foreground anchor by its target score.
     Returns ``(out_loss (8,) [total, box, cls, dfl, normaliser, #fg, ..], grad or None, trace)``.
     """
     _cabi.require_cuda(preds, "preds")
+    if cls_loss not in ("bce", "vfl"):
+        raise ValueError(f"cls_loss must be 'bce' or 'vfl', got {cls_loss!r}")
     n, c, a = preds.shape
     if c != 4 * reg_max + num_classes:
         raise ValueError(f"preds has {c} channels, expected 4*{reg_max} + {num_classes}")
@@ -241,11 +246,14 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
         tss = (tss / torch.distributed.get_world_size())[:1].contiguous()
     grad = torch.empty_like(x) if want_grad else None
     out = torch.empty(8, dtype=torch.float32, device=dev)
+    head = (_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr, _cabi.ptr(gt_offsets),
+            gt_total, int(topk), _cabi.ptr(tss), float(lambda_box), float(lambda_cls), float(lambda_dfl))
+    tail = (_cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     with torch.cuda.device(dev):
-        rc = lib.yb_tal_loss(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
-                             _cabi.ptr(gt_offsets), gt_total, int(topk), _cabi.ptr(tss), float(lambda_box), float(lambda_cls),
-                             float(lambda_dfl), _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(),
-                             _cabi.stream_ptr(dev))
+        if cls_loss == "vfl":
+            rc = lib.yb_tal_loss_vfl(*head, float(vfl_alpha), float(vfl_gamma), *tail)
+        else:
+            rc = lib.yb_tal_loss(*head, *tail)
     _cabi.check(rc, "yb_tal_loss")
     _cabi.count_launches(3 if gt_total else 2)
     trace = {"assigned_gt": asg, "target_score": tsc, "stats": stats} if want_trace else {}
@@ -257,7 +265,8 @@ class _FusedTalLoss(torch.autograd.Function):
     def forward(ctx, preds, gt, gt_offsets, anchors, strides, num_classes, lambdas, reg_max, tal, need, holder):
         out, grad, _ = fused_tal_loss(preds, gt, gt_offsets, anchors, strides, num_classes, lambdas[0], lambdas[1],
                                       lambdas[2], reg_max, tal["topk"], tal["alpha"], tal["beta"], want_grad=need,
-                                      sync_normalizer=tal["sync_normalizer"])
+                                      sync_normalizer=tal["sync_normalizer"], cls_loss=tal.get("cls_loss", "bce"),
+                                      vfl_alpha=tal.get("vfl_alpha", 0.75), vfl_gamma=tal.get("vfl_gamma", 2.0))
         ctx.grad = grad
         holder.append(out)
         return out[0]
@@ -287,12 +296,14 @@ class YoloDFLQFLoss(nn.Module):
     for ``training.distributed_setup.reduce_loss_stats``.
 
     ``assigner="tal"`` (not in the reference; BASELINE.json's north_star) switches to the task-aligned
-    assigner with CIoU + DFL + BCE losses (``topk``, ``alpha``, ``beta``); the dict then also carries
+    assigner with CIoU + DFL + BCE losses (``topk``, ``alpha``, ``beta``; ``cls_loss="vfl"`` weights the
+    class term varifocally with ``vfl_alpha``, ``vfl_gamma``); the dict then also carries
     ``"dfl_loss"`` and ``"box_loss"`` is the CIoU term.  Under DDP the normaliser is all-reduced.
     """
 
     def __init__(self, num_classes=171, lambda_box=1.5, lambda_cls=1.0, lambda_dfl=1.5, reg_max=16,
-                 assigner="nearest_center", topk=10, alpha=0.5, beta=6.0, sync_normalizer=True):
+                 assigner="nearest_center", topk=10, alpha=0.5, beta=6.0, sync_normalizer=True, cls_loss="bce",
+                 vfl_alpha=0.75, vfl_gamma=2.0):
         super().__init__()
         if assigner not in ("nearest_center", "tal"):
             raise ValueError(f"assigner must be 'nearest_center' (the reference's behaviour) or 'tal', got {assigner!r}")
@@ -302,7 +313,10 @@ class YoloDFLQFLoss(nn.Module):
         self.lambda_dfl = lambda_dfl
         self.reg_max = reg_max
         self.assigner = assigner
-        self.tal = {"topk": topk, "alpha": alpha, "beta": beta, "sync_normalizer": sync_normalizer}
+        if cls_loss not in ("bce", "vfl"):
+            raise ValueError(f"cls_loss must be 'bce' or 'vfl' (task-aligned variant only), got {cls_loss!r}")
+        self.tal = {"topk": topk, "alpha": alpha, "beta": beta, "sync_normalizer": sync_normalizer,
+                    "cls_loss": cls_loss, "vfl_alpha": vfl_alpha, "vfl_gamma": vfl_gamma}
         self.last_stats = None
 
     def forward(self, preds, gt_boxes_list, anchors, strides):

@@ -125,6 +125,16 @@ int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max,
                 int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl,
                 void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream);
 
+/* yb_tal_loss with the varifocal weighting of the class term (north_star "VFL-BCE"; published VFL,
+ * specified in oracle/tal_oracle.py): weight = vfl_alpha * sigmoid(x)^vfl_gamma on background cells
+ * (differentiated), = the target score on the positive cell of a foreground anchor;
+ * cls = sum(weight * BCE(x, target)) / normaliser.  out_loss[2] is that term. */
+int yb_tal_loss_vfl(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                    const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
+                    int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl,
+                    float vfl_alpha, float vfl_gamma,
+                    void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Decode.  Replaces DFL.forward (src/model/model_blocks.py:278-280), dist2bbox
  * (src/utils/model_utils.py:120-129) and the decode block of decode_predictions

@@ -20,6 +20,10 @@ Specification (SURVEY.md §8(a'), public YOLOv8-style task-aligned learning), pe
               the maxima taken over the GT's anchors after conflict resolution
   normaliser  tss = max(sum_i t_i over the whole batch, 1)   (all-reduced SUM / world under DDP)
   losses      cls  = sum BCEWithLogits(logits, T) / tss                      over all (anchor, class)
+              cls (cls_loss="vfl", the published varifocal weighting; "VFL-BCE" in the north_star)
+                   = sum w * BCEWithLogits(logits, T) / tss  with  w = vfl_alpha * sigmoid(logit)**vfl_gamma
+                     on background cells (differentiated) and w = T on the one positive cell of a
+                     foreground anchor (label 1 even when its target score is 0)
               box  = sum_fg (1 - CIoU(pred_i, gt_j)) * t_i / tss
               dfl  = sum_fg mean_4sides[CE(left)*wl + CE(right)*wr] * t_i / tss   (target clamp [0, 14.99])
               total = lambda_box * box + lambda_cls * cls + lambda_dfl * dfl
@@ -113,7 +117,8 @@ def assign_image(xyxy: torch.Tensor, cls_logits: torch.Tensor, gt: torch.Tensor,
 def tal_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torch.Tensor, strides: torch.Tensor,
                 num_classes: int, lambda_box: float = 1.5, lambda_cls: float = 1.0, lambda_dfl: float = 1.5,
                 reg_max: int = 16, topk: int = 10, alpha: float = 0.5, beta: float = 6.0,
-                tss_override: Optional[float] = None) -> TalTrace:
+                tss_override: Optional[float] = None, cls_loss: str = "bce", vfl_alpha: float = 0.75,
+                vfl_gamma: float = 2.0) -> TalTrace:
     """``tss_override`` replaces the local normaliser (DDP: the all-reduced sum / world)."""
     n = preds.shape[0]
     logits, _, xyxy, _ = decode_boxes(preds, anchors, strides, reg_max)
@@ -126,6 +131,7 @@ def tal_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torch
     tr.assigned_gt = torch.full((n, a), -1, dtype=torch.long)
     tr.target_score = torch.zeros(n, a)
     target = torch.zeros(n, a, num_classes)
+    label = torch.zeros(n, a, num_classes)
     with torch.no_grad():
         for b in range(n):
             gt = gts[b]
@@ -137,10 +143,16 @@ def tal_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torch
             tr.topk_anchor.append(tk)
             fg = asg >= 0
             target[b, fg.nonzero()[:, 0], gt[asg[fg], 4].long()] = t[fg]
+            label[b, fg.nonzero()[:, 0], gt[asg[fg], 4].long()] = 1.0
     tr.tss = float(tr.target_score.sum())
     tr.num_fg = int((tr.assigned_gt >= 0).sum())
     tss = max(tss_override if tss_override is not None else tr.tss, 1.0)
-    tr.cls = F.binary_cross_entropy_with_logits(cls, target, reduction="none").sum() / tss
+    bce = F.binary_cross_entropy_with_logits(cls, target, reduction="none")
+    if cls_loss == "vfl":
+        weight = vfl_alpha * cls.sigmoid().pow(vfl_gamma) * (1.0 - label) + target * label
+        tr.cls = (bce * weight).sum() / tss
+    else:
+        tr.cls = bce.sum() / tss
     box_sum = torch.zeros(())
     dfl_sum = torch.zeros(())
     for b in range(n):

@@ -53,6 +53,26 @@ def test_tal_matches_oracle(n, nc, imgsz, gmax, seed, topk, cuda_device):
         assert ((grad[:, :64].abs().sum(1) > 0) <= (asg >= 0)).all()
 
 
+@pytest.mark.parametrize("gamma", [2.0, 1.5])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tal_varifocal_class_loss_matches_oracle(gamma, dtype, cuda_device):
+    """cls_loss="vfl" (yb_tal_loss_vfl): same assignment, varifocally weighted class term and its gradient."""
+    preds, gts, anchors, strides = make_inputs(2, 20, 320, 40, 35, dtype=dtype)
+    out, grad, asg, tsc, stats = run_cuda(preds, gts, anchors, strides, 20, cuda_device, cls_loss="vfl", vfl_alpha=0.6,
+                                          vfl_gamma=gamma)
+    ora = T.tal_forward_backward(preds, gts, anchors, strides, 20, cls_loss="vfl", vfl_alpha=0.6, vfl_gamma=gamma)
+    if not asg.equal(ora.assigned_gt):
+        pytest.skip("assignment differs on a numerical near-tie; covered by test_tal_matches_oracle")
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for k, ref in enumerate((ora.total, ora.box, ora.cls, ora.dfl)):
+        assert abs(out[k].item() - ref.item()) <= tol * abs(ref.item()) + 1e-7, (k, out[k].item(), ref.item())
+    scale = ora.grad.abs().max().item()
+    assert (grad.float() - ora.grad.float()).abs().max().item() <= tol * scale
+    # and it is a different loss from plain BCE
+    plain = run_cuda(preds, gts, anchors, strides, 20, cuda_device)[0]
+    assert abs(plain[2].item() - out[2].item()) > 1e-3 * plain[2].item()
+
+
 def test_tal_module_api_backward_and_normaliser_override(cuda_device):
     preds, gts, anchors, strides = make_inputs(2, 80, 640, 40, 41)
     dev = cuda_device

@@ -89,6 +89,20 @@ def test_known_answer_two_gt_six_anchors():
             tgt = t[i] if (tr.assigned_gt[0, i].item() == c) else 0.0
             bce += max(x, 0) - x * tgt + math.log1p(math.exp(-abs(x)))
     assert abs(tr.cls.item() - bce / tss) < 1e-5 * bce / tss
+    # varifocal weighting of the same cells: alpha * p^gamma on background, the target score on the positive cell
+    trv = T.tal_forward(preds, gts, anchors, strides, 2, topk=2, lambda_box=1.0, lambda_cls=1.0, lambda_dfl=1.0,
+                        cls_loss="vfl", vfl_alpha=0.75, vfl_gamma=2.0)
+    vfl = 0.0
+    for i in range(6):
+        for c in range(2):
+            x = cls[i, c].item()
+            pos = tr.assigned_gt[0, i].item() == c
+            tgt = t[i] if pos else 0.0
+            cell = max(x, 0) - x * tgt + math.log1p(math.exp(-abs(x)))
+            p = 1.0 / (1.0 + math.exp(-x))
+            vfl += cell * (tgt if pos else 0.75 * p ** 2)
+    assert abs(trv.cls.item() - vfl / tss) < 1e-5 * vfl / tss
+    assert trv.assigned_gt.equal(tr.assigned_gt) and abs(trv.box.item() - tr.box.item()) < 1e-7
     # box loss
     bl = sum((1 - _ciou_scalar(box(*ctr[i]), (g0 if tr.assigned_gt[0, i] == 0 else g1))) * t[i] for i in range(6) if t[i] > 0)
     assert abs(tr.box.item() - bl / tss) < 1e-5
