@@ -11,18 +11,24 @@ agg = collections.OrderedDict()
 for row in csv.DictReader(lines):
     k = row['Kernel Name'].split('(')[0].replace('void ', '')[:60]
     agg.setdefault(k, []).append(float(row['Metric Value'].replace(',', '')) / 1e3)
-loss_k = ('fused_main_kernel', 'match_kernel', 'finalize_kernel')
-step = sum(sum(v) / len(v) for k, v in agg.items() if any(t in k for t in loss_k))
-nms_k = ('nms_scan', 'nms_class', 'nms_sort', 'nms_sweep')
-nms = sum(sum(v) / len(v) for k, v in agg.items() if any(t in k for t in nms_k))
+def mean(k): return sum(agg[k]) / len(agg[k])
+groups = collections.OrderedDict([
+    ("the cfg2 fp32 loss step", lambda k: k.startswith('yb::fused_main_kernel<float') or k.startswith('yb::match_kernel<float') or k.startswith('yb::finalize_kernel')),
+    ("the NMS step", lambda k: k.startswith('yb::nms_')),
+    ("the task-aligned step", lambda k: k.startswith('yb::tal_')),
+    ("the cfg5 bf16 loss step (+ finalize_kernel above)", lambda k: k.startswith('yb::fused_main_kernel<__nv_bfloat16') or k.startswith('yb::match_kernel<__nv_bfloat16')),
+])
+totals = {g: sum(mean(k) for k in agg if f(k)) for g, f in groups.items()}
 out = ["# Round-1 profile summary (B200, sm_100a)", "",
        "## 1. ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline`", "",
        "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` — per-launch times are cold-cache and serialised:",
        "compare SHARES, not absolutes (the CUDA-event numbers of `bench.py` are the timings). Raw list: `r1_bench_launches.csv`.", "",
        "| kernel | launches | mean µs | share |", "|---|---|---|---|"]
 for k, v in agg.items():
-    m = sum(v) / len(v)
-    share = f"{100 * m / step:.1f} % of the loss step" if any(t in k for t in loss_k) else (f"{100 * m / nms:.1f} % of the NMS step" if any(t in k for t in nms_k) else "(torch: host-side tensor prep of the bench)")
+    m = mean(k)
+    share = "(torch: host-side tensor prep of the bench)"
+    for g, f in groups.items():
+        if f(k): share = f"{100 * m / totals[g]:.1f} % of {g}"
     out.append(f"| `{k}` | {len(v)} | {m:.1f} | {share} |")
 want = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'DRAM read'), ('dram__bytes_write.sum', 'DRAM write'),
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM % (ncu peak)'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %'),
