@@ -20,12 +20,13 @@ YB_F32, YB_BF16 = 0, 1
 _lib = None
 _lock = threading.Lock()
 
-# kernels launched through this binding since import (bench.py reports the delta as gpu_launches)
-launch_count = 0
+# ``_cabi.launch_count`` (module attribute, see __getattr__ below): kernels the library has launched in
+# this process, counted inside the library at every launch site (bench.py reports the delta as gpu_launches)
 
 _SIGNATURES = {
     "yb_abi_version": (c_int, []),
     "yb_last_error": (ctypes.c_char_p, []),
+    "yb_launch_count": (ctypes.c_longlong, []),
     "yb_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "yb_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -123,6 +124,7 @@ def dtype_code(dt: torch.dtype) -> int:
     raise TypeError(f"unsupported dtype {dt}; the kernels take float32 or bfloat16 head outputs")
 
 
-def count_launches(n: int) -> None:
-    global launch_count
-    launch_count += n
+def __getattr__(name):
+    if name == "launch_count":
+        return int(lib().yb_launch_count())
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

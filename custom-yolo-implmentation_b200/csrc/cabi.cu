@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: version, thread-local error text.
 #include <cstdarg>
+#include <atomic>
 #include <cstdio>
 
 #include "common.cuh"
@@ -20,7 +21,11 @@ int cuda_fail(cudaError_t e, const char *what) {
     return YB_ERR_CUDA;
 }
 
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 }  // namespace yb
 
 extern "C" int yb_abi_version(void) { return YB_ABI_VERSION; }
 extern "C" const char *yb_last_error(void) { return yb::g_err; }
+extern "C" long long yb_launch_count(void) { return yb::g_launches.load(std::memory_order_relaxed); }

@@ -11,6 +11,7 @@ namespace yb {
 // ---- host-side error plumbing (cabi.cu) -------------------------------------------------------
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
+void note_launch();
 
 #define YB_CUDA(call)                                            \
     do {                                                         \
@@ -18,6 +19,12 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return ::yb::cuda_fail(e__, #call); \
     } while (0)
 
+// after every kernel launch: count it (yb_launch_count) and surface a launch error
+#define YB_LAUNCH_CHECK()                  \
+    do {                                   \
+        ::yb::note_launch();               \
+        YB_CUDA(cudaGetLastError());       \
+    } while (0)
 #define YB_REQUIRE(cond, ...)            \
     do {                                 \
         if (!(cond)) {                   \

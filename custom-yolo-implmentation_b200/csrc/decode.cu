@@ -239,7 +239,7 @@ static int launch_decode(const T *x, int n_images, int n_anchors, size_t image_s
         dfl_decode_kernel<T, 1><<<grid, kDecThreads, 0, st>>>(x, image_stride, n_anchors, anchors, strides, out_ltrb,
                                                               out_box, fmt == 0, scale);
     }
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -259,12 +259,12 @@ static int launch_val(const T *preds, int n_images, int nc, int n_anchors, const
         val_scan_kernel<T, 1><<<grid, kDecThreads, 0, st>>>(preds, n_ch, nc, n_anchors, conf, w.count, w.cls, w.keys,
                                                             w.a_pad);
     }
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
     YB_CUDA(cudaFuncSetAttribute(val_emit_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     val_emit_kernel<T><<<n_images, kSortThreads, smem, st>>>(preds, n_ch, n_anchors, anchors, strides, w.count, w.cls,
                                                             w.keys, w.a_pad, top_k, out_rows, out_count, out_anchor);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -304,7 +304,7 @@ extern "C" int yb_make_anchors(const int32_t *shapes_host, const float *strides_
         YB_REQUIRE(h > 0 && w > 0, "yb_make_anchors: level %d has shape (%d, %d)", l, h, w);
         anchor_level_kernel<<<(h * w + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             h, w, strides_host[l], out_grid + 2 * off, out_strides + off);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
         off += (size_t)h * w;
     }
     return YB_OK;
@@ -316,7 +316,7 @@ extern "C" int yb_dist2bbox(const float *ltrb, const float *anchors, int n_image
     YB_REQUIRE(n_images > 0 && n_anchors > 0 && n_images <= 65535, "yb_dist2bbox: bad sizes");
     dim3 grid((n_anchors + 255) / 256, n_images);
     dist2bbox_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ltrb, anchors, n_anchors, xywh, out_box);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 

@@ -68,7 +68,7 @@ static int launch_head(const HeadLevels &lv, void *packed, int n_images, int box
         dim3 grid(rows, (n_anchors + kHeadThreads * kHeadIters - 1) / (kHeadThreads * kHeadIters));
         head_tail_kernel<T, 1, GATHER><<<grid, kHeadThreads, 0, stream>>>(lv, static_cast<T *>(packed), box_ch, nc, n_anchors);
     }
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 

@@ -173,7 +173,7 @@ extern "C" int yb_xywh2xyxy(const float *in, size_t n_boxes, float *out, void *s
     }
     xywh2xyxy_kernel<<<(unsigned)((n_boxes + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         (const float4 *)in, n_boxes, (float4 *)out);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -189,7 +189,7 @@ extern "C" int yb_bbox_iou(const float *box1, const float *box2, int m, float *o
     }
     bbox_iou_kernel<<<(m + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         (const float4 *)box1, (const float4 *)box2, m, out_iou, grad_out, (float4 *)grad_box1);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -207,7 +207,7 @@ static int pairwise(const float *box1, int n, const float *box2, int m, float ep
         box_iou_kernel<true><<<grid, 256, 0, st>>>((const float4 *)box1, n, (const float4 *)box2, m, eps, out);
     else
         box_iou_kernel<false><<<grid, 256, 0, st>>>((const float4 *)box1, n, (const float4 *)box2, m, eps, out);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -236,9 +236,9 @@ extern "C" int yb_quality_focal_loss(const float *pred_scores, const float *targ
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float inv_m = 1.f / (float)m;
     qfl_dense_kernel<<<blocks, kQflThreads, 0, st>>>(pred_scores, target_scores, n, inv_m, grad_scores, (float *)workspace);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     qfl_finish_kernel<<<1, 256, 0, st>>>((const float *)workspace, blocks, inv_m, out_loss);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -247,6 +247,6 @@ extern "C" int yb_distribution_focal_loss(const float *pred_dist, const float *t
     YB_REQUIRE(pred_dist && target && out_loss, "yb_distribution_focal_loss: null pointer");
     YB_REQUIRE(m > 0 && r > 1, "yb_distribution_focal_loss: bad sizes");
     dfl_rows_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred_dist, target, m, r, out_loss, grad_dist);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }

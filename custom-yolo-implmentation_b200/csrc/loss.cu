@@ -43,6 +43,12 @@ namespace yb {
 #ifndef YB_SCAN_UNROLL
 #define YB_SCAN_UNROLL 4
 #endif
+#ifndef YB_ASSIGN_PRUNE
+#define YB_ASSIGN_PRUNE 1
+#endif
+#ifndef YB_COARSE_FIRST
+#define YB_COARSE_FIRST 1
+#endif
 constexpr int kScanUnroll = YB_SCAN_UNROLL;
 constexpr int kAssignThreads = YB_ASSIGN_THREADS;
 constexpr int kClsThreads = YB_CLS_THREADS;
@@ -104,6 +110,10 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
     // predicted centres of the tile's anchors, structure-of-arrays so that four anchors are one LDS.128
     __shared__ __align__(16) float s_x[TILE4], s_y[TILE4], s_p[TILE4];     // cx, cy, cx^2 + cy^2
     __shared__ unsigned long long s_key[kAssignThreads];
+    __shared__ float s_ext[4][kAssignThreads / 32];        // per warp: extent of the predicted centres
+    __shared__ int s_list[2 * kAssignThreads];             // GTs (image-local index) that still need this tile
+    __shared__ int s_cnt[kAssignThreads / 32];
+    float lo_x = __int_as_float(0x7f800000), lo_y = lo_x, hi_x = -lo_x, hi_y = -lo_x;
 
     const int tile0 = tile * TILE;
     const int a0 = tile0 + threadIdx.x * VW;
@@ -155,6 +165,8 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
                 s_x[threadIdx.x * VW + v] = b.cx;
                 s_y[threadIdx.x * VW + v] = b.cy;
                 s_p[threadIdx.x * VW + v] = __fadd_rn(__fmul_rn(b.cx, b.cx), __fmul_rn(b.cy, b.cy));
+                lo_x = fminf(lo_x, b.cx); hi_x = fmaxf(hi_x, b.cx);
+                lo_y = fminf(lo_y, b.cy); hi_y = fmaxf(hi_y, b.cy);
             }
         }
     } else if (m_img > 0) {
@@ -177,23 +189,79 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
         s_y[TILE + threadIdx.x] = 0.f;
         s_p[TILE + threadIdx.x] = __int_as_float(0x7f800000);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
+        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+        hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+        hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_ext[0][threadIdx.x >> 5] = lo_x; s_ext[1][threadIdx.x >> 5] = lo_y;
+        s_ext[2][threadIdx.x >> 5] = hi_x; s_ext[3][threadIdx.x >> 5] = hi_y;
+    }
     __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kAssignThreads / 32; ++w) {
+        lo_x = fminf(lo_x, s_ext[0][w]); lo_y = fminf(lo_y, s_ext[1][w]);
+        hi_x = fmaxf(hi_x, s_ext[2][w]); hi_y = fmaxf(hi_y, s_ext[3][w]);
+    }
+    // largest |p|^2 of the tile, for the rounding bound of the matmul-form distance
+    const float pn_max = fmaxf(lo_x * lo_x, hi_x * hi_x) + fmaxf(lo_y * lo_y, hi_y * hi_y);
 
     const int tile_n = min(TILE, n_anchors - tile0);
     const int tile_n4 = (tile_n + 3) & ~3;                 // entries in [tile_n, tile_n4) are at infinity
-    // GT chunks of up to 128: thread <-> one GT; when the chunk is small the anchors of the tile are
-    // split into slices so that all warps have work.  Lanes of a warp share the slice, so every
-    // shared-memory read below is a broadcast.  Four anchors per step, evaluated as two packed pairs.
-    for (int g0 = 0; g0 < m_img; g0 += kAssignThreads) {
-        const int m_chunk = min(kAssignThreads, m_img - g0);
+    // GTs are tested 128 at a time and the survivors appended to s_list; whenever 128 survivors are waiting
+    // (or the GTs are exhausted) they are scanned as one chunk: thread <-> one GT; when the chunk is small
+    // the anchors of the tile are split into slices so that all warps have work.  Lanes of a warp share
+    // the slice, so every shared-memory read below is a broadcast.  Four anchors per step, two packed pairs.
+    int count = 0, g0 = 0;                                  // uniform
+    while (g0 < m_img || count > 0) {
+        while (g0 < m_img && count < kAssignThreads) {
+            // Which GTs can still find (or tie) their nearest centre in this tile?  `best` holds what the
+            // CTAs that already finished found; a GT whose distance to the extent of this tile's centres
+            // exceeds that (with the rounding of the matmul-form d^2 and of the sqrt on its side) cannot.
+            // Exact whatever the timing: a stale or empty entry only means less pruning.
+            const int gi = g0 + threadIdx.x;
+            bool need = gi < m_img;
+#if YB_ASSIGN_PRUNE
+            if (need) {
+                const unsigned long long kinv = __ldcg(best + g_begin + gi);
+                if (kinv != 0ull) {
+                    const float gx = __ldg(gt + (size_t)(g_begin + gi) * 5 + 0);
+                    const float gy = __ldg(gt + (size_t)(g_begin + gi) * 5 + 1);
+                    const float sb = __uint_as_float((unsigned int)((~kinv) >> 32)) * 1.000001f;
+                    const float dx = fmaxf(fmaxf(lo_x - gx, gx - hi_x), 0.f), dy = fmaxf(fmaxf(lo_y - gy, gy - hi_y), 0.f);
+                    const float lb2 = (dx * dx + dy * dy) * 0.999999f;
+                    need = !(lb2 > fmaf(sb * sb, 1.000001f, 1e-6f * (gx * gx + gy * gy + pn_max)));
+                }
+            }
+#endif
+            const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+            if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(need_mask);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kAssignThreads / 32; ++w) {
+                before += w < (int)(threadIdx.x >> 5) ? s_cnt[w] : 0;
+                total += s_cnt[w];
+            }
+            if (need) s_list[count + before + __popc(need_mask & ((1u << (threadIdx.x & 31)) - 1u))] = gi;
+            count += total;
+            g0 += kAssignThreads;
+            __syncthreads();
+        }
+        if (count == 0) break;                              // uniform: nobody (else) needs this tile
+        const int m_chunk = min(count, kAssignThreads);
         const int m_pad = (m_chunk + 31) & ~31;
         const int n_slice = kAssignThreads / m_pad;
         const int g = threadIdx.x % m_pad;
         const int slice = threadIdx.x / m_pad;
         unsigned long long key = kNoKey;
         if (g < m_chunk && slice < n_slice) {
-            const float gx = __ldg(gt + (size_t)(g_begin + g0 + g) * 5 + 0);
-            const float gy = __ldg(gt + (size_t)(g_begin + g0 + g) * 5 + 1);
+            const int gl = s_list[g];
+            const float gx = __ldg(gt + (size_t)(g_begin + gl) * 5 + 0);
+            const float gy = __ldg(gt + (size_t)(g_begin + gl) * 5 + 1);
             // ATen _euclidean_dist: [-2gx, -2gy, |g|^2, 1] . [px, py, 1, |p|^2], K = 4, FMA chain k = 0..3
             const float c0 = __fmul_rn(-2.f, gx), c1 = __fmul_rn(-2.f, gy);
             const float gn = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
@@ -255,8 +323,13 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
             }
             // smallest (distance, anchor) wins == first-min argmin; stored inverted so that the
             // workspace can be armed with a plain memset(0).
-            if (k != kNoKey) atomicMax(best + g_begin + g0 + threadIdx.x, ~k);
+            if (k != kNoKey) atomicMax(best + g_begin + s_list[threadIdx.x], ~k);
         }
+        const int rest = count - m_chunk;                   // < kAssignThreads survivors still waiting
+        const int carry = (int)threadIdx.x < rest ? s_list[m_chunk + threadIdx.x] : 0;
+        __syncthreads();
+        if ((int)threadIdx.x < rest) s_list[threadIdx.x] = carry;
+        count = rest;
         __syncthreads();
     }
 }
@@ -708,18 +781,35 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
 #endif
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kAssignThreads, YB_FUSED_MINBLOCKS ? YB_FUSED_MINBLOCKS : (VW == 8 ? 5 : 6))
-fused_main_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, int n_tiles, const float *__restrict__ anchors,
+fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc, int n_tiles, int coarse,
+                  const float *__restrict__ anchors,
                   const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
                   unsigned long long *__restrict__ best, int *__restrict__ gt_img, float k_cls, T *__restrict__ grad,
                   float *__restrict__ part) {
     static_assert(kAssignThreads == kClsThreads, "roles share one block shape");
     constexpr int ROLES = 1 + YB_CLS_CSPLIT;
-    const int tile = blockIdx.x / ROLES, role = blockIdx.x % ROLES;
+    // Launch order: first the `coarse` LAST tiles of every image (image-major), then the other tiles
+    // (image-major again).  Roles of a tile stay adjacent, so every SM holds a mix of box and class CTAs.
+    int id = blockIdx.x, image, tile, role;
+    {
+        const int per_c = coarse * ROLES, per_f = (n_tiles - coarse) * ROLES;
+        if (id < per_c * n_images) {
+            image = id / per_c;
+            id -= image * per_c;
+            tile = n_tiles - coarse + id / ROLES;
+        } else {
+            id -= per_c * n_images;
+            image = id / per_f;
+            id -= image * per_f;
+            tile = id / ROLES;
+        }
+        role = id % ROLES;
+    }
     if (role == 0)
-        assign_body<T, VW>(blockIdx.y, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
+        assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
                            WRITE_GRAD ? grad : nullptr);
     else
-        cls_body<T, VW, WRITE_GRAD>(blockIdx.y, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
+        cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
                                     part);
 }
 
@@ -786,25 +876,35 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(0, st)) return rc;
     if (fused_layout()) {
-        dim3 grid(n_tiles * (1 + cls_split), n_images);
+        // Block order: first the last quarter of the tiles of every image -- the coarse pyramid levels (P4 + P5
+        // hold 23.8 % of a three-level grid's anchors), whose anchors lie within a cell or two of every GT --
+        // then the rest, where assign_body prunes every (GT, tile) pair that cannot beat the distance already
+        // published in `best`.  The result never depends on what has been published (see assign_body).
+        int coarse = 0;
+#if YB_COARSE_FIRST && YB_ASSIGN_PRUNE
+        if (gt_total > 0 && n_tiles >= 4) coarse = (n_tiles * 61 + 255) / 256;          // ceil(0.238 n_tiles)
+#endif
+        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images;
+        YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
         if (grad != nullptr)
-            fused_main_kernel<T, VW, true><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, nc, n_tiles, anchors, strides,
-                                                                            gt, gt_off, w.best, w.gt_img, k_cls, grad, w.part);
+            fused_main_kernel<T, VW, true><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
+                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, grad,
+                w.part);
         else
-            fused_main_kernel<T, VW, false><<<grid, kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, nc, n_tiles, anchors,
-                                                                             strides, gt, gt_off, w.best, w.gt_img, k_cls, grad,
-                                                                             w.part);
-        YB_CUDA(cudaGetLastError());
+            fused_main_kernel<T, VW, false><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
+                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, grad,
+                w.part);
+        YB_LAUNCH_CHECK();
     } else {
         assign_kernel<T, VW><<<dim3(n_tiles, n_images), kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt,
                                                                                  gt_off, w.best, w.gt_img, grad);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
         dim3 grid(n_tiles, n_images, cls_split);
         if (grad != nullptr)
             cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
         else
             cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     if (int rc = stage_mark(1, st)) return rc;
     if (gt_total > 0) {
@@ -812,7 +912,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         match_kernel<T><<<(gt_total + per_cta - 1) / per_cta, kMatchThreads, 0, st>>>(
             preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.gt_img, gt_total, w.best, k_dfl_num, k_cls,
             grad, w.m_dfl, w.m_dcls, w.m_idx, out_idx, out_iou);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     if (int rc = stage_mark(2, st)) return rc;
     {
@@ -820,7 +920,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         finalize_kernel<<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
             n_images, n_anchors, cls_tiles, gt_off, w.part, w.m_dfl, w.m_dcls, w.m_idx, lambda_cls, lambda_dfl, w.img_terms,
             w.ticket, out_loss, out_per_image);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     if (int rc = stage_mark(3, st)) return rc;
     return YB_OK;
@@ -909,7 +1009,7 @@ extern "C" int yb_scale_grad(void *grad, int dtype, size_t n_elements, const flo
         scale_kernel<float><<<blocks, 256, 0, st>>>((float *)grad, n_elements, scale);
     else
         scale_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16 *)grad, n_elements, scale);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 

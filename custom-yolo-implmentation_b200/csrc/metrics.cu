@@ -140,6 +140,6 @@ extern "C" int yb_detection_match(const float *pred_rows, int row_stride, const 
     detection_match_kernel<<<(n_images + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         pred_rows, row_stride, pred_count, pred_scores, score_threshold, gt, gt_offsets, n_images, nc, iou_threshold,
         reinterpret_cast<unsigned long long *>(counters));
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }

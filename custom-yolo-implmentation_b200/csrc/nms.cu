@@ -787,7 +787,7 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
         nms_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(prediction, nc, n_anchors, conf_thres, class_filter,
                                                           n_class_filter, w.count, w.cls, w.keys, w.a_pad);
     }
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     if (!agnostic && nc <= kClassMaxNc && n_anchors < (1 << kAnchorBits) && max_det <= kClassMaxDet) {
         const size_t csmem = sizeof(float4) * (size_t)kClassCap;      // boxes; later keys + histogram + selection
         YB_CUDA(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
@@ -796,13 +796,13 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
         nms_class_kernel<<<dim3(split, n_images), kClassThreads, csmem, st>>>(
             prediction, nc, n_anchors, w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det,
             w.mode, out_rows, out_count, out_anchor);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     // generic path for whatever the class-parallel kernel left (mode == 0)
     const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
     YB_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_sort_kernel<<<n_images, kSortThreads, smem, st>>>(w.count, w.mode, w.keys, w.a_pad);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     if (n_anchors <= kRegCols * kSortThreads)
         nms_sweep_kernel<true><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
                                                                   w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
@@ -811,6 +811,6 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
         nms_sweep_kernel<false><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
                                                                    w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
                                                                    out_count, out_anchor);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }

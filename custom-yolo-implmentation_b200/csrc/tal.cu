@@ -748,17 +748,17 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
         YB_CUDA(cudaFuncSetAttribute(tal_candidates_kernel<T, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tal_candidates_kernel<T, VW><<<grid, kTalThreads, smem, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
                                                                      topk, alpha, beta, w.cand_count, w.cand, w.cand_cap);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
         const int blocks = (gt_total + 3) / 4;
         tal_select_kernel<<<blocks, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, topk, w.cand_count, w.cand,
                                                   w.cand_cap, w.sel, w.sel_count, w.akey);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
         tal_resolve_kernel<<<blocks, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, w.akey, w.sel, w.sel_count,
                                                    w.g_tsum, w.g_npos, w.aslot, topk, out_assigned, out_tscore);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     tal_stats_kernel<<<1, 256, 0, st>>>(gt_total, w.g_tsum, w.g_npos, out_stats);
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
@@ -774,7 +774,7 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
                                                          gt_total, topk, w.sel, w.sel_count, tss_dev, lambda_box, lambda_cls,
                                                          lambda_dfl, vfl, vp, grad != nullptr, w.fgrad, w.fcell_off, w.fcell_val,
                                                          w.fg_box, w.fg_dfl, w.fg_cls);
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     {
         constexpr int TILE = kTalThreads * VW;
@@ -785,7 +785,7 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
         if (grad != nullptr) { if (vfl) YB_TAL_CLS(true, true); else YB_TAL_CLS(true, false); }
         else { if (vfl) YB_TAL_CLS(false, true); else YB_TAL_CLS(false, false); }
 #undef YB_TAL_CLS
-        YB_CUDA(cudaGetLastError());
+        YB_LAUNCH_CHECK();
     }
     {
         const int n_part = n_images * w.cls_tiles, n_slots = gt_total * topk;
@@ -796,7 +796,7 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
                                                                   lambda_box, lambda_cls, lambda_dfl, w.cta_sums, w.ticket,
                                                                   out_loss);
     }
-    YB_CUDA(cudaGetLastError());
+    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 

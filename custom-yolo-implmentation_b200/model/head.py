@@ -63,7 +63,6 @@ class _GatherLevels(torch.autograd.Function):
                                                 _cabi.dtype_code(out.dtype), n, box_ch, nc, _cabi.ptr(out),
                                                 _cabi.stream_ptr(dev))
             _cabi.check(rc, "yb_head_gather")
-            _cabi.count_launches(1)
         ctx.meta = (n_levels, n, box_ch, nc, hw, [tuple(t.shape) for t in levels])
         return out
 
@@ -79,7 +78,6 @@ class _GatherLevels(torch.autograd.Function):
                                                  box_ch, nc, _pointer_table(grads[:n_levels]),
                                                  _pointer_table(grads[n_levels:]), _cabi.stream_ptr(grad.device))
             _cabi.check(rc, "yb_head_scatter")
-            _cabi.count_launches(1)
         return (None, *grads)
 
 

@@ -165,7 +165,6 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
                                  _cabi.ptr(idx), _cabi.ptr(iou), _cabi.ptr(per_image), _cabi.ptr(ws), ws.numel(),
                                  _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_loss_fwd_bwd")
-    _cabi.count_launches(3 if gt_total else 2)
     return out, grad, trace
 
 
@@ -193,7 +192,6 @@ class _FusedLoss(torch.autograd.Function):
             rc = _cabi.lib().yb_scale_grad(_cabi.ptr(g), _cabi.dtype_code(g.dtype), g.numel(), _cabi.ptr(scale),
                                            _cabi.stream_ptr(g.device))
         _cabi.check(rc, "yb_scale_grad")
-        _cabi.count_launches(1)
         return (g,) + (None,) * 11
 
 
@@ -237,7 +235,6 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
                                _cabi.ptr(gt_offsets), gt_total, int(topk), float(alpha), float(beta), _cabi.ptr(stats),
                                _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_tal_assign")
-    _cabi.count_launches(4 if gt_total else 1)
     tss = stats[:1]
     if sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
             and torch.distributed.get_world_size() > 1:
@@ -255,7 +252,6 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
         else:
             rc = lib.yb_tal_loss(*head, *tail)
     _cabi.check(rc, "yb_tal_loss")
-    _cabi.count_launches(3 if gt_total else 2)
     trace = {"assigned_gt": asg, "target_score": tsc, "stats": stats} if want_trace else {}
     return out, grad, trace
 
@@ -282,7 +278,6 @@ class _FusedTalLoss(torch.autograd.Function):
             rc = _cabi.lib().yb_scale_grad(_cabi.ptr(g), _cabi.dtype_code(g.dtype), g.numel(), _cabi.ptr(scale),
                                            _cabi.stream_ptr(g.device))
         _cabi.check(rc, "yb_scale_grad")
-        _cabi.count_launches(1)
         return (g,) + (None,) * 10
 
 
@@ -368,7 +363,6 @@ class _BboxIou(torch.autograd.Function):
                 rc = _cabi.lib().yb_bbox_iou(_cabi.ptr(b1), _cabi.ptr(b2), b1.shape[0], _cabi.ptr(out), None, None,
                                              _cabi.stream_ptr(b1.device))
             _cabi.check(rc, "yb_bbox_iou")
-            _cabi.count_launches(1)
         ctx.save_for_backward(b1, b2)
         ctx.in_dtype = box1.dtype
         return out
@@ -384,7 +378,6 @@ class _BboxIou(torch.autograd.Function):
                 rc = _cabi.lib().yb_bbox_iou(_cabi.ptr(b1), _cabi.ptr(b2), b1.shape[0], _cabi.ptr(scratch),
                                              _cabi.ptr(go), _cabi.ptr(g1), _cabi.stream_ptr(b1.device))
             _cabi.check(rc, "yb_bbox_iou")
-            _cabi.count_launches(1)
         return g1.to(ctx.in_dtype), None
 
 
@@ -415,7 +408,6 @@ class _Qfl(torch.autograd.Function):
             rc = lib.yb_quality_focal_loss(_cabi.ptr(x), _cabi.ptr(t), m, c, float(beta), _cabi.ptr(out),
                                            _cabi.ptr(grad), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(x.device))
         _cabi.check(rc, "yb_quality_focal_loss")
-        _cabi.count_launches(2)
         ctx.grad = grad
         ctx.in_dtype = pred_scores.dtype
         return out[0]
@@ -448,7 +440,6 @@ class _Dfl(torch.autograd.Function):
             rc = _cabi.lib().yb_distribution_focal_loss(_cabi.ptr(x), _cabi.ptr(t), m, r, _cabi.ptr(out),
                                                         _cabi.ptr(grad), _cabi.stream_ptr(x.device))
         _cabi.check(rc, "yb_distribution_focal_loss")
-        _cabi.count_launches(1)
         ctx.grad = grad
         ctx.in_dtype = pred_dist.dtype
         return out[0]

@@ -43,7 +43,6 @@ def dfl_decode(box_logits: torch.Tensor, anchors=None, strides=None, reg_max: in
                                            1 if box_format == "xyxy" else 0, int(bool(scale_by_stride and box_format)),
                                            _cabi.stream_ptr(dev))
         _cabi.check(rc, "yb_dfl_decode")
-        _cabi.count_launches(1)
     return ltrb, box
 
 

@@ -37,7 +37,6 @@ def box_iou_batch(boxes1: torch.Tensor, boxes2: torch.Tensor) -> torch.Tensor:
             rc = _cabi.lib().yb_box_iou_batch(_cabi.ptr(b1[lo:hi]), hi - lo, _cabi.ptr(b2), m, _cabi.ptr(out[lo:hi]),
                                               _cabi.stream_ptr(b1.device))
         _cabi.check(rc, "yb_box_iou_batch")
-        _cabi.count_launches(1)
     return out.to(boxes1.dtype)
 
 
@@ -104,7 +103,6 @@ class DetectionMetrics:
                                                 _cabi.ptr(gt_offsets), int(gmax), n, self.num_classes,
                                                 float(self.iou_threshold), _cabi.ptr(c), _cabi.stream_ptr(dev))
         _cabi.check(rc, "yb_detection_match")
-        _cabi.count_launches(1)
 
     def update(self, predictions: torch.Tensor, targets: torch.Tensor, pred_scores: torch.Tensor = None,
                score_threshold: float = 0.5):

@@ -34,7 +34,6 @@ def decode_predictions_raw(preds, anchors, strides, conf_threshold=0.25, top_k=1
                                _cabi.ptr(st), float(conf_threshold), int(top_k), _cabi.ptr(rows), _cabi.ptr(count),
                                _cabi.ptr(anchor), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_val_decode")
-    _cabi.count_launches(2)
     return rows, count, anchor
 
 

@@ -48,7 +48,6 @@ def make_anchors(x: List[torch.Tensor], strides: Sequence, offset: float = 0.5):
             rc = _cabi.lib().yb_make_anchors(_cabi.ctypes.c_void_p(hs.data_ptr()), _cabi.ctypes.c_void_p(ss.data_ptr()),
                                              len(shapes), _cabi.ptr(grid), _cabi.ptr(st), _cabi.stream_ptr(device))
         _cabi.check(rc, "yb_make_anchors")
-        _cabi.count_launches(len(shapes))
         # integer cell indices -> dtype, then + offset in dtype: the reference's rounding sequence
         hit = (grid.to(dtype) + offset, st.to(dtype))
         _anchor_cache[key] = hit
@@ -85,7 +84,6 @@ def dist2bbox(distance, anchor_points, xywh=True, dim=-1):
             rc = _cabi.lib().yb_dist2bbox(_cabi.ptr(ltrb), _cabi.ptr(anc), ltrb.shape[0], a, int(bool(xywh)),
                                           _cabi.ptr(out), _cabi.stream_ptr(d.device))
         _cabi.check(rc, "yb_dist2bbox")
-        _cabi.count_launches(1)
     out = out.reshape(*lead, 4, a).to(distance.dtype)
     return out.movedim(-2, dim) if dim != nd - 2 else out
 
@@ -106,7 +104,6 @@ def box_iou(box1, box2, eps=1e-7):
             rc = _cabi.lib().yb_box_iou(_cabi.ptr(b1[lo:hi]), hi - lo, _cabi.ptr(b2), m, float(eps), _cabi.ptr(out[lo:hi]),
                                         _cabi.stream_ptr(b1.device))
         _cabi.check(rc, "yb_box_iou")
-        _cabi.count_launches(1)
     return out.to(box1.dtype)
 
 
@@ -121,7 +118,6 @@ def xywh2xyxy(x):
         with torch.cuda.device(x.device):
             rc = _cabi.lib().yb_xywh2xyxy(_cabi.ptr(src), n, _cabi.ptr(out), _cabi.stream_ptr(x.device))
         _cabi.check(rc, "yb_xywh2xyxy")
-        _cabi.count_launches(1)
     return out.to(x.dtype)
 
 
@@ -153,7 +149,6 @@ def batched_nms_raw(prediction: torch.Tensor, conf_thres: float, iou_thres: floa
                         _cabi.ptr(filt), 0 if filt is None else filt.numel(), _cabi.ptr(rows), _cabi.ptr(count),
                         _cabi.ptr(anchor), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_nms")
-    _cabi.count_launches(3)
     return rows, count, anchor
 
 

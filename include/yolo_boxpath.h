@@ -43,6 +43,8 @@ typedef enum {
 
 int yb_abi_version(void);
 const char *yb_last_error(void);
+/* Kernels this library has launched in this process so far (bench.py reports the delta as gpu_launches). */
+long long yb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Training: fused decode + nearest-centre assignment + DFL/QFL loss + backward.
