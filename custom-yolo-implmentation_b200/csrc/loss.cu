@@ -104,7 +104,7 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
                                             const float *__restrict__ anchors, const float *__restrict__ strides,
                                             const float *__restrict__ gt, const int *__restrict__ gt_off,
                                             unsigned long long *__restrict__ best, int *__restrict__ gt_img,
-                                            T *__restrict__ grad) {
+                                            T *__restrict__ grad, bool prune) {
     constexpr int TILE = kAssignThreads * VW;
     constexpr int TILE4 = (TILE + 3) & ~3;
     // predicted centres of the tile's anchors, structure-of-arrays so that four anchors are one LDS.128
@@ -225,7 +225,7 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
             const int gi = g0 + threadIdx.x;
             bool need = gi < m_img;
 #if YB_ASSIGN_PRUNE
-            if (need) {
+            if (need && prune) {
                 const unsigned long long kinv = __ldcg(best + g_begin + gi);
                 if (kinv != 0ull) {
                     const float gx = __ldg(gt + (size_t)(g_begin + gi) * 5 + 0);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kAssignThreads, YB_ASSIGN_MINBLOCKS ? YB_ASSIG
 assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
               const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
               unsigned long long *__restrict__ best, int *__restrict__ gt_img, T *__restrict__ grad) {
-    assign_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img, grad);
+    assign_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img, grad, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -790,6 +790,8 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     constexpr int ROLES = 1 + YB_CLS_CSPLIT;
     // Launch order: first the `coarse` LAST tiles of every image (image-major), then the other tiles
     // (image-major again).  Roles of a tile stay adjacent, so every SM holds a mix of box and class CTAs.
+    const bool prune = coarse >= 0;                        // coarse < 0: YB_ASSIGN_PRUNE=0 in the environment (tests)
+    coarse = max(coarse, 0);
     int id = blockIdx.x, image, tile, role;
     {
         const int per_c = coarse * ROLES, per_f = (n_tiles - coarse) * ROLES;
@@ -807,7 +809,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     }
     if (role == 0)
         assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
-                           WRITE_GRAD ? grad : nullptr);
+                           WRITE_GRAD ? grad : nullptr, prune);
     else
         cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
                                     part);
@@ -884,6 +886,10 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
 #if YB_COARSE_FIRST && YB_ASSIGN_PRUNE
         if (gt_total > 0 && n_tiles >= 4) coarse = (n_tiles * 61 + 255) / 256;          // ceil(0.238 n_tiles)
 #endif
+        {   // YB_ASSIGN_PRUNE=0 switches the pruning (and the coarse-first order) off: the exactness tests compare both
+            const char *e = getenv("YB_ASSIGN_PRUNE");
+            if (e && e[0] == '0') coarse = -1;
+        }
         const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images;
         YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
         if (grad != nullptr)

@@ -257,3 +257,27 @@ def test_fused_loss_is_cuda_graph_capturable(cuda_device):
     torch.cuda.synchronize()
     chk_out, chk_grad, _ = P.fused_loss(x, gt, off, max(counts), a, s, 80, 1.0, 1.5)
     assert torch.equal(out, chk_out) and torch.equal(grad, chk_grad)
+
+
+@pytest.mark.parametrize("n,imgsz,gmax,dtype,seed", [
+    (3, 1280, 300, torch.bfloat16, 61),        # cfg5 shape: 33 tiles, three GT chunks per image
+    (2, 1280, 300, torch.float32, 62),         # 66 tiles
+    (4, 640, 100, torch.float32, 63),          # cfg2 shape
+    (2, 640, 500, torch.float32, 64),          # more survivors than one chunk holds
+])
+def test_tile_pruning_never_changes_the_result(n, imgsz, gmax, dtype, seed, cuda_device, monkeypatch):
+    """The box role skips (GT, tile) pairs that cannot beat the distance already published (csrc/loss.cu,
+    assign_body).  That must be invisible: matched anchors, IoUs, loss terms and the gradient are bit-identical
+    with the pruning switched off (YB_ASSIGN_PRUNE=0), at sizes where almost every pair is pruned."""
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, 80, imgsz, gmax, seed, dtype=dtype)
+    monkeypatch.setenv("YB_ASSIGN_PRUNE", "0")
+    ref = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
+    monkeypatch.delenv("YB_ASSIGN_PRUNE")
+    for _ in range(3):                          # what is pruned depends on CTA timing; the result must not
+        got = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
+        assert torch.equal(got[0], ref[0])
+        assert torch.equal(got[1], ref[1])
+        for a, b in zip(got[2], ref[2]):
+            assert torch.equal(a, b)
+        for a, b in zip(got[3], ref[3]):
+            assert torch.equal(a, b)
