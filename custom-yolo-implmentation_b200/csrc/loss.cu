@@ -1,15 +1,19 @@
 // Fused decode + nearest-centre assignment + DFL/QFL loss + backward (sm_100a).
 //
 // Replaces YoloDFLQFLoss.forward and its autograd backward (src/model/losses.py:93-281).
-// Three launches per step (the last two are tiny; assign + class pass share one launch, see fused_main_kernel), every head-output byte read once and every gradient byte written once;
-// the (M x A) distance matrix, the decoded boxes and the dense (A x nc) QFL target never exist:
+// Three launches per step (the last two are tiny), every head-output byte read once and every gradient
+// byte written once; the (M x A) distance matrix, the decoded boxes and the dense (A x nc) QFL target
+// never exist:
 //
-//   assign_kernel    reads the 4*16 box channels (128-bit loads), decodes each anchor's predicted
-//                    centre, scans it against the image's GT centres (one GT per thread, anchors
-//                    streamed from shared memory), merges the per-CTA winners with a 64-bit
-//                    atomicMax on (distance, anchor) keys, and zero-fills the box-channel gradient.
-//   cls_loss_kernel  reads the nc class channels: QFL loss + gradient of every cell for target 0
-//                    (all but <= one cell per GT), per-CTA partial sums.  Independent of the matching.
+//   fused_main_kernel  one launch whose CTAs alternate between two roles (YB_LAYOUT=split runs them as the
+//                      separate kernels assign_kernel / cls_loss_kernel):
+//     box role    reads the 4*16 box channels (128-bit loads), decodes each anchor's predicted centre,
+//                 zero-fills the box-channel gradient, drops the GTs that cannot find their nearest centre
+//                 in this tile (extent of the tile's centres vs the distance already published), scans the
+//                 rest (one GT per thread, anchors streamed from shared memory) and merges the per-CTA
+//                 winners with a 64-bit atomicMax on (distance, anchor) keys.
+//     class role  reads the nc class channels: QFL loss + gradient of every cell for target 0 (all but
+//                 <= one cell per GT), per-CTA partial sums.  Independent of the matching.
 //   match_kernel     one half-warp per GT: gathers the 64 logits of the matched anchor, DFL loss and its
 //                    gradient, IoU soft target (reference formula, slip included) and the gradient
 //                    that flows through it, duplicate-anchor resolution; corrects the one positive
@@ -145,11 +149,7 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
                         float x[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
-#ifdef YB_ASSIGN_NODECODE
-                        DflPartial ph; ph.o = x[0] + x[7]; ph.s = x[1] + x[2] + x[3]; ph.w = x[4] + x[5] + x[6];
-#else
                         const DflPartial ph = dfl_half8(x, h * 8);
-#endif
                         if (h == 0) part[v] = ph;
                         else dist[side][v] = dfl_merge(part[v], ph);
                     }
@@ -179,11 +179,6 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
         }
     }
     if (m_img == 0) return;                                // uniform per CTA
-#ifdef YB_ASSIGN_NOSCAN
-    __syncthreads();
-    if (threadIdx.x == 0 && s_x[5] + s_y[77] + s_p[300] == 12345.f) best[0] = 1;   // keep the decode alive
-    return;
-#endif
     if (TILE4 != TILE && threadIdx.x < TILE4 - TILE) {
         s_x[TILE + threadIdx.x] = 0.f;
         s_y[TILE + threadIdx.x] = 0.f;
@@ -684,10 +679,6 @@ __device__ __noinline__ void qfl_bg_slow(float x, float k_cls, float &term, floa
 template <typename T, int VW>
 __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cls, f32x2 k2, f32x2 &acc2, float &fix,
                                              float (&g)[VW]) {
-#ifdef YB_CLS_NOMATH
-    for (int v = 0; v < VW; ++v) g[v] = row.get(v) * k_cls;
-    return;
-#endif
     if constexpr (VW == 1) {
         float q0, q1, t0, t1, g1;
         f32x2 dummy = pack2(0.f, 0.f);
