@@ -50,6 +50,9 @@ namespace yb {
 #ifndef YB_ASSIGN_PRUNE
 #define YB_ASSIGN_PRUNE 1
 #endif
+#ifndef YB_COARSE_FRAC256
+#define YB_COARSE_FRAC256 61
+#endif
 #ifndef YB_COARSE_FIRST
 #define YB_COARSE_FIRST 1
 #endif
@@ -875,7 +878,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         // published in `best`.  The result never depends on what has been published (see assign_body).
         int coarse = 0;
 #if YB_COARSE_FIRST && YB_ASSIGN_PRUNE
-        if (gt_total > 0 && n_tiles >= 4) coarse = (n_tiles * 61 + 255) / 256;          // ceil(0.238 n_tiles)
+        if (gt_total > 0 && n_tiles >= 4) coarse = (n_tiles * YB_COARSE_FRAC256 + 255) / 256;   // ceil(0.238 n_tiles)
 #endif
         {   // YB_ASSIGN_PRUNE=0 switches the pruning (and the coarse-first order) off: the exactness tests compare both
             const char *e = getenv("YB_ASSIGN_PRUNE");
