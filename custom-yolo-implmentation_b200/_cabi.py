@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libyolo_boxpath.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 YB_F32, YB_BF16 = 0, 1
 
 _lib = None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 1
+#define YB_ABI_VERSION 2
 
 typedef enum { YB_F32 = 0, YB_BF16 = 1 } yb_dtype;
 
