@@ -1,12 +1,13 @@
 // Batched class-aware NMS (sm_100a).  Replaces non_max_suppression (src/utils/model_utils.py:174-279)
-// and the per-image torchvision.ops.nms call inside it, for all images of a batch in three launches:
+// and the per-image torchvision.ops.nms call inside it, for all images of a batch in three launches
+// (scan, class-parallel kernel, generic kernel for whatever the class-parallel one declined):
 //
 //   nms_scan_kernel    reads (N, 4+nc, A) once with 128-bit loads: best class (first max), strict
 //                      `> conf`, optional class filter; candidates are compacted with one atomic per
 //                      warp into 64-bit (score, anchor) keys.
-//   nms_sort_kernel    one CTA per image: bitonic sort of the keys in shared memory
-//                      (score descending, ties -> lowest anchor).
-//   nms_sweep_kernel   one CTA per image: greedy suppression in score order.  Each thread keeps its
+//   nms_class_kernel   see "Class-parallel path" below.
+//   nms_sweep_kernel   one CTA per image the class-parallel kernel left: bitonic sort of the keys (score
+//                      descending, ties -> lowest anchor), then greedy suppression in score order.  Each thread keeps its
 //                      columns' class-offset boxes in registers; the sorted list is walked 32 boxes at
 //                      a time: the owning warp resolves the 32x32 block with shuffles + ballots, the
 //                      kept rows are broadcast through shared memory and every thread clears the alive
@@ -140,20 +141,6 @@ nms_scan_kernel(const float *__restrict__ pred, int nc, int n_anchors, float con
         if (pass[v]) keys[(size_t)n * a_pad + slot++] = make_score_key(best[v], (unsigned int)(a0 + v));
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-nms_sort_kernel(const int *__restrict__ count, const int *__restrict__ mode, unsigned long long *__restrict__ keys,
-                int a_pad) {
-    extern __shared__ unsigned long long s_keys[];
-    const int n = blockIdx.x;
-    const int cnt = count[n];
-    if (cnt <= 1 || mode[n] != 0) return;
-    unsigned long long *k = keys + (size_t)n * a_pad;
-    const int n_pad = next_pow2(cnt);
-    for (int t = cnt + threadIdx.x; t < n_pad; t += blockDim.x) k[t] = kSentinel;
-    __syncthreads();
-    cta_bitonic_sort(k, n_pad, s_keys);
-}
-
 // torchvision's IoU test on two xyxy boxes, bit-exact:  fl(inter / (area_a + area_b - inter)) > thr
 // with thr the largest float <= the double threshold.  Boxes that do not intersect give IoU 0 (or
 // NaN), never above thr >= 0; otherwise a MUFU.RCP estimate decides unless it lands within 1e-6
@@ -260,7 +247,7 @@ __device__ __forceinline__ void emit_row(float *__restrict__ out_rows, int *__re
 template <bool REG>
 __global__ void __launch_bounds__(kSortThreads, 1)
 nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const int *__restrict__ count,
-                 const int *__restrict__ mode, const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
+                 const int *__restrict__ mode, const int *__restrict__ cls, unsigned long long *__restrict__ keys, int a_pad,
                  float4 *__restrict__ sbox, float thr, int max_det, int agnostic, float *__restrict__ out_rows,
                  int *__restrict__ out_count, int *__restrict__ out_anchor) {
     __shared__ float4 s_row[32];
@@ -278,8 +265,20 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     }
     if (REG && n_cand > kRegCols * kSortThreads) return;      // host picks the other variant; never taken
     const float *img = pred + (size_t)n * (4 + nc) * n_anchors;
-    const unsigned long long *k = keys + (size_t)n * a_pad;
     const int *cls_n = cls + (size_t)n * n_anchors;
+    {   // bitonic sort of all the image's keys (ascending key = descending score, ties -> lowest anchor)
+        extern __shared__ unsigned long long s_keys[];
+        unsigned long long *ks = keys + (size_t)n * a_pad;
+        const int cnt = count[n];
+        if (cnt > 1) {
+            const int n_pad = next_pow2(cnt);
+            for (int t = cnt + threadIdx.x; t < n_pad; t += blockDim.x) ks[t] = kSentinel;
+            __syncthreads();
+            cta_bitonic_sort(ks, n_pad, s_keys);
+        }
+        __syncthreads();
+    }
+    const unsigned long long *k = keys + (size_t)n * a_pad;
 
     float4 box[REG ? kRegCols : 1];
     unsigned alive = 0;
@@ -800,17 +799,17 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
     }
     // generic path for whatever the class-parallel kernel left (mode == 0)
     const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
-    YB_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_sort_kernel<<<n_images, kSortThreads, smem, st>>>(w.count, w.mode, w.keys, w.a_pad);
-    YB_LAUNCH_CHECK();
-    if (n_anchors <= kRegCols * kSortThreads)
-        nms_sweep_kernel<true><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
-                                                                  w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
-                                                                  out_count, out_anchor);
-    else
-        nms_sweep_kernel<false><<<n_images, kSortThreads, 0, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
-                                                                   w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
-                                                                   out_count, out_anchor);
+    if (n_anchors <= kRegCols * kSortThreads) {
+        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<true><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
+                                                                     w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
+                                                                     out_count, out_anchor);
+    } else {
+        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<false><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
+                                                                      w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
+                                                                      out_count, out_anchor);
+    }
     YB_LAUNCH_CHECK();
     return YB_OK;
 }
