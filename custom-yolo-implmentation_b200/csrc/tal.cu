@@ -14,8 +14,9 @@
 //                   tal_select_kernel      one warp per GT: global top-k (metric desc, anchor asc),
 //                                          64-bit atomicMax (overlap, ~gt) per anchor resolves conflicts
 //                   tal_resolve_kernel     one warp per GT: which of its k anchors it kept, max metric /
-//                                          overlap, normalised target scores, per-GT score sum, anchor -> slot map
-//                   tal_stats_kernel       fixed-order sum -> [sum of target scores, #foreground]
+//                                          overlap, normalised target scores, per-GT score sum, anchor -> slot map;
+//                                          the last CTA adds the per-GT sums in a fixed order
+//                                          -> [sum of target scores, #foreground]
 //   yb_tal_loss     tal_fg_kernel          one warp per foreground anchor: CIoU and DFL loss, and the gradient of
 //                                          its 64 box logits into a compact, coalesced buffer
 //                   tal_cls_kernel         dense BCE-with-logits at target 0 + gradient; writes the box rows of the
@@ -337,15 +338,12 @@ tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, i
             const int a = __float_as_int(e.z);
             if (e.x > bm || (e.x == bm && a < ba)) { bm = e.x; ba = a; bo = e.y; bt = q; }
         }
-        float wm = bm; int wa = ba; float wo = bo; int wl = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float om = __shfl_xor_sync(0xffffffffu, wm, o);
-            const int oa = __shfl_xor_sync(0xffffffffu, wa, o);
-            const float oo = __shfl_xor_sync(0xffffffffu, wo, o);
-            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-            if (om > wm || (om == wm && oa < wa)) { wm = om; wa = oa; wo = oo; wl = ol; }
-        }
+        // metrics are >= 0 (or -2 once taken), so their bit patterns order like signed integers
+        const int wmi = __reduce_max_sync(0xffffffffu, __float_as_int(bm));
+        const int wa = __reduce_min_sync(0xffffffffu, __float_as_int(bm) == wmi ? ba : 0x7fffffff);
+        const int wl = __ffs(__ballot_sync(0xffffffffu, __float_as_int(bm) == wmi && ba == wa)) - 1;
+        const float wm = __int_as_float(wmi);
+        const float wo = __shfl_sync(0xffffffffu, bo, wl);
         if (lane == wl && bt >= 0) c[bt].x = -2.f;         // taken (metrics are >= 0)
         __syncwarp();
         if (lane == 0) {
@@ -359,14 +357,11 @@ tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, i
 }
 
 // one warp per GT: keep the anchors this GT won, normalise their target scores
-__global__ void __launch_bounds__(128)
-tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total,
-                   const unsigned long long *__restrict__ akey, float4 *__restrict__ sel, const int *__restrict__ sel_count,
-                   float *__restrict__ g_tsum, int *__restrict__ g_npos, int *__restrict__ aslot, int topk,
-                   int *__restrict__ out_assigned, float *__restrict__ out_tscore) {
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (g >= gt_total) return;
+__device__ __forceinline__ void resolve_one_gt(int g, int lane, int n_images, int n_anchors, const int *__restrict__ gt_off,
+                                               const unsigned long long *__restrict__ akey, float4 *__restrict__ sel,
+                                               const int *__restrict__ sel_count, float *__restrict__ g_tsum,
+                                               int *__restrict__ g_npos, int *__restrict__ aslot, int topk,
+                                               int *__restrict__ out_assigned, float *__restrict__ out_tscore) {
     const int n = gt_image(gt_off, n_images, g);
     const int g_local = g - __ldg(gt_off + n);
     const int ns = sel_count[g];
@@ -400,16 +395,35 @@ tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, 
     if (lane == 0) { g_tsum[g] = ts; g_npos[g] = np; }
 }
 
-__global__ void __launch_bounds__(256)
-tal_stats_kernel(int gt_total, const float *__restrict__ g_tsum, const int *__restrict__ g_npos, float *__restrict__ out_stats) {
-    __shared__ double s_t[256];
-    __shared__ double s_n[256];
+
+__global__ void __launch_bounds__(128)
+tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total,
+                   const unsigned long long *__restrict__ akey, float4 *__restrict__ sel, const int *__restrict__ sel_count,
+                   float *__restrict__ g_tsum, int *__restrict__ g_npos, int *__restrict__ aslot, int topk,
+                   int *__restrict__ out_assigned, float *__restrict__ out_tscore, unsigned int *__restrict__ ticket,
+                   float *__restrict__ out_stats) {
+    __shared__ double s_t[128];
+    __shared__ double s_n[128];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (g < gt_total) resolve_one_gt(g, lane, n_images, n_anchors, gt_off, akey, sel, sel_count, g_tsum, g_npos, aslot, topk,
+                                     out_assigned, out_tscore);
+    // the last CTA to finish adds the per-GT sums up, always in the same order -> [sum of target scores, #foreground]
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     double t = 0.0, np = 0.0;
-    for (int g = threadIdx.x; g < gt_total; g += 256) { t += (double)g_tsum[g]; np += (double)g_npos[g]; }
+    for (int i = threadIdx.x; i < gt_total; i += 128) { t += (double)__ldcg(g_tsum + i); np += (double)__ldcg(g_npos + i); }
     s_t[threadIdx.x] = t; s_n[threadIdx.x] = np;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) { s_t[threadIdx.x] += s_t[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_t[threadIdx.x] += s_t[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -754,11 +768,12 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
                                                   w.cand_cap, w.sel, w.sel_count, w.akey);
         YB_LAUNCH_CHECK();
         tal_resolve_kernel<<<blocks, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, w.akey, w.sel, w.sel_count,
-                                                   w.g_tsum, w.g_npos, w.aslot, topk, out_assigned, out_tscore);
+                                                   w.g_tsum, w.g_npos, w.aslot, topk, out_assigned, out_tscore, w.ticket + 1,
+                                                   out_stats);
         YB_LAUNCH_CHECK();
+    } else {
+        YB_CUDA(cudaMemsetAsync(out_stats, 0, sizeof(float) * 8, st));
     }
-    tal_stats_kernel<<<1, 256, 0, st>>>(gt_total, w.g_tsum, w.g_npos, out_stats);
-    YB_LAUNCH_CHECK();
     return YB_OK;
 }
 
