@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libyolo_boxpath.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 YB_F32, YB_BF16 = 0, 1
 
 _lib = None
@@ -55,6 +55,9 @@ _SIGNATURES = {
     "yb_val_decode": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "yb_nms_multilabel_workspace_bytes": (c_size_t, [c_int]),
+    "yb_nms_multilabel": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_void_p,
                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_xywh2xyxy": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -225,10 +225,13 @@ __device__ __forceinline__ unsigned resolve_block(const float4 &bx, bool alive, 
     return kept;
 }
 
+__device__ __forceinline__ int cls_n_of(const int *__restrict__ cls, int n, int n_anchors, int a) {
+    return cls[(size_t)n * n_anchors + a];
+}
+
 __device__ __forceinline__ void emit_row(float *__restrict__ out_rows, int *__restrict__ out_anchor, int n, int max_det,
-                                         int pos, const float *__restrict__ img, int n_anchors, unsigned long long key,
+                                         int pos, const float *__restrict__ img, int n_anchors, int a, float score,
                                          int cls) {
-    const int a = (int)key_anchor(key);
     const float x = __ldg(img + a), y = __ldg(img + n_anchors + a);
     const float dw = __fmul_rn(__ldg(img + 2 * (size_t)n_anchors + a), 0.5f);
     const float dh = __fmul_rn(__ldg(img + 3 * (size_t)n_anchors + a), 0.5f);
@@ -237,18 +240,19 @@ __device__ __forceinline__ void emit_row(float *__restrict__ out_rows, int *__re
     row[1] = __fsub_rn(y, dh);
     row[2] = __fadd_rn(x, dw);
     row[3] = __fadd_rn(y, dh);
-    row[4] = key_score(key);
+    row[4] = score;
     row[5] = (float)cls;
     if (out_anchor) out_anchor[(size_t)n * max_det + pos] = a;
 }
 
 // REG = true: up to kRegCols*1024 candidates, boxes and alive bits in registers.
 // REG = false: any count up to kMaxNms, boxes in a global scratch, alive bits in shared memory.
-template <bool REG>
+// MULTI (multi_label): a key's low word is anchor * nc + class instead of the anchor.
+template <bool REG, bool MULTI>
 __global__ void __launch_bounds__(kSortThreads, 1)
 nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const int *__restrict__ count,
                  const int *__restrict__ mode, const int *__restrict__ cls, unsigned long long *__restrict__ keys, int a_pad,
-                 float4 *__restrict__ sbox, float thr, int max_det, int agnostic, float *__restrict__ out_rows,
+                 float4 *__restrict__ sbox, int sbox_stride, float thr, int max_det, int agnostic, float *__restrict__ out_rows,
                  int *__restrict__ out_count, int *__restrict__ out_anchor) {
     __shared__ float4 s_row[32];
     __shared__ float s_area[32];
@@ -257,8 +261,10 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
 
     const int n = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (mode[n] != 0) return;                              // finished by the class-parallel kernel
-    const int n_cand = min(count[n], kMaxNms);
+    if (!MULTI && mode[n] != 0) return;                    // finished by the class-parallel kernel
+    const int n_cand = min(min(count[n], a_pad), kMaxNms);
+    auto anchor_of = [&](unsigned id) { return MULTI ? (int)(id / (unsigned)nc) : (int)id; };
+    auto class_of = [&](unsigned id, int a) { return MULTI ? (int)(id % (unsigned)nc) : cls_n_of(cls, n, n_anchors, a); };
     if (n_cand == 0 || max_det <= 0) {
         if (tid == 0) out_count[n] = 0;
         return;
@@ -269,7 +275,7 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     {   // bitonic sort of all the image's keys (ascending key = descending score, ties -> lowest anchor)
         extern __shared__ unsigned long long s_keys[];
         unsigned long long *ks = keys + (size_t)n * a_pad;
-        const int cnt = count[n];
+        const int cnt = min(count[n], a_pad);
         if (cnt > 1) {
             const int n_pad = next_pow2(cnt);
             for (int t = cnt + threadIdx.x; t < n_pad; t += blockDim.x) ks[t] = kSentinel;
@@ -288,22 +294,24 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
             const int j = tid + t * kSortThreads;
             box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < n_cand) {
-                const int a = (int)key_anchor(k[j]);
-                box[t] = load_offset_box(img, n_anchors, a, cls_n[a], agnostic != 0);
+                const unsigned id = key_anchor(k[j]);
+                const int a = anchor_of(id);
+                box[t] = load_offset_box(img, n_anchors, a, class_of(id, a), agnostic != 0);
                 alive |= 1u << t;
             }
         }
     } else {
-        float4 *sb = sbox + (size_t)n * n_anchors;
+        float4 *sb = sbox + (size_t)n * sbox_stride;
         for (int j = tid; j < n_cand; j += kSortThreads) {
-            const int a = (int)key_anchor(k[j]);
-            sb[j] = load_offset_box(img, n_anchors, a, cls_n[a], agnostic != 0);
+            const unsigned id = key_anchor(k[j]);
+            const int a = anchor_of(id);
+            sb[j] = load_offset_box(img, n_anchors, a, class_of(id, a), agnostic != 0);
         }
         for (int w = tid; w < (n_cand + 31) / 32; w += kSortThreads)
             s_alive[w] = (w * 32 + 32 <= n_cand) ? 0xffffffffu : ((1u << (n_cand - w * 32)) - 1u);
     }
     __syncthreads();
-    const float4 *sb = REG ? nullptr : sbox + (size_t)n * n_anchors;
+    const float4 *sb = REG ? nullptr : sbox + (size_t)n * sbox_stride;
 
     int kept_total = 0;
     for (int c0 = 0; c0 < n_cand; c0 += 32) {
@@ -326,8 +334,9 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
                 s_row[rank] = bx;
                 s_area[rank] = box_area(bx);
                 const unsigned long long key = k[c0 + lane];
-                emit_row(out_rows, out_anchor, n, max_det, kept_total + rank, img, n_anchors, key,
-                         cls_n[key_anchor(key)]);
+                const int a = anchor_of(key_anchor(key));
+                emit_row(out_rows, out_anchor, n, max_det, kept_total + rank, img, n_anchors, a, key_score(key),
+                         class_of(key_anchor(key), a));
             }
             if (lane == 0) s_nrow = __popc(kept);
         }
@@ -730,11 +739,148 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
         const unsigned long long k54 = e >> 10;
         const unsigned a = (unsigned)(k54 & ((1u << kAnchorBits) - 1u));
         const unsigned inv = (unsigned)(k54 >> kAnchorBits);
-        emit_row(out_rows, out_anchor, img, max_det, r, img_pred, n_anchors, ((unsigned long long)inv << 32) | a, c);
+        emit_row(out_rows, out_anchor, img, max_det, r, img_pred, n_anchors, (int)a, __uint_as_float(0xFFFFFFFFu - inv), c);
     }
     YB_MARK(9);
     if (tid == 0) { out_count[img] = n_sel; mode[img] = 1; }
 }
+// ------------------------------------------------------------------------------------------
+// multi_label=True (model_utils.py:240-242): every (anchor, class) pair whose score exceeds conf is a
+// candidate, up to A * nc per image, of which the reference keeps the max_nms = 30000 best (:211, :259).
+// Candidates are never all materialised: two histogram passes over the scores (12 + 12 bits of the
+// inverted score word) find, per image, the 24-bit prefix of the 30000-th best score; a third pass emits
+// the keys at or above it (30000 plus the few that share that prefix), and the generic sort + sweep kernel
+// finishes, cutting at 30000 in (score, anchor * nc + class) order.
+// ------------------------------------------------------------------------------------------
+constexpr int kMlBins = 4096;
+constexpr int kMlCap = 65536;          // keys per image (>= kMaxNms + the boundary bin)
+constexpr int kMlThreads = 128;
+
+struct MlWorkspace {
+    int *count;                  // [N] keys emitted                         } zeroed every call
+    int *hist1, *hist2;          // [N * kMlBins]                            }
+    int *thr;                    // [N * 4]  b1, need1 (still wanted inside bin b1), b2, -
+    unsigned long long *keys;    // [N * kMlCap]
+    float4 *sbox;                // [N * kMaxNms]
+    size_t zero_bytes, total_bytes;
+};
+
+static MlWorkspace carve_ml(void *base, int n_images) {
+    MlWorkspace w;
+    char *p = static_cast<char *>(base);
+    size_t off = 0;
+    w.count = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * (size_t)n_images, 64);
+    w.hist1 = reinterpret_cast<int *>(p + off);
+    off += sizeof(int) * (size_t)n_images * kMlBins;
+    w.hist2 = reinterpret_cast<int *>(p + off);
+    off += sizeof(int) * (size_t)n_images * kMlBins;
+    w.zero_bytes = off;
+    w.thr = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(int) * 4 * (size_t)n_images, 64);
+    w.keys = reinterpret_cast<unsigned long long *>(p + off);
+    off += sizeof(unsigned long long) * (size_t)n_images * kMlCap;
+    w.sbox = reinterpret_cast<float4 *>(p + off);
+    off += sizeof(float4) * (size_t)n_images * kMaxNms;
+    w.total_bytes = off;
+    return w;
+}
+
+// PASS 0: histogram of the top 12 bits of every candidate's inverted score word
+// PASS 1: histogram of the next 12 bits, candidates of the image's boundary bin b1 only
+// PASS 2: emit the keys with (bin1 < b1) or (bin1 == b1 and bin2 <= b2)
+template <int PASS>
+__global__ void __launch_bounds__(kMlThreads)
+ml_pass_kernel(const float *__restrict__ pred, int nc, int n_anchors, float conf, const int *__restrict__ filter, int n_filter,
+               int *__restrict__ hist1, int *__restrict__ hist2, const int *__restrict__ thr, int *__restrict__ count,
+               unsigned long long *__restrict__ keys) {
+    __shared__ int s_hist[PASS < 2 ? kMlBins : 1];
+    const int n = blockIdx.y;
+    const int a = blockIdx.x * kMlThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (PASS < 2) {
+        for (int b = threadIdx.x; b < kMlBins; b += kMlThreads) s_hist[b] = 0;
+        __syncthreads();
+    }
+    const int b1 = PASS > 0 ? thr[4 * n] : 0, b2 = PASS > 1 ? thr[4 * n + 2] : 0;
+    const float *img = pred + ((size_t)n * (4 + nc) + 4) * n_anchors;
+    for (int c = 0; c < nc; ++c) {                         // warp-uniform trip count: the emit pass votes
+        bool ok = false;
+        unsigned inv = 0;
+        if (a < n_anchors) {
+            const float sc = __ldg(img + (size_t)c * n_anchors + a);
+            ok = sc > conf;                                // strict (model_utils.py:241)
+            inv = 0xFFFFFFFFu - __float_as_uint(sc);
+        }
+        if (ok && n_filter > 0) {
+            bool in = false;
+            for (int f = 0; f < n_filter; ++f) in |= (__ldg(filter + f) == c);
+            ok = in;
+        }
+        const int bin1 = (int)(inv >> 20), bin2 = (int)((inv >> 8) & 0xFFFu);
+        if (PASS == 0) {
+            if (ok) atomicAdd(&s_hist[bin1], 1);
+        } else if (PASS == 1) {
+            if (ok && bin1 == b1) atomicAdd(&s_hist[bin2], 1);
+        } else {
+            ok = ok && (bin1 < b1 || (bin1 == b1 && bin2 <= b2));
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (mask) {
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(count + n, __popc(mask));
+                slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(mask & ((1u << lane) - 1u));
+                if (ok && slot < kMlCap)
+                    keys[(size_t)n * kMlCap + slot] = ((unsigned long long)inv << 32) | ((unsigned)a * (unsigned)nc + (unsigned)c);
+            }
+        }
+    }
+    if (PASS < 2) {
+        __syncthreads();
+        int *h = (PASS == 0 ? hist1 : hist2) + (size_t)n * kMlBins;
+        for (int b = threadIdx.x; b < kMlBins; b += kMlThreads)
+            if (s_hist[b]) atomicAdd(h + b, s_hist[b]);
+    }
+}
+
+// one warp per image: the bin in which the running count (best scores first) reaches `want`
+template <int LEVEL>
+__global__ void __launch_bounds__(32)
+ml_threshold_kernel(const int *__restrict__ hist1, const int *__restrict__ hist2, int *__restrict__ thr) {
+    const int n = blockIdx.x, lane = threadIdx.x;
+    const int *h = (LEVEL == 0 ? hist1 : hist2) + (size_t)n * kMlBins;
+    const int want = LEVEL == 0 ? kMaxNms : thr[4 * n + 1];
+    constexpr int PER = kMlBins / 32;
+    int local = 0;
+    for (int b = 0; b < PER; ++b) local += h[lane * PER + b];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total < want || want <= 0) {                       // fewer candidates than wanted: keep them all
+        if (lane == 0) {
+            thr[4 * n + 2 * LEVEL] = kMlBins;              // every bin index is below it
+            if (LEVEL == 0) { thr[4 * n + 1] = 0; thr[4 * n + 2] = kMlBins; }
+        }
+        return;
+    }
+    const int excl = incl - local;
+    if (excl < want && want <= incl) {                     // exactly one lane
+        int run = excl;
+        for (int b = 0; b < PER; ++b) {
+            const int v = h[lane * PER + b];
+            if (run + v >= want) {
+                thr[4 * n + 2 * LEVEL] = lane * PER + b;
+                if (LEVEL == 0) thr[4 * n + 1] = want - run;
+                break;
+            }
+            run += v;
+        }
+    }
+}
+
 #ifdef YB_NMS_PROFILE
 extern "C" int yb_nms_profile_read(long long *out_host) {
     return (int)cudaMemcpyFromSymbol(out_host, g_nms_clk, sizeof(long long) * 16);
@@ -800,16 +946,67 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
     // generic path for whatever the class-parallel kernel left (mode == 0)
     const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
     if (n_anchors <= kRegCols * kSortThreads) {
-        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_sweep_kernel<true><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
-                                                                     w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
-                                                                     out_count, out_anchor);
+        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<true, false><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls,
+                                                                            w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
+                                                                            agnostic, out_rows, out_count, out_anchor);
     } else {
-        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_sweep_kernel<false><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls, w.keys,
-                                                                      w.a_pad, w.sbox, thr, max_det, agnostic, out_rows,
-                                                                      out_count, out_anchor);
+        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<false, false><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls,
+                                                                             w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
+                                                                             agnostic, out_rows, out_count, out_anchor);
     }
+    YB_LAUNCH_CHECK();
+    return YB_OK;
+}
+
+extern "C" size_t yb_nms_multilabel_workspace_bytes(int n_images) {
+    if (n_images <= 0) return 0;
+    return carve_ml(nullptr, n_images).total_bytes;
+}
+
+extern "C" int yb_nms_multilabel(const float *prediction, int n_images, int nc, int n_anchors, float conf_thres,
+                                 double iou_thres, int max_det, int agnostic, const int32_t *class_filter,
+                                 int n_class_filter, float *out_rows, int32_t *out_count, int32_t *out_anchor,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
+    YB_REQUIRE(prediction && out_rows && out_count && workspace, "yb_nms_multilabel: null pointer");
+    YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && max_det > 0 && n_images <= 65535, "yb_nms_multilabel: bad sizes");
+    YB_REQUIRE((long long)n_anchors * nc < (1ll << 32), "yb_nms_multilabel: anchors x classes must fit 32 bits");
+    YB_REQUIRE(n_class_filter >= 0 && (n_class_filter == 0 || class_filter), "yb_nms_multilabel: bad class filter");
+    YB_REQUIRE(conf_thres >= 0.f, "yb_nms_multilabel: conf_thres must be >= 0 (scores are ordered by their bit pattern)");
+    if (workspace_bytes < yb_nms_multilabel_workspace_bytes(n_images)) {
+        set_error("yb_nms_multilabel: workspace %zu B < required %zu B", workspace_bytes,
+                  yb_nms_multilabel_workspace_bytes(n_images));
+        return YB_ERR_WORKSPACE;
+    }
+    if (!aligned16(workspace)) {
+        set_error("yb_nms_multilabel: workspace must be 16-byte aligned");
+        return YB_ERR_ALIGN;
+    }
+    const MlWorkspace w = carve_ml(workspace, n_images);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float thr = (float)iou_thres;
+    if ((double)thr > iou_thres) thr = nextafterf(thr, -INFINITY);
+    YB_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
+    const dim3 grid((n_anchors + kMlThreads - 1) / kMlThreads, n_images);
+    ml_pass_kernel<0><<<grid, kMlThreads, 0, st>>>(prediction, nc, n_anchors, conf_thres, class_filter, n_class_filter, w.hist1,
+                                                   w.hist2, w.thr, w.count, w.keys);
+    YB_LAUNCH_CHECK();
+    ml_threshold_kernel<0><<<n_images, 32, 0, st>>>(w.hist1, w.hist2, w.thr);
+    YB_LAUNCH_CHECK();
+    ml_pass_kernel<1><<<grid, kMlThreads, 0, st>>>(prediction, nc, n_anchors, conf_thres, class_filter, n_class_filter, w.hist1,
+                                                   w.hist2, w.thr, w.count, w.keys);
+    YB_LAUNCH_CHECK();
+    ml_threshold_kernel<1><<<n_images, 32, 0, st>>>(w.hist1, w.hist2, w.thr);
+    YB_LAUNCH_CHECK();
+    ml_pass_kernel<2><<<grid, kMlThreads, 0, st>>>(prediction, nc, n_anchors, conf_thres, class_filter, n_class_filter, w.hist1,
+                                                   w.hist2, w.thr, w.count, w.keys);
+    YB_LAUNCH_CHECK();
+    const size_t smem = sizeof(unsigned long long) * (size_t)kSortTile;
+    YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_sweep_kernel<false, true><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, nullptr, nullptr,
+                                                                        w.keys, kMlCap, w.sbox, kMaxNms, thr, max_det, agnostic,
+                                                                        out_rows, out_count, out_anchor);
     YB_LAUNCH_CHECK();
     return YB_OK;
 }

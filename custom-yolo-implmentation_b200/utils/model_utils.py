@@ -122,9 +122,9 @@ def xywh2xyxy(x):
 
 
 def batched_nms_raw(prediction: torch.Tensor, conf_thres: float, iou_thres: float, max_det: int, nc: int,
-                    agnostic: bool = False, classes=None, want_anchor: bool = False):
-    """One ``yb_nms`` call.  Returns device tensors ``(rows (N, max_det, 6), count (N,), anchor or None)``
-    without any host synchronisation."""
+                    agnostic: bool = False, classes=None, want_anchor: bool = False, multi_label: bool = False):
+    """One ``yb_nms`` (or, with ``multi_label``, ``yb_nms_multilabel``) call.  Returns device tensors
+    ``(rows (N, max_det, 6), count (N,), anchor or None)`` without any host synchronisation."""
     _cabi.require_cuda(prediction, "prediction")
     pred = prediction.detach()
     if pred.dtype != torch.float32:
@@ -137,18 +137,20 @@ def batched_nms_raw(prediction: torch.Tensor, conf_thres: float, iou_thres: floa
                            f"(input tensor's size at dimension 1), but got split_sizes=[4, {nc}]")
     dev = pred.device
     lib = _cabi.lib()
-    ws = torch.empty(max(lib.yb_nms_workspace_bytes(n, a), 16), dtype=torch.uint8, device=dev)
+    ws_bytes = lib.yb_nms_multilabel_workspace_bytes(n) if multi_label else lib.yb_nms_workspace_bytes(n, a)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     rows = torch.empty(n, max_det, 6, dtype=torch.float32, device=dev)
     count = torch.empty(n, dtype=torch.int32, device=dev)
     anchor = torch.empty(n, max_det, dtype=torch.int32, device=dev) if want_anchor else None
     filt = None
     if classes is not None:
         filt = torch.tensor([int(c) for c in classes], dtype=torch.int32).to(dev)
+    entry = lib.yb_nms_multilabel if multi_label else lib.yb_nms
     with torch.cuda.device(dev):
-        rc = lib.yb_nms(_cabi.ptr(pred), n, nc, a, float(conf_thres), float(iou_thres), int(max_det), int(bool(agnostic)),
-                        _cabi.ptr(filt), 0 if filt is None else filt.numel(), _cabi.ptr(rows), _cabi.ptr(count),
-                        _cabi.ptr(anchor), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
-    _cabi.check(rc, "yb_nms")
+        rc = entry(_cabi.ptr(pred), n, nc, a, float(conf_thres), float(iou_thres), int(max_det), int(bool(agnostic)),
+                   _cabi.ptr(filt), 0 if filt is None else filt.numel(), _cabi.ptr(rows), _cabi.ptr(count),
+                   _cabi.ptr(anchor), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "yb_nms_multilabel" if multi_label else "yb_nms")
     return rows, count, anchor
 
 
@@ -169,8 +171,9 @@ def non_max_suppression(
     descending, on ``prediction.device`` (reference :174-279).  All images are processed by three
     kernel launches and ONE device-to-host copy (the per-image counts); the reference's wall-clock
     abort (:212, :275-277) is deliberately not reproduced — every image is processed.
-    ``multi_label=True`` (with nc > 1) is not on the reference's own call path
-    (src/model/model_builder.py:139) and raises NotImplementedError.  Non-empty apriori ``labels``
+    ``multi_label=True`` (with nc > 1, :213) makes every (anchor, class) pair above ``conf_thres`` a candidate
+    (:240-242) and keeps the 30000 best of an image (:259): six launches, no (A x nc) candidate list.
+    Non-empty apriori ``labels``
     raise the RuntimeError the reference raises: it builds label rows ``nc + nm + 5`` wide (:227, the
     YOLOv5 layout with an objectness column) and cannot concatenate them with its ``4 + nc + nm`` wide
     candidates (:231).
@@ -181,15 +184,15 @@ def non_max_suppression(
         prediction = prediction[0]
     bs = prediction.shape[0]
     nc = nc or (prediction.shape[1] - 4)
-    if multi_label and nc > 1:
-        raise NotImplementedError("non_max_suppression(multi_label=True) is not implemented by the CUDA path")
+    multi_label = bool(multi_label) and nc > 1             # :213
     if labels and any(len(lb) for lb in labels):
         width = prediction.shape[1]
         raise RuntimeError(f"Sizes of tensors must match except in dimension 0. Expected size {width} but got size "
                            f"{width + 1} for tensor number 1 in the list.")
     if classes is not None and len(classes) == 0:
         return [torch.zeros((0, 6), device=prediction.device)] * bs
-    rows, count, _ = batched_nms_raw(prediction, conf_thres, iou_thres, max_det, nc, agnostic, classes)
+    rows, count, _ = batched_nms_raw(prediction, conf_thres, iou_thres, max_det, nc, agnostic, classes,
+                                     multi_label=multi_label)
     counts = count.tolist()                                  # the only host sync
     empty = torch.zeros((0, 6), device=prediction.device)
     return [rows[i, :c] if c else empty for i, c in enumerate(counts)]

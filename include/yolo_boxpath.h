@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 2
+#define YB_ABI_VERSION 3
 
 typedef enum { YB_F32 = 0, YB_BF16 = 1 } yb_dtype;
 
@@ -202,6 +202,16 @@ int yb_nms(const float *prediction, int n_images, int nc, int n_anchors,
            const int32_t *class_filter, int n_class_filter,
            float *out_rows, int32_t *out_count, int32_t *out_anchor,
            void *workspace, size_t workspace_bytes, void *stream);
+
+/* multi_label=True (src/utils/model_utils.py:240-242): every (anchor, class) pair with score > conf_thres is
+ * a candidate; the max_nms = 30000 best of an image (:211, :259; score descending, ties -> lower
+ * anchor * nc + class, the order of the reference's nonzero()) go through the same greedy NMS.
+ * Same arguments and outputs as yb_nms; its own workspace. */
+size_t yb_nms_multilabel_workspace_bytes(int n_images);
+int yb_nms_multilabel(const float *prediction, int n_images, int nc, int n_anchors, float conf_thres, double iou_thres,
+                      int max_det, int agnostic, const int32_t *class_filter, int n_class_filter,
+                      float *out_rows, int32_t *out_count, int32_t *out_anchor,
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * IoU / box utilities (fp32).

@@ -72,15 +72,35 @@ class NmsTrace:
 
 def nms_forward(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
                 classes: Optional[Sequence[int]] = None, agnostic: bool = False, max_det: int = 300,
-                nc: int = 0) -> NmsTrace:
+                nc: int = 0, multi_label: bool = False) -> NmsTrace:
     assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
     pred = prediction.detach().float().cpu()
     bs = pred.shape[0]
     nc = nc or (pred.shape[1] - 4)
     nm = pred.shape[1] - nc - 4
     rows, keep_anchor, ncand = [], [], []
+    multi_label = multi_label and nc > 1                          # model_utils.py:213
     for i in range(bs):
         x = pred[i].transpose(0, 1)                               # (A, 4+nc+nm)
+        if multi_label:
+            # every (anchor, class) pair above the threshold, in nonzero() order (:240-242), then as below
+            ai, cj = (x[:, 4:4 + nc] > conf_thres).nonzero(as_tuple=True)
+            sc = x[ai, 4 + cj]
+            if classes is not None and ai.numel():
+                ok = (cj[:, None] == torch.tensor(list(classes))[None, :]).any(1)
+                ai, cj, sc = ai[ok], cj[ok], sc[ok]
+            ncand.append(int(ai.numel()))
+            if ai.numel() == 0:
+                rows.append(torch.zeros(0, 6 + nm)); keep_anchor.append(torch.zeros(0, dtype=torch.long))
+                continue
+            order = torch.sort(sc, descending=True, stable=True).indices[:MAX_NMS]
+            ai, cj, sc = ai[order], cj[order], sc[order]
+            box = xywh_to_xyxy(x[ai, :4])
+            cls_f = cj.float()
+            kept = nms_greedy_sorted(box + cls_f[:, None] * (0.0 if agnostic else MAX_WH), iou_thres, max_det)
+            rows.append(torch.cat((box[kept], sc[kept][:, None], cls_f[kept][:, None], x[ai[kept], 4 + nc:]), 1))
+            keep_anchor.append(ai[kept])
+            continue
         conf, j = x[:, 4:4 + nc].max(1)                           # first max index
         cand = (conf > conf_thres).nonzero()[:, 0]                # strict, anchor order
         if classes is not None and cand.numel():

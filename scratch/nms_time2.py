@@ -16,3 +16,12 @@ for name, kw in (("class-aware conf 0.001", dict(conf=0.001, agn=False)), ("agno
     for _ in range(20): rows, count, _ = f()
     e1.record(); torch.cuda.synchronize()
     print(f'{name:26s} {e0.elapsed_time(e1)/20*1e3:9.1f} us/call  kept {count[:3].tolist()}')
+for name, conf in (("multi_label conf 0.001", 0.001), ("multi_label conf 0.25", 0.25)):
+    f = lambda: U.batched_nms_raw(y, conf, 0.7, 300, 80, False, None, multi_label=True)
+    for _ in range(3): rows, count, _ = f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): rows, count, _ = f()
+    e1.record(); torch.cuda.synchronize()
+    print(f'{name:26s} {e0.elapsed_time(e1)/10*1e3:9.1f} us/call  kept {count[:3].tolist()}')

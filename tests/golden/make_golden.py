@@ -128,18 +128,21 @@ def loss_case(name, n, nc, imgsz, gmax, seed, dtype=torch.float32, conflict=0.0,
           f"GT {int(gt_cnt.sum())} duplicate-anchor GTs {dup}")
 
 
-def nms_case(name, n, nc, imgsz, seed, conf, iou, max_det=300, agnostic=False, classes=None, dense=False, nm=0):
+def nms_case(name, n, nc, imgsz, seed, conf, iou, max_det=300, agnostic=False, classes=None, dense=False, nm=0,
+             multi_label=False, allow_ties=False, store_inputs=True):
     x = syn.make_nms_input(n, nc, imgsz, seed, dense_uniform=dense)
     if nm:
         g = torch.Generator().manual_seed(seed + 1)
         x = torch.cat((x, torch.randn(n, nm, x.shape[2], generator=g)), 1)
     for b in range(n):      # bit-exact keep lists need unique scores per image (Q10)
-        best = x[b, 4:4 + nc].amax(0)
-        assert best.unique().numel() == best.numel(), "duplicate best scores; pick another seed"
+        best = x[b, 4:4 + nc].flatten() if multi_label else x[b, 4:4 + nc].amax(0)
+        assert allow_ties or best.unique().numel() == best.numel(), "duplicate best scores; pick another seed"
     out = ref_utils.non_max_suppression(x, conf_thres=conf, iou_thres=iou, classes=classes, agnostic=agnostic,
-                                        max_det=max_det, nc=nc)
+                                        multi_label=multi_label, max_det=max_det, nc=nc)
     rows, cnt = pack_ragged(out, 6 + nm, np.float32)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), prediction=x.numpy(), rows=rows, count=cnt,
+    # store_inputs=False: the test regenerates the prediction from (n, nc, imgsz, seed) with utils/synthetic.py
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), prediction=x.numpy() if store_inputs else np.zeros(0, np.float32),
+                        rows=rows, count=cnt,
                         meta=np.array([n, nc, imgsz, seed, max_det, int(agnostic), nm], np.int64),
                         conf=np.float64(conf), iou=np.float64(iou),
                         classes=np.array(classes if classes is not None else [], np.int64))
@@ -264,6 +267,11 @@ if __name__ == "__main__":
     nms_case("nms_agnostic", 2, 6, 160, 13, conf=0.05, iou=0.5, agnostic=True)
     nms_case("nms_classes", 2, 6, 160, 14, conf=0.3, iou=0.6, classes=[1, 4])
     nms_case("nms_few", 3, 6, 160, 15, conf=0.9, iou=0.3)
+    nms_case("nms_multilabel", 3, 6, 160, 16, conf=0.05, iou=0.6, multi_label=True)
+    nms_case("nms_multilabel_classes", 2, 6, 160, 19, conf=0.02, iou=0.5, multi_label=True, classes=[0, 2, 5], max_det=50)
+    # 672 000 candidates > max_nms = 30 000; equal scores exist among them (the reference's argsort decides their order)
+    nms_case("nms_multilabel_cap", 1, 80, 640, 18, conf=0.001, iou=0.7, multi_label=True, allow_ties=True,
+             store_inputs=False)
     decode_case("decode_topk", 3, 6, 160, 21, conf=0.25, top_k=100, cls_mean=-1.0)
     decode_case("decode_sparse", 3, 6, 160, 22, conf=0.6, top_k=100, cls_mean=-4.0)
     helper_case("helpers", 31)

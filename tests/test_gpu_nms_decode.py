@@ -36,6 +36,35 @@ def test_nms_matches_reference_golden(name, cuda_device):
         assert np.array_equal(out[b].cpu().numpy(), z["rows"][b, :k])          # bit-exact rows, same order
 
 
+@pytest.mark.parametrize("name", ["nms_multilabel", "nms_multilabel_classes", "nms_multilabel_cap"])
+def test_nms_multi_label_matches_reference_golden(name, cuda_device):
+    z = load_golden(name)
+    n, nc, imgsz, seed, max_det, agnostic, _ = (int(v) for v in z["meta"])
+    classes = z["classes"].tolist() or None
+    x = torch.from_numpy(z["prediction"]) if z["prediction"].size else syn.make_nms_input(n, nc, imgsz, seed)
+    out = U.non_max_suppression(x.to(cuda_device), float(z["conf"]), float(z["iou"]), classes=classes,
+                                agnostic=bool(agnostic), multi_label=True, max_det=max_det, nc=nc)
+    for b in range(n):
+        k = int(z["count"][b])
+        assert out[b].shape == (k, 6)
+        assert np.array_equal(out[b].cpu().numpy(), z["rows"][b, :k])
+
+
+@pytest.mark.parametrize("agnostic", [False, True])
+def test_nms_multi_label_against_oracle(agnostic, cuda_device):
+    """More candidates than max_nms on a 320 px grid with 40 classes, several images, both offset modes."""
+    x = syn.make_nms_input(3, 40, 320, 97)
+    rows, count, anchor = U.batched_nms_raw(x.to(cuda_device), 0.001, 0.6, 300, 40, agnostic, None, want_anchor=True,
+                                            multi_label=True)
+    ora = N.nms_forward(x, 0.001, 0.6, agnostic=agnostic, max_det=300, nc=40, multi_label=True)
+    assert min(ora.n_candidates) > 30000
+    for b in range(3):
+        k = int(count[b])
+        assert k == ora.rows[b].shape[0]
+        assert torch.equal(anchor[b, :k].cpu().long(), ora.keep_anchor[b])
+        assert torch.equal(rows[b, :k].cpu(), ora.rows[b])
+
+
 def _check_against_oracle(x, conf, iou, max_det, nc, dev, agnostic=False, classes=None):
     rows, count, anchor = U.batched_nms_raw(x.to(dev), conf, iou, max_det, nc, agnostic, classes, want_anchor=True)
     ora = N.nms_forward(x, conf, iou, classes=classes, agnostic=agnostic, max_det=max_det, nc=nc)

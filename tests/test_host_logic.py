@@ -93,7 +93,7 @@ def test_nms_argument_checks_happen_before_any_device_work():
         U.non_max_suppression(x, conf_thres=-0.1)
     with pytest.raises(AssertionError, match="Invalid IoU"):
         U.non_max_suppression(x, iou_thres=1.1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):                              # multi_label is implemented: it reaches the device check
         U.non_max_suppression(x, multi_label=True, nc=4)
     with pytest.raises(RuntimeError, match="Sizes of tensors must match"):       # the reference's own failure (:227-231)
         U.non_max_suppression(x, labels=[torch.tensor([[1.0, 10.0, 10.0, 5.0, 5.0]])] * x.shape[0], nc=4)

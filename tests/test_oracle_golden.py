@@ -166,3 +166,24 @@ def test_head_tail_oracle_matches_reference(name):
     assert np.array_equal(x.numpy(), z["x"])                                   # a copy: bit-exact
     grid, st = D.make_anchor_grid([tuple(int(v) for v in s) for s in z["shapes"]], [8.0, 16.0, 32.0][:nl])
     assert np.array_equal(grid.t().numpy(), z["anchors"]) and np.array_equal(st.t().numpy(), z["strides"])
+
+
+def _multilabel_prediction(z):
+    n, nc, imgsz, seed = (int(v) for v in z["meta"][:4])
+    if z["prediction"].size:
+        return torch.from_numpy(z["prediction"])
+    return syn.make_nms_input(n, nc, imgsz, seed)                              # inputs regenerated from the seed
+
+
+@pytest.mark.parametrize("name", ["nms_multilabel", "nms_multilabel_classes", "nms_multilabel_cap"])
+def test_nms_oracle_multi_label_matches_reference(name):
+    """multi_label=True (model_utils.py:240-242); the _cap case has 672 000 candidates, cut to max_nms = 30 000."""
+    z = load_golden(name)
+    n, nc, _, _, max_det, agnostic, _ = (int(v) for v in z["meta"])
+    classes = z["classes"].tolist() or None
+    tr = N.nms_forward(_multilabel_prediction(z), float(z["conf"]), float(z["iou"]), classes=classes, agnostic=bool(agnostic),
+                       max_det=max_det, nc=nc, multi_label=True)
+    for b in range(n):
+        k = int(z["count"][b])
+        assert tr.rows[b].shape[0] == k
+        assert np.array_equal(tr.rows[b].numpy(), z["rows"][b, :k])
