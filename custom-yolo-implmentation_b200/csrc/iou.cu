@@ -79,7 +79,7 @@ box_iou_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ 
 // dense QFL: per-CTA partial sums -> workspace, finished by qfl_finish_kernel in a fixed order
 constexpr int kQflThreads = 256;
 __global__ void __launch_bounds__(kQflThreads)
-qfl_dense_kernel(const float *__restrict__ x, const float *__restrict__ t, size_t n, float inv_m,
+qfl_dense_kernel(const float *__restrict__ x, const float *__restrict__ t, size_t n, float inv_m, float beta,
                  float *__restrict__ grad, float *__restrict__ part) {
     __shared__ float s_red[kQflThreads / 32];
     float acc = 0.f;
@@ -90,10 +90,14 @@ qfl_dense_kernel(const float *__restrict__ x, const float *__restrict__ t, size_
         const float q = 1.f - p;
         const float lp = logf(p + kEpsLog), lq = logf(q + kEpsLog);
         const float u = 1.f - tv;
-        acc += tv * q * q * lp + u * p * p * lq;
+        // (1 - p)^beta and p^beta (src/model/losses.py:53-54); beta == 2 is the reference's only use
+        const bool sq = beta == 2.f;
+        const float qb = sq ? q * q : powf(q, beta), pb = sq ? p * p : powf(p, beta);
+        acc += tv * qb * lp + u * pb * lq;
         if (grad) {
-            const float dpos = tv * (-2.f * q * lp + q * q / (p + kEpsLog));
-            const float dneg = u * (2.f * p * lq - p * p / (q + kEpsLog));
+            const float qb1 = sq ? q : powf(q, beta - 1.f), pb1 = sq ? p : powf(p, beta - 1.f);
+            const float dpos = tv * (-beta * qb1 * lp + qb / (p + kEpsLog));
+            const float dneg = u * (beta * pb1 * lq - pb / (q + kEpsLog));
             grad[i] = -inv_m * (dpos + dneg) * p * q;
         }
     }
@@ -226,7 +230,7 @@ extern "C" int yb_quality_focal_loss(const float *pred_scores, const float *targ
                                      void *stream) {
     YB_REQUIRE(pred_scores && target_scores && out_loss && workspace, "yb_quality_focal_loss: null pointer");
     YB_REQUIRE(m > 0 && c > 0, "yb_quality_focal_loss: bad sizes");
-    YB_REQUIRE(beta == 2.0f, "yb_quality_focal_loss: only beta == 2 is implemented");
+    YB_REQUIRE(beta > 0.f, "yb_quality_focal_loss: beta must be positive");
     const size_t n = (size_t)m * c;
     const int blocks = qfl_blocks(n);
     if (workspace_bytes < sizeof(float) * (size_t)blocks) {
@@ -235,7 +239,8 @@ extern "C" int yb_quality_focal_loss(const float *pred_scores, const float *targ
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float inv_m = 1.f / (float)m;
-    qfl_dense_kernel<<<blocks, kQflThreads, 0, st>>>(pred_scores, target_scores, n, inv_m, grad_scores, (float *)workspace);
+    qfl_dense_kernel<<<blocks, kQflThreads, 0, st>>>(pred_scores, target_scores, n, inv_m, beta, grad_scores,
+                                                     (float *)workspace);
     YB_LAUNCH_CHECK();
     qfl_finish_kernel<<<1, 256, 0, st>>>((const float *)workspace, blocks, inv_m, out_loss);
     YB_LAUNCH_CHECK();

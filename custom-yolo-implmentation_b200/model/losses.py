@@ -320,6 +320,10 @@ class YoloDFLQFLoss(nn.Module):
 
     def forward(self, preds, gt_boxes_list, anchors, strides):
         n = preds.shape[0]
+        if preds.dtype not in (torch.float32, torch.bfloat16):
+            # fp16 (autocast + GradScaler) / fp64 head outputs: the kernels read fp32 or bf16, so do what the
+            # reference does (losses.py:142 `.float()`); autograd casts the gradient back
+            preds = preds.float()
         if len(gt_boxes_list) != n:
             raise IndexError(f"gt_boxes_list has {len(gt_boxes_list)} entries for a batch of {n}")
         if isinstance(gt_boxes_list, PackedGT):
@@ -397,8 +401,8 @@ class _Qfl(torch.autograd.Function):
     def forward(ctx, pred_scores, target_scores, beta):
         _cabi.require_cuda(pred_scores, "pred_scores")
         _cabi.require_cuda(target_scores, "target_scores")
-        if beta != 2.0:
-            raise NotImplementedError("quality_focal_loss: the CUDA kernel implements beta == 2.0 (the reference's only use)")
+        if not beta > 0:
+            raise ValueError("quality_focal_loss: beta must be positive")
         if pred_scores.dim() != 2 or pred_scores.shape != target_scores.shape:
             raise ValueError("quality_focal_loss expects two (M, C) tensors of the same shape")
         x = pred_scores.detach().float().contiguous()

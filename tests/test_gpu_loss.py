@@ -281,3 +281,18 @@ def test_tile_pruning_never_changes_the_result(n, imgsz, gmax, dtype, seed, cuda
             assert torch.equal(a, b)
         for a, b in zip(got[3], ref[3]):
             assert torch.equal(a, b)
+
+
+def test_fp16_head_output_goes_through_float_like_the_reference(cuda_device):
+    """autocast(float16) head outputs: the module converts with .float() as the reference does (losses.py:142)
+    and autograd hands an fp16 gradient back."""
+    preds, gts, anchors, strides = syn.make_loss_inputs(2, 6, 128, 6, 71)
+    x16 = preds.half()
+    x = x16.to(cuda_device).requires_grad_(True)
+    crit = P.YoloDFLQFLoss(num_classes=6)
+    loss, parts = crit(x, [g.to(cuda_device) for g in gts], anchors.to(cuda_device), strides.to(cuda_device))
+    loss.backward()
+    assert x.grad.dtype == torch.float16
+    ora = L.loss_forward_backward(x16.float(), gts, anchors, strides, 6)
+    assert abs(loss.item() - ora.total.item()) <= F32_RTOL * abs(ora.total.item())
+    assert_grad_close(x.grad.cpu(), ora.grad.half(), 2e-3)          # one fp16 rounding of the gradient

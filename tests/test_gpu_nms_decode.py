@@ -221,6 +221,18 @@ def test_helper_gradients_match_oracle_autograd(cuda_device):
     gs = torch.from_numpy(z["scores"]).to(dev).requires_grad_(True)
     (PL.quality_focal_loss(gs, torch.from_numpy(z["target"]).to(dev)) * 3.0).backward()
     assert torch.allclose(gs.grad.cpu(), s.grad, rtol=1e-4, atol=1e-7)
+    # ... and with another focusing exponent (the reference's formula, src/model/losses.py:46-57, restated inline)
+    for beta in (1.5, 3.0):
+        s = torch.from_numpy(z["scores"]).clone().requires_grad_(True)
+        tgt = torch.from_numpy(z["target"])
+        p = s.sigmoid()
+        ref = -(tgt * (1 - p).pow(beta) * torch.log(p + 1e-12) + (1 - tgt) * p.pow(beta) * torch.log(1 - p + 1e-12)).sum() / s.shape[0]
+        ref.backward()
+        gs = torch.from_numpy(z["scores"]).to(dev).requires_grad_(True)
+        got = PL.quality_focal_loss(gs, tgt.to(dev), beta=beta)
+        got.backward()
+        assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert torch.allclose(gs.grad.cpu(), s.grad, rtol=1e-4, atol=1e-7)
     # distribution_focal_loss
     d = torch.from_numpy(z["dist"]).clone().requires_grad_(True)
     L.dfl_loss_rows(d, torch.from_numpy(z["tval"])).mean().backward()
