@@ -445,6 +445,32 @@ __device__ __forceinline__ void bce_bg_elem(float x, float kc, float &acc, float
     g = kc * (x >= 0.f ? r : e * r);
 }
 
+// The same for two cells at a time, branch-free, on the packed fp32 pipe.  With t = exp(-|x|) in (0, 1] and
+// r = 1 / (1 + t) in [0.5, 1):  softplus(x) = max(x, 0) - log(r)  and  sigmoid(x) = r (x >= 0) or t r (x < 0).
+// log(r) comes from the degree-5 polynomial of log(1 + f) on [-0.293, 0]: f = r sqrt2 - 1 (and -ln2/2 added) when
+// r < 1/sqrt2, else f = -t r, which is r - 1 without the cancellation.  acc2 accumulates softplus.
+__device__ __forceinline__ void softplus_sigmoid_pair(float x0, float x1, f32x2 &sp, f32x2 &sg) {
+    float a0, a1;
+    unpack2(mul2(pack2(fabsf(x0), fabsf(x1)), pack2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+    const float t0 = fast_ex2(a0), t1 = fast_ex2(a1);
+    float u0, u1;
+    unpack2(add2(pack2(t0, t1), pack2(1.f, 1.f)), u0, u1);
+    const float r0 = fast_rcp(u0), r1 = fast_rcp(u1);
+    float tr0, tr1;
+    unpack2(mul2(pack2(t0, t1), pack2(r0, r1)), tr0, tr1);                    // t r = 1 - r, exactly enough
+    const bool lo0 = r0 < 0.70710678f, lo1 = r1 < 0.70710678f;
+    const float f0 = lo0 ? fmaf(r0, 1.41421356f, -1.f) : -tr0, f1 = lo1 ? fmaf(r1, 1.41421356f, -1.f) : -tr1;
+    const f32x2 lr = add2(log1p_neg_small2(pack2(f0, f1)), pack2(lo0 ? -0.34657359f : 0.f, lo1 ? -0.34657359f : 0.f));
+    sp = fma2(lr, pack2(-1.f, -1.f), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));     // max(x, 0) - log(r)
+    sg = pack2(x0 >= 0.f ? r0 : tr0, x1 >= 0.f ? r1 : tr1);
+}
+__device__ __forceinline__ void bce_bg_pair(float x0, float x1, f32x2 k2, f32x2 &acc2, float &g0, float &g1) {
+    f32x2 sp, sg;
+    softplus_sigmoid_pair(x0, x1, sp, sg);
+    acc2 = add2(acc2, sp);
+    unpack2(mul2(sg, k2), g0, g1);
+}
+
 // Varifocal weighting of the background cells (label 0, target 0): w = va * sigmoid(x)^vg, loss = w * softplus(x);
 // the weight is differentiated too:  d/dx = w * (vg * (1 - sigmoid) * softplus + sigmoid).
 struct VflParams {
@@ -463,6 +489,25 @@ __device__ __forceinline__ void vfl_bg_elem(float x, float kc, const VflParams &
     g = kc * w * fmaf(vp.gamma * (1.f - sg), sp, sg);
 }
 
+// two cells, packed: w = alpha s^gamma, loss w sp, gradient k w (gamma (1 - s) sp + s)
+__device__ __forceinline__ void vfl_bg_pair(float x0, float x1, f32x2 k2, const VflParams &vp, f32x2 &acc2, float &g0,
+                                            float &g1) {
+    f32x2 sp, sg;
+    softplus_sigmoid_pair(x0, x1, sp, sg);
+    f32x2 w;
+    if (vp.gamma == 2.f) {
+        w = mul2(mul2(sg, sg), pack2(vp.alpha, vp.alpha));
+    } else {
+        float s0, s1;
+        unpack2(sg, s0, s1);
+        w = pack2(vfl_bg_weight(s0, vp), vfl_bg_weight(s1, vp));
+    }
+    acc2 = fma2(w, sp, acc2);
+    const f32x2 one_minus = fma2(sg, pack2(-1.f, -1.f), pack2(1.f, 1.f));
+    const f32x2 inner = fma2(mul2(one_minus, pack2(vp.gamma, vp.gamma)), sp, sg);
+    unpack2(mul2(mul2(w, k2), inner), g0, g1);
+}
+
 template <typename T, int VW, bool WRITE_GRAD, bool VFL>
 __global__ void __launch_bounds__(kTalThreads)
 tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ tss_dev,
@@ -472,7 +517,9 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     const int n = blockIdx.y;
     const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
     const float kc = lambda_cls / fmaxf(__ldg(tss_dev), 1.f);
+    const f32x2 k2 = pack2(kc, kc);
     float acc = 0.f;
+    f32x2 acc2 = pack2(0.f, 0.f);                          // packed BCE path: two running sums of softplus
     if (a0 < n_anchors) {
         const size_t img = (size_t)n * n_ch * n_anchors + a0;
         if (WRITE_GRAD) {
@@ -505,8 +552,16 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
                     float g[VW];
 #pragma unroll
                     for (int v = 0; v < VW; ++v) {
+                        if (VW > 1) break;                 // scalar fall-back path only
                         if (VFL) vfl_bg_elem(cur[u].get(v), kc, vp, acc, g[v]);
                         else bce_bg_elem(cur[u].get(v), kc, acc, g[v]);
+                    }
+                    if (VW > 1) {
+#pragma unroll
+                        for (int v = 0; v + 1 < VW; v += 2) {
+                            if (VFL) vfl_bg_pair(cur[u].get(v), cur[u].get(v + 1), k2, vp, acc2, g[v], g[v + 1]);
+                            else bce_bg_pair(cur[u].get(v), cur[u].get(v + 1), k2, acc2, g[v], g[v + 1]);
+                        }
                     }
                     if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
                 }
@@ -514,6 +569,11 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
 #pragma unroll
             for (int u = 0; u < U; ++u) cur[u] = nxt[u];
         }
+    }
+    {
+        float lo, hi;
+        unpack2(acc2, lo, hi);
+        acc += lo + hi;
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;

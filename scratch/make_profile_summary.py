@@ -33,7 +33,9 @@ for k, v in agg.items():
 want = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'DRAM read'), ('dram__bytes_write.sum', 'DRAM write'),
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM % (ncu peak)'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %'),
         ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue active %'), ('launch__registers_per_thread', 'regs'),
-        ('launch__grid_size', 'grid'), ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %')]
+        ('launch__grid_size', 'grid'), ('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'FMA pipe %'),
+        ('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'ALU pipe %'), ('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'XU (MUFU) pipe %'),
+        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %')]
 traffic = {}
 for title, rep, note in (("## 2. `ncu --set full` — loss kernels at cfg2 (`scratch/prof_loss.py loss`)", 'gpurun_out/r1_loss_full.ncu-rep', 'loss'),
                          ("## 3. `ncu --set full` — NMS kernels at cfg4 (`scratch/prof_loss.py nms`)", 'gpurun_out/r1_nms_full.ncu-rep', 'nms'),
