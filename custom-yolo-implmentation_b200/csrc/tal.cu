@@ -586,7 +586,8 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     }
 }
 
-// one warp per (GT, selected anchor) slot
+// One HALF-warp per (GT, selected anchor) slot: lane & 15 is the DFL bin, and the lane holds that bin of all four
+// sides, so the scalar part (CIoU, its gradient, the class cell) is issued once for two slots.
 template <typename T>
 __global__ void __launch_bounds__(128)
 tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
@@ -597,26 +598,26 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
               long long *__restrict__ fcell_off,
               float *__restrict__ fcell_val, float *__restrict__ fg_box, float *__restrict__ fg_dfl,
               float *__restrict__ fg_cls) {
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);          // slot = g * topk + r
-    const int g = slot / topk, r = slot % topk;
-    if (g >= gt_total) return;
+    const int lane = threadIdx.x & 31, bin = lane & 15, base = lane & 16;
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 4);          // slot = g * topk + r
+    const int g_raw = slot / topk, r = slot - g_raw * topk;
     float4 e = make_float4(0.f, 0.f, 0.f, -1.f);
-    if (r < sel_count[g]) e = sel[(size_t)g * kTalMaxK + r];
-    if (!(e.w >= 0.f)) {                                   // unused slot or anchor lost to another GT
-        if (lane == 0) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; fcell_off[slot] = -1; }
-        return;
-    }
-    const int idx = __float_as_int(e.x);
-    const float t = e.w;
+    if (g_raw < gt_total && r < sel_count[g_raw]) e = sel[(size_t)g_raw * kTalMaxK + r];
+    const bool live = e.w >= 0.f;                          // else: past the end, unused slot or anchor lost to another GT
+    if (!live && bin == 0 && g_raw < gt_total) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; fcell_off[slot] = -1; }
+    if (!__any_sync(0xffffffffu, live)) return;            // both halves idle
+    // an idle half walks through the same shuffles on harmless stand-in data and writes nothing
+    const int g = live ? g_raw : 0;
+    const int idx = live ? __float_as_int(e.x) : 0;
+    const float t = live ? e.w : 0.f;
     const int n = gt_image(gt_off, n_images, g);
     const T *img = preds + (size_t)n * n_ch * n_anchors;
     const float inv_tss = 1.f / fmaxf(__ldg(tss_dev), 1.f);
     const float wgt = t * inv_tss;
 
-    const int bin = lane & 15, half = lane >> 4;
-    const float z_lo = load_as_float(img + (size_t)lane * n_anchors + idx);
-    const float z_hi = load_as_float(img + (size_t)(lane + 32) * n_anchors + idx);
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
     const float *g5 = gt + (size_t)g * 5;
     const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
     int cls = (int)__ldg(g5 + 4);
@@ -624,28 +625,24 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
     const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
     const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
 
-    float m_lo = z_lo, m_hi = z_hi;
+    // softmax and expectation of each side over the 16 lanes of the half (xor offsets <= 8 stay inside it)
+    float mx[4], sm[4], pr[4], ds[4];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, o));
-        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, o));
-    }
-    const float e_lo = expf(z_lo - m_lo), e_hi = expf(z_hi - m_hi);
-    float s_lo = e_lo, s_hi = e_hi;
+    for (int k = 0; k < 4; ++k) {
+        float m = z[k];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        s_lo += __shfl_xor_sync(0xffffffffu, s_lo, o);
-        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
-    }
-    const float p_lo = __fdiv_rn(e_lo, s_lo), p_hi = __fdiv_rn(e_hi, s_hi);
-    float d_lo = p_lo * (float)bin, d_hi = p_hi * (float)bin;
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float ex = expf(z[k] - m);
+        float sum = ex;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        d_lo += __shfl_xor_sync(0xffffffffu, d_lo, o);
-        d_hi += __shfl_xor_sync(0xffffffffu, d_hi, o);
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float p = __fdiv_rn(ex, sum);
+        float d = p * (float)bin;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        mx[k] = m; sm[k] = sum; pr[k] = p; ds[k] = d;
     }
-    const float dl = __shfl_sync(0xffffffffu, d_lo, 0), dt = __shfl_sync(0xffffffffu, d_lo, 16);
-    const float dr = __shfl_sync(0xffffffffu, d_hi, 0), db = __shfl_sync(0xffffffffu, d_hi, 16);
+    const float dl = ds[0], dt = ds[1], dr = ds[2], db = ds[3];
     const PredBox b = decode_box(ax, ay, s, dl, dt, dr, db);
     const float4 pb = make_float4(b.x1, b.y1, b.x2, b.y2);
     const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
@@ -682,37 +679,30 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
     gy2 -= c.alpha * dv_dh1;
     // L_box = (1 - ciou) * t / tss * lambda_box
     const float kb = -lambda_box * wgt;
-    const float d_dl = kb * gx1 * (-s), d_dt = kb * gy1 * (-s), d_dr = kb * gx2 * s, d_db = kb * gy2 * s;
+    const float dd[4] = {kb * gx1 * (-s), kb * gy1 * (-s), kb * gx2 * s, kb * gy2 * s};   // d / d (dl, dt, dr, db)
 
     // ---- DFL rows (same target rule as the reference, src/model/losses.py:226-246, :63-78) -------
-    const float t_l = ax - gb.x / s, t_t = ay - gb.y / s, t_r = gb.z / s - ax, t_b = gb.w / s - ay;
+    const float tgt[4] = {ax - gb.x / s, ay - gb.y / s, gb.z / s - ax, gb.w / s - ay};
     const float hi_clamp = (float)(kRegMax - 1 - 0.01);
-    const float t_lo = fminf(fmaxf(half == 0 ? t_l : t_t, 0.f), hi_clamp);
-    const float t_hi = fminf(fmaxf(half == 0 ? t_r : t_b, 0.f), hi_clamp);
-    const int bl_lo = (int)t_lo, bl_hi = (int)t_hi;
-    const float wl_lo = (float)(bl_lo + 1) - t_lo, wr_lo = t_lo - (float)bl_lo;
-    const float wl_hi = (float)(bl_hi + 1) - t_hi, wr_hi = t_hi - (float)bl_hi;
-    const float lp_lo = (z_lo - m_lo) - logf(s_lo), lp_hi = (z_hi - m_hi) - logf(s_hi);
-    const int base = lane & 16;
-    const float ce_lo = -(__shfl_sync(0xffffffffu, lp_lo, base + bl_lo) * wl_lo +
-                          __shfl_sync(0xffffffffu, lp_lo, base + bl_lo + 1) * wr_lo);
-    const float ce_hi = -(__shfl_sync(0xffffffffu, lp_hi, base + bl_hi) * wl_hi +
-                          __shfl_sync(0xffffffffu, lp_hi, base + bl_hi + 1) * wr_hi);
-    const float ce_half = ce_lo + ce_hi;
-    const float dfl4 = ce_half + __shfl_xor_sync(0xffffffffu, ce_half, 16);      // sum over the four sides
     const float kd = lambda_dfl * wgt * 0.25f;
+    float dfl4 = 0.f, gk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float tk = fminf(fmaxf(tgt[k], 0.f), hi_clamp);
+        const int bl = (int)tk;
+        const float wl = (float)(bl + 1) - tk, wr = tk - (float)bl;
+        const float lpk = (z[k] - mx[k]) - logf(sm[k]);               // log-softmax of this lane's bin
+        dfl4 -= __shfl_sync(0xffffffffu, lpk, base + bl) * wl + __shfl_sync(0xffffffffu, lpk, base + bl + 1) * wr;
+        const float oh = (bin == bl ? wl : 0.f) + (bin == bl + 1 ? wr : 0.f);
+        gk[k] = kd * ((wl + wr) * pr[k] - oh) + dd[k] * pr[k] * ((float)bin - ds[k]);
+    }
+    if (!live) return;                                     // no shuffles below
 
     if (want_grad) {
-        const float dd_lo = half == 0 ? d_dl : d_dt, dd_hi = half == 0 ? d_dr : d_db;
-        const float dk_lo = half == 0 ? dl : dt, dk_hi = half == 0 ? dr : db;
-        const float oh_lo = (bin == bl_lo ? wl_lo : 0.f) + (bin == bl_lo + 1 ? wr_lo : 0.f);
-        const float oh_hi = (bin == bl_hi ? wl_hi : 0.f) + (bin == bl_hi + 1 ? wr_hi : 0.f);
-        const float g_lo = kd * ((wl_lo + wr_lo) * p_lo - oh_lo) + dd_lo * p_lo * ((float)bin - dk_lo);
-        const float g_hi = kd * ((wl_hi + wr_hi) * p_hi - oh_hi) + dd_hi * p_hi * ((float)bin - dk_hi);
         // compact, coalesced: the dense kernel merges these 64 values into the anchor's box rows
-        fgrad[(size_t)slot * (4 * kRegMax) + lane] = g_lo;
-        fgrad[(size_t)slot * (4 * kRegMax) + 32 + lane] = g_hi;
-        if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fgrad[(size_t)slot * (4 * kRegMax) + k * kRegMax + bin] = gk[k];
+        if (bin == 0) {
             // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / tss;
             // patched in by tal_finalize_kernel after the dense kernel has written the background value
             const float sg = __fdiv_rn(1.f, 1.f + expf(-z_cls));
@@ -720,10 +710,10 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
             // varifocal: the positive cell is weighted by its own target score, a constant
             fcell_val[slot] = lambda_cls * inv_tss * (sg - t) * (vfl ? t : 1.f);
         }
-    } else if (lane == 0) {
+    } else if (bin == 0) {
         fcell_off[slot] = -1;
     }
-    if (lane == 0) {
+    if (bin == 0) {
         fg_box[slot] = (1.f - c.value) * t;
         fg_dfl[slot] = dfl4 * 0.25f * t;
         if (vfl) {
@@ -845,7 +835,7 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
     const int n_ch = 4 * kRegMax + nc;
     if (gt_total > 0) {                                    // foreground terms first: the dense kernel merges their gradient
         const int slots = gt_total * topk;
-        tal_fg_kernel<T><<<(slots + 3) / 4, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
+        tal_fg_kernel<T><<<(slots + 7) / 8, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
                                                          gt_total, topk, w.sel, w.sel_count, tss_dev, lambda_box, lambda_cls,
                                                          lambda_dfl, vfl, vp, grad != nullptr, w.fgrad, w.fcell_off, w.fcell_val,
                                                          w.fg_box, w.fg_dfl, w.fg_cls);
