@@ -157,6 +157,7 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
     constexpr int NW = kTalThreads / 32;
     constexpr int NG = TILE / 32;                          // groups of 32 consecutive anchors (<= 32)
     constexpr int GL = 32 / VW;                            // lanes that share one group
+    constexpr int NE = VW == 8 ? 8 : 4;                    // queue entries per lane the register top-k holds
     // dynamic shared memory: 24 B per anchor of the tile + 6 B per anchor and warp (see tal_cand_smem)
     extern __shared__ __align__(16) unsigned char tal_smem[];
     float4 *s_box = reinterpret_cast<float4 *>(tal_smem);                         // decoded xyxy (pixels)
@@ -280,6 +281,25 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
         int my_q = lane, my_m = 0;
         if (nq <= topk) {
             if (lane < nq) my_m = __float_as_int(s_qm[warp][lane]);
+        } else if (nq <= 32 * NE) {
+            // the usual case: the lane keeps its (at most NE) queue entries q = lane + 32 i in registers
+            int v[NE];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) v[i] = lane + 32 * i < nq ? __float_as_int(s_qm[warp][lane + 32 * i]) : (int)0x80000000;
+            for (int r = 0; r < n_sel; ++r) {
+                int bm = v[0], bi = 0;                     // strict: the lowest q of the lane wins its ties
+#pragma unroll
+                for (int i = 1; i < NE; ++i)
+                    if (v[i] > bm) { bm = v[i]; bi = i; }
+                const int wm = __reduce_max_sync(0xffffffffu, bm);
+                const int wq = __reduce_min_sync(0xffffffffu, bm == wm ? lane + 32 * bi : 0x7fffffff);
+                if (lane == r) { my_q = wq; my_m = wm; }
+                if (lane == (wq & 31)) {
+#pragma unroll
+                    for (int i = 0; i < NE; ++i)
+                        if (i == (wq >> 5)) v[i] = (int)0x80000000;          // taken
+                }
+            }
         } else {
             for (int r = 0; r < n_sel; ++r) {
                 int bm = -1, bq = 0x7fffffff;
