@@ -166,6 +166,7 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
     float (*s_qm)[TILE] = reinterpret_cast<float (*)[TILE]>(s_grp + NG);          // per-warp queue: metric
     unsigned short (*s_q)[TILE] = reinterpret_cast<unsigned short (*)[TILE]>(&s_qm[NW][0]);   //     anchor
     __shared__ float s_bb[4][NW];                        // tile extent of the anchor centres
+    __shared__ int s_next_gt;
 
     const int n = blockIdx.y;
     const int tile0 = blockIdx.x * TILE;
@@ -175,6 +176,7 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
     const int g_begin = gt_off[n];
     const int m_img = gt_off[n + 1] - g_begin;
     if (m_img == 0) return;                               // uniform per CTA
+    if (threadIdx.x == 0) s_next_gt = 0;                  // visible after the barrier below
 
     float lo_x = __int_as_float(0x7f800000), lo_y = lo_x, hi_x = -lo_x, hi_y = -lo_x;
     if (a0 < n_anchors) {
@@ -230,7 +232,12 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
     float4 my_grp = make_float4(0.f, 0.f, -1.f, -1.f);    // an empty extent never intersects
     if (lane < NG) my_grp = s_grp[lane];
 
-    for (int g = warp; g < m_img; g += NW) {                              // one warp per GT
+    // one warp per GT, handed out from a shared counter: GTs that miss the tile cost nothing, the others a lot
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&s_next_gt, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= m_img) break;
         const float *g5 = gt + (size_t)(g_begin + g) * 5;
         const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
         const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
