@@ -937,7 +937,7 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
         const size_t csmem = sizeof(float4) * (size_t)kClassCap;      // boxes; later keys + histogram + selection
         YB_CUDA(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         // CTAs per image: enough to put every SM to work on small batches
-        const int split = n_images >= 96 ? 1 : (n_images >= 48 ? 2 : 4);
+        const int split = n_images >= 96 ? 1 : (n_images >= 48 ? 2 : (n_images >= 24 ? 4 : 8));
         nms_class_kernel<<<dim3(split, n_images), kClassThreads, csmem, st>>>(
             prediction, nc, n_anchors, w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det,
             w.mode, out_rows, out_count, out_anchor);

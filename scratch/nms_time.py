@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 from custom_yolo_implmentation_b200.utils import synthetic as syn
 from custom_yolo_implmentation_b200.utils import model_utils as U
 dev = torch.device('cuda:0')
-for n in (64, 16, 128):
+for n in (64, 16, 8, 32, 128):
     y = syn.make_nms_input(n, 80, 640, 2024).to(dev)
     for _ in range(5): rows, count, _ = U.batched_nms_raw(y, 0.001, 0.7, 300, 80, False, None)
     torch.cuda.synchronize()
