@@ -36,6 +36,9 @@ constexpr float kEpsIn = 1e-9f;
 constexpr float kEpsNorm = 1e-9f;
 constexpr float kFourOverPi2 = 0.40528473456935109f;
 constexpr int kTalFinThreadsDecl = 256;
+#ifndef YB_TAL_CLS_UNROLL
+#define YB_TAL_CLS_UNROLL 4
+#endif
 #ifndef YB_TAL_CAND_MINBLOCKS
 #define YB_TAL_CAND_MINBLOCKS 8
 #endif
@@ -563,7 +566,7 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
             }
         }
         const size_t base = img + (size_t)4 * kRegMax * n_anchors;
-        constexpr int U = 4;
+        constexpr int U = YB_TAL_CLS_UNROLL;
         Group<T, VW> cur[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
