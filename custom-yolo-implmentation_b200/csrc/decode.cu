@@ -127,16 +127,35 @@ val_scan_kernel(const T *__restrict__ preds, int n_ch, int nc, int n_anchors, fl
     int arg[VW];
     int n_pass = 0;
     if (a0 < n_anchors) {
+        // The reference takes max / argmax over the SIGMOIDS (train_model.py:115-116): first index among the largest
+        // float sigmoid.  The sigmoid is monotone, so the pass tracks the largest LOGIT (first index) and the largest
+        // logit before it; one sigmoid per anchor at the end.  Only when that earlier logit rounds to the same (or a
+        // larger) sigmoid can an earlier class win the tie: that anchor is then redone the reference's way.
+        const float ninf = -__int_as_float(0x7f800000);
+        float bx[VW], sx[VW];
 #pragma unroll
-        for (int v = 0; v < VW; ++v) { best[v] = -1.f; arg[v] = 0; }
+        for (int v = 0; v < VW; ++v) { bx[v] = ninf; sx[v] = ninf; arg[v] = 0; }
         const size_t base = ((size_t)n * n_ch + 4 * kRegMax) * n_anchors + a0;
         for (int c = 0; c < nc; ++c) {
             Group<T, VW> row;
             row.load(preds + base + (size_t)c * n_anchors);
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
-                const float s = __fdiv_rn(1.f, 1.f + expf(-row.get(v)));      // Tensor.sigmoid()
-                if (s > best[v]) { best[v] = s; arg[v] = c; }
+                const float x = row.get(v);
+                if (x > bx[v]) { sx[v] = bx[v]; bx[v] = x; arg[v] = c; }
+            }
+        }
+        auto sigmoid = [](float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); };       // Tensor.sigmoid()
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            best[v] = bx[v] > ninf ? sigmoid(bx[v]) : -1.f;
+            if (sx[v] > ninf && sigmoid(sx[v]) >= best[v]) {                          // rare: a tie in sigmoid space
+                best[v] = -1.f;
+                arg[v] = 0;
+                for (int c = 0; c < nc; ++c) {
+                    const float sg = sigmoid(load_as_float(preds + base + (size_t)c * n_anchors + v));
+                    if (sg > best[v]) { best[v] = sg; arg[v] = c; }
+                }
             }
         }
 #pragma unroll

@@ -107,3 +107,28 @@ def test_tal_gt_without_inside_anchor_and_out_of_range_class(cuda_device):
     assert (asg[1] == -1).all()
     assert abs(out[0].item() - ora.total.item()) <= 1e-5 * abs(ora.total.item())
     assert (grad.cpu() - ora.grad).abs().max().item() <= 1e-5 * ora.grad.abs().max().item()
+
+
+def test_val_decode_class_ties_in_sigmoid_space(cuda_device):
+    """decode_predictions takes the argmax over float SIGMOIDS (train_model.py:115-116): two different logits can
+    round to the same sigmoid, and then the EARLIER class wins even if its logit is the smaller one.  The kernel
+    tracks logits and must fall back to the reference's rule exactly in that case."""
+    from custom_yolo_implmentation_b200.training.train_model import decode_predictions_raw
+    from oracle import decode_oracle as D
+    anchors, strides = syn.anchor_grid(160)
+    a = anchors.shape[1]
+    preds = syn.make_preds(2, 6, a, 601, cls_mean=-2.0, cls_std=1.0)
+    cls = preds[:, 64:]
+    cls[0, :, 0:40] = torch.tensor([17.0, 18.0, 20.0, -3.0, 19.0, 30.0])[:, None]      # all saturate to 1.0: class 0 wins
+    cls[0, :, 40:80] = torch.tensor([-3.0, 9.99995, 10.0, 9.9999, -1.0, 0.0])[:, None]  # near-ties around 10
+    cls[1, :, 0:40] = torch.tensor([-120.0, -110.0, -105.0, -130.0, -104.0, -200.0])[:, None]   # all underflow to 0
+    cls[1, 2, 40:80] = 5.0
+    cls[1, 4, 40:80] = 5.0                                                              # exactly equal logits: first wins
+    rows, count, anchor = decode_predictions_raw(preds.to(cuda_device), anchors.to(cuda_device), strides.to(cuda_device),
+                                                 0.0, a, 6, want_anchor=True)
+    ora = D.val_decode(preds, anchors, strides, 0.0, a, 6)
+    for b in range(2):
+        k = int(count[b])
+        assert k == a == ora.rows[b].shape[0]                                           # conf 0: every anchor is kept, anchor order
+        assert torch.equal(anchor[b, :k].cpu().long(), ora.anchor[b])
+        assert torch.equal(rows[b, :k, 4].cpu(), ora.rows[b][:, 4])                     # class ids, bit-exact
