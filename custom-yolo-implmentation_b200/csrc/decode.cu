@@ -127,7 +127,7 @@ val_scan_kernel(const T *__restrict__ preds, int n_ch, int nc, int n_anchors, fl
     int arg[VW];
     int n_pass = 0;
     if (a0 < n_anchors) {
-        // The reference takes max / argmax over the SIGMOIDS (train_model.py:115-116): first index among the largest
+        // The reference takes max / argmax over the SIGMOIDS (train_model.py:116-119): first index among the largest
         // float sigmoid.  The sigmoid is monotone, so the pass tracks the largest LOGIT (first index) and the largest
         // logit before it; one sigmoid per anchor at the end.  Only when that earlier logit rounds to the same (or a
         // larger) sigmoid can an earlier class win the tie: that anchor is then redone the reference's way.

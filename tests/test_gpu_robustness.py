@@ -110,7 +110,7 @@ def test_tal_gt_without_inside_anchor_and_out_of_range_class(cuda_device):
 
 
 def test_val_decode_class_ties_in_sigmoid_space(cuda_device):
-    """decode_predictions takes the argmax over float SIGMOIDS (train_model.py:115-116): two different logits can
+    """decode_predictions takes the argmax over float SIGMOIDS (train_model.py:116-119): two different logits can
     round to the same sigmoid, and then the EARLIER class wins even if its logit is the smaller one.  The kernel
     tracks logits and must fall back to the reference's rule exactly in that case."""
     from custom_yolo_implmentation_b200.training.train_model import decode_predictions_raw
