@@ -71,35 +71,65 @@ detection_match_kernel(const float *__restrict__ pred_rows, int row_stride, cons
     }
     unsigned used = 0;                                     // bit t: my t-th strided target is consumed
     int tp = 0, fp = 0;
-    for (int i = 0; i < p_all; ++i) {                      // prediction order matters: sequential
-        if (sc && !(sc[i] >= score_thr)) continue;         // warp-uniform
-        const float4 pb = make_float4(rows[(size_t)i * 5], rows[(size_t)i * 5 + 1], rows[(size_t)i * 5 + 2],
-                                      rows[(size_t)i * 5 + 3]);
-        const int pc = (int)rows[(size_t)i * 5 + 4];
-        float best = 0.f;
-        int bj = -1;
-        for (int j = lane, t = 0; j < m; j += 32, ++t) {
-            if ((used >> t) & 1u) continue;
-            const float *g5 = gt + (size_t)(g0 + j) * 5;
-            if ((int)g5[4] != pc) continue;
-            const float v = iou_xywh(pb, make_float4(g5[0], g5[1], g5[2], g5[3]));
-            if (v > best) { best = v; bj = j; }            // strict: first maximum within the lane
-        }
-        float wb = best;
-        int wj = bj < 0 ? 0x7fffffff : bj;
+    // the lane's first two targets stay in registers (images with up to 64 targets never re-read them)
+    float4 gbox[2];
+    int gcls[2];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, wj, o);
-            if (ob > wb || (ob == wb && oj < wj)) { wb = ob; wj = oj; }
+    for (int t = 0; t < 2; ++t) {
+        const int j = lane + 32 * t;
+        gbox[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gcls[t] = -0x7fffffff;
+        if (j < m) {
+            const float *g5 = gt + (size_t)(g0 + j) * 5;
+            gbox[t] = make_float4(g5[0], g5[1], g5[2], g5[3]);
+            gcls[t] = (int)g5[4];
         }
-        if (wj != 0x7fffffff && wb >= iou_thr) {           // :136-141 (an IoU of 0 never selects a target)
-            ++tp;
-            if ((wj & 31) == lane) used |= 1u << (wj >> 5);
-            if (lane == 0) bump(counters, nc, 0, pc);
-        } else {
-            ++fp;
-            if (lane == 0) bump(counters, nc, 1, pc);
+    }
+    for (int i0 = 0; i0 < p_all; i0 += 32) {               // 32 predictions at a time: lane l fetches row i0 + l
+        float4 my_pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        int my_pc = 0;
+        bool my_ok = false;
+        if (i0 + lane < p_all) {
+            const float *r5 = rows + (size_t)(i0 + lane) * 5;
+            my_pb = make_float4(r5[0], r5[1], r5[2], r5[3]);
+            my_pc = (int)r5[4];
+            my_ok = !sc || sc[i0 + lane] >= score_thr;
+        }
+        const unsigned ok_mask = __ballot_sync(0xffffffffu, my_ok);
+        const int n_here = min(32, p_all - i0);
+        for (int k = 0; k < n_here; ++k) {                 // prediction order matters: sequential
+            if (!((ok_mask >> k) & 1u)) continue;          // warp-uniform
+            const float4 pb = make_float4(__shfl_sync(0xffffffffu, my_pb.x, k), __shfl_sync(0xffffffffu, my_pb.y, k),
+                                          __shfl_sync(0xffffffffu, my_pb.z, k), __shfl_sync(0xffffffffu, my_pb.w, k));
+            const int pc = __shfl_sync(0xffffffffu, my_pc, k);
+            float best = 0.f;
+            int bj = 0x7fffffff;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (!((used >> t) & 1u) && gcls[t] == pc) {
+                    const float v = iou_xywh(pb, gbox[t]);
+                    if (v > best) { best = v; bj = lane + 32 * t; }           // strict: first maximum within the lane
+                }
+            }
+            for (int j = lane + 64, t = 2; j < m; j += 32, ++t) {
+                if ((used >> t) & 1u) continue;
+                const float *g5 = gt + (size_t)(g0 + j) * 5;
+                if ((int)g5[4] != pc) continue;
+                const float v = iou_xywh(pb, make_float4(g5[0], g5[1], g5[2], g5[3]));
+                if (v > best) { best = v; bj = j; }
+            }
+            // IoUs are >= 0, so their bit patterns order like integers; ties go to the lowest target index
+            const int wbi = __reduce_max_sync(0xffffffffu, __float_as_int(best));
+            const int wj = __reduce_min_sync(0xffffffffu, __float_as_int(best) == wbi ? bj : 0x7fffffff);
+            const float wb = __int_as_float(wbi);
+            if (wj != 0x7fffffff && wb >= iou_thr) {       // :136-141 (an IoU of 0 never selects a target)
+                ++tp;
+                if ((wj & 31) == lane) used |= 1u << (wj >> 5);
+                if (lane == 0) bump(counters, nc, 0, pc);
+            } else {
+                ++fp;
+                if (lane == 0) bump(counters, nc, 1, pc);
+            }
         }
     }
     int fn = 0;
