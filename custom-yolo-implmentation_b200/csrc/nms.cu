@@ -411,7 +411,7 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     __shared__ int s_flag, s_total;
     __shared__ unsigned s_minx, s_maxx;
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_k;
+    __shared__ int s_k, s_exact;
     __shared__ float4 s_rowbox[kClassThreads / 32][32];   // per warp: kept rows of the current 32-box block
     __shared__ float s_rowla[kClassThreads / 32][32];     //           and log2 of their areas
     __shared__ unsigned short s_order[kClassMaxNc + 1];   // this CTA's classes, largest segment first
@@ -670,7 +670,7 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
     const unsigned long long key_mask = (1ull << 54) - 1ull;
     unsigned long long limit = key_mask;                   // select every survivor whose key54 <= limit
     if (n_surv > max_det) {
-        if (tid == 0) { s_prefix = 0ull; s_k = max_det; }
+        if (tid == 0) { s_prefix = 0ull; s_k = max_det; s_exact = 0; }
         int shift = 54;
         for (int pass = 0; pass < 5; ++pass) {
             const int bits = pass < 4 ? kSelBits : 54 - 4 * kSelBits;
@@ -708,6 +708,7 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
                         if (run + h >= k) {
                             s_prefix = (prefix << bits) | (unsigned long long)(lane * per + b);
                             s_k = k - run;
+                            s_exact = (run + h == k) ? 1 : 0;      // the whole bucket is wanted: no need to look inside it
                             break;
                         }
                         run += h;
@@ -715,8 +716,12 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
                 }
             }
             __syncthreads();
+            if (s_exact) {                                 // every key with this prefix (or a smaller one) is selected
+                limit = (s_prefix << shift) | ((1ull << shift) - 1ull);
+                break;
+            }
+            if (pass == 4) limit = s_prefix;               // the max_det-th smallest key
         }
-        limit = s_prefix;                                  // the max_det-th smallest key
     }
     YB_MARK(6);
     // collect, sort (ascending key = descending score), emit
