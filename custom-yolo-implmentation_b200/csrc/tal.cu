@@ -552,19 +552,19 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     f32x2 acc2 = pack2(0.f, 0.f);                          // packed BCE path: two running sums of softplus
     if (a0 < n_anchors) {
         const size_t img = (size_t)n * n_ch * n_anchors + a0;
-        if (WRITE_GRAD) {
-            // box rows: zero, except the foreground anchors, whose 64 values tal_fg_kernel left in fgrad
-            int fo[VW];                                    // offset of the anchor's 64 values in fgrad, -1 = background
+        // box rows of the gradient: zero, except the foreground anchors, whose 64 values tal_fg_kernel left in fgrad
+        // (predicated loads, no divergence).  One box row is written per class row of the loop below, so that the
+        // kernel's reads and writes stay interleaved instead of opening with a write-only burst.
+        int fo[VW];                                        // offset of the anchor's 64 values in fgrad, < 0 = background
 #pragma unroll
-            for (int v = 0; v < VW; ++v) fo[v] = (__ldg(aslot + (size_t)n * n_anchors + a0 + v) - 1) * (4 * kRegMax);
-#pragma unroll 8
-            for (int c = 0; c < 4 * kRegMax; ++c) {        // predicated loads, no divergence; rows are independent
-                float vals[VW];
+        for (int v = 0; v < VW; ++v)
+            fo[v] = WRITE_GRAD ? (__ldg(aslot + (size_t)n * n_anchors + a0 + v) - 1) * (4 * kRegMax) : -1;
+        auto box_row = [&](int c) {
+            float vals[VW];
 #pragma unroll
-                for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? __ldg(fgrad + fo[v] + c) : 0.f;
-                Group<T, VW>::store(grad + img + (size_t)c * n_anchors, vals);
-            }
-        }
+            for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? __ldg(fgrad + fo[v] + c) : 0.f;
+            Group<T, VW>::store(grad + img + (size_t)c * n_anchors, vals);
+        };
         const size_t base = img + (size_t)4 * kRegMax * n_anchors;
         constexpr int U = YB_TAL_CLS_UNROLL;
         Group<T, VW> cur[U];
@@ -593,12 +593,17 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
                             else bce_bg_pair(cur[u].get(v), cur[u].get(v + 1), k2, acc2, g[v], g[v + 1]);
                         }
                     }
-                    if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
+                    if (WRITE_GRAD) {
+                        Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
+                        if (c + u < 4 * kRegMax) box_row(c + u);
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) cur[u] = nxt[u];
         }
+        if (WRITE_GRAD)
+            for (int c = nc; c < 4 * kRegMax; ++c) box_row(c);      // fewer classes than box rows
     }
     {
         float lo, hi;
