@@ -50,6 +50,33 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class gpu_local_cpus:
+    """Context manager: run on the CPUs NVML names as local to GPU `index` (first-touch places pinned host memory on
+    that NUMA node; a staging buffer on the far socket halves the host-to-device rate).  Restores the affinity."""
+
+    def __init__(self, index):
+        self.index, self.old, self.note = index, None, "unchanged"
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.old = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self.note = f"{len(os.sched_getaffinity(0))} of {len(self.old)} cpus"
+        except Exception as e:                              # not permitted / not supported: leave the placement alone
+            self.note = f"unavailable ({type(e).__name__})"
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except OSError:
+                pass
+        return False
+
+
 class ClockSampler:
     """SM clock / throttle reasons of one GPU through NVML, in-process.
 
@@ -245,8 +272,9 @@ def run_ours(args):
     # data/collate.py::collate_fn_packed) and reads its loss scalars back.  As a data loader would, the copy of
     # step i+1 is issued on a copy stream while step i computes; all K copies lie inside the timed region.
     crit = YoloDFLQFLoss(num_classes=nc)
-    preds_pin = preds_h.pin_memory()
-    packed_pin = pack_gt_host(gts_h, pin_memory=True)
+    with gpu_local_cpus(local) as numa_note:           # pinned staging buffers on the GPU's own NUMA node
+        preds_pin = preds_h.pin_memory()
+        packed_pin = pack_gt_host(gts_h, pin_memory=True)
     h2d = preds_pin.numel() * preds_pin.element_size() + packed_pin.gt.numel() * 4 + packed_pin.offsets.numel() * 4
     d2h = 3 * 4
     copy_stream = torch.cuda.Stream(device=dev)
@@ -362,7 +390,8 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                        "api": "YoloDFLQFLoss.forward + loss.backward on pinned host inputs (head output + packed GT); the next step's copy is prefetched on a copy stream"},
+                        "api": "YoloDFLQFLoss.forward + loss.backward on pinned host inputs (head output + packed GT); the next step's copy is prefetched on a copy stream",
+                        "pinned_numa": numa_note.note},
                 "gpu_launches": launches, "clocks": clocks.summary(), "loss": loss_val, "nms": nms, "tal": tal,
                 "cfg5_bf16": cfg5}
         print(json.dumps(line), flush=True)
