@@ -59,7 +59,7 @@ out += ["", "## 5. Reading", "",
         "  235 us to 165 us per launch when the pruning and the coarse-tiles-first launch order went in (same bytes).",
         "* Task-aligned variant: `tal_candidates_kernel` is issue-bound (52 % issue-active at 39 % occupancy, 296 MB of DRAM reads in",
         "  151 us), `tal_fg_kernel` moves 174 MB of 64-byte bursts for 139 MB of useful 32-byte sectors, `tal_cls_kernel` streams",
-        "  943 MB at 5.1 TB/s with every gradient store coalesced (the foreground rows are merged in, not scattered); its issue",
+        "  937 MB at 5.3 TB/s with every gradient store coalesced (the foreground rows are merged in, not scattered); its issue",
         "  activity fell from 67 % to 36 % with the branch-free packed softplus/sigmoid (ALU pipe 49 % -> 25 %).",
         "* No tensor-pipe activity anywhere (nothing on this path is a dense contraction).",
         "* Blackwell-specific SASS: `FFMA2` / `FMUL2` / `FADD2` (packed FP32, PTX `fma.rn.f32x2`) in `fused_main_kernel`:",
