@@ -20,6 +20,7 @@
 //                    QFL cell of each matched anchor (loss delta + gradient).
 //   finalize_kernel  one warp per image reduces that image's partial sums; the last CTA adds the
 //                    images up; everything in a fixed order, so the loss is run-to-run identical.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -49,6 +50,9 @@ namespace yb {
 #endif
 #ifndef YB_ASSIGN_PRUNE
 #define YB_ASSIGN_PRUNE 1
+#endif
+#ifndef YB_BOX_SKEW                   // tile groups by which a box CTA precedes its tile's class CTAs in launch order
+#define YB_BOX_SKEW 256
 #endif
 #ifndef YB_COARSE_FRAC256
 #define YB_COARSE_FRAC256 61
@@ -776,7 +780,7 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kAssignThreads, YB_FUSED_MINBLOCKS ? YB_FUSED_MINBLOCKS : (VW == 8 ? 5 : 6))
 fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc, int n_tiles, int coarse,
-                  const float *__restrict__ anchors,
+                  int skew, const float *__restrict__ anchors,
                   const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
                   unsigned long long *__restrict__ best, int *__restrict__ gt_img, float k_cls, T *__restrict__ grad,
                   float *__restrict__ part) {
@@ -786,20 +790,34 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     // (image-major again).  Roles of a tile stay adjacent, so every SM holds a mix of box and class CTAs.
     const bool prune = coarse >= 0;                        // coarse < 0: YB_ASSIGN_PRUNE=0 in the environment (tests)
     coarse = max(coarse, 0);
-    int id = blockIdx.x, image, tile, role;
+    // A tile's box CTA lives about three times as long as one of its class CTAs, so it is launched `skew` tile
+    // groups AHEAD of them: the first `skew` blocks are the box CTAs of the first groups, and the last groups of
+    // the grid carry class CTAs only -- the grid drains on short CTAs instead of waiting for a few long ones.
+    int group, role, image, tile;
     {
-        const int per_c = coarse * ROLES, per_f = (n_tiles - coarse) * ROLES;
-        if (id < per_c * n_images) {
-            image = id / per_c;
-            id -= image * per_c;
-            tile = n_tiles - coarse + id / ROLES;
+        const int n_groups = n_tiles * n_images;
+        int id = blockIdx.x;
+        if (id < skew) {
+            group = id;
+            role = 0;
         } else {
-            id -= per_c * n_images;
-            image = id / per_f;
-            id -= image * per_f;
-            tile = id / ROLES;
+            id -= skew;
+            group = id / ROLES;
+            role = id - group * ROLES;
+            if (role == 0) {
+                group += skew;
+                if (group >= n_groups) return;             // the box CTAs of the last groups went out earlier
+            }
         }
-        role = id % ROLES;
+        const int groups_c = coarse * n_images;
+        if (group < groups_c) {
+            image = group / coarse;
+            tile = n_tiles - coarse + (group - image * coarse);
+        } else {
+            const int fine = n_tiles - coarse, gf = group - groups_c;
+            image = gf / fine;
+            tile = gf - image * fine;
+        }
     }
     if (role == 0)
         assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
@@ -884,16 +902,17 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
             const char *e = getenv("YB_ASSIGN_PRUNE");
             if (e && e[0] == '0') coarse = -1;
         }
-        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images;
+        const int skew = (int)std::min<long long>(YB_BOX_SKEW, (long long)n_tiles * n_images);
+        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + skew;
         YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
         if (grad != nullptr)
             fused_main_kernel<T, VW, true><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, grad,
-                w.part);
+                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, skew, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls,
+                grad, w.part);
         else
             fused_main_kernel<T, VW, false><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, grad,
-                w.part);
+                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, skew, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls,
+                grad, w.part);
         YB_LAUNCH_CHECK();
     } else {
         assign_kernel<T, VW><<<dim3(n_tiles, n_images), kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt,
