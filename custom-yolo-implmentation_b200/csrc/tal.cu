@@ -171,8 +171,10 @@ tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, cons
     __shared__ float s_bb[4][NW];                        // tile extent of the anchor centres
     __shared__ int s_next_gt;
 
-    const int n = blockIdx.y;
-    const int tile0 = blockIdx.x * TILE;
+    // Launch order: image fastest, LAST tile first.  The coarse levels sit at the end of the anchor axis and meet
+    // nearly every GT of their image, so their CTAs are the long ones: they go out first and the grid drains on short ones.
+    const int n = blockIdx.x;
+    const int tile0 = ((int)gridDim.y - 1 - (int)blockIdx.y) * TILE;
     const int a0 = tile0 + threadIdx.x * VW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t img = (size_t)n * n_ch * n_anchors;
@@ -842,7 +844,7 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
     if (out_tscore) YB_CUDA(cudaMemsetAsync(out_tscore, 0, sizeof(float) * (size_t)n_images * n_anchors, st));
     if (gt_total > 0) {
         constexpr int TILE = kTalThreads * VW;
-        dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
+        dim3 grid(n_images, (n_anchors + TILE - 1) / TILE);
         const size_t smem = tal_cand_smem(TILE);
         YB_CUDA(cudaFuncSetAttribute(tal_candidates_kernel<T, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tal_candidates_kernel<T, VW><<<grid, kTalThreads, smem, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
