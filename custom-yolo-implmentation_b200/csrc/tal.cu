@@ -36,6 +36,9 @@ constexpr float kEpsIn = 1e-9f;
 constexpr float kEpsNorm = 1e-9f;
 constexpr float kFourOverPi2 = 0.40528473456935109f;
 constexpr int kTalFinThreadsDecl = 256;
+// CTAs per anchor tile in the dense pass (each takes 1/SPLIT of the class and box rows): measured best 8 for
+// 512-anchor (fp32) tiles, 4 for 1024-anchor (bf16) tiles; the scalar fall-back (128-anchor tiles) uses 8 too
+__host__ __device__ constexpr int tal_cls_split(int tile) { return tile >= 1024 ? 4 : 8; }
 #ifndef YB_TAL_CLS_UNROLL
 #define YB_TAL_CLS_UNROLL 4
 #endif
@@ -87,7 +90,7 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     off += round_up(sizeof(int) * (size_t)n_images * n_anchors, 64);
     w.zero_bytes = off;
     w.cand_cap = topk * tiles;
-    w.cls_tiles = tiles;
+    w.cls_tiles = tiles * tal_cls_split(tile);             // partial sums per image
     w.cand = reinterpret_cast<float4 *>(p + off);
     off += round_up(sizeof(float4) * g * (size_t)w.cand_cap, 64);
     w.sel = reinterpret_cast<float4 *>(p + off);
@@ -111,9 +114,9 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     w.fcell_val = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * g * kTalMaxK, 64);
     w.part = reinterpret_cast<float *>(p + off);
-    off += round_up(sizeof(float) * (size_t)n_images * tiles, 64);
+    off += round_up(sizeof(float) * (size_t)n_images * w.cls_tiles, 64);
     w.cta_sums = reinterpret_cast<double *>(p + off);
-    off += round_up(sizeof(double) * 4 * (((size_t)n_images * tiles + g * kTalMaxK) / kTalFinThreadsDecl + 2), 64);
+    off += round_up(sizeof(double) * 4 * (((size_t)n_images * w.cls_tiles + g * kTalMaxK) / kTalFinThreadsDecl + 2), 64);
     w.total_bytes = off;
     return w;
 }
@@ -546,8 +549,15 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
                float lambda_cls, VflParams vp, const int *__restrict__ aslot, const float *__restrict__ fgrad,
                T *__restrict__ grad, float *__restrict__ part) {
     __shared__ float s_red[kTalThreads / 32];
+    // kTalClsSplit CTAs share an anchor tile: each takes a slice of the class rows and of the box rows, so the CTAs
+    // are short and the grid has several waves (one CTA per tile left a 1.6-wave grid with a long tail)
+    constexpr int kTalClsSplit = tal_cls_split(kTalThreads * VW);
     const int n = blockIdx.y;
-    const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
+    const int tile = blockIdx.x / kTalClsSplit, split = blockIdx.x - tile * kTalClsSplit;
+    const int a0 = (tile * kTalThreads + threadIdx.x) * VW;
+    const int c_per = (nc + kTalClsSplit - 1) / kTalClsSplit, c_lo = min(split * c_per, nc), c_hi = min(c_lo + c_per, nc);
+    constexpr int B_PER = (4 * kRegMax + kTalClsSplit - 1) / kTalClsSplit;
+    const int b_lo = min(split * B_PER, 4 * kRegMax), b_hi = min(b_lo + B_PER, 4 * kRegMax);
     const float kc = lambda_cls / fmaxf(__ldg(tss_dev), 1.f);
     const f32x2 k2 = pack2(kc, kc);
     float acc = 0.f;
@@ -572,15 +582,16 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
         Group<T, VW> cur[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (u < nc) cur[u].load(preds + base + (size_t)u * n_anchors);
-        for (int c = 0; c < nc; c += U) {
+            if (c_lo + u < c_hi) cur[u].load(preds + base + (size_t)(c_lo + u) * n_anchors);
+        int b_next = b_lo;                                 // next box row of this CTA's slice
+        for (int c = c_lo; c < c_hi; c += U) {
             Group<T, VW> nxt[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (c + U + u < nc) nxt[u].load(preds + base + (size_t)(c + U + u) * n_anchors);
+                if (c + U + u < c_hi) nxt[u].load(preds + base + (size_t)(c + U + u) * n_anchors);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (c + u < nc) {
+                if (c + u < c_hi) {
                     float g[VW];
 #pragma unroll
                     for (int v = 0; v < VW; ++v) {
@@ -597,7 +608,7 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
                     }
                     if (WRITE_GRAD) {
                         Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
-                        if (c + u < 4 * kRegMax) box_row(c + u);
+                        if (b_next < b_hi) box_row(b_next++);
                     }
                 }
             }
@@ -605,7 +616,7 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
             for (int u = 0; u < U; ++u) cur[u] = nxt[u];
         }
         if (WRITE_GRAD)
-            for (int c = nc; c < 4 * kRegMax; ++c) box_row(c);      // fewer classes than box rows
+            for (; b_next < b_hi; ++b_next) box_row(b_next);       // fewer class rows than box rows in this slice
     }
     {
         float lo, hi;
@@ -880,7 +891,7 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
     }
     {
         constexpr int TILE = kTalThreads * VW;
-        dim3 grid((n_anchors + TILE - 1) / TILE, n_images);
+        dim3 grid(((n_anchors + TILE - 1) / TILE) * tal_cls_split(TILE), n_images);
 #define YB_TAL_CLS(WG, VF)                                                                                           \
     tal_cls_kernel<T, VW, WG, VF><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, lambda_cls, vp, w.aslot, \
                                                                 w.fgrad, grad, w.part)
