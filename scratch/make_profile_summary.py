@@ -57,9 +57,9 @@ out += ["", "## 5. Reading", "",
         "  shortfall is gradient lines still in L2 when the kernel ends.",
         "* The box role's (GT, tile) pruning shows in the cfg5 line of section 1: `fused_main_kernel<__nv_bfloat16, 8, 1>` fell from",
         "  235 us to 165 us per launch when the pruning and the coarse-tiles-first launch order went in (same bytes).",
-        "* Task-aligned variant: `tal_candidates_kernel` is issue-bound (52 % issue-active at 39 % occupancy, 296 MB of DRAM reads in",
-        "  151 us), `tal_fg_kernel` moves 174 MB of 64-byte bursts for 139 MB of useful 32-byte sectors, `tal_cls_kernel` streams",
-        "  937 MB at 5.3 TB/s with every gradient store coalesced (the foreground rows are merged in, not scattered); its issue",
+        "* Task-aligned variant: `tal_candidates_kernel` is issue-bound (53 % issue-active at 40 % occupancy, 297 MB of DRAM reads in",
+        "  140 us), `tal_fg_kernel` moves 174 MB of 64-byte bursts for 139 MB of useful 32-byte sectors, `tal_cls_kernel` streams",
+        "  928 MB at 6.1 TB/s (152 us, eight short CTAs per tile) with every gradient store coalesced (the foreground rows are merged in, not scattered); its issue",
         "  activity fell from 67 % to 36 % with the branch-free packed softplus/sigmoid (ALU pipe 49 % -> 25 %).",
         "* No tensor-pipe activity anywhere (nothing on this path is a dense contraction).",
         "* Blackwell-specific SASS: `FFMA2` / `FMUL2` / `FADD2` (packed FP32, PTX `fma.rn.f32x2`) in `fused_main_kernel`:",
