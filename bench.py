@@ -15,19 +15,24 @@ synthetic head outputs.  Workload at every N: cfg2 of BASELINE.json per GPU (bat
               scalars back.
   roofline    dominant kernel (fused_main_kernel): algorithmic bytes / CUDA-event duration vs the
               measured copy bandwidth in MEASURED_PEAKS.json.
+  parity      on-hardware correctness of THIS run: every rank's loss scalars and matched anchors against the
+              reference's own outputs for that rank's batch (tests/golden/loss_cfg3_ranks.npz).
   cpu_baseline / --impl reference
-              the CPU oracle port of the reference's loss (oracle/loss_oracle.py; the reference is
-              Python and cannot travel to the box) on all host cores, on a bounded sample.
-  nms         cfg4 (batch 64, 8400 candidates, conf 0.001, IoU 0.7, max_det 300) through yb_nms.
+              the UNMODIFIED reference (baseline/_ref, vendored by baseline/vendor_ref.py) on the box's host
+              cores on a bounded sample; falls back to the oracle port only when baseline/_ref is missing.
+  cuda_eager_baseline (N=1)
+              the same unmodified reference code on device="cuda" (PyTorch eager on this B200): what one
+              gets without this repo.
+  nms         cfg4 (batch 64, 8400 candidates, conf 0.001, IoU 0.7, max_det 300) through yb_nms, with the
+              reference's non_max_suppression (torchvision.ops.nms per image) on CUDA and on the CPU beside it.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -37,7 +42,11 @@ import torch  # noqa: E402
 
 CFG = dict(batch_per_gpu=128, imgsz=640, nc=80, gmax=100, reg_max=16)
 CPU_SAMPLE_IMAGES = 16
+SEED0 = 1236                     # rank r draws its batch with SEED0 + r (tests/golden/loss_cfg3_ranks.npz pins ranks 0-7)
+MIN_TIMED_STEPS = 100            # the timed window never shrinks below this (one NCCL call / barrier skew must not dominate)
 METRIC = "images/sec through decode+assign+loss(+bwd)"
+WORKLOAD = ("cfg2 per GPU: batch 128, 640x640 (8400 anchors, reg_max 16), 80 classes, <=100 GT/img, "
+            "fused decode+assign+loss+backward (cfg3 = global batch 1024 at 8 GPUs)")
 
 
 def measured_peak_gbs():
@@ -130,24 +139,75 @@ def dist_env():
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# the unmodified reference (baseline/_ref), for the CPU / CUDA-eager legs.  Never on our arm's timed path.
 # ---------------------------------------------------------------------------------------------
-def cpu_loss_images_per_s(steps, warmup, seed=1236):
+_REF = None
+
+
+def reference_modules():
+    """(losses, model_utils) of the vendored reference, or None when baseline/_ref is not there.  The only
+    intervention is the frozen NMS clock, applied per call by ref_nms()."""
+    global _REF
+    if _REF is None:
+        ref_root = os.path.join(ROOT, "baseline", "_ref")
+        if not os.path.isfile(os.path.join(ref_root, "src", "model", "losses.py")):
+            _REF = False
+        else:
+            sys.path.insert(0, ref_root)
+            try:
+                import src.model.losses as ref_losses
+                import src.utils.model_utils as ref_utils
+                _REF = (ref_losses, ref_utils)
+            except Exception as e:                       # e.g. a missing third-party import on the box
+                sys.stderr.write(f"bench.py: baseline/_ref is not importable ({type(e).__name__}: {e})\n")
+                _REF = False
+            finally:
+                sys.path.remove(ref_root)
+    return _REF or None
+
+
+def ref_nms(ref_utils, y, frozen=True, **kw):
+    """The reference's non_max_suppression; `frozen` stops its wall-clock abort (model_utils.py:212, :275-277)."""
+    real = ref_utils.time
+    if frozen:
+        ref_utils.time = types.SimpleNamespace(time=lambda: 0.0)
+    try:
+        return ref_utils.non_max_suppression(y, **kw)
+    finally:
+        ref_utils.time = real
+
+
+def cpu_loss_images_per_s(steps, warmup):
+    """Reference loss forward + backward on the host cores over CPU_SAMPLE_IMAGES images of the cfg2 workload."""
     from custom_yolo_implmentation_b200.utils import synthetic as syn
-    from oracle import loss_oracle
 
     torch.set_num_threads(os.cpu_count() or 1)
     n = CPU_SAMPLE_IMAGES
-    preds, gts, anchors, strides = syn.make_loss_inputs(n, CFG["nc"], CFG["imgsz"], CFG["gmax"], seed)
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, CFG["nc"], CFG["imgsz"], CFG["gmax"], SEED0)
+    ref = reference_modules()
+    if ref is not None:
+        kind, what = "reference", "the unmodified reference's YoloDFLQFLoss.forward + loss.backward (baseline/_ref/src/model/losses.py)"
+        crit = ref[0].YoloDFLQFLoss(num_classes=CFG["nc"])
+
+        def run():
+            x = preds.clone().requires_grad_(True)
+            loss, _ = crit(x, gts, anchors, strides)
+            loss.backward()
+    else:
+        from oracle import loss_oracle
+        kind, what = "port", "oracle/loss_oracle.py fwd+bwd (baseline/_ref missing)"
+
+        def run():
+            loss_oracle.loss_forward_backward(preds, gts, anchors, strides, CFG["nc"])
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        loss_oracle.loss_forward_backward(preds, gts, anchors, strides, CFG["nc"])
+        run()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     med = statistics.median(times)
-    return n / med, med, torch.get_num_threads()
+    return n / med, med, torch.get_num_threads(), kind, what
 
 
 def run_reference(args):
@@ -156,15 +216,14 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 20))
     warmup = max(1, min(args.warmup, 3))
-    ips, med, threads = cpu_loss_images_per_s(steps, warmup)
+    ips, med, threads, kind, what = cpu_loss_images_per_s(steps, warmup)
     sample = (f"{CPU_SAMPLE_IMAGES} images of the cfg2 workload per step (640x640, 8400 anchors, nc=80, <=100 GT/img, fp32), "
-              f"oracle/loss_oracle.py fwd+bwd on torch CPU, median of {steps} steps")
+              f"{what} on torch CPU, median of {steps} steps")
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: batch 128/GPU, 640x640 (8400 anchors, reg_max 16), 80 classes, <=100 GT/img, "
-                                   "fused decode+assign+loss+backward", "cpu_sample_images": CPU_SAMPLE_IMAGES},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "cpu_sample_images": CPU_SAMPLE_IMAGES},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -180,7 +239,7 @@ def run_ours(args):
     from custom_yolo_implmentation_b200.model.losses import YoloDFLQFLoss, fused_loss, fused_tal_loss, pack_gt, pack_gt_host
     from custom_yolo_implmentation_b200.training.distributed_setup import reduce_loss_stats
     from custom_yolo_implmentation_b200.utils import synthetic as syn
-    from custom_yolo_implmentation_b200.utils.model_utils import batched_nms_raw
+    from custom_yolo_implmentation_b200.utils.model_utils import batched_nms_raw, non_max_suppression
 
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -189,16 +248,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.lib()
+    _cabi.lib()
+    warmup = max(args.warmup, 3)
+    timed_steps = max(args.steps, MIN_TIMED_STEPS)
 
     n, nc, imgsz, gmax = CFG["batch_per_gpu"], CFG["nc"], CFG["imgsz"], CFG["gmax"]
-    preds_h, gts_h, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, 1236 + rank)
+    preds_h, gts_h, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, SEED0 + rank)
     a = preds_h.shape[2]
     preds = preds_h.to(dev)
     anchors_d, strides_d = anchors.to(dev), strides.to(dev)
-    gt, off, counts = pack_gt([g.to(dev) for g in gts_h], dev)
+    gts_d = [g.to(dev) for g in gts_h]
+    gt, off, counts = pack_gt(gts_d, dev)
     gmax_real = max(counts)
     bytes_per_step = 2 * preds.numel() * preds.element_size()          # read once + gradient written once
+    peak, peak_src = measured_peak_gbs()
 
     def step():
         out, grad, _ = fused_loss(preds, gt, off, gmax_real, anchors_d, strides_d, nc, 1.0, 1.5, want_grad=True)
@@ -209,7 +272,14 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):             # results bound exactly as in the timed loop, so the caching
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(warmup):                          # results bound exactly as in the timed loop, so the caching
         out, grad = step()                           # allocator already owns both 619 MB gradient blocks
     if world > 1:
         reduce_loss_stats(out, n)                    # NCCL connects its channels lazily on the first collective
@@ -217,66 +287,125 @@ def run_ours(args):
     launches0 = _cabi.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local)
-    if True:
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            out, grad = step()
-        if world > 1:
-            # the path has no per-step exchange (every image is independent); like the reference, which
-            # all-reduces its logging scalars once per epoch (src/training/train_model.py:285-288), the
-            # loss statistics are reduced once per run — one 8-float message, inside the timed region
-            reduced = reduce_loss_stats(out, n)
-        ev1.record()
-        clocks.sample(3)                     # the GPU is still draining the queued steps: samples under load
-        barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = _cabi.launch_count - launches0
+    barrier()
+    ev0.record()
+    for _ in range(timed_steps):
+        out, grad = step()
     if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = world * n * args.steps / (elapsed_ms * 1e-3)
+        # the path has no per-step exchange (every image is independent); like the reference, which
+        # all-reduces its logging scalars once per epoch (src/training/train_model.py:285-288), the
+        # loss statistics are reduced once per run — one 8-float message, inside the timed region
+        reduced = reduce_loss_stats(out, n)
+    ev1.record()
+    clocks.sample(3)                         # the GPU is still draining the queued steps: samples under load
+    barrier()
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = (_cabi.launch_count - launches0) * args.steps // timed_steps      # per K steps, as the contract counts
+    ms_per_step = elapsed_ms / timed_steps
+    value = world * n * timed_steps / (elapsed_ms * 1e-3)
     loss_val = float(out[0].item())
 
-    # ---- per-kernel durations for the roofline (separate pass, events on the launching stream) ----
-    lib.yb_stage_timing(1)
+    # ---- on-hardware parity of this very run: each rank against the reference's outputs for ITS batch ----
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", "loss_cfg3_ranks.npz")
+    if os.path.exists(gpath) and rank < 8:
+        import numpy as np
+        z = np.load(gpath)
+        if tuple(int(v) for v in z["meta"][1:]) == (n, nc, imgsz, gmax, SEED0):
+            _, _, tr = fused_loss(preds, gt, off, gmax_real, anchors_d, strides_d, nc, 1.0, 1.5, want_grad=False, want_trace=True)
+            host = out.cpu()
+            rel = max(abs(host[k].item() - float(z[key][rank])) / abs(float(z[key][rank]))
+                      for k, key in enumerate(("total_loss", "box_loss", "cls_loss")))
+            idx_ref = torch.from_numpy(z["idx"][rank, : int(sum(counts))].astype("int64"))
+            agree = int((tr["idx"].cpu().long() == idx_ref).sum())
+            res = torch.tensor([rel, float(agree), float(sum(counts))], dtype=torch.float64, device=dev)
+            if world > 1:
+                allr = [torch.zeros_like(res) for _ in range(world)]
+                dist.all_gather(allr, res)
+            else:
+                allr = [res]
+            allr = [r.cpu().tolist() for r in allr]
+            parity = {"against": "the unmodified reference's loss scalars and matched anchors for each rank's batch "
+                                 "(tests/golden/loss_cfg3_ranks.npz, generated by tests/golden/make_golden.py)",
+                      "ranks_checked": len(allr), "loss_rel_err_max": max(r[0] for r in allr),
+                      "matched_anchors_identical": f"{int(sum(r[1] for r in allr))}/{int(sum(r[2] for r in allr))}"}
+            if parity["loss_rel_err_max"] > 1e-5 or sum(r[1] for r in allr) != sum(r[2] for r in allr):
+                raise SystemExit(f"bench.py: PARITY FAILURE on the benchmark batch: {parity}")
+    if world > 1:
+        full = reduced.cpu()
+        if not (abs(full[4].item() - world * n) < 0.5):
+            raise SystemExit(f"bench.py: the reduced statistics count {full[4].item()} images, expected {world * n}")
+
+    # ---- per-kernel durations for the roofline (separate pass, the caller's events on the launching stream) ----
+    stage_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     stage = []
-    import ctypes
-    buf = (ctypes.c_float * 3)()
     for _ in range(max(5, min(args.steps, 20))):
-        step()
-        _cabi.check(lib.yb_loss_last_stage_ms(buf), "yb_loss_last_stage_ms")
-        stage.append([buf[0], buf[1], buf[2]])
-    lib.yb_stage_timing(0)
-    main_ms, match_ms, fin_ms = (statistics.mean(s[i] for s in stage) for i in range(3))   # launch order
-    peak, peak_src = measured_peak_gbs()
+        fused_loss(preds, gt, off, gmax_real, anchors_d, strides_d, nc, 1.0, 1.5, want_grad=True, stage_events=stage_ev)
+        torch.cuda.synchronize(dev)
+        stage.append([stage_ev[0].elapsed_time(stage_ev[1]), stage_ev[1].elapsed_time(stage_ev[2])])
+    main_ms, match_ms = (statistics.mean(s[i] for s in stage) for i in range(2))
     # fused_main_kernel = box role (reads the 64 box channels, writes their gradient) + class role (reads the nc
     # class channels, writes their gradient): every byte of preds read once, every byte of grad written once
     main_bytes = bytes_per_step
     main_gbs = main_bytes / (main_ms * 1e-3) / 1e9
     traffic = None                                   # dram read+write per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and (n, nc, a, preds.element_size()) == (128, 80, 8400, 4):
-        traffic = json.load(open(tpath)).get("fused_main_kernel")
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath) and (n, nc, a, preds.element_size()) == (128, 80, 8400, 4):
+            traffic = json.load(open(tpath)).get("fused_main_kernel")
+            break
     roofline = {"bound": "hbm", "kernel": "fused_main_kernel", "achieved": main_gbs, "peak": peak, "unit": "GB/s",
                 "frac": main_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": main_bytes, "ms_per_launch": main_ms,
-                "other_kernels": {"match_kernel": {"ms": match_ms}, "finalize_kernel": {"ms": fin_ms}},
+                "other_kernels": {"match_kernel (+ final reduction)": {"ms": match_ms}},
                 "whole_step": {"algorithmic_bytes": bytes_per_step, "GB/s": bytes_per_step / (ms_per_step * 1e-3) / 1e9,
                                "frac": bytes_per_step / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    def time_steps(fn, k):
+        for _ in range(3):
+            keep = fn()
+        barrier()
+        ev0.record()
+        for _ in range(k):
+            keep = fn()
+        ev1.record()
+        barrier()
+        del keep
+        return max_over_ranks(ev0.elapsed_time(ev1) / k)
+
+    extra_steps = max(20, min(args.steps, 100))
+
+    # ---- the same step through the public module, inputs already on the device ----
+    # (what a training loop calls: GT list -> pack, autograd bridge, one D2H copy of the loss scalars per step)
+    crit = YoloDFLQFLoss(num_classes=nc)
+    x_leaf = preds.clone().requires_grad_(True)
+
+    def api_step(gt_arg):
+        x_leaf.grad = None
+        loss, parts = crit(x_leaf, gt_arg, anchors_d, strides_d)
+        loss.backward()
+        return parts
+
+    packed_d = pack_gt_host(gts_h, pin_memory=False).to(dev)
+    api_list_ms = time_steps(lambda: api_step(gts_d), extra_steps)
+    api_packed_ms = time_steps(lambda: api_step(packed_d), extra_steps)
+    api = {"what": "YoloDFLQFLoss.forward + loss.backward, head output and GT resident on the device",
+           "gt_list_of_tensors": {"ms_per_step": api_list_ms, "value": world * n / (api_list_ms * 1e-3), "unit": "images/s",
+                                  "note": "the reference's signature: 128 small device tensors packed per step (torch.cat) + loss dict D2H"},
+           "packed_gt": {"ms_per_step": api_packed_ms, "value": world * n / (api_packed_ms * 1e-3), "unit": "images/s",
+                         "note": "PackedGT wire format (data/collate.py::collate_fn_packed) + loss dict D2H"},
+           "kernels_only_ms_per_step": ms_per_step}
+    del x_leaf
 
     # ---- end to end through the public API, host inputs ----
     # Every step copies its own inputs from pinned host memory (the head output and the packed GT wire format of
     # data/collate.py::collate_fn_packed) and reads its loss scalars back.  As a data loader would, the copy of
     # step i+1 is issued on a copy stream while step i computes; all K copies lie inside the timed region.
-    crit = YoloDFLQFLoss(num_classes=nc)
     with gpu_local_cpus(local) as numa_note:           # pinned staging buffers on the GPU's own NUMA node
         preds_pin = preds_h.pin_memory()
         packed_pin = pack_gt_host(gts_h, pin_memory=True)
     h2d = preds_pin.numel() * preds_pin.element_size() + packed_pin.gt.numel() * 4 + packed_pin.offsets.numel() * 4
-    d2h = 3 * 4
+    d2h = 8 * 4
     copy_stream = torch.cuda.Stream(device=dev)
 
     def fetch():
@@ -309,59 +438,49 @@ def run_ours(args):
     parts = e2e_run(e2e_steps)
     ev1.record()
     barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
+    del preds_pin
 
     # ---- NMS (cfg4), reported alongside ----
-    nms = None
-    if rank == 0 or world > 1:
-        y = syn.make_nms_input(64, nc, imgsz, 2024 + rank).to(dev)
-        for _ in range(3):
-            rows, cnt, _ = batched_nms_raw(y, 0.001, 0.7, 300, nc)
-        barrier()
-        ev0.record()
-        nms_steps = max(5, min(args.steps, 20))
-        for _ in range(nms_steps):
-            rows, cnt, _ = batched_nms_raw(y, 0.001, 0.7, 300, nc)
-        ev1.record()
-        barrier()
-        nms_ms = ev0.elapsed_time(ev1) / nms_steps
-        if world > 1:
-            t = torch.tensor([nms_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            nms_ms = float(t.item())
-        nms_bytes = y.numel() * 4 + 64 * 300 * 6 * 4
-        nms = {"metric": "images/sec through batched class-aware NMS", "value": world * 64 / (nms_ms * 1e-3), "unit": "images/s",
-               "ms_per_step": nms_ms, "config": {"workload": "cfg4: batch 64/GPU, 8400 candidates, nc=80, conf 0.001, IoU 0.7, max_det 300"},
-               "hbm_frac_of_scan_roofline": nms_bytes / (nms_ms * 1e-3) / 1e9 / peak, "kept_min": int(cnt.min().item())}
+    y = syn.make_nms_input(64, nc, imgsz, 2024 + rank).to(dev)
+    nms_ms = time_steps(lambda: batched_nms_raw(y, 0.001, 0.7, 300, nc), max(5, min(args.steps, 20)))
+    rows, cnt, _ = batched_nms_raw(y, 0.001, 0.7, 300, nc)
+    nms_bytes = y.numel() * 4 + 64 * 300 * 6 * 4
+    nms = {"metric": "images/sec through batched class-aware NMS", "value": world * 64 / (nms_ms * 1e-3), "unit": "images/s",
+           "ms_per_step": nms_ms, "config": {"workload": "cfg4: batch 64/GPU, 8400 candidates, nc=80, conf 0.001, IoU 0.7, max_det 300"},
+           "hbm_frac_of_scan_roofline": nms_bytes / (nms_ms * 1e-3) / 1e9 / peak, "kept_min": int(cnt.min().item())}
+    ppath = os.path.join(ROOT, "profiles", "r2_nms_pipes.json")          # from the committed ncu --set full capture
+    if os.path.exists(ppath):
+        nms["pipes_ncu"] = json.load(open(ppath))
 
-    # ---- extra lines (not the headline): the task-aligned variant and the dense bf16 config ----
-    def time_steps(fn, k):
-        for _ in range(3):
-            keep = fn()
-        barrier()
-        ev0.record()
-        for _ in range(k):
-            keep = fn()
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1) / k
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    extra_steps = max(5, min(args.steps, 50))
+    # ---- extra lines (not the headline): the task-aligned variant, the dense bf16 config, adverse class logits ----
     tal_ms = time_steps(lambda: fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5), extra_steps)
+    tal_out, _, _ = fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5)
     tal = {"metric": "images/sec through decode+TAL assign+CIoU/DFL/BCE loss+bwd (no reference counterpart; parity vs in-repo oracle)",
            "value": world * n / (tal_ms * 1e-3), "unit": "images/s", "ms_per_step": tal_ms,
            "hbm_frac_whole_step": bytes_per_step / (tal_ms * 1e-3) / 1e9 / peak,
            "exchange": "all-reduce of [sum target scores, #fg] between assign and loss" if world > 1 else "none (1 GPU)"}
+    if world > 1:                        # the exchange on real hardware: every rank must have used the SAME normaliser
+        used = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(used, tal_out[4:5].clone())
+        used = [float(u.item()) for u in used]
+        tal["normaliser_used_by_rank"] = used
+        if max(used) != min(used):
+            raise SystemExit(f"bench.py: PARITY FAILURE: ranks normalised the task-aligned loss differently: {used}")
+    # class logits ~ N(0, 2): half of them positive, nothing like the head's bias initialisation the headline input
+    # follows; the class role's packed fast path (background logits <= -0.88) does not apply to most groups
+    g = torch.Generator().manual_seed(4321 + rank)
+    preds_w = preds_h.clone()
+    preds_w[:, 64:] = torch.randn(preds_w[:, 64:].shape, generator=g) * 2.0
+    preds_w = preds_w.to(dev)
+    worst_ms = time_steps(lambda: fused_loss(preds_w, gt, off, gmax_real, anchors_d, strides_d, nc, 1.0, 1.5), extra_steps)
+    worst_tal_ms = time_steps(lambda: fused_tal_loss(preds_w, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5), extra_steps)
+    worst = {"input": "cfg2 with class logits ~ N(0, 2) instead of N(-4.6, 1)", "ms_per_step": worst_ms,
+             "value": world * n / (worst_ms * 1e-3), "unit": "images/s",
+             "hbm_frac_whole_step": bytes_per_step / (worst_ms * 1e-3) / 1e9 / peak,
+             "tal_ms_per_step": worst_tal_ms, "tal_hbm_frac_whole_step": bytes_per_step / (worst_tal_ms * 1e-3) / 1e9 / peak}
+    del preds_w
     p5, g5, a5, s5 = syn.make_loss_inputs(32, nc, 1280, 300, 1240 + rank, dtype=torch.bfloat16)
     p5 = p5.to(dev); a5 = a5.float().to(dev); s5 = s5.float().to(dev)
     gt5, off5, c5 = pack_gt([g.to(dev) for g in g5], dev)
@@ -371,29 +490,93 @@ def run_ours(args):
             "unit": "images/s", "ms_per_step": cfg5_ms, "hbm_frac_whole_step": cfg5_bytes / (cfg5_ms * 1e-3) / 1e9 / peak}
     del p5, gt5
 
+    # ---- N = 1 only: the reference's own code on this box (CUDA eager, CPU), never part of our timed path ----
+    cpu = cuda_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, med, threads, kind, what = cpu_loss_images_per_s(3, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+               "sample": f"{CPU_SAMPLE_IMAGES} images of the same workload per step, {what} on torch CPU, "
+                         f"median of 3 steps ({med * 1e3:.0f} ms/step)"}
+        ref = reference_modules()
+        if ref is not None:
+            ref_losses, ref_utils = ref
+            rcrit = ref_losses.YoloDFLQFLoss(num_classes=nc)
+
+            def ref_cuda_step():
+                x = preds.detach().clone().requires_grad_(True)
+                loss, parts = rcrit(x, gts_d, anchors_d, strides_d)
+                loss.backward()
+                return parts, x.grad
+
+            ref_cuda_step()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                rparts, rgrad = ref_cuda_step()
+            torch.cuda.synchronize(dev)
+            ref_ms = (time.perf_counter() - t0) / 2 * 1e3
+            gerr = float((rgrad - grad).abs().max().item() / rgrad.abs().max().item())
+            cuda_eager = {"what": "the unmodified reference's YoloDFLQFLoss.forward + loss.backward on device='cuda' "
+                                  "(PyTorch eager on this B200), full cfg2 batch", "ms_per_step": ref_ms,
+                          "value": n / (ref_ms * 1e-3), "unit": "images/s", "speedup_of_this_repo": ref_ms / ms_per_step,
+                          "speedup_through_public_api": ref_ms / api_list_ms,
+                          "loss_rel_diff_vs_this_repo": abs(rparts["total_loss"] - loss_val) / abs(rparts["total_loss"]),
+                          "grad_max_abs_diff_over_max": gerr,
+                          "note": "duplicate matched anchors make the reference's CUDA index_put_ order-dependent (SURVEY Q4)"}
+            del rgrad
+            # NMS: the reference's wrapper calls torchvision.ops.nms once per image
+            kw = dict(conf_thres=0.001, iou_thres=0.7, max_det=300, nc=nc)
+            ref_rows = ref_nms(ref_utils, y, **kw)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ref_rows = ref_nms(ref_utils, y, **kw)
+            torch.cuda.synchronize(dev)
+            tv_ms = (time.perf_counter() - t0) / 3 * 1e3
+            ours = non_max_suppression(y, **kw)
+            same = all(torch.equal(o, r) for o, r in zip(ours, ref_rows))
+            t0 = time.perf_counter()
+            live = ref_nms(ref_utils, y, frozen=False, **kw)
+            torch.cuda.synchronize(dev)
+            live_ms = (time.perf_counter() - t0) * 1e3
+            y_cpu = y[:4].cpu()
+            ref_nms(ref_utils, y_cpu[:1], **kw)
+            t0 = time.perf_counter()
+            ref_nms(ref_utils, y_cpu, **kw)
+            cpu_nms_ms = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            live_cpu = ref_nms(ref_utils, y.cpu(), frozen=False, **kw)
+            live_cpu_s = time.perf_counter() - t0
+            nms["reference_torchvision_cuda"] = {
+                "what": "the unmodified reference's non_max_suppression on device='cuda' (torchvision.ops.nms per image, clock frozen), same 64 images",
+                "ms_per_step": tv_ms, "value": 64 / (tv_ms * 1e-3), "unit": "images/s", "rows_identical_to_this_repo": bool(same),
+                "unfrozen_clock": {"ms": live_ms, "images_left_empty": sum(1 for r in live if r.shape[0] == 0)}}
+            nms["vs_torchvision_cuda"] = tv_ms / nms_ms
+            nms["reference_cpu"] = {"what": "the same function on the host cores, clock frozen, 4 of the 64 images",
+                                    "ms_per_image": cpu_nms_ms / 4, "value": 4 / (cpu_nms_ms * 1e-3), "unit": "images/s",
+                                    "cores": torch.get_num_threads(),
+                                    "unfrozen_clock_64_images": {"seconds": live_cpu_s, "images_left_empty": sum(1 for r in live_cpu if r.shape[0] == 0),
+                                                                 "note": "the reference stops after 0.5 + 0.05 * 64 = 3.7 s (model_utils.py:212, :275-277)"}}
+            if not same:
+                raise SystemExit("bench.py: PARITY FAILURE: NMS rows differ from the reference's on the benchmark input")
+
     if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            ips, med, threads = cpu_loss_images_per_s(3, 1)
-            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                   "sample": f"{CPU_SAMPLE_IMAGES} images of the same workload per step, oracle/loss_oracle.py fwd+bwd on torch CPU, "
-                             f"median of 3 steps ({med * 1e3:.0f} ms/step)"}
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": "cfg2 per GPU: batch 128, 640x640 (8400 anchors, reg_max 16), 80 classes, <=100 GT/img, "
-                                       "fused decode+assign+loss+backward (cfg3 = global batch 1024 at 8 GPUs)",
-                           "global_batch": world * n, "gt_boxes_per_step_per_gpu": int(sum(counts)),
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "timed_steps": timed_steps, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * n, "gt_boxes_per_step_per_gpu": int(sum(counts)),
                            "l2_policy": "inputs+outputs are 1.24 GB per step, larger than the 126 MB L2",
+                           "timed_window": f"max(K, {MIN_TIMED_STEPS}) consecutive steps",
                            "parallelism": (f"batch-sharded x{world}: no data-path collective, one 8-float all-reduce of the loss statistics per run"
                                            if world > 1 else "single GPU")},
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "cuda_eager_baseline": cuda_eager, "parity": parity,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                         "api": "YoloDFLQFLoss.forward + loss.backward on pinned host inputs (head output + packed GT); the next step's copy is prefetched on a copy stream",
                         "pinned_numa": numa_note.note},
+                "api_device_resident": api,
                 "gpu_launches": launches, "clocks": clocks.summary(), "loss": loss_val, "nms": nms, "tal": tal,
-                "cfg5_bf16": cfg5}
+                "cfg5_bf16": cfg5, "adverse_logits": worst}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

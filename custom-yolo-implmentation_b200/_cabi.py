@@ -14,8 +14,9 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libyolo_boxpath.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 YB_F32, YB_BF16 = 0, 1
+YB_LOSS_NO_PRUNE, YB_LOSS_SPLIT_LAUNCH = 1, 2
 
 _lib = None
 _lock = threading.Lock()
@@ -30,7 +31,7 @@ _SIGNATURES = {
     "yb_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "yb_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_size_t, ctypes.c_uint, c_void_p, c_void_p]),
     "yb_tal_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "yb_tal_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -39,8 +40,6 @@ _SIGNATURES = {
     "yb_tal_loss_vfl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),
-    "yb_stage_timing": (c_int, [c_int]),
-    "yb_loss_last_stage_ms": (c_int, [c_void_p]),
     "yb_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "yb_loss_fwd_bwd_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -66,7 +65,7 @@ _SIGNATURES = {
     "yb_box_iou_batch": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "yb_detection_counters_bytes": (c_size_t, [c_int]),
     "yb_detection_match": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
-                                   c_float, c_void_p, c_void_p]),
+                                   c_float, c_int, c_void_p, c_void_p]),
     "yb_qfl_workspace_bytes": (c_size_t, [c_size_t]),
     "yb_quality_focal_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),

@@ -1,7 +1,7 @@
 // Fused decode + nearest-centre assignment + DFL/QFL loss + backward (sm_100a).
 //
 // Replaces YoloDFLQFLoss.forward and its autograd backward (src/model/losses.py:93-281).
-// Three launches per step (the last two are tiny), every head-output byte read once and every gradient
+// Two launches per step (the second is tiny), every head-output byte read once and every gradient
 // byte written once; the (M x A) distance matrix, the decoded boxes and the dense (A x nc) QFL target
 // never exist:
 //
@@ -17,9 +17,11 @@
 //   match_kernel     one half-warp per GT: gathers the 64 logits of the matched anchor, DFL loss and its
 //                    gradient, IoU soft target (reference formula, slip included) and the gradient
 //                    that flows through it, duplicate-anchor resolution; corrects the one positive
-//                    QFL cell of each matched anchor (loss delta + gradient).
-//   finalize_kernel  one warp per image reduces that image's partial sums; the last CTA adds the
-//                    images up; everything in a fixed order, so the loss is run-to-run identical.
+//                    QFL cell of each matched anchor (loss delta + gradient).  Its last CTA (ticket)
+//                    turns the per-image accumulators into the loss scalars.
+// Partial sums (one per class-role CTA, three per GT) are added into per-image 64-bit FIXED-POINT
+// accumulators (2^-32 resolution) with integer atomics: integer addition is associative, so the loss is
+// run-to-run bit-identical whatever the order in which CTAs finish, and nothing has to be re-read.
 #include <algorithm>
 #include <cstdlib>
 
@@ -65,46 +67,46 @@ constexpr int kAssignThreads = YB_ASSIGN_THREADS;
 constexpr int kClsThreads = YB_CLS_THREADS;
 constexpr unsigned long long kNoKey = ~0ull;
 
+constexpr int kAccCls = 16;           // class-role sub-accumulators per image (spreads same-address atomics)
+constexpr int kAccDfl = 16, kAccDcls = 17, kAccWin = 18, kAccPerImage = 20;
+constexpr double kFixScale = 4294967296.0;   // 2^32
+
 struct LossWorkspace {
-    unsigned int *ticket;          // [1]   finalize_kernel completion counter      } zeroed
-    unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys   } every call
-    int *m_idx;                    // [gt_total] 1 if this GT owns its anchor's QFL target row (last of its duplicates)
+    unsigned int *ticket;          // [16] [0] match_kernel ticket, [1] non-finite partial seen, [2] class ids out of range } zeroed
+    unsigned long long *acc;       // [N * kAccPerImage] fixed-point sums: 16 x class part, DFL, QFL cell correction, winners } every
+    unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys                                           } call
     int *gt_img;                   // [gt_total] image of each GT (written by the box role, read by match_kernel)
-    float *m_iou;                  // [gt_total]
-    float *m_dfl;                  // [gt_total] sum over the 4 sides of the DFL term
-    float *m_dcls;                 // [gt_total] QFL correction of the GT's positive cell: T (q^2 log p - p^2 log q)
-    float *part;                   // [N * tiles] per-CTA sums of p^2 log(1-p)
-    float *img_terms;              // [3 * N] per-image DFL term, QFL term, matched-anchor count
     size_t zero_bytes;
     size_t total_bytes;
 };
 
-static LossWorkspace carve(void *base, int n_images, int cls_tiles, int gt_total) {
+static LossWorkspace carve(void *base, int n_images, int gt_total) {
     LossWorkspace w;
     char *p = static_cast<char *>(base);
     size_t off = 0;
     w.ticket = reinterpret_cast<unsigned int *>(p + off);
     off += 64;
+    w.acc = reinterpret_cast<unsigned long long *>(p + off);
+    off += round_up(sizeof(unsigned long long) * (size_t)n_images * kAccPerImage, 64);
     w.best = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
     w.zero_bytes = off;
-    const size_t g4 = round_up(sizeof(int) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
-    w.m_idx = reinterpret_cast<int *>(p + off);
-    off += g4;
     w.gt_img = reinterpret_cast<int *>(p + off);
-    off += g4;
-    w.m_iou = reinterpret_cast<float *>(p + off);
-    off += g4;
-    w.m_dfl = reinterpret_cast<float *>(p + off);
-    off += g4;
-    w.m_dcls = reinterpret_cast<float *>(p + off);
-    off += g4;
-    w.part = reinterpret_cast<float *>(p + off);
-    off += round_up(sizeof(float) * (size_t)n_images * cls_tiles, 64);
-    w.img_terms = reinterpret_cast<float *>(p + off);
-    off += round_up(sizeof(float) * 3 * (size_t)n_images, 64);
+    off += round_up(sizeof(int) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
     w.total_bytes = off;
     return w;
+}
+
+// float partial -> fixed point, added with an integer atomic (two's complement: negative values work)
+__device__ __forceinline__ void acc_add(unsigned long long *slot, float v, unsigned int *flags) {
+    if (!isfinite(v)) {                                   // NaN / Inf must reach the loss, not vanish in the conversion
+        atomicOr(flags + 1, 1u);
+        return;
+    }
+    atomicAdd(slot, (unsigned long long)__double2ll_rn((double)v * kFixScale));
+}
+__device__ __forceinline__ double acc_get(const unsigned long long *slot) {
+    return (double)(long long)__ldcg(slot) * (1.0 / kFixScale);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -345,9 +347,18 @@ assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float 
 }
 
 // ------------------------------------------------------------------------------------------
-// match_kernel: one warp per GT
+// match_kernel: one half-warp per GT; its last CTA writes the loss scalars
 // ------------------------------------------------------------------------------------------
 // Sixteen lanes per GT: lane l of a half-warp holds bin l of all four box sides of the matched anchor.
+// What depends on the anchor only (shared by all GTs matched to it):
+struct AnchorTerms {
+    float z[4];         // this lane's bin of the four sides (raw logits)
+    float mx[4], sm[4]; // softmax max / sum of each side
+    float pr[4];        // softmax probability of this lane's bin
+    float ds[4];        // expected distance of each side
+    float ax, ay, s;
+    PredBox b;
+};
 struct GtTerms {
     float g[4];         // gradient of this lane's bin on sides l, t, r, b
     float dfl;          // sum over the four sides of the DFL term (all lanes)
@@ -357,31 +368,16 @@ struct GtTerms {
     float cell_grad1;
 };
 
-// All 32 lanes of the warp must call this together (full-mask shuffles; xor offsets <= 8 stay in a half).
-template <typename T>
-__device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anchors, int idx,
-                                            const float *__restrict__ anchors, const float *__restrict__ strides,
-                                            const float *__restrict__ g5, float k_dfl, float k_cls, int nc) {
-    const int lane = threadIdx.x & 31;
-    const int bin = lane & 15;
-    const int base = lane & 16;
-    float z[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
-    const float gcx = __ldg(g5 + 0), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
-    int cls = (int)__ldg(g5 + 4);                                                     // .long(): truncation
-    cls = min(max(cls, 0), nc - 1);
-    const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
-    const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
-
+// All 32 lanes of the warp must call these together (full-mask shuffles; xor offsets <= 8 stay in a half).
+__device__ __forceinline__ void anchor_softmax(AnchorTerms &a) {
+    const int bin = threadIdx.x & 15;
     // softmax + expectation of each side over the 16 lanes of the half
-    float mx[4], sm[4], pr[4], ds[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float m = z[k];
+        float m = a.z[k];
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float e = expf(z[k] - m);
+        const float e = expf(a.z[k] - m);
         float sum = e;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -389,9 +385,18 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
         float d = p * (float)bin;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        mx[k] = m; sm[k] = sum; pr[k] = p; ds[k] = d;
+        a.mx[k] = m; a.sm[k] = sum; a.pr[k] = p; a.ds[k] = d;
     }
-    const PredBox b = decode_box(ax, ay, s, ds[0], ds[1], ds[2], ds[3]);
+    a.b = decode_box(a.ax, a.ay, a.s, a.ds[0], a.ds[1], a.ds[2], a.ds[3]);
+}
+
+__device__ __forceinline__ GtTerms gt_terms(const AnchorTerms &a, float z_cls, float gcx, float gcy, float gw, float gh,
+                                            float k_dfl, float k_cls) {
+    const int lane = threadIdx.x & 31;
+    const int bin = lane & 15;
+    const int base = lane & 16;
+    const PredBox &b = a.b;
+    const float ax = a.ax, ay = a.ay, s = a.s;
 
     // ---- IoU soft target, reference formula (src/model/losses.py:17-40) and its gradient ------
     const float hw = b.w * 0.5f, hh = b.h * 0.5f;
@@ -425,8 +430,8 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
     const float d_area1 = -g_iou * inter / (den * den);
     const float d_iw = (iw_raw >= 0.f) ? d_inter * ih : 0.f;
     const float d_ih = (ih_raw >= 0.f) ? d_inter * iw : 0.f;
-    auto pick_max = [](float a, float o) { return a > o ? 1.f : (a == o ? 0.5f : 0.f); };   // weight on `a`
-    auto pick_min = [](float a, float o) { return a < o ? 1.f : (a == o ? 0.5f : 0.f); };
+    auto pick_max = [](float x, float o) { return x > o ? 1.f : (x == o ? 0.5f : 0.f); };   // weight on `x`
+    auto pick_min = [](float x, float o) { return x < o ? 1.f : (x == o ? 0.5f : 0.f); };
     const float d_ax1 = -d_iw * pick_max(ax1, bx1) - d_area1 * ah;
     const float d_ax2 = d_iw * pick_min(ax2, bx2) + d_area1 * ah;
     const float d_ay1 = -d_ih * pick_max(ay1, by1) - d_area1 * aw;
@@ -451,10 +456,10 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
         const float t = fminf(fmaxf(tgt[k], 0.f), hi_clamp);
         const int bl = (int)t;
         const float wl = (float)(bl + 1) - t, wr = t - (float)bl;
-        const float lpk = (z[k] - mx[k]) - logf(sm[k]);               // log-softmax of this lane's bin
+        const float lpk = (a.z[k] - a.mx[k]) - logf(a.sm[k]);         // log-softmax of this lane's bin
         dfl -= __shfl_sync(0xffffffffu, lpk, base + bl) * wl + __shfl_sync(0xffffffffu, lpk, base + bl + 1) * wr;
         const float oh = (bin == bl ? wl : 0.f) + (bin == bl + 1 ? wr : 0.f);
-        r.g[k] = k_dfl * ((wl + wr) * pr[k] - oh) + dd[k] * pr[k] * ((float)bin - ds[k]);
+        r.g[k] = k_dfl * ((wl + wr) * a.pr[k] - oh) + dd[k] * a.pr[k] * ((float)bin - a.ds[k]);
     }
     r.dfl = dfl;
     r.iou = iou;
@@ -466,141 +471,123 @@ __device__ __forceinline__ GtTerms gt_terms(const T *__restrict__ img, int n_anc
 
 constexpr int kMatchThreads = 128;
 
-// one HALF-warp per GT (8 GTs per CTA)
-template <typename T>
-__global__ void __launch_bounds__(kMatchThreads, 6)
-match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
-             const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
-             const int *__restrict__ gt_off, const int *__restrict__ gt_img, int gt_total,
-             const unsigned long long *__restrict__ best, float k_dfl_num, float k_cls, T *__restrict__ grad,
-             float *__restrict__ m_dfl, float *__restrict__ m_dcls, int *__restrict__ m_win, int *__restrict__ out_idx,
-             float *__restrict__ out_iou) {
-    (void)n_images;
-    const int bin = threadIdx.x & 15;
-    const int g_raw = (blockIdx.x * kMatchThreads + threadIdx.x) >> 4;
-    if ((blockIdx.x * kMatchThreads + (threadIdx.x & ~31)) >> 4 >= gt_total) return;      // whole warp past the end
-    const bool live = g_raw < gt_total;                    // the second half of the last warp may be idle
-    const int g = live ? g_raw : gt_total - 1;             // ... but must walk through the same shuffles
-    const int n = __ldg(gt_img + g);
-    const int g_begin = __ldg(gt_off + n);
-    const int m_img = __ldg(gt_off + n + 1) - g_begin;
-    const int m = g - g_begin;
-    const T *img = preds + (size_t)n * n_ch * n_anchors;
-    auto idx_of = [&](int mm) {
-        const unsigned long long inv = best[g_begin + mm];
-        return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
-    };
-    const int idx = idx_of(m);
-    const float k_dfl = k_dfl_num / (float)m_img;          // lambda_dfl / (N * 4 * M)
-
-    // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
-    // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
-    int first = m, last = m, n_later = 0;
-    for (int mm = bin; mm < m_img; mm += 16) {
-        if (idx_of(mm) == idx) {
-            first = min(first, mm);
-            last = max(last, mm);
-            n_later += mm > m ? 1 : 0;
-        }
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-        n_later += __shfl_xor_sync(0xffffffffu, n_later, o);
-    }
-
-    const GtTerms mine = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)g * 5, k_dfl, k_cls, nc);
-    const bool winner = (last == m);
-    T *gimg = grad ? grad + (size_t)n * n_ch * n_anchors : nullptr;
-    if (live && bin == 0) {
-        m_dfl[g] = mine.dfl;
-        m_dcls[g] = winner ? mine.iou * mine.cell_delta : 0.f;
-        m_win[g] = winner ? 1 : 0;
-        if (out_idx) out_idx[g] = idx;
-        if (out_iou) out_iou[g] = mine.iou;
-        if (winner && gimg) {
-            // the anchor's one positive QFL cell: overwrite the target-0 gradient the class pass wrote
-            int cls = (int)__ldg(gt + (size_t)g * 5 + 4);
-            cls = min(max(cls, 0), nc - 1);
-            store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
-                             mine.cell_grad0 + mine.iou * mine.cell_grad1);
-        }
-    }
-    // the owner adds the terms of the later GTs that share its anchor (rare); the trip count is made
-    // warp-uniform because gt_terms shuffles across the whole warp
-    float acc[4] = {mine.g[0], mine.g[1], mine.g[2], mine.g[3]};
-    const bool owner = live && first == m && gimg != nullptr;
-    int todo = owner ? n_later : 0;
-    const int trips = max(todo, __shfl_xor_sync(0xffffffffu, todo, 16));
-    int cur = m;
-    for (int it = 0; it < trips; ++it) {
-        int nxt = 0x7fffffff;
-        if (it < todo)
-            for (int mm = bin; mm < m_img; mm += 16)
-                if (mm > cur && idx_of(mm) == idx) nxt = min(nxt, mm);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
-        const bool has = nxt != 0x7fffffff;
-        const GtTerms o = gt_terms(img, n_anchors, idx, anchors, strides, gt + (size_t)(g_begin + (has ? nxt : m)) * 5, k_dfl,
-                                   k_cls, nc);
-        if (has) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] += o.g[k];
-            cur = nxt;
-        }
-    }
-    if (owner) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) store_from_float(gimg + (size_t)(k * kRegMax + bin) * n_anchors + idx, acc[k]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// finalize_kernel: one warp per image sums that image's partials in a fixed order; the last CTA
-// to finish adds the per-image terms up (again in a fixed order) and writes the loss scalars.
-// ------------------------------------------------------------------------------------------
-constexpr int kFinThreads = 256;
-
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-__global__ void __launch_bounds__(kFinThreads)
-finalize_kernel(int n_images, int n_anchors, int cls_tiles, const int *__restrict__ gt_off,
-                const float *__restrict__ part, const float *__restrict__ m_dfl, const float *__restrict__ m_dcls,
-                const int *__restrict__ m_win, float lambda_cls, float lambda_dfl, float *__restrict__ img_terms,
-                unsigned int *__restrict__ ticket, float *__restrict__ out_loss, float *__restrict__ out_per_image) {
-    __shared__ bool s_last;
-    __shared__ double s_d[kFinThreads / 32], s_c[kFinThreads / 32], s_f[kFinThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * (kFinThreads / 32) + warp;
-    if (b < n_images) {
-        double c_img = 0.0, d_img = 0.0, f_img = 0.0;
-        for (int t = lane; t < cls_tiles; t += 32) c_img += (double)__ldcg(part + (size_t)b * cls_tiles + t);
-        const int gb = gt_off[b], mb = gt_off[b + 1] - gb;
-        for (int m = lane; m < mb; m += 32) {
-            d_img += (double)__ldcg(m_dfl + gb + m);
-            c_img += (double)__ldcg(m_dcls + gb + m);
-            f_img += (double)__ldcg(m_win + gb + m);
-        }
-        c_img = warp_sum_d(c_img);
-        d_img = warp_sum_d(d_img);
-        f_img = warp_sum_d(f_img);
-        if (lane == 0) {
-            const float cls_b = (float)(-c_img / (double)n_anchors);                     // losses.py:56
-            const float dfl_b = mb > 0 ? (float)(d_img / (4.0 * (double)mb)) : 0.f;      // losses.py:78, :252
-            img_terms[b] = dfl_b;
-            img_terms[n_images + b] = cls_b;
-            img_terms[2 * n_images + b] = (float)f_img;
-            if (out_per_image) {
-                out_per_image[b] = dfl_b;
-                out_per_image[n_images + b] = cls_b;
+// one HALF-warp per GT (8 GTs per CTA); the grid has at least one CTA even without GTs, because the
+// last CTA to finish (ticket) reduces the per-image accumulators in a fixed order -> 8 loss scalars
+template <typename T>
+__global__ void __launch_bounds__(kMatchThreads, 6)
+match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
+             const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
+             const int *__restrict__ gt_off, const int *__restrict__ gt_img, int gt_total,
+             const unsigned long long *__restrict__ best, float k_dfl_num, float k_cls, float lambda_cls, float lambda_dfl,
+             T *__restrict__ grad, unsigned long long *__restrict__ acc, unsigned int *__restrict__ ticket,
+             int *__restrict__ out_idx, float *__restrict__ out_iou, float *__restrict__ out_loss,
+             float *__restrict__ out_per_image) {
+    const int bin = threadIdx.x & 15;
+    const int g_raw = (blockIdx.x * kMatchThreads + threadIdx.x) >> 4;
+    const bool warp_has_work = ((blockIdx.x * kMatchThreads + (threadIdx.x & ~31)) >> 4) < gt_total;
+    if (warp_has_work) {                                       // warp-uniform
+        const bool live = g_raw < gt_total;                    // the second half of the last warp may be idle
+        const int g = live ? g_raw : gt_total - 1;             // ... but must walk through the same shuffles
+        const int n = __ldg(gt_img + g);
+        const int g_begin = __ldg(gt_off + n);
+        const int m_img = __ldg(gt_off + n + 1) - g_begin;
+        const int m = g - g_begin;
+        const T *img = preds + (size_t)n * n_ch * n_anchors;
+        auto idx_of = [&](int mm) {
+            const unsigned long long inv = best[g_begin + mm];
+            return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
+        };
+        const int idx = idx_of(m);
+        const float k_dfl = k_dfl_num / (float)m_img;          // lambda_dfl / (N * 4 * M)
+
+        // the gathers (DRAM latency) are issued first; the duplicate search below runs in their shadow
+        AnchorTerms at;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) at.z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
+        const float *g5 = gt + (size_t)g * 5;
+        const float gcx = __ldg(g5 + 0), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
+        const int cls_raw = (int)__ldg(g5 + 4);                                        // .long(): truncation
+        const int cls = min(max(cls_raw, 0), nc - 1);          // memory-safe; the violation itself is reported below
+        const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
+        at.ax = __ldg(anchors + idx); at.ay = __ldg(anchors + n_anchors + idx); at.s = __ldg(strides + idx);
+
+        // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
+        // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
+        int first = m, last = m, n_later = 0;
+        for (int mm = bin; mm < m_img; mm += 16) {
+            if (idx_of(mm) == idx) {
+                first = min(first, mm);
+                last = max(last, mm);
+                n_later += mm > m ? 1 : 0;
             }
         }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            n_later += __shfl_xor_sync(0xffffffffu, n_later, o);
+        }
+
+        anchor_softmax(at);
+        const GtTerms mine = gt_terms(at, z_cls, gcx, gcy, gw, gh, k_dfl, k_cls);
+        const bool winner = (last == m);
+        T *gimg = grad ? grad + (size_t)n * n_ch * n_anchors : nullptr;
+        if (live && bin == 0) {
+            unsigned long long *a_img = acc + (size_t)n * kAccPerImage;
+            acc_add(a_img + kAccDfl, mine.dfl, ticket);
+            if (winner) {
+                acc_add(a_img + kAccDcls, mine.iou * mine.cell_delta, ticket);
+                atomicAdd(a_img + kAccWin, 1ull);
+            }
+            if (cls_raw != cls) atomicAdd(ticket + 2, 1u);     // the reference's scatter_ raises here (losses.py:260)
+            if (out_idx) out_idx[g] = idx;
+            if (out_iou) out_iou[g] = mine.iou;
+            if (winner && gimg) {
+                // the anchor's one positive QFL cell: overwrite the target-0 gradient the class pass wrote
+                store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
+                                 mine.cell_grad0 + mine.iou * mine.cell_grad1);
+            }
+        }
+        // the owner adds the terms of the later GTs that share its anchor (rare); the trip count is made
+        // warp-uniform because gt_terms shuffles across the whole warp
+        float sum[4] = {mine.g[0], mine.g[1], mine.g[2], mine.g[3]};
+        const bool owner = live && first == m && gimg != nullptr;
+        int todo = owner ? n_later : 0;
+        const int trips = max(todo, __shfl_xor_sync(0xffffffffu, todo, 16));
+        int cur = m;
+        for (int it = 0; it < trips; ++it) {
+            int nxt = 0x7fffffff;
+            if (it < todo)
+                for (int mm = bin; mm < m_img; mm += 16)
+                    if (mm > cur && idx_of(mm) == idx) nxt = min(nxt, mm);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+            const bool has = nxt != 0x7fffffff;
+            const float *o5 = gt + (size_t)(g_begin + (has ? nxt : m)) * 5;
+            const int ocls = min(max((int)__ldg(o5 + 4), 0), nc - 1);
+            const float oz = load_as_float(img + (size_t)(4 * kRegMax + ocls) * n_anchors + idx);
+            const GtTerms o = gt_terms(at, oz, __ldg(o5 + 0), __ldg(o5 + 1), __ldg(o5 + 2), __ldg(o5 + 3), k_dfl, k_cls);
+            if (has) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sum[k] += o.g[k];
+                cur = nxt;
+            }
+        }
+        if (owner) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) store_from_float(gimg + (size_t)(k * kRegMax + bin) * n_anchors + idx, sum[k]);
+        }
     }
+
+    // ---- the last CTA to finish: per-image terms, then the batch means, in a fixed order -------
+    __shared__ bool s_last;
+    __shared__ double s_d[kMatchThreads / 32], s_c[kMatchThreads / 32], s_f[kMatchThreads / 32];
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -609,25 +596,40 @@ finalize_kernel(int n_images, int n_anchors, int cls_tiles, const int *__restric
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double d = 0.0, c = 0.0, f = 0.0;
-    for (int i = threadIdx.x; i < n_images; i += kFinThreads) {
-        d += (double)__ldcg(img_terms + i);
-        c += (double)__ldcg(img_terms + n_images + i);
-        f += (double)__ldcg(img_terms + 2 * n_images + i);
+    for (int b = threadIdx.x; b < n_images; b += kMatchThreads) {
+        const unsigned long long *a_img = acc + (size_t)b * kAccPerImage;
+        double c_img = acc_get(a_img + kAccDcls);
+#pragma unroll
+        for (int k = 0; k < kAccCls; ++k) c_img += acc_get(a_img + k);
+        const double d_img = acc_get(a_img + kAccDfl);
+        const int mb = __ldg(gt_off + b + 1) - __ldg(gt_off + b);
+        const float cls_b = (float)(-c_img / (double)n_anchors);                     // losses.py:56
+        const float dfl_b = mb > 0 ? (float)(d_img / (4.0 * (double)mb)) : 0.f;      // losses.py:78, :252
+        if (out_per_image) {
+            out_per_image[b] = dfl_b;
+            out_per_image[n_images + b] = cls_b;
+        }
+        d += (double)dfl_b;
+        c += (double)cls_b;
+        f += (double)__ldcg(a_img + kAccWin);
     }
     d = warp_sum_d(d); c = warp_sum_d(c); f = warp_sum_d(f);
     if (lane == 0) { s_d[warp] = d; s_c[warp] = c; s_f[warp] = f; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double dd = 0.0, cc = 0.0, ff = 0.0;
-        for (int w = 0; w < kFinThreads / 32; ++w) { dd += s_d[w]; cc += s_c[w]; ff += s_f[w]; }
-        const float mean_dfl = (float)(dd / (double)n_images);        // N counts images without GT (losses.py:271)
-        const float mean_cls = (float)(cc / (double)n_images);
+        for (int w = 0; w < kMatchThreads / 32; ++w) { dd += s_d[w]; cc += s_c[w]; ff += s_f[w]; }
+        float mean_dfl = (float)(dd / (double)n_images);              // N counts images without GT (losses.py:271)
+        float mean_cls = (float)(cc / (double)n_images);
+        if (__ldcg(ticket + 1) != 0u) mean_cls = __int_as_float(0x7fc00000);   // a non-finite partial: NaN, as the reference
         out_loss[0] = lambda_dfl * mean_dfl + lambda_cls * mean_cls;  // losses.py:275
         out_loss[1] = mean_dfl;
         out_loss[2] = mean_cls;
         out_loss[3] = (float)ff;
-        out_loss[4] = out_loss[5] = out_loss[6] = out_loss[7] = 0.f;
+        out_loss[4] = out_loss[5] = out_loss[6] = 0.f;
+        out_loss[7] = (float)__ldcg(ticket + 2);                      // GT rows whose class id is outside [0, nc)
     }
 }
 
@@ -716,7 +718,7 @@ __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cl
 template <typename T, int VW, bool WRITE_GRAD>
 __device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split, int n_split, const T *__restrict__ preds,
                                          int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
-                                         float *__restrict__ part) {
+                                         unsigned long long *__restrict__ acc, unsigned int *__restrict__ flags) {
     __shared__ float s_red[kClsThreads / 32];
     const int a0 = (tile * kClsThreads + threadIdx.x) * VW;
     const int c_per = (nc + n_split - 1) / n_split;
@@ -752,23 +754,24 @@ __device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split
     }
     float lo, hi;
     unpack2(acc2, lo, hi);
-    float acc = warp_sum((lo + hi) + fix);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    const float wsum = warp_sum((lo + hi) + fix);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = wsum;
     __syncthreads();
     if (threadIdx.x == 0) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kClsThreads / 32; ++w) s += s_red[w];
-        part[((size_t)n * n_split + split) * n_tiles + tile] = s;
+        // per-image fixed-point accumulator; consecutive CTAs use different sub-accumulators
+        acc_add(acc + (size_t)n * kAccPerImage + ((tile * n_split + split) & (kAccCls - 1)), s, flags);
     }
 }
 
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kClsThreads, YB_CLS_MINBLOCKS)
 cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, float k_cls, T *__restrict__ grad,
-                float *__restrict__ part) {
+                unsigned long long *__restrict__ acc, unsigned int *__restrict__ flags) {
     cls_body<T, VW, WRITE_GRAD>(blockIdx.y, blockIdx.x, gridDim.x, blockIdx.z, gridDim.z, preds, n_ch, n_anchors, nc, k_cls,
-                                grad, part);
+                                grad, acc, flags);
 }
 
 // One launch for both big passes: CTAs alternate between the box role (assign_body) and the class role
@@ -783,12 +786,12 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
                   int skew, const float *__restrict__ anchors,
                   const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
                   unsigned long long *__restrict__ best, int *__restrict__ gt_img, float k_cls, T *__restrict__ grad,
-                  float *__restrict__ part) {
+                  unsigned long long *__restrict__ acc, unsigned int *__restrict__ flags) {
     static_assert(kAssignThreads == kClsThreads, "roles share one block shape");
     constexpr int ROLES = 1 + YB_CLS_CSPLIT;
     // Launch order: first the `coarse` LAST tiles of every image (image-major), then the other tiles
     // (image-major again).  Roles of a tile stay adjacent, so every SM holds a mix of box and class CTAs.
-    const bool prune = coarse >= 0;                        // coarse < 0: YB_ASSIGN_PRUNE=0 in the environment (tests)
+    const bool prune = coarse >= 0;                        // coarse < 0: YB_LOSS_NO_PRUNE (exactness tests)
     coarse = max(coarse, 0);
     // A tile's box CTA lives about three times as long as one of its class CTAs, so it is launched `skew` tile
     // groups AHEAD of them: the first `skew` blocks are the box CTAs of the first groups, and the last groups of
@@ -824,7 +827,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
                            WRITE_GRAD ? grad : nullptr, prune);
     else
         cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
-                                    part);
+                                    acc, flags);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -848,36 +851,20 @@ static bool vector_ok(const void *preds, const void *grad, int n_anchors) {
     return n_anchors % VW == 0 && aligned16(preds) && (grad == nullptr || aligned16(grad));
 }
 
-// Optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching
-// stream around each of the three kernels.  Off by default; never on during a timed benchmark step.
-static bool g_stage_timing = false;
-static cudaEvent_t g_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-
-static int stage_mark(int i, cudaStream_t st) {
-    if (!g_stage_timing) return YB_OK;
-    if (g_stage_ev[i] == nullptr) YB_CUDA(cudaEventCreate(&g_stage_ev[i]));
-    YB_CUDA(cudaEventRecord(g_stage_ev[i], st));
+// Optional per-kernel timing (bench.py's roofline leg): the caller may pass three of ITS OWN cudaEvent_t handles,
+// recorded on the launching stream before the main launch, between the two launches and after the second.
+static int stage_mark(void *const *events, int i, cudaStream_t st) {
+    if (events == nullptr || events[i] == nullptr) return YB_OK;
+    YB_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(events[i]), st));
     return YB_OK;
-}
-
-// YB_LAYOUT (environment, read once): "fused" (default) = assign + class pass in ONE launch
-// (fused_main_kernel), "split" = two launches (assign_kernel, cls_loss_kernel) — kept for profiling the
-// two roles separately.  Stream-level overlap of the two big kernels was measured and does not help:
-// the first kernel's CTAs fill every SM, so the second only starts as the first drains.
-static bool fused_layout() {
-    static int fused = -1;
-    if (fused < 0) {
-        const char *e = getenv("YB_LAYOUT");
-        fused = (e && e[0] == 's') ? 0 : 1;
-    }
-    return fused != 0;
 }
 
 template <typename T, int VW>
 static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, const float *anchors, const float *strides,
                        const float *gt, const int32_t *gt_off, int gt_total, int gmax, float lambda_cls,
                        float lambda_dfl, T *grad, float *out_loss, int32_t *out_idx, float *out_iou,
-                       float *out_per_image, const LossWorkspace &w, cudaStream_t st) {
+                       float *out_per_image, const LossWorkspace &w, unsigned flags, void *const *stage_events,
+                       cudaStream_t st) {
     (void)gmax;
     const int n_ch = 4 * kRegMax + nc;
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
@@ -886,10 +873,9 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     static_assert(TILE_A == TILE_C, "both roles tile the anchors identically");
     const int cls_split = YB_CLS_CSPLIT;
     const int n_tiles = (n_anchors + TILE_C - 1) / TILE_C;
-    const int cls_tiles = n_tiles * cls_split;                                  // partial sums per image
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
-    if (int rc = stage_mark(0, st)) return rc;
-    if (fused_layout()) {
+    if (int rc = stage_mark(stage_events, 0, st)) return rc;
+    if (!(flags & YB_LOSS_SPLIT_LAUNCH)) {
         // Block order: first the last quarter of the tiles of every image -- the coarse pyramid levels (P4 + P5
         // hold 23.8 % of a three-level grid's anchors), whose anchors lie within a cell or two of every GT --
         // then the rest, where assign_body prunes every (GT, tile) pair that cannot beat the distance already
@@ -898,57 +884,43 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
 #if YB_COARSE_FIRST && YB_ASSIGN_PRUNE
         if (gt_total > 0 && n_tiles >= 4) coarse = (n_tiles * YB_COARSE_FRAC256 + 255) / 256;   // ceil(0.238 n_tiles)
 #endif
-        {   // YB_ASSIGN_PRUNE=0 switches the pruning (and the coarse-first order) off: the exactness tests compare both
-            const char *e = getenv("YB_ASSIGN_PRUNE");
-            if (e && e[0] == '0') coarse = -1;
-        }
+        if (flags & YB_LOSS_NO_PRUNE) coarse = -1;      // pruning (and the coarse-first order) off: the exactness tests compare both
         const int skew = (int)std::min<long long>(YB_BOX_SKEW, (long long)n_tiles * n_images);
         const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + skew;
         YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
         if (grad != nullptr)
             fused_main_kernel<T, VW, true><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
                 preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, skew, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls,
-                grad, w.part);
+                grad, w.acc, w.ticket);
         else
             fused_main_kernel<T, VW, false><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
                 preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, skew, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls,
-                grad, w.part);
+                grad, w.acc, w.ticket);
         YB_LAUNCH_CHECK();
     } else {
+        // two launches (profiling the roles separately).  Stream-level overlap of the two was measured and does
+        // not help: the first kernel's CTAs fill every SM, so the second only starts as the first drains.
         assign_kernel<T, VW><<<dim3(n_tiles, n_images), kAssignThreads, 0, st>>>(preds, n_ch, n_anchors, anchors, strides, gt,
                                                                                  gt_off, w.best, w.gt_img, grad);
         YB_LAUNCH_CHECK();
         dim3 grid(n_tiles, n_images, cls_split);
         if (grad != nullptr)
-            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+            cls_loss_kernel<T, VW, true><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.acc, w.ticket);
         else
-            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.part);
+            cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.acc, w.ticket);
         YB_LAUNCH_CHECK();
     }
-    if (int rc = stage_mark(1, st)) return rc;
-    if (gt_total > 0) {
-        const int per_cta = kMatchThreads / 16;                                  // one half-warp per GT
-        match_kernel<T><<<(gt_total + per_cta - 1) / per_cta, kMatchThreads, 0, st>>>(
-            preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.gt_img, gt_total, w.best, k_dfl_num, k_cls,
-            grad, w.m_dfl, w.m_dcls, w.m_idx, out_idx, out_iou);
-        YB_LAUNCH_CHECK();
-    }
-    if (int rc = stage_mark(2, st)) return rc;
+    if (int rc = stage_mark(stage_events, 1, st)) return rc;
     {
-        const int warps = kFinThreads / 32;
-        finalize_kernel<<<(n_images + warps - 1) / warps, kFinThreads, 0, st>>>(
-            n_images, n_anchors, cls_tiles, gt_off, w.part, w.m_dfl, w.m_dcls, w.m_idx, lambda_cls, lambda_dfl, w.img_terms,
-            w.ticket, out_loss, out_per_image);
+        const int per_cta = kMatchThreads / 16;                                  // one half-warp per GT
+        const int blocks = std::max(1, (gt_total + per_cta - 1) / per_cta);       // >= 1: its last CTA writes the loss
+        match_kernel<T><<<blocks, kMatchThreads, 0, st>>>(
+            preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.gt_img, gt_total, w.best, k_dfl_num, k_cls,
+            lambda_cls, lambda_dfl, grad, w.acc, w.ticket, out_idx, out_iou, out_loss, out_per_image);
         YB_LAUNCH_CHECK();
     }
-    if (int rc = stage_mark(3, st)) return rc;
+    if (int rc = stage_mark(stage_events, 2, st)) return rc;
     return YB_OK;
-}
-
-static int cls_tiles_for(int n_anchors, int dtype, bool vec) {
-    const int vw = vec ? (dtype == YB_BF16 ? 8 : 4) : 1;
-    const int tile = kClsThreads * vw;
-    return ((n_anchors + tile - 1) / tile) * YB_CLS_CSPLIT;
 }
 
 }  // namespace yb
@@ -957,21 +929,24 @@ using namespace yb;
 
 extern "C" size_t yb_loss_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype) {
     if (n_images <= 0 || n_anchors <= 0 || gt_total < 0) return 0;
-    // sized for the scalar fall-back (most tiles); the vector path needs less
-    return carve(nullptr, n_images, cls_tiles_for(n_anchors, dtype, false), gt_total).total_bytes;
+    (void)n_anchors; (void)dtype;
+    return carve(nullptr, n_images, gt_total).total_bytes;
 }
 
 extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
                                const float *anchors, const float *strides, const float *gt,
                                const int32_t *gt_offsets, int gt_total, int gmax, float lambda_cls, float lambda_dfl,
                                void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou,
-                               float *out_per_image, void *workspace, size_t workspace_bytes, void *stream) {
+                               float *out_per_image, void *workspace, size_t workspace_bytes, unsigned flags,
+                               void *const *stage_events, void *stream) {
     YB_REQUIRE(preds && anchors && strides && gt_offsets && out_loss && workspace, "yb_loss_fwd_bwd: null pointer");
     YB_REQUIRE(gt_total == 0 || gt != nullptr, "yb_loss_fwd_bwd: gt is null but gt_total > 0");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && gt_total >= 0 && gmax >= 0, "yb_loss_fwd_bwd: bad sizes");
     YB_REQUIRE(reg_max == kRegMax, "yb_loss_fwd_bwd: reg_max must be %d (got %d)", kRegMax, reg_max);
     YB_REQUIRE(dtype == YB_F32 || dtype == YB_BF16, "yb_loss_fwd_bwd: dtype must be YB_F32 or YB_BF16");
     YB_REQUIRE(n_images <= 65535, "yb_loss_fwd_bwd: at most 65535 images per call");
+    // the per-image class sums are kept in 2^-32 fixed point: |sum| <= 27.7 * A * nc must stay below 2^31
+    YB_REQUIRE((double)n_anchors * (double)nc * 27.7 < 2147483648.0, "yb_loss_fwd_bwd: A * nc too large for the fixed-point sums");
     if (workspace_bytes < yb_loss_workspace_bytes(n_images, n_anchors, gt_total, dtype)) {
         set_error("yb_loss_fwd_bwd: workspace %zu B < required %zu B", workspace_bytes,
                   yb_loss_workspace_bytes(n_images, n_anchors, gt_total, dtype));
@@ -984,38 +959,25 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == YB_F32) {
         const bool vec = vector_ok<float>(preds, grad_preds, n_anchors);
-        const LossWorkspace w = carve(workspace, n_images, cls_tiles_for(n_anchors, dtype, vec), gt_total);
+        const LossWorkspace w = carve(workspace, n_images, gt_total);
         if (vec)
             return launch_loss<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt,
                                          gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl, (float *)grad_preds,
-                                         out_loss, out_idx, out_iou, out_per_image, w, st);
+                                         out_loss, out_idx, out_iou, out_per_image, w, flags, stage_events, st);
         return launch_loss<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
                                      gt_total, gmax, lambda_cls, lambda_dfl, (float *)grad_preds, out_loss, out_idx,
-                                     out_iou, out_per_image, w, st);
+                                     out_iou, out_per_image, w, flags, stage_events, st);
     }
     const bool vec = vector_ok<__nv_bfloat16>(preds, grad_preds, n_anchors);
-    const LossWorkspace w = carve(workspace, n_images, cls_tiles_for(n_anchors, dtype, vec), gt_total);
+    const LossWorkspace w = carve(workspace, n_images, gt_total);
     if (vec)
         return launch_loss<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides,
                                              gt, gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl,
                                              (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w,
-                                             st);
+                                             flags, stage_events, st);
     return launch_loss<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
                                          gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl,
-                                         (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w, st);
-}
-
-extern "C" int yb_stage_timing(int enable) {
-    g_stage_timing = enable != 0;
-    return YB_OK;
-}
-
-extern "C" int yb_loss_last_stage_ms(float *out_ms_host) {
-    YB_REQUIRE(out_ms_host != nullptr, "yb_loss_last_stage_ms: null pointer");
-    for (int i = 0; i < 4; ++i) YB_REQUIRE(g_stage_ev[i] != nullptr, "yb_loss_last_stage_ms: no timed call has run");
-    YB_CUDA(cudaEventSynchronize(g_stage_ev[3]));
-    for (int i = 0; i < 3; ++i) YB_CUDA(cudaEventElapsedTime(out_ms_host + i, g_stage_ev[i], g_stage_ev[i + 1]));
-    return YB_OK;
+                                         (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w, flags, stage_events, st);
 }
 
 extern "C" int yb_scale_grad(void *grad, int dtype, size_t n_elements, const float *scale, void *stream) {
@@ -1054,7 +1016,7 @@ extern "C" int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_ima
                             cudaMemcpyHostToDevice, st));
     const int rc = yb_loss_fwd_bwd(preds_dev, dtype, n_images, nc, reg_max, n_anchors, anchors, strides, gt_dev,
                                    gt_offsets_dev, gt_total, gmax, lambda_cls, lambda_dfl, grad_dev, out_loss_dev,
-                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, 0u, nullptr, stream);
     if (rc != YB_OK) return rc;
     YB_CUDA(cudaMemcpyAsync(out_loss_host, out_loss_dev, sizeof(float) * 8, cudaMemcpyDeviceToHost, st));
     if (grad_host != nullptr && grad_dev != nullptr)

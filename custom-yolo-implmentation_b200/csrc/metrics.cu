@@ -38,7 +38,7 @@ __device__ __forceinline__ float iou_xywh(const float4 &a, const float4 &b) {
 __global__ void __launch_bounds__(128)
 detection_match_kernel(const float *__restrict__ pred_rows, int row_stride, const int *__restrict__ pred_count,
                        const float *__restrict__ pred_scores, float score_thr, const float *__restrict__ gt,
-                       const int *__restrict__ gt_off, int n_images, int nc, float iou_thr,
+                       const int *__restrict__ gt_off, int n_images, int nc, float iou_thr, int skip_empty_targets,
                        unsigned long long *__restrict__ counters) {
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -47,6 +47,8 @@ detection_match_kernel(const float *__restrict__ pred_rows, int row_stride, cons
     const float *sc = pred_scores ? pred_scores + (size_t)n * row_stride : nullptr;
     const int p_all = pred_count[n];
     const int g0 = gt_off[n], m = gt_off[n + 1] - g0;
+    // the reference's validation loop only calls update() for images that have targets (train_model.py:326-328)
+    if (m == 0 && skip_empty_targets) return;
 
     // predictions that pass the score filter (metrics.py:82-86)
     int p = 0;
@@ -161,7 +163,7 @@ extern "C" size_t yb_detection_counters_bytes(int nc) { return nc > 0 ? sizeof(u
 extern "C" int yb_detection_match(const float *pred_rows, int row_stride, const int32_t *pred_count,
                                   const float *pred_scores, float score_threshold, const float *gt,
                                   const int32_t *gt_offsets, int gmax, int n_images, int nc, float iou_threshold,
-                                  uint64_t *counters, void *stream) {
+                                  int skip_empty_targets, uint64_t *counters, void *stream) {
     YB_REQUIRE(pred_count && gt_offsets && counters, "yb_detection_match: null pointer");
     YB_REQUIRE(n_images > 0 && nc > 0 && row_stride >= 0, "yb_detection_match: bad sizes");
     YB_REQUIRE(row_stride == 0 || pred_rows, "yb_detection_match: pred_rows is null");
@@ -169,7 +171,7 @@ extern "C" int yb_detection_match(const float *pred_rows, int row_stride, const 
     YB_REQUIRE(gmax == 0 || gt, "yb_detection_match: gt is null");
     detection_match_kernel<<<(n_images + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         pred_rows, row_stride, pred_count, pred_scores, score_threshold, gt, gt_offsets, n_images, nc, iou_threshold,
-        reinterpret_cast<unsigned long long *>(counters));
+        skip_empty_targets, reinterpret_cast<unsigned long long *>(counters));
     YB_LAUNCH_CHECK();
     return YB_OK;
 }

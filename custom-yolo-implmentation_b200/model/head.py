@@ -48,6 +48,13 @@ def _check_levels(box_outs, cls_outs):
     return n, box_ch, nc, [int(b.shape[2]) * int(b.shape[3]) for b in box_outs]
 
 
+def _copy_code(dtype) -> int:
+    """The gather / scatter kernels are pure copies and only care about the element size: fp16 head outputs (the
+    reference trains under fp16 autocast + GradScaler unless precision == 'bfloat16', train_model.py:240-246)
+    travel as the 2-byte type."""
+    return _cabi.YB_F32 if dtype == torch.float32 else _cabi.YB_BF16
+
+
 class _GatherLevels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n_levels, *levels):
@@ -60,7 +67,7 @@ class _GatherLevels(torch.autograd.Function):
         if out.numel():
             with torch.cuda.device(dev):
                 rc = _cabi.lib().yb_head_gather(_pointer_table(box_outs), _pointer_table(cls_outs), hw_host, n_levels,
-                                                _cabi.dtype_code(out.dtype), n, box_ch, nc, _cabi.ptr(out),
+                                                _copy_code(out.dtype), n, box_ch, nc, _cabi.ptr(out),
                                                 _cabi.stream_ptr(dev))
             _cabi.check(rc, "yb_head_gather")
         ctx.meta = (n_levels, n, box_ch, nc, hw, [tuple(t.shape) for t in levels])
@@ -74,7 +81,7 @@ class _GatherLevels(torch.autograd.Function):
         if grad.numel():
             hw_host = (ctypes.c_int32 * n_levels)(*hw)
             with torch.cuda.device(grad.device):
-                rc = _cabi.lib().yb_head_scatter(_cabi.ptr(grad), hw_host, n_levels, _cabi.dtype_code(grad.dtype), n,
+                rc = _cabi.lib().yb_head_scatter(_cabi.ptr(grad), hw_host, n_levels, _copy_code(grad.dtype), n,
                                                  box_ch, nc, _pointer_table(grads[:n_levels]),
                                                  _pointer_table(grads[n_levels:]), _cabi.stream_ptr(grad.device))
             _cabi.check(rc, "yb_head_scatter")
@@ -83,8 +90,8 @@ class _GatherLevels(torch.autograd.Function):
 
 def gather_levels(box_outs: List[torch.Tensor], cls_outs: List[torch.Tensor]) -> torch.Tensor:
     """``cat([cat((b, c), 1).view(N, C, -1) for b, c in levels], 2)`` (head.py:86-87, :119) in one launch."""
-    if box_outs[0].dtype not in (torch.float32, torch.bfloat16):
-        raise TypeError(f"head_tail: dtype must be float32 or bfloat16, got {box_outs[0].dtype}")
+    if box_outs[0].dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise TypeError(f"head_tail: dtype must be float32, bfloat16 or float16, got {box_outs[0].dtype}")
     return _GatherLevels.apply(len(box_outs), *box_outs, *cls_outs)
 
 

@@ -116,6 +116,25 @@ def _stream_workspace(n_bytes: int, device) -> torch.Tensor:
     return buf
 
 
+def _as_offsets(gt: torch.Tensor, gt_offsets: torch.Tensor, n: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The GT wire format as the kernels read it: ``gt (sum Mi, 5)`` fp32 and ``offsets (N+1,)`` int32, contiguous, on
+    ``device``.  A CPU (pinned) ``PackedGT`` straight from ``collate_fn_packed`` is moved, not dereferenced as a device
+    pointer.  Shape mistakes raise here; the VALUES of device-resident offsets cannot be checked without a sync."""
+    if gt_offsets.dim() != 1 or gt_offsets.numel() != n + 1:
+        raise ValueError(f"gt_offsets must have shape ({n + 1},) for a batch of {n}, got {tuple(gt_offsets.shape)}")
+    if gt.dim() != 2 or (gt.shape[0] and gt.shape[1] != 5):
+        raise ValueError(f"gt must have shape (sum Mi, 5), got {tuple(gt.shape)}")
+    if not gt_offsets.is_cuda:                                  # host offsets are free to validate
+        off = gt_offsets.tolist()
+        if off[0] != 0 or off[-1] != gt.shape[0] or any(b < a for a, b in zip(off, off[1:])):
+            raise ValueError(f"gt_offsets must rise from 0 to {gt.shape[0]} (the number of gt rows), got {off[:4]}...{off[-1]}")
+    if gt_offsets.device != device or gt_offsets.dtype != torch.int32 or not gt_offsets.is_contiguous():
+        gt_offsets = gt_offsets.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+    if gt.device != device or gt.dtype != torch.float32 or not gt.is_contiguous():
+        gt = gt.detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    return gt, gt_offsets
+
+
 def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
     if t.dtype == torch.float32 and t.device == device and t.is_contiguous() and not t.requires_grad:
         return t
@@ -124,12 +143,14 @@ def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
 
 def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, gmax: int, anchors: torch.Tensor,
                strides: torch.Tensor, num_classes: int, lambda_cls: float, lambda_dfl: float, reg_max: int = 16,
-               want_grad: bool = True, want_trace: bool = False):
+               want_grad: bool = True, want_trace: bool = False, flags: int = 0, stage_events=None):
     """One call of ``yb_loss_fwd_bwd``.  Returns ``(out_loss (8,), grad or None, trace dict)``.
 
-    ``out_loss`` = [total, mean DFL, mean QFL, #matched anchors, 0...] on the device.
-    ``trace`` (``want_trace``) holds the per-GT matched anchor / IoU and per-image loss terms the
-    parity tests compare against the oracle.
+    ``out_loss`` = [total, mean DFL, mean QFL, #matched anchors, 0, 0, 0, #GT rows with a class id outside
+    [0, nc)] on the device.  ``trace`` (``want_trace``) holds the per-GT matched anchor / IoU and per-image
+    loss terms the parity tests compare against the oracle.  ``flags``: ``_cabi.YB_LOSS_NO_PRUNE`` /
+    ``YB_LOSS_SPLIT_LAUNCH`` (test / profiling aids).  ``stage_events``: three ``torch.cuda.Event(enable_timing=True)``
+    recorded around the two launches (bench.py's roofline leg).
     """
     _cabi.require_cuda(preds, "preds")
     if preds.dim() != 3:
@@ -146,9 +167,17 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
     st = _as_f32(strides, dev)
     if anc.shape != (2, a) or st.numel() != a:
         raise ValueError(f"anchors must be (2, {a}) and strides (1, {a}); got {tuple(anc.shape)}, {tuple(st.shape)}")
+    gt, gt_offsets = _as_offsets(gt, gt_offsets, n, dev)
     gt_total = int(gt.shape[0])
     lib = _cabi.lib()
     ws = _stream_workspace(lib.yb_loss_workspace_bytes(n, a, gt_total, dt), dev)
+    ev = None
+    if stage_events is not None:
+        import ctypes
+        for e in stage_events:                      # torch creates the CUDA event lazily, on the first record
+            if not e.cuda_event:
+                e.record()
+        ev = (ctypes.c_void_p * 3)(*[e.cuda_event for e in stage_events])
     grad = torch.empty_like(x) if want_grad else None
     out = torch.empty(8, dtype=torch.float32, device=dev)
     trace = {}
@@ -163,9 +192,27 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
                                  _cabi.ptr(gt) if gt_total else None, _cabi.ptr(gt_offsets), gt_total, gmax,
                                  float(lambda_cls), float(lambda_dfl), _cabi.ptr(grad), _cabi.ptr(out),
                                  _cabi.ptr(idx), _cabi.ptr(iou), _cabi.ptr(per_image), _cabi.ptr(ws), ws.numel(),
-                                 _cabi.stream_ptr(dev))
+                                 int(flags), ev, _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_loss_fwd_bwd")
     return out, grad, trace
+
+
+def _take_grad(ctx):
+    """The gradient produced during the forward call is handed over once (it is scaled in place).  A second
+    backward through the same graph raises, as autograd does for freed buffers, instead of returning None."""
+    if getattr(ctx, "grad_taken", False):
+        raise RuntimeError("Trying to backward through the fused loss a second time: the gradient buffer was handed "
+                           "over (and scaled in place) by the first backward; run forward again")
+    ctx.grad_taken = True
+    g = ctx.grad
+    ctx.grad = None
+    return g
+
+
+def _raise_on_bad_class(n_bad: float, num_classes: int):
+    # the reference's scatter_ raises on these (src/model/losses.py:260); the kernels clamp and count
+    if n_bad:
+        raise RuntimeError(f"index out of range: {int(n_bad)} ground-truth row(s) carry a class id outside [0, {num_classes})")
 
 
 class _FusedLoss(torch.autograd.Function):
@@ -183,8 +230,7 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_total):
-        g = ctx.grad
-        ctx.grad = None
+        g = _take_grad(ctx)
         if g is None:
             return (None,) * 12
         scale = grad_total.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
@@ -221,6 +267,7 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     if not x.is_contiguous():
         x = x.contiguous()
     anc, st = _as_f32(anchors, dev), _as_f32(strides, dev)
+    gt, gt_offsets = _as_offsets(gt, gt_offsets, n, dev)
     gt_total = int(gt.shape[0])
     lib = _cabi.lib()
     ws = _stream_workspace(lib.yb_tal_workspace_bytes(n, a, gt_total, dt, topk), dev)
@@ -273,8 +320,7 @@ class _FusedTalLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_total):
-        g = ctx.grad
-        ctx.grad = None
+        g = _take_grad(ctx)
         if g is None:
             return (None,) * 11
         scale = grad_total.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
@@ -310,6 +356,9 @@ class YoloDFLQFLoss(nn.Module):
         self.lambda_box = lambda_box
         self.lambda_cls = lambda_cls
         self.lambda_dfl = lambda_dfl
+        if reg_max != 16:
+            # the reference's Head is hard-wired to 16 bins (src/model/head.py:35) and the kernels are built for that
+            raise ValueError(f"reg_max must be 16 (the head's DFL channel count, src/model/head.py:35), got {reg_max}")
         self.reg_max = reg_max
         self.assigner = assigner
         if cls_loss not in ("bce", "vfl"):
@@ -320,6 +369,8 @@ class YoloDFLQFLoss(nn.Module):
 
     def forward(self, preds, gt_boxes_list, anchors, strides):
         n = preds.shape[0]
+        if n == 0:                                  # the reference returns a zero loss and an empty dict (losses.py:268-269)
+            return torch.tensor(0.0, device=preds.device), {}
         if preds.dtype not in (torch.float32, torch.bfloat16):
             # fp16 (autocast + GradScaler) / fp64 head outputs: the kernels read fp32 or bf16, so do what the
             # reference does (losses.py:142 `.float()`); autograd casts the gradient back
@@ -339,7 +390,8 @@ class YoloDFLQFLoss(nn.Module):
                                         (self.lambda_box, self.lambda_cls, self.lambda_dfl), self.reg_max, self.tal,
                                         need_grad, holder)
             stats = self.last_stats = holder[0]
-            host = stats[:4].tolist()
+            host = stats.tolist()
+            _raise_on_bad_class(host[7], self.num_classes)
             return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2], "dfl_loss": host[3]}
         if n > 0 and sum(counts) == 0:
             # the reference fails here: total_dfl is still the python float 0.0 (losses.py:271-279)
@@ -349,7 +401,8 @@ class YoloDFLQFLoss(nn.Module):
         total = _FusedLoss.apply(preds, gt, off, max(counts), anchors, strides, self.num_classes,
                                  self.lambda_cls, self.lambda_dfl, self.reg_max, need_grad, holder)
         stats = self.last_stats = holder[0]
-        host = stats[:3].tolist()                       # one D2H copy (the reference does three .item())
+        host = stats.tolist()                           # one D2H copy (the reference does three .item())
+        _raise_on_bad_class(host[7], self.num_classes)
         return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2]}
 
 

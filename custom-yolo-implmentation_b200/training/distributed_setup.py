@@ -18,19 +18,19 @@ __all__ = ["reduce_value", "reduce_loss_stats", "shard_batch"]
 
 
 def reduce_value(value: Union[float, torch.Tensor], average: bool = True):
-    """Same contract as the reference's ``reduce_value`` (:28-63): sum (or mean) over all ranks;
-    identity when not distributed."""
+    """Same contract as the reference's ``reduce_value`` (:28-63): sum (or mean) over all ranks, returned as a
+    Python float (``value.item()``, :63) whatever was passed in; a tensor argument is reduced IN PLACE, as the
+    reference does (:58-61).  Identity when not distributed (:41-42)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() < 2:
         return value
     with torch.no_grad():
-        was_float = not isinstance(value, torch.Tensor)
-        t = torch.tensor(float(value)) if was_float else value
+        t = value if isinstance(value, torch.Tensor) else torch.tensor(float(value))
         if dist.get_backend() == "nccl" and not t.is_cuda:
             t = t.cuda()
         dist.all_reduce(t)
         if average:
-            t = t / dist.get_world_size()
-        return t.item() if was_float else t
+            t /= dist.get_world_size()
+        return t.item()
 
 
 def reduce_loss_stats(stats: torch.Tensor, n_local: int, group=None, async_op: bool = False):

@@ -85,13 +85,26 @@ class DetectionMetrics:
     class_gt_count = property(lambda self: self._class(3))
 
     # ---- updates ----
-    def update_batch(self, pred_rows: torch.Tensor, pred_count: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor,
-                     gmax: int, pred_scores: torch.Tensor = None, score_threshold: float = 0.5):
+    def update_batch(self, pred_rows: torch.Tensor, pred_count: torch.Tensor, gt, gt_offsets: torch.Tensor = None,
+                     gmax: int = None, pred_scores: torch.Tensor = None, score_threshold: float = 0.5,
+                     skip_empty_targets: bool = True):
         """All images of a batch in one launch.  ``pred_rows (N, K, 5)`` / ``pred_count (N,) int32`` as written by
-        ``decode_predictions_raw``; ``gt (sum Mi, 5)`` / ``gt_offsets (N+1,) int32`` as built by ``pack_gt``."""
+        ``decode_predictions_raw``; ``gt (sum Mi, 5)`` / ``gt_offsets (N+1,) int32`` as built by ``pack_gt``, or a
+        ``PackedGT`` (on any device: it is moved) in place of ``gt``.
+
+        ``skip_empty_targets`` (default, = the reference's validation loop, train_model.py:326-328, which calls
+        ``update`` only for images that HAVE targets): images without ground truth add nothing.  ``False`` applies
+        ``update``'s own rule to them (their predictions count as false positives, metrics.py:98-104)."""
         _cabi.require_cuda(pred_rows, "pred_rows")
         n, k = pred_rows.shape[0], pred_rows.shape[1]
         dev = pred_rows.device
+        if hasattr(gt, "offsets") and hasattr(gt, "counts"):            # a PackedGT
+            gt_offsets, gmax, gt = gt.offsets, (max(gt.counts) if len(gt.counts) else 0), gt.gt
+        if gt_offsets is None or gt_offsets.dim() != 1 or gt_offsets.numel() != n + 1:
+            raise ValueError(f"gt_offsets must have shape ({n + 1},) for a batch of {n}")
+        if gmax is None:
+            raise ValueError("gmax (the largest number of targets of one image) is required with raw gt / gt_offsets")
+        gt_offsets = gt_offsets.to(device=dev, dtype=torch.int32).contiguous()
         rows = pred_rows.detach().float().contiguous()
         cnt = pred_count.to(device=dev, dtype=torch.int32).contiguous()
         sc = None if pred_scores is None else pred_scores.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -101,7 +114,8 @@ class DetectionMetrics:
             rc = _cabi.lib().yb_detection_match(_cabi.ptr(rows) if k else None, k, _cabi.ptr(cnt), _cabi.ptr(sc),
                                                 float(score_threshold), _cabi.ptr(g) if g.shape[0] else None,
                                                 _cabi.ptr(gt_offsets), int(gmax), n, self.num_classes,
-                                                float(self.iou_threshold), _cabi.ptr(c), _cabi.stream_ptr(dev))
+                                                float(self.iou_threshold), int(bool(skip_empty_targets)), _cabi.ptr(c),
+                                                _cabi.stream_ptr(dev))
         _cabi.check(rc, "yb_detection_match")
 
     def update(self, predictions: torch.Tensor, targets: torch.Tensor, pred_scores: torch.Tensor = None,
@@ -118,7 +132,7 @@ class DetectionMetrics:
         gt = targets[:, :5] if m else torch.zeros(0, 5, device=dev)
         off = torch.tensor([0, m], dtype=torch.int32).to(dev)
         cnt = torch.tensor([p], dtype=torch.int32).to(dev)
-        self.update_batch(rows, cnt, gt, off, m, sc, score_threshold)
+        self.update_batch(rows, cnt, gt, off, m, sc, score_threshold, skip_empty_targets=False)
 
     # ---- results (same formulas as the reference, :162-207) ----
     def compute(self) -> Dict[str, float]:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 3
+#define YB_ABI_VERSION 4
 
 typedef enum { YB_F32 = 0, YB_BF16 = 1 } yb_dtype;
 
@@ -58,10 +58,16 @@ long long yb_launch_count(void);
  *   gmax         max boxes of any one image (host-known from the list shapes)
  *   grad_preds   (N, C, A) dtype or NULL                  d total_loss / d preds (NULL: forward only)
  *   out_loss     8 floats: [0] total  [1] mean DFL ("box_loss")  [2] mean QFL ("cls_loss")
- *                          [3] number of distinct matched anchors  [4..7] reserved (zero)
+ *                          [3] number of distinct matched anchors  [4..6] reserved (zero)
+ *                          [7] number of GT rows whose class id lies outside [0, nc): the reference raises on
+ *                              those (scatter_, src/model/losses.py:260); the kernels clamp the id to stay
+ *                              memory-safe and report the count, so the caller can raise without an extra sync
  *   out_idx      (gt_total) int32 or NULL                 matched anchor per GT  (losses.py:215)
  *   out_iou      (gt_total) fp32  or NULL                 IoU soft target per GT (losses.py:256)
  *   out_per_image (2, N) fp32 or NULL                     per-image DFL and QFL terms
+ *   flags        0, or YB_LOSS_NO_PRUNE / YB_LOSS_SPLIT_LAUNCH (test and profiling aids, results identical)
+ *   stage_events NULL, or three cudaEvent_t handles of the CALLER (as void*), recorded on `stream` before the
+ *                main launch, between the two launches and after the second (bench.py's roofline leg)
  *
  * The quirks of the reference that decide results are kept (Q1-Q6, Q16).
  * Images with no boxes contribute their QFL term and count in the mean (Q6).  The all-empty
@@ -75,13 +81,10 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
                     const float *gt, const int32_t *gt_offsets, int gt_total, int gmax,
                     float lambda_cls, float lambda_dfl,
                     void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou, float *out_per_image,
-                    void *workspace, size_t workspace_bytes, void *stream);
+                    void *workspace, size_t workspace_bytes, unsigned flags, void *const *stage_events, void *stream);
 
-/* Measurement aid: when enabled, yb_loss_fwd_bwd records CUDA events on its stream around each of its
- * three launches (fused main pass, match, finalize); yb_loss_last_stage_ms waits for the last timed
- * call and returns the three durations in milliseconds (host array of 3).  Off by default. */
-int yb_stage_timing(int enable);
-int yb_loss_last_stage_ms(float *out_ms_host);
+#define YB_LOSS_NO_PRUNE 1u      /* box role scans every (GT, tile) pair: the exactness tests compare with and without */
+#define YB_LOSS_SPLIT_LAUNCH 2u  /* box and class roles as two launches instead of one (profiling the roles apart) */
 
 /* grad *= *scale (device scalar), in place; returns without touching memory when *scale == 1.
  * Used by the autograd bridge for `loss.backward()` under a GradScaler
@@ -233,6 +236,9 @@ int yb_box_iou_batch(const float *box1, int n, const float *box2, int m, float *
  *   pred_rows   (N, row_stride, 5) fp32 [cx, cy, w, h, cls] (the layout yb_val_decode writes), pred_count (N)
  *   pred_scores (N, row_stride) or NULL; rows with score < score_threshold are ignored (:82-86)
  *   gt / gt_offsets as in yb_loss_fwd_bwd; gmax = most targets of one image (<= 1024)
+ *   skip_empty_targets != 0: images without targets add nothing, as in the reference's validation loop, which calls
+ *               update() only `if gt_box[i].numel() > 0` (train_model.py:327); 0 = update()'s own rule (their
+ *               predictions count as false positives, metrics.py:98-104)
  *   counters    uint64[8 + 4*nc], ACCUMULATED (zero them to reset):
  *               [0] tp [1] fp [2] fn [3] total_predictions [4] total_ground_truths
  *               [8..] class_tp, then class_fp, class_fn, class_gt_count (nc each)
@@ -240,7 +246,7 @@ int yb_box_iou_batch(const float *box1, int n, const float *box2, int m, float *
 size_t yb_detection_counters_bytes(int nc);
 int yb_detection_match(const float *pred_rows, int row_stride, const int32_t *pred_count, const float *pred_scores,
                        float score_threshold, const float *gt, const int32_t *gt_offsets, int gmax, int n_images,
-                       int nc, float iou_threshold, uint64_t *counters, void *stream);
+                       int nc, float iou_threshold, int skip_empty_targets, uint64_t *counters, void *stream);
 
 /* quality_focal_loss (src/model/losses.py:46-57) on dense (M, C) logits/targets, fp32:
  * out_loss[0] = -sum(...)/M; grad_scores (M, C) or NULL = d out_loss / d pred_scores (times *grad_out if given). */

@@ -76,13 +76,19 @@ class TalTrace:
     assigned_gt: Optional[torch.Tensor] = None      # (N, A) int64, -1 = background
     target_score: Optional[torch.Tensor] = None     # (N, A) fp32 t_i (0 for background)
     topk_anchor: List[torch.Tensor] = field(default_factory=list)   # per image (M, k) int64, -1 padded
+    margin: List[torch.Tensor] = field(default_factory=list)        # per image (M,) relative k-th / (k+1)-th metric gap
     grad: Optional[torch.Tensor] = None
 
 
 def assign_image(xyxy: torch.Tensor, cls_logits: torch.Tensor, gt: torch.Tensor, anc_px: torch.Tensor, topk: int,
-                 alpha: float, beta: float):
+                 alpha: float, beta: float, forced_assigned: Optional[torch.Tensor] = None):
     """Task-aligned assignment of one image.  xyxy (A,4) pixels, cls_logits (A,nc), gt (M,5), anc_px (A,2).
-    Returns (assigned_gt (A,) int64 with -1, target_score (A,), topk_anchor (M,k) with -1)."""
+    Returns (assigned_gt (A,) int64 with -1, target_score (A,), topk_anchor (M,k) with -1, margin (M,)).
+
+    ``margin``: relative gap between the GT's k-th and (k+1)-th best metric — a disagreement of the CUDA path on an
+    anchor of GT j is a numerical near-tie only if margin[j] is tiny.  ``forced_assigned`` (A,) skips the top-k and
+    the conflict resolution and takes this anchor -> GT map instead (the later stages — target scores, losses,
+    gradients — can then be checked on the CUDA path's own assignment when a near-tie went the other way)."""
     a = xyxy.shape[0]
     m = gt.shape[0]
     g = gt[:, :4].float()
@@ -96,7 +102,13 @@ def assign_image(xyxy: torch.Tensor, cls_logits: torch.Tensor, gt: torch.Tensor,
     metric = score.pow(alpha) * overlap.pow(beta) * inside
     # top-k among the inside anchors: metric descending, ties -> lowest anchor index
     key = torch.where(inside, metric, torch.full_like(metric, -1.0))
-    order = torch.sort(key, dim=1, descending=True, stable=True).indices[:, :topk]
+    ranked = torch.sort(key, dim=1, descending=True, stable=True)
+    order = ranked.indices[:, :topk]
+    if a > topk:
+        kth, nxt = ranked.values[:, topk - 1], ranked.values[:, topk]
+        margin = torch.where(nxt > 0, (kth - nxt) / kth.clamp(min=1e-30), torch.ones_like(kth))
+    else:
+        margin = torch.ones(m)
     chosen = torch.zeros(m, a, dtype=torch.bool)
     chosen.scatter_(1, order, True)
     chosen &= inside
@@ -105,21 +117,24 @@ def assign_image(xyxy: torch.Tensor, cls_logits: torch.Tensor, gt: torch.Tensor,
     ov = torch.where(chosen, overlap, torch.full_like(overlap, -1.0))
     best = ov.max(0)
     assigned = torch.where(chosen.any(0), best.indices, torch.full((a,), -1, dtype=torch.long))
+    if forced_assigned is not None:
+        assigned = forced_assigned.long()
     pos = torch.zeros(m, a, dtype=torch.bool)
     fg = assigned >= 0
     pos[assigned[fg], fg.nonzero()[:, 0]] = True
     max_metric = (metric * pos).amax(1)
     max_overlap = (overlap * pos).amax(1)
     norm = (metric * pos * (max_overlap / (max_metric + EPS_NORM))[:, None]).amax(0)    # (A,)
-    return assigned, norm * fg, topk_anchor
+    return assigned, norm * fg, topk_anchor, margin
 
 
 def tal_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torch.Tensor, strides: torch.Tensor,
                 num_classes: int, lambda_box: float = 1.5, lambda_cls: float = 1.0, lambda_dfl: float = 1.5,
                 reg_max: int = 16, topk: int = 10, alpha: float = 0.5, beta: float = 6.0,
                 tss_override: Optional[float] = None, cls_loss: str = "bce", vfl_alpha: float = 0.75,
-                vfl_gamma: float = 2.0) -> TalTrace:
-    """``tss_override`` replaces the local normaliser (DDP: the all-reduced sum / world)."""
+                vfl_gamma: float = 2.0, forced_assigned: Optional[torch.Tensor] = None) -> TalTrace:
+    """``tss_override`` replaces the local normaliser (DDP: the all-reduced sum / world);
+    ``forced_assigned`` (N, A) replaces the assignment (see ``assign_image``)."""
     n = preds.shape[0]
     logits, _, xyxy, _ = decode_boxes(preds, anchors, strides, reg_max)
     a = xyxy.shape[1]
@@ -137,10 +152,13 @@ def tal_forward(preds: torch.Tensor, gts: Sequence[torch.Tensor], anchors: torch
             gt = gts[b]
             if gt.numel() == 0:
                 tr.topk_anchor.append(torch.zeros(0, topk, dtype=torch.long))
+                tr.margin.append(torch.zeros(0))
                 continue
-            asg, t, tk = assign_image(xyxy[b], cls[b], gt, anc_px, topk, alpha, beta)
+            asg, t, tk, mg = assign_image(xyxy[b], cls[b], gt, anc_px, topk, alpha, beta,
+                                          None if forced_assigned is None else forced_assigned[b])
             tr.assigned_gt[b], tr.target_score[b] = asg, t
             tr.topk_anchor.append(tk)
+            tr.margin.append(mg)
             fg = asg >= 0
             target[b, fg.nonzero()[:, 0], gt[asg[fg], 4].long()] = t[fg]
             label[b, fg.nonzero()[:, 0], gt[asg[fg], 4].long()] = 1.0

@@ -97,7 +97,16 @@ def ref_matched_idx(preds, gts, anchors, strides, reg_max=16):
     return out, ious, xywh
 
 
+ONLY = set(sys.argv[1:])          # optional: regenerate just the named fixtures
+
+
+def _skip(name):
+    return bool(ONLY) and name not in ONLY
+
+
 def loss_case(name, n, nc, imgsz, gmax, seed, dtype=torch.float32, conflict=0.0, store_inputs=True, sample=None):
+    if _skip(name):
+        return
     preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed, dtype=dtype, conflict_frac=conflict)
     leaf = preds.clone().requires_grad_(True)
     crit = ref_losses.YoloDFLQFLoss(num_classes=nc)
@@ -128,8 +137,33 @@ def loss_case(name, n, nc, imgsz, gmax, seed, dtype=torch.float32, conflict=0.0,
           f"GT {int(gt_cnt.sum())} duplicate-anchor GTs {dup}")
 
 
+def rank_losses_case(name, world, n, nc, imgsz, gmax, seed0):
+    """cfg3 (8 ranks x cfg2): the reference's loss scalars and matched anchors of every rank's shard of bench.py
+    (rank r draws its batch with seed seed0 + r), so that the multi-GPU run can be checked rank by rank on the box."""
+    if _skip(name):
+        return
+    tot, box, cls, idx_all, cnt_all = [], [], [], [], []
+    for r in range(world):
+        preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed0 + r)
+        with torch.no_grad():
+            loss, parts = ref_losses.YoloDFLQFLoss(num_classes=nc)(preds, gts, anchors, strides)
+        idx, _, _ = ref_matched_idx(preds, gts, anchors, strides)
+        tot.append(parts["total_loss"]); box.append(parts["box_loss"]); cls.append(parts["cls_loss"])
+        idx_all.append(torch.cat(idx).numpy().astype(np.int32)); cnt_all.append(np.array([g.shape[0] for g in gts], np.int32))
+        print(f"{name} rank {r}: loss {parts['total_loss']:.6f} GT {int(cnt_all[-1].sum())}")
+    k = max(len(i) for i in idx_all)
+    idx_pad = np.full((world, k), -1, np.int32)
+    for r, i in enumerate(idx_all):
+        idx_pad[r, : len(i)] = i
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array([world, n, nc, imgsz, gmax, seed0], np.int64),
+                        total_loss=np.array(tot, np.float32), box_loss=np.array(box, np.float32),
+                        cls_loss=np.array(cls, np.float32), idx=idx_pad, gt_count=np.stack(cnt_all))
+
+
 def nms_case(name, n, nc, imgsz, seed, conf, iou, max_det=300, agnostic=False, classes=None, dense=False, nm=0,
              multi_label=False, allow_ties=False, store_inputs=True):
+    if _skip(name):
+        return
     x = syn.make_nms_input(n, nc, imgsz, seed, dense_uniform=dense)
     if nm:
         g = torch.Generator().manual_seed(seed + 1)
@@ -150,6 +184,8 @@ def nms_case(name, n, nc, imgsz, seed, conf, iou, max_det=300, agnostic=False, c
 
 
 def decode_case(name, n, nc, imgsz, seed, conf, top_k, cls_mean):
+    if _skip(name):
+        return
     anchors, strides = syn.anchor_grid(imgsz)
     preds = syn.make_preds(n, nc, anchors.shape[1], seed, cls_mean=cls_mean, cls_std=1.5)
     out = ref_train.decode_predictions(preds, anchors, strides, conf_threshold=conf, top_k=top_k, num_classes=nc)
@@ -168,6 +204,8 @@ def decode_case(name, n, nc, imgsz, seed, conf, top_k, cls_mean):
 
 
 def metrics_case(name, seed, n_images, nc, thr):
+    if _skip(name):
+        return
     """DetectionMetrics of the reference on seeded predictions/targets (incl. empty images, score filter)."""
     g = torch.Generator().manual_seed(seed)
     mt = ref_metrics.DetectionMetrics(nc, iou_threshold=thr)
@@ -208,6 +246,8 @@ def metrics_case(name, seed, n_images, nc, thr):
 
 
 def helper_case(name, seed):
+    if _skip(name):
+        return
     g = torch.Generator().manual_seed(seed)
     m, c = 37, 11
     b1 = torch.cat((torch.rand(m, 2, generator=g) * 200, 5 + torch.rand(m, 2, generator=g) * 90), 1)
@@ -233,6 +273,8 @@ def helper_case(name, seed):
 
 
 def head_case(name, seed, n, nc, shapes, dtype=torch.float32):
+    if _skip(name):
+        return
     """Head.forward of the reference (head.py:77-121) on random feature maps; the outputs of its box / cls
     towers (what the tail concatenates) are captured with forward hooks."""
     torch.manual_seed(seed)
@@ -262,6 +304,11 @@ if __name__ == "__main__":
     loss_case("loss_small_bf16", 2, 6, 128, 10, 303, dtype=torch.bfloat16)
     loss_case("loss_nc171_fp32", 1, 171, 96, 5, 404)
     loss_case("loss_cfg1_summary", 16, 80, 640, 50, 1235, store_inputs=False, sample=4099)
+    # the full cfg2 batch (N=128, <=100 GT/img, fp32) and four images of the cfg5 shape (1280x1280, <=300 GT/img, bf16
+    # head outputs): summaries only, the tests regenerate the inputs from the seed
+    loss_case("loss_cfg2_summary", 128, 80, 640, 100, 1236, store_inputs=False, sample=65537)
+    loss_case("loss_cfg5_summary", 4, 80, 1280, 300, 1240, dtype=torch.bfloat16, store_inputs=False, sample=16411)
+    rank_losses_case("loss_cfg3_ranks", 8, 128, 80, 640, 100, 1236)
     nms_case("nms_small", 3, 6, 160, 11, conf=0.001, iou=0.7)
     nms_case("nms_dense_maxdet", 2, 4, 160, 12, conf=0.25, iou=0.45, max_det=40, dense=True)
     nms_case("nms_agnostic", 2, 6, 160, 13, conf=0.05, iou=0.5, agnostic=True)

@@ -36,7 +36,9 @@ def _worker(rank, world, port, out):
     stats = torch.tensor([tr.total.item(), tr.dfl_mean.item(), tr.cls_mean.item(), fg, 0, 0, 0, 0])
     red = DS.reduce_loss_stats(stats, hi - lo)
     mean3 = [DS.reduce_value(v, average=True) for v in (tr.total.item(), tr.dfl_mean.item(), tr.cls_mean.item())]
-    tsum = DS.reduce_value(torch.tensor([float(rank + 1)]), average=False)
+    tbuf = torch.tensor([float(rank + 1)])
+    tsum = DS.reduce_value(tbuf, average=False)           # a Python float, and the tensor is reduced in place (reference :58-63)
+    assert isinstance(tsum, float) and tbuf.item() == tsum
     if rank == 0:
         full = L.loss_forward(preds, gts, anchors, strides, nc)
         torch.save({"red": red, "mean3": mean3, "tsum": tsum, "full": [full.total.item(), full.dfl_mean.item(), full.cls_mean.item()],
@@ -56,7 +58,7 @@ def test_sharded_loss_stats_match_the_unsharded_batch(tmp_path):
         assert abs(red[k].item() - full[k]) <= 2e-6 * abs(full[k])
         assert abs(r["mean3"][k] - full[k]) <= 2e-6 * abs(full[k])       # the reference's three reduce_value calls
     assert red[3].item() == r["fg_full"] and red[4].item() == 4.0
-    assert r["tsum"].item() == 3.0
+    assert r["tsum"] == 3.0
 
 
 def test_reduce_helpers_are_identity_without_a_process_group():

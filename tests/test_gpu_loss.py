@@ -26,10 +26,10 @@ def run_cuda(preds, gts, anchors, strides, nc, dev, **kw):
     return loss.detach().cpu(), parts, x.grad.detach().cpu(), crit
 
 
-def run_cuda_trace(preds, gts, anchors, strides, nc, dev, want_grad=True, lambda_cls=1.0, lambda_dfl=1.5):
+def run_cuda_trace(preds, gts, anchors, strides, nc, dev, want_grad=True, lambda_cls=1.0, lambda_dfl=1.5, flags=0):
     gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
     out, grad, tr = P.fused_loss(preds.to(dev), gt, off, max(counts), anchors.to(dev), strides.to(dev), nc,
-                                 lambda_cls, lambda_dfl, want_grad=want_grad, want_trace=True)
+                                 lambda_cls, lambda_dfl, want_grad=want_grad, want_trace=True, flags=flags)
     idx = tr["idx"].cpu().long()
     split = lambda t: list(torch.split(t, counts))
     return out.cpu(), (grad.cpu() if grad is not None else None), split(idx), split(tr["iou"].cpu()), \
@@ -138,6 +138,62 @@ def test_cfg1_summary_against_reference(cuda_device):
     assert abs(g.double().abs().sum().item() - float(z["grad_abs_sum"])) <= 1e-5 * float(z["grad_abs_sum"])
 
 
+def _summary_check(name, cuda_device, rtol):
+    """A committed summary of the reference's own outputs (tests/golden/make_golden.py) on inputs regenerated from
+    the seed: loss scalars, every matched anchor, a strided sample of the gradient and its L1 norm."""
+    z = load_golden(name)
+    n, nc, imgsz, gmax, seed = (int(v) for v in z["meta"][:5])
+    dtype = torch.bfloat16 if int(z["meta"][5]) else torch.float32
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed, dtype=dtype)
+    out, grad, idx, _, _, _ = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    for k, key in enumerate(("total_loss", "box_loss", "cls_loss")):
+        assert abs(out[k].item() - float(z[key])) <= rtol * float(z[key]), (key, out[k].item(), float(z[key]))
+    total = int(z["gt_count"].sum())
+    agree = sum(int((idx[b].numpy() == z["idx"][b, : len(idx[b])]).sum()) for b in range(n))
+    print(f"{name}: {agree} of {total} matched anchors identical to the reference's")
+    g = grad.float().flatten()
+    samp = g[:: int(z["grad_sample_stride"])]
+    gerr = (samp - torch.from_numpy(z["grad_sample"])).abs().max().item()
+    l1err = abs(g.double().abs().sum().item() - float(z["grad_abs_sum"])) / float(z["grad_abs_sum"])
+    return agree, total, gerr / float(z["grad_absmax"]), l1err
+
+
+def test_cfg2_summary_against_reference(cuda_device):
+    """cfg2 in full (N=128, 640x640, nc=80, <=100 GT/img, fp32): the reference's own outputs."""
+    agree, total, gerr, l1err = _summary_check("loss_cfg2_summary", cuda_device, F32_RTOL)
+    assert agree == total                                   # 6747 of 6747
+    assert gerr <= F32_RTOL and l1err <= 1e-5
+
+
+def test_cfg5_shape_summary_against_reference(cuda_device):
+    """Four images of cfg5's shape (1280x1280 = 33600 anchors, <=300 GT/img, bf16 head outputs)."""
+    agree, total, gerr, l1err = _summary_check("loss_cfg5_summary", cuda_device, BF16_RTOL)
+    assert agree == total                                   # the matching runs in fp32 on the bf16 values: exact
+    assert gerr <= BF16_RTOL and l1err <= BF16_RTOL
+
+
+def test_cfg5_shape_matches_oracle(cuda_device):
+    """The same shape against the CPU oracle stage by stage (indices, IoUs, per-image terms, whole gradient)."""
+    n, nc = 4, 80
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, 1280, 300, 1240, dtype=torch.bfloat16)
+    out, grad, idx, iou, dfl_img, cls_img = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    ora = L.loss_forward_backward(preds, gts, anchors, strides, nc)
+    tot, bad = idx_agreement(idx, ora)
+    print(f"cfg5 shape: {tot - len(bad)} of {tot} matched anchors identical to the oracle's")
+    for b, m, margin in bad:
+        assert margin < 5e-3, f"image {b} GT {m}: anchors differ with a runner-up margin of {margin}"
+    if bad:
+        ora = L.loss_forward_backward(preds, gts, anchors, strides, nc, forced_idx=idx)
+    assert grad.dtype == torch.bfloat16 and max(g.shape[0] for g in gts) > 256       # three GT chunks per tile
+    assert abs(out[0].item() - ora.total.item()) <= BF16_RTOL * abs(ora.total.item())
+    # the loss terms themselves are fp32 arithmetic on the bf16 values: far inside the bf16 budget
+    assert torch.allclose(dfl_img, ora.dfl_per_image, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(cls_img, ora.cls_per_image, rtol=1e-4, atol=1e-8)
+    for b in range(n):
+        assert torch.allclose(iou[b], ora.iou[b], rtol=1e-3, atol=1e-5)
+    assert_grad_close(grad, ora.grad, BF16_RTOL)
+
+
 def test_full_size_properties_cfg2(cuda_device):
     """cfg2 (N=128, 640x640, nc=80, <=100 GT): size-independent properties + oracle on a slice."""
     n, nc = 128, 80
@@ -164,11 +220,15 @@ def test_full_size_properties_cfg2(cuda_device):
     # (5) oracle on 6 of the 128 images (per-image terms do not depend on the rest of the batch)
     sel = [0, 1, 2, 50, 100, 127]
     ora = L.loss_forward_backward(preds[sel], [gts[i] for i in sel], anchors, strides, nc)
+    redo = False
     for k, i in enumerate(sel):
         if not torch.equal(idx[i], ora.idx[k]):
             bad = (idx[i] != ora.idx[k]).nonzero()[:, 0]
             assert float(ora.margin[k][bad].max()) < 5e-3
-            continue
+            redo = True
+    if redo:        # a near-tie went the other way: the later stages are checked on the GPU's own matching, never skipped
+        ora = L.loss_forward_backward(preds[sel], [gts[i] for i in sel], anchors, strides, nc, forced_idx=[idx[i] for i in sel])
+    for k, i in enumerate(sel):
         assert abs(dfl_img[i].item() - ora.dfl_per_image[k].item()) <= F32_RTOL * max(abs(ora.dfl_per_image[k].item()), 1e-6)
         assert abs(cls_img[i].item() - ora.cls_per_image[k].item()) <= F32_RTOL * abs(ora.cls_per_image[k].item())
         assert_grad_close(grad[i] * (n / len(sel)), ora.grad[k], F32_RTOL)
@@ -186,6 +246,41 @@ def test_forward_only_under_no_grad_and_empty_batch(cuda_device):
     assert parts == parts2 and loss2.requires_grad
     with pytest.raises(AttributeError):        # the reference fails the same way
         crit(x, [torch.zeros(0, 5, device=cuda_device)] * 3, anchors.to(cuda_device), strides.to(cuda_device))
+
+
+def test_reference_error_behaviour_is_kept(cuda_device):
+    """What the reference does on malformed calls: a class id outside [0, nc) raises (scatter_, losses.py:260); an empty
+    batch returns (0, {}) (losses.py:268-269); a second backward through the same graph raises."""
+    dev = cuda_device
+    preds, gts, anchors, strides = syn.make_loss_inputs(2, 6, 128, 10, 102)
+    crit = P.YoloDFLQFLoss(num_classes=6)
+    bad = [g.clone() for g in gts]
+    k = next(i for i, g in enumerate(bad) if g.shape[0] > 0)
+    bad[k][0, 4] = 6.0
+    with pytest.raises(RuntimeError, match="class id outside"):
+        crit(preds.to(dev), [g.to(dev) for g in bad], anchors.to(dev), strides.to(dev))
+    bad[k][0, 4] = -1.0
+    with pytest.raises(RuntimeError, match="class id outside"):
+        P.YoloDFLQFLoss(num_classes=6, assigner="tal")(preds.to(dev), [g.to(dev) for g in bad], anchors.to(dev), strides.to(dev))
+    loss0, parts0 = crit(preds[:0].to(dev), [], anchors.to(dev), strides.to(dev))
+    assert loss0.item() == 0.0 and parts0 == {}
+    x = preds.to(dev).requires_grad_(True)
+    loss, _ = crit(x, [g.to(dev) for g in gts], anchors.to(dev), strides.to(dev))
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+    with pytest.raises(ValueError, match="reg_max"):
+        P.YoloDFLQFLoss(num_classes=6, reg_max=8)
+    # the GT wire format may still sit in (pinned) host memory, or carry int64 offsets: it is normalised, never
+    # dereferenced as a device pointer
+    packed = P.pack_gt_host(gts)
+    out_a, _, _ = P.fused_loss(preds.to(dev), packed.gt, packed.offsets.long(), max(packed.counts), anchors.to(dev), strides.to(dev),
+                               6, 1.0, 1.5)
+    gt_d, off_d, counts = P.pack_gt([g.to(dev) for g in gts], dev)
+    out_b, _, _ = P.fused_loss(preds.to(dev), gt_d, off_d, max(counts), anchors.to(dev), strides.to(dev), 6, 1.0, 1.5)
+    assert torch.equal(out_a, out_b)
+    with pytest.raises(ValueError, match="gt_offsets"):
+        P.fused_loss(preds.to(dev), gt_d, off_d[:-1], max(counts), anchors.to(dev), strides.to(dev), 6, 1.0, 1.5)
 
 
 def test_grad_output_scaling_and_noncontiguous_input(cuda_device):
@@ -265,16 +360,17 @@ def test_fused_loss_is_cuda_graph_capturable(cuda_device):
     (4, 640, 100, torch.float32, 63),          # cfg2 shape
     (2, 640, 500, torch.float32, 64),          # more survivors than one chunk holds
 ])
-def test_tile_pruning_never_changes_the_result(n, imgsz, gmax, dtype, seed, cuda_device, monkeypatch):
+def test_tile_pruning_never_changes_the_result(n, imgsz, gmax, dtype, seed, cuda_device):
     """The box role skips (GT, tile) pairs that cannot beat the distance already published (csrc/loss.cu,
     assign_body).  That must be invisible: matched anchors, IoUs, loss terms and the gradient are bit-identical
-    with the pruning switched off (YB_ASSIGN_PRUNE=0), at sizes where almost every pair is pruned."""
+    with the pruning switched off (flag YB_LOSS_NO_PRUNE) and with the two roles launched separately
+    (YB_LOSS_SPLIT_LAUNCH), at sizes where almost every pair is pruned."""
+    from custom_yolo_implmentation_b200 import _cabi
     preds, gts, anchors, strides = syn.make_loss_inputs(n, 80, imgsz, gmax, seed, dtype=dtype)
-    monkeypatch.setenv("YB_ASSIGN_PRUNE", "0")
-    ref = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
-    monkeypatch.delenv("YB_ASSIGN_PRUNE")
-    for _ in range(3):                          # what is pruned depends on CTA timing; the result must not
-        got = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
+    ref = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device, flags=_cabi.YB_LOSS_NO_PRUNE)
+    for it in range(3):                         # what is pruned depends on CTA timing; the result must not
+        got = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device,
+                             flags=_cabi.YB_LOSS_SPLIT_LAUNCH if it == 2 else 0)
         assert torch.equal(got[0], ref[0])
         assert torch.equal(got[1], ref[1])
         for a, b in zip(got[2], ref[2]):

@@ -167,25 +167,58 @@ def test_decode_matches_reference_golden(name, cuda_device):
     assert torch.allclose(fused.cpu(), torch.from_numpy(z["box_xywh"]), rtol=1e-5, atol=1e-4)
 
 
+def _check_val_decode(rows, anchor, k, preds_b, box_b, conf, top_k, tol=2e-6):
+    """One image of decode_predictions against exact arithmetic, allowing ONLY what float rounding of the sigmoid can
+    change: an anchor may enter / leave at the confidence threshold or at the top-k boundary, or swap places with a
+    neighbour, if and only if the scores involved agree to `tol` relative.  Everything else is exact."""
+    sc = preds_b[64:, :].double().sigmoid()                     # (nc, A) in fp64: the arbiter of near-ties
+    best, cid = sc.max(0)
+    a = anchor[:k].long()
+    assert a.unique().numel() == k                              # no anchor twice
+    n_cand = int((best >= conf).sum())
+    near_thr = int(((best - conf).abs() <= tol * conf).sum())
+    assert abs(k - min(n_cand, top_k)) <= near_thr, (k, n_cand, near_thr)
+    got = best[a]
+    assert (got >= conf * (1 - tol)).all()                      # nothing below the threshold
+    if n_cand <= top_k - near_thr:
+        assert torch.equal(a, a.sort().values)                  # no top-k: rows stay in anchor order (train_model.py:126-133)
+    else:
+        kth = best.sort(descending=True).values[min(top_k, n_cand) - 1]
+        assert (got >= kth * (1 - tol)).all()                   # every row belongs to the top-k
+        assert (got[1:] <= got[:-1] * (1 + tol)).all()          # ... in descending score order
+        # equal scores (frequent with bf16 logits): lowest anchor first
+        tie = (got[1:] == got[:-1])
+        assert (a[1:][tie] > a[:-1][tie]).all()
+    # class id: the first maximum, unless the two best classes tie to rounding
+    top2 = sc[:, a].topk(2, 0).values
+    clear = (top2[0] - top2[1]) > tol * top2[0]
+    assert torch.equal(rows[:k, 4].long()[clear], cid[a][clear])
+    assert torch.allclose(rows[:k, :4], box_b[a].float(), rtol=1e-5, atol=1e-4)
+
+
 def test_val_decode_against_oracle_full_grid(cuda_device):
     anchors, strides = syn.anchor_grid(640)
+    agree = {}
     for seed, conf, top_k, mean, dt in [(5, 0.25, 100, -1.0, torch.float32), (6, 0.5, 100, -6.0, torch.float32),
-                                        (7, 0.25, 17, -2.0, torch.float32), (8, 0.25, 100, -1.0, torch.bfloat16)]:
+                                        (7, 0.25, 17, -2.0, torch.float32), (8, 0.25, 100, -1.0, torch.bfloat16),
+                                        (9, 0.9, 100, -3.0, torch.bfloat16)]:
         preds = syn.make_preds(3, 80, anchors.shape[1], seed, cls_mean=mean, cls_std=1.5, dtype=dt)
         rows, count, anchor = decode_predictions_raw(preds.to(cuda_device), anchors.to(cuda_device), strides.to(cuda_device),
                                                      conf, top_k, 80, want_anchor=True)
         ora = D.val_decode(preds.float(), anchors, strides, conf, top_k, 80)
+        ltrb = D.dfl_expectation(preds.float()[:, :64, :]).permute(0, 2, 1)
+        box = D.ltrb_to_box(ltrb, anchors.float().transpose(0, 1).unsqueeze(0), xywh=True, dim=2) * strides.float().transpose(0, 1).unsqueeze(0)
+        same = tot = 0
         for b in range(3):
             k = int(count[b])
-            assert k == ora.rows[b].shape[0]
-            if dt == torch.float32:
-                # bit-exact rows order unless two scores tie to the last ulp between CPU and GPU sigmoid
-                same = anchor[b, :k].cpu().long() == ora.anchor[b]
-                assert same.float().mean().item() >= 0.97
-                sel = same.nonzero()[:, 0]
-                assert torch.allclose(rows[b, :k].cpu()[sel], ora.rows[b][sel], rtol=1e-5, atol=1e-4)
-            else:
-                assert set(anchor[b, :k].cpu().tolist()) & set(ora.anchor[b].tolist())
+            _check_val_decode(rows[b].cpu(), anchor[b].cpu(), k, preds[b].float(), box[b], conf, top_k)
+            if k == ora.rows[b].shape[0]:
+                same += int((anchor[b, :k].cpu().long() == ora.anchor[b]).sum())
+            tot += ora.rows[b].shape[0]
+        agree[(seed, str(dt))] = (same, tot)
+    print("val decode rows in the oracle's exact position:", agree)
+    # with fp32 logits score ties are rare: the CPU oracle's own float ordering is matched almost everywhere
+    assert all(s >= 0.97 * t for (seed, dt), (s, t) in agree.items() if dt == "torch.float32")
 
 
 def test_make_anchors_and_helpers_match_reference(cuda_device):

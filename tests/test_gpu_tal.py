@@ -19,6 +19,28 @@ def run_cuda(preds, gts, anchors, strides, nc, dev, **kw):
     return out.cpu(), grad.cpu(), tr["assigned_gt"].cpu().long(), tr["target_score"].cpu(), tr["stats"].cpu()
 
 
+def oracle_on_gpu_assignment(asg, preds, gts, anchors, strides, nc, backward=True, **kw):
+    """The oracle, and how far the CUDA assignment is from it.  A differing anchor is acceptable only when the metric
+    of its GT has a numerical near-tie at the top-k boundary (relative gap k-th / (k+1)-th below 1e-4) or it is a
+    conflict decided by near-equal overlaps; in that case the oracle is re-run ON THE CUDA ASSIGNMENT, so that target
+    scores, losses and gradients are still checked — never skipped.  Returns (oracle trace, #differing anchors)."""
+    run = T.tal_forward_backward if backward else T.tal_forward
+    ora = run(preds, gts, anchors, strides, nc, **kw)
+    diff = asg != ora.assigned_gt
+    n_diff = int(diff.sum())
+    n_fg = int((ora.assigned_gt >= 0).sum())
+    assert n_diff <= max(2, n_fg // 200), f"{n_diff} of {n_fg} foreground anchors differ"
+    if n_diff:
+        for b, a in diff.nonzero().tolist():
+            involved = {int(asg[b, a]), int(ora.assigned_gt[b, a])} - {-1}
+            tight = min(float(ora.margin[b][j]) for j in involved)
+            both_fg = len(involved) == 2            # a conflict between two GTs: decided by near-equal overlaps
+            assert tight < 1e-4 or both_fg, f"image {b} anchor {a}: GTs {involved}, top-k margin {tight:.3e}"
+        ora = run(preds, gts, anchors, strides, nc, forced_assigned=asg, **kw)
+        assert torch.equal(ora.assigned_gt, asg)
+    return ora, n_diff
+
+
 def make_inputs(n, nc, imgsz, gmax, seed, dtype=torch.float32):
     preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed, dtype=dtype)
     # give the class logits some spread so that the alignment metric is not dominated by ties
@@ -36,21 +58,17 @@ def make_inputs(n, nc, imgsz, gmax, seed, dtype=torch.float32):
 def test_tal_matches_oracle(n, nc, imgsz, gmax, seed, topk, cuda_device):
     preds, gts, anchors, strides = make_inputs(n, nc, imgsz, gmax, seed)
     out, grad, asg, tsc, stats = run_cuda(preds, gts, anchors, strides, nc, cuda_device, topk=topk)
-    ora = T.tal_forward_backward(preds, gts, anchors, strides, nc, topk=topk)
-    diff = (asg != ora.assigned_gt)
-    n_fg = int((ora.assigned_gt >= 0).sum())
-    assert n_fg > 0
-    assert int(diff.sum()) <= max(1, n_fg // 200), f"{int(diff.sum())} of {n_fg} foreground anchors differ"
-    if int(diff.sum()) == 0:
-        assert int(stats[1].item()) == ora.num_fg
-        assert torch.allclose(tsc, ora.target_score, rtol=2e-5, atol=1e-7)
-        assert abs(stats[0].item() - ora.tss) <= 1e-5 * max(ora.tss, 1.0)
-        for k, ref in enumerate((ora.total, ora.box, ora.cls, ora.dfl)):
-            assert abs(out[k].item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7, (k, out[k].item(), ref.item())
-        scale = ora.grad.abs().max().item()
-        assert (grad - ora.grad).abs().max().item() <= 1e-5 * scale
-        # box-channel gradient only on foreground anchors
-        assert ((grad[:, :64].abs().sum(1) > 0) <= (asg >= 0)).all()
+    ora, n_diff = oracle_on_gpu_assignment(asg, preds, gts, anchors, strides, nc, topk=topk)
+    print(f"TAL assignment: {int((asg >= 0).sum()) - n_diff} of {int((asg >= 0).sum())} foreground anchors bit-exact")
+    assert ora.num_fg > 0 and int(stats[1].item()) == ora.num_fg
+    assert torch.allclose(tsc, ora.target_score, rtol=2e-5, atol=1e-7)
+    assert abs(stats[0].item() - ora.tss) <= 1e-5 * max(ora.tss, 1.0)
+    for k, ref in enumerate((ora.total, ora.box, ora.cls, ora.dfl)):
+        assert abs(out[k].item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7, (k, out[k].item(), ref.item())
+    scale = ora.grad.abs().max().item()
+    assert (grad - ora.grad).abs().max().item() <= 1e-5 * scale
+    # box-channel gradient only on foreground anchors
+    assert ((grad[:, :64].abs().sum(1) > 0) <= (asg >= 0)).all()
 
 
 @pytest.mark.parametrize("gamma", [2.0, 1.5])
@@ -60,9 +78,7 @@ def test_tal_varifocal_class_loss_matches_oracle(gamma, dtype, cuda_device):
     preds, gts, anchors, strides = make_inputs(2, 20, 320, 40, 35, dtype=dtype)
     out, grad, asg, tsc, stats = run_cuda(preds, gts, anchors, strides, 20, cuda_device, cls_loss="vfl", vfl_alpha=0.6,
                                           vfl_gamma=gamma)
-    ora = T.tal_forward_backward(preds, gts, anchors, strides, 20, cls_loss="vfl", vfl_alpha=0.6, vfl_gamma=gamma)
-    if not asg.equal(ora.assigned_gt):
-        pytest.skip("assignment differs on a numerical near-tie; covered by test_tal_matches_oracle")
+    ora, _ = oracle_on_gpu_assignment(asg, preds, gts, anchors, strides, 20, cls_loss="vfl", vfl_alpha=0.6, vfl_gamma=gamma)
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     for k, ref in enumerate((ora.total, ora.box, ora.cls, ora.dfl)):
         assert abs(out[k].item() - ref.item()) <= tol * abs(ref.item()) + 1e-7, (k, out[k].item(), ref.item())
@@ -80,7 +96,7 @@ def test_tal_module_api_backward_and_normaliser_override(cuda_device):
     x = preds.to(dev).requires_grad_(True)
     loss, parts = crit(x, [g.to(dev) for g in gts], anchors.to(dev), strides.to(dev))
     loss.backward()
-    ora = T.tal_forward_backward(preds, gts, anchors, strides, 80)
+    ora, _ = oracle_on_gpu_assignment(run_cuda(preds, gts, anchors, strides, 80, dev)[2], preds, gts, anchors, strides, 80)
     assert set(parts) == {"total_loss", "box_loss", "cls_loss", "dfl_loss"}
     assert abs(parts["total_loss"] - ora.total.item()) <= 1e-5 * ora.total.item()
     assert (x.grad.cpu() - ora.grad).abs().max().item() <= 1e-5 * ora.grad.abs().max().item()
@@ -91,10 +107,9 @@ def test_tal_module_api_backward_and_normaliser_override(cuda_device):
     # bf16 head output
     pb = preds.bfloat16()
     out, grad, asg, _, _ = run_cuda(pb, gts, anchors, strides, 80, dev)
-    orb = T.tal_forward_backward(pb, gts, anchors, strides, 80)
-    if int((asg != orb.assigned_gt).sum()) == 0:
-        assert abs(out[0].item() - orb.total.item()) <= 1e-2 * orb.total.item()
-        assert (grad.float() - orb.grad.float()).abs().max().item() <= 1e-2 * orb.grad.float().abs().max().item()
+    orb, _ = oracle_on_gpu_assignment(asg, pb, gts, anchors, strides, 80)
+    assert abs(out[0].item() - orb.total.item()) <= 1e-2 * orb.total.item()
+    assert (grad.float() - orb.grad.float()).abs().max().item() <= 1e-2 * orb.grad.float().abs().max().item()
 
 
 def test_tal_full_size_properties(cuda_device):
@@ -105,8 +120,9 @@ def test_tal_full_size_properties(cuda_device):
     assert torch.equal(out, out2) and torch.equal(grad, grad2) and torch.equal(asg, asg2)       # run-to-run identical
     outh, gradh, asgh, tsch, _ = run_cuda(preds[:8], gts[:8], anchors, strides, 80, cuda_device)
     assert torch.equal(asgh, asg[:8]) and torch.equal(tsch, tsc[:8])                             # images are independent
-    ora = T.tal_forward(preds[:4], gts[:4], anchors, strides, 80)
-    assert int((asg[:4] != ora.assigned_gt).sum()) <= 2
+    ora, n_diff = oracle_on_gpu_assignment(asg[:4], preds[:4], gts[:4], anchors, strides, 80, backward=False)
+    print(f"TAL cfg2-size assignment: {int((asg[:4] >= 0).sum()) - n_diff} of {int((asg[:4] >= 0).sum())} foreground anchors bit-exact")
+    assert torch.allclose(tsc[:4], ora.target_score, rtol=2e-5, atol=1e-7)
     # each anchor has at most one GT; every GT gets at most topk anchors
     for b in range(0, 128, 17):
         a = asg[b]

@@ -57,7 +57,8 @@ def test_metrics_cuda_matches_reference(name, cuda_device):
     rows = torch.from_numpy(z["preds"]).to(dev)
     sc = torch.from_numpy(z["scores"]).to(dev).clone()
     sc[~torch.from_numpy(z["use_scores"]).to(dev)] = 1.0
-    mb.update_batch(rows, torch.from_numpy(z["pred_count"]).to(dev), gt, off, max(counts), sc, 0.3)
+    mb.update_batch(rows, torch.from_numpy(z["pred_count"]).to(dev), gt, off, max(counts), sc, 0.3,
+                    skip_empty_targets=False)               # the golden pins update() on EVERY image
     assert np.array_equal(mb._host().numpy(), _expected(z))
     mb.reset()
     assert mb.true_positives == 0 and mb.compute()["mAP"] == 0.0
@@ -86,12 +87,24 @@ def test_metrics_cuda_matches_oracle_at_validation_size(cuda_device):
             rows[b, 11] = gts[b][-1].to(dev)                  # a duplicate: its target is already consumed -> false positive
     gt, off, counts = pack_gt([g.to(dev) for g in gts], dev)
     mt = DetectionMetrics(nc, 0.5)
-    mt.update_batch(rows, count, gt, off, max(counts))
+    mt.update_batch(rows, count, gt, off, max(counts), skip_empty_targets=False)
     o = MetricsOracle(nc, 0.5)
     rows_h, count_h = rows.cpu(), count.cpu()
     for b in range(n):
         o.update(rows_h[b, : int(count_h[b])], gts[b])
     assert np.array_equal(mt._host().numpy(), o.vector())
     assert mt.true_positives > 0
+    # the reference's validation loop (train_model.py:326-328) skips images without targets: that is the default,
+    # also with a PackedGT straight from the collate function (host memory: moved, not dereferenced)
+    assert any(g.shape[0] == 0 for g in gts)
+    from custom_yolo_implmentation_b200.model.losses import pack_gt_host
+    ml = DetectionMetrics(nc, 0.5)
+    ml.update_batch(rows, count, pack_gt_host(gts))
+    ol = MetricsOracle(nc, 0.5)
+    for b in range(n):
+        if gts[b].numel() > 0:
+            ol.update(rows_h[b, : int(count_h[b])], gts[b])
+    assert np.array_equal(ml._host().numpy(), ol.vector())
+    assert ml.false_positives < mt.false_positives
     avg = compute_average_iou([rows[b, : int(count_h[b]), :4] for b in range(4)], [g[:, :4].to(dev) for g in gts[:4]])
     assert 0.0 <= avg <= 1.0
