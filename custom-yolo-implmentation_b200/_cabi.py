@@ -34,12 +34,9 @@ _SIGNATURES = {
                                 c_void_p, c_size_t, ctypes.c_uint, c_void_p, c_void_p]),
     "yb_tal_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "yb_tal_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                              c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "yb_tal_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                            c_int, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "yb_tal_loss_vfl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                c_int, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
-                                c_size_t, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_tal_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_size_t, c_void_p]),
     "yb_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "yb_loss_fwd_bwd_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -72,6 +69,12 @@ _SIGNATURES = {
     "yb_distribution_focal_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
+
+
+class TalParams(ctypes.Structure):
+    """``yb_tal_params`` of include/yolo_boxpath.h."""
+    _fields_ = [("topk", c_int), ("alpha", c_float), ("beta", c_float), ("lambda_box", c_float), ("lambda_cls", c_float),
+                ("lambda_dfl", c_float), ("vfl", c_int), ("vfl_alpha", c_float), ("vfl_gamma", c_float)]
 
 
 class ExtensionMissing(RuntimeError):

@@ -251,7 +251,7 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
 
     Between the two calls the normaliser ``sum(target scores)`` is all-reduced (SUM / world) when a
     process group is initialised and ``sync_normalizer`` is set — the path's one real exchange step.
-    ``cls_loss="vfl"`` weights the class term varifocally (``yb_tal_loss_vfl``): background cells by
+    ``cls_loss="vfl"`` weights the class term varifocally (``yb_tal_params.vfl``): background cells by
     ``vfl_alpha * sigmoid(x) ** vfl_gamma``, the positive cell of a foreground anchor by its target score.
     Returns ``(out_loss (8,) [total, box, cls, dfl, normaliser, #fg, ..], grad or None, trace)``.
     """
@@ -277,15 +277,19 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
         asg = torch.empty(n, a, dtype=torch.int32, device=dev)
         tsc = torch.empty(n, a, dtype=torch.float32, device=dev)
     gt_ptr = _cabi.ptr(gt) if gt_total else None
+    import ctypes
+    params = _cabi.TalParams(int(topk), float(alpha), float(beta), float(lambda_box), float(lambda_cls), float(lambda_dfl),
+                             int(cls_loss == "vfl"), float(vfl_alpha), float(vfl_gamma))
     with torch.cuda.device(dev):
         rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
-                               _cabi.ptr(gt_offsets), gt_total, int(topk), float(alpha), float(beta), _cabi.ptr(stats),
+                               _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params), _cabi.ptr(stats),
                                _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_tal_assign")
     tss = stats[:1]
     if sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
             and torch.distributed.get_world_size() > 1:
-        # [sum of target scores, #foreground] -> mean over the ranks, in place: one collective, no extra kernels
+        # [sum of target scores, #foreground] -> mean over the ranks, in place: one collective, no extra kernels.
+        # Nothing of the step is left to overlap it with: everything that does not need the normaliser has already run.
         if torch.distributed.get_backend() == "nccl":
             torch.distributed.all_reduce(stats[:2], op=torch.distributed.ReduceOp.AVG)
         else:                                                   # gloo has no AVG
@@ -294,14 +298,9 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
         tss = stats[:1]
     grad = torch.empty_like(x) if want_grad else None
     out = torch.empty(8, dtype=torch.float32, device=dev)
-    head = (_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr, _cabi.ptr(gt_offsets),
-            gt_total, int(topk), _cabi.ptr(tss), float(lambda_box), float(lambda_cls), float(lambda_dfl))
-    tail = (_cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     with torch.cuda.device(dev):
-        if cls_loss == "vfl":
-            rc = lib.yb_tal_loss_vfl(*head, float(vfl_alpha), float(vfl_gamma), *tail)
-        else:
-            rc = lib.yb_tal_loss(*head, *tail)
+        rc = lib.yb_tal_loss(_cabi.ptr(x), dt, n, num_classes, reg_max, a, gt_total, ctypes.byref(params), _cabi.ptr(tss),
+                             _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_tal_loss")
     trace = {"assigned_gt": asg, "target_score": tsc, "stats": stats} if want_trace else {}
     return out, grad, trace

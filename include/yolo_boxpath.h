@@ -114,31 +114,33 @@ int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_images, int nc
  *                     out_assigned_gt (N, A) int32 (-1 background) / out_target_score (N, A) fp32: optional
  *   yb_tal_loss    <- tss_dev: device scalar, the normaliser to use (clamped at 1 inside);
  *                  -> grad_preds (or NULL), out_loss: [0] total [1] box (CIoU) [2] cls (BCE) [3] dfl
- *                     [4] normaliser used [5] #foreground
+ *                     [4] normaliser used [5] #foreground [7] #GT rows with a class id outside [0, nc)
+ *                     (clamped to stay memory-safe; the module raises, as the reference's scatter_ would)
  * The same workspace must be passed to both calls (it carries the assignment).
  * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int topk;                                   /* anchors per GT, 1..16 (public default 10) */
+    float alpha, beta;                          /* metric = sigmoid(cls)^alpha * CIoU^beta (0.5, 6.0) */
+    float lambda_box, lambda_cls, lambda_dfl;   /* loss weights */
+    int vfl;                                    /* 0: plain BCE class term; 1: varifocal weighting (north_star "VFL-BCE"): */
+    float vfl_alpha, vfl_gamma;                 /*    weight = vfl_alpha * sigmoid(x)^vfl_gamma on background cells
+                                                      (differentiated), = the target score on the positive cell */
+} yb_tal_params;                                /* host struct, read during the call; pass the SAME values to both calls */
+
 size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype, int topk);
 
+/* Decode, assignment and everything of the loss that does not need the normaliser (the foreground anchors' CIoU / DFL
+ * terms and box-logit gradients, kept un-normalised in the workspace). */
 int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
                   const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                  int gt_total, int topk, float alpha, float beta, float *out_stats,
+                  int gt_total, const yb_tal_params *params, float *out_stats,
                   int32_t *out_assigned_gt, float *out_target_score,
                   void *workspace, size_t workspace_bytes, void *stream);
 
-int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
-                const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl,
+/* The dense class pass (reads the class logits, writes the whole gradient) and the loss scalars. */
+int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors, int gt_total,
+                const yb_tal_params *params, const float *tss_dev,
                 void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream);
-
-/* yb_tal_loss with the varifocal weighting of the class term (north_star "VFL-BCE"; published VFL,
- * specified in oracle/tal_oracle.py): weight = vfl_alpha * sigmoid(x)^vfl_gamma on background cells
- * (differentiated), = the target score on the positive cell of a foreground anchor;
- * cls = sum(weight * BCE(x, target)) / normaliser.  out_loss[2] is that term. */
-int yb_tal_loss_vfl(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
-                    const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                    int gt_total, int topk, const float *tss_dev, float lambda_box, float lambda_cls, float lambda_dfl,
-                    float vfl_alpha, float vfl_gamma,
-                    void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Decode.  Replaces DFL.forward (src/model/model_blocks.py:278-280), dist2bbox

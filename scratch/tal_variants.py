@@ -20,13 +20,17 @@ def build_all():
         if p.returncode: print('BUILD FAIL', name(v), out.decode()[-600:])
 def run_all():
     import torch
+    from custom_yolo_implmentation_b200 import _cabi
     from custom_yolo_implmentation_b200.model import losses as P
+    from custom_yolo_implmentation_b200.utils import synthetic as syn
     from test_gpu_tal import make_inputs
     dev = torch.device('cuda:0')
     data = {}
-    for cn, (dt, code) in {'fp32': (torch.float32, 0), 'bf16': (torch.bfloat16, 1)}.items():
-        preds, gts, anchors, strides = make_inputs(128, 80, 640, 100, 51)
+    for cn in ('bench', 'spread', 'bf16'):
+        if cn == 'bench': preds, gts, anchors, strides = syn.make_loss_inputs(128, 80, 640, 100, 1236)
+        else: preds, gts, anchors, strides = make_inputs(128, 80, 640, 100, 51)
         gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
+        dt, code = (torch.bfloat16, 1) if cn == 'bf16' else (torch.float32, 0)
         data[cn] = (preds.to(dev, dt), gt, off, anchors.to(dev), strides.to(dev), code)
     for v in VARIANTS:
         so = os.path.join(OUT, f'libtal_{name(v)}.so')
@@ -34,10 +38,11 @@ def run_all():
         lib = ctypes.CDLL(so)
         lib.yb_tal_workspace_bytes.restype = ctypes.c_size_t
         lib.yb_tal_workspace_bytes.argtypes = [ctypes.c_int] * 5
-        Pp, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-        lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, I, F, F, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
-        lib.yb_tal_loss.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, I, Pp, F, F, F, Pp, Pp, Pp, ctypes.c_size_t, Pp]
+        Pp, I = ctypes.c_void_p, ctypes.c_int
+        lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
+        lib.yb_tal_loss.argtypes = [Pp, I, I, I, I, I, I, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
         lib.yb_last_error.restype = ctypes.c_char_p
+        prm = _cabi.TalParams(10, 0.5, 6.0, 1.5, 1.0, 1.5, 0, 0.75, 2.0)
         line = [f'{name(v):24s}']
         for cn, (x, gt, off, a, s, code) in data.items():
             n, c, A = x.shape; G = gt.shape[0]
@@ -45,10 +50,10 @@ def run_all():
             stats = torch.empty(8, device=dev); out = torch.empty(8, device=dev); grad = torch.empty_like(x)
             st = torch.cuda.current_stream().cuda_stream
             def assign():
-                rc = lib.yb_tal_assign(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, 10, 0.5, 6.0, stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st)
+                rc = lib.yb_tal_assign(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, ctypes.byref(prm), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st)
                 assert rc == 0, lib.yb_last_error()
             def loss():
-                rc = lib.yb_tal_loss(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, 10, stats.data_ptr(), 1.5, 1.0, 1.5, grad.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st)
+                rc = lib.yb_tal_loss(x.data_ptr(), code, n, 80, 16, A, G, ctypes.byref(prm), stats.data_ptr(), grad.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st)
                 assert rc == 0, lib.yb_last_error()
             for _ in range(3): assign(); loss()
             torch.cuda.synchronize()

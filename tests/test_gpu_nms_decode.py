@@ -348,4 +348,13 @@ def test_head_tail_rejects_bad_input(cuda_device):
     with pytest.raises(RuntimeError):
         head_tail([torch.zeros(1, 64, 2, 2)], [torch.zeros(1, 3, 2, 2)], [8.0])
     with pytest.raises(TypeError):
-        head_tail([t.half() for t in b], [torch.zeros(1, 3, 2, 2, device=cuda_device).half()], [8.0])
+        head_tail([t.double() for t in b], [torch.zeros(1, 3, 2, 2, device=cuda_device).double()], [8.0])
+    # fp16 (the reference's default autocast dtype, train_model.py:240-246) is a plain 2-byte copy, forward and backward
+    g = torch.Generator().manual_seed(3)
+    bx = torch.randn(2, 64, 3, 5, generator=g).half().to(cuda_device).requires_grad_(True)
+    cx = torch.randn(2, 3, 3, 5, generator=g).half().to(cuda_device).requires_grad_(True)
+    x, anc, st = head_tail([bx], [cx], [8.0])
+    assert x.dtype == torch.float16 and torch.equal(x, torch.cat((bx, cx), 1).view(2, 67, -1))
+    w = torch.randn(x.shape, generator=g).half().to(cuda_device)
+    (x * w).sum().backward()
+    assert torch.equal(bx.grad.view(2, 64, -1), w[:, :64]) and torch.equal(cx.grad.view(2, 3, -1), w[:, 64:])
