@@ -34,7 +34,7 @@ _SIGNATURES = {
                                 c_void_p, c_size_t, ctypes.c_uint, c_void_p, c_void_p]),
     "yb_tal_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "yb_tal_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_tal_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_size_t, c_void_p]),
     "yb_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
@@ -75,6 +75,15 @@ class TalParams(ctypes.Structure):
     """``yb_tal_params`` of include/yolo_boxpath.h."""
     _fields_ = [("topk", c_int), ("alpha", c_float), ("beta", c_float), ("lambda_box", c_float), ("lambda_cls", c_float),
                 ("lambda_dfl", c_float), ("vfl", c_int), ("vfl_alpha", c_float), ("vfl_gamma", c_float)]
+
+
+TAL_MAX_LEVELS = 8
+
+
+class TalGrid(ctypes.Structure):
+    """``yb_tal_grid`` of include/yolo_boxpath.h."""
+    _fields_ = [("n_levels", c_int), ("start", c_int * TAL_MAX_LEVELS), ("w", c_int * TAL_MAX_LEVELS), ("h", c_int * TAL_MAX_LEVELS),
+                ("stride", c_float * TAL_MAX_LEVELS), ("x0", c_float * TAL_MAX_LEVELS), ("y0", c_float * TAL_MAX_LEVELS)]
 
 
 class ExtensionMissing(RuntimeError):

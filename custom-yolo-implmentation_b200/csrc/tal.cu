@@ -8,22 +8,21 @@
 // Two ABI calls so that the normaliser can be exchanged between them (the path's one real exchange step).
 // Everything that does not need the normaliser runs in the FIRST call, so a collective issued between the
 // two has nothing left to hide behind but also nothing left to wait for:
-//   yb_tal_assign   tal_candidates_kernel  per (image, anchor tile): decode the tile into shared memory; the
-//                                          GTs that meet the tile are found by all threads at once and then
-//                                          handed to the warps: group-extent skip + ballot compaction of the
-//                                          anchors whose centre lies inside the GT, alignment metric of the
-//                                          queue (approximate-reciprocal arithmetic: it only RANKS), and
-//                                          either the whole queue (<= 64 entries) or its k best (REDUX
-//                                          rounds) are appended to the GT's candidate list
-//                   tal_select_kernel      one warp per GT: global top-k (metric desc, anchor asc) with the
-//                                          list in registers, 64-bit atomicMax (overlap, ~gt) per anchor
+//   yb_tal_assign   tal_decode_kernel      streaming: reads the 4 x 16 box rows once (128-bit loads) and leaves the
+//                                          decoded pixel box of every anchor in the workspace (16 B per anchor,
+//                                          L2-resident for the next kernel)
+//                   tal_topk_kernel        one warp per GT over the whole image: group-extent skip + ballot
+//                                          compaction of the anchors whose centre lies inside the GT, alignment
+//                                          metric 64 anchors at a time (approximate-reciprocal arithmetic: it only
+//                                          RANKS), running top-k (metric desc, anchor asc) by REDUX rounds with the
+//                                          candidate list in registers, 64-bit atomicMax (overlap, ~gt) per anchor
 //                                          resolves conflicts
 //                   tal_fg_kernel          one half-warp per (GT, selected anchor): did the GT keep the anchor,
 //                                          the GT's max metric / overlap -> target score; CIoU and DFL loss and
 //                                          the gradient of the anchor's 64 box logits (NOT yet divided by the
-//                                          normaliser) into a compact buffer; anchor -> slot map; per-CTA sums of
-//                                          the target scores, added as fixed point; the last CTA writes
-//                                          [sum of target scores, #foreground]
+//                                          normaliser) into a compact buffer; anchor -> slot map; the target scores
+//                                          are summed in fixed point (integer atomics: order-independent)
+//                   tal_stats_kernel       -> [sum of target scores, #foreground] of this rank
 //   yb_tal_loss     tal_cls_kernel         dense BCE-with-logits at target 0 + gradient; writes the box rows of the
 //                                          gradient too: zero, or the foreground anchor's 64 values / normaliser
 //                                          (predicated loads through the anchor -> slot map, no scattered stores)
@@ -31,6 +30,7 @@
 //                                          fixed-order reduction -> loss scalars
 // The anchors x GT overlap / metric matrices never exist.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -38,13 +38,12 @@ namespace yb {
 
 constexpr int kTalThreads = 128;
 constexpr int kTalMaxK = 16;
-constexpr int kTalAppendAll = 64;          // a (GT, tile) queue of at most this many anchors is appended unselected
 constexpr float kEpsCiou = 1e-7f;
 constexpr float kEpsIn = 1e-9f;
 constexpr float kEpsNorm = 1e-9f;
 constexpr float kFourOverPi2 = 0.40528473456935109f;
 constexpr int kTalFinThreadsDecl = 256;
-constexpr int kTalStatAcc = 16;            // sub-accumulators of the target-score sum (spreads same-address atomics)
+constexpr int kTalStatAcc = 64;            // sub-accumulators of the target-score sum / foreground count (spreads same-address atomics)
 constexpr double kTalFix = 4294967296.0;   // 2^32: target scores are summed in fixed point (order-independent, exact)
 // CTAs per anchor tile in the dense pass (each takes 1/SPLIT of the class and box rows): measured best 8 for
 // 512-anchor (fp32) tiles, 4 for 1024-anchor (bf16) tiles; the scalar fall-back (128-anchor tiles) uses 8 too
@@ -52,23 +51,18 @@ __host__ __device__ constexpr int tal_cls_split(int tile) { return tile >= 1024 
 #ifndef YB_TAL_CLS_UNROLL
 #define YB_TAL_CLS_UNROLL 4
 #endif
-#ifndef YB_TAL_CAND_MINBLOCKS
-#define YB_TAL_CAND_MINBLOCKS 8
-#endif
-constexpr int kTalCandMinBlocks = YB_TAL_CAND_MINBLOCKS;
-// shared memory of tal_candidates_kernel: box 16 B + centre 8 B per anchor, 16 B per group of 32 anchors,
-// and per warp a queue of (metric 4 B, anchor 2 B) per anchor
-static size_t tal_cand_smem(int tile) { return (size_t)tile * (16 + 8 + (kTalThreads / 32) * (4 + 2)) + (size_t)(tile / 32) * 16; }
-
 struct TalWorkspace {
-    // zeroed by yb_tal_assign
-    unsigned int *ticket;               // [0] finalize ticket, [1] fg ticket, [2] GT rows with a class id outside [0, nc)
-    unsigned long long *stat_acc;       // [kTalStatAcc + 1] fixed-point sums of the target scores, then #foreground
-    int *cand_count;                    // [gt_total]
+    // zeroed by yb_tal_assign's first kernels (the counters by a memset, the per-anchor arrays by tal_decode_kernel)
+    unsigned int *ticket;               // [0] finalize ticket, [1] next work unit of tal_topk_kernel, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected
+    unsigned long long *stat_acc;       // [kTalStatAcc] fixed-point sums of the target scores, [kTalStatAcc] foreground counts, [1] total #foreground
+    int *gt_done;                       // [gt_total] units of the GT that tal_topk_kernel has finished
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
     int *aslot;                         // [N * A]  1 + (g * topk + r) of the GT slot that owns the anchor (0 = background)
     // plain scratch
-    float4 *cand;                       // [gt_total * cand_cap]  metric, overlap, anchor (as int bits), -
+    float4 *dbox;                       // [N * A]  decoded pixel box (xyxy) of every anchor
+    float4 *gext;                       // [ceil(A / 32)]  extent of the anchor centres of each group of 32 anchors
+    float2 *ctr;                        // [A]  anchor centres in pixels
+    float4 *psel;                       // [gt_total * kTopkSplit * kTalMaxK]  per-unit partial lists (same fields as sel)
     float4 *sel;                        // [gt_total * kTalMaxK]  anchor bits, metric, overlap, -
     int *sel_count;                     // [gt_total]
     float *fg_box, *fg_dfl, *fg_cls;    // [gt_total * kTalMaxK] per-foreground loss terms (not yet divided by the normaliser)
@@ -77,8 +71,8 @@ struct TalWorkspace {
     float *fcell_val;                   // [gt_total * kTalMaxK] its gradient (ditto)
     float *part;                        // [N * cls_tiles]
     double *cta_sums;                   // [4 * finalize CTAs]
-    int cand_cap, cls_tiles;
-    size_t zero_bytes, total_bytes;
+    int cls_tiles;
+    size_t small_zero_bytes, zero_bytes, total_bytes;
 };
 
 static int tal_tile(int dtype, bool vec) { return kTalThreads * (vec ? (dtype == YB_BF16 ? 8 : 4) : 1); }
@@ -92,18 +86,25 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     w.ticket = reinterpret_cast<unsigned int *>(p + off);
     off += 64;
     w.stat_acc = reinterpret_cast<unsigned long long *>(p + off);
-    off += round_up(sizeof(unsigned long long) * (kTalStatAcc + 1), 64);
-    w.cand_count = reinterpret_cast<int *>(p + off);
+    off += round_up(sizeof(unsigned long long) * (2 * kTalStatAcc + 1), 64);
+    w.gt_done = reinterpret_cast<int *>(p + off);
     off += round_up(sizeof(int) * g, 64);
+    w.small_zero_bytes = off;
     w.akey = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)n_images * n_anchors, 64);
     w.aslot = reinterpret_cast<int *>(p + off);
     off += round_up(sizeof(int) * (size_t)n_images * n_anchors, 64);
     w.zero_bytes = off;
-    w.cand_cap = std::max(topk, std::min(tile, kTalAppendAll)) * tiles;   // what one tile can append, times the tiles
+    (void)topk;
     w.cls_tiles = tiles * tal_cls_split(tile);             // partial sums per image
-    w.cand = reinterpret_cast<float4 *>(p + off);
-    off += round_up(sizeof(float4) * g * (size_t)w.cand_cap, 64);
+    w.dbox = reinterpret_cast<float4 *>(p + off);
+    off += round_up(sizeof(float4) * (size_t)n_images * n_anchors, 64);
+    w.gext = reinterpret_cast<float4 *>(p + off);
+    off += round_up(sizeof(float4) * (size_t)((n_anchors + 31) / 32), 64);
+    w.ctr = reinterpret_cast<float2 *>(p + off);
+    off += round_up(sizeof(float2) * (size_t)n_anchors, 64);
+    w.psel = reinterpret_cast<float4 *>(p + off);
+    off += round_up(sizeof(float4) * g * kTalMaxK * 8, 64);           // 8 >= kTopkSplit
     w.sel = reinterpret_cast<float4 *>(p + off);
     off += round_up(sizeof(float4) * g * kTalMaxK, 64);
     w.sel_count = reinterpret_cast<int *>(p + off);
@@ -209,227 +210,113 @@ __device__ __forceinline__ float metric_fast(float logit, float ov, float alpha,
 }
 
 // ------------------------------------------------------------------------------------------
-// tal_candidates_kernel
+// Grid hint.  Do the anchors form the reference's pyramid of regular grids (src/utils/model_utils.py:60-70: per level
+// x fastest, x = x0 + col, y = y0 + row, one stride per level)?  Anchors are an INPUT of the loss (they may be
+// bf16-rounded, SURVEY Q13, or anything else), so nothing is assumed: the caller may pass the structure it believes in
+// (yb_tal_grid, a host struct handed to the kernels by value), and tal_decode_kernel VERIFIES it against the anchor /
+// stride arrays element by element, bit for bit, every call.  When it holds, tal_topk_kernel enumerates the anchors
+// inside a GT as one rectangle of cells per level instead of scanning groups of anchors; when it does not (or no hint
+// is given) the generic scan runs and out_stats[2] reports the rejection.
+// ------------------------------------------------------------------------------------------
+typedef yb_tal_grid TalGrid;
+constexpr int kGridMaxLevels = YB_TAL_MAX_LEVELS;
+
+__device__ __forceinline__ bool grid_matches(const TalGrid &gr, int a, float ax, float ay, float s) {
+    int l = 0;
+    while (l + 1 < gr.n_levels && a >= gr.start[l + 1]) ++l;
+    const int j = a - gr.start[l], row = j / gr.w[l], col = j - row * gr.w[l];
+    return row < gr.h[l] && ax == gr.x0[l] + (float)col && ay == gr.y0[l] + (float)row && s == gr.stride[l];
+}
+
+// ------------------------------------------------------------------------------------------
+// tal_decode_kernel: the streaming half of the assignment.  One thread per VW consecutive anchors reads the
+// 4 x 16 box rows (128-bit loads, 8 rows in flight), and leaves the decoded pixel box of every anchor in the
+// workspace (16 B per anchor: 17 MB at cfg2, it stays in L2 for tal_topk_kernel).  The CTAs of image 0 also
+// write the anchor CENTRES in pixels and their extent per group of 32 consecutive anchors (the same for all images).
 // ------------------------------------------------------------------------------------------
 template <typename T, int VW>
-__global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : kTalCandMinBlocks)   // bf16 tiles: 4 CTAs of shared memory per SM
-tal_candidates_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
-                      const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
-                      int topk, float alpha, float beta, int *__restrict__ cand_count, float4 *__restrict__ cand,
-                      int cand_cap) {
-    constexpr int TILE = kTalThreads * VW;
-    constexpr int NW = kTalThreads / 32;
-    constexpr int NG = TILE / 32;                          // groups of 32 consecutive anchors (<= 32)
-    constexpr int GL = 32 / VW;                            // lanes that share one group
-    constexpr int NE = VW == 8 ? 8 : 4;                    // queue entries per lane the register top-k holds
-    // dynamic shared memory: 24 B per anchor of the tile + 6 B per anchor and warp (see tal_cand_smem)
-    extern __shared__ __align__(16) unsigned char tal_smem[];
-    float4 *s_box = reinterpret_cast<float4 *>(tal_smem);                         // decoded xyxy (pixels)
-    float2 *s_ctr = reinterpret_cast<float2 *>(s_box + TILE);                     // anchor centres (pixels)
-    float4 *s_grp = reinterpret_cast<float4 *>(s_ctr + TILE);                     // centre extent of each group
-    float (*s_qm)[TILE] = reinterpret_cast<float (*)[TILE]>(s_grp + NG);          // per-warp queue: metric
-    unsigned short (*s_q)[TILE] = reinterpret_cast<unsigned short (*)[TILE]>(&s_qm[NW][0]);   //     anchor
-    __shared__ float s_bb[4][NW];                        // tile extent of the anchor centres
-    __shared__ int s_list[kTalThreads];                  // GTs of the current chunk that meet the tile
-    __shared__ int s_cnt[NW];
-    __shared__ int s_next;
-
-    // Launch order: image fastest, LAST tile first.  The coarse levels sit at the end of the anchor axis and meet
-    // nearly every GT of their image, so their CTAs are the long ones: they go out first and the grid drains on short ones.
-    const int n = blockIdx.x;
-    const int tile0 = ((int)gridDim.y - 1 - (int)blockIdx.y) * TILE;
-    const int a0 = tile0 + threadIdx.x * VW;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : 6)
+tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
+                  const float *__restrict__ strides, const int *__restrict__ gt_off, float4 *__restrict__ dbox,
+                  float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,
+                  int *__restrict__ aslot, const TalGrid grid, unsigned int *__restrict__ grid_rejected) {
+    constexpr int GL = 32 / VW;                            // lanes that share one group of 32 anchors
+    const int n = blockIdx.y;
+    const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
+    // arm the per-anchor conflict keys and the anchor -> slot map of this thread's anchors (all images: the dense
+    // pass reads the map everywhere)
+#pragma unroll
+    for (int v = 0; v < VW; ++v)
+        if (a0 + v < n_anchors) { akey[(size_t)n * n_anchors + a0 + v] = 0ull; aslot[(size_t)n * n_anchors + a0 + v] = 0; }
+    const bool want_ext = n == 0;                          // uniform per CTA
+    if (gt_off[n + 1] == gt_off[n] && !want_ext) return;   // an image without GT has no candidates (uniform per CTA)
+    const bool have_gt = gt_off[n + 1] != gt_off[n];
     const size_t img = (size_t)n * n_ch * n_anchors;
-    const int g_begin = gt_off[n];
-    const int m_img = gt_off[n + 1] - g_begin;
-    if (m_img == 0) return;                               // uniform per CTA
-
     float lo_x = __int_as_float(0x7f800000), lo_y = lo_x, hi_x = -lo_x, hi_y = -lo_x;
     if (a0 < n_anchors) {
         float dist[4][VW];
+        if (have_gt) {
 #pragma unroll
-        for (int side = 0; side < 4; ++side) {
-            DflPartial part[VW];
+            for (int side = 0; side < 4; ++side) {
+                DflPartial part[VW];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                Group<T, VW> row[8];
+                for (int h = 0; h < 2; ++h) {
+                    Group<T, VW> row[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) row[j].load(preds + img + (size_t)(side * kRegMax + h * 8 + j) * n_anchors + a0);
+                    for (int j = 0; j < 8; ++j) row[j].load(preds + img + (size_t)(side * kRegMax + h * 8 + j) * n_anchors + a0);
 #pragma unroll
-                for (int v = 0; v < VW; ++v) {
-                    float x[8];
+                    for (int v = 0; v < VW; ++v) {
+                        float x[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
-                    const DflPartial ph = dfl_half8(x, h * 8);
-                    if (h == 0) part[v] = ph;
-                    else dist[side][v] = dfl_merge(part[v], ph);
+                        for (int j = 0; j < 8; ++j) x[j] = row[j].get(v);
+                        const DflPartial ph = dfl_half8(x, h * 8);
+                        if (h == 0) part[v] = ph;
+                        else dist[side][v] = dfl_merge(part[v], ph);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int v = 0; v < VW; ++v) {
             const float ax = __ldg(anchors + a0 + v), ay = __ldg(anchors + n_anchors + a0 + v), s = __ldg(strides + a0 + v);
-            const PredBox b = decode_box(ax, ay, s, dist[0][v], dist[1][v], dist[2][v], dist[3][v]);
-            s_box[threadIdx.x * VW + v] = make_float4(b.x1, b.y1, b.x2, b.y2);
+            if (have_gt) {
+                const PredBox b = decode_box(ax, ay, s, dist[0][v], dist[1][v], dist[2][v], dist[3][v]);
+                dbox[(size_t)n * n_anchors + a0 + v] = make_float4(b.x1, b.y1, b.x2, b.y2);
+            }
             const float cx = ax * s, cy = ay * s;
-            s_ctr[threadIdx.x * VW + v] = make_float2(cx, cy);
+            if (want_ext) {
+                ctr[a0 + v] = make_float2(cx, cy);
+                if (grid.n_levels > 0 && !grid_matches(grid, a0 + v, ax, ay, s)) atomicOr(grid_rejected, 1u);
+            }
             lo_x = fminf(lo_x, cx); hi_x = fmaxf(hi_x, cx);
             lo_y = fminf(lo_y, cy); hi_y = fmaxf(hi_y, cy);
         }
     }
+    if (want_ext) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        if (o == GL && (lane & (GL - 1)) == 0)             // extent of this lane's group of 32 anchors
-            s_grp[(threadIdx.x * VW) >> 5] = make_float4(lo_x, lo_y, hi_x, hi_y);
-        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
-        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
-        hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
-        hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
-    }
-    if (GL == 32 && lane == 0) s_grp[warp] = make_float4(lo_x, lo_y, hi_x, hi_y);
-    if (lane == 0) { s_bb[0][warp] = lo_x; s_bb[1][warp] = lo_y; s_bb[2][warp] = hi_x; s_bb[3][warp] = hi_y; }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        lo_x = fminf(lo_x, s_bb[0][w]); lo_y = fminf(lo_y, s_bb[1][w]);
-        hi_x = fmaxf(hi_x, s_bb[2][w]); hi_y = fmaxf(hi_y, s_bb[3][w]);
-    }
-    const int tile_n = min(TILE, n_anchors - tile0);
-    float4 my_grp = make_float4(0.f, 0.f, -1.f, -1.f);    // an empty extent never intersects
-    if (lane < NG) my_grp = s_grp[lane];
-    const int n_cls = n_ch - 4 * kRegMax;
-
-    // GTs are tested against the tile's centre extent 128 at a time, one GT per thread; the hits are compacted into
-    // s_list and handed to the warps from a shared counter (a GT that meets the tile costs a warp a lot, one that
-    // misses it costs one thread a few compares)
-    for (int g0 = 0; g0 < m_img; g0 += kTalThreads) {
-        const int gi = g0 + threadIdx.x;
-        bool hit = false;
-        if (gi < m_img) {
-            const float *g5 = gt + (size_t)(g_begin + gi) * 5;
-            const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), hw = __ldg(g5 + 2) * 0.5f, hh = __ldg(g5 + 3) * 0.5f;
-            hit = gcx - hw < hi_x && gcx + hw > lo_x && gcy - hh < hi_y && gcy + hh > lo_y;
+        for (int o = 1; o < GL; o <<= 1) {
+            lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
+            lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+            hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+            hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
         }
-        const unsigned hit_mask = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_cnt[warp] = __popc(hit_mask);
-        if (threadIdx.x == 0) s_next = 0;
-        __syncthreads();
-        int before = 0, n_hit = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            before += w < warp ? s_cnt[w] : 0;
-            n_hit += s_cnt[w];
-        }
-        if (hit) s_list[before + __popc(hit_mask & ((1u << lane) - 1u))] = gi;
-        __syncthreads();
-        for (;;) {
-            int li = 0;
-            if (lane == 0) li = atomicAdd(&s_next, 1);
-            li = __shfl_sync(0xffffffffu, li, 0);
-            if (li >= n_hit) break;
-            const int g = s_list[li];
-            const float *g5 = gt + (size_t)(g_begin + g) * 5;
-            const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
-            const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
-            // 1. queue the anchors whose centre is strictly inside the GT (ascending anchor order); only the
-            //    groups of 32 anchors whose centre extent meets the GT are looked at
-            unsigned groups = __ballot_sync(0xffffffffu, gb.x < my_grp.z && gb.z > my_grp.x && gb.y < my_grp.w && gb.w > my_grp.y);
-            int nq = 0;
-            while (groups) {
-                const int a = ((__ffs(groups) - 1) << 5) + lane;
-                groups &= groups - 1;
-                bool in = false;
-                if (a < tile_n) {
-                    const float2 c = s_ctr[a];
-                    in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, in);
-                if (in) s_q[warp][nq + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)a;
-                nq += __popc(mask);
-            }
-            if (nq == 0) continue;
-            const int cls = min(max((int)__ldg(g5 + 4), 0), n_cls - 1);
-            const float at_g = gt_atan_fast(gb);
-            const float area_g = (gb.z - gb.x) * (gb.w - gb.y + kEpsCiou);
-            const T *cls_row = preds + img + (size_t)(4 * kRegMax + cls) * n_anchors + tile0;
-            __syncwarp();
-            float4 *out = cand + (size_t)(g_begin + g) * cand_cap;
-            if (nq <= kTalAppendAll || nq <= topk) {
-                // 2a. a short queue goes to the GT's list as it is: tal_select_kernel ranks the whole list anyway
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(cand_count + g_begin + g, nq);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                for (int q = lane; q < nq; q += 32) {
-                    const int a = s_q[warp][q];
-                    const float ov = overlap_fast(s_box[a], gb, at_g, area_g);
-                    const float m = metric_fast(load_as_float(cls_row + a), ov, alpha, beta);
-                    if (slot + q < cand_cap) out[slot + q] = make_float4(m, ov, __int_as_float(tile0 + a), 0.f);
-                }
-                __syncwarp();                                     // the queue is reused by the warp's next GT
-                continue;
-            }
-            // 2b. a long queue: its metrics ...
-            for (int q = lane; q < nq; q += 32) {
-                const int a = s_q[warp][q];
-                const float ov = overlap_fast(s_box[a], gb, at_g, area_g);
-                s_qm[warp][q] = metric_fast(load_as_float(cls_row + a), ov, alpha, beta);
-            }
-            __syncwarp();
-            // 3. ... and the tile's k best (metric descending, ties -> lowest anchor = lowest queue position).
-            //    Metrics are >= 0, so their bit patterns order like signed integers; lane r ends up holding the
-            //    r-th best (queue position, metric) and re-evaluates its overlap once, all lanes in parallel.
-            const int n_sel = topk;
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(cand_count + g_begin + g, n_sel);
-            int my_q = lane, my_m = 0;
-            if (nq <= 32 * NE) {
-                // the usual case: the lane keeps its (at most NE) queue entries q = lane + 32 i in registers
-                int v[NE];
-#pragma unroll
-                for (int i = 0; i < NE; ++i) v[i] = lane + 32 * i < nq ? __float_as_int(s_qm[warp][lane + 32 * i]) : (int)0x80000000;
-                for (int r = 0; r < n_sel; ++r) {
-                    int bm = v[0], bi = 0;                     // strict: the lowest q of the lane wins its ties
-#pragma unroll
-                    for (int i = 1; i < NE; ++i)
-                        if (v[i] > bm) { bm = v[i]; bi = i; }
-                    const int wm = __reduce_max_sync(0xffffffffu, bm);
-                    const int wq = __reduce_min_sync(0xffffffffu, bm == wm ? lane + 32 * bi : 0x7fffffff);
-                    if (lane == r) { my_q = wq; my_m = wm; }
-                    if (lane == (wq & 31)) {
-#pragma unroll
-                        for (int i = 0; i < NE; ++i)
-                            if (i == (wq >> 5)) v[i] = (int)0x80000000;          // taken
-                    }
-                }
-            } else {
-                for (int r = 0; r < n_sel; ++r) {
-                    int bm = -1, bq = 0x7fffffff;
-                    for (int q = lane; q < nq; q += 32) {
-                        const int m = __float_as_int(s_qm[warp][q]);
-                        if (m > bm) { bm = m; bq = q; }               // strict: first (lowest q) maximum per lane
-                    }
-                    const int wm = __reduce_max_sync(0xffffffffu, bm);
-                    const int wq = __reduce_min_sync(0xffffffffu, bm == wm ? bq : 0x7fffffff);
-                    if (lane == r) { my_q = wq; my_m = wm; }
-                    if (lane == (wq & 31)) s_qm[warp][wq] = -2.f;     // taken (negative as an integer too)
-                    __syncwarp();
-                }
-            }
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (lane < n_sel && slot + lane < cand_cap) {
-                const int a = s_q[warp][my_q];
-                const float ov = overlap_fast(s_box[a], gb, at_g, area_g);
-                out[slot + lane] = make_float4(__int_as_float(my_m), ov, __int_as_float(tile0 + a), 0.f);
-            }
-            __syncwarp();                                             // the queue is reused by the warp's next GT
-        }
-        __syncthreads();                                              // s_list / s_next are rewritten by the next chunk
+        if ((threadIdx.x & (GL - 1)) == 0 && a0 < n_anchors) gext[a0 >> 5] = make_float4(lo_x, lo_y, hi_x, hi_y);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// tal_select_kernel: one warp per GT, global top-k of its candidates
+// tal_topk_kernel: the latency-bound half of the assignment.  A GT's candidates are the anchors whose centre lies
+// strictly inside it; they are found through the per-group centre extents and ranked by the alignment metric.
+// Work unit = (GT, j): the groups of 32 anchors with index = j (mod kTopkSplit) — an even split whatever the GT's
+// shape, and short units: the kernel's tail is one unit, not one GT.  Units are handed out to WARPS from a global
+// counter (no wave quantisation, no idle warps inside a CTA).  Per unit, in ascending anchor order: group-extent test
+// (32 groups per ballot), ballot compaction of the inside anchors into a small queue, evaluation 64 at a time
+// (decoded boxes from L2, class logit from HBM; approximate-reciprocal arithmetic: the metric only RANKS), and a
+// running top-k in registers, lane r holding the r-th best (metric desc, anchor asc): entries that beat the current
+// k-th best are merged in, a few by insertion (ballot + shuffle-up), many at once by REDUX rounds.  Within a unit a
+// later entry that only TIES the k-th best can never displace it (ties -> lowest anchor), so the strict test is exact.
+// The last unit of a GT to finish (per-GT ticket) merges the kTopkSplit partial lists and publishes the GT's k anchors;
+// conflicts: 64-bit atomicMax (overlap, ~gt) per anchor.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_images, int g) {
     int lo = 0, hi = n_images;
@@ -440,83 +327,260 @@ __device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_im
     return lo;
 }
 
-constexpr int kSelNE = 12;                                  // list entries a lane keeps in registers: lists up to 384
+#ifndef YB_TOPK_SPLIT
+#define YB_TOPK_SPLIT 1
+#endif
+constexpr int kTopkSplit = YB_TOPK_SPLIT;        // units per GT (power of two, <= 8)
+constexpr int kTopkWarps = 4;
+constexpr int kTopkQueue = 96;                   // inside-anchor queue per warp: evaluated 64 at a time
+constexpr int kEmptyKey = (int)0x80000000;       // below every metric bit pattern (metrics are >= 0)
 
-__global__ void __launch_bounds__(128)
-tal_select_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total, int topk,
-                  const int *__restrict__ cand_count, float4 *__restrict__ cand, int cand_cap,
-                  float4 *__restrict__ sel, int *__restrict__ sel_count, unsigned long long *__restrict__ akey,
-                  const float *__restrict__ gt, int n_classes, unsigned int *__restrict__ bad_cls) {
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (g >= gt_total) return;
-    if (lane == 0) {                                       // class ids outside [0, nc) are clamped by the kernels and counted here
-        const int c = (int)__ldg(gt + (size_t)g * 5 + 4);
-        if (c < 0 || c >= n_classes) atomicAdd(bad_cls, 1u);
+struct TopK {                                    // lane r: the r-th best so far (r < topk), or empty
+    int m, a;
+    float o;
+};
+
+// one candidate (the same values in all lanes) into the sorted winners
+__device__ __forceinline__ void topk_insert(TopK &w, int lane, int topk, int m, int a, float o) {
+    const int p = __popc(__ballot_sync(0xffffffffu, lane < topk && w.m >= m));   // winners that stay ahead (ties: earlier anchor)
+    const int um = __shfl_up_sync(0xffffffffu, w.m, 1), ua = __shfl_up_sync(0xffffffffu, w.a, 1);
+    const float uo = __shfl_up_sync(0xffffffffu, w.o, 1);
+    if (lane > p) { w.m = um; w.a = ua; w.o = uo; }
+    if (lane == p) { w.m = m; w.a = a; w.o = o; }
+}
+
+// the k best of NE entries per lane (metric bits, anchor, overlap; kEmptyKey = none), by REDUX rounds: lane r <- r-th best
+template <int NE>
+__device__ __forceinline__ TopK topk_select(int (&vm)[NE], const int (&va)[NE], const float (&vo)[NE], int lane, int topk) {
+    TopK nw = {kEmptyKey, 0x7fffffff, 0.f};
+    for (int r = 0; r < topk; ++r) {
+        int bm = vm[0], ba = va[0], bi = 0;
+#pragma unroll
+        for (int i = 1; i < NE; ++i)
+            if (vm[i] > bm || (vm[i] == bm && va[i] < ba)) { bm = vm[i]; ba = va[i]; bi = i; }
+        const int wm = __reduce_max_sync(0xffffffffu, bm);
+        if (wm == kEmptyKey) break;                        // fewer than k entries in all (warp-uniform)
+        const int wa = __reduce_min_sync(0xffffffffu, bm == wm ? ba : 0x7fffffff);
+        const bool mine = bm == wm && ba == wa;            // exactly one lane: an anchor appears once
+        const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+        float bo = vo[0];
+#pragma unroll
+        for (int i = 1; i < NE; ++i) bo = i == bi ? vo[i] : bo;
+        const float wo = __shfl_sync(0xffffffffu, bo, src);
+        if (mine) {
+#pragma unroll
+            for (int i = 0; i < NE; ++i) vm[i] = i == bi ? kEmptyKey : vm[i];
+        }
+        if (lane == r) { nw.m = wm; nw.a = wa; nw.o = wo; }
     }
-    const int n = gt_image(gt_off, n_images, g);
-    const int g_local = g - __ldg(gt_off + n);
-    const int nc = min(cand_count[g], cand_cap);
-    float4 *c = cand + (size_t)g * cand_cap;
-    const int n_sel = min(nc, topk);
-    auto publish = [&](int r, int wa, float wm, float wo) {            // lane 0
-        sel[(size_t)g * kTalMaxK + r] = make_float4(__int_as_float(wa), wm, wo, 0.f);
-        // conflict resolution: the anchor goes to the GT with the largest overlap, ties -> lowest GT
-        atomicMax(akey + (size_t)n * n_anchors + wa,
-                  ((unsigned long long)__float_as_uint(wo) << 32) | (unsigned int)(~(unsigned int)g_local));
-    };
-    if (nc <= 32 * kSelNE) {
-        // the list in registers: (metric bits, anchor) of entries q = lane + 32 i; metrics are >= 0, so their bit
-        // patterns order like signed integers; ties -> lowest anchor
-        int vm[kSelNE], va[kSelNE];
+    return nw;
+}
+
+#ifndef YB_TOPK_MINBLOCKS
+#define YB_TOPK_MINBLOCKS 8
+#endif
+template <typename T>
+__global__ void __launch_bounds__(32 * kTopkWarps, YB_TOPK_MINBLOCKS)
+tal_topk_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, const float *__restrict__ gt,
+                const int *__restrict__ gt_off, int gt_total, int topk, float alpha, float beta,
+                const float4 *__restrict__ dbox, const float4 *__restrict__ gext, const float2 *__restrict__ ctr,
+                const TalGrid grid, const unsigned int *__restrict__ grid_rejected, float4 *__restrict__ psel, int *__restrict__ gt_done, float4 *__restrict__ sel,
+                int *__restrict__ sel_count, unsigned long long *__restrict__ akey, unsigned int *__restrict__ next_unit,
+                unsigned int *__restrict__ bad_cls) {
+    __shared__ int s_aq[kTopkWarps][kTopkQueue];           // queue of inside anchors
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *aq = s_aq[warp];
+    const int n_cls = n_ch - 4 * kRegMax;
+    const int n_groups = (n_anchors + 31) >> 5;
+    const int n_units = gt_total * kTopkSplit;
+    const int n_levels = grid.n_levels;
+    const bool regular = n_levels > 0 && __ldg(grid_rejected) == 0u;   // uniform over the launch
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = (int)atomicAdd(next_unit, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const int g = unit / kTopkSplit, part = unit - g * kTopkSplit;
+        const int n = gt_image(gt_off, n_images, g);
+        const int g_local = g - __ldg(gt_off + n);
+        const float *g5 = gt + (size_t)g * 5;
+        const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
+        const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
+        const int cls_raw = (int)__ldg(g5 + 4);
+        const int cls = min(max(cls_raw, 0), n_cls - 1);
+        if (lane == 0 && part == 0 && cls_raw != cls) atomicAdd(bad_cls, 1u);   // clamped (memory-safe), counted: the caller raises
+        const float at_g = gt_atan_fast(gb);
+        const float area_g = (gb.z - gb.x) * (gb.w - gb.y + kEpsCiou);
+        const T *cls_row = preds + ((size_t)n * n_ch + 4 * kRegMax + cls) * n_anchors;
+        const float4 *box_row = dbox + (size_t)n * n_anchors;
+
+        TopK win = {kEmptyKey, 0x7fffffff, 0.f};
+        int thr = -1;                                      // bit pattern of the k-th best metric once k winners exist
+        int nq = 0;                                        // queue fill (warp-uniform)
+
+        // evaluate up to 64 anchors, two per lane (a < 0: none), in ascending order lane-major within each of the two
+        auto evaluate2 = [&](const int (&a)[2]) {
+            float4 pb[2];
+            float lg[2];
 #pragma unroll
-        for (int i = 0; i < kSelNE; ++i) {
-            vm[i] = (int)0x80000000; va[i] = 0x7fffffff;
-            if (lane + 32 * i < nc) {
-                const float4 e = c[lane + 32 * i];
-                vm[i] = __float_as_int(e.x); va[i] = __float_as_int(e.z);
+            for (int u = 0; u < 2; ++u)                    // all four loads in flight together
+                if (a[u] >= 0) { pb[u] = box_row[a[u]]; lg[u] = load_as_float(cls_row + a[u]); }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float ov = 0.f;
+                int m = kEmptyKey;
+                if (a[u] >= 0) {
+                    ov = overlap_fast(pb[u], gb, at_g, area_g);
+                    m = __float_as_int(metric_fast(lg[u], ov, alpha, beta));
+                }
+                unsigned keep = __ballot_sync(0xffffffffu, m > thr);
+                if (keep == 0u) continue;                  // warp-uniform
+                if (__popc(keep) > 6) {
+                    int vm[2] = {lane < topk ? win.m : kEmptyKey, ((keep >> lane) & 1u) ? m : kEmptyKey};
+                    const int va[2] = {win.a, a[u]};
+                    const float vo[2] = {win.o, ov};
+                    win = topk_select<2>(vm, va, vo, lane, topk);
+                    const int kth = __shfl_sync(0xffffffffu, win.m, topk - 1);
+                    thr = kth == kEmptyKey ? -1 : kth;
+                } else {
+                    while (keep) {                         // ascending lane = ascending anchor
+                        const int src = __ffs(keep) - 1;
+                        keep &= keep - 1;
+                        const int sm = __shfl_sync(0xffffffffu, m, src);
+                        const int sa = __shfl_sync(0xffffffffu, a[u], src);
+                        const float so = __shfl_sync(0xffffffffu, ov, src);
+                        if (sm > thr) {                    // thr may have risen since the ballot (warp-uniform)
+                            topk_insert(win, lane, topk, sm, sa, so);
+                            const int kth = __shfl_sync(0xffffffffu, win.m, topk - 1);
+                            thr = kth == kEmptyKey ? -1 : kth;
+                        }
+                    }
+                }
+            }
+        };
+        // `cnt` (<= 64) queue entries: lane handles entries lane and 32 + lane
+        auto evaluate = [&](int cnt) {
+            const int a[2] = {lane < cnt ? aq[lane] : -1, lane + 32 < cnt ? aq[lane + 32] : -1};
+            evaluate2(a);
+        };
+
+        if (regular) {
+            // ---- the anchors form regular grids: the inside anchors of a level are a rectangle of cells --------
+            int batch = 0;                                 // batches of 64 cells are dealt round-robin to the GT's units
+            for (int l = 0; l < n_levels; ++l) {
+                const int W = grid.w[l], H = grid.h[l], st = grid.start[l];
+                const float s = grid.stride[l], x0 = grid.x0[l], y0 = grid.y0[l];
+                // first / last column and row whose centre is strictly inside: a guess from the division, made exact
+                // with the very comparison the generic path applies to the stored centres ((x0 + col) * s is the
+                // stored value bit for bit: tal_decode_kernel verified that)
+                auto first_in = [&](float lo, float c0, int n) {
+                    int i = min(max((int)floorf(lo / s - c0), 0), n);
+                    while (i > 0 && (c0 + (float)(i - 1)) * s - lo > kEpsIn) --i;
+                    while (i < n && !((c0 + (float)i) * s - lo > kEpsIn)) ++i;
+                    return i;
+                };
+                auto last_in = [&](float hi, float c0, int n) {
+                    int i = min(max((int)ceilf(hi / s - c0), -1), n - 1);
+                    while (i < n - 1 && hi - (c0 + (float)(i + 1)) * s > kEpsIn) ++i;
+                    while (i >= 0 && !(hi - (c0 + (float)i) * s > kEpsIn)) --i;
+                    return i;
+                };
+                const int ix0 = first_in(gb.x, x0, W), ix1 = last_in(gb.z, x0, W);
+                const int iy0 = first_in(gb.y, y0, H), iy1 = last_in(gb.w, y0, H);
+                const int nx = ix1 - ix0 + 1, ny = iy1 - iy0 + 1;
+                if (nx <= 0 || ny <= 0) continue;          // uniform
+                const int cells = nx * ny;
+                const float inv_nx = 1.f / (float)nx;
+                for (int c0 = 0; c0 < cells; c0 += 64, ++batch) {
+                    if (kTopkSplit > 1 && (batch & (kTopkSplit - 1)) != part) continue;
+                    int a[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = c0 + 32 * u + lane;
+                        int row = (int)(((float)c + 0.5f) * inv_nx), col = c - row * nx;
+                        if (col < 0) { --row; col += nx; } else if (col >= nx) { ++row; col -= nx; }
+                        a[u] = c < cells ? st + (iy0 + row) * W + ix0 + col : -1;
+                    }
+                    evaluate2(a);
+                }
+            }
+        } else {
+
+        // lane l of round i looks at group (i * 32 + l) * kTopkSplit + part
+        for (int gb0 = part; gb0 < n_groups; gb0 += 32 * kTopkSplit) {
+            const int my_group = gb0 + lane * kTopkSplit;
+            float4 ext = make_float4(0.f, 0.f, -1.f, -1.f);   // an empty extent never intersects
+            if (my_group < n_groups) ext = __ldg(gext + my_group);
+            unsigned groups = __ballot_sync(0xffffffffu, gb.x < ext.z && gb.z > ext.x && gb.y < ext.w && gb.w > ext.y);
+            while (groups) {
+                const int a = ((gb0 + (__ffs(groups) - 1) * kTopkSplit) << 5) + lane;
+                groups &= groups - 1;
+                bool in = false;
+                if (a < n_anchors) {
+                    const float2 c = __ldg(ctr + a);
+                    in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, in);
+                if (in) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a;
+                nq += __popc(mask);
+                __syncwarp();
+                if (nq >= 64) {                            // warp-uniform
+                    evaluate(64);
+                    const int rest = nq - 64;              // < 32
+                    const int keep_a = lane < rest ? aq[64 + lane] : 0;
+                    __syncwarp();
+                    if (lane < rest) aq[lane] = keep_a;
+                    nq = rest;
+                    __syncwarp();
+                }
             }
         }
-        for (int r = 0; r < n_sel; ++r) {
-            int bm = vm[0], ba = va[0], bi = 0;
-#pragma unroll
-            for (int i = 1; i < kSelNE; ++i)
-                if (vm[i] > bm || (vm[i] == bm && va[i] < ba)) { bm = vm[i]; ba = va[i]; bi = i; }
-            const int wm = __reduce_max_sync(0xffffffffu, bm);
-            const int wa = __reduce_min_sync(0xffffffffu, bm == wm ? ba : 0x7fffffff);
-            const bool mine = bm == wm && ba == wa;        // exactly one lane: an anchor is in a GT's list once
-            const int wl = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-            float wo = 0.f;
-            if (mine) {
-                wo = c[lane + 32 * bi].y;
-#pragma unroll
-                for (int i = 0; i < kSelNE; ++i)
-                    if (i == bi) vm[i] = (int)0x80000000;  // taken
-            }
-            wo = __shfl_sync(0xffffffffu, wo, wl);
-            if (lane == 0) publish(r, wa, __int_as_float(wm), wo);
+        if (nq > 0) evaluate(nq);
+        __syncwarp();                                      // the queue is reused by the warp's next unit
         }
-    } else {
-        // long list: scanned in global memory, a selected entry gets metric -2
-        for (int r = 0; r < n_sel; ++r) {
-            float bm = -1.f;
-            int ba = 0x7fffffff, bt = -1;
-            float bo = 0.f;
-            for (int q = lane; q < nc; q += 32) {
-                const float4 e = c[q];
-                const int a = __float_as_int(e.z);
-                if (e.x > bm || (e.x == bm && a < ba)) { bm = e.x; ba = a; bo = e.y; bt = q; }
+
+        if (kTopkSplit == 1) {                             // one unit per GT: its list is the GT's list
+            const int n_sel = __popc(__ballot_sync(0xffffffffu, lane < topk && win.m != kEmptyKey));
+            if (lane < n_sel) {
+                sel[(size_t)g * kTalMaxK + lane] = make_float4(__int_as_float(win.a), __int_as_float(win.m), win.o, 0.f);
+                atomicMax(akey + (size_t)n * n_anchors + win.a,
+                          ((unsigned long long)__float_as_uint(win.o) << 32) | (unsigned int)(~(unsigned int)g_local));
             }
-            const int wmi = __reduce_max_sync(0xffffffffu, __float_as_int(bm));
-            const int wa = __reduce_min_sync(0xffffffffu, __float_as_int(bm) == wmi ? ba : 0x7fffffff);
-            const int wl = __ffs(__ballot_sync(0xffffffffu, __float_as_int(bm) == wmi && ba == wa)) - 1;
-            const float wo = __shfl_sync(0xffffffffu, bo, wl);
-            if (lane == wl && bt >= 0) c[bt].x = -2.f;         // taken (metrics are >= 0)
-            __syncwarp();
-            if (lane == 0) publish(r, wa, __int_as_float(wmi), wo);
+            if (lane == 0) sel_count[g] = n_sel;
+            continue;
         }
+        // ---- publish the unit's list; the GT's last unit merges the kTopkSplit lists -------------------
+        float4 *mine = psel + (size_t)unit * kTalMaxK;
+        if (lane < topk) mine[lane] = make_float4(__int_as_float(win.a), __int_as_float(win.m), win.o, 0.f);
+        __threadfence();
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) done = atomicAdd(gt_done + g, 1);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done != kTopkSplit - 1) continue;              // warp-uniform
+        __threadfence();
+        constexpr int NE = kTopkSplit * kTalMaxK / 32 > 0 ? kTopkSplit * kTalMaxK / 32 : 1;
+        int vm[NE], va[NE];
+        float vo[NE];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+            const int q = lane + 32 * i;                   // entry q: unit q / kTalMaxK of this GT, rank q % kTalMaxK
+            vm[i] = kEmptyKey; va[i] = 0x7fffffff; vo[i] = 0.f;
+            if (q < kTopkSplit * kTalMaxK && (q & (kTalMaxK - 1)) < topk) {
+                const float4 e = __ldcg(psel + ((size_t)g * kTopkSplit + q / kTalMaxK) * kTalMaxK + (q & (kTalMaxK - 1)));
+                vm[i] = __float_as_int(e.y); va[i] = __float_as_int(e.x); vo[i] = e.z;
+            }
+        }
+        const TopK fin = topk_select<NE>(vm, va, vo, lane, topk);
+        const int n_sel = __popc(__ballot_sync(0xffffffffu, lane < topk && fin.m != kEmptyKey));
+        if (lane < n_sel) {
+            sel[(size_t)g * kTalMaxK + lane] = make_float4(__int_as_float(fin.a), __int_as_float(fin.m), fin.o, 0.f);
+            // conflict resolution: the anchor goes to the GT with the largest overlap, ties -> lowest GT
+            atomicMax(akey + (size_t)n * n_anchors + fin.a,
+                      ((unsigned long long)__float_as_uint(fin.o) << 32) | (unsigned int)(~(unsigned int)g_local));
+        }
+        if (lane == 0) sel_count[g] = n_sel;
     }
-    if (lane == 0) sel_count[g] = n_sel;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -687,11 +751,13 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
 
 // One HALF-warp per (GT, selected anchor) slot: lane & 15 is the DFL bin, and the lane holds that bin of all four
 // sides, so the scalar part (CIoU, its gradient, the class cell) is issued once for two slots.  The half-warp first
-// works out what tal_select_kernel left open: whether its GT kept the anchor (conflicts went to the larger overlap)
+// works out what tal_topk_kernel left open: whether its GT kept the anchor (conflicts went to the larger overlap)
 // and the GT's largest metric / overlap over the anchors it kept -> the slot's target score t.  Everything written
 // here is NOT yet divided by the normaliser (the sum of all t, possibly over several ranks): tal_cls_kernel and
-// tal_finalize_kernel apply 1 / normaliser.  The per-CTA sums of t are added in fixed point, so the statistics the
-// last CTA writes do not depend on the order in which CTAs finish.
+// tal_finalize_kernel apply 1 / normaliser.  The target scores are summed in fixed point with integer atomics, so the
+// statistics do not depend on the order in which warps finish.  (Measured and not kept: one THREAD per slot with all 64
+// logits in flight and no shuffles -- 66 us against 60 us: the kernel is bound by its 2.8 million scattered 64-byte DRAM
+// accesses, not by its 38 million warp instructions.)
 template <typename T>
 __global__ void __launch_bounds__(128)
 tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
@@ -701,10 +767,7 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
               float lambda_cls, float lambda_dfl, int vfl, VflParams vp, float *__restrict__ fgrad,
               long long *__restrict__ fcell_off, float *__restrict__ fcell_val, float *__restrict__ fg_box,
               float *__restrict__ fg_dfl, float *__restrict__ fg_cls, int *__restrict__ aslot,
-              int *__restrict__ out_assigned, float *__restrict__ out_tscore, unsigned long long *__restrict__ stat_acc,
-              unsigned int *__restrict__ ticket, float *__restrict__ out_stats) {
-    __shared__ float s_t[8];
-    __shared__ bool s_last;
+              int *__restrict__ out_assigned, float *__restrict__ out_tscore, unsigned long long *__restrict__ stat_acc) {
     const int lane = threadIdx.x & 31, bin = lane & 15, base = lane & 16;
     const int slot = blockIdx.x * 8 + (threadIdx.x >> 4);          // slot = g * topk + r
     const int g_raw = slot / topk, r = slot - g_raw * topk;
@@ -734,8 +797,12 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
     const bool live = __shfl_sync(0xffffffffu, (int)pos, base + min(r, 15)) != 0 && r < ns;
     const int idx = live ? idx_r : 0;
     const float t = live ? t_r : 0.f;
-    if (bin == 0) s_t[threadIdx.x >> 4] = t;
     if (bin == 0 && in_range) {
+        if (live) {
+            // statistics in fixed point: integer atomics are order-independent, so the sums are run-to-run identical
+            atomicAdd(stat_acc + (slot & (kTalStatAcc - 1)), (unsigned long long)__double2ll_rn((double)t * kTalFix));
+            atomicAdd(stat_acc + kTalStatAcc + (slot & (kTalStatAcc - 1)), 1ull);
+        }
         if (!live) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; fcell_off[slot] = -1; }
         else {
             aslot[(size_t)n * n_anchors + idx] = slot + 1;
@@ -849,33 +916,27 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
             }
         }
     }
-    // ---- statistics: sum of the target scores and number of foreground anchors ----------------------
-    {   // foreground count: exact integer atomics, one per warp, fenced before the CTA takes its ticket
-        const unsigned live_mask = __ballot_sync(0xffffffffu, live && bin == 0);
-        if (lane == 0 && live_mask) {
-            atomicAdd(stat_acc + kTalStatAcc, (unsigned long long)__popc(live_mask));
-            __threadfence();
-        }
-    }
+}
+
+// [sum of target scores, #foreground] of this rank from the sub-accumulators tal_fg_kernel filled
+__global__ void __launch_bounds__(kTalStatAcc)
+tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *__restrict__ grid_rejected, int have_hint,
+                 float *__restrict__ out_stats) {
+    __shared__ long long s_t[kTalStatAcc], s_n[kTalStatAcc];
+    s_t[threadIdx.x] = (long long)stat_acc[threadIdx.x];
+    s_n[threadIdx.x] = (long long)stat_acc[kTalStatAcc + threadIdx.x];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sum += s_t[k];                // fixed order within the CTA
-        atomicAdd(stat_acc + (blockIdx.x & (kTalStatAcc - 1)), (unsigned long long)__double2ll_rn((double)sum * kTalFix));
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    for (int o = kTalStatAcc / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_t[threadIdx.x] += s_t[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
+        __syncthreads();
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     if (threadIdx.x == 0) {
-        long long acc = 0;
-        for (int k = 0; k < kTalStatAcc; ++k) acc += (long long)__ldcg(stat_acc + k);
-        out_stats[0] = (float)((double)acc / kTalFix);            // local sum of target scores (un-clamped)
-        out_stats[1] = (float)__ldcg(stat_acc + kTalStatAcc);      // foreground anchors
+        stat_acc[2 * kTalStatAcc] = (unsigned long long)s_n[0];
+        out_stats[0] = (float)((double)s_t[0] / kTalFix);          // local sum of target scores (un-clamped)
+        out_stats[1] = (float)s_n[0];                              // foreground anchors
+        out_stats[2] = have_hint && *grid_rejected ? 1.f : 0.f;    // the grid hint did not describe the anchors
 #pragma unroll
-        for (int i = 2; i < 8; ++i) out_stats[i] = 0.f;
+        for (int i = 3; i < 8; ++i) out_stats[i] = 0.f;
     }
 }
 
@@ -933,8 +994,8 @@ tal_finalize_kernel(T *__restrict__ grad, const long long *__restrict__ fcell_of
         out_loss[2] = l_cls;
         out_loss[3] = l_dfl;
         out_loss[4] = (float)tss;
-        out_loss[5] = (float)__ldcg(stat_acc + kTalStatAcc);      // foreground anchors (counted by tal_fg_kernel)
-        out_loss[6] = 0.f;
+        out_loss[5] = (float)__ldcg(stat_acc + 2 * kTalStatAcc);   // foreground anchors (counted by tal_fg_kernel)
+        out_loss[6] = (float)ticket[3];                    // 1: yb_tal_assign was given a grid hint that does not describe the anchors
         out_loss[7] = (float)ticket[2];                    // GT rows whose class id lies outside [0, nc) (counted by yb_tal_assign)
         *ticket = 0u;                                      // re-armed for the next yb_tal_loss on this workspace
     }
@@ -952,29 +1013,32 @@ static bool tal_vec_ok(const void *preds, const void *grad, int n_anchors) {
 template <typename T, int VW>
 static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors, const float *anchors,
                              const float *strides, const float *gt, const int32_t *gt_off, int gt_total,
-                             const yb_tal_params &p, float *out_stats, int32_t *out_assigned, float *out_tscore,
-                             const TalWorkspace &w, cudaStream_t st) {
+                             const yb_tal_params &p, const TalGrid &grid, float *out_stats, int32_t *out_assigned,
+                             float *out_tscore, const TalWorkspace &w, cudaStream_t st) {
     const int n_ch = 4 * kRegMax + nc;
-    YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
+    // the counters (tickets, statistics, per-GT unit counts) here; the per-anchor arrays by tal_decode_kernel
+    YB_CUDA(cudaMemsetAsync(w.ticket, 0, gt_total == 0 ? w.zero_bytes : w.small_zero_bytes, st));
     if (out_assigned) YB_CUDA(cudaMemsetAsync(out_assigned, 0xff, sizeof(int32_t) * (size_t)n_images * n_anchors, st));
     if (out_tscore) YB_CUDA(cudaMemsetAsync(out_tscore, 0, sizeof(float) * (size_t)n_images * n_anchors, st));
     if (gt_total > 0) {
         constexpr int TILE = kTalThreads * VW;
-        dim3 grid(n_images, (n_anchors + TILE - 1) / TILE);
-        const size_t smem = tal_cand_smem(TILE);
-        YB_CUDA(cudaFuncSetAttribute(tal_candidates_kernel<T, VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tal_candidates_kernel<T, VW><<<grid, kTalThreads, smem, st>>>(preds, n_ch, n_anchors, anchors, strides, gt, gt_off,
-                                                                     p.topk, p.alpha, p.beta, w.cand_count, w.cand, w.cand_cap);
+        tal_decode_kernel<T, VW><<<dim3((n_anchors + TILE - 1) / TILE, n_images), kTalThreads, 0, st>>>(
+            preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, grid, w.ticket + 3);
         YB_LAUNCH_CHECK();
-        tal_select_kernel<<<(gt_total + 3) / 4, 128, 0, st>>>(n_images, n_anchors, gt_off, gt_total, p.topk, w.cand_count, w.cand,
-                                                              w.cand_cap, w.sel, w.sel_count, w.akey, gt, nc, w.ticket + 2);
+        // warps draw (GT, part) units from a counter
+        const int topk_ctas = (int)std::min<long long>(((long long)gt_total * kTopkSplit + kTopkWarps - 1) / kTopkWarps, 148 * YB_TOPK_MINBLOCKS);
+        tal_topk_kernel<T><<<topk_ctas, 32 * kTopkWarps, 0, st>>>(
+            preds, n_images, n_ch, n_anchors, gt, gt_off, gt_total, p.topk, p.alpha, p.beta, w.dbox, w.gext, w.ctr,
+            grid, w.ticket + 3, w.psel, w.gt_done, w.sel, w.sel_count, w.akey, w.ticket + 1, w.ticket + 2);
         YB_LAUNCH_CHECK();
         const int slots = gt_total * p.topk;
         tal_fg_kernel<T><<<(slots + 7) / 8, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
                                                          gt_total, p.topk, w.sel, w.sel_count, w.akey, p.lambda_box, p.lambda_cls,
                                                          p.lambda_dfl, p.vfl, VflParams{p.vfl_alpha, p.vfl_gamma}, w.fgrad,
                                                          w.fcell_off, w.fcell_val, w.fg_box, w.fg_dfl, w.fg_cls, w.aslot,
-                                                         out_assigned, out_tscore, w.stat_acc, w.ticket + 1, out_stats);
+                                                         out_assigned, out_tscore, w.stat_acc);
+        YB_LAUNCH_CHECK();
+        tal_stats_kernel<<<1, kTalStatAcc, 0, st>>>(w.stat_acc, w.ticket + 3, grid.n_levels > 0, out_stats);
         YB_LAUNCH_CHECK();
     } else {
         YB_CUDA(cudaMemsetAsync(out_stats, 0, sizeof(float) * 8, st));
@@ -1040,8 +1104,9 @@ extern "C" size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_tot
 
 extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
                              const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                             int gt_total, const yb_tal_params *params, float *out_stats, int32_t *out_assigned_gt,
-                             float *out_target_score, void *workspace, size_t workspace_bytes, void *stream) {
+                             int gt_total, const yb_tal_params *params, const yb_tal_grid *grid_hint, float *out_stats,
+                             int32_t *out_assigned_gt, float *out_target_score, void *workspace, size_t workspace_bytes,
+                             void *stream) {
     if (int rc = tal_check(preds, workspace, params, dtype, n_images, nc, reg_max, n_anchors, gt_total, "yb_tal_assign"))
         return rc;
     YB_REQUIRE(anchors && strides && gt_offsets && out_stats, "yb_tal_assign: null pointer");
@@ -1051,23 +1116,37 @@ extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc,
         return YB_ERR_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TalGrid grid;
+    memset(&grid, 0, sizeof(grid));                        // n_levels = 0: no hint, generic scan
+    if (grid_hint != nullptr && grid_hint->n_levels > 0) {
+        // a hint must at least be a partition of [0, A) into h x w grids; its VALUES are verified on the device
+        YB_REQUIRE(grid_hint->n_levels <= YB_TAL_MAX_LEVELS, "yb_tal_assign: grid hint has more than %d levels", YB_TAL_MAX_LEVELS);
+        long long next = 0;
+        for (int l = 0; l < grid_hint->n_levels; ++l) {
+            YB_REQUIRE(grid_hint->start[l] == next && grid_hint->w[l] > 0 && grid_hint->h[l] > 0 && grid_hint->stride[l] > 0.f,
+                       "yb_tal_assign: grid hint level %d is inconsistent", l);
+            next += (long long)grid_hint->w[l] * grid_hint->h[l];
+        }
+        YB_REQUIRE(next == n_anchors, "yb_tal_assign: grid hint covers %lld anchors, not %d", next, n_anchors);
+        grid = *grid_hint;
+    }
     if (dtype == YB_F32) {
         const bool vec = tal_vec_ok<float>(preds, nullptr, n_anchors);
         const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, params->topk, tal_tile(dtype, vec));
         if (vec)
             return launch_tal_assign<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
-                                               gt_total, *params, out_stats, out_assigned_gt, out_target_score, w, st);
+                                               gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score, w, st);
         return launch_tal_assign<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
-                                           gt_total, *params, out_stats, out_assigned_gt, out_target_score, w, st);
+                                           gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score, w, st);
     }
     const bool vec = tal_vec_ok<__nv_bfloat16>(preds, nullptr, n_anchors);
     const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, params->topk, tal_tile(dtype, vec));
     if (vec)
         return launch_tal_assign<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
-                                                   gt_offsets, gt_total, *params, out_stats, out_assigned_gt, out_target_score,
+                                                   gt_offsets, gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score,
                                                    w, st);
     return launch_tal_assign<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
-                                               gt_offsets, gt_total, *params, out_stats, out_assigned_gt, out_target_score, w,
+                                               gt_offsets, gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score, w,
                                                st);
 }
 

@@ -241,11 +241,67 @@ class _FusedLoss(torch.autograd.Function):
         return (g,) + (None,) * 11
 
 
+# ----------------------------------------------------------------------------------------------
+# host logic: the anchors' grid structure, as a hint the kernels verify (never a precondition)
+# ----------------------------------------------------------------------------------------------
+_grid_hints = {}        # (device index, A) -> TalGrid | None (the anchors are not a pyramid of grids)
+_grid_strikes = {}
+
+
+def build_grid_hint(anchors: torch.Tensor, strides: torch.Tensor):
+    """Describe ``anchors (2, A)`` / ``strides (1, A)`` as the reference's pyramid of regular grids
+    (``make_anchors``, model_utils.py:60-70: per level x fastest, ``(x0 + col, y0 + row)``, one stride per level), or
+    return ``None`` when they are not one.  Pure host logic on a CPU copy; called once per anchor-set size, the
+    device re-verifies the result on every call."""
+    anc = anchors.detach().float().cpu().reshape(2, -1)
+    st = strides.detach().float().cpu().reshape(-1)
+    a = st.numel()
+    if a == 0 or anc.shape[1] != a:
+        return None
+    cuts = [0] + (torch.nonzero(st[1:] != st[:-1])[:, 0] + 1).tolist() + [a]
+    if len(cuts) - 1 > _cabi.TAL_MAX_LEVELS:
+        return None
+    hint = _cabi.TalGrid()
+    hint.n_levels = len(cuts) - 1
+    for l, (lo, hi) in enumerate(zip(cuts, cuts[1:])):
+        ax, ay = anc[0, lo:hi], anc[1, lo:hi]
+        rows = torch.nonzero(ay[1:] != ay[:-1])[:, 0]
+        w = int(rows[0]) + 1 if rows.numel() else hi - lo
+        if (hi - lo) % w or not st[lo] > 0:
+            return None
+        h = (hi - lo) // w
+        col = torch.arange(w, dtype=torch.float32).repeat(h)
+        row = torch.arange(h, dtype=torch.float32).repeat_interleave(w)
+        if not (torch.equal(ax, ax[0] + col) and torch.equal(ay, ay[0] + row)):
+            return None
+        hint.start[l], hint.w[l], hint.h[l] = lo, w, h
+        hint.stride[l], hint.x0[l], hint.y0[l] = float(st[lo]), float(ax[0]), float(ay[0])
+    return hint
+
+
+def _grid_hint_for(anc: torch.Tensor, st: torch.Tensor):
+    key = (anc.device.index, anc.shape[1])
+    if key not in _grid_hints:
+        _grid_hints[key] = build_grid_hint(anc, st)       # one device-to-host copy, the first time this size is seen
+    return _grid_hints[key]
+
+
+def grid_hint_rejected(anc_device_index: int, a: int):
+    """The kernels reported (out_loss[6]) that the cached hint does not describe the anchors they were given: forget it,
+    so that the next call rebuilds it from the new anchors; give up on a size whose fresh hints keep failing."""
+    key = (anc_device_index, a)
+    _grid_strikes[key] = _grid_strikes.get(key, 0) + 1
+    if _grid_strikes[key] >= 3:
+        _grid_hints[key] = None
+    else:
+        _grid_hints.pop(key, None)
+
+
 def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, anchors: torch.Tensor,
                    strides: torch.Tensor, num_classes: int, lambda_box: float, lambda_cls: float, lambda_dfl: float,
                    reg_max: int = 16, topk: int = 10, alpha: float = 0.5, beta: float = 6.0, want_grad: bool = True,
                    want_trace: bool = False, sync_normalizer: bool = True, cls_loss: str = "bce",
-                   vfl_alpha: float = 0.75, vfl_gamma: float = 2.0):
+                   vfl_alpha: float = 0.75, vfl_gamma: float = 2.0, grid_hint="auto"):
     """Task-aligned variant (``yb_tal_assign`` + ``yb_tal_loss``).  Not in the reference: specified by
     ``oracle/tal_oracle.py`` (SURVEY.md §8(a')).
 
@@ -253,7 +309,9 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     process group is initialised and ``sync_normalizer`` is set — the path's one real exchange step.
     ``cls_loss="vfl"`` weights the class term varifocally (``yb_tal_params.vfl``): background cells by
     ``vfl_alpha * sigmoid(x) ** vfl_gamma``, the positive cell of a foreground anchor by its target score.
-    Returns ``(out_loss (8,) [total, box, cls, dfl, normaliser, #fg, ..], grad or None, trace)``.
+    ``grid_hint``: ``"auto"`` (describe the anchors as a pyramid of grids once per size and let the kernels verify it on
+    every call), ``None`` (structure-free candidate scan) or a ``_cabi.TalGrid``.  Results never depend on it.
+    Returns ``(out_loss (8,) [total, box, cls, dfl, normaliser, #fg, hint rejected, #bad class ids], grad or None, trace)``.
     """
     _cabi.require_cuda(preds, "preds")
     if cls_loss not in ("bce", "vfl"):
@@ -278,11 +336,13 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
         tsc = torch.empty(n, a, dtype=torch.float32, device=dev)
     gt_ptr = _cabi.ptr(gt) if gt_total else None
     import ctypes
+    hint = _grid_hint_for(anc, st) if isinstance(grid_hint, str) else grid_hint
     params = _cabi.TalParams(int(topk), float(alpha), float(beta), float(lambda_box), float(lambda_cls), float(lambda_dfl),
                              int(cls_loss == "vfl"), float(vfl_alpha), float(vfl_gamma))
     with torch.cuda.device(dev):
         rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
-                               _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params), _cabi.ptr(stats),
+                               _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params),
+                               ctypes.byref(hint) if hint is not None else None, _cabi.ptr(stats),
                                _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_tal_assign")
     tss = stats[:1]
@@ -391,6 +451,8 @@ class YoloDFLQFLoss(nn.Module):
             stats = self.last_stats = holder[0]
             host = stats.tolist()
             _raise_on_bad_class(host[7], self.num_classes)
+            if host[6]:                             # the anchors changed under a cached grid hint (the result is still right)
+                grid_hint_rejected(preds.device.index, preds.shape[2])
             return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2], "dfl_loss": host[3]}
         if n > 0 and sum(counts) == 0:
             # the reference fails here: total_dfl is still the python float 0.0 (losses.py:271-279)

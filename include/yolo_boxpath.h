@@ -110,11 +110,12 @@ int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_images, int nc
  * CIoU (ties -> lowest GT), normalised target scores; CIoU + DFL + BCE-with-logits loss and backward.
  * Two calls with the normaliser in between, so the caller can all-reduce it (SUM / world) under DDP:
  *
- *   yb_tal_assign  -> out_stats[0] = sum of target scores of this rank (un-clamped), [1] = #foreground;
+ *   yb_tal_assign  -> out_stats[0] = sum of target scores of this rank (un-clamped), [1] = #foreground,
+ *                     [2] = 1 if a grid hint was given and rejected;
  *                     out_assigned_gt (N, A) int32 (-1 background) / out_target_score (N, A) fp32: optional
  *   yb_tal_loss    <- tss_dev: device scalar, the normaliser to use (clamped at 1 inside);
  *                  -> grad_preds (or NULL), out_loss: [0] total [1] box (CIoU) [2] cls (BCE) [3] dfl
- *                     [4] normaliser used [5] #foreground [7] #GT rows with a class id outside [0, nc)
+ *                     [4] normaliser used [5] #foreground [6] grid hint rejected [7] #GT rows with a class id outside [0, nc)
  *                     (clamped to stay memory-safe; the module raises, as the reference's scatter_ would)
  * The same workspace must be passed to both calls (it carries the assignment).
  * ---------------------------------------------------------------------------------------- */
@@ -127,14 +128,26 @@ typedef struct {
                                                       (differentiated), = the target score on the positive cell */
 } yb_tal_params;                                /* host struct, read during the call; pass the SAME values to both calls */
 
+/* Optional hint: the anchors as a pyramid of regular grids, what the reference's make_anchors produces
+ * (src/utils/model_utils.py:60-70): level l owns anchors [start, start + w*h), x fastest, anchor (row, col) =
+ * (x0 + col, y0 + row) in grid units, one stride per level.  The kernels VERIFY the hint against the anchor / stride
+ * arrays on every call (bit for bit) and fall back to a structure-free scan when it does not hold — results never
+ * depend on it, only the speed of the candidate enumeration does.  out_stats[2] = 1 reports a rejected hint. */
+#define YB_TAL_MAX_LEVELS 8
+typedef struct {
+    int n_levels;                               /* 0: no hint */
+    int start[YB_TAL_MAX_LEVELS], w[YB_TAL_MAX_LEVELS], h[YB_TAL_MAX_LEVELS];
+    float stride[YB_TAL_MAX_LEVELS], x0[YB_TAL_MAX_LEVELS], y0[YB_TAL_MAX_LEVELS];
+} yb_tal_grid;                                  /* host struct, read during the call */
+
 size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype, int topk);
 
 /* Decode, assignment and everything of the loss that does not need the normaliser (the foreground anchors' CIoU / DFL
  * terms and box-logit gradients, kept un-normalised in the workspace). */
 int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
                   const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                  int gt_total, const yb_tal_params *params, float *out_stats,
-                  int32_t *out_assigned_gt, float *out_target_score,
+                  int gt_total, const yb_tal_params *params, const yb_tal_grid *grid_hint /* or NULL */,
+                  float *out_stats, int32_t *out_assigned_gt, float *out_target_score,
                   void *workspace, size_t workspace_bytes, void *stream);
 
 /* The dense class pass (reads the class logits, writes the whole gradient) and the loss scalars. */

@@ -39,18 +39,19 @@ def run_all():
         lib.yb_tal_workspace_bytes.restype = ctypes.c_size_t
         lib.yb_tal_workspace_bytes.argtypes = [ctypes.c_int] * 5
         Pp, I = ctypes.c_void_p, ctypes.c_int
-        lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
+        lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, Pp, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
         lib.yb_tal_loss.argtypes = [Pp, I, I, I, I, I, I, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
         lib.yb_last_error.restype = ctypes.c_char_p
         prm = _cabi.TalParams(10, 0.5, 6.0, 1.5, 1.0, 1.5, 0, 0.75, 2.0)
         line = [f'{name(v):24s}']
         for cn, (x, gt, off, a, s, code) in data.items():
             n, c, A = x.shape; G = gt.shape[0]
+            hint = P.build_grid_hint(a, s) if os.environ.get('YB_NO_HINT') is None else None
             ws = torch.empty(lib.yb_tal_workspace_bytes(n, A, G, code, 10), dtype=torch.uint8, device=dev)
             stats = torch.empty(8, device=dev); out = torch.empty(8, device=dev); grad = torch.empty_like(x)
             st = torch.cuda.current_stream().cuda_stream
             def assign():
-                rc = lib.yb_tal_assign(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, ctypes.byref(prm), stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st)
+                rc = lib.yb_tal_assign(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, ctypes.byref(prm), ctypes.byref(hint) if hint is not None else None, stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st)
                 assert rc == 0, lib.yb_last_error()
             def loss():
                 rc = lib.yb_tal_loss(x.data_ptr(), code, n, 80, 16, A, G, ctypes.byref(prm), stats.data_ptr(), grad.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st)

@@ -71,6 +71,39 @@ def test_tal_matches_oracle(n, nc, imgsz, gmax, seed, topk, cuda_device):
     assert ((grad[:, :64].abs().sum(1) > 0) <= (asg >= 0)).all()
 
 
+def test_grid_hint_never_changes_the_result(cuda_device):
+    """The candidate enumeration has two forms: one rectangle of cells per pyramid level when the anchors are verified
+    (on the device, every call) to be the regular grids the caller's hint describes, a structure-free scan of anchor
+    groups otherwise.  Both must give bit-identical results; a hint that does not describe the anchors is rejected
+    (out_loss[6] = 1) and changes nothing."""
+    from custom_yolo_implmentation_b200 import _cabi
+    preds, gts, anchors, strides = make_inputs(3, 80, 640, 60, 36)
+    ref = run_cuda(preds, gts, anchors, strides, 80, cuda_device)                       # "auto": hint accepted
+    assert ref[0][6].item() == 0.0
+    hint = P.build_grid_hint(anchors, strides)
+    assert hint is not None and hint.n_levels == 3 and list(hint.w)[:3] == [80, 40, 20]
+    wrong = _cabi.TalGrid.from_buffer_copy(hint)
+    wrong.x0[1] = 0.25                                                                  # level 1 shifted by a quarter cell
+    for h, rejected in ((None, 0.0), (wrong, 1.0), (hint, 0.0)):
+        got = run_cuda(preds, gts, anchors, strides, 80, cuda_device, grid_hint=h)
+        assert got[0][6].item() == rejected
+        assert torch.equal(got[0][:6], ref[0][:6]) and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+        assert torch.equal(got[3], ref[3])
+    # anchors that are NOT a grid (two of them swapped): no hint can be built, the scan handles them
+    perm = torch.arange(anchors.shape[1]); perm[[10, 4000]] = perm[[4000, 10]]
+    assert P.build_grid_hint(anchors[:, perm], strides[:, perm]) is None
+    a_out = run_cuda(preds[:, :, perm], gts, anchors[:, perm], strides[:, perm], 80, cuda_device, grid_hint=None)
+    # the same anchors in another order: ties between equal metrics may resolve to another (lowest-index) anchor, nothing else
+    same = (a_out[2] == ref[2][:, perm]).float().mean().item()
+    assert same > 0.999 and abs(a_out[0][0].item() - ref[0][0].item()) <= 1e-4 * ref[0][0].item()
+    # bf16-rounded anchors of a 1280 px grid (159.5 is not a bf16 number, SURVEY Q13): not a regular grid either
+    pb, gb_, ab, sb = make_inputs(1, 20, 1280, 30, 37, dtype=torch.bfloat16)
+    assert P.build_grid_hint(ab, sb) is None
+    out_b, _, asg_b, _, _ = run_cuda(pb, gb_, ab, sb, 20, cuda_device)
+    orb, _ = oracle_on_gpu_assignment(asg_b, pb, gb_, ab, sb, 20, backward=False)
+    assert abs(out_b[0].item() - orb.total.item()) <= 1e-2 * orb.total.item()
+
+
 @pytest.mark.parametrize("gamma", [2.0, 1.5])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_tal_varifocal_class_loss_matches_oracle(gamma, dtype, cuda_device):
