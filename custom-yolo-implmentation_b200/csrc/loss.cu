@@ -639,18 +639,26 @@ match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors,
 // One element of the quality focal loss at target 0 and its gradient w.r.t. the logit
 // (src/model/losses.py:51-56 with target_scores == 0):
 //     loss term  p^2 log(1 - p + 1e-12)          (sign and 1/A applied by the reduction)
-//     gradient   k p^2 (p - 2 q log q)           k = lambda_cls / (N A),  q = 1 - p
-// Fast path for q >= 0.7071 (logit <= -0.88, i.e. background): ex2.approx / rcp.approx and a degree-5
-// minimax polynomial of log1p on [-0.293, 0] (max relative error 9.4e-8, fitted offline); q is formed
-// as fl(1 - p) exactly as the reference does, so its rounding near 1 is reproduced, not avoided.
-// The +1e-12 inside the reference's log is below half an ulp of q there and drops out.
+//     gradient   k p^2 (p q / (q + 1e-12) - 2 q log(q + 1e-12)),   k = lambda_cls / (N A),  q = fl(1 - p)
+// One formula for ANY logit, two elements at a time on the packed fp32 pipe (FMUL2 / FFMA2 / FADD2):
+//   p        MUFU.EX2 + MUFU.RCP; q is formed as fl(1 - p) exactly as the reference does, so its rounding near 1 (and its
+//            collapse to 0 for logits above ~16.6, where the reference's gradient vanishes) is reproduced, not avoided;
+//   log q    q >= 0.7071 (logit <= -0.88, the background): degree-5 minimax polynomial of log1p on [-0.293, 0] (max
+//            relative error 9.4e-8, fitted offline) -- MUFU.LG2's 2^-22 ABSOLUTE error would be a 1e-5 RELATIVE error
+//            on these, the cells that carry the loss; the +1e-12 is below half an ulp of q there and drops out;
+//            q < 0.7071: MUFU.LG2 of q + 1e-12, whose absolute error is harmless next to |log q| >= 0.35;
+//   q / (q + 1e-12) is 1 to within 1.7e-5 for every non-zero float q (>= 2^-24) and is taken as 1; q == 0 zeroes the gradient.
+// (Round 1 took a non-inlined scalar expf / logf path for every group of four with a logit above -0.88: 0.47 ms per step
+// instead of 0.26 on class logits ~ N(0, 2).)
 constexpr float kFastQ = 0.70710678f;
 
-// Two elements at a time on the packed fp32 pipe (FMUL2 / FFMA2 / FADD2); MUFU.EX2 and MUFU.RCP are
-// the only scalar operations.  Returns q of both so the caller can detect, once per group, the rare
-// elements that need the general formula.
-__device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 &acc2, float &g0, float &g1,
-                                            float &q0, float &q1, float &t0, float &t1) {
+__device__ __forceinline__ float fast_lg2(float x) {         // MUFU.LG2
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 &acc2, float &g0, float &g1) {
     const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), mtwo = pack2(-2.f, -2.f);
     float a0, a1;
     unpack2(mul2(pack2(x0, x1), pack2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
@@ -659,58 +667,46 @@ __device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 
     unpack2(u, u0, u1);
     const f32x2 p = pack2(fast_rcp(u0), fast_rcp(u1));
     const f32x2 q = fma2(p, mone, one);                                       // fl(1 - p), as the reference
-    const f32x2 f = add2(q, mone);                                            // exact for q in [0.5, 1]
+    float q0, q1;
+    unpack2(q, q0, q1);
+    // log q, polynomial branch: f = q - 1 is exact for q in [0.5, 1]
+    const f32x2 f = add2(q, mone);
     f32x2 r = pack2(0.3410167098045349f, 0.3410167098045349f);
     r = fma2(r, f, pack2(-0.08926734328269958f, -0.08926734328269958f));
     r = fma2(r, f, pack2(0.21280372142791748f, 0.21280372142791748f));
     r = fma2(r, f, pack2(-0.249073788523674f, -0.249073788523674f));
     r = fma2(r, f, pack2(0.33335742354393005f, 0.33335742354393005f));
     r = fma2(r, f, pack2(-0.49999991059303284f, -0.49999991059303284f));
-    const f32x2 lq = fma2(mul2(f, f), r, f);                                  // log(q) = f + f^2 R(f)
+    float lp0, lp1;
+    unpack2(fma2(mul2(f, f), r, f), lp0, lp1);                                // log(q) = f + f^2 R(f)
+    // ... and the MUFU branch for the rest: skipped by the warps whose lanes all hold background logits (the usual case);
+    // when taken it costs two MUFU.LG2 and a handful of selects, not a function call
+    if (!(fminf(q0, q1) >= kFastQ)) {
+        const float lm0 = fast_lg2(q0 + kEpsLog) * 0.6931471805599453f, lm1 = fast_lg2(q1 + kEpsLog) * 0.6931471805599453f;
+        lp0 = q0 >= kFastQ ? lp0 : lm0;
+        lp1 = q1 >= kFastQ ? lp1 : lm1;
+    }
+    const f32x2 lq = pack2(lp0, lp1);
     const f32x2 p2 = mul2(p, p);
-    const f32x2 term = mul2(p2, lq);
-    acc2 = add2(acc2, term);
+    acc2 = fma2(p2, lq, acc2);
     const f32x2 g = mul2(mul2(p2, k2), fma2(mul2(q, mtwo), lq, p));           // k p^2 (p - 2 q log q)
     unpack2(g, g0, g1);
-    unpack2(q, q0, q1);
-    unpack2(term, t0, t1);
-}
-
-// general formula for target 0 (any logit), used for the few elements with q < kFastQ
-__device__ __noinline__ void qfl_bg_slow(float x, float k_cls, float &term, float &g) {
-    const float p = __fdiv_rn(1.f, 1.f + expf(-x));
-    const float q = 1.f - p;
-    const float lq = logf(q + kEpsLog);
-    term = p * p * lq;
-    g = -k_cls * (2.f * p * lq - p * p / (q + kEpsLog)) * p * q;
+    g0 = q0 == 0.f ? 0.f : g0;                                                // sigmoid'(x) = p q = 0: no gradient (NaN stays NaN)
+    g1 = q1 == 0.f ? 0.f : g1;
 }
 
 template <typename T, int VW>
-__device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, float k_cls, f32x2 k2, f32x2 &acc2, float &fix,
-                                             float (&g)[VW]) {
+__device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, f32x2 k2, f32x2 &acc2, float (&g)[VW]) {
     if constexpr (VW == 1) {
-        float q0, q1, t0, t1, g1;
-        f32x2 dummy = pack2(0.f, 0.f);
-        qfl_bg_pair(row.get(0), row.get(0), k2, dummy, g[0], g1, q0, q1, t0, t1);
-        if (!(q0 >= kFastQ)) qfl_bg_slow(row.get(0), k_cls, t0, g[0]);
-        fix += t0;
+        float g1;
+        f32x2 pair = pack2(0.f, 0.f);
+        qfl_bg_pair(row.get(0), row.get(0), k2, pair, g[0], g1);
+        float lo, hi;
+        unpack2(pair, lo, hi);
+        acc2 = add2(acc2, pack2(lo, 0.f));                 // the second lane is a copy: count it once
     } else {
-        float q[VW], t[VW];
-        float qmin = 1.f;
 #pragma unroll
-        for (int v = 0; v < VW; v += 2) {
-            qfl_bg_pair(row.get(v), row.get(v + 1), k2, acc2, g[v], g[v + 1], q[v], q[v + 1], t[v], t[v + 1]);
-            qmin = fminf(qmin, fminf(q[v], q[v + 1]));
-        }
-        if (!(qmin >= kFastQ)) {                           // rare (also catches NaN)
-#pragma unroll
-            for (int v = 0; v < VW; ++v)
-                if (!(q[v] >= kFastQ)) {
-                    float ts;
-                    qfl_bg_slow(row.get(v), k_cls, ts, g[v]);
-                    fix += ts - t[v];                      // replace the fast-path term already in acc2
-                }
-        }
+        for (int v = 0; v < VW; v += 2) qfl_bg_pair(row.get(v), row.get(v + 1), k2, acc2, g[v], g[v + 1]);
     }
 }
 
@@ -725,7 +721,6 @@ __device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split
     const int c_lo = split * c_per;
     nc = min(nc, c_lo + c_per) - c_lo;
     f32x2 acc2 = pack2(0.f, 0.f);
-    float fix = 0.f;
     if (a0 < n_anchors && nc > 0) {
         const size_t base = ((size_t)n * n_ch + 4 * kRegMax + c_lo) * n_anchors + a0;
         const f32x2 k2 = pack2(k_cls, k_cls);
@@ -744,7 +739,7 @@ __device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split
             for (int u = 0; u < U; ++u) {
                 if (c + u < nc) {
                     float g[VW];
-                    qfl_bg_group<T, VW>(cur[u], k_cls, k2, acc2, fix, g);
+                    qfl_bg_group<T, VW>(cur[u], k2, acc2, g);
                     if (WRITE_GRAD) Group<T, VW>::store(grad + base + (size_t)(c + u) * n_anchors, g);
                 }
             }
@@ -754,7 +749,7 @@ __device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split
     }
     float lo, hi;
     unpack2(acc2, lo, hi);
-    const float wsum = warp_sum((lo + hi) + fix);
+    const float wsum = warp_sum(lo + hi);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = wsum;
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -108,6 +108,25 @@ def test_loss_matches_oracle(n, nc, imgsz, gmax, seed, conflict, cuda_device):
     assert (grad[:, :64].abs().sum(1) > 0).le(fg).all()
 
 
+@pytest.mark.parametrize("std,mean", [(2.0, 0.0), (6.0, 2.0)])
+def test_confident_class_logits_match_oracle(std, mean, cuda_device):
+    """Class logits far from the head's bias initialisation: half of them positive, some above 16.6 where fl(1 - p) is 0
+    and the reference's gradient vanishes, some so negative that p underflows.  The class role is one branch-free
+    formula for every logit; it must meet the same tolerances here as on background-like inputs."""
+    n, nc = 3, 80
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, 640, 40, 1250)
+    g = torch.Generator().manual_seed(7)
+    preds[:, 64:] = torch.randn(preds[:, 64:].shape, generator=g) * std + mean
+    preds[0, 64:, :50] = torch.linspace(-110.0, 40.0, 50)           # the extremes, including exp(-x) = inf
+    out, grad, idx, iou, dfl_img, cls_img = run_cuda_trace(preds, gts, anchors, strides, nc, cuda_device)
+    ora = L.loss_forward_backward(preds, gts, anchors, strides, nc, forced_idx=idx)
+    assert torch.isfinite(out[:4]).all() and torch.isfinite(grad).all()
+    assert abs(out[0].item() - ora.total.item()) <= F32_RTOL * abs(ora.total.item())
+    assert torch.allclose(cls_img, ora.cls_per_image, rtol=F32_RTOL, atol=1e-9)
+    assert_grad_close(grad, ora.grad, F32_RTOL)
+    assert (grad[:, 64:][preds[:, 64:] > 17.0] == 0).all()          # p rounds to 1: sigmoid'(x) = 0 in the reference too
+
+
 def test_bf16_inputs_match_oracle(cuda_device):
     preds, gts, anchors, strides = syn.make_loss_inputs(3, 80, 640, 60, 1240, dtype=torch.bfloat16)
     out, grad, idx, iou, _, _ = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
