@@ -480,19 +480,35 @@ def run_ours(args):
         nms["pipes_ncu"] = json.load(open(ppath))
 
     # ---- extra lines (not the headline): the task-aligned variant, the dense bf16 config, adverse class logits ----
-    tal_ms = time_steps(lambda: fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5), extra_steps)
-    tal_out, _, _ = fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5)
+    # the task-aligned path's one exchange step: [sum of target scores, #fg] averaged over the ranks between assignment and
+    # loss.  Headline: through peer-mapped mailboxes (csrc/peer.cu: NVLink stores from the assign call's last kernel, a poll
+    # in the loss call's first); beside it the same step with a torch.distributed (NCCL) all-reduce.
+    px = None
+    if world > 1:
+        from custom_yolo_implmentation_b200.training.distributed_setup import PeerExchange
+        px = PeerExchange()
+    tal_ms = time_steps(lambda: fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5, exchange=px), extra_steps)
+    tal_out, _, _ = fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5, exchange=px)
     tal = {"metric": "images/sec through decode+TAL assign+CIoU/DFL/BCE loss+bwd (no reference counterpart; parity vs in-repo oracle)",
            "value": world * n / (tal_ms * 1e-3), "unit": "images/s", "ms_per_step": tal_ms,
            "hbm_frac_whole_step": bytes_per_step / (tal_ms * 1e-3) / 1e9 / peak,
-           "exchange": "all-reduce of [sum target scores, #fg] between assign and loss" if world > 1 else "none (1 GPU)"}
+           "exchange": ("peer mailboxes over NVLink: [sum target scores, #fg] stored into every rank's mailbox by yb_tal_assign's last "
+                        "kernel, polled by yb_tal_loss's first") if world > 1 else "none (1 GPU)"}
     if world > 1:                        # the exchange on real hardware: every rank must have used the SAME normaliser
-        used = [torch.zeros(1, device=dev) for _ in range(world)]
-        dist.all_gather(used, tal_out[4:5].clone())
-        used = [float(u.item()) for u in used]
+        def normalisers(o):
+            used = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(used, o[4:5].clone())
+            return [float(u.item()) for u in used]
+        used = normalisers(tal_out)
+        nccl_ms = time_steps(lambda: fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5, exchange=None), extra_steps)
+        nccl_out, _, _ = fused_tal_loss(preds, gt, off, anchors_d, strides_d, nc, 1.5, 1.0, 1.5, exchange=None)
+        used_nccl = normalisers(nccl_out)
         tal["normaliser_used_by_rank"] = used
-        if max(used) != min(used):
-            raise SystemExit(f"bench.py: PARITY FAILURE: ranks normalised the task-aligned loss differently: {used}")
+        tal["with_nccl_all_reduce_instead"] = {"ms_per_step": nccl_ms, "value": world * n / (nccl_ms * 1e-3), "unit": "images/s",
+                                               "normaliser_used_by_rank": used_nccl}
+        if max(used) != min(used) or max(used_nccl) != min(used_nccl) or abs(used[0] - used_nccl[0]) > 1e-6 * used[0]:
+            raise SystemExit(f"bench.py: PARITY FAILURE: ranks normalised the task-aligned loss differently: {used} / {used_nccl}")
+        px.close()
     # class logits ~ N(0, 2): half of them positive, nothing like the head's bias initialisation the headline input
     # follows; the class role's packed fast path (background logits <= -0.88) does not apply to most groups
     g = torch.Generator().manual_seed(4321 + rank)

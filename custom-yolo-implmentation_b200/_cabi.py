@@ -34,9 +34,15 @@ _SIGNATURES = {
                                 c_void_p, c_size_t, ctypes.c_uint, c_void_p, c_void_p]),
     "yb_tal_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "yb_tal_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yb_tal_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                            c_void_p, c_size_t, c_void_p]),
+                            c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_peer_mailbox_bytes": (c_size_t, []),
+    "yb_peer_mailbox_alloc": (c_int, [c_void_p]),
+    "yb_peer_mailbox_free": (c_int, [c_void_p]),
+    "yb_peer_mailbox_export": (c_int, [c_void_p, c_void_p]),
+    "yb_peer_mailbox_open": (c_int, [c_void_p, c_void_p]),
+    "yb_peer_mailbox_close": (c_int, [c_void_p]),
     "yb_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "yb_loss_fwd_bwd_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -78,6 +84,14 @@ class TalParams(ctypes.Structure):
 
 
 TAL_MAX_LEVELS = 8
+PEER_MAX_WORLD = 16
+PEER_HANDLE_BYTES = 64
+
+
+class PeerExchangeStruct(ctypes.Structure):
+    """``yb_peer_exchange`` of include/yolo_boxpath.h."""
+    _fields_ = [("world", c_int), ("rank", c_int), ("seq", ctypes.c_uint), ("mailbox", c_void_p * PEER_MAX_WORLD)]
+
 
 
 class TalGrid(ctypes.Structure):

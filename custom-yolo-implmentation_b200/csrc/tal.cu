@@ -36,6 +36,10 @@
 
 namespace yb {
 
+int launch_peer_wait(const yb_peer_exchange &px, float *out2, unsigned int *timed_out, cudaStream_t st);   // csrc/peer.cu
+int check_peer(const yb_peer_exchange *px, const char *who);
+constexpr int kPeerSlotsTal = 4;                 // = kPeerSlots of csrc/peer.cu
+
 constexpr int kTalThreads = 128;
 constexpr int kTalMaxK = 16;
 constexpr float kEpsCiou = 1e-7f;
@@ -53,7 +57,7 @@ __host__ __device__ constexpr int tal_cls_split(int tile) { return tile >= 1024 
 #endif
 struct TalWorkspace {
     // zeroed by yb_tal_assign's first kernels (the counters by a memset, the per-anchor arrays by tal_decode_kernel)
-    unsigned int *ticket;               // [0] finalize ticket, [1] next work unit of tal_topk_kernel, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected
+    unsigned int *ticket;               // [0] finalize ticket, [1] next work unit of tal_topk_kernel, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived
     unsigned long long *stat_acc;       // [kTalStatAcc] fixed-point sums of the target scores, [kTalStatAcc] foreground counts, [1] total #foreground
     int *gt_done;                       // [gt_total] units of the GT that tal_topk_kernel has finished
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
@@ -62,6 +66,7 @@ struct TalWorkspace {
     float4 *dbox;                       // [N * A]  decoded pixel box (xyxy) of every anchor
     float4 *gext;                       // [ceil(A / 32)]  extent of the anchor centres of each group of 32 anchors
     float2 *ctr;                        // [A]  anchor centres in pixels
+    float *peer_tss;                    // [2]  normaliser and #foreground averaged over the ranks (peer exchange, csrc/peer.cu)
     float4 *psel;                       // [gt_total * kTopkSplit * kTalMaxK]  per-unit partial lists (same fields as sel)
     float4 *sel;                        // [gt_total * kTalMaxK]  anchor bits, metric, overlap, -
     int *sel_count;                     // [gt_total]
@@ -103,6 +108,8 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     off += round_up(sizeof(float4) * (size_t)((n_anchors + 31) / 32), 64);
     w.ctr = reinterpret_cast<float2 *>(p + off);
     off += round_up(sizeof(float2) * (size_t)n_anchors, 64);
+    w.peer_tss = reinterpret_cast<float *>(p + off);
+    off += 64;
     w.psel = reinterpret_cast<float4 *>(p + off);
     off += round_up(sizeof(float4) * g * kTalMaxK * 8, 64);           // 8 >= kTopkSplit
     w.sel = reinterpret_cast<float4 *>(p + off);
@@ -921,7 +928,7 @@ tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors
 // [sum of target scores, #foreground] of this rank from the sub-accumulators tal_fg_kernel filled
 __global__ void __launch_bounds__(kTalStatAcc)
 tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *__restrict__ grid_rejected, int have_hint,
-                 float *__restrict__ out_stats) {
+                 float *__restrict__ out_stats, const yb_peer_exchange px) {
     __shared__ long long s_t[kTalStatAcc], s_n[kTalStatAcc];
     s_t[threadIdx.x] = (long long)stat_acc[threadIdx.x];
     s_n[threadIdx.x] = (long long)stat_acc[kTalStatAcc + threadIdx.x];
@@ -937,6 +944,15 @@ tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *
         out_stats[2] = have_hint && *grid_rejected ? 1.f : 0.f;    // the grid hint did not describe the anchors
 #pragma unroll
         for (int i = 3; i < 8; ++i) out_stats[i] = 0.f;
+    }
+    // the exchange, producer side (csrc/peer.cu): thread r stores this rank's entry of step px.seq into rank r's mailbox —
+    // a peer store over NVLink / NVSwitch for r != rank.  Two self-validating 8-byte words: (seq << 32) | payload.
+    if ((int)threadIdx.x < px.world) {
+        const float t = (float)((double)s_t[0] / kTalFix), nf = (float)s_n[0];
+        volatile unsigned long long *e = static_cast<unsigned long long *>(px.mailbox[threadIdx.x]) +
+                                         ((size_t)(px.seq % kPeerSlotsTal) * YB_PEER_MAX_WORLD + px.rank) * 2;
+        e[0] = ((unsigned long long)px.seq << 32) | __float_as_uint(t);
+        e[1] = ((unsigned long long)px.seq << 32) | __float_as_uint(nf);
     }
 }
 
@@ -1013,8 +1029,8 @@ static bool tal_vec_ok(const void *preds, const void *grad, int n_anchors) {
 template <typename T, int VW>
 static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors, const float *anchors,
                              const float *strides, const float *gt, const int32_t *gt_off, int gt_total,
-                             const yb_tal_params &p, const TalGrid &grid, float *out_stats, int32_t *out_assigned,
-                             float *out_tscore, const TalWorkspace &w, cudaStream_t st) {
+                             const yb_tal_params &p, const TalGrid &grid, const yb_peer_exchange &px, float *out_stats,
+                             int32_t *out_assigned, float *out_tscore, const TalWorkspace &w, cudaStream_t st) {
     const int n_ch = 4 * kRegMax + nc;
     // the counters (tickets, statistics, per-GT unit counts) here; the per-anchor arrays by tal_decode_kernel
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, gt_total == 0 ? w.zero_bytes : w.small_zero_bytes, st));
@@ -1038,10 +1054,14 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
                                                          w.fcell_off, w.fcell_val, w.fg_box, w.fg_dfl, w.fg_cls, w.aslot,
                                                          out_assigned, out_tscore, w.stat_acc);
         YB_LAUNCH_CHECK();
-        tal_stats_kernel<<<1, kTalStatAcc, 0, st>>>(w.stat_acc, w.ticket + 3, grid.n_levels > 0, out_stats);
+        tal_stats_kernel<<<1, kTalStatAcc, 0, st>>>(w.stat_acc, w.ticket + 3, grid.n_levels > 0, out_stats, px);
         YB_LAUNCH_CHECK();
     } else {
         YB_CUDA(cudaMemsetAsync(out_stats, 0, sizeof(float) * 8, st));
+        if (px.world > 0) {                                // a rank without boxes still owes its peers an entry
+            tal_stats_kernel<<<1, kTalStatAcc, 0, st>>>(w.stat_acc, w.ticket + 3, 0, out_stats, px);
+            YB_LAUNCH_CHECK();
+        }
     }
     return YB_OK;
 }
@@ -1104,9 +1124,9 @@ extern "C" size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_tot
 
 extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
                              const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
-                             int gt_total, const yb_tal_params *params, const yb_tal_grid *grid_hint, float *out_stats,
-                             int32_t *out_assigned_gt, float *out_target_score, void *workspace, size_t workspace_bytes,
-                             void *stream) {
+                             int gt_total, const yb_tal_params *params, const yb_tal_grid *grid_hint,
+                             const yb_peer_exchange *peers, float *out_stats, int32_t *out_assigned_gt,
+                             float *out_target_score, void *workspace, size_t workspace_bytes, void *stream) {
     if (int rc = tal_check(preds, workspace, params, dtype, n_images, nc, reg_max, n_anchors, gt_total, "yb_tal_assign"))
         return rc;
     YB_REQUIRE(anchors && strides && gt_offsets && out_stats, "yb_tal_assign: null pointer");
@@ -1116,6 +1136,12 @@ extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc,
         return YB_ERR_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    yb_peer_exchange px;
+    memset(&px, 0, sizeof(px));                            // world = 0: no exchange here (the caller all-reduces out_stats)
+    if (peers != nullptr) {
+        if (int rc = check_peer(peers, "yb_tal_assign")) return rc;
+        px = *peers;
+    }
     TalGrid grid;
     memset(&grid, 0, sizeof(grid));                        // n_levels = 0: no hint, generic scan
     if (grid_hint != nullptr && grid_hint->n_levels > 0) {
@@ -1135,33 +1161,42 @@ extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc,
         const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, params->topk, tal_tile(dtype, vec));
         if (vec)
             return launch_tal_assign<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
-                                               gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score, w, st);
+                                               gt_total, *params, grid, px, out_stats, out_assigned_gt, out_target_score, w, st);
         return launch_tal_assign<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
-                                           gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score, w, st);
+                                           gt_total, *params, grid, px, out_stats, out_assigned_gt, out_target_score, w, st);
     }
     const bool vec = tal_vec_ok<__nv_bfloat16>(preds, nullptr, n_anchors);
     const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, params->topk, tal_tile(dtype, vec));
     if (vec)
         return launch_tal_assign<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
-                                                   gt_offsets, gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score,
+                                                   gt_offsets, gt_total, *params, grid, px, out_stats, out_assigned_gt, out_target_score,
                                                    w, st);
     return launch_tal_assign<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
-                                               gt_offsets, gt_total, *params, grid, out_stats, out_assigned_gt, out_target_score, w,
+                                               gt_offsets, gt_total, *params, grid, px, out_stats, out_assigned_gt, out_target_score, w,
                                                st);
 }
 
 extern "C" int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors, int gt_total,
-                           const yb_tal_params *params, const float *tss_dev, void *grad_preds, float *out_loss,
-                           void *workspace, size_t workspace_bytes, void *stream) {
+                           const yb_tal_params *params, const float *tss_dev, const yb_peer_exchange *peers,
+                           void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream) {
     if (int rc = tal_check(preds, workspace, params, dtype, n_images, nc, reg_max, n_anchors, gt_total, "yb_tal_loss"))
         return rc;
-    YB_REQUIRE(tss_dev && out_loss, "yb_tal_loss: null pointer");
+    YB_REQUIRE((tss_dev || peers) && out_loss, "yb_tal_loss: null pointer");
+    if (peers != nullptr)
+        if (int rc = check_peer(peers, "yb_tal_loss")) return rc;
     if (workspace_bytes < yb_tal_workspace_bytes(n_images, n_anchors, gt_total, dtype, params->topk)) {
         set_error("yb_tal_loss: workspace too small");
         return YB_ERR_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the tile (hence the workspace carving) must be the one yb_tal_assign used: decided by preds only
+    if (peers != nullptr) {
+        // the exchange, consumer side: wait for every rank's entry of this step, average in rank order -> workspace
+        const bool vec_p = dtype == YB_F32 ? tal_vec_ok<float>(preds, nullptr, n_anchors) : tal_vec_ok<__nv_bfloat16>(preds, nullptr, n_anchors);
+        const TalWorkspace wp = carve_tal(workspace, n_images, n_anchors, gt_total, params->topk, tal_tile(dtype, vec_p));
+        if (int rc = launch_peer_wait(*peers, wp.peer_tss, wp.ticket + 4, st)) return rc;
+        tss_dev = wp.peer_tss;
+    }
     if (dtype == YB_F32) {
         const bool vec_a = tal_vec_ok<float>(preds, nullptr, n_anchors);
         const TalWorkspace w = carve_tal(workspace, n_images, n_anchors, gt_total, params->topk, tal_tile(dtype, vec_a));

@@ -301,7 +301,7 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
                    strides: torch.Tensor, num_classes: int, lambda_box: float, lambda_cls: float, lambda_dfl: float,
                    reg_max: int = 16, topk: int = 10, alpha: float = 0.5, beta: float = 6.0, want_grad: bool = True,
                    want_trace: bool = False, sync_normalizer: bool = True, cls_loss: str = "bce",
-                   vfl_alpha: float = 0.75, vfl_gamma: float = 2.0, grid_hint="auto"):
+                   vfl_alpha: float = 0.75, vfl_gamma: float = 2.0, grid_hint="auto", exchange="default"):
     """Task-aligned variant (``yb_tal_assign`` + ``yb_tal_loss``).  Not in the reference: specified by
     ``oracle/tal_oracle.py`` (SURVEY.md §8(a')).
 
@@ -309,6 +309,8 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     process group is initialised and ``sync_normalizer`` is set — the path's one real exchange step.
     ``cls_loss="vfl"`` weights the class term varifocally (``yb_tal_params.vfl``): background cells by
     ``vfl_alpha * sigmoid(x) ** vfl_gamma``, the positive cell of a foreground anchor by its target score.
+    ``exchange``: a ``training.distributed_setup.PeerExchange`` fuses that step into the kernels (peer stores over
+    NVLink + a poll, no collective call); ``"default"`` takes the one ``enable_peer_exchange()`` installed, if any.
     ``grid_hint``: ``"auto"`` (describe the anchors as a pyramid of grids once per size and let the kernels verify it on
     every call), ``None`` (structure-free candidate scan) or a ``_cabi.TalGrid``.  Results never depend on it.
     Returns ``(out_loss (8,) [total, box, cls, dfl, normaliser, #fg, hint rejected, #bad class ids], grad or None, trace)``.
@@ -337,16 +339,21 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     gt_ptr = _cabi.ptr(gt) if gt_total else None
     import ctypes
     hint = _grid_hint_for(anc, st) if isinstance(grid_hint, str) else grid_hint
+    if isinstance(exchange, str):
+        from ..training.distributed_setup import default_peer_exchange
+        exchange = default_peer_exchange()
+    px = exchange.next_step() if (exchange is not None and sync_normalizer) else None
+    px_ref = ctypes.byref(px) if px is not None else None
     params = _cabi.TalParams(int(topk), float(alpha), float(beta), float(lambda_box), float(lambda_cls), float(lambda_dfl),
                              int(cls_loss == "vfl"), float(vfl_alpha), float(vfl_gamma))
     with torch.cuda.device(dev):
         rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
                                _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params),
-                               ctypes.byref(hint) if hint is not None else None, _cabi.ptr(stats),
+                               ctypes.byref(hint) if hint is not None else None, px_ref, _cabi.ptr(stats),
                                _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_tal_assign")
     tss = stats[:1]
-    if sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
+    if px is None and sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
             and torch.distributed.get_world_size() > 1:
         # [sum of target scores, #foreground] -> mean over the ranks, in place: one collective, no extra kernels.
         # Nothing of the step is left to overlap it with: everything that does not need the normaliser has already run.
@@ -360,7 +367,7 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     out = torch.empty(8, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.yb_tal_loss(_cabi.ptr(x), dt, n, num_classes, reg_max, a, gt_total, ctypes.byref(params), _cabi.ptr(tss),
-                             _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
+                             px_ref, _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_tal_loss")
     trace = {"assigned_gt": asg, "target_score": tsc, "stats": stats} if want_trace else {}
     return out, grad, trace

@@ -14,7 +14,7 @@ from typing import Union
 import torch
 import torch.distributed as dist
 
-__all__ = ["reduce_value", "reduce_loss_stats", "shard_batch"]
+__all__ = ["reduce_value", "reduce_loss_stats", "shard_batch", "PeerExchange", "enable_peer_exchange", "default_peer_exchange"]
 
 
 def reduce_value(value: Union[float, torch.Tensor], average: bool = True):
@@ -66,3 +66,78 @@ def shard_batch(n_global: int, rank: int, world: int):
     """Contiguous image range ``[lo, hi)`` of ``rank`` (DistributedSampler/drop_last semantics)."""
     per = n_global // world
     return rank * per, (rank + 1) * per
+
+
+# ----------------------------------------------------------------------------------------------
+# peer exchange of the task-aligned normaliser (csrc/peer.cu): NVLink stores + a poll instead of a collective call
+# ----------------------------------------------------------------------------------------------
+class PeerExchange:
+    """Peer-mapped mailboxes for the one exchange step of the task-aligned loss (the all-reduce of
+    ``[sum of target scores, #foreground]`` between assignment and loss).
+
+    Set-up is collective: every rank of ``group`` must construct it.  Each rank allocates a 2 KB mailbox with plain
+    ``cudaMalloc`` (the C ABI does it: CUDA IPC cannot export memory of PyTorch's caching allocator), the 64-byte IPC
+    handles travel through ``torch.distributed.all_gather_object`` and every rank maps all the others.  After that the
+    exchange needs no host call at all: ``yb_tal_assign``'s last kernel stores into all mailboxes, ``yb_tal_loss``'s first
+    kernel polls the own one.  Single node only (the ranks must be able to map each other's memory); the NCCL
+    all-reduce of ``fused_tal_loss`` remains the general path."""
+
+    def __init__(self, group=None, device=None):
+        import ctypes
+
+        from .. import _cabi
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _cabi.PEER_MAX_WORLD:
+            raise ValueError(f"PeerExchange supports at most {_cabi.PEER_MAX_WORLD} ranks (one NVSwitch domain), got {self.world}")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        lib = _cabi.lib()
+        self._lib, self._own, self._opened = lib, ctypes.c_void_p(), []
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.yb_peer_mailbox_alloc(ctypes.byref(self._own)), "yb_peer_mailbox_alloc")
+            handle = ctypes.create_string_buffer(_cabi.PEER_HANDLE_BYTES)
+            _cabi.check(lib.yb_peer_mailbox_export(self._own, handle), "yb_peer_mailbox_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._struct = _cabi.PeerExchangeStruct()
+            self._struct.world, self._struct.rank, self._struct.seq = self.world, self.rank, 0
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self._struct.mailbox[r] = self._own.value
+                    continue
+                peer = ctypes.c_void_p()
+                _cabi.check(lib.yb_peer_mailbox_open(ctypes.create_string_buffer(h, _cabi.PEER_HANDLE_BYTES), ctypes.byref(peer)),
+                            f"yb_peer_mailbox_open (rank {r})")
+                self._opened.append(peer)
+                self._struct.mailbox[r] = peer.value
+        dist.barrier(group=group)                          # nobody stores before everybody has mapped
+
+    def next_step(self):
+        """The struct for the next exchange (all ranks call this once per step, in lockstep)."""
+        self._struct.seq = (self._struct.seq % 0xFFFFFFFF) + 1
+        return self._struct
+
+    def close(self):
+        for p in self._opened:
+            self._lib.yb_peer_mailbox_close(p)
+        self._opened = []
+        if self._own:
+            self._lib.yb_peer_mailbox_free(self._own)
+            self._own = None
+
+
+_default_exchange = None
+
+
+def enable_peer_exchange(group=None):
+    """Make ``YoloDFLQFLoss(assigner="tal")`` / ``fused_tal_loss`` exchange the normaliser through peer mailboxes
+    instead of an NCCL all-reduce.  Collective: call on every rank, after ``init_process_group``."""
+    global _default_exchange
+    _default_exchange = PeerExchange(group)
+    return _default_exchange
+
+
+def default_peer_exchange():
+    return _default_exchange

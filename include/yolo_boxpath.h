@@ -133,6 +133,29 @@ typedef struct {
  * (x0 + col, y0 + row) in grid units, one stride per level.  The kernels VERIFY the hint against the anchor / stride
  * arrays on every call (bit for bit) and fall back to a structure-free scan when it does not hold — results never
  * depend on it, only the speed of the candidate enumeration does.  out_stats[2] = 1 reports a rejected hint. */
+/* Optional peer exchange of the normaliser: instead of returning between the two calls for a collective, yb_tal_assign's
+ * last kernel stores this rank's [sum of target scores, #foreground] into every rank's mailbox (peer memory over NVLink /
+ * NVSwitch) and yb_tal_loss's first kernel waits on the own mailbox for all `world` entries of step `seq` and averages them
+ * in rank order (every rank gets the bit-identical normaliser) — see csrc/peer.cu.  Replaces the one collective this path
+ * has (the suggested `yolo_allreduce_small(ncclComm_t, ...)` of §8(b) — NCCL's ~35 us floor for an 8-byte
+ * message is what this removes).  Set-up, once per process group, single node:
+ *   yb_peer_mailbox_alloc -> own mailbox;  yb_peer_mailbox_export -> 64-byte CUDA IPC handle to send to the other ranks;
+ *   yb_peer_mailbox_open(handle of rank r) -> mailbox[r] as mapped in this process;  mailbox[rank] = the own one.
+ * `seq` must be the same on all ranks for one step, start at 1 and increase by 1 per step. */
+#define YB_PEER_MAX_WORLD 16
+#define YB_PEER_HANDLE_BYTES 64
+typedef struct {
+    int world, rank;
+    unsigned int seq;
+    void *mailbox[YB_PEER_MAX_WORLD];
+} yb_peer_exchange;                             /* host struct, read during the call */
+size_t yb_peer_mailbox_bytes(void);
+int yb_peer_mailbox_alloc(void **mailbox_out);
+int yb_peer_mailbox_free(void *mailbox);
+int yb_peer_mailbox_export(void *mailbox, void *handle_out_64);
+int yb_peer_mailbox_open(const void *handle_64, void **peer_mailbox_out);
+int yb_peer_mailbox_close(void *peer_mailbox);
+
 #define YB_TAL_MAX_LEVELS 8
 typedef struct {
     int n_levels;                               /* 0: no hint */
@@ -147,12 +170,14 @@ size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_total, int dty
 int yb_tal_assign(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors,
                   const float *anchors, const float *strides, const float *gt, const int32_t *gt_offsets,
                   int gt_total, const yb_tal_params *params, const yb_tal_grid *grid_hint /* or NULL */,
+                  const yb_peer_exchange *peers /* or NULL */,
                   float *out_stats, int32_t *out_assigned_gt, float *out_target_score,
                   void *workspace, size_t workspace_bytes, void *stream);
 
 /* The dense class pass (reads the class logits, writes the whole gradient) and the loss scalars. */
 int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors, int gt_total,
-                const yb_tal_params *params, const float *tss_dev,
+                const yb_tal_params *params, const float *tss_dev /* ignored when peers != NULL */,
+                const yb_peer_exchange *peers /* or NULL: the struct given to yb_tal_assign */,
                 void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------

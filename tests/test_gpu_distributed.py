@@ -1,6 +1,7 @@
 """World-size-2 run of the CUDA path on ONE GPU (both ranks on cuda:0, gloo carrying the CUDA tensors —
 NCCL refuses two ranks on one device): the batch shards, the nearest-centre path exchanges nothing but
-the loss statistics, and the task-aligned path all-reduces its normaliser between its two ABI calls."""
+the loss statistics, and the task-aligned path all-reduces its normaliser between its two ABI calls — once with a
+collective, once through peer-mapped mailboxes (CUDA IPC works between two processes on one device too)."""
 import os
 import socket
 import sys
@@ -52,8 +53,24 @@ def _worker(rank, world, port, out):
     tal = P.YoloDFLQFLoss(num_classes=nc, assigner="tal")
     loss_t, d = tal(x, g, a, s)
     loss_t.backward()
-    torch.save({"red": red, "grad_a": grad_a, "tal_total": loss_t.item(), "tal_dict": d, "tal_norm": tal.last_stats[4].item(),
-                "tal_grad": x.grad.detach().cpu(), "lo": lo, "hi": hi}, out.format(rank))
+    res = {"red": red, "grad_a": grad_a, "tal_total": loss_t.item(), "tal_dict": d, "tal_norm": tal.last_stats[4].item(),
+           "tal_grad": x.grad.detach().cpu(), "lo": lo, "hi": hi}
+
+    # the same exchange through peer-mapped mailboxes (csrc/peer.cu): the assign call's last kernel stores into both
+    # ranks' mailboxes, the loss call's first kernel polls the own one.  Seven steps in a row: the ring of 4 slots wraps.
+    px = DS.enable_peer_exchange()
+    assert DS.default_peer_exchange() is px and px.world == 2
+    peer = []
+    for step in range(7):
+        x.grad = None
+        loss_p, _ = tal(x, g, a, s)
+        loss_p.backward()
+        peer.append((loss_p.item(), tal.last_stats[4].item(), tal.last_stats[5].item()))
+    res.update(peer=peer, peer_grad=x.grad.detach().cpu())
+    torch.cuda.synchronize()
+    dist.barrier()
+    px.close()
+    torch.save(res, out.format(rank))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -92,3 +109,9 @@ def test_two_ranks_shard_the_batch_and_exchange_only_statistics(tmp_path, cuda_d
         ora = T.tal_forward_backward(preds[lo:hi], gts[lo:hi], anchors, strides, nc, tss_override=whole.tss / 2.0)
         assert abs(r[k]["tal_total"] - ora.total.item()) <= 1e-5 * abs(ora.total.item())
         assert (r[k]["tal_grad"] - ora.grad).abs().max().item() <= 1e-5 * ora.grad.abs().max().item()
+        # peer mailboxes: every step gives what the collective gave (normaliser equal up to the summation order)
+        for total, norm_p, nfg in r[k]["peer"]:
+            assert abs(norm_p - norm) <= 1e-6 * norm and abs(total - r[k]["tal_total"]) <= 2e-6 * abs(total)
+        assert (r[k]["peer_grad"] - r[k]["tal_grad"]).abs().max().item() <= 2e-6 * r[k]["tal_grad"].abs().max().item()
+    # ... and both ranks used the BIT-identical normaliser in every step (out_loss[5], the foreground count, is the rank's own)
+    assert [p[1] for p in r[0]["peer"]] == [p[1] for p in r[1]["peer"]]
