@@ -283,6 +283,44 @@ __device__ __forceinline__ f32x2 log1p_neg_small2(f32x2 f) {
     return fma2(mul2(f, f), r, f);
 }
 
+// ---- in-kernel dependencies between the CTAs of ONE launch --------------------------------------
+// A launch may hold CTAs of several roles where a later role consumes what an earlier one produced (the matched-anchor
+// terms need every tile of their image; the per-GT top-k needs the image's decoded boxes).  Producers count themselves
+// off on a per-image counter when their global writes are done; a consumer polls that counter before it starts.
+// Consumers always sit LATER in the grid's linear block order than everything they wait for, and the hardware hands out
+// the blocks of a one-dimensional grid in that order, so whatever a resident consumer waits for is resident or finished:
+// no deadlock.  That dispatch order is an observation, not a documented guarantee, hence the bounded poll: a consumer
+// that waits longer than ~2 s raises *timeout_flag (reported through the entry point's out_loss and raised by the host
+// side) and carries on, so a violated assumption shows up as an error, never as a hang.
+__device__ __forceinline__ void dep_signal(unsigned int *counter) {      // ONE thread, after a __syncthreads()
+#ifndef YB_DEP_NOFENCE                                     // (measurement aid: what the fence costs)
+    __threadfence();                                      // the CTA's writes (ordered before by the barrier) are visible first
+#endif
+    atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dep_wait(const unsigned int *counter, unsigned int target, unsigned int *timeout_flag) {
+    if (ld_acquire_u32(counter) >= target) return;
+    const long long t0 = clock64();
+    unsigned int ns = 64;
+    while (ld_acquire_u32(counter) < target) {
+        __nanosleep(ns);
+        ns = min(ns * 2u, 1024u);
+        if (clock64() - t0 > (4ll << 30)) {               // ~2 s at 2 GHz
+            atomicOr(timeout_flag, 1u);
+            return;
+        }
+    }
+#ifdef YB_DEP_STATS                                        // (measurement aid: how long consumers wait; timeout_flag[5], [6])
+    atomicAdd(timeout_flag + 5, 1u);
+    atomicAdd(timeout_flag + 6, (unsigned int)((clock64() - t0) >> 10));
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

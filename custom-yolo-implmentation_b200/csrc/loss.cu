@@ -1,12 +1,11 @@
 // Fused decode + nearest-centre assignment + DFL/QFL loss + backward (sm_100a).
 //
 // Replaces YoloDFLQFLoss.forward and its autograd backward (src/model/losses.py:93-281).
-// Two launches per step (the second is tiny), every head-output byte read once and every gradient
-// byte written once; the (M x A) distance matrix, the decoded boxes and the dense (A x nc) QFL target
-// never exist:
+// ONE launch per step, every head-output byte read once and every gradient byte written once; the (M x A)
+// distance matrix, the decoded boxes and the dense (A x nc) QFL target never exist:
 //
-//   fused_main_kernel  one launch whose CTAs alternate between two roles (YB_LAYOUT=split runs them as the
-//                      separate kernels assign_kernel / cls_loss_kernel):
+//   fused_main_kernel  CTAs of four roles (YB_LOSS_SPLIT_LAUNCH runs them as the separate kernels assign_kernel /
+//                      cls_loss_kernel / match_kernel):
 //     box role    reads the 4*16 box channels (128-bit loads), decodes each anchor's predicted centre,
 //                 zero-fills the box-channel gradient, drops the GTs that cannot find their nearest centre
 //                 in this tile (extent of the tile's centres vs the distance already published), scans the
@@ -14,11 +13,12 @@
 //                 winners with a 64-bit atomicMax on (distance, anchor) keys.
 //     class role  reads the nc class channels: QFL loss + gradient of every cell for target 0 (all but
 //                 <= one cell per GT), per-CTA partial sums.  Independent of the matching.
-//   match_kernel     one half-warp per GT: gathers the 64 logits of the matched anchor, DFL loss and its
-//                    gradient, IoU soft target (reference formula, slip included) and the gradient
-//                    that flows through it, duplicate-anchor resolution; corrects the one positive
-//                    QFL cell of each matched anchor (loss delta + gradient).  Its last CTA (ticket)
-//                    turns the per-image accumulators into the loss scalars.
+//     match role  one half-warp per GT, after every tile of the GT's image has counted itself off (in-kernel
+//                 dependency, common.cuh): gathers the 64 logits of the matched anchor, DFL loss and its
+//                 gradient, IoU soft target (reference formula, slip included) and the gradient that flows
+//                 through it, duplicate-anchor resolution; corrects the one positive QFL cell of each matched
+//                 anchor (loss delta + gradient); the anchor's 64 box-gradient values go out as whole 32-byte sectors.
+//     reducer     the last CTA: waits for every image, turns the per-image accumulators into the loss scalars.
 // Partial sums (one per class-role CTA, three per GT) are added into per-image 64-bit FIXED-POINT
 // accumulators (2^-32 resolution) with integer atomics: integer addition is associative, so the loss is
 // run-to-run bit-identical whatever the order in which CTAs finish, and nothing has to be re-read.
@@ -62,6 +62,15 @@ namespace yb {
 #ifndef YB_COARSE_FIRST
 #define YB_COARSE_FIRST 1
 #endif
+#ifndef YB_MATCH_MAX_CTAS
+#define YB_MATCH_MAX_CTAS 64
+#endif
+#ifndef YB_MATCH_SEPARATE             // 1: match_kernel as a launch of its own after fused_main_kernel (measurement aid)
+#define YB_MATCH_SEPARATE 0
+#endif
+#ifndef YB_MATCH_WHOLE_SECTORS
+#define YB_MATCH_WHOLE_SECTORS 1
+#endif
 constexpr int kScanUnroll = YB_SCAN_UNROLL;
 constexpr int kAssignThreads = YB_ASSIGN_THREADS;
 constexpr int kClsThreads = YB_CLS_THREADS;
@@ -72,9 +81,11 @@ constexpr int kAccDfl = 16, kAccDcls = 17, kAccWin = 18, kAccPerImage = 20;
 constexpr double kFixScale = 4294967296.0;   // 2^32
 
 struct LossWorkspace {
-    unsigned int *ticket;          // [16] [0] match_kernel ticket, [1] non-finite partial seen, [2] class ids out of range } zeroed
-    unsigned long long *acc;       // [N * kAccPerImage] fixed-point sums: 16 x class part, DFL, QFL cell correction, winners } every
-    unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys                                           } call
+    unsigned int *ticket;          // [16] [0] match_kernel ticket, [1] non-finite partial seen, [2] class ids out of range, } zeroed
+                                   //      [3] a consumer CTA timed out (common.cuh::dep_wait)                               } every
+    unsigned int *done;            // [N] CTAs of fused_main_kernel that have finished with the image                        } call
+    unsigned long long *acc;       // [N * kAccPerImage] fixed-point sums: 16 x class part, DFL, QFL cell correction, winners }
+    unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys                                           }
     int *gt_img;                   // [gt_total] image of each GT (written by the box role, read by match_kernel)
     size_t zero_bytes;
     size_t total_bytes;
@@ -86,6 +97,8 @@ static LossWorkspace carve(void *base, int n_images, int gt_total) {
     size_t off = 0;
     w.ticket = reinterpret_cast<unsigned int *>(p + off);
     off += 64;
+    w.done = reinterpret_cast<unsigned int *>(p + off);
+    off += round_up(sizeof(unsigned int) * (size_t)n_images, 64);
     w.acc = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)n_images * kAccPerImage, 64);
     w.best = reinterpret_cast<unsigned long long *>(p + off);
@@ -477,125 +490,144 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// one HALF-warp per GT (8 GTs per CTA); the grid has at least one CTA even without GTs, because the
-// last CTA to finish (ticket) reduces the per-image accumulators in a fixed order -> 8 loss scalars
+// One HALF-warp per GT; all 32 lanes of a warp call this together (the two halves may serve different images).
+// `m` is the GT's index within image n (of m_img > 0 GTs starting at row g_begin); an idle half (live == false) walks
+// through the same shuffles on the image's last GT and writes nothing.
 template <typename T>
-__global__ void __launch_bounds__(kMatchThreads, 6)
-match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
-             const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
-             const int *__restrict__ gt_off, const int *__restrict__ gt_img, int gt_total,
-             const unsigned long long *__restrict__ best, float k_dfl_num, float k_cls, float lambda_cls, float lambda_dfl,
-             T *__restrict__ grad, unsigned long long *__restrict__ acc, unsigned int *__restrict__ ticket,
-             int *__restrict__ out_idx, float *__restrict__ out_iou, float *__restrict__ out_loss,
-             float *__restrict__ out_per_image) {
+__device__ __forceinline__ void match_gt(const T *__restrict__ preds, int n, int g_begin, int m_img, int m, bool live, int n_ch,
+                                         int n_anchors, int nc, const float *__restrict__ anchors,
+                                         const float *__restrict__ strides, const float *__restrict__ gt,
+                                         const unsigned long long *best, float k_dfl_num, float k_cls, T *grad,
+                                         bool whole_sectors, unsigned long long *acc, unsigned int *ticket,
+                                         int *__restrict__ out_idx, float *__restrict__ out_iou) {
+    constexpr int SEC = 32 / (int)sizeof(T);               // anchors per 32-byte sector of a gradient row
     const int bin = threadIdx.x & 15;
-    const int g_raw = (blockIdx.x * kMatchThreads + threadIdx.x) >> 4;
-    const bool warp_has_work = ((blockIdx.x * kMatchThreads + (threadIdx.x & ~31)) >> 4) < gt_total;
-    if (warp_has_work) {                                       // warp-uniform
-        const bool live = g_raw < gt_total;                    // the second half of the last warp may be idle
-        const int g = live ? g_raw : gt_total - 1;             // ... but must walk through the same shuffles
-        const int n = __ldg(gt_img + g);
-        const int g_begin = __ldg(gt_off + n);
-        const int m_img = __ldg(gt_off + n + 1) - g_begin;
-        const int m = g - g_begin;
-        const T *img = preds + (size_t)n * n_ch * n_anchors;
-        auto idx_of = [&](int mm) {
-            const unsigned long long inv = best[g_begin + mm];
-            return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
-        };
-        const int idx = idx_of(m);
-        const float k_dfl = k_dfl_num / (float)m_img;          // lambda_dfl / (N * 4 * M)
+    const int g = g_begin + m;
+    const T *img = preds + (size_t)n * n_ch * n_anchors;
+    auto idx_of = [&](int mm) {
+        // a plain (L1-cached) load: every CTA of the image scans the same few hundred keys.  Final by now, and ordered
+        // after the producers' atomics by the acquire of dep_wait (or by the kernel boundary); never the .nc path,
+        // which is only defined for data nobody writes during the launch
+        const unsigned long long inv = best[g_begin + mm];
+        return inv == 0ull ? 0 : (int)(unsigned int)(~inv & 0xffffffffull);   // no finite distance -> anchor 0
+    };
+    const int idx = idx_of(m);
+    const float k_dfl = k_dfl_num / (float)m_img;          // lambda_dfl / (N * 4 * M)
 
-        // the gathers (DRAM latency) are issued first; the duplicate search below runs in their shadow
-        AnchorTerms at;
+    // the gathers (DRAM latency) are issued first; the duplicate search below runs in their shadow
+    AnchorTerms at;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) at.z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
-        const float *g5 = gt + (size_t)g * 5;
-        const float gcx = __ldg(g5 + 0), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
-        const int cls_raw = (int)__ldg(g5 + 4);                                        // .long(): truncation
-        const int cls = min(max(cls_raw, 0), nc - 1);          // memory-safe; the violation itself is reported below
-        const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
-        at.ax = __ldg(anchors + idx); at.ay = __ldg(anchors + n_anchors + idx); at.s = __ldg(strides + idx);
+    for (int k = 0; k < 4; ++k) at.z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
+    const float *g5 = gt + (size_t)g * 5;
+    const float gcx = __ldg(g5 + 0), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
+    const int cls_raw = (int)__ldg(g5 + 4);                                        // .long(): truncation
+    const int cls = min(max(cls_raw, 0), nc - 1);          // memory-safe; the violation itself is reported below
+    const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
+    at.ax = __ldg(anchors + idx); at.ay = __ldg(anchors + n_anchors + idx); at.s = __ldg(strides + idx);
 
-        // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
-        // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
-        int first = m, last = m, n_later = 0;
-        for (int mm = bin; mm < m_img; mm += 16) {
-            if (idx_of(mm) == idx) {
-                first = min(first, mm);
-                last = max(last, mm);
-                n_later += mm > m ? 1 : 0;
-            }
+    // Which GTs of this image share my anchor?  owner = lowest such m (writes the summed gradient),
+    // winner = highest (its class row is the anchor's QFL target: "last write wins", losses.py:261).
+    // ... and does another GT's anchor share a 32-byte sector of the gradient rows with mine (a sector mate)?
+    int first = m, last = m, n_later = 0, mate = 0;
+    for (int mm = bin; mm < m_img; mm += 16) {
+        const int o = idx_of(mm);
+        if (o == idx) {
+            first = min(first, mm);
+            last = max(last, mm);
+            n_later += mm > m ? 1 : 0;
+        } else if (o / SEC == idx / SEC) {
+            mate = 1;
         }
+    }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-            n_later += __shfl_xor_sync(0xffffffffu, n_later, o);
-        }
+    for (int o = 8; o > 0; o >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        n_later += __shfl_xor_sync(0xffffffffu, n_later, o);
+        mate |= __shfl_xor_sync(0xffffffffu, mate, o);
+    }
 
-        anchor_softmax(at);
-        const GtTerms mine = gt_terms(at, z_cls, gcx, gcy, gw, gh, k_dfl, k_cls);
-        const bool winner = (last == m);
-        T *gimg = grad ? grad + (size_t)n * n_ch * n_anchors : nullptr;
-        if (live && bin == 0) {
-            unsigned long long *a_img = acc + (size_t)n * kAccPerImage;
-            acc_add(a_img + kAccDfl, mine.dfl, ticket);
-            if (winner) {
-                acc_add(a_img + kAccDcls, mine.iou * mine.cell_delta, ticket);
-                atomicAdd(a_img + kAccWin, 1ull);
-            }
-            if (cls_raw != cls) atomicAdd(ticket + 2, 1u);     // the reference's scatter_ raises here (losses.py:260)
-            if (out_idx) out_idx[g] = idx;
-            if (out_iou) out_iou[g] = mine.iou;
-            if (winner && gimg) {
-                // the anchor's one positive QFL cell: overwrite the target-0 gradient the class pass wrote
-                store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
-                                 mine.cell_grad0 + mine.iou * mine.cell_grad1);
-            }
+    anchor_softmax(at);
+    const GtTerms mine = gt_terms(at, z_cls, gcx, gcy, gw, gh, k_dfl, k_cls);
+    const bool winner = (last == m);
+    T *gimg = grad ? grad + (size_t)n * n_ch * n_anchors : nullptr;
+    if (live && bin == 0) {
+        unsigned long long *a_img = acc + (size_t)n * kAccPerImage;
+        acc_add(a_img + kAccDfl, mine.dfl, ticket);
+        if (winner) {
+            acc_add(a_img + kAccDcls, mine.iou * mine.cell_delta, ticket);
+            atomicAdd(a_img + kAccWin, 1ull);
         }
-        // the owner adds the terms of the later GTs that share its anchor (rare); the trip count is made
-        // warp-uniform because gt_terms shuffles across the whole warp
-        float sum[4] = {mine.g[0], mine.g[1], mine.g[2], mine.g[3]};
-        const bool owner = live && first == m && gimg != nullptr;
-        int todo = owner ? n_later : 0;
-        const int trips = max(todo, __shfl_xor_sync(0xffffffffu, todo, 16));
-        int cur = m;
-        for (int it = 0; it < trips; ++it) {
-            int nxt = 0x7fffffff;
-            if (it < todo)
-                for (int mm = bin; mm < m_img; mm += 16)
-                    if (mm > cur && idx_of(mm) == idx) nxt = min(nxt, mm);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
-            const bool has = nxt != 0x7fffffff;
-            const float *o5 = gt + (size_t)(g_begin + (has ? nxt : m)) * 5;
-            const int ocls = min(max((int)__ldg(o5 + 4), 0), nc - 1);
-            const float oz = load_as_float(img + (size_t)(4 * kRegMax + ocls) * n_anchors + idx);
-            const GtTerms o = gt_terms(at, oz, __ldg(o5 + 0), __ldg(o5 + 1), __ldg(o5 + 2), __ldg(o5 + 3), k_dfl, k_cls);
-            if (has) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) sum[k] += o.g[k];
-                cur = nxt;
-            }
+        if (cls_raw != cls) atomicAdd(ticket + 2, 1u);     // the reference's scatter_ raises here (losses.py:260)
+        if (out_idx) out_idx[g] = idx;
+        if (out_iou) out_iou[g] = mine.iou;
+        if (winner && gimg) {
+            // the anchor's one positive QFL cell: overwrite the target-0 gradient the class pass wrote
+            store_from_float(gimg + (size_t)(4 * kRegMax + cls) * n_anchors + idx,
+                             mine.cell_grad0 + mine.iou * mine.cell_grad1);
         }
-        if (owner) {
+    }
+    // the owner adds the terms of the later GTs that share its anchor (rare); the trip count is made
+    // warp-uniform because gt_terms shuffles across the whole warp
+    float sum[4] = {mine.g[0], mine.g[1], mine.g[2], mine.g[3]};
+    const bool owner = live && first == m && gimg != nullptr;
+    int todo = owner ? n_later : 0;
+    const int trips = max(todo, __shfl_xor_sync(0xffffffffu, todo, 16));
+    int cur = m;
+    for (int it = 0; it < trips; ++it) {
+        int nxt = 0x7fffffff;
+        if (it < todo)
+            for (int mm = bin; mm < m_img; mm += 16)
+                if (mm > cur && idx_of(mm) == idx) nxt = min(nxt, mm);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+        const bool has = nxt != 0x7fffffff;
+        const float *o5 = gt + (size_t)(g_begin + (has ? nxt : m)) * 5;
+        const int ocls = min(max((int)__ldg(o5 + 4), 0), nc - 1);
+        const float oz = load_as_float(img + (size_t)(4 * kRegMax + ocls) * n_anchors + idx);
+        const GtTerms o = gt_terms(at, oz, __ldg(o5 + 0), __ldg(o5 + 1), __ldg(o5 + 2), __ldg(o5 + 3), k_dfl, k_cls);
+        if (has) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sum[k] += o.g[k];
+            cur = nxt;
+        }
+    }
+    if (owner) {
+        // The box role left zeros in these rows, so every neighbour of the anchor inside its 32-byte sector is known to be
+        // zero unless a sector mate exists: the whole sector is written with one 256-bit store and DRAM never has to be
+        // read to merge a 4-byte write into it (the read-modify-write was half of this step's scattered DRAM traffic).
+        if (whole_sectors && !mate) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                const int pos = idx % SEC;
+                if (sizeof(T) == 4) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = i == pos ? __float_as_uint(sum[k]) : 0u;
+                } else {
+                    const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(sum[k])) << ((pos & 1) * 16);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = i == (pos >> 1) ? h : 0u;
+                }
+                T *p = gimg + (size_t)(k * kRegMax + bin) * n_anchors + (idx - pos);
+                asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                             "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                             : "memory");
+            }
+        } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) store_from_float(gimg + (size_t)(k * kRegMax + bin) * n_anchors + idx, sum[k]);
         }
     }
+}
 
-    // ---- the last CTA to finish: per-image terms, then the batch means, in a fixed order -------
-    __shared__ bool s_last;
+// per-image terms, then the batch means, in a fixed order -> 8 loss scalars.  One whole CTA of kMatchThreads threads,
+// after every accumulator of the call is final.
+__device__ __forceinline__ void final_reduce(int n_images, int n_anchors, const int *__restrict__ gt_off,
+                                             const unsigned long long *acc, const unsigned int *ticket, float lambda_cls,
+                                             float lambda_dfl, float *__restrict__ out_loss,
+                                             float *__restrict__ out_per_image) {
     __shared__ double s_d[kMatchThreads / 32], s_c[kMatchThreads / 32], s_f[kMatchThreads / 32];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double d = 0.0, c = 0.0, f = 0.0;
     for (int b = threadIdx.x; b < n_images; b += kMatchThreads) {
@@ -624,13 +656,50 @@ match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors,
         float mean_dfl = (float)(dd / (double)n_images);              // N counts images without GT (losses.py:271)
         float mean_cls = (float)(cc / (double)n_images);
         if (__ldcg(ticket + 1) != 0u) mean_cls = __int_as_float(0x7fc00000);   // a non-finite partial: NaN, as the reference
-        out_loss[0] = lambda_dfl * mean_dfl + lambda_cls * mean_cls;  // losses.py:275
+        const unsigned int stalled = __ldcg(ticket + 3);              // a consumer CTA gave up waiting (common.cuh::dep_wait)
+        out_loss[0] = stalled ? __int_as_float(0x7fc00000) : lambda_dfl * mean_dfl + lambda_cls * mean_cls;  // losses.py:275
         out_loss[1] = mean_dfl;
         out_loss[2] = mean_cls;
         out_loss[3] = (float)ff;
-        out_loss[4] = out_loss[5] = out_loss[6] = 0.f;
+        out_loss[4] = out_loss[5] = 0.f;
+        out_loss[6] = (float)stalled;
         out_loss[7] = (float)__ldcg(ticket + 2);                      // GT rows whose class id is outside [0, nc)
     }
+}
+
+// the split launch's third kernel (YB_LOSS_SPLIT_LAUNCH; the fused launch runs the same code as a role of
+// fused_main_kernel): 8 GTs per CTA; the grid has at least one CTA even without GTs, because the last CTA to finish
+// (ticket) writes the loss scalars
+template <typename T>
+__global__ void __launch_bounds__(kMatchThreads, 6)
+match_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
+             const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
+             const int *__restrict__ gt_off, const int *__restrict__ gt_img, int gt_total,
+             const unsigned long long *best, float k_dfl_num, float k_cls, float lambda_cls, float lambda_dfl,
+             T *__restrict__ grad, int whole_sectors, unsigned long long *__restrict__ acc, unsigned int *__restrict__ ticket,
+             int *__restrict__ out_idx, float *__restrict__ out_iou, float *__restrict__ out_loss,
+             float *__restrict__ out_per_image) {
+    const int g_raw = (blockIdx.x * kMatchThreads + threadIdx.x) >> 4;
+    const bool warp_has_work = ((blockIdx.x * kMatchThreads + (threadIdx.x & ~31)) >> 4) < gt_total;
+    if (warp_has_work) {                                       // warp-uniform
+        const bool live = g_raw < gt_total;                    // the second half of the last warp may be idle
+        const int g = live ? g_raw : gt_total - 1;             // ... but must walk through the same shuffles
+        const int n = __ldg(gt_img + g);
+        const int g_begin = __ldg(gt_off + n);
+        const int m_img = __ldg(gt_off + n + 1) - g_begin;
+        match_gt<T>(preds, n, g_begin, m_img, g - g_begin, live, n_ch, n_anchors, nc, anchors, strides, gt, best, k_dfl_num,
+                    k_cls, grad, whole_sectors != 0, acc, ticket, out_idx, out_iou);
+    }
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    final_reduce(n_images, n_anchors, gt_off, acc, ticket, lambda_cls, lambda_dfl, out_loss, out_per_image);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -769,44 +838,98 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
                                 grad, acc, flags);
 }
 
-// One launch for both big passes: CTAs alternate between the box role (assign_body) and the class role
-// (cls_body, YB_CLS_CSPLIT CTAs per tile), so every SM holds a mix of the latency-bound decode/scan
-// CTAs and the streaming class CTAs and the two underused halves of the machine fill each other.
+// One launch for the whole step.  Its CTAs take one of four roles:
+//   box role    (assign_body)  } consecutive CTAs alternate between the two (YB_CLS_CSPLIT class CTAs per box CTA), so every
+//   class role  (cls_body)     } SM holds a mix of the latency-bound decode/scan CTAs and the streaming class CTAs
+//   match role  (match_gt)     the per-GT terms of ONE image, once every box and class CTA of that image has counted itself
+//                              off (common.cuh: in-kernel dependencies)
+//   reducer     (final_reduce) the grid's last CTA: waits for every image, then writes the loss scalars.
+// Block order: [skew box CTAs] [coarse tiles, image-major] [fine tiles, image-major] [match CTAs, image-major] [reducer].
+// The match CTAs become resident while the last tiles are still streaming and start on the early images at once: the
+// step no longer pays a kernel boundary, a second launch and a reduction launch for them (36 us -> 21 us of a 255 us
+// step at cfg2).  Measured and not kept: match CTAs of image i placed right behind the tiles of image i + lag, so that
+// they run UNDER the streaming roles -- 250 / 244 / 240 us per step for a lag of 1 / 4 / all machine-loads of CTAs: the
+// scattered sector reads and writes of the match role cost the same DRAM time wherever they run, and more when they
+// break into the streams' open rows.
+struct FusedPlan {
+    int n_tiles, coarse, skew;     // coarse < 0: pruning (and the coarse-first order) off
+    int match_ctas;                // match CTAs per image (0: no GT in the whole batch); < 0: match_kernel is launched separately
+                                   // (no match / reducer CTAs here and nobody counts itself off)
+    int whole_sectors;             // gradient rows may be patched with whole 32-byte sectors (match_gt)
+};
 #ifndef YB_FUSED_MINBLOCKS           // measured on B200: 6 resident CTAs/SM is best for fp32 rows, 5 for bf16 rows
 #define YB_FUSED_MINBLOCKS 0
 #endif
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kAssignThreads, YB_FUSED_MINBLOCKS ? YB_FUSED_MINBLOCKS : (VW == 8 ? 5 : 6))
-fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc, int n_tiles, int coarse,
-                  int skew, const float *__restrict__ anchors,
-                  const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
-                  unsigned long long *__restrict__ best, int *__restrict__ gt_img, float k_cls, T *__restrict__ grad,
-                  unsigned long long *__restrict__ acc, unsigned int *__restrict__ flags) {
-    static_assert(kAssignThreads == kClsThreads, "roles share one block shape");
+fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc, const FusedPlan plan,
+                  const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
+                  const int *__restrict__ gt_off, unsigned long long *best, int *__restrict__ gt_img, float k_cls,
+                  float k_dfl_num, float lambda_cls, float lambda_dfl, T *grad, unsigned long long *acc,
+                  unsigned int *flags, unsigned int *done, int *__restrict__ out_idx, float *__restrict__ out_iou,
+                  float *__restrict__ out_loss, float *__restrict__ out_per_image) {
+    static_assert(kAssignThreads == kClsThreads && kAssignThreads == kMatchThreads, "roles share one block shape");
     constexpr int ROLES = 1 + YB_CLS_CSPLIT;
-    // Launch order: first the `coarse` LAST tiles of every image (image-major), then the other tiles
-    // (image-major again).  Roles of a tile stay adjacent, so every SM holds a mix of box and class CTAs.
-    const bool prune = coarse >= 0;                        // coarse < 0: YB_LOSS_NO_PRUNE (exactness tests)
-    coarse = max(coarse, 0);
+    const int n_tiles = plan.n_tiles, skew = plan.skew;
+    const bool prune = plan.coarse >= 0;                   // coarse < 0: YB_LOSS_NO_PRUNE (exactness tests)
+    const int coarse = max(plan.coarse, 0);
+    const int n_groups = n_tiles * n_images;
+    const unsigned int tile_ctas = (unsigned int)(n_tiles * ROLES);      // box + class CTAs of one image
+    const bool chained = plan.match_ctas >= 0;             // the match role and the reducer are part of this launch
     // A tile's box CTA lives about three times as long as one of its class CTAs, so it is launched `skew` tile
     // groups AHEAD of them: the first `skew` blocks are the box CTAs of the first groups, and the last groups of
-    // the grid carry class CTAs only -- the grid drains on short CTAs instead of waiting for a few long ones.
-    int group, role, image, tile;
+    // the grid carry class CTAs only.
+    int group = -1, role = 0, match_image = -1, match_j = 0;
+    bool reducer = false;
     {
-        const int n_groups = n_tiles * n_images;
         int id = blockIdx.x;
         if (id < skew) {
             group = id;
-            role = 0;
         } else {
             id -= skew;
-            group = id / ROLES;
-            role = id - group * ROLES;
-            if (role == 0) {
-                group += skew;
-                if (group >= n_groups) return;             // the box CTAs of the last groups went out earlier
+            if (id < n_groups * ROLES) {
+                group = id / ROLES;
+                role = id - group * ROLES;
+                if (role == 0) {
+                    group += skew;
+                    if (group >= n_groups) return;         // the box CTAs of the last groups went out earlier
+                }
+            } else {
+                id -= n_groups * ROLES;                    // only reached when chained
+                if (id < n_images * plan.match_ctas) {
+                    match_image = id / plan.match_ctas;
+                    match_j = id - match_image * plan.match_ctas;
+                } else {
+                    reducer = true;
+                }
             }
         }
+    }
+    if (reducer) {
+        for (int b = threadIdx.x; b < n_images; b += kAssignThreads)
+            dep_wait(done + b, tile_ctas + (unsigned int)plan.match_ctas, flags + 3);
+        __syncthreads();
+        final_reduce(n_images, n_anchors, gt_off, acc, flags, lambda_cls, lambda_dfl, out_loss, out_per_image);
+        return;
+    }
+    int image;
+    if (match_image >= 0) {
+        image = match_image;
+        const int g_begin = __ldg(gt_off + image), m_img = __ldg(gt_off + image + 1) - g_begin;
+        if (m_img > 0) {                                    // uniform per CTA
+            if (threadIdx.x == 0) dep_wait(done + image, tile_ctas, flags + 3);
+            __syncthreads();
+            // 8 GTs (half-warps) per pass; CTA j of the image takes passes j, j + match_ctas, ...
+            for (int base = match_j * (kMatchThreads / 16); base < m_img; base += plan.match_ctas * (kMatchThreads / 16)) {
+                const int m_raw = base + (threadIdx.x >> 4);
+                if (base + ((threadIdx.x & ~31) >> 4) < m_img)                       // warp-uniform
+                    match_gt<T>(preds, image, g_begin, m_img, min(m_raw, m_img - 1), m_raw < m_img, n_ch, n_anchors, nc, anchors,
+                                strides, gt, best, k_dfl_num, k_cls, WRITE_GRAD ? grad : nullptr, plan.whole_sectors != 0, acc, flags,
+                                out_idx, out_iou);
+            }
+        }
+    } else {
+        int tile;
         const int groups_c = coarse * n_images;
         if (group < groups_c) {
             image = group / coarse;
@@ -816,13 +939,16 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
             image = gf / fine;
             tile = gf - image * fine;
         }
+        if (role == 0)
+            assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
+                               WRITE_GRAD ? grad : nullptr, prune);
+        else
+            cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
+                                        acc, flags);
     }
-    if (role == 0)
-        assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
-                           WRITE_GRAD ? grad : nullptr, prune);
-    else
-        cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
-                                    acc, flags);
+    if (!chained) return;
+    __syncthreads();
+    if (threadIdx.x == 0) dep_signal(done + image);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -860,7 +986,6 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
                        float lambda_dfl, T *grad, float *out_loss, int32_t *out_idx, float *out_iou,
                        float *out_per_image, const LossWorkspace &w, unsigned flags, void *const *stage_events,
                        cudaStream_t st) {
-    (void)gmax;
     const int n_ch = 4 * kRegMax + nc;
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
     const float k_dfl_num = lambda_dfl / ((float)n_images * 4.f);
@@ -868,6 +993,9 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     static_assert(TILE_A == TILE_C, "both roles tile the anchors identically");
     const int cls_split = YB_CLS_CSPLIT;
     const int n_tiles = (n_anchors + TILE_C - 1) / TILE_C;
+    // whole-sector patches of the gradient rows need 32-byte aligned rows (match_gt)
+    const int whole_sectors = YB_MATCH_WHOLE_SECTORS && grad != nullptr && n_anchors % (32 / (int)sizeof(T)) == 0 &&
+                              (reinterpret_cast<uintptr_t>(grad) & 31u) == 0;
     YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(stage_events, 0, st)) return rc;
     if (!(flags & YB_LOSS_SPLIT_LAUNCH)) {
@@ -875,23 +1003,41 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         // hold 23.8 % of a three-level grid's anchors), whose anchors lie within a cell or two of every GT --
         // then the rest, where assign_body prunes every (GT, tile) pair that cannot beat the distance already
         // published in `best`.  The result never depends on what has been published (see assign_body).
-        int coarse = 0;
+        FusedPlan plan;
+        plan.n_tiles = n_tiles;
+        plan.coarse = 0;
 #if YB_COARSE_FIRST && YB_ASSIGN_PRUNE
-        if (gt_total > 0 && n_tiles >= 4) coarse = (n_tiles * YB_COARSE_FRAC256 + 255) / 256;   // ceil(0.238 n_tiles)
+        if (gt_total > 0 && n_tiles >= 4) plan.coarse = (n_tiles * YB_COARSE_FRAC256 + 255) / 256;   // ceil(0.238 n_tiles)
 #endif
-        if (flags & YB_LOSS_NO_PRUNE) coarse = -1;      // pruning (and the coarse-first order) off: the exactness tests compare both
-        const int skew = (int)std::min<long long>(YB_BOX_SKEW, (long long)n_tiles * n_images);
-        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + skew;
+        if (flags & YB_LOSS_NO_PRUNE) plan.coarse = -1;      // pruning (and the coarse-first order) off: the exactness tests compare both
+        plan.skew = (int)std::min<long long>(YB_BOX_SKEW, (long long)n_tiles * n_images);
+        // match CTAs per image: enough for the largest image in one pass when the caller's gmax is right (8 GTs per
+        // CTA); an image with more GTs than that takes further passes, so the result never depends on gmax
+        const int g_hint = gmax > 0 ? gmax : (gt_total + n_images - 1) / n_images;
+        plan.match_ctas = gt_total > 0 ? std::min(std::max((g_hint + 7) / 8, 1), YB_MATCH_MAX_CTAS) : 0;
+        if (YB_MATCH_SEPARATE) plan.match_ctas = -1;
+        plan.whole_sectors = whole_sectors;
+        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + plan.skew +
+                                 (plan.match_ctas < 0 ? 0 : (long long)plan.match_ctas * n_images + 1);
         YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
         if (grad != nullptr)
             fused_main_kernel<T, VW, true><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, skew, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls,
-                grad, w.acc, w.ticket);
+                preds, n_images, n_ch, n_anchors, nc, plan, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, k_dfl_num,
+                lambda_cls, lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
         else
             fused_main_kernel<T, VW, false><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, n_tiles, coarse, skew, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls,
-                grad, w.acc, w.ticket);
+                preds, n_images, n_ch, n_anchors, nc, plan, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, k_dfl_num,
+                lambda_cls, lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
         YB_LAUNCH_CHECK();
+        if (int rc = stage_mark(stage_events, 1, st)) return rc;
+        if (plan.match_ctas < 0) {
+            const int per_cta = kMatchThreads / 16;
+            const int mblocks = std::max(1, (gt_total + per_cta - 1) / per_cta);
+            match_kernel<T><<<mblocks, kMatchThreads, 0, st>>>(
+                preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.gt_img, gt_total, w.best, k_dfl_num, k_cls,
+                lambda_cls, lambda_dfl, grad, whole_sectors, w.acc, w.ticket, out_idx, out_iou, out_loss, out_per_image);
+            YB_LAUNCH_CHECK();
+        }
     } else {
         // two launches (profiling the roles separately).  Stream-level overlap of the two was measured and does
         // not help: the first kernel's CTAs fill every SM, so the second only starts as the first drains.
@@ -904,14 +1050,12 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         else
             cls_loss_kernel<T, VW, false><<<grid, kClsThreads, 0, st>>>(preds, n_ch, n_anchors, nc, k_cls, grad, w.acc, w.ticket);
         YB_LAUNCH_CHECK();
-    }
-    if (int rc = stage_mark(stage_events, 1, st)) return rc;
-    {
+        if (int rc = stage_mark(stage_events, 1, st)) return rc;
         const int per_cta = kMatchThreads / 16;                                  // one half-warp per GT
         const int blocks = std::max(1, (gt_total + per_cta - 1) / per_cta);       // >= 1: its last CTA writes the loss
         match_kernel<T><<<blocks, kMatchThreads, 0, st>>>(
             preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off, w.gt_img, gt_total, w.best, k_dfl_num, k_cls,
-            lambda_cls, lambda_dfl, grad, w.acc, w.ticket, out_idx, out_iou, out_loss, out_per_image);
+            lambda_cls, lambda_dfl, grad, whole_sectors, w.acc, w.ticket, out_idx, out_iou, out_loss, out_per_image);
         YB_LAUNCH_CHECK();
     }
     if (int rc = stage_mark(stage_events, 2, st)) return rc;

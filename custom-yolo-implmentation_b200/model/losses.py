@@ -146,11 +146,11 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
                want_grad: bool = True, want_trace: bool = False, flags: int = 0, stage_events=None):
     """One call of ``yb_loss_fwd_bwd``.  Returns ``(out_loss (8,), grad or None, trace dict)``.
 
-    ``out_loss`` = [total, mean DFL, mean QFL, #matched anchors, 0, 0, 0, #GT rows with a class id outside
-    [0, nc)] on the device.  ``trace`` (``want_trace``) holds the per-GT matched anchor / IoU and per-image
+    ``out_loss`` = [total, mean DFL, mean QFL, #matched anchors, 0, 0, in-kernel dependency timed out (never, see
+    csrc/common.cuh), #GT rows with a class id outside [0, nc)] on the device.  ``trace`` (``want_trace``) holds the per-GT matched anchor / IoU and per-image
     loss terms the parity tests compare against the oracle.  ``flags``: ``_cabi.YB_LOSS_NO_PRUNE`` /
     ``YB_LOSS_SPLIT_LAUNCH`` (test / profiling aids).  ``stage_events``: three ``torch.cuda.Event(enable_timing=True)``
-    recorded around the two launches (bench.py's roofline leg).
+    recorded around the launch(es) (bench.py's roofline leg).
     """
     _cabi.require_cuda(preds, "preds")
     if preds.dim() != 3:
@@ -213,6 +213,13 @@ def _raise_on_bad_class(n_bad: float, num_classes: int):
     # the reference's scatter_ raises on these (src/model/losses.py:260); the kernels clamp and count
     if n_bad:
         raise RuntimeError(f"index out of range: {int(n_bad)} ground-truth row(s) carry a class id outside [0, {num_classes})")
+
+
+def _raise_on_stall(flag: float, who: str):
+    # a consumer CTA of the fused launch gave up waiting for its producers (csrc/common.cuh::dep_wait): the block
+    # dispatch order the launch relies on did not hold -- fail loudly, the loss of that call is NaN
+    if flag:
+        raise RuntimeError(f"{who}: an in-kernel dependency timed out (blocks were not dispatched in index order)")
 
 
 class _FusedLoss(torch.autograd.Function):
@@ -471,6 +478,7 @@ class YoloDFLQFLoss(nn.Module):
         stats = self.last_stats = holder[0]
         host = stats.tolist()                           # one D2H copy (the reference does three .item())
         _raise_on_bad_class(host[7], self.num_classes)
+        _raise_on_stall(host[6], "yb_loss_fwd_bwd")
         return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2]}
 
 

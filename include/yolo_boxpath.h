@@ -55,10 +55,13 @@ long long yb_launch_count(void);
  *   anchors      (2, A) fp32, strides (1, A) fp32         (src/model/head.py:112-114)
  *   gt           (gt_total, 5) fp32 [cx, cy, w, h, cls]   all images' boxes concatenated
  *   gt_offsets   (N + 1) int32                            image b owns rows [off[b], off[b+1])
- *   gmax         max boxes of any one image (host-known from the list shapes)
+ *   gmax         max boxes of any one image (host-known from the list shapes; sizes the per-image match work units:
+ *                a wrong value costs time, never correctness; 0 = unknown)
  *   grad_preds   (N, C, A) dtype or NULL                  d total_loss / d preds (NULL: forward only)
  *   out_loss     8 floats: [0] total  [1] mean DFL ("box_loss")  [2] mean QFL ("cls_loss")
- *                          [3] number of distinct matched anchors  [4..6] reserved (zero)
+ *                          [3] number of distinct matched anchors  [4..5] reserved (zero)
+ *                          [6] 1 if an in-kernel dependency of the launch timed out (then [0] is NaN; never seen: the
+ *                              launch's consumers sit behind their producers in block-dispatch order, csrc/common.cuh)
  *                          [7] number of GT rows whose class id lies outside [0, nc): the reference raises on
  *                              those (scatter_, src/model/losses.py:260); the kernels clamp the id to stay
  *                              memory-safe and report the count, so the caller can raise without an extra sync
@@ -67,7 +70,7 @@ long long yb_launch_count(void);
  *   out_per_image (2, N) fp32 or NULL                     per-image DFL and QFL terms
  *   flags        0, or YB_LOSS_NO_PRUNE / YB_LOSS_SPLIT_LAUNCH (test and profiling aids, results identical)
  *   stage_events NULL, or three cudaEvent_t handles of the CALLER (as void*), recorded on `stream` before the
- *                main launch, between the two launches and after the second (bench.py's roofline leg)
+ *                launch, after it, and (YB_LOSS_SPLIT_LAUNCH) after match_kernel (bench.py's roofline leg)
  *
  * The quirks of the reference that decide results are kept (Q1-Q6, Q16).
  * Images with no boxes contribute their QFL term and count in the mean (Q6).  The all-empty
@@ -84,7 +87,7 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
                     void *workspace, size_t workspace_bytes, unsigned flags, void *const *stage_events, void *stream);
 
 #define YB_LOSS_NO_PRUNE 1u      /* box role scans every (GT, tile) pair: the exactness tests compare with and without */
-#define YB_LOSS_SPLIT_LAUNCH 2u  /* box and class roles as two launches instead of one (profiling the roles apart) */
+#define YB_LOSS_SPLIT_LAUNCH 2u  /* box, class and match roles as three launches instead of one (profiling the roles apart) */
 
 /* grad *= *scale (device scalar), in place; returns without touching memory when *scale == 1.
  * Used by the autograd bridge for `loss.backward()` under a GradScaler

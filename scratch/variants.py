@@ -9,13 +9,13 @@ VARIANTS = (json.load(open(os.path.join(ROOT, 'scratch', 'variants.json'))) if o
     {}, {"YB_CLS_THREADS": 256}, {"YB_CLS_UNROLL": 8}, {"YB_CLS_UNROLL": 2}, {"YB_CLS_MINBLOCKS": 8},
     {"YB_CLS_THREADS": 256, "YB_CLS_UNROLL": 2}, {"YB_ASSIGN_THREADS": 256}, {"YB_ASSIGN_THREADS": 64}, {"YB_ASSIGN_MINBLOCKS": 8},
 ]
-def name(v): return 'base' if not v else '_'.join(f"{k[3:].lower()}{val}" for k, val in sorted(v.items()))
+def name(v): return "base" if not v else v["_name"] if "_name" in v else '_'.join(f"{k[3:].lower()}{val}" for k, val in sorted(v.items()))
 def build_all():
     os.makedirs(OUT, exist_ok=True)
     procs = []
     for v in VARIANTS:
         so = os.path.join(OUT, f'lib_{name(v)}.so')
-        defs = [f'-D{k}={val}' for k, val in v.items()]
+        defs = [f'-D{k}={val}' for k, val in v.items() if not k.startswith('_')]
         cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC',
                '--expt-relaxed-constexpr', '-shared', '-o', so, os.path.join(CSRC, 'loss.cu'), os.path.join(CSRC, 'cabi.cu'), '-lcudart'] + defs
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -41,8 +41,7 @@ def run_all():
         lib.yb_loss_workspace_bytes.argtypes = [ctypes.c_int] * 4
         P = ctypes.c_void_p
         lib.yb_loss_fwd_bwd.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P, P, P, ctypes.c_int, ctypes.c_int,
-                                        ctypes.c_float, ctypes.c_float, P, P, P, P, P, P, ctypes.c_size_t, P]
-        lib.yb_loss_last_stage_ms.argtypes = [P]
+                                        ctypes.c_float, ctypes.c_float, P, P, P, P, P, P, ctypes.c_size_t, ctypes.c_uint, P, P]
         line = [f'{name(v):28s}']
         for cn, d in data.items():
             ws = torch.empty(lib.yb_loss_workspace_bytes(d['n'], d['a'], d['gt_total'], d['dt']), dtype=torch.uint8, device=dev)
@@ -50,22 +49,16 @@ def run_all():
             st = torch.cuda.current_stream().cuda_stream
             def call():
                 rc = lib.yb_loss_fwd_bwd(d['preds'].data_ptr(), d['dt'], d['n'], d['nc'], 16, d['a'], d['anc'].data_ptr(), d['st'].data_ptr(), d['gt'].data_ptr(),
-                                         d['off'].data_ptr(), d['gt_total'], d['gmax'], 1.0, 1.5, grad.data_ptr(), out.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), st)
+                                         d['off'].data_ptr(), d['gt_total'], d['gmax'], 1.0, 1.5, grad.data_ptr(), out.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), 0, None, st)
                 assert rc == 0, lib.yb_last_error()
             for _ in range(3): call()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(50): call()
+            for _ in range(200): call()
             e1.record(); torch.cuda.synchronize()
-            total = e0.elapsed_time(e1) / 50
-            lib.yb_stage_timing(1)
-            buf = (ctypes.c_float * 3)(); acc = [0, 0, 0]
-            for _ in range(10):
-                call(); lib.yb_loss_last_stage_ms(buf)
-                for i in range(3): acc[i] += buf[i] / 10
-            lib.yb_stage_timing(0)
-            line.append(f'{cn}: step {total*1e3:6.1f} us  assign {acc[0]*1e3:6.1f}  cls {acc[1]*1e3:6.1f}  match+fin {acc[2]*1e3:5.1f}  loss {out[0].item():.6f}')
+            total = e0.elapsed_time(e1) / 200
+            tk = ws[:64].view(torch.int32).tolist(); line.append(f'{cn}: step {total*1e3:6.1f} us  loss {out[0].item():.6f} waits {tk[8]} kcyc {tk[9]}')
         print(' | '.join(line), flush=True)
 if __name__ == '__main__':
     if sys.argv[1] == 'build': build_all()

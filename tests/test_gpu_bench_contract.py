@@ -30,7 +30,7 @@ def test_our_arm_prints_the_contract_line(cuda_device):
     assert d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] == 3 and d["higher_is_better"] is True
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
     assert d["value"] > 0 and d["vs_baseline"] is None
-    assert d["gpu_launches"] == 2 * d["steps"]                      # fused main + match: counted inside the library
+    assert d["gpu_launches"] == d["steps"]                          # the step is one launch: counted inside the library
     assert d["timed_steps"] >= 100 and abs(d["value"] - 128 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
     ok, tot = (int(v) for v in d["parity"]["matched_anchors_identical"].split("/"))
     assert tot == 6747 and ok >= tot - 4 and d["parity"]["loss_rel_err_max"] <= (1e-5 if ok == tot else 2e-4)

@@ -83,6 +83,7 @@ def test_loss_matches_reference_golden(name, cuda_device):
     (3, 80, 640, 100, 1236, 0.05),      # cfg2 GT density, with forced duplicate anchors
     (2, 20, 320, 300, 1238, 0.0),       # more than 128 GT per image: multi-chunk scan
     (2, 3, 96, 7, 1239, 0.0),           # A = 189: scalar (unaligned) path
+    (2, 20, 256, 300, 1242, 0.05),      # A = 1344, 300 GT: matched anchors crowd into the same 32-byte gradient sectors
 ])
 def test_loss_matches_oracle(n, nc, imgsz, gmax, seed, conflict, cuda_device):
     preds, gts, anchors, strides = syn.make_loss_inputs(n, nc, imgsz, gmax, seed, conflict_frac=conflict)
@@ -127,8 +128,9 @@ def test_confident_class_logits_match_oracle(std, mean, cuda_device):
     assert (grad[:, 64:][preds[:, 64:] > 17.0] == 0).all()          # p rounds to 1: sigmoid'(x) = 0 in the reference too
 
 
-def test_bf16_inputs_match_oracle(cuda_device):
-    preds, gts, anchors, strides = syn.make_loss_inputs(3, 80, 640, 60, 1240, dtype=torch.bfloat16)
+@pytest.mark.parametrize("n,imgsz,gmax,seed", [(3, 640, 60, 1240), (2, 256, 200, 1243)])   # the second: crowded gradient sectors
+def test_bf16_inputs_match_oracle(n, imgsz, gmax, seed, cuda_device):
+    preds, gts, anchors, strides = syn.make_loss_inputs(n, 80, imgsz, gmax, seed, dtype=torch.bfloat16)
     out, grad, idx, iou, _, _ = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device)
     ora = L.loss_forward_backward(preds, gts, anchors, strides, 80)
     tot, bad = idx_agreement(idx, ora)
