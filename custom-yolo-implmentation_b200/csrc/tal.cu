@@ -11,23 +11,26 @@
 //   yb_tal_assign   tal_decode_kernel      streaming: reads the 4 x 16 box rows once (128-bit loads) and leaves the
 //                                          decoded pixel box of every anchor in the workspace (16 B per anchor,
 //                                          L2-resident for the next kernel)
-//                   tal_topk_kernel        one warp per GT over the whole image: group-extent skip + ballot
-//                                          compaction of the anchors whose centre lies inside the GT, alignment
-//                                          metric 64 anchors at a time (approximate-reciprocal arithmetic: it only
-//                                          RANKS), running top-k (metric desc, anchor asc) by REDUX rounds with the
-//                                          candidate list in registers, 64-bit atomicMax (overlap, ~gt) per anchor
-//                                          resolves conflicts
-//                   tal_fg_kernel          one half-warp per (GT, selected anchor): did the GT keep the anchor,
-//                                          the GT's max metric / overlap -> target score; CIoU and DFL loss and
-//                                          the gradient of the anchor's 64 box logits (NOT yet divided by the
-//                                          normaliser) into a compact buffer; anchor -> slot map; the target scores
-//                                          are summed in fixed point (integer atomics: order-independent)
-//                   tal_stats_kernel       -> [sum of target scores, #foreground] of this rank
+//                   tal_gt_kernel          one warp per GT over the whole image.  (1) candidates: the anchors whose centre
+//                                          lies inside the GT (rectangle enumeration on a verified grid hint, group-extent
+//                                          skip + ballot compaction otherwise), alignment metric 64 anchors at a time
+//                                          (approximate-reciprocal arithmetic: it only RANKS), running top-k (metric desc,
+//                                          anchor asc) by REDUX rounds with the candidate list in registers, 64-bit
+//                                          atomicMax (overlap, ~gt) per anchor for conflicts.  (2) the foreground terms of
+//                                          the k selected anchors, two at a time (one per half-warp), before anybody knows
+//                                          whether the GT keeps them: every term is LINEAR in the anchor's target score t,
+//                                          so CIoU / DFL loss and the gradient of the anchor's 64 box logits are left per
+//                                          unit of t (compact buffer); the scattered gathers of one warp run under the
+//                                          ranking arithmetic of the others
+//                   tal_resolve_kernel     one half-warp per GT: which selected anchors did the GT keep, the GT's max
+//                                          metric / overlap -> target score t per slot (or "not kept"), anchor -> slot map;
+//                                          target scores summed in fixed point (integer atomics: order-independent); the
+//                                          last CTA -> [sum of target scores, #foreground] of this rank (+ the peer stores)
 //   yb_tal_loss     tal_cls_kernel         dense BCE-with-logits at target 0 + gradient; writes the box rows of the
-//                                          gradient too: zero, or the foreground anchor's 64 values / normaliser
+//                                          gradient too: zero, or the foreground anchor's 64 values * t / normaliser
 //                                          (predicated loads through the anchor -> slot map, no scattered stores)
-//                   tal_finalize_kernel    patches the one positive class cell of every foreground anchor, then
-//                                          fixed-order reduction -> loss scalars
+//                   tal_finalize_kernel    patches the one positive class cell of every foreground anchor, scales the
+//                                          per-slot terms by t, fixed-order reduction -> loss scalars
 // The anchors x GT overlap / metric matrices never exist.
 #include <algorithm>
 #include <cstring>
@@ -57,9 +60,8 @@ __host__ __device__ constexpr int tal_cls_split(int tile) { return tile >= 1024 
 #endif
 struct TalWorkspace {
     // zeroed by yb_tal_assign's first kernels (the counters by a memset, the per-anchor arrays by tal_decode_kernel)
-    unsigned int *ticket;               // [0] finalize ticket, [1] next work unit of tal_topk_kernel, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived
+    unsigned int *ticket;               // [0] finalize ticket, [1] next GT of tal_gt_kernel, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived, [5] resolve ticket
     unsigned long long *stat_acc;       // [kTalStatAcc] fixed-point sums of the target scores, [kTalStatAcc] foreground counts, [1] total #foreground
-    int *gt_done;                       // [gt_total] units of the GT that tal_topk_kernel has finished
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
     int *aslot;                         // [N * A]  1 + (g * topk + r) of the GT slot that owns the anchor (0 = background)
     // plain scratch
@@ -67,13 +69,13 @@ struct TalWorkspace {
     float4 *gext;                       // [ceil(A / 32)]  extent of the anchor centres of each group of 32 anchors
     float2 *ctr;                        // [A]  anchor centres in pixels
     float *peer_tss;                    // [2]  normaliser and #foreground averaged over the ranks (peer exchange, csrc/peer.cu)
-    float4 *psel;                       // [gt_total * kTopkSplit * kTalMaxK]  per-unit partial lists (same fields as sel)
     float4 *sel;                        // [gt_total * kTalMaxK]  anchor bits, metric, overlap, -
     int *sel_count;                     // [gt_total]
-    float *fg_box, *fg_dfl, *fg_cls;    // [gt_total * kTalMaxK] per-foreground loss terms (not yet divided by the normaliser)
-    float *fgrad;                       // [gt_total * kTalMaxK * 64] box-logit gradient of every foreground anchor (ditto)
-    long long *fcell_off;               // [gt_total * kTalMaxK] element offset of the anchor's positive class cell (-1 = none)
-    float *fcell_val;                   // [gt_total * kTalMaxK] its gradient (ditto)
+    // per slot = (GT, r-th selected anchor), written by tal_gt_kernel PER UNIT of the target score t:
+    float4 *fterm;                      // [gt_total * kTalMaxK]  1 - CIoU, DFL term, class logit of the GT's class, its sigmoid
+    float *fgrad;                       // [gt_total * kTalMaxK * 64] gradient of the anchor's 64 box logits
+    long long *fcell_off;               // [gt_total * kTalMaxK] element offset of the anchor's positive class cell
+    float *tsc;                         // [gt_total * kTalMaxK] target score t of the slot, < 0: the GT did not keep the anchor (tal_resolve_kernel)
     float *part;                        // [N * cls_tiles]
     double *cta_sums;                   // [4 * finalize CTAs]
     int cls_tiles;
@@ -92,8 +94,6 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     off += 64;
     w.stat_acc = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (2 * kTalStatAcc + 1), 64);
-    w.gt_done = reinterpret_cast<int *>(p + off);
-    off += round_up(sizeof(int) * g, 64);
     w.small_zero_bytes = off;
     w.akey = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)n_images * n_anchors, 64);
@@ -110,23 +110,17 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     off += round_up(sizeof(float2) * (size_t)n_anchors, 64);
     w.peer_tss = reinterpret_cast<float *>(p + off);
     off += 64;
-    w.psel = reinterpret_cast<float4 *>(p + off);
-    off += round_up(sizeof(float4) * g * kTalMaxK * 8, 64);           // 8 >= kTopkSplit
     w.sel = reinterpret_cast<float4 *>(p + off);
     off += round_up(sizeof(float4) * g * kTalMaxK, 64);
     w.sel_count = reinterpret_cast<int *>(p + off);
     off += round_up(sizeof(int) * g, 64);
-    w.fg_box = reinterpret_cast<float *>(p + off);
-    off += round_up(sizeof(float) * g * kTalMaxK, 64);
-    w.fg_dfl = reinterpret_cast<float *>(p + off);
-    off += round_up(sizeof(float) * g * kTalMaxK, 64);
-    w.fg_cls = reinterpret_cast<float *>(p + off);
-    off += round_up(sizeof(float) * g * kTalMaxK, 64);
+    w.fterm = reinterpret_cast<float4 *>(p + off);
+    off += round_up(sizeof(float4) * g * kTalMaxK, 64);
     w.fgrad = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * g * kTalMaxK * 4 * kRegMax, 64);
     w.fcell_off = reinterpret_cast<long long *>(p + off);
     off += round_up(sizeof(long long) * g * kTalMaxK, 64);
-    w.fcell_val = reinterpret_cast<float *>(p + off);
+    w.tsc = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * g * kTalMaxK, 64);
     w.part = reinterpret_cast<float *>(p + off);
     off += round_up(sizeof(float) * (size_t)n_images * w.cls_tiles, 64);
@@ -187,14 +181,20 @@ __device__ __forceinline__ float fast_atan_pos(float x) {
 }
 __device__ __forceinline__ float gt_atan_fast(const float4 &g) { return fast_atan_pos(fast_div(g.z - g.x, g.w - g.y + kEpsCiou)); }
 
-// overlap = max(CIoU, 0) of predicted box p and GT box g
-__device__ __forceinline__ float overlap_fast(const float4 &p, const float4 &g, float atan_g, float area_g) {
+// plain IoU of predicted box p and GT box g, the very value overlap_fast starts from (0 when they do not intersect)
+__device__ __forceinline__ float iou_fast(const float4 &p, const float4 &g, float area_g) {
     const float w1 = p.z - p.x, h1 = p.w - p.y + kEpsCiou;
     const float iw = fmaxf(fminf(p.z, g.z) - fmaxf(p.x, g.x), 0.f), ih = fmaxf(fminf(p.w, g.w) - fmaxf(p.y, g.y), 0.f);
     const float inter = iw * ih;
-    if (inter <= 0.f) return 0.f;                          // IoU 0: the penalties can only push the CIoU below zero
-    const float uni = w1 * h1 + area_g - inter + kEpsCiou;
-    const float iou = fast_div(inter, uni);
+    if (inter <= 0.f) return 0.f;
+    return fast_div(inter, w1 * h1 + area_g - inter + kEpsCiou);
+}
+
+// overlap = max(CIoU, 0) of predicted box p and GT box g
+__device__ __forceinline__ float overlap_fast(const float4 &p, const float4 &g, float atan_g, float area_g) {
+    const float w1 = p.z - p.x, h1 = p.w - p.y + kEpsCiou;
+    const float iou = iou_fast(p, g, area_g);
+    if (iou <= 0.f) return 0.f;                            // IoU 0: the penalties can only push the CIoU below zero
     const float cw = fmaxf(p.z, g.z) - fminf(p.x, g.x), ch = fmaxf(p.w, g.w) - fminf(p.y, g.y);
     const float c2 = cw * cw + ch * ch + kEpsCiou;
     const float dxs = g.x + g.z - p.x - p.z, dys = g.y + g.w - p.y - p.w;
@@ -214,6 +214,17 @@ __device__ __forceinline__ float metric_fast(float logit, float ov, float alpha,
         return rs * (o2 * o2 * o2);
     }
     return powf(sc, alpha) * powf(ov, beta);
+}
+
+// An upper bound of metric_fast over every class score, from the plain IoU alone: score^alpha <= 1 and the CIoU
+// penalties only lower the overlap (alpha, beta >= 0; the caller does not filter otherwise).  The margin covers the
+// approximate square root of a score that rounds to 1.
+__device__ __forceinline__ float metric_bound(float iou, float beta) {
+    if (beta == 6.f) {
+        const float o2 = iou * iou;
+        return (o2 * o2 * o2) * 1.0001f;
+    }
+    return powf(iou, beta) * 1.0001f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -242,14 +253,13 @@ __device__ __forceinline__ bool grid_matches(const TalGrid &gr, int a, float ax,
 // write the anchor CENTRES in pixels and their extent per group of 32 consecutive anchors (the same for all images).
 // ------------------------------------------------------------------------------------------
 template <typename T, int VW>
-__global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : 6)
-tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
-                  const float *__restrict__ strides, const int *__restrict__ gt_off, float4 *__restrict__ dbox,
-                  float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,
-                  int *__restrict__ aslot, const TalGrid grid, unsigned int *__restrict__ grid_rejected) {
+__device__ __forceinline__ void tal_decode_body(int n, int tile, const T *__restrict__ preds, int n_ch, int n_anchors,
+                                                const float *__restrict__ anchors, const float *__restrict__ strides,
+                                                const int *__restrict__ gt_off, float4 *dbox, float4 *gext, float2 *ctr,
+                                                unsigned long long *akey, int *aslot, const TalGrid &grid,
+                                                unsigned int *grid_rejected) {
     constexpr int GL = 32 / VW;                            // lanes that share one group of 32 anchors
-    const int n = blockIdx.y;
-    const int a0 = (blockIdx.x * kTalThreads + threadIdx.x) * VW;
+    const int a0 = (tile * kTalThreads + threadIdx.x) * VW;
     // arm the per-anchor conflict keys and the anchor -> slot map of this thread's anchors (all images: the dense
     // pass reads the map everywhere)
 #pragma unroll
@@ -311,19 +321,32 @@ tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const fl
     }
 }
 
+template <typename T, int VW>
+__global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : 6)
+tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
+                  const float *__restrict__ strides, const int *__restrict__ gt_off, float4 *__restrict__ dbox,
+                  float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,
+                  int *__restrict__ aslot, const TalGrid grid, unsigned int *__restrict__ grid_rejected) {
+    tal_decode_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt_off, dbox, gext, ctr, akey, aslot,
+                           grid, grid_rejected);
+}
+
 // ------------------------------------------------------------------------------------------
-// tal_topk_kernel: the latency-bound half of the assignment.  A GT's candidates are the anchors whose centre lies
-// strictly inside it; they are found through the per-group centre extents and ranked by the alignment metric.
-// Work unit = (GT, j): the groups of 32 anchors with index = j (mod kTopkSplit) — an even split whatever the GT's
-// shape, and short units: the kernel's tail is one unit, not one GT.  Units are handed out to WARPS from a global
-// counter (no wave quantisation, no idle warps inside a CTA).  Per unit, in ascending anchor order: group-extent test
-// (32 groups per ballot), ballot compaction of the inside anchors into a small queue, evaluation 64 at a time
-// (decoded boxes from L2, class logit from HBM; approximate-reciprocal arithmetic: the metric only RANKS), and a
-// running top-k in registers, lane r holding the r-th best (metric desc, anchor asc): entries that beat the current
-// k-th best are merged in, a few by insertion (ballot + shuffle-up), many at once by REDUX rounds.  Within a unit a
-// later entry that only TIES the k-th best can never displace it (ties -> lowest anchor), so the strict test is exact.
-// The last unit of a GT to finish (per-GT ticket) merges the kTopkSplit partial lists and publishes the GT's k anchors;
-// conflicts: 64-bit atomicMax (overlap, ~gt) per anchor.
+// tal_gt_kernel: everything that is per GT.  GTs are handed out to WARPS from a global counter (no wave quantisation, no
+// idle warps inside a CTA).
+// (1) The GT's candidates are the anchors whose centre lies strictly inside it; in ascending anchor order they are
+// evaluated 64 at a time (decoded boxes from L2, class logit from HBM; approximate-reciprocal arithmetic: the metric only
+// RANKS) against a running top-k in registers, lane r holding the r-th best (metric desc, anchor asc): entries that beat
+// the current k-th best are merged in, a few by insertion (ballot + shuffle-up), many at once by REDUX rounds.  A later
+// entry that only TIES the k-th best can never displace it (ties -> lowest anchor), so the strict test is exact.
+// Conflicts: 64-bit atomicMax (overlap, ~gt) per anchor.
+// (2) The foreground terms of the selected anchors, one HALF-warp per anchor (lane & 15 is the DFL bin and the lane holds
+// that bin of all four sides, so the scalar part -- CIoU, its gradient, the class cell -- is issued once for two
+// anchors), while it is still open whether the GT keeps the anchor and what its target score t will be: CIoU loss, DFL
+// loss and the gradient of the 64 box logits are all proportional to t, so they are stored per unit of t and
+// tal_cls_kernel / tal_finalize_kernel apply t / normaliser.  (The anchors a GT loses to another GT -- a few per cent --
+// are computed for nothing.)  As a kernel of its own this half was bound by its scattered 64-byte DRAM accesses (60 us
+// after a 73 us ranking kernel bound by instruction issue); in one kernel the two overlap across warps.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_images, int g) {
     int lo = 0, hi = n_images;
@@ -334,10 +357,6 @@ __device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_im
     return lo;
 }
 
-#ifndef YB_TOPK_SPLIT
-#define YB_TOPK_SPLIT 1
-#endif
-constexpr int kTopkSplit = YB_TOPK_SPLIT;        // units per GT (power of two, <= 8)
 constexpr int kTopkWarps = 4;
 constexpr int kTopkQueue = 96;                   // inside-anchor queue per warp: evaluated 64 at a time
 constexpr int kEmptyKey = (int)0x80000000;       // below every metric bit pattern (metrics are >= 0)
@@ -383,42 +402,76 @@ __device__ __forceinline__ TopK topk_select(int (&vm)[NE], const int (&va)[NE], 
     return nw;
 }
 
-#ifndef YB_TOPK_MINBLOCKS
-#define YB_TOPK_MINBLOCKS 8
-#endif
+// what a half-warp fetches for one selected anchor: this lane's bin of the four sides and the class logit
+struct FgFetch {
+    float z[4], z_cls;
+};
 template <typename T>
-__global__ void __launch_bounds__(32 * kTopkWarps, YB_TOPK_MINBLOCKS)
-tal_topk_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, const float *__restrict__ gt,
-                const int *__restrict__ gt_off, int gt_total, int topk, float alpha, float beta,
-                const float4 *__restrict__ dbox, const float4 *__restrict__ gext, const float2 *__restrict__ ctr,
-                const TalGrid grid, const unsigned int *__restrict__ grid_rejected, float4 *__restrict__ psel, int *__restrict__ gt_done, float4 *__restrict__ sel,
-                int *__restrict__ sel_count, unsigned long long *__restrict__ akey, unsigned int *__restrict__ next_unit,
-                unsigned int *__restrict__ bad_cls) {
-    __shared__ int s_aq[kTopkWarps][kTopkQueue];           // queue of inside anchors
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int *aq = s_aq[warp];
+__device__ __forceinline__ FgFetch fg_fetch(const T *__restrict__ img, const T *__restrict__ cls_row, int n_anchors, int idx,
+                                            int bin) {
+    FgFetch f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f.z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
+    f.z_cls = load_as_float(cls_row + idx);
+    return f;
+}
+
+#ifndef YB_TOPK_MINBLOCKS
+#define YB_TOPK_MINBLOCKS 6
+#endif
+// what the per-GT work reads and writes (one struct so that the stand-alone kernel and the fused launch share the body)
+template <typename T>
+struct TalGtArgs {
+    const T *preds;
+    int n_images, n_ch, n_anchors;
+    const float *anchors, *strides, *gt;
+    const int *gt_off;
+    int gt_total, topk;
+    float alpha, beta, lambda_box, lambda_dfl;
+    const float4 *dbox, *gext;
+    const float2 *ctr;
+    TalGrid grid;
+    float4 *sel;
+    int *sel_count;
+    unsigned long long *akey;
+    float4 *fterm;
+    float *fgrad;
+    long long *fcell_off;
+    unsigned int *bad_cls;
+};
+
+// GT g (image n, g_local-th box of it) by one warp; aq = the warp's queue of kTopkQueue ints in shared memory
+template <typename T>
+__device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n, int g_local, bool regular, int *aq) {
+    const int lane = threadIdx.x & 31;
+    const T *__restrict__ preds = A.preds;
+    const float *__restrict__ anchors = A.anchors, *__restrict__ strides = A.strides, *__restrict__ gt = A.gt;
+    const int n_ch = A.n_ch, n_anchors = A.n_anchors, topk = A.topk;
+    const float alpha = A.alpha, beta = A.beta, lambda_box = A.lambda_box, lambda_dfl = A.lambda_dfl;
+    const float4 *dbox = A.dbox, *gext = A.gext;
+    const float2 *ctr = A.ctr;
+    const TalGrid &grid = A.grid;
+    float4 *__restrict__ sel = A.sel;
+    int *__restrict__ sel_count = A.sel_count;
+    unsigned long long *akey = A.akey;
+    float4 *__restrict__ fterm = A.fterm;
+    float *__restrict__ fgrad = A.fgrad;
+    long long *__restrict__ fcell_off = A.fcell_off;
+    unsigned int *bad_cls = A.bad_cls;
     const int n_cls = n_ch - 4 * kRegMax;
     const int n_groups = (n_anchors + 31) >> 5;
-    const int n_units = gt_total * kTopkSplit;
     const int n_levels = grid.n_levels;
-    const bool regular = n_levels > 0 && __ldg(grid_rejected) == 0u;   // uniform over the launch
-    for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = (int)atomicAdd(next_unit, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
-        const int g = unit / kTopkSplit, part = unit - g * kTopkSplit;
-        const int n = gt_image(gt_off, n_images, g);
-        const int g_local = g - __ldg(gt_off + n);
+    {
         const float *g5 = gt + (size_t)g * 5;
         const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
         const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
         const int cls_raw = (int)__ldg(g5 + 4);
         const int cls = min(max(cls_raw, 0), n_cls - 1);
-        if (lane == 0 && part == 0 && cls_raw != cls) atomicAdd(bad_cls, 1u);   // clamped (memory-safe), counted: the caller raises
+        if (lane == 0 && cls_raw != cls) atomicAdd(bad_cls, 1u);   // clamped (memory-safe), counted: the caller raises
         const float at_g = gt_atan_fast(gb);
         const float area_g = (gb.z - gb.x) * (gb.w - gb.y + kEpsCiou);
-        const T *cls_row = preds + ((size_t)n * n_ch + 4 * kRegMax + cls) * n_anchors;
+        const T *img = preds + (size_t)n * n_ch * n_anchors;
+        const T *cls_row = img + (size_t)(4 * kRegMax + cls) * n_anchors;
         const float4 *box_row = dbox + (size_t)n * n_anchors;
 
         TopK win = {kEmptyKey, 0x7fffffff, 0.f};
@@ -471,12 +524,39 @@ tal_topk_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_ancho
             evaluate2(a);
         };
 
+        // Cheap filter in front of the evaluation: a candidate whose plain IoU already bounds its metric at or below the
+        // k-th best so far (or strictly below a k-th best known from a seed of central cells) can never be selected; only the
+        // survivors, compacted into the queue in ascending order, pay for the CIoU, the class logit and the merge.
+        const bool can_bound = alpha >= 0.f && beta >= 0.f;
+        int thr_seed = -1;
+        auto survives = [&](int a) {                       // a >= 0
+            if (!can_bound) return true;
+            const int ub = __float_as_int(metric_bound(iou_fast(box_row[a], gb, area_g), beta));
+            return ub > thr && ub >= thr_seed;
+        };
+        auto enqueue = [&](bool keep, int a) {             // whole warp; appends the kept anchors in lane order
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a;
+            nq += __popc(mask);
+            __syncwarp();
+            if (nq >= 64) {                                // warp-uniform
+                evaluate(64);
+                const int rest = nq - 64;                  // < 32
+                const int keep_a = lane < rest ? aq[64 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) aq[lane] = keep_a;
+                nq = rest;
+                __syncwarp();
+            }
+        };
+
         if (regular) {
             // ---- the anchors form regular grids: the inside anchors of a level are a rectangle of cells --------
-            int batch = 0;                                 // batches of 64 cells are dealt round-robin to the GT's units
-            for (int l = 0; l < n_levels; ++l) {
-                const int W = grid.w[l], H = grid.h[l], st = grid.start[l];
-                const float s = grid.stride[l], x0 = grid.x0[l], y0 = grid.y0[l];
+            // lane l works out the rectangle of level l (the others fetch it by shuffle)
+            int r_x0 = 0, r_y0 = 0, r_nx = 0, r_ny = 0;
+            if (lane < n_levels) {
+                const int W = grid.w[lane], H = grid.h[lane];
+                const float s = grid.stride[lane], x0 = grid.x0[lane], y0 = grid.y0[lane];
                 // first / last column and row whose centre is strictly inside: a guess from the division, made exact
                 // with the very comparison the generic path applies to the stored centres ((x0 + col) * s is the
                 // stored value bit for bit: tal_decode_kernel verified that)
@@ -492,101 +572,209 @@ tal_topk_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_ancho
                     while (i >= 0 && !(hi - (c0 + (float)i) * s > kEpsIn)) --i;
                     return i;
                 };
-                const int ix0 = first_in(gb.x, x0, W), ix1 = last_in(gb.z, x0, W);
-                const int iy0 = first_in(gb.y, y0, H), iy1 = last_in(gb.w, y0, H);
-                const int nx = ix1 - ix0 + 1, ny = iy1 - iy0 + 1;
+                r_x0 = first_in(gb.x, x0, W);
+                r_y0 = first_in(gb.y, y0, H);
+                r_nx = max(last_in(gb.z, x0, W) - r_x0 + 1, 0);
+                r_ny = max(last_in(gb.w, y0, H) - r_y0 + 1, 0);
+            }
+            __syncwarp();
+            if (can_bound) {
+                // seed: the 3 x 3 cells around the GT's centre on (up to) three levels, one per lane; the k-th best metric
+                // among them is a lower bound of the final k-th best.  Only used to DROP candidates strictly below it: the
+                // ranking itself starts empty and still sees these cells, in their place in the anchor order.
+                const int sl = min(lane / 9, n_levels - 1), k9 = lane % 9;
+                const int sx0 = __shfl_sync(0xffffffffu, r_x0, sl), sy0 = __shfl_sync(0xffffffffu, r_y0, sl);
+                const int snx = __shfl_sync(0xffffffffu, r_nx, sl), sny = __shfl_sync(0xffffffffu, r_ny, sl);
+                int v = kEmptyKey;
+                if (lane < 27 && lane / 9 < n_levels && snx > 0 && sny > 0) {
+                    const float s = grid.stride[sl];
+                    const int cc = min(max((int)floorf(gcx / s - grid.x0[sl] + 0.5f), sx0), sx0 + snx - 1) + (k9 % 3) - 1;
+                    const int cr = min(max((int)floorf(gcy / s - grid.y0[sl] + 0.5f), sy0), sy0 + sny - 1) + (k9 / 3) - 1;
+                    if (cc >= sx0 && cc < sx0 + snx && cr >= sy0 && cr < sy0 + sny) {
+                        const int a = grid.start[sl] + cr * grid.w[sl] + cc;
+                        v = __float_as_int(metric_fast(load_as_float(cls_row + a), overlap_fast(box_row[a], gb, at_g, area_g), alpha, beta));
+                    }
+                }
+                int kth = kEmptyKey;
+                for (int r = 0; r < topk; ++r) {           // k-th largest of the lanes' values
+                    kth = __reduce_max_sync(0xffffffffu, v);
+                    if (kth == kEmptyKey) break;           // fewer than k seeds
+                    const unsigned eq = __ballot_sync(0xffffffffu, v == kth);
+                    if (lane == __ffs(eq) - 1) v = kEmptyKey;
+                }
+                thr_seed = kth == kEmptyKey ? -1 : kth;
+            }
+            for (int l = 0; l < n_levels; ++l) {
+                const int ix0 = __shfl_sync(0xffffffffu, r_x0, l), iy0 = __shfl_sync(0xffffffffu, r_y0, l);
+                const int nx = __shfl_sync(0xffffffffu, r_nx, l), ny = __shfl_sync(0xffffffffu, r_ny, l);
                 if (nx <= 0 || ny <= 0) continue;          // uniform
+                const int W = grid.w[l], st = grid.start[l];
                 const int cells = nx * ny;
                 const float inv_nx = 1.f / (float)nx;
-                for (int c0 = 0; c0 < cells; c0 += 64, ++batch) {
-                    if (kTopkSplit > 1 && (batch & (kTopkSplit - 1)) != part) continue;
-                    int a[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int c = c0 + 32 * u + lane;
-                        int row = (int)(((float)c + 0.5f) * inv_nx), col = c - row * nx;
-                        if (col < 0) { --row; col += nx; } else if (col >= nx) { ++row; col -= nx; }
-                        a[u] = c < cells ? st + (iy0 + row) * W + ix0 + col : -1;
-                    }
-                    evaluate2(a);
+                for (int c0 = 0; c0 < cells; c0 += 32) {
+                    const int c = c0 + lane;
+                    int row = (int)(((float)c + 0.5f) * inv_nx), col = c - row * nx;
+                    if (col < 0) { --row; col += nx; } else if (col >= nx) { ++row; col -= nx; }
+                    const int a = st + (iy0 + row) * W + ix0 + col;
+                    enqueue(c < cells && survives(a), a);
                 }
             }
         } else {
-
-        // lane l of round i looks at group (i * 32 + l) * kTopkSplit + part
-        for (int gb0 = part; gb0 < n_groups; gb0 += 32 * kTopkSplit) {
-            const int my_group = gb0 + lane * kTopkSplit;
-            float4 ext = make_float4(0.f, 0.f, -1.f, -1.f);   // an empty extent never intersects
-            if (my_group < n_groups) ext = __ldg(gext + my_group);
-            unsigned groups = __ballot_sync(0xffffffffu, gb.x < ext.z && gb.z > ext.x && gb.y < ext.w && gb.w > ext.y);
-            while (groups) {
-                const int a = ((gb0 + (__ffs(groups) - 1) * kTopkSplit) << 5) + lane;
-                groups &= groups - 1;
-                bool in = false;
-                if (a < n_anchors) {
-                    const float2 c = __ldg(ctr + a);
-                    in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, in);
-                if (in) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a;
-                nq += __popc(mask);
-                __syncwarp();
-                if (nq >= 64) {                            // warp-uniform
-                    evaluate(64);
-                    const int rest = nq - 64;              // < 32
-                    const int keep_a = lane < rest ? aq[64 + lane] : 0;
-                    __syncwarp();
-                    if (lane < rest) aq[lane] = keep_a;
-                    nq = rest;
-                    __syncwarp();
+            // ---- no structure assumed: lane l of round i looks at the centre extent of group i * 32 + l --------
+            for (int gb0 = 0; gb0 < n_groups; gb0 += 32) {
+                const int my_group = gb0 + lane;
+                float4 ext = make_float4(0.f, 0.f, -1.f, -1.f);   // an empty extent never intersects
+                if (my_group < n_groups) ext = gext[my_group];
+                unsigned groups = __ballot_sync(0xffffffffu, gb.x < ext.z && gb.z > ext.x && gb.y < ext.w && gb.w > ext.y);
+                while (groups) {
+                    const int a = ((gb0 + (__ffs(groups) - 1)) << 5) + lane;
+                    groups &= groups - 1;
+                    bool in = false;
+                    if (a < n_anchors) {
+                        const float2 c = ctr[a];
+                        in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
+                    }
+                    enqueue(in && survives(a), a);
                 }
             }
         }
         if (nq > 0) evaluate(nq);
-        __syncwarp();                                      // the queue is reused by the warp's next unit
-        }
+        __syncwarp();                                      // the queue is reused by the warp's next GT
 
-        if (kTopkSplit == 1) {                             // one unit per GT: its list is the GT's list
-            const int n_sel = __popc(__ballot_sync(0xffffffffu, lane < topk && win.m != kEmptyKey));
-            if (lane < n_sel) {
-                sel[(size_t)g * kTalMaxK + lane] = make_float4(__int_as_float(win.a), __int_as_float(win.m), win.o, 0.f);
-                atomicMax(akey + (size_t)n * n_anchors + win.a,
-                          ((unsigned long long)__float_as_uint(win.o) << 32) | (unsigned int)(~(unsigned int)g_local));
-            }
-            if (lane == 0) sel_count[g] = n_sel;
-            continue;
-        }
-        // ---- publish the unit's list; the GT's last unit merges the kTopkSplit lists -------------------
-        float4 *mine = psel + (size_t)unit * kTalMaxK;
-        if (lane < topk) mine[lane] = make_float4(__int_as_float(win.a), __int_as_float(win.m), win.o, 0.f);
-        __threadfence();
-        __syncwarp();
-        int done = 0;
-        if (lane == 0) done = atomicAdd(gt_done + g, 1);
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done != kTopkSplit - 1) continue;              // warp-uniform
-        __threadfence();
-        constexpr int NE = kTopkSplit * kTalMaxK / 32 > 0 ? kTopkSplit * kTalMaxK / 32 : 1;
-        int vm[NE], va[NE];
-        float vo[NE];
-#pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            const int q = lane + 32 * i;                   // entry q: unit q / kTalMaxK of this GT, rank q % kTalMaxK
-            vm[i] = kEmptyKey; va[i] = 0x7fffffff; vo[i] = 0.f;
-            if (q < kTopkSplit * kTalMaxK && (q & (kTalMaxK - 1)) < topk) {
-                const float4 e = __ldcg(psel + ((size_t)g * kTopkSplit + q / kTalMaxK) * kTalMaxK + (q & (kTalMaxK - 1)));
-                vm[i] = __float_as_int(e.y); va[i] = __float_as_int(e.x); vo[i] = e.z;
-            }
-        }
-        const TopK fin = topk_select<NE>(vm, va, vo, lane, topk);
-        const int n_sel = __popc(__ballot_sync(0xffffffffu, lane < topk && fin.m != kEmptyKey));
+        // ---- publish the GT's list; conflicts: the anchor goes to the GT with the largest overlap, ties -> lowest GT ----
+        const int n_sel = __popc(__ballot_sync(0xffffffffu, lane < topk && win.m != kEmptyKey));
         if (lane < n_sel) {
-            sel[(size_t)g * kTalMaxK + lane] = make_float4(__int_as_float(fin.a), __int_as_float(fin.m), fin.o, 0.f);
-            // conflict resolution: the anchor goes to the GT with the largest overlap, ties -> lowest GT
-            atomicMax(akey + (size_t)n * n_anchors + fin.a,
-                      ((unsigned long long)__float_as_uint(fin.o) << 32) | (unsigned int)(~(unsigned int)g_local));
+            sel[(size_t)g * kTalMaxK + lane] = make_float4(__int_as_float(win.a), __int_as_float(win.m), win.o, 0.f);
+            atomicMax(akey + (size_t)n * n_anchors + win.a,
+                      ((unsigned long long)__float_as_uint(win.o) << 32) | (unsigned int)(~(unsigned int)g_local));
         }
         if (lane == 0) sel_count[g] = n_sel;
+
+        // ---- (2) foreground terms of the selected anchors, per unit of the target score ----------------------------
+        // (2a) what is scalar per anchor -- CIoU, its gradient w.r.t. the four distances, the DFL target of each side --
+        // once, lane r for the r-th selected anchor (spec: oracle/tal_oracle.py::ciou; the exact arithmetic from here on).
+        // The box is the one tal_decode_kernel left in the workspace.
+        float s_dd[4], s_tk[4], s_box;
+        {
+            const int ar = __shfl_sync(0xffffffffu, win.a, lane < n_sel ? lane : 0);     // idle lanes shadow anchor 0 of the list
+            const int idx = n_sel > 0 ? ar : 0;
+            const float4 pb = box_row[idx];
+            const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
+            const Ciou c = ciou_eval(pb, gb, gt_atan(gb));
+            auto w_gt = [](float a, float o) { return a > o ? 1.f : (a == o ? 0.5f : 0.f); };     // d max(a,o)/da
+            auto w_lt = [](float a, float o) { return a < o ? 1.f : (a == o ? 0.5f : 0.f); };     // d min(a,o)/da
+            const float iw = fmaxf(c.iw_raw, 0.f), ih = fmaxf(c.ih_raw, 0.f);
+            const float inv_u2 = 1.f / (c.uni * c.uni);
+            const float d_inter = (c.uni + c.inter) * inv_u2;                // d iou / d inter (union contains -inter)
+            const float d_area1 = -c.inter * inv_u2;
+            const float d_iw = c.iw_raw >= 0.f ? d_inter * ih : 0.f;
+            const float d_ih = c.ih_raw >= 0.f ? d_inter * iw : 0.f;
+            // iou part
+            float gx1 = -d_iw * w_gt(pb.x, gb.x) - d_area1 * c.h1;
+            float gx2 = d_iw * w_lt(pb.z, gb.z) + d_area1 * c.h1;
+            float gy1 = -d_ih * w_gt(pb.y, gb.y) - d_area1 * c.w1;
+            float gy2 = d_ih * w_lt(pb.w, gb.w) + d_area1 * c.w1;
+            // - rho2 / c2
+            const float inv_c2 = 1.f / c.c2;
+            const float k_r = c.rho2 * inv_c2 * inv_c2;                      // rho2 / c2^2
+            // d rho2/dx1 = d rho2/dx2 = -dxs/2 ;  d c2/dx2 = 2 cw [x2 > u2], d c2/dx1 = -2 cw [x1 < u1]
+            gx1 -= (-0.5f * c.dxs) * inv_c2 - k_r * (-2.f * c.cw * w_lt(pb.x, gb.x));
+            gx2 -= (-0.5f * c.dxs) * inv_c2 - k_r * (2.f * c.cw * w_gt(pb.z, gb.z));
+            gy1 -= (-0.5f * c.dys) * inv_c2 - k_r * (-2.f * c.ch * w_lt(pb.y, gb.y));
+            gy2 -= (-0.5f * c.dys) * inv_c2 - k_r * (2.f * c.ch * w_gt(pb.w, gb.w));
+            // - alpha v :  v = k at^2, at = atan(w2/h2) - atan(w1/h1)
+            const float dv_dA1 = -2.f * kFourOverPi2 * c.at;
+            const float inv_hyp = 1.f / (c.h1 * c.h1 + c.w1 * c.w1);
+            const float dv_dw1 = dv_dA1 * (c.h1 * inv_hyp), dv_dh1 = dv_dA1 * (-c.w1 * inv_hyp);
+            gx1 -= c.alpha * (-dv_dw1);
+            gx2 -= c.alpha * dv_dw1;
+            gy1 -= c.alpha * (-dv_dh1);
+            gy2 -= c.alpha * dv_dh1;
+            // L_box = (1 - ciou) * t / tss * lambda_box   (t / tss applied later)
+            const float kb = -lambda_box * s;
+            s_dd[0] = -kb * gx1; s_dd[1] = -kb * gy1; s_dd[2] = kb * gx2; s_dd[3] = kb * gy2;   // d / d (dl, dt, dr, db)
+            s_box = 1.f - c.value;
+            // DFL target of each side (same rule as the reference, src/model/losses.py:226-246)
+            const float inv_s = 1.f / s;
+            const float hi_clamp = (float)(kRegMax - 1 - 0.01);
+            s_tk[0] = fminf(fmaxf(ax - gb.x * inv_s, 0.f), hi_clamp);
+            s_tk[1] = fminf(fmaxf(ay - gb.y * inv_s, 0.f), hi_clamp);
+            s_tk[2] = fminf(fmaxf(gb.z * inv_s - ax, 0.f), hi_clamp);
+            s_tk[3] = fminf(fmaxf(gb.w * inv_s - ay, 0.f), hi_clamp);
+        }
+        // (2b) what is per bin, one HALF-warp per anchor, two anchors per round
+        const int half = lane >> 4, bin = lane & 15, base = lane & 16;
+        FgFetch cur;
+        if (n_sel > 0) cur = fg_fetch<T>(img, cls_row, n_anchors, __shfl_sync(0xffffffffu, win.a, min(half, n_sel - 1)), bin);
+        for (int r0 = 0; r0 < n_sel; r0 += 2) {            // warp-uniform
+            const int r = r0 + half;
+            const bool live = r < n_sel;                   // an idle half walks through the same shuffles and writes nothing
+            const int src = min(r, n_sel - 1);
+            const int idx = __shfl_sync(0xffffffffu, win.a, src);
+            FgFetch nxt = cur;
+            if (r0 + 2 < n_sel)                            // the next round's gathers fly under this round's arithmetic
+                nxt = fg_fetch<T>(img, cls_row, n_anchors, __shfl_sync(0xffffffffu, win.a, min(r + 2, n_sel - 1)), bin);
+            const float kd = lambda_dfl * 0.25f;
+            float dfl4 = 0.f, gk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // softmax and expectation of the side over the 16 lanes of the half (xor offsets <= 8 stay inside it)
+                float m = cur.z[k];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const float zs = cur.z[k] - m;
+                const float ex = fast_ex2(zs * 1.4426950408889634f);
+                float sum = ex;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float p = ex * fast_rcp(sum);
+                float d = p * (float)bin;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                // DFL row (src/model/losses.py:63-78) and the gradient of this lane's logit
+                const float tk = __shfl_sync(0xffffffffu, s_tk[k], src), ddk = __shfl_sync(0xffffffffu, s_dd[k], src);
+                const int bl = (int)tk;
+                const float wl = (float)(bl + 1) - tk, wr = tk - (float)bl;
+                const float lpk = zs - __logf(sum);                          // log-softmax of this lane's bin
+                dfl4 -= __shfl_sync(0xffffffffu, lpk, base + bl) * wl + __shfl_sync(0xffffffffu, lpk, base + bl + 1) * wr;
+                const float oh = (bin == bl ? wl : 0.f) + (bin == bl + 1 ? wr : 0.f);
+                gk[k] = kd * ((wl + wr) * p - oh) + ddk * p * ((float)bin - d);
+            }
+            const float u_box = __shfl_sync(0xffffffffu, s_box, src);
+            if (live) {                                            // no shuffles below
+                const size_t slot = (size_t)g * topk + r;
+                // compact, coalesced: the dense kernel merges these 64 values (times t / normaliser) into the anchor's box rows
+#pragma unroll
+                for (int k = 0; k < 4; ++k) fgrad[slot * (4 * kRegMax) + k * kRegMax + bin] = gk[k];
+                if (bin == 0) {
+                    const float sg = __fdiv_rn(1.f, 1.f + expf(-cur.z_cls));
+                    fterm[slot] = make_float4(u_box, dfl4 * 0.25f, cur.z_cls, sg);
+                    fcell_off[slot] = (long long)((size_t)n * n_ch * n_anchors + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
+                }
+            }
+            cur = nxt;
+        }
+    }
+}
+
+// GTs are handed out to warps from a global counter (no wave quantisation, no idle warps inside a CTA).
+// Measured and not kept: decode CTAs and per-GT CTAs as two roles of ONE launch behind per-image in-kernel dependencies
+// (common.cuh), GT CTAs of image i placed `lag` CTAs behind the image's decode CTAs: 255 / 244 / 225 / 216 us for the
+// assign phase at a lag of 100 / 300 / 1000 / all CTAs against 206 us for the two launches -- the long-lived GT CTAs take
+// the resident slots the streaming role needs to keep HBM busy, and a per-image GT queue balances worse than a global one.
+template <typename T>
+__global__ void __launch_bounds__(32 * kTopkWarps, YB_TOPK_MINBLOCKS)
+tal_gt_kernel(const TalGtArgs<T> A, const unsigned int *__restrict__ grid_rejected, unsigned int *__restrict__ next_gt) {
+    __shared__ int s_aq[kTopkWarps][kTopkQueue];           // queue of inside anchors
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool regular = A.grid.n_levels > 0 && __ldg(grid_rejected) == 0u;   // uniform over the launch
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(next_gt, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= A.gt_total) break;
+        const int n = gt_image(A.gt_off, A.n_images, g);
+        tal_gt_body<T>(A, g, n, g - __ldg(A.gt_off + n), regular, s_aq[warp]);
     }
 }
 
@@ -668,7 +856,7 @@ template <typename T, int VW, bool WRITE_GRAD, bool VFL>
 __global__ void __launch_bounds__(kTalThreads)
 tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ tss_dev,
                float lambda_cls, VflParams vp, const int *__restrict__ aslot, const float *__restrict__ fgrad,
-               T *__restrict__ grad, float *__restrict__ part) {
+               const float *__restrict__ tsc, T *__restrict__ grad, float *__restrict__ part) {
     __shared__ float s_red[kTalThreads / 32];
     // kTalClsSplit CTAs share an anchor tile: each takes a slice of the class rows and of the box rows, so the CTAs
     // are short and the grid has several waves (one CTA per tile left a 1.6-wave grid with a long tail)
@@ -686,17 +874,22 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     f32x2 acc2 = pack2(0.f, 0.f);                          // packed BCE path: two running sums of softplus
     if (a0 < n_anchors) {
         const size_t img = (size_t)n * n_ch * n_anchors + a0;
-        // box rows of the gradient: zero, except the foreground anchors, whose 64 values tal_fg_kernel left in fgrad
-        // (predicated loads, no divergence), here divided by the normaliser.  One box row is written per class row of the loop below, so that the
-        // kernel's reads and writes stay interleaved instead of opening with a write-only burst.
+        // box rows of the gradient: zero, except the foreground anchors, whose 64 values tal_gt_kernel left in fgrad per
+        // unit of the target score (predicated loads, no divergence), here times t / normaliser.  One box row is written per
+        // class row of the loop below, so that the kernel's reads and writes stay interleaved instead of opening with a
+        // write-only burst.
         int fo[VW];                                        // offset of the anchor's 64 values in fgrad, < 0 = background
+        float fs[VW];                                      // t / normaliser of the anchor's slot
 #pragma unroll
-        for (int v = 0; v < VW; ++v)
-            fo[v] = WRITE_GRAD ? (__ldg(aslot + (size_t)n * n_anchors + a0 + v) - 1) * (4 * kRegMax) : -1;
+        for (int v = 0; v < VW; ++v) {
+            const int slot = WRITE_GRAD ? __ldg(aslot + (size_t)n * n_anchors + a0 + v) - 1 : -1;
+            fo[v] = slot * (4 * kRegMax);
+            fs[v] = slot >= 0 ? __ldg(tsc + slot) * inv_tss : 0.f;
+        }
         auto box_row = [&](int c) {
             float vals[VW];
 #pragma unroll
-            for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? __ldg(fgrad + fo[v] + c) * inv_tss : 0.f;
+            for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? __ldg(fgrad + fo[v] + c) * fs[v] : 0.f;
             Group<T, VW>::store(grad + img + (size_t)c * n_anchors, vals);
         };
         const size_t base = img + (size_t)4 * kRegMax * n_anchors;
@@ -756,182 +949,15 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     }
 }
 
-// One HALF-warp per (GT, selected anchor) slot: lane & 15 is the DFL bin, and the lane holds that bin of all four
-// sides, so the scalar part (CIoU, its gradient, the class cell) is issued once for two slots.  The half-warp first
-// works out what tal_topk_kernel left open: whether its GT kept the anchor (conflicts went to the larger overlap)
-// and the GT's largest metric / overlap over the anchors it kept -> the slot's target score t.  Everything written
-// here is NOT yet divided by the normaliser (the sum of all t, possibly over several ranks): tal_cls_kernel and
-// tal_finalize_kernel apply 1 / normaliser.  The target scores are summed in fixed point with integer atomics, so the
-// statistics do not depend on the order in which warps finish.  (Measured and not kept: one THREAD per slot with all 64
-// logits in flight and no shuffles -- 66 us against 60 us: the kernel is bound by its 2.8 million scattered 64-byte DRAM
-// accesses, not by its 38 million warp instructions.)
-template <typename T>
-__global__ void __launch_bounds__(128)
-tal_fg_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc,
-              const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
-              const int *__restrict__ gt_off, int gt_total, int topk, const float4 *__restrict__ sel,
-              const int *__restrict__ sel_count, const unsigned long long *__restrict__ akey, float lambda_box,
-              float lambda_cls, float lambda_dfl, int vfl, VflParams vp, float *__restrict__ fgrad,
-              long long *__restrict__ fcell_off, float *__restrict__ fcell_val, float *__restrict__ fg_box,
-              float *__restrict__ fg_dfl, float *__restrict__ fg_cls, int *__restrict__ aslot,
-              int *__restrict__ out_assigned, float *__restrict__ out_tscore, unsigned long long *__restrict__ stat_acc) {
-    const int lane = threadIdx.x & 31, bin = lane & 15, base = lane & 16;
-    const int slot = blockIdx.x * 8 + (threadIdx.x >> 4);          // slot = g * topk + r
-    const int g_raw = slot / topk, r = slot - g_raw * topk;
-    const bool in_range = g_raw < gt_total;
-    const int g = in_range ? g_raw : 0;
-    const int n = gt_image(gt_off, n_images, g);
-    const int g_local = g - __ldg(gt_off + n);
-    // lane `bin` of the half looks at the GT's bin-th selected anchor
-    const int ns = in_range ? sel_count[g] : 0;
-    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool pos = false;
-    if (bin < ns) {
-        e = sel[(size_t)g * kTalMaxK + bin];
-        const unsigned long long k = akey[(size_t)n * n_anchors + __float_as_int(e.x)];
-        pos = (unsigned int)(k & 0xffffffffull) == (unsigned int)(~(unsigned int)g_local);
-    }
-    float mm = pos ? e.y : 0.f, mo = pos ? e.z : 0.f;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
-    }
-    const float my_t = pos ? e.y * (mo / (mm + kEpsNorm)) : 0.f;
-    // the half's own slot is entry r
-    const int idx_r = __shfl_sync(0xffffffffu, __float_as_int(e.x), base + min(r, 15));
-    const float t_r = __shfl_sync(0xffffffffu, my_t, base + min(r, 15));
-    const bool live = __shfl_sync(0xffffffffu, (int)pos, base + min(r, 15)) != 0 && r < ns;
-    const int idx = live ? idx_r : 0;
-    const float t = live ? t_r : 0.f;
-    if (bin == 0 && in_range) {
-        if (live) {
-            // statistics in fixed point: integer atomics are order-independent, so the sums are run-to-run identical
-            atomicAdd(stat_acc + (slot & (kTalStatAcc - 1)), (unsigned long long)__double2ll_rn((double)t * kTalFix));
-            atomicAdd(stat_acc + kTalStatAcc + (slot & (kTalStatAcc - 1)), 1ull);
-        }
-        if (!live) { fg_box[slot] = 0.f; fg_dfl[slot] = 0.f; fg_cls[slot] = 0.f; fcell_off[slot] = -1; }
-        else {
-            aslot[(size_t)n * n_anchors + idx] = slot + 1;
-            if (out_assigned) out_assigned[(size_t)n * n_anchors + idx] = g_local;
-            if (out_tscore) out_tscore[(size_t)n * n_anchors + idx] = t;
-        }
-    }
-    if (__any_sync(0xffffffffu, live)) {                   // else both halves idle
-        // an idle half walks through the same shuffles on harmless stand-in data and writes nothing
-        const T *img = preds + (size_t)n * n_ch * n_anchors;
-        float z[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) z[k] = load_as_float(img + (size_t)(k * kRegMax + bin) * n_anchors + idx);
-        const float *g5 = gt + (size_t)g * 5;
-        const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
-        int cls = (int)__ldg(g5 + 4);
-        cls = min(max(cls, 0), nc - 1);
-        const float z_cls = load_as_float(img + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
-        const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
-
-        // softmax and expectation of each side over the 16 lanes of the half (xor offsets <= 8 stay inside it)
-        float mx[4], sm[4], pr[4], ds[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float m = z[k];
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            const float ex = expf(z[k] - m);
-            float sum = ex;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float p = __fdiv_rn(ex, sum);
-            float d = p * (float)bin;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            mx[k] = m; sm[k] = sum; pr[k] = p; ds[k] = d;
-        }
-        const PredBox b = decode_box(ax, ay, s, ds[0], ds[1], ds[2], ds[3]);
-        const float4 pb = make_float4(b.x1, b.y1, b.x2, b.y2);
-        const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
-
-        // ---- CIoU and its gradient w.r.t. the predicted corners (alpha_v constant) --------------------
-        const Ciou c = ciou_eval(pb, gb, gt_atan(gb));
-        auto w_gt = [](float a, float o) { return a > o ? 1.f : (a == o ? 0.5f : 0.f); };     // d max(a,o)/da
-        auto w_lt = [](float a, float o) { return a < o ? 1.f : (a == o ? 0.5f : 0.f); };     // d min(a,o)/da
-        const float iw = fmaxf(c.iw_raw, 0.f), ih = fmaxf(c.ih_raw, 0.f);
-        const float d_inter = (c.uni + c.inter) / (c.uni * c.uni);       // d iou / d inter (union contains -inter)
-        const float d_area1 = -c.inter / (c.uni * c.uni);
-        const float d_iw = c.iw_raw >= 0.f ? d_inter * ih : 0.f;
-        const float d_ih = c.ih_raw >= 0.f ? d_inter * iw : 0.f;
-        // iou part
-        float gx1 = -d_iw * w_gt(pb.x, gb.x) - d_area1 * c.h1;
-        float gx2 = d_iw * w_lt(pb.z, gb.z) + d_area1 * c.h1;
-        float gy1 = -d_ih * w_gt(pb.y, gb.y) - d_area1 * c.w1;
-        float gy2 = d_ih * w_lt(pb.w, gb.w) + d_area1 * c.w1;
-        // - rho2 / c2
-        const float inv_c2 = 1.f / c.c2;
-        const float k_r = c.rho2 * inv_c2 * inv_c2;                      // rho2 / c2^2
-        // d rho2/dx1 = d rho2/dx2 = -dxs/2 ;  d c2/dx2 = 2 cw [x2 > u2], d c2/dx1 = -2 cw [x1 < u1]
-        gx1 -= (-0.5f * c.dxs) * inv_c2 - k_r * (-2.f * c.cw * w_lt(pb.x, gb.x));
-        gx2 -= (-0.5f * c.dxs) * inv_c2 - k_r * (2.f * c.cw * w_gt(pb.z, gb.z));
-        gy1 -= (-0.5f * c.dys) * inv_c2 - k_r * (-2.f * c.ch * w_lt(pb.y, gb.y));
-        gy2 -= (-0.5f * c.dys) * inv_c2 - k_r * (2.f * c.ch * w_gt(pb.w, gb.w));
-        // - alpha v :  v = k at^2, at = atan(w2/h2) - atan(w1/h1)
-        const float dv_dA1 = -2.f * kFourOverPi2 * c.at;
-        const float hyp = c.h1 * c.h1 + c.w1 * c.w1;
-        const float dv_dw1 = dv_dA1 * (c.h1 / hyp), dv_dh1 = dv_dA1 * (-c.w1 / hyp);
-        gx1 -= c.alpha * (-dv_dw1);
-        gx2 -= c.alpha * dv_dw1;
-        gy1 -= c.alpha * (-dv_dh1);
-        gy2 -= c.alpha * dv_dh1;
-        // L_box = (1 - ciou) * t / tss * lambda_box   (1 / tss applied later)
-        const float kb = -lambda_box * t;
-        const float dd[4] = {kb * gx1 * (-s), kb * gy1 * (-s), kb * gx2 * s, kb * gy2 * s};   // d / d (dl, dt, dr, db)
-
-        // ---- DFL rows (same target rule as the reference, src/model/losses.py:226-246, :63-78) -------
-        const float tgt[4] = {ax - gb.x / s, ay - gb.y / s, gb.z / s - ax, gb.w / s - ay};
-        const float hi_clamp = (float)(kRegMax - 1 - 0.01);
-        const float kd = lambda_dfl * t * 0.25f;
-        float dfl4 = 0.f, gk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float tk = fminf(fmaxf(tgt[k], 0.f), hi_clamp);
-            const int bl = (int)tk;
-            const float wl = (float)(bl + 1) - tk, wr = tk - (float)bl;
-            const float lpk = (z[k] - mx[k]) - logf(sm[k]);               // log-softmax of this lane's bin
-            dfl4 -= __shfl_sync(0xffffffffu, lpk, base + bl) * wl + __shfl_sync(0xffffffffu, lpk, base + bl + 1) * wr;
-            const float oh = (bin == bl ? wl : 0.f) + (bin == bl + 1 ? wr : 0.f);
-            gk[k] = kd * ((wl + wr) * pr[k] - oh) + dd[k] * pr[k] * ((float)bin - ds[k]);
-        }
-        if (live) {                                            // no shuffles below
-            // compact, coalesced: the dense kernel merges these 64 values (times 1 / normaliser) into the anchor's box rows
-#pragma unroll
-            for (int k = 0; k < 4; ++k) fgrad[(size_t)slot * (4 * kRegMax) + k * kRegMax + bin] = gk[k];
-            if (bin == 0) {
-                // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / tss;
-                // patched in by tal_finalize_kernel after the dense kernel has written the background value
-                const float sg = __fdiv_rn(1.f, 1.f + expf(-z_cls));
-                fcell_off[slot] = (long long)((size_t)n * n_ch * n_anchors + (size_t)(4 * kRegMax + cls) * n_anchors + idx);
-                // varifocal: the positive cell is weighted by its own target score, a constant
-                fcell_val[slot] = lambda_cls * (sg - t) * (vfl ? t : 1.f);
-                fg_box[slot] = (1.f - c.value) * t;
-                fg_dfl[slot] = dfl4 * 0.25f * t;
-                if (vfl) {
-                    // the dense pass counted this cell as background (w_bg * softplus); it is t * BCE(x, t) instead
-                    const float sp = fmaxf(z_cls, 0.f) + log1pf(expf(-fabsf(z_cls)));
-                    fg_cls[slot] = t * (sp - t * z_cls) - vfl_bg_weight(sg, vp) * sp;
-                } else {
-                    fg_cls[slot] = -t * z_cls;                       // BCE(x, t) - BCE(x, 0)
-                }
-            }
-        }
-    }
-}
-
-// [sum of target scores, #foreground] of this rank from the sub-accumulators tal_fg_kernel filled
-__global__ void __launch_bounds__(kTalStatAcc)
-tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *__restrict__ grid_rejected, int have_hint,
-                 float *__restrict__ out_stats, const yb_peer_exchange px) {
+// [sum of target scores, #foreground] of this rank from the fixed-point sub-accumulators, and the producer side of the
+// exchange (csrc/peer.cu).  One whole CTA (>= kTalStatAcc threads), after every slot has been resolved.
+__device__ __forceinline__ void tal_publish_stats(unsigned long long *stat_acc, const unsigned int *grid_rejected, int have_hint,
+                                                  float *__restrict__ out_stats, const yb_peer_exchange &px) {
     __shared__ long long s_t[kTalStatAcc], s_n[kTalStatAcc];
-    s_t[threadIdx.x] = (long long)stat_acc[threadIdx.x];
-    s_n[threadIdx.x] = (long long)stat_acc[kTalStatAcc + threadIdx.x];
+    if (threadIdx.x < kTalStatAcc) {
+        s_t[threadIdx.x] = (long long)__ldcg(stat_acc + threadIdx.x);
+        s_n[threadIdx.x] = (long long)__ldcg(stat_acc + kTalStatAcc + threadIdx.x);
+    }
     __syncthreads();
     for (int o = kTalStatAcc / 2; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) { s_t[threadIdx.x] += s_t[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
@@ -941,7 +967,7 @@ tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *
         stat_acc[2 * kTalStatAcc] = (unsigned long long)s_n[0];
         out_stats[0] = (float)((double)s_t[0] / kTalFix);          // local sum of target scores (un-clamped)
         out_stats[1] = (float)s_n[0];                              // foreground anchors
-        out_stats[2] = have_hint && *grid_rejected ? 1.f : 0.f;    // the grid hint did not describe the anchors
+        out_stats[2] = have_hint && __ldcg(grid_rejected) ? 1.f : 0.f;    // the grid hint did not describe the anchors
 #pragma unroll
         for (int i = 3; i < 8; ++i) out_stats[i] = 0.f;
     }
@@ -956,28 +982,110 @@ tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *
     }
 }
 
+// a rank without boxes still owes its peers an entry
+__global__ void __launch_bounds__(kTalStatAcc)
+tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *__restrict__ grid_rejected, int have_hint,
+                 float *__restrict__ out_stats, const yb_peer_exchange px) {
+    tal_publish_stats(stat_acc, grid_rejected, have_hint, out_stats, px);
+}
+
+// One HALF-warp per GT, lane & 15 = the GT's r-th selected anchor: did the GT keep it (conflicts went to the larger
+// overlap, tal_gt_kernel's atomicMax), the GT's largest metric / overlap over the anchors it kept -> the slot's target
+// score t.  Slots the GT did not keep (or never filled) get t = -1.  The target scores are summed in fixed point with
+// integer atomics, so the statistics do not depend on the order in which warps finish; the last CTA publishes them.
+constexpr int kResolveThreads = 128;
+static_assert(kResolveThreads >= kTalStatAcc, "the last CTA publishes with kTalStatAcc threads");
+__global__ void __launch_bounds__(kResolveThreads)
+tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total, int topk,
+                   const float4 *__restrict__ sel, const int *__restrict__ sel_count,
+                   const unsigned long long *__restrict__ akey, float *__restrict__ tsc, int *__restrict__ aslot,
+                   int *__restrict__ out_assigned, float *__restrict__ out_tscore, unsigned long long *__restrict__ stat_acc,
+                   unsigned int *__restrict__ ticket, const unsigned int *__restrict__ grid_rejected, int have_hint,
+                   float *__restrict__ out_stats, const yb_peer_exchange px) {
+    const int bin = threadIdx.x & 15;
+    const int g = blockIdx.x * (kResolveThreads / 16) + (threadIdx.x >> 4);
+    if ((blockIdx.x * (kResolveThreads / 16) + ((threadIdx.x & ~31) >> 4)) < gt_total) {     // warp-uniform
+        const bool in_range = g < gt_total;
+        const int gg = in_range ? g : gt_total - 1;
+        const int n = gt_image(gt_off, n_images, gg);
+        const int g_local = gg - __ldg(gt_off + n);
+        const int ns = in_range ? sel_count[gg] : 0;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool pos = false;
+        if (bin < ns) {
+            e = sel[(size_t)gg * kTalMaxK + bin];
+            const unsigned long long k = akey[(size_t)n * n_anchors + __float_as_int(e.x)];
+            pos = (unsigned int)(k & 0xffffffffull) == (unsigned int)(~(unsigned int)g_local);
+        }
+        float mm = pos ? e.y : 0.f, mo = pos ? e.z : 0.f;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+            mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+        }
+        const float t = pos ? e.y * (mo / (mm + kEpsNorm)) : -1.f;
+        if (in_range && bin < topk) {
+            const int slot = gg * topk + bin;
+            tsc[slot] = t;
+            if (pos) {
+                const int idx = __float_as_int(e.x);
+                atomicAdd(stat_acc + (slot & (kTalStatAcc - 1)), (unsigned long long)__double2ll_rn((double)t * kTalFix));
+                atomicAdd(stat_acc + kTalStatAcc + (slot & (kTalStatAcc - 1)), 1ull);
+                aslot[(size_t)n * n_anchors + idx] = slot + 1;
+                if (out_assigned) out_assigned[(size_t)n * n_anchors + idx] = g_local;
+                if (out_tscore) out_tscore[(size_t)n * n_anchors + idx] = t;
+            }
+        }
+    }
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    tal_publish_stats(stat_acc, grid_rejected, have_hint, out_stats, px);
+}
+
 // fixed-order reduction in two levels: CTA b sums its slice of every array (tree of fixed shape) and
 // publishes 4 partials; the last CTA to finish adds the partials up in index order.
 constexpr int kTalFinThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kTalFinThreads)
-tal_finalize_kernel(T *__restrict__ grad, const long long *__restrict__ fcell_off, const float *__restrict__ fcell_val,
-                    int n_part, int n_slots, int gt_total, const float *__restrict__ part,
-                    const float *__restrict__ fg_box, const float *__restrict__ fg_dfl, const float *__restrict__ fg_cls,
+tal_finalize_kernel(T *__restrict__ grad, const long long *__restrict__ fcell_off, const float4 *__restrict__ fterm,
+                    const float *__restrict__ tsc, int n_part, int n_slots, const float *__restrict__ part,
                     const unsigned long long *__restrict__ stat_acc, const float *__restrict__ tss_dev, float lambda_box,
-                    float lambda_cls, float lambda_dfl, double *__restrict__ cta_sums, unsigned int *__restrict__ ticket,
-                    float *__restrict__ out_loss) {
+                    float lambda_cls, float lambda_dfl, int vfl, VflParams vp, double *__restrict__ cta_sums,
+                    unsigned int *__restrict__ ticket, float *__restrict__ out_loss) {
     __shared__ double s[3][kTalFinThreads];
     __shared__ bool s_last;
-    (void)gt_total;
     const size_t i = (size_t)blockIdx.x * kTalFinThreads + threadIdx.x;
-    if (grad != nullptr && i < (size_t)n_slots) {          // positive class cell of every foreground anchor
-        const long long cell = fcell_off[i];
-        if (cell >= 0) store_from_float(grad + cell, fcell_val[i] * (1.f / fmaxf(__ldg(tss_dev), 1.f)));
+    float f_cls = 0.f, f_box = 0.f, f_dfl = 0.f;
+    if (i < (size_t)n_slots) {
+        const float t = tsc[i];
+        if (t >= 0.f) {                                    // a foreground anchor: the slot's terms, now that t is known
+            const float4 u = fterm[i];                     // 1 - CIoU, DFL term, class logit, its sigmoid
+            const float z = u.z, sg = u.w;
+            f_box = u.x * t;
+            f_dfl = u.y * t;
+            if (vfl) {
+                // the dense pass counted this cell as background (w_bg * softplus); it is t * BCE(x, t) instead
+                const float sp = fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+                f_cls = t * (sp - t * z) - vfl_bg_weight(sg, vp) * sp;
+            } else {
+                f_cls = -t * z;                            // BCE(x, t) - BCE(x, 0)
+            }
+            // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / normaliser, over
+            // the background value the dense kernel wrote (varifocal: weighted by its own target score, a constant)
+            if (grad != nullptr)
+                store_from_float(grad + fcell_off[i], lambda_cls * (sg - t) * (vfl ? t : 1.f) * (1.f / fmaxf(__ldg(tss_dev), 1.f)));
+        }
     }
-    s[0][threadIdx.x] = (i < (size_t)n_part ? (double)part[i] : 0.0) + (i < (size_t)n_slots ? (double)fg_cls[i] : 0.0);
-    s[1][threadIdx.x] = i < (size_t)n_slots ? (double)fg_box[i] : 0.0;
-    s[2][threadIdx.x] = i < (size_t)n_slots ? (double)fg_dfl[i] : 0.0;
+    s[0][threadIdx.x] = (i < (size_t)n_part ? (double)part[i] : 0.0) + (double)f_cls;
+    s[1][threadIdx.x] = (double)f_box;
+    s[2][threadIdx.x] = (double)f_dfl;
     __syncthreads();
     for (int o = kTalFinThreads / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o)
@@ -1038,23 +1146,25 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
     if (out_tscore) YB_CUDA(cudaMemsetAsync(out_tscore, 0, sizeof(float) * (size_t)n_images * n_anchors, st));
     if (gt_total > 0) {
         constexpr int TILE = kTalThreads * VW;
-        tal_decode_kernel<T, VW><<<dim3((n_anchors + TILE - 1) / TILE, n_images), kTalThreads, 0, st>>>(
+        const int n_tiles = (n_anchors + TILE - 1) / TILE;
+        TalGtArgs<T> A;
+        A.preds = preds; A.n_images = n_images; A.n_ch = n_ch; A.n_anchors = n_anchors;
+        A.anchors = anchors; A.strides = strides; A.gt = gt; A.gt_off = gt_off; A.gt_total = gt_total; A.topk = p.topk;
+        A.alpha = p.alpha; A.beta = p.beta; A.lambda_box = p.lambda_box; A.lambda_dfl = p.lambda_dfl;
+        A.dbox = w.dbox; A.gext = w.gext; A.ctr = w.ctr; A.grid = grid;
+        A.sel = w.sel; A.sel_count = w.sel_count; A.akey = w.akey; A.fterm = w.fterm; A.fgrad = w.fgrad; A.fcell_off = w.fcell_off;
+        A.bad_cls = w.ticket + 2;
+        tal_decode_kernel<T, VW><<<dim3(n_tiles, n_images), kTalThreads, 0, st>>>(
             preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, grid, w.ticket + 3);
         YB_LAUNCH_CHECK();
-        // warps draw (GT, part) units from a counter
-        const int topk_ctas = (int)std::min<long long>(((long long)gt_total * kTopkSplit + kTopkWarps - 1) / kTopkWarps, 148 * YB_TOPK_MINBLOCKS);
-        tal_topk_kernel<T><<<topk_ctas, 32 * kTopkWarps, 0, st>>>(
-            preds, n_images, n_ch, n_anchors, gt, gt_off, gt_total, p.topk, p.alpha, p.beta, w.dbox, w.gext, w.ctr,
-            grid, w.ticket + 3, w.psel, w.gt_done, w.sel, w.sel_count, w.akey, w.ticket + 1, w.ticket + 2);
+        // warps draw GTs from a counter
+        const int gt_ctas = (int)std::min<long long>(((long long)gt_total + kTopkWarps - 1) / kTopkWarps, 148 * YB_TOPK_MINBLOCKS);
+        tal_gt_kernel<T><<<gt_ctas, 32 * kTopkWarps, 0, st>>>(A, w.ticket + 3, w.ticket + 1);
         YB_LAUNCH_CHECK();
-        const int slots = gt_total * p.topk;
-        tal_fg_kernel<T><<<(slots + 7) / 8, 128, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, anchors, strides, gt, gt_off,
-                                                         gt_total, p.topk, w.sel, w.sel_count, w.akey, p.lambda_box, p.lambda_cls,
-                                                         p.lambda_dfl, p.vfl, VflParams{p.vfl_alpha, p.vfl_gamma}, w.fgrad,
-                                                         w.fcell_off, w.fcell_val, w.fg_box, w.fg_dfl, w.fg_cls, w.aslot,
-                                                         out_assigned, out_tscore, w.stat_acc);
-        YB_LAUNCH_CHECK();
-        tal_stats_kernel<<<1, kTalStatAcc, 0, st>>>(w.stat_acc, w.ticket + 3, grid.n_levels > 0, out_stats, px);
+        const int per_cta = kResolveThreads / 16;
+        tal_resolve_kernel<<<(gt_total + per_cta - 1) / per_cta, kResolveThreads, 0, st>>>(
+            n_images, n_anchors, gt_off, gt_total, p.topk, w.sel, w.sel_count, w.akey, w.tsc, w.aslot, out_assigned, out_tscore,
+            w.stat_acc, w.ticket + 5, w.ticket + 3, grid.n_levels > 0, out_stats, px);
         YB_LAUNCH_CHECK();
     } else {
         YB_CUDA(cudaMemsetAsync(out_stats, 0, sizeof(float) * 8, st));
@@ -1076,7 +1186,7 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
         dim3 grid(((n_anchors + TILE - 1) / TILE) * tal_cls_split(TILE), n_images);
 #define YB_TAL_CLS(WG, VF)                                                                                           \
     tal_cls_kernel<T, VW, WG, VF><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, p.lambda_cls, vp, w.aslot, \
-                                                                w.fgrad, grad, w.part)
+                                                                w.fgrad, w.tsc, grad, w.part)
         if (grad != nullptr) { if (p.vfl) YB_TAL_CLS(true, true); else YB_TAL_CLS(true, false); }
         else { if (p.vfl) YB_TAL_CLS(false, true); else YB_TAL_CLS(false, false); }
 #undef YB_TAL_CLS
@@ -1086,10 +1196,9 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
         const int n_part = n_images * w.cls_tiles, n_slots = gt_total * p.topk;
         const int n_max = max(max(n_part, n_slots), 1);
         const int blocks = (n_max + kTalFinThreads - 1) / kTalFinThreads;
-        tal_finalize_kernel<T><<<blocks, kTalFinThreads, 0, st>>>(grad, w.fcell_off, w.fcell_val, n_part, n_slots, gt_total,
-                                                                  w.part, w.fg_box, w.fg_dfl, w.fg_cls, w.stat_acc, tss_dev,
-                                                                  p.lambda_box, p.lambda_cls, p.lambda_dfl, w.cta_sums, w.ticket,
-                                                                  out_loss);
+        tal_finalize_kernel<T><<<blocks, kTalFinThreads, 0, st>>>(grad, w.fcell_off, w.fterm, w.tsc, n_part, n_slots, w.part,
+                                                                  w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl,
+                                                                  p.vfl, vp, w.cta_sums, w.ticket, out_loss);
     }
     YB_LAUNCH_CHECK();
     return YB_OK;

@@ -13,7 +13,7 @@ def build_all():
     for v in VARIANTS:
         so = os.path.join(OUT, f'libtal_{name(v)}.so')
         cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'),
-               '--expt-relaxed-constexpr', '-shared', '-o', so, os.path.join(CSRC, 'tal.cu'), os.path.join(CSRC, 'cabi.cu'), '-lcudart'] + [f'-D{k}={val}' for k, val in v.items()]
+               '--expt-relaxed-constexpr', '-shared', '-o', so, os.path.join(CSRC, 'tal.cu'), os.path.join(CSRC, 'peer.cu'), os.path.join(CSRC, 'cabi.cu'), '-lcudart'] + [f'-D{k}={val}' for k, val in v.items()]
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for v, p in procs:
         out, _ = p.communicate()
@@ -39,8 +39,8 @@ def run_all():
         lib.yb_tal_workspace_bytes.restype = ctypes.c_size_t
         lib.yb_tal_workspace_bytes.argtypes = [ctypes.c_int] * 5
         Pp, I = ctypes.c_void_p, ctypes.c_int
-        lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, Pp, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
-        lib.yb_tal_loss.argtypes = [Pp, I, I, I, I, I, I, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
+        lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, Pp, Pp, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
+        lib.yb_tal_loss.argtypes = [Pp, I, I, I, I, I, I, Pp, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
         lib.yb_last_error.restype = ctypes.c_char_p
         prm = _cabi.TalParams(10, 0.5, 6.0, 1.5, 1.0, 1.5, 0, 0.75, 2.0)
         line = [f'{name(v):24s}']
@@ -51,10 +51,10 @@ def run_all():
             stats = torch.empty(8, device=dev); out = torch.empty(8, device=dev); grad = torch.empty_like(x)
             st = torch.cuda.current_stream().cuda_stream
             def assign():
-                rc = lib.yb_tal_assign(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, ctypes.byref(prm), ctypes.byref(hint) if hint is not None else None, stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st)
+                rc = lib.yb_tal_assign(x.data_ptr(), code, n, 80, 16, A, a.data_ptr(), s.data_ptr(), gt.data_ptr(), off.data_ptr(), G, ctypes.byref(prm), ctypes.byref(hint) if hint is not None else None, None, stats.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st)
                 assert rc == 0, lib.yb_last_error()
             def loss():
-                rc = lib.yb_tal_loss(x.data_ptr(), code, n, 80, 16, A, G, ctypes.byref(prm), stats.data_ptr(), grad.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st)
+                rc = lib.yb_tal_loss(x.data_ptr(), code, n, 80, 16, A, G, ctypes.byref(prm), stats.data_ptr(), None, grad.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st)
                 assert rc == 0, lib.yb_last_error()
             for _ in range(3): assign(); loss()
             torch.cuda.synchronize()
@@ -65,9 +65,9 @@ def run_all():
                 ta += ev[0].elapsed_time(ev[1]); tl += ev[1].elapsed_time(ev[2])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(50): assign(); loss()
+            for _ in range(100): assign(); loss()
             e1.record(); torch.cuda.synchronize()
-            line.append(f'{cn}: assign {ta/30*1e3:6.1f} loss {tl/30*1e3:6.1f} step {e0.elapsed_time(e1)/50*1e3:6.1f} us  L={out[0].item():.5f} gsum={grad.float().abs().sum().item():.4f}')
+            line.append(f'{cn}: assign {ta/30*1e3:6.1f} loss {tl/30*1e3:6.1f} step {e0.elapsed_time(e1)/100*1e3:6.1f} us  L={out[0].item():.5f} gsum={grad.float().abs().sum().item():.4f}')
         print(' | '.join(line), flush=True)
 if __name__ == '__main__':
     build_all() if sys.argv[1] == 'build' else run_all()
