@@ -22,10 +22,11 @@
 //                                          so CIoU / DFL loss and the gradient of the anchor's 64 box logits are left per
 //                                          unit of t (compact buffer); the scattered gathers of one warp run under the
 //                                          ranking arithmetic of the others
-//                   tal_resolve_kernel     one half-warp per GT: which selected anchors did the GT keep, the GT's max
-//                                          metric / overlap -> target score t per slot (or "not kept"), anchor -> slot map;
-//                                          target scores summed in fixed point (integer atomics: order-independent); the
-//                                          last CTA -> [sum of target scores, #foreground] of this rank (+ the peer stores)
+//                                          (3) once every selection is in: which selected anchors did each GT keep, the
+//                                          GT's max metric / overlap -> target score t per slot (or "not kept"), anchor ->
+//                                          slot map; target scores summed in fixed point (integer atomics: order-
+//                                          independent); the last unit -> [sum of target scores, #foreground] of this rank
+//                                          (+ the peer stores)
 //   yb_tal_loss     tal_cls_kernel         dense BCE-with-logits at target 0 + gradient; writes the box rows of the
 //                                          gradient too: zero, or the foreground anchor's 64 values * t / normaliser
 //                                          (predicated loads through the anchor -> slot map, no scattered stores)
@@ -60,7 +61,7 @@ __host__ __device__ constexpr int tal_cls_split(int tile) { return tile >= 1024 
 #endif
 struct TalWorkspace {
     // zeroed by yb_tal_assign's first kernels (the counters by a memset, the per-anchor arrays by tal_decode_kernel)
-    unsigned int *ticket;               // [0] finalize ticket, [1] next GT of tal_gt_kernel, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived, [5] resolve ticket
+    unsigned int *ticket;               // [0] finalize ticket, [1] / [7] / [8] next unit of tal_gt_kernel's three kinds of work, [9] units resolved, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived
     unsigned long long *stat_acc;       // [kTalStatAcc] fixed-point sums of the target scores, [kTalStatAcc] foreground counts, [1] total #foreground
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
     int *aslot;                         // [N * A]  1 + (g * topk + r) of the GT slot that owns the anchor (0 = background)
@@ -70,12 +71,12 @@ struct TalWorkspace {
     float2 *ctr;                        // [A]  anchor centres in pixels
     float *peer_tss;                    // [2]  normaliser and #foreground averaged over the ranks (peer exchange, csrc/peer.cu)
     float4 *sel;                        // [gt_total * kTalMaxK]  anchor bits, metric, overlap, -
-    int *sel_count;                     // [gt_total]
+    int *sel_count;                     // [gt_total]  (image << 8) | number of selected anchors; -1 until the GT's selection is published
     // per slot = (GT, r-th selected anchor), written by tal_gt_kernel PER UNIT of the target score t:
     float4 *fterm;                      // [gt_total * kTalMaxK]  1 - CIoU, DFL term, class logit of the GT's class, its sigmoid
     float *fgrad;                       // [gt_total * kTalMaxK * 64] gradient of the anchor's 64 box logits
     long long *fcell_off;               // [gt_total * kTalMaxK] element offset of the anchor's positive class cell
-    float *tsc;                         // [gt_total * kTalMaxK] target score t of the slot, < 0: the GT did not keep the anchor (tal_resolve_kernel)
+    float *tsc;                         // [gt_total * kTalMaxK] target score t of the slot, < 0: the GT did not keep the anchor (tal_gt_resolve)
     float *part;                        // [N * cls_tiles]
     double *cta_sums;                   // [4 * finalize CTAs]
     int cls_tiles;
@@ -256,10 +257,13 @@ template <typename T, int VW>
 __device__ __forceinline__ void tal_decode_body(int n, int tile, const T *__restrict__ preds, int n_ch, int n_anchors,
                                                 const float *__restrict__ anchors, const float *__restrict__ strides,
                                                 const int *__restrict__ gt_off, float4 *dbox, float4 *gext, float2 *ctr,
-                                                unsigned long long *akey, int *aslot, const TalGrid &grid,
+                                                unsigned long long *akey, int *aslot, int *sel_count, const TalGrid &grid,
                                                 unsigned int *grid_rejected) {
     constexpr int GL = 32 / VW;                            // lanes that share one group of 32 anchors
     const int a0 = (tile * kTalThreads + threadIdx.x) * VW;
+    // arm the "selection published" words of the image's GTs (the image's tiles share the job)
+    for (int m = tile * kTalThreads + threadIdx.x, m_img = gt_off[n + 1] - gt_off[n]; m < m_img; m += gridDim.x * kTalThreads)
+        sel_count[gt_off[n] + m] = -1;
     // arm the per-anchor conflict keys and the anchor -> slot map of this thread's anchors (all images: the dense
     // pass reads the map everywhere)
 #pragma unroll
@@ -326,9 +330,10 @@ __global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : 6)
 tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
                   const float *__restrict__ strides, const int *__restrict__ gt_off, float4 *__restrict__ dbox,
                   float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,
-                  int *__restrict__ aslot, const TalGrid grid, unsigned int *__restrict__ grid_rejected) {
+                  int *__restrict__ aslot, int *__restrict__ sel_count, const TalGrid grid,
+                  unsigned int *__restrict__ grid_rejected) {
     tal_decode_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt_off, dbox, gext, ctr, akey, aslot,
-                           grid, grid_rejected);
+                           sel_count, grid, grid_rejected);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -518,11 +523,6 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
                 }
             }
         };
-        // `cnt` (<= 64) queue entries: lane handles entries lane and 32 + lane
-        auto evaluate = [&](int cnt) {
-            const int a[2] = {lane < cnt ? aq[lane] : -1, lane + 32 < cnt ? aq[lane + 32] : -1};
-            evaluate2(a);
-        };
 
         // Cheap filter in front of the evaluation: a candidate whose plain IoU already bounds its metric at or below the
         // k-th best so far (or strictly below a k-th best known from a seed of central cells) can never be selected; only the
@@ -534,26 +534,11 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
             const int ub = __float_as_int(metric_bound(iou_fast(box_row[a], gb, area_g), beta));
             return ub > thr && ub >= thr_seed;
         };
-        auto enqueue = [&](bool keep, int a) {             // whole warp; appends the kept anchors in lane order
-            const unsigned mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a;
-            nq += __popc(mask);
-            __syncwarp();
-            if (nq >= 64) {                                // warp-uniform
-                evaluate(64);
-                const int rest = nq - 64;                  // < 32
-                const int keep_a = lane < rest ? aq[64 + lane] : 0;
-                __syncwarp();
-                if (lane < rest) aq[lane] = keep_a;
-                nq = rest;
-                __syncwarp();
-            }
-        };
 
+        // lane l works out the rectangle of level l (the others fetch it by shuffle)
+        int r_x0 = 0, r_y0 = 0, r_nx = 0, r_ny = 0;
         if (regular) {
             // ---- the anchors form regular grids: the inside anchors of a level are a rectangle of cells --------
-            // lane l works out the rectangle of level l (the others fetch it by shuffle)
-            int r_x0 = 0, r_y0 = 0, r_nx = 0, r_ny = 0;
             if (lane < n_levels) {
                 const int W = grid.w[lane], H = grid.h[lane];
                 const float s = grid.stride[lane], x0 = grid.x0[lane], y0 = grid.y0[lane];
@@ -604,41 +589,72 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
                 }
                 thr_seed = kth == kEmptyKey ? -1 : kth;
             }
-            for (int l = 0; l < n_levels; ++l) {
-                const int ix0 = __shfl_sync(0xffffffffu, r_x0, l), iy0 = __shfl_sync(0xffffffffu, r_y0, l);
-                const int nx = __shfl_sync(0xffffffffu, r_nx, l), ny = __shfl_sync(0xffffffffu, r_ny, l);
-                if (nx <= 0 || ny <= 0) continue;          // uniform
-                const int W = grid.w[l], st = grid.start[l];
-                const int cells = nx * ny;
-                const float inv_nx = 1.f / (float)nx;
-                for (int c0 = 0; c0 < cells; c0 += 32) {
+        }
+        // One loop for both forms of the enumeration, so that the evaluation below exists ONCE in the kernel (one copy of
+        // its arithmetic: the two forms give bit-identical metrics; and a third of the code).  Each round yields up to 32
+        // candidates in ascending anchor order -- the next cells of the current level's rectangle, or the next group of 32
+        // anchors whose centre extent meets the GT -- which pass the cheap filter into the queue.
+        int lvl = -1, c0 = 0, cells = 0, ix0 = 0, iy0 = 0, nx = 1, lw = 0, lst = 0;        // grid form
+        float inv_nx = 1.f;
+        int gb0 = -32;                                                                      // group form
+        unsigned groups = 0u;
+        for (bool more = true; more;) {
+            int a = -1;
+            bool keep = false;
+            if (regular) {
+                while (c0 >= cells) {                      // warp-uniform: on to the next level with cells inside the GT
+                    if (++lvl >= n_levels) { more = false; break; }
+                    ix0 = __shfl_sync(0xffffffffu, r_x0, lvl); iy0 = __shfl_sync(0xffffffffu, r_y0, lvl);
+                    nx = __shfl_sync(0xffffffffu, r_nx, lvl);
+                    cells = nx * __shfl_sync(0xffffffffu, r_ny, lvl);
+                    lw = grid.w[lvl]; lst = grid.start[lvl];
+                    inv_nx = 1.f / (float)max(nx, 1);
+                    c0 = 0;
+                }
+                if (more) {
                     const int c = c0 + lane;
                     int row = (int)(((float)c + 0.5f) * inv_nx), col = c - row * nx;
                     if (col < 0) { --row; col += nx; } else if (col >= nx) { ++row; col -= nx; }
-                    const int a = st + (iy0 + row) * W + ix0 + col;
-                    enqueue(c < cells && survives(a), a);
+                    a = lst + (iy0 + row) * lw + ix0 + col;
+                    keep = c < cells && survives(a);
+                    c0 += 32;
                 }
-            }
-        } else {
-            // ---- no structure assumed: lane l of round i looks at the centre extent of group i * 32 + l --------
-            for (int gb0 = 0; gb0 < n_groups; gb0 += 32) {
-                const int my_group = gb0 + lane;
-                float4 ext = make_float4(0.f, 0.f, -1.f, -1.f);   // an empty extent never intersects
-                if (my_group < n_groups) ext = gext[my_group];
-                unsigned groups = __ballot_sync(0xffffffffu, gb.x < ext.z && gb.z > ext.x && gb.y < ext.w && gb.w > ext.y);
-                while (groups) {
-                    const int a = ((gb0 + (__ffs(groups) - 1)) << 5) + lane;
+            } else {
+                while (groups == 0u) {                     // warp-uniform: lane l looks at the centre extent of group gb0 + l
+                    gb0 += 32;
+                    if (gb0 >= n_groups) { more = false; break; }
+                    float4 ext = make_float4(0.f, 0.f, -1.f, -1.f);   // an empty extent never intersects
+                    if (gb0 + lane < n_groups) ext = gext[gb0 + lane];
+                    groups = __ballot_sync(0xffffffffu, gb.x < ext.z && gb.z > ext.x && gb.y < ext.w && gb.w > ext.y);
+                }
+                if (more) {
+                    a = ((gb0 + (__ffs(groups) - 1)) << 5) + lane;
                     groups &= groups - 1;
                     bool in = false;
                     if (a < n_anchors) {
                         const float2 c = ctr[a];
                         in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
                     }
-                    enqueue(in && survives(a), a);
+                    keep = in && survives(a);
                 }
             }
+            // append the kept anchors in lane order; evaluate 64 at a time (and what is left once the enumeration ends)
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a;
+            nq += __popc(mask);
+            __syncwarp();
+            while (nq >= 64 || (!more && nq > 0)) {        // warp-uniform
+                const int cnt = min(nq, 64);
+                const int a2[2] = {lane < cnt ? aq[lane] : -1, lane + 32 < cnt ? aq[lane + 32] : -1};
+                evaluate2(a2);
+                const int rest = nq - cnt;                 // < 32
+                const int keep_a = lane < rest ? aq[64 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) aq[lane] = keep_a;
+                nq = rest;
+                __syncwarp();
+            }
         }
-        if (nq > 0) evaluate(nq);
         __syncwarp();                                      // the queue is reused by the warp's next GT
 
         // ---- publish the GT's list; conflicts: the anchor goes to the GT with the largest overlap, ties -> lowest GT ----
@@ -648,16 +664,48 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
             atomicMax(akey + (size_t)n * n_anchors + win.a,
                       ((unsigned long long)__float_as_uint(win.o) << 32) | (unsigned int)(~(unsigned int)g_local));
         }
-        if (lane == 0) sel_count[g] = n_sel;
+        __threadfence();                                   // the list before the word that announces it
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int *>(sel_count + g) = (n << 8) | n_sel;
+    }
+}
 
-        // ---- (2) foreground terms of the selected anchors, per unit of the target score ----------------------------
+// (2) The foreground terms of GT g's selected anchors, per unit of the target score, by one warp -- any warp, once the GT's
+// selection is published.
+template <typename T>
+__device__ __forceinline__ void tal_gt_terms(const TalGtArgs<T> &A, int g) {
+    const int lane = threadIdx.x & 31;
+    const T *__restrict__ preds = A.preds;
+    const float *__restrict__ anchors = A.anchors, *__restrict__ strides = A.strides, *__restrict__ gt = A.gt;
+    const int n_ch = A.n_ch, n_anchors = A.n_anchors, topk = A.topk;
+    const float lambda_box = A.lambda_box, lambda_dfl = A.lambda_dfl;
+    float4 *__restrict__ fterm = A.fterm;
+    float *__restrict__ fgrad = A.fgrad;
+    long long *__restrict__ fcell_off = A.fcell_off;
+    const int n_cls = n_ch - 4 * kRegMax;
+    {
+        // wait for the selection (the warp that owns it drew the GT before this one did, so it is running or done)
+        int packed;
+        do {
+            packed = (int)ld_acquire_u32(reinterpret_cast<const unsigned int *>(A.sel_count + g));
+        } while (packed < 0);
+        const int n = packed >> 8, n_sel = packed & 0xff;
+        if (n_sel == 0) return;                            // warp-uniform
+        const float *g5 = gt + (size_t)g * 5;
+        const float gcx = __ldg(g5), gcy = __ldg(g5 + 1), gw = __ldg(g5 + 2), gh = __ldg(g5 + 3);
+        const float4 gb = make_float4(gcx - gw * 0.5f, gcy - gh * 0.5f, gcx + gw * 0.5f, gcy + gh * 0.5f);
+        const int cls = min(max((int)__ldg(g5 + 4), 0), n_cls - 1);
+        const T *img = preds + (size_t)n * n_ch * n_anchors;
+        const T *cls_row = img + (size_t)(4 * kRegMax + cls) * n_anchors;
+        const float4 *box_row = A.dbox + (size_t)n * n_anchors;
+        // lane r: the r-th selected anchor
+        const int my_a = __float_as_int(__ldcg(A.sel + (size_t)g * kTalMaxK + min(lane, n_sel - 1)).x);
         // (2a) what is scalar per anchor -- CIoU, its gradient w.r.t. the four distances, the DFL target of each side --
         // once, lane r for the r-th selected anchor (spec: oracle/tal_oracle.py::ciou; the exact arithmetic from here on).
         // The box is the one tal_decode_kernel left in the workspace.
         float s_dd[4], s_tk[4], s_box;
         {
-            const int ar = __shfl_sync(0xffffffffu, win.a, lane < n_sel ? lane : 0);     // idle lanes shadow anchor 0 of the list
-            const int idx = n_sel > 0 ? ar : 0;
+            const int idx = my_a;
             const float4 pb = box_row[idx];
             const float ax = __ldg(anchors + idx), ay = __ldg(anchors + n_anchors + idx), s = __ldg(strides + idx);
             const Ciou c = ciou_eval(pb, gb, gt_atan(gb));
@@ -705,15 +753,15 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
         // (2b) what is per bin, one HALF-warp per anchor, two anchors per round
         const int half = lane >> 4, bin = lane & 15, base = lane & 16;
         FgFetch cur;
-        if (n_sel > 0) cur = fg_fetch<T>(img, cls_row, n_anchors, __shfl_sync(0xffffffffu, win.a, min(half, n_sel - 1)), bin);
+        cur = fg_fetch<T>(img, cls_row, n_anchors, __shfl_sync(0xffffffffu, my_a, min(half, n_sel - 1)), bin);
         for (int r0 = 0; r0 < n_sel; r0 += 2) {            // warp-uniform
             const int r = r0 + half;
             const bool live = r < n_sel;                   // an idle half walks through the same shuffles and writes nothing
             const int src = min(r, n_sel - 1);
-            const int idx = __shfl_sync(0xffffffffu, win.a, src);
+            const int idx = __shfl_sync(0xffffffffu, my_a, src);
             FgFetch nxt = cur;
             if (r0 + 2 < n_sel)                            // the next round's gathers fly under this round's arithmetic
-                nxt = fg_fetch<T>(img, cls_row, n_anchors, __shfl_sync(0xffffffffu, win.a, min(r + 2, n_sel - 1)), bin);
+                nxt = fg_fetch<T>(img, cls_row, n_anchors, __shfl_sync(0xffffffffu, my_a, min(r + 2, n_sel - 1)), bin);
             const float kd = lambda_dfl * 0.25f;
             float dfl4 = 0.f, gk[4];
 #pragma unroll
@@ -757,6 +805,99 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
     }
 }
 
+// [sum of target scores, #foreground] of this rank from the fixed-point sub-accumulators, and the producer side of the
+// exchange (csrc/peer.cu).  One whole WARP, after every slot has been resolved.
+__device__ __forceinline__ void tal_publish_stats(unsigned long long *stat_acc, const unsigned int *grid_rejected, int have_hint,
+                                                  float *__restrict__ out_stats, const yb_peer_exchange &px) {
+    static_assert(kTalStatAcc == 64, "two sub-accumulators per lane");
+    const int lane = threadIdx.x & 31;
+    long long s_t = (long long)__ldcg(stat_acc + lane) + (long long)__ldcg(stat_acc + 32 + lane);
+    long long s_n = (long long)__ldcg(stat_acc + kTalStatAcc + lane) + (long long)__ldcg(stat_acc + kTalStatAcc + 32 + lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_t += __shfl_xor_sync(0xffffffffu, s_t, o);
+        s_n += __shfl_xor_sync(0xffffffffu, s_n, o);
+    }
+    const float t = (float)((double)s_t / kTalFix), nf = (float)s_n;
+    if (lane == 0) stat_acc[2 * kTalStatAcc] = (unsigned long long)s_n;
+    if (lane < 8)
+        out_stats[lane] = lane == 0 ? t                                                 // local sum of target scores (un-clamped)
+                        : lane == 1 ? nf                                                // foreground anchors
+                        : lane == 2 ? (have_hint && __ldcg(grid_rejected) ? 1.f : 0.f)  // the grid hint did not describe the anchors
+                                    : 0.f;
+    // the exchange, producer side (csrc/peer.cu): lane r stores this rank's entry of step px.seq into rank r's mailbox —
+    // a peer store over NVLink / NVSwitch for r != rank.  Two self-validating 8-byte words: (seq << 32) | payload.
+    for (int r = lane; r < px.world; r += 32) {
+        volatile unsigned long long *e = static_cast<unsigned long long *>(px.mailbox[r]) +
+                                         ((size_t)(px.seq % kPeerSlotsTal) * YB_PEER_MAX_WORLD + px.rank) * 2;
+        e[0] = ((unsigned long long)px.seq << 32) | __float_as_uint(t);
+        e[1] = ((unsigned long long)px.seq << 32) | __float_as_uint(nf);
+    }
+}
+
+// a rank without boxes still owes its peers an entry
+__global__ void __launch_bounds__(32)
+tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *__restrict__ grid_rejected, int have_hint,
+                 float *__restrict__ out_stats, const yb_peer_exchange px) {
+    tal_publish_stats(stat_acc, grid_rejected, have_hint, out_stats, px);
+}
+
+// (3) What stays open until every GT of an image has published its selection: did the GT keep the anchor (conflicts went
+// to the larger overlap: the atomicMax on akey), and from the GT's largest metric / overlap over the anchors it kept, the
+// target score t of every slot (t = -1: not kept, or never filled).  One HALF-warp per GT, lane & 15 = the GT's r-th
+// selected anchor; GTs 2u and 2u + 1 by one warp.  The target scores are summed in fixed point with integer atomics, so
+// the statistics do not depend on the order in which warps finish.
+struct TalResolveArgs {
+    float *tsc;
+    int *aslot;
+    int *out_assigned;
+    float *out_tscore;
+    unsigned long long *stat_acc;
+};
+template <typename T>
+__device__ __forceinline__ void tal_gt_resolve(const TalGtArgs<T> &A, const TalResolveArgs &R, int unit) {
+    const int lane = threadIdx.x & 31, bin = lane & 15;
+    const int g = 2 * unit + (lane >> 4);
+    const bool in_range = g < A.gt_total;
+    const int gg = in_range ? g : A.gt_total - 1;
+    // the image(s) of the two GTs must be complete: every selection of theirs published (all were drawn before this unit)
+    const int n_lo = gt_image(A.gt_off, A.n_images, 2 * unit), n_hi = gt_image(A.gt_off, A.n_images, min(2 * unit + 1, A.gt_total - 1));
+    for (int i = __ldg(A.gt_off + n_lo) + lane, end = __ldg(A.gt_off + n_hi + 1); __any_sync(0xffffffffu, i < end); i += 32)
+        if (i < end)
+            while ((int)ld_acquire_u32(reinterpret_cast<const unsigned int *>(A.sel_count + i)) < 0) {}
+    __syncwarp();
+    const int packed = __ldcg(A.sel_count + gg);           // (image << 8) | count
+    const int n = packed >> 8;
+    const int g_local = gg - __ldg(A.gt_off + n);
+    const int ns = in_range ? packed & 0xff : 0;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool pos = false;
+    if (bin < ns) {
+        e = __ldcg(A.sel + (size_t)gg * kTalMaxK + bin);
+        const unsigned long long k = __ldcg(A.akey + (size_t)n * A.n_anchors + __float_as_int(e.x));
+        pos = (unsigned int)(k & 0xffffffffull) == (unsigned int)(~(unsigned int)g_local);
+    }
+    float mm = pos ? e.y : 0.f, mo = pos ? e.z : 0.f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    }
+    const float t = pos ? e.y * (mo / (mm + kEpsNorm)) : -1.f;
+    if (in_range && bin < A.topk) {
+        const int slot = gg * A.topk + bin;
+        R.tsc[slot] = t;
+        if (pos) {
+            const int idx = __float_as_int(e.x);
+            atomicAdd(R.stat_acc + (slot & (kTalStatAcc - 1)), (unsigned long long)__double2ll_rn((double)t * kTalFix));
+            atomicAdd(R.stat_acc + kTalStatAcc + (slot & (kTalStatAcc - 1)), 1ull);
+            R.aslot[(size_t)n * A.n_anchors + idx] = slot + 1;
+            if (R.out_assigned) R.out_assigned[(size_t)n * A.n_anchors + idx] = g_local;
+            if (R.out_tscore) R.out_tscore[(size_t)n * A.n_anchors + idx] = t;
+        }
+    }
+}
+
 // GTs are handed out to warps from a global counter (no wave quantisation, no idle warps inside a CTA).
 // Measured and not kept: decode CTAs and per-GT CTAs as two roles of ONE launch behind per-image in-kernel dependencies
 // (common.cuh), GT CTAs of image i placed `lag` CTAs behind the image's decode CTAs: 255 / 244 / 225 / 216 us for the
@@ -764,10 +905,17 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
 // the resident slots the streaming role needs to keep HBM busy, and a per-image GT queue balances worse than a global one.
 template <typename T>
 __global__ void __launch_bounds__(32 * kTopkWarps, YB_TOPK_MINBLOCKS)
-tal_gt_kernel(const TalGtArgs<T> A, const unsigned int *__restrict__ grid_rejected, unsigned int *__restrict__ next_gt) {
+tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *__restrict__ grid_rejected,
+              unsigned int *__restrict__ next_gt, int have_hint, float *__restrict__ out_stats, const yb_peer_exchange px) {
     __shared__ int s_aq[kTopkWarps][kTopkQueue];           // queue of inside anchors
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool regular = A.grid.n_levels > 0 && __ldg(grid_rejected) == 0u;   // uniform over the launch
+    // Three kinds of work units, three counters: first every GT's selection (the long kind), then every GT's foreground
+    // terms (the short kind) by whichever warp comes free -- a warp that runs out of selections while others are still
+    // ranking goes on with terms instead of idling --, last the target scores (tiny: the launch ends on them), whose
+    // last unit publishes the rank's statistics.  (Measured and not kept: the warp that finishes an image's last GT
+    // resolving that image, one lane per GT: a release fence per GT and a serial tail per image, 216 us against 185 us
+    // for the assign phase; the target scores as a launch of their own: 10 us more.)
     for (;;) {
         int g = 0;
         if (lane == 0) g = (int)atomicAdd(next_gt, 1u);
@@ -775,6 +923,30 @@ tal_gt_kernel(const TalGtArgs<T> A, const unsigned int *__restrict__ grid_reject
         if (g >= A.gt_total) break;
         const int n = gt_image(A.gt_off, A.n_images, g);
         tal_gt_body<T>(A, g, n, g - __ldg(A.gt_off + n), regular, s_aq[warp]);
+    }
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = (int)atomicAdd(next_gt + 6, 1u);     // ticket[7]
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= A.gt_total) break;
+        tal_gt_terms<T>(A, g);
+    }
+    const int n_units = (A.gt_total + 1) >> 1;
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = (int)atomicAdd(next_gt + 7, 1u);     // ticket[8]
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        tal_gt_resolve<T>(A, R, u);
+        __threadfence();                                   // this unit's statistics and slots before the count below
+        __syncwarp();
+        unsigned int before = 0;
+        if (lane == 0) before = atomicAdd(next_gt + 8, 1u);     // ticket[9]: units resolved
+        before = __shfl_sync(0xffffffffu, before, 0);
+        if ((int)before == n_units - 1) {                   // the launch's last unit
+            __threadfence();
+            tal_publish_stats(R.stat_acc, grid_rejected, have_hint, out_stats, px);
+        }
     }
 }
 
@@ -949,106 +1121,6 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     }
 }
 
-// [sum of target scores, #foreground] of this rank from the fixed-point sub-accumulators, and the producer side of the
-// exchange (csrc/peer.cu).  One whole CTA (>= kTalStatAcc threads), after every slot has been resolved.
-__device__ __forceinline__ void tal_publish_stats(unsigned long long *stat_acc, const unsigned int *grid_rejected, int have_hint,
-                                                  float *__restrict__ out_stats, const yb_peer_exchange &px) {
-    __shared__ long long s_t[kTalStatAcc], s_n[kTalStatAcc];
-    if (threadIdx.x < kTalStatAcc) {
-        s_t[threadIdx.x] = (long long)__ldcg(stat_acc + threadIdx.x);
-        s_n[threadIdx.x] = (long long)__ldcg(stat_acc + kTalStatAcc + threadIdx.x);
-    }
-    __syncthreads();
-    for (int o = kTalStatAcc / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) { s_t[threadIdx.x] += s_t[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        stat_acc[2 * kTalStatAcc] = (unsigned long long)s_n[0];
-        out_stats[0] = (float)((double)s_t[0] / kTalFix);          // local sum of target scores (un-clamped)
-        out_stats[1] = (float)s_n[0];                              // foreground anchors
-        out_stats[2] = have_hint && __ldcg(grid_rejected) ? 1.f : 0.f;    // the grid hint did not describe the anchors
-#pragma unroll
-        for (int i = 3; i < 8; ++i) out_stats[i] = 0.f;
-    }
-    // the exchange, producer side (csrc/peer.cu): thread r stores this rank's entry of step px.seq into rank r's mailbox —
-    // a peer store over NVLink / NVSwitch for r != rank.  Two self-validating 8-byte words: (seq << 32) | payload.
-    if ((int)threadIdx.x < px.world) {
-        const float t = (float)((double)s_t[0] / kTalFix), nf = (float)s_n[0];
-        volatile unsigned long long *e = static_cast<unsigned long long *>(px.mailbox[threadIdx.x]) +
-                                         ((size_t)(px.seq % kPeerSlotsTal) * YB_PEER_MAX_WORLD + px.rank) * 2;
-        e[0] = ((unsigned long long)px.seq << 32) | __float_as_uint(t);
-        e[1] = ((unsigned long long)px.seq << 32) | __float_as_uint(nf);
-    }
-}
-
-// a rank without boxes still owes its peers an entry
-__global__ void __launch_bounds__(kTalStatAcc)
-tal_stats_kernel(unsigned long long *__restrict__ stat_acc, const unsigned int *__restrict__ grid_rejected, int have_hint,
-                 float *__restrict__ out_stats, const yb_peer_exchange px) {
-    tal_publish_stats(stat_acc, grid_rejected, have_hint, out_stats, px);
-}
-
-// One HALF-warp per GT, lane & 15 = the GT's r-th selected anchor: did the GT keep it (conflicts went to the larger
-// overlap, tal_gt_kernel's atomicMax), the GT's largest metric / overlap over the anchors it kept -> the slot's target
-// score t.  Slots the GT did not keep (or never filled) get t = -1.  The target scores are summed in fixed point with
-// integer atomics, so the statistics do not depend on the order in which warps finish; the last CTA publishes them.
-constexpr int kResolveThreads = 128;
-static_assert(kResolveThreads >= kTalStatAcc, "the last CTA publishes with kTalStatAcc threads");
-__global__ void __launch_bounds__(kResolveThreads)
-tal_resolve_kernel(int n_images, int n_anchors, const int *__restrict__ gt_off, int gt_total, int topk,
-                   const float4 *__restrict__ sel, const int *__restrict__ sel_count,
-                   const unsigned long long *__restrict__ akey, float *__restrict__ tsc, int *__restrict__ aslot,
-                   int *__restrict__ out_assigned, float *__restrict__ out_tscore, unsigned long long *__restrict__ stat_acc,
-                   unsigned int *__restrict__ ticket, const unsigned int *__restrict__ grid_rejected, int have_hint,
-                   float *__restrict__ out_stats, const yb_peer_exchange px) {
-    const int bin = threadIdx.x & 15;
-    const int g = blockIdx.x * (kResolveThreads / 16) + (threadIdx.x >> 4);
-    if ((blockIdx.x * (kResolveThreads / 16) + ((threadIdx.x & ~31) >> 4)) < gt_total) {     // warp-uniform
-        const bool in_range = g < gt_total;
-        const int gg = in_range ? g : gt_total - 1;
-        const int n = gt_image(gt_off, n_images, gg);
-        const int g_local = gg - __ldg(gt_off + n);
-        const int ns = in_range ? sel_count[gg] : 0;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool pos = false;
-        if (bin < ns) {
-            e = sel[(size_t)gg * kTalMaxK + bin];
-            const unsigned long long k = akey[(size_t)n * n_anchors + __float_as_int(e.x)];
-            pos = (unsigned int)(k & 0xffffffffull) == (unsigned int)(~(unsigned int)g_local);
-        }
-        float mm = pos ? e.y : 0.f, mo = pos ? e.z : 0.f;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-            mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
-        }
-        const float t = pos ? e.y * (mo / (mm + kEpsNorm)) : -1.f;
-        if (in_range && bin < topk) {
-            const int slot = gg * topk + bin;
-            tsc[slot] = t;
-            if (pos) {
-                const int idx = __float_as_int(e.x);
-                atomicAdd(stat_acc + (slot & (kTalStatAcc - 1)), (unsigned long long)__double2ll_rn((double)t * kTalFix));
-                atomicAdd(stat_acc + kTalStatAcc + (slot & (kTalStatAcc - 1)), 1ull);
-                aslot[(size_t)n * n_anchors + idx] = slot + 1;
-                if (out_assigned) out_assigned[(size_t)n * n_anchors + idx] = g_local;
-                if (out_tscore) out_tscore[(size_t)n * n_anchors + idx] = t;
-            }
-        }
-    }
-    __shared__ bool s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    tal_publish_stats(stat_acc, grid_rejected, have_hint, out_stats, px);
-}
-
 // fixed-order reduction in two levels: CTA b sums its slice of every array (tree of fixed shape) and
 // publishes 4 partials; the last CTA to finish adds the partials up in index order.
 constexpr int kTalFinThreads = 256;
@@ -1155,21 +1227,18 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
         A.sel = w.sel; A.sel_count = w.sel_count; A.akey = w.akey; A.fterm = w.fterm; A.fgrad = w.fgrad; A.fcell_off = w.fcell_off;
         A.bad_cls = w.ticket + 2;
         tal_decode_kernel<T, VW><<<dim3(n_tiles, n_images), kTalThreads, 0, st>>>(
-            preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, grid, w.ticket + 3);
+            preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3);
         YB_LAUNCH_CHECK();
         // warps draw GTs from a counter
         const int gt_ctas = (int)std::min<long long>(((long long)gt_total + kTopkWarps - 1) / kTopkWarps, 148 * YB_TOPK_MINBLOCKS);
-        tal_gt_kernel<T><<<gt_ctas, 32 * kTopkWarps, 0, st>>>(A, w.ticket + 3, w.ticket + 1);
-        YB_LAUNCH_CHECK();
-        const int per_cta = kResolveThreads / 16;
-        tal_resolve_kernel<<<(gt_total + per_cta - 1) / per_cta, kResolveThreads, 0, st>>>(
-            n_images, n_anchors, gt_off, gt_total, p.topk, w.sel, w.sel_count, w.akey, w.tsc, w.aslot, out_assigned, out_tscore,
-            w.stat_acc, w.ticket + 5, w.ticket + 3, grid.n_levels > 0, out_stats, px);
+        TalResolveArgs R;
+        R.tsc = w.tsc; R.aslot = w.aslot; R.out_assigned = out_assigned; R.out_tscore = out_tscore; R.stat_acc = w.stat_acc;
+        tal_gt_kernel<T><<<gt_ctas, 32 * kTopkWarps, 0, st>>>(A, R, w.ticket + 3, w.ticket + 1, grid.n_levels > 0, out_stats, px);
         YB_LAUNCH_CHECK();
     } else {
         YB_CUDA(cudaMemsetAsync(out_stats, 0, sizeof(float) * 8, st));
         if (px.world > 0) {                                // a rank without boxes still owes its peers an entry
-            tal_stats_kernel<<<1, kTalStatAcc, 0, st>>>(w.stat_acc, w.ticket + 3, 0, out_stats, px);
+            tal_stats_kernel<<<1, 32, 0, st>>>(w.stat_acc, w.ticket + 3, 0, out_stats, px);
             YB_LAUNCH_CHECK();
         }
     }

@@ -6,14 +6,14 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 CSRC = os.path.join(ROOT, 'custom-yolo-implmentation_b200', 'csrc')
 OUT = os.path.join(ROOT, 'scratch', 'variants')
 VARIANTS = json.load(open(os.path.join(ROOT, 'scratch', 'tal_variants.json')))
-def name(v): return 'base' if not v else '_'.join(f"{k[3:].lower()}{val}" for k, val in sorted(v.items()))
+def name(v): return v['_name'] if '_name' in v else 'base' if not v else '_'.join(f"{k[3:].lower()}{val}" for k, val in sorted(v.items()))
 def build_all():
     os.makedirs(OUT, exist_ok=True)
     procs = []
     for v in VARIANTS:
         so = os.path.join(OUT, f'libtal_{name(v)}.so')
         cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'),
-               '--expt-relaxed-constexpr', '-shared', '-o', so, os.path.join(CSRC, 'tal.cu'), os.path.join(CSRC, 'peer.cu'), os.path.join(CSRC, 'cabi.cu'), '-lcudart'] + [f'-D{k}={val}' for k, val in v.items()]
+               '--expt-relaxed-constexpr', '-shared', '-o', so, os.path.join(ROOT, v['_src']) if '_src' in v else os.path.join(CSRC, 'tal.cu'), os.path.join(CSRC, 'peer.cu'), os.path.join(CSRC, 'cabi.cu'), '-lcudart', '-I', CSRC] + [f'-D{k}={val}' for k, val in v.items() if not k.startswith('_')]
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for v, p in procs:
         out, _ = p.communicate()
