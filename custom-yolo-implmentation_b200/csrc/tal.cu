@@ -250,7 +250,8 @@ __device__ __forceinline__ bool grid_matches(const TalGrid &gr, int a, float ax,
 // ------------------------------------------------------------------------------------------
 // tal_decode_kernel: the streaming half of the assignment.  One thread per VW consecutive anchors reads the
 // 4 x 16 box rows (128-bit loads, 8 rows in flight), and leaves the decoded pixel box of every anchor in the
-// workspace (16 B per anchor: 17 MB at cfg2, it stays in L2 for tal_topk_kernel).  The CTAs of image 0 also
+// workspace (16 B per anchor: 17 MB at cfg2, it stays in L2 for tal_gt_kernel; loading the box rows with an L2
+// evict-first policy to protect it changed nothing, 171.2 vs 171.3 us for the assign phase).  The CTAs of image 0 also
 // write the anchor CENTRES in pixels and their extent per group of 32 consecutive anchors (the same for all images).
 // ------------------------------------------------------------------------------------------
 template <typename T, int VW>
