@@ -68,11 +68,24 @@ static NmsWorkspace carve_nms(void *base, int n_images, int n_anchors) {
     return w;
 }
 
-template <int VW>
+// Where a launch finds its inputs.  The reference hands NMS one (N, 4 + nc, A) fp32 tensor [xywh | scores]
+// (src/utils/model_utils.py:174); the fused post-processing entry point (yb_postprocess) reads the scores straight from
+// the head output (N, 64 + nc, A), fp32 or bf16, optionally through a sigmoid, and the boxes from a compact (N, 4, A)
+// buffer the decode kernel wrote.
+struct NmsInput {
+    const float *box;            // image b: box + b * box_stride, rows x, y, w, h of n_anchors floats each
+    size_t box_stride;
+    const void *score;           // image b: score + b * score_stride (elements), nc rows of n_anchors elements
+    size_t score_stride;
+};
+
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }   // as Tensor.sigmoid()
+
+template <typename T, int VW, bool SIGMOID>
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const float *__restrict__ pred, int nc, int n_anchors, float conf, const int *__restrict__ filter,
-                int n_filter, int *__restrict__ count, int *__restrict__ cls_out, unsigned long long *__restrict__ keys,
-                int a_pad) {
+nms_scan_kernel(const T *__restrict__ score, size_t score_stride, int nc, int n_anchors, float conf,
+                const int *__restrict__ filter, int n_filter, int *__restrict__ count, int *__restrict__ cls_out,
+                unsigned long long *__restrict__ keys, int a_pad) {
     const int n = blockIdx.y;
     const int a0 = (blockIdx.x * kScanThreads + threadIdx.x) * VW;
     const int lane = threadIdx.x & 31;
@@ -83,33 +96,35 @@ nms_scan_kernel(const float *__restrict__ pred, int nc, int n_anchors, float con
 #pragma unroll
     for (int v = 0; v < VW; ++v) pass[v] = false;
     if (a0 < n_anchors) {
-        const size_t base = ((size_t)n * (4 + nc) + 4) * n_anchors + a0;
+        const T *pred = score;
+        const size_t base = (size_t)n * score_stride + a0;
+        auto val = [](float x) { return SIGMOID ? sigmoid_rn(x) : x; };
         {
-            Group<float, VW> row;
+            Group<T, VW> row;
             row.load(pred + base);
 #pragma unroll
-            for (int v = 0; v < VW; ++v) { best[v] = row.get(v); arg[v] = 0; }
+            for (int v = 0; v < VW; ++v) { best[v] = val(row.get(v)); arg[v] = 0; }
         }
         constexpr int U = 4;
         int c = 1;
         for (; c + U <= nc; c += U) {
-            Group<float, VW> row[U];
+            Group<T, VW> row[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) row[u].load(pred + base + (size_t)(c + u) * n_anchors);
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int v = 0; v < VW; ++v) {
-                    const float s = row[u].get(v);
+                    const float s = val(row[u].get(v));
                     if (s > best[v]) { best[v] = s; arg[v] = c + u; }      // first maximum wins
                 }
         }
         for (; c < nc; ++c) {
-            Group<float, VW> row;
+            Group<T, VW> row;
             row.load(pred + base + (size_t)c * n_anchors);
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
-                const float s = row.get(v);
+                const float s = val(row.get(v));
                 if (s > best[v]) { best[v] = s; arg[v] = c; }
             }
         }
@@ -250,7 +265,7 @@ __device__ __forceinline__ void emit_row(float *__restrict__ out_rows, int *__re
 // MULTI (multi_label): a key's low word is anchor * nc + class instead of the anchor.
 template <bool REG, bool MULTI>
 __global__ void __launch_bounds__(kSortThreads, 1)
-nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const int *__restrict__ count,
+nms_sweep_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *__restrict__ count,
                  const int *__restrict__ mode, const int *__restrict__ cls, unsigned long long *__restrict__ keys, int a_pad,
                  float4 *__restrict__ sbox, int sbox_stride, float thr, int max_det, int agnostic, float *__restrict__ out_rows,
                  int *__restrict__ out_count, int *__restrict__ out_anchor) {
@@ -270,7 +285,7 @@ nms_sweep_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
         return;
     }
     if (REG && n_cand > kRegCols * kSortThreads) return;      // host picks the other variant; never taken
-    const float *img = pred + (size_t)n * (4 + nc) * n_anchors;
+    const float *img = pred + (size_t)n * box_stride;
     const int *cls_n = cls + (size_t)n * n_anchors;
     {   // bitonic sort of all the image's keys (ascending key = descending score, ties -> lowest anchor)
         extern __shared__ unsigned long long s_keys[];
@@ -398,7 +413,7 @@ constexpr int kAnchorBits = 22;
 constexpr int kSelBits = 11;
 
 __global__ void __launch_bounds__(kClassThreads, 1)
-nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const int *__restrict__ count,
+nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *__restrict__ count,
                  const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
                  unsigned long long *__restrict__ keys2, unsigned char *__restrict__ alive_g,
                  unsigned *__restrict__ tick, unsigned *__restrict__ range, float thr, int max_det,
@@ -426,7 +441,7 @@ nms_class_kernel(const float *__restrict__ pred, int nc, int n_anchors, const in
         return;
     }
     if (n > kClassCap) return;                             // generic path (same decision in every CTA)
-    const float *img_pred = pred + (size_t)img * (4 + nc) * n_anchors;
+    const float *img_pred = pred + (size_t)img * box_stride;
     const unsigned long long *k_in = keys + (size_t)img * a_pad;
     unsigned long long *k2 = keys2 + (size_t)img * a_pad;
     const int *cls_n = cls + (size_t)img * n_anchors;
@@ -906,6 +921,68 @@ extern "C" size_t yb_nms_workspace_bytes(int n_images, int n_anchors) {
     return carve_nms(nullptr, n_images, n_anchors).total_bytes;
 }
 
+// scan + class-parallel kernel + generic sweep on whatever layout `in` describes
+template <typename T, bool SIGMOID>
+static int launch_scan(const NmsInput &in, int n_images, int nc, int n_anchors, float conf_thres, const int32_t *class_filter,
+                       int n_class_filter, const NmsWorkspace &w, cudaStream_t st) {
+    constexpr int VW = ElemsPer16<T>::value;
+    const T *score = static_cast<const T *>(in.score);
+    if (n_anchors % VW == 0 && aligned16(score) && (in.score_stride * sizeof(T)) % 16 == 0) {
+        dim3 grid((n_anchors / VW + kScanThreads - 1) / kScanThreads, n_images);
+        nms_scan_kernel<T, VW, SIGMOID><<<grid, kScanThreads, 0, st>>>(score, in.score_stride, nc, n_anchors, conf_thres, class_filter,
+                                                                       n_class_filter, w.count, w.cls, w.keys, w.a_pad);
+    } else {
+        dim3 grid((n_anchors + kScanThreads - 1) / kScanThreads, n_images);
+        nms_scan_kernel<T, 1, SIGMOID><<<grid, kScanThreads, 0, st>>>(score, in.score_stride, nc, n_anchors, conf_thres, class_filter,
+                                                                      n_class_filter, w.count, w.cls, w.keys, w.a_pad);
+    }
+    YB_LAUNCH_CHECK();
+    return YB_OK;
+}
+
+static int run_nms(const NmsInput &in, int score_dtype, int sigmoid, int n_images, int nc, int n_anchors, float conf_thres,
+                   double iou_thres, int max_det, int agnostic, const int32_t *class_filter, int n_class_filter,
+                   float *out_rows, int32_t *out_count, int32_t *out_anchor, const NmsWorkspace &w, cudaStream_t st) {
+    // "float IoU promoted to double > thr"  <=>  "IoU > largest float that is <= thr"
+    float thr = (float)iou_thres;
+    if ((double)thr > iou_thres) thr = nextafterf(thr, -INFINITY);
+
+    YB_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
+    int rc;
+    if (score_dtype == YB_F32)
+        rc = sigmoid ? launch_scan<float, true>(in, n_images, nc, n_anchors, conf_thres, class_filter, n_class_filter, w, st)
+                     : launch_scan<float, false>(in, n_images, nc, n_anchors, conf_thres, class_filter, n_class_filter, w, st);
+    else
+        rc = sigmoid ? launch_scan<__nv_bfloat16, true>(in, n_images, nc, n_anchors, conf_thres, class_filter, n_class_filter, w, st)
+                     : launch_scan<__nv_bfloat16, false>(in, n_images, nc, n_anchors, conf_thres, class_filter, n_class_filter, w, st);
+    if (rc != YB_OK) return rc;
+    if (!agnostic && nc <= kClassMaxNc && n_anchors < (1 << kAnchorBits) && max_det <= kClassMaxDet) {
+        const size_t csmem = sizeof(float4) * (size_t)kClassCap;      // boxes; later keys + histogram + selection
+        YB_CUDA(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        // CTAs per image: enough to put every SM to work on small batches
+        const int split = n_images >= 96 ? 1 : (n_images >= 48 ? 2 : (n_images >= 24 ? 4 : 8));
+        nms_class_kernel<<<dim3(split, n_images), kClassThreads, csmem, st>>>(
+            in.box, in.box_stride, nc, n_anchors, w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det,
+            w.mode, out_rows, out_count, out_anchor);
+        YB_LAUNCH_CHECK();
+    }
+    // generic path for whatever the class-parallel kernel left (mode == 0)
+    const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
+    if (n_anchors <= kRegCols * kSortThreads) {
+        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<true, false><<<n_images, kSortThreads, smem, st>>>(in.box, in.box_stride, nc, n_anchors, w.count, w.mode, w.cls,
+                                                                            w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
+                                                                            agnostic, out_rows, out_count, out_anchor);
+    } else {
+        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_sweep_kernel<false, false><<<n_images, kSortThreads, smem, st>>>(in.box, in.box_stride, nc, n_anchors, w.count, w.mode, w.cls,
+                                                                             w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
+                                                                             agnostic, out_rows, out_count, out_anchor);
+    }
+    YB_LAUNCH_CHECK();
+    return YB_OK;
+}
+
 extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_anchors, float conf_thres, double iou_thres,
                       int max_det, int agnostic, const int32_t *class_filter, int n_class_filter, float *out_rows,
                       int32_t *out_count, int32_t *out_anchor, void *workspace, size_t workspace_bytes, void *stream) {
@@ -922,47 +999,59 @@ extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_ancho
         return YB_ERR_ALIGN;
     }
     const NmsWorkspace w = carve_nms(workspace, n_images, n_anchors);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // "float IoU promoted to double > thr"  <=>  "IoU > largest float that is <= thr"
-    float thr = (float)iou_thres;
-    if ((double)thr > iou_thres) thr = nextafterf(thr, -INFINITY);
+    NmsInput in;
+    in.box = prediction;
+    in.box_stride = (size_t)(4 + nc) * n_anchors;
+    in.score = prediction + (size_t)4 * n_anchors;
+    in.score_stride = in.box_stride;
+    return run_nms(in, YB_F32, 0, n_images, nc, n_anchors, conf_thres, iou_thres, max_det, agnostic, class_filter, n_class_filter,
+                   out_rows, out_count, out_anchor, w, static_cast<cudaStream_t>(stream));
+}
 
-    YB_CUDA(cudaMemsetAsync(w.count, 0, w.zero_bytes, st));
-    if (n_anchors % 4 == 0 && aligned16(prediction)) {
-        dim3 grid((n_anchors / 4 + kScanThreads - 1) / kScanThreads, n_images);
-        nms_scan_kernel<4><<<grid, kScanThreads, 0, st>>>(prediction, nc, n_anchors, conf_thres, class_filter,
-                                                          n_class_filter, w.count, w.cls, w.keys, w.a_pad);
-    } else {
-        dim3 grid((n_anchors + kScanThreads - 1) / kScanThreads, n_images);
-        nms_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(prediction, nc, n_anchors, conf_thres, class_filter,
-                                                          n_class_filter, w.count, w.cls, w.keys, w.a_pad);
+// Model.inference after the network (src/model/model_builder.py:123-139) as one entry point: the head output's box
+// channels are decoded (DFL expectation -> dist2bbox xywh -> x stride) into a compact (N, 4, A) buffer of the workspace,
+// and the NMS kernels read their scores straight from the head output's class channels -- the (N, 4 + nc, A) tensor the
+// reference concatenates (:136) never exists.
+static size_t postprocess_box_bytes(int n_images, int n_anchors) { return round_up(sizeof(float) * 4 * (size_t)n_images * n_anchors, 64); }
+
+extern "C" size_t yb_postprocess_workspace_bytes(int n_images, int n_anchors) {
+    if (n_images <= 0 || n_anchors <= 0) return 0;
+    return postprocess_box_bytes(n_images, n_anchors) + carve_nms(nullptr, n_images, n_anchors).total_bytes;
+}
+
+extern "C" int yb_postprocess(const void *head_out, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                              const float *anchors, const float *strides, int apply_sigmoid, float conf_thres,
+                              double iou_thres, int max_det, int agnostic, const int32_t *class_filter, int n_class_filter,
+                              float *out_rows, int32_t *out_count, int32_t *out_anchor, void *workspace,
+                              size_t workspace_bytes, void *stream) {
+    YB_REQUIRE(head_out && anchors && strides && out_rows && out_count && workspace, "yb_postprocess: null pointer");
+    YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && max_det > 0 && n_images <= 65535, "yb_postprocess: bad sizes");
+    YB_REQUIRE(dtype == YB_F32 || dtype == YB_BF16, "yb_postprocess: dtype must be YB_F32 or YB_BF16");
+    YB_REQUIRE(n_class_filter >= 0 && (n_class_filter == 0 || class_filter), "yb_postprocess: bad class filter");
+    YB_REQUIRE(conf_thres >= 0.f, "yb_postprocess: conf_thres must be >= 0 (scores are ordered by their bit pattern)");
+    if (workspace_bytes < yb_postprocess_workspace_bytes(n_images, n_anchors)) {
+        set_error("yb_postprocess: workspace %zu B < required %zu B", workspace_bytes, yb_postprocess_workspace_bytes(n_images, n_anchors));
+        return YB_ERR_WORKSPACE;
     }
-    YB_LAUNCH_CHECK();
-    if (!agnostic && nc <= kClassMaxNc && n_anchors < (1 << kAnchorBits) && max_det <= kClassMaxDet) {
-        const size_t csmem = sizeof(float4) * (size_t)kClassCap;      // boxes; later keys + histogram + selection
-        YB_CUDA(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        // CTAs per image: enough to put every SM to work on small batches
-        const int split = n_images >= 96 ? 1 : (n_images >= 48 ? 2 : (n_images >= 24 ? 4 : 8));
-        nms_class_kernel<<<dim3(split, n_images), kClassThreads, csmem, st>>>(
-            prediction, nc, n_anchors, w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det,
-            w.mode, out_rows, out_count, out_anchor);
-        YB_LAUNCH_CHECK();
+    if (!aligned16(workspace)) {
+        set_error("yb_postprocess: workspace must be 16-byte aligned");
+        return YB_ERR_ALIGN;
     }
-    // generic path for whatever the class-parallel kernel left (mode == 0)
-    const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
-    if (n_anchors <= kRegCols * kSortThreads) {
-        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_sweep_kernel<true, false><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls,
-                                                                            w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
-                                                                            agnostic, out_rows, out_count, out_anchor);
-    } else {
-        YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_sweep_kernel<false, false><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, w.mode, w.cls,
-                                                                             w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
-                                                                             agnostic, out_rows, out_count, out_anchor);
-    }
-    YB_LAUNCH_CHECK();
-    return YB_OK;
+    float *boxes = static_cast<float *>(workspace);
+    const size_t image_stride = (size_t)(4 * reg_max + nc) * n_anchors;
+    // DFL.forward + dist2bbox(xywh) + "* strides" (model_builder.py:127-133), fp32 boxes whatever the head's dtype
+    if (int rc = yb_dfl_decode(head_out, dtype, n_images, reg_max, n_anchors, image_stride, anchors, strides, nullptr, boxes,
+                               0 /* xywh */, 1, stream))
+        return rc;
+    const NmsWorkspace w = carve_nms(static_cast<char *>(workspace) + postprocess_box_bytes(n_images, n_anchors), n_images, n_anchors);
+    const size_t esz = dtype == YB_BF16 ? 2 : 4;
+    NmsInput in;
+    in.box = boxes;
+    in.box_stride = (size_t)4 * n_anchors;
+    in.score = static_cast<const char *>(head_out) + esz * (size_t)4 * reg_max * n_anchors;
+    in.score_stride = image_stride;
+    return run_nms(in, dtype, apply_sigmoid, n_images, nc, n_anchors, conf_thres, iou_thres, max_det, agnostic, class_filter,
+                   n_class_filter, out_rows, out_count, out_anchor, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t yb_nms_multilabel_workspace_bytes(int n_images) {
@@ -1009,7 +1098,7 @@ extern "C" int yb_nms_multilabel(const float *prediction, int n_images, int nc, 
     YB_LAUNCH_CHECK();
     const size_t smem = sizeof(unsigned long long) * (size_t)kSortTile;
     YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_sweep_kernel<false, true><<<n_images, kSortThreads, smem, st>>>(prediction, nc, n_anchors, w.count, nullptr, nullptr,
+    nms_sweep_kernel<false, true><<<n_images, kSortThreads, smem, st>>>(prediction, (size_t)(4 + nc) * n_anchors, nc, n_anchors, w.count, nullptr, nullptr,
                                                                         w.keys, kMlCap, w.sbox, kMaxNms, thr, max_det, agnostic,
                                                                         out_rows, out_count, out_anchor);
     YB_LAUNCH_CHECK();

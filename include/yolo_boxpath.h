@@ -249,6 +249,19 @@ int yb_nms(const float *prediction, int n_images, int nc, int n_anchors,
            float *out_rows, int32_t *out_count, int32_t *out_anchor,
            void *workspace, size_t workspace_bytes, void *stream);
 
+/* Model.inference after the network (src/model/model_builder.py:123-139: split, DFL, dist2bbox, "* strides", cat, NMS)
+ * as ONE entry point.  The box channels of the head output are decoded into a compact (N, 4, A) fp32 buffer inside the
+ * workspace; the NMS kernels take their scores straight from the head output's class channels -- raw logits, as the
+ * reference feeds them, or through a sigmoid when apply_sigmoid != 0 -- so the (N, 4 + nc, A) tensor the
+ * reference concatenates (:136) never exists.  Everything else as yb_nms.
+ *   head_out  (N, 4*reg_max + nc, A) fp32 or bf16      anchors (2, A), strides (1, A) fp32 */
+size_t yb_postprocess_workspace_bytes(int n_images, int n_anchors);
+int yb_postprocess(const void *head_out, int dtype, int n_images, int nc, int reg_max, int n_anchors,
+                   const float *anchors, const float *strides, int apply_sigmoid, float conf_thres, double iou_thres,
+                   int max_det, int agnostic, const int32_t *class_filter, int n_class_filter,
+                   float *out_rows, int32_t *out_count, int32_t *out_anchor,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
 /* multi_label=True (src/utils/model_utils.py:240-242): every (anchor, class) pair with score > conf_thres is
  * a candidate; the max_nms = 30000 best of an image (:211, :259; score descending, ties -> lower
  * anchor * nc + class, the order of the reference's nonzero()) go through the same greedy NMS.

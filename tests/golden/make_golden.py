@@ -203,6 +203,31 @@ def decode_case(name, n, nc, imgsz, seed, conf, top_k, cls_mean):
     print(f"{name}: rows per image {cnt.tolist()}")
 
 
+def inference_case(name, n, nc, imgsz, seed, conf, iou, cls_mean):
+    """Model.inference after the network, the reference's own lines (src/model/model_builder.py:123-139) on a seeded
+    head output: split, DFL, dist2bbox(xywh), * strides, cat, non_max_suppression -- RAW logits as scores."""
+    if _skip(name):
+        return
+    anchors, strides = syn.anchor_grid(imgsz)
+    x = syn.make_preds(n, nc, anchors.shape[1], seed, cls_mean=cls_mean, cls_std=1.5)
+    dfl = ref_blocks.DFL(16)
+    with torch.no_grad():
+        box, cls = x.split((64, nc), 1)                                  # :123
+        box = dfl(box)                                                   # :127
+        box = ref_utils.dist2bbox(box, anchors.unsqueeze(0), xywh=True, dim=1)   # :130
+        box = box * strides                                              # :133
+        y = torch.cat((box, cls), 1)                                     # :136
+        for b in range(n):
+            best = y[b, 4:].amax(0)
+            assert best.unique().numel() == best.numel(), "duplicate best scores; pick another seed"
+        out = ref_utils.non_max_suppression(y, conf_thres=conf, iou_thres=iou, nc=nc)   # :139
+    rows, cnt = pack_ragged(out, 6, np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x.numpy(), anchors=anchors.numpy(), strides=strides.numpy(),
+                        rows=rows, count=cnt, meta=np.array([n, nc, imgsz, seed], np.int64), conf=np.float64(conf),
+                        iou=np.float64(iou))
+    print(f"{name}: kept per image {cnt.tolist()}")
+
+
 def metrics_case(name, seed, n_images, nc, thr):
     if _skip(name):
         return
@@ -321,6 +346,7 @@ if __name__ == "__main__":
              store_inputs=False)
     decode_case("decode_topk", 3, 6, 160, 21, conf=0.25, top_k=100, cls_mean=-1.0)
     decode_case("decode_sparse", 3, 6, 160, 22, conf=0.6, top_k=100, cls_mean=-4.0)
+    inference_case("inference_post", 3, 6, 160, 23, conf=0.25, iou=0.45, cls_mean=-1.0)
     helper_case("helpers", 31)
     metrics_case("metrics_a", 41, 12, 5, 0.5)
     metrics_case("metrics_b", 42, 9, 3, 0.3)

@@ -301,6 +301,43 @@ def test_packed_gt_and_inference_postprocess(cuda_device):
         assert torch.allclose(out[b].cpu(), ora.rows[b], rtol=1e-6, atol=1e-6)
 
 
+def test_fused_postprocess_matches_reference_golden(cuda_device):
+    """§8(f).4: yb_postprocess against the reference's own Model.inference tail (model_builder.py:123-139: split, DFL,
+    dist2bbox, * strides, cat, NMS on RAW logits) captured in tests/golden/inference_post.npz, and bit for bit against the
+    unfused sequence of this repo's own ops (decode kernel -> torch.cat -> yb_nms)."""
+    from custom_yolo_implmentation_b200 import _cabi
+    from custom_yolo_implmentation_b200.utils.postprocess import postprocess_inference
+    dev = cuda_device
+    z = load_golden("inference_post")
+    x = torch.from_numpy(z["x"]).to(dev)
+    anc, st = torch.from_numpy(z["anchors"]).to(dev), torch.from_numpy(z["strides"]).to(dev)
+    n, nc = int(z["meta"][0]), int(z["meta"][1])
+    before = _cabi.launch_count
+    out = postprocess_inference(x, anc, st, nc, conf_thres=float(z["conf"]), iou_thres=float(z["iou"]))
+    assert _cabi.launch_count - before == 4                 # decode, scan, class-parallel NMS, generic sweep: nothing else
+    for b in range(n):
+        ref = torch.from_numpy(z["rows"][b, : int(z["count"][b])])
+        assert out[b].shape == ref.shape
+        assert torch.equal(out[b][:, 5].cpu(), ref[:, 5]) and torch.equal(out[b][:, 4].cpu(), ref[:, 4])   # classes, raw-logit scores
+        assert torch.allclose(out[b][:, :4].cpu(), ref[:, :4], rtol=1e-5, atol=1e-4)
+    for dtype in (torch.float32, torch.bfloat16):
+        xd = x.to(dtype)
+        fused = postprocess_inference(xd, anc, st, nc, conf_thres=0.25, iou_thres=0.45)
+        _, box = dfl_decode(xd, anc, st, want_ltrb=False, box_format="xywh")
+        unfused = U.non_max_suppression(torch.cat((box, xd[:, 64:].float()), 1), conf_thres=0.25, iou_thres=0.45, nc=nc)
+        for a, b in zip(fused, unfused):
+            assert torch.equal(a, b)
+        sig = postprocess_inference(xd, anc, st, nc, conf_thres=0.25, iou_thres=0.45, apply_sigmoid=True)
+        unf = U.non_max_suppression(torch.cat((box, xd[:, 64:].float().sigmoid()), 1), conf_thres=0.25, iou_thres=0.45, nc=nc)
+        for a, b in zip(sig, unf):
+            assert a.shape == b.shape and torch.equal(a[:, 5], b[:, 5]) and torch.equal(a[:, :4], b[:, :4])
+            assert torch.allclose(a[:, 4], b[:, 4], rtol=1e-6, atol=0)
+    # the filters of the NMS signature
+    only = postprocess_inference(x, anc, st, nc, conf_thres=0.25, iou_thres=0.45, classes=[1, 4], max_det=7)
+    assert all(o.shape[0] <= 7 and set(o[:, 5].tolist()) <= {1.0, 4.0} for o in only)
+    assert all(o.shape == (0, 6) for o in postprocess_inference(x, anc, st, nc, classes=[]))
+
+
 # ------------------------------------------------------------------------------------------ head tail
 @pytest.mark.parametrize("name", ["head_aligned", "head_ragged"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
