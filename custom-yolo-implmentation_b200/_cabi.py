@@ -14,9 +14,9 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libyolo_boxpath.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 YB_F32, YB_BF16 = 0, 1
-YB_LOSS_NO_PRUNE, YB_LOSS_SPLIT_LAUNCH = 1, 2
+YB_LOSS_NO_PRUNE, YB_LOSS_SPLIT_LAUNCH, YB_LOSS_FORCE_PROBE = 1, 2, 4
 
 _lib = None
 _lock = threading.Lock()
@@ -31,7 +31,7 @@ _SIGNATURES = {
     "yb_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "yb_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_size_t, ctypes.c_uint, c_void_p, c_void_p]),
+                                c_void_p, c_size_t, ctypes.c_uint, c_void_p, c_void_p, c_void_p]),
     "yb_tal_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "yb_tal_assign": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -24,6 +24,7 @@
 // run-to-run bit-identical whatever the order in which CTAs finish, and nothing has to be re-read.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -71,6 +72,12 @@ namespace yb {
 #ifndef YB_MATCH_WHOLE_SECTORS
 #define YB_MATCH_WHOLE_SECTORS 1
 #endif
+#ifndef YB_LOSS_PROBE                 // 0: ignore the grid hint (measurement aid)
+#define YB_LOSS_PROBE 1
+#endif
+#ifndef YB_PROBE_MIN_GT               // the probe role runs when an image can hold more GTs than this (gmax)
+#define YB_PROBE_MIN_GT 128
+#endif
 constexpr int kScanUnroll = YB_SCAN_UNROLL;
 constexpr int kAssignThreads = YB_ASSIGN_THREADS;
 constexpr int kClsThreads = YB_CLS_THREADS;
@@ -86,6 +93,7 @@ struct LossWorkspace {
     unsigned int *done;            // [N] CTAs of fused_main_kernel that have finished with the image                        } call
     unsigned long long *acc;       // [N * kAccPerImage] fixed-point sums: 16 x class part, DFL, QFL cell correction, winners }
     unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys                                           }
+    unsigned int *bound;           // [gt_total] bits of an upper bound of the GT's nearest-centre distance (0 = none yet)   }
     int *gt_img;                   // [gt_total] image of each GT (written by the box role, read by match_kernel)
     size_t zero_bytes;
     size_t total_bytes;
@@ -103,6 +111,8 @@ static LossWorkspace carve(void *base, int n_images, int gt_total) {
     off += round_up(sizeof(unsigned long long) * (size_t)n_images * kAccPerImage, 64);
     w.best = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
+    w.bound = reinterpret_cast<unsigned int *>(p + off);
+    off += round_up(sizeof(unsigned int) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
     w.zero_bytes = off;
     w.gt_img = reinterpret_cast<int *>(p + off);
     off += round_up(sizeof(int) * (size_t)(gt_total > 0 ? gt_total : 1), 64);
@@ -129,8 +139,8 @@ template <typename T, int VW>
 __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict__ preds, int n_ch, int n_anchors,
                                             const float *__restrict__ anchors, const float *__restrict__ strides,
                                             const float *__restrict__ gt, const int *__restrict__ gt_off,
-                                            unsigned long long *__restrict__ best, int *__restrict__ gt_img,
-                                            T *__restrict__ grad, bool prune) {
+                                            unsigned long long *__restrict__ best, const unsigned int *bound,
+                                            int *__restrict__ gt_img, T *__restrict__ grad, bool prune) {
     constexpr int TILE = kAssignThreads * VW;
     constexpr int TILE4 = (TILE + 3) & ~3;
     // predicted centres of the tile's anchors, structure-of-arrays so that four anchors are one LDS.128
@@ -244,10 +254,14 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
 #if YB_ASSIGN_PRUNE
             if (need && prune) {
                 const unsigned long long kinv = __ldcg(best + g_begin + gi);
-                if (kinv != 0ull) {
+                // ... or the probe role's bound (the distance to SOME predicted centre, inflated: see probe_body)
+                const unsigned int pb = bound != nullptr ? __ldcg(bound + g_begin + gi) : 0u;
+                if (kinv != 0ull || pb != 0u) {
                     const float gx = __ldg(gt + (size_t)(g_begin + gi) * 5 + 0);
                     const float gy = __ldg(gt + (size_t)(g_begin + gi) * 5 + 1);
-                    const float sb = __uint_as_float((unsigned int)((~kinv) >> 32)) * 1.000001f;
+                    float sb = __int_as_float(0x7f800000);
+                    if (kinv != 0ull) sb = __uint_as_float((unsigned int)((~kinv) >> 32)) * 1.000001f;
+                    if (pb != 0u) sb = fminf(sb, __uint_as_float(pb));
                     const float dx = fmaxf(fmaxf(lo_x - gx, gx - hi_x), 0.f), dy = fmaxf(fmaxf(lo_y - gy, gy - hi_y), 0.f);
                     const float lb2 = (dx * dx + dy * dy) * 0.999999f;
                     need = !(lb2 > fmaf(sb * sb, 1.000001f, 1e-6f * (gx * gx + gy * gy + pn_max)));
@@ -356,7 +370,8 @@ __global__ void __launch_bounds__(kAssignThreads, YB_ASSIGN_MINBLOCKS ? YB_ASSIG
 assign_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
               const float *__restrict__ strides, const float *__restrict__ gt, const int *__restrict__ gt_off,
               unsigned long long *__restrict__ best, int *__restrict__ gt_img, T *__restrict__ grad) {
-    assign_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img, grad, true);
+    assign_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, nullptr, gt_img, grad,
+                       true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -401,6 +416,65 @@ __device__ __forceinline__ void anchor_softmax(AnchorTerms &a) {
         a.mx[k] = m; a.sm[k] = sum; a.pr[k] = p; a.ds[k] = d;
     }
     a.b = decode_box(a.ax, a.ay, a.s, a.ds[0], a.ds[1], a.ds[2], a.ds[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// probe role: an upper bound of every GT's nearest-centre distance before any tile has been scanned
+// ------------------------------------------------------------------------------------------
+// One half-warp per GT.  When the caller describes the anchors as a pyramid of regular grids (yb_anchor_grid, the same
+// hint the task-aligned path takes), the cell of each level that holds the GT's centre is a very good guess of where
+// the nearest predicted centre will be; the half-warp decodes those few anchors and publishes the smallest distance,
+// inflated far beyond any rounding, as the GT's bound.  The box role then drops (GT, tile) pairs from its very first
+// tile on -- the tiles of the coarse levels, which used to scan every GT of the image, included.  Nothing depends on
+// the hint being right: ANY anchor's distance bounds the minimum from above, so a wrong hint only costs pruning.
+template <typename T>
+__device__ __forceinline__ void probe_gts(const T *__restrict__ preds, const float *__restrict__ gt, int g0, int gt_total,
+                                          const int *__restrict__ gt_off, int n_images, int n_ch, int n_anchors,
+                                          const float *__restrict__ anchors, const float *__restrict__ strides,
+                                          const yb_anchor_grid &grid, unsigned int *bound) {
+    const int lane = threadIdx.x & 31, bin = lane & 15;
+    const int g_raw = g0 + (threadIdx.x >> 4);
+    if (g0 + ((threadIdx.x & ~31) >> 4) >= gt_total) return;          // warp-uniform
+    const bool live = g_raw < gt_total;
+    const int g = live ? g_raw : gt_total - 1;
+    int lo = 0, hi = n_images;                                         // image of the GT
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(gt_off + mid) <= g) lo = mid; else hi = mid;
+    }
+    const int n = lo;
+    const float gx = __ldg(gt + (size_t)g * 5), gy = __ldg(gt + (size_t)g * 5 + 1);
+    float best_d = __int_as_float(0x7f800000);
+    for (int l0 = 0; l0 < grid.n_levels; l0 += 4) {        // the gathers of four levels fly together
+        float z[4][4];
+        int a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int l = min(l0 + u, grid.n_levels - 1);  // the tail repeats the last level: harmless
+            const float s = grid.stride[l];
+            const int col = min(max((int)floorf(gx / s - grid.x0[l] + 0.5f), 0), grid.w[l] - 1);
+            const int row = min(max((int)floorf(gy / s - grid.y0[l] + 0.5f), 0), grid.h[l] - 1);
+            a[u] = min(max(grid.start[l] + row * grid.w[l] + col, 0), n_anchors - 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                z[u][k] = load_as_float(preds + ((size_t)n * n_ch + k * kRegMax + bin) * n_anchors + a[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (l0 + u >= grid.n_levels) break;            // warp-uniform
+            AnchorTerms at;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) at.z[k] = z[u][k];
+            at.ax = __ldg(anchors + a[u]); at.ay = __ldg(anchors + n_anchors + a[u]); at.s = __ldg(strides + a[u]);
+            anchor_softmax(at);
+            const float dx = at.b.cx - gx, dy = at.b.cy - gy;
+            best_d = fminf(best_d, sqrtf(dx * dx + dy * dy));
+        }
+    }
+    // the decode here and the box role's differ by ~1e-6 relative, the matmul-form d^2 by ~1e-6 (|g|^2 + |p|^2):
+    // 0.1 % + 0.05 px is orders of magnitude more; a non-finite distance publishes nothing
+    const float b = fmaf(best_d, 1.001f, 0.05f);
+    if (live && bin == 0 && b < __int_as_float(0x7f800000)) bound[g] = __float_as_uint(b);
 }
 
 __device__ __forceinline__ GtTerms gt_terms(const AnchorTerms &a, float z_cls, float gcx, float gcy, float gw, float gh,
@@ -844,7 +918,8 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
 //   match role  (match_gt)     the per-GT terms of ONE image, once every box and class CTA of that image has counted itself
 //                              off (common.cuh: in-kernel dependencies)
 //   reducer     (final_reduce) the grid's last CTA: waits for every image, then writes the loss scalars.
-// Block order: [skew box CTAs] [coarse tiles, image-major] [fine tiles, image-major] [match CTAs, image-major] [reducer].
+// Block order: [probe CTAs] [skew box CTAs] [coarse tiles, image-major] [fine tiles, image-major] [match CTAs, image-major]
+// [reducer].  (probe role: probe_gts above; its bounds are read as they come, like `best`: exact whatever the timing.)
 // The match CTAs become resident while the last tiles are still streaming and start on the early images at once: the
 // step no longer pays a kernel boundary, a second launch and a reduction launch for them (36 us -> 21 us of a 255 us
 // step at cfg2).  Measured and not kept: match CTAs of image i placed right behind the tiles of image i + lag, so that
@@ -856,6 +931,8 @@ struct FusedPlan {
     int match_ctas;                // match CTAs per image (0: no GT in the whole batch); < 0: match_kernel is launched separately
                                    // (no match / reducer CTAs here and nobody counts itself off)
     int whole_sectors;             // gradient rows may be patched with whole 32-byte sectors (match_gt)
+    int probe_ctas;                // CTAs of the probe role at the head of the grid (0: no grid hint)
+    int gt_total;
 };
 #ifndef YB_FUSED_MINBLOCKS           // measured on B200: 6 resident CTAs/SM is best for fp32 rows, 5 for bf16 rows
 #define YB_FUSED_MINBLOCKS 0
@@ -863,8 +940,9 @@ struct FusedPlan {
 template <typename T, int VW, bool WRITE_GRAD>
 __global__ void __launch_bounds__(kAssignThreads, YB_FUSED_MINBLOCKS ? YB_FUSED_MINBLOCKS : (VW == 8 ? 5 : 6))
 fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anchors, int nc, const FusedPlan plan,
-                  const float *__restrict__ anchors, const float *__restrict__ strides, const float *__restrict__ gt,
-                  const int *__restrict__ gt_off, unsigned long long *best, int *__restrict__ gt_img, float k_cls,
+                  const yb_anchor_grid grid, const float *__restrict__ anchors, const float *__restrict__ strides,
+                  const float *__restrict__ gt, const int *__restrict__ gt_off, unsigned long long *best,
+                  unsigned int *bound, int *__restrict__ gt_img, float k_cls,
                   float k_dfl_num, float lambda_cls, float lambda_dfl, T *grad, unsigned long long *acc,
                   unsigned int *flags, unsigned int *done, int *__restrict__ out_idx, float *__restrict__ out_iou,
                   float *__restrict__ out_loss, float *__restrict__ out_per_image) {
@@ -883,6 +961,12 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     bool reducer = false;
     {
         int id = blockIdx.x;
+        if (id < plan.probe_ctas) {                        // probe role: the grid's first CTAs, 8 GTs each
+            probe_gts<T>(preds, gt, id * (kAssignThreads / 16), plan.gt_total, gt_off, n_images, n_ch, n_anchors, anchors, strides,
+                         grid, bound);
+            return;
+        }
+        id -= plan.probe_ctas;
         if (id < skew) {
             group = id;
         } else {
@@ -940,8 +1024,8 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
             tile = gf - image * fine;
         }
         if (role == 0)
-            assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best, gt_img,
-                               WRITE_GRAD ? grad : nullptr, prune);
+            assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best,
+                               plan.probe_ctas > 0 ? bound : nullptr, gt_img, WRITE_GRAD ? grad : nullptr, prune);
         else
             cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
                                         acc, flags);
@@ -984,8 +1068,8 @@ template <typename T, int VW>
 static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, const float *anchors, const float *strides,
                        const float *gt, const int32_t *gt_off, int gt_total, int gmax, float lambda_cls,
                        float lambda_dfl, T *grad, float *out_loss, int32_t *out_idx, float *out_iou,
-                       float *out_per_image, const LossWorkspace &w, unsigned flags, void *const *stage_events,
-                       cudaStream_t st) {
+                       float *out_per_image, const LossWorkspace &w, unsigned flags, const yb_anchor_grid &grid,
+                       void *const *stage_events, cudaStream_t st) {
     const int n_ch = 4 * kRegMax + nc;
     const float k_cls = lambda_cls / ((float)n_images * (float)n_anchors);
     const float k_dfl_num = lambda_dfl / ((float)n_images * 4.f);
@@ -1017,16 +1101,22 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         plan.match_ctas = gt_total > 0 ? std::min(std::max((g_hint + 7) / 8, 1), YB_MATCH_MAX_CTAS) : 0;
         if (YB_MATCH_SEPARATE) plan.match_ctas = -1;
         plan.whole_sectors = whole_sectors;
-        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + plan.skew +
+        plan.gt_total = gt_total;
+        // the probe role pays once the coarse tiles would otherwise scan more than one chunk of GTs per image (measured:
+        // cfg5, <= 300 GT per image, 188 -> 170 us; cfg2, <= 100 GT per image, 241 -> 252 us with it)
+        plan.probe_ctas = (YB_LOSS_PROBE && grid.n_levels > 0 && gt_total > 0 && !(flags & YB_LOSS_NO_PRUNE) &&
+                           (g_hint > YB_PROBE_MIN_GT || (flags & YB_LOSS_FORCE_PROBE)))
+                              ? (gt_total + kAssignThreads / 16 - 1) / (kAssignThreads / 16) : 0;
+        const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + plan.skew + plan.probe_ctas +
                                  (plan.match_ctas < 0 ? 0 : (long long)plan.match_ctas * n_images + 1);
         YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
         if (grad != nullptr)
             fused_main_kernel<T, VW, true><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, plan, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, k_dfl_num,
+                preds, n_images, n_ch, n_anchors, nc, plan, grid, anchors, strides, gt, gt_off, w.best, w.bound, w.gt_img, k_cls, k_dfl_num,
                 lambda_cls, lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
         else
             fused_main_kernel<T, VW, false><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, plan, anchors, strides, gt, gt_off, w.best, w.gt_img, k_cls, k_dfl_num,
+                preds, n_images, n_ch, n_anchors, nc, plan, grid, anchors, strides, gt, gt_off, w.best, w.bound, w.gt_img, k_cls, k_dfl_num,
                 lambda_cls, lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
         YB_LAUNCH_CHECK();
         if (int rc = stage_mark(stage_events, 1, st)) return rc;
@@ -1077,7 +1167,7 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
                                const int32_t *gt_offsets, int gt_total, int gmax, float lambda_cls, float lambda_dfl,
                                void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou,
                                float *out_per_image, void *workspace, size_t workspace_bytes, unsigned flags,
-                               void *const *stage_events, void *stream) {
+                               const yb_anchor_grid *grid_hint, void *const *stage_events, void *stream) {
     YB_REQUIRE(preds && anchors && strides && gt_offsets && out_loss && workspace, "yb_loss_fwd_bwd: null pointer");
     YB_REQUIRE(gt_total == 0 || gt != nullptr, "yb_loss_fwd_bwd: gt is null but gt_total > 0");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && gt_total >= 0 && gmax >= 0, "yb_loss_fwd_bwd: bad sizes");
@@ -1096,16 +1186,24 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
         return YB_ERR_ALIGN;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    yb_anchor_grid grid;
+    memset(&grid, 0, sizeof(grid));                        // n_levels = 0: no hint, no probe role
+    if (grid_hint != nullptr && grid_hint->n_levels > 0 && grid_hint->n_levels <= YB_TAL_MAX_LEVELS) {
+        bool sane = true;                                  // shapes only; the VALUES cannot hurt (probe_gts clamps)
+        for (int l = 0; l < grid_hint->n_levels; ++l)
+            sane = sane && grid_hint->w[l] > 0 && grid_hint->h[l] > 0 && grid_hint->stride[l] > 0.f;
+        if (sane) grid = *grid_hint;
+    }
     if (dtype == YB_F32) {
         const bool vec = vector_ok<float>(preds, grad_preds, n_anchors);
         const LossWorkspace w = carve(workspace, n_images, gt_total);
         if (vec)
             return launch_loss<float, 4>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt,
                                          gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl, (float *)grad_preds,
-                                         out_loss, out_idx, out_iou, out_per_image, w, flags, stage_events, st);
+                                         out_loss, out_idx, out_iou, out_per_image, w, flags, grid, stage_events, st);
         return launch_loss<float, 1>((const float *)preds, n_images, nc, n_anchors, anchors, strides, gt, gt_offsets,
                                      gt_total, gmax, lambda_cls, lambda_dfl, (float *)grad_preds, out_loss, out_idx,
-                                     out_iou, out_per_image, w, flags, stage_events, st);
+                                     out_iou, out_per_image, w, flags, grid, stage_events, st);
     }
     const bool vec = vector_ok<__nv_bfloat16>(preds, grad_preds, n_anchors);
     const LossWorkspace w = carve(workspace, n_images, gt_total);
@@ -1113,10 +1211,10 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
         return launch_loss<__nv_bfloat16, 8>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides,
                                              gt, gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl,
                                              (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w,
-                                             flags, stage_events, st);
+                                             flags, grid, stage_events, st);
     return launch_loss<__nv_bfloat16, 1>((const __nv_bfloat16 *)preds, n_images, nc, n_anchors, anchors, strides, gt,
                                          gt_offsets, gt_total, gmax, lambda_cls, lambda_dfl,
-                                         (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w, flags, stage_events, st);
+                                         (__nv_bfloat16 *)grad_preds, out_loss, out_idx, out_iou, out_per_image, w, flags, grid, stage_events, st);
 }
 
 extern "C" int yb_scale_grad(void *grad, int dtype, size_t n_elements, const float *scale, void *stream) {
@@ -1155,7 +1253,7 @@ extern "C" int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_ima
                             cudaMemcpyHostToDevice, st));
     const int rc = yb_loss_fwd_bwd(preds_dev, dtype, n_images, nc, reg_max, n_anchors, anchors, strides, gt_dev,
                                    gt_offsets_dev, gt_total, gmax, lambda_cls, lambda_dfl, grad_dev, out_loss_dev,
-                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, 0u, nullptr, stream);
+                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, 0u, nullptr, nullptr, stream);
     if (rc != YB_OK) return rc;
     YB_CUDA(cudaMemcpyAsync(out_loss_host, out_loss_dev, sizeof(float) * 8, cudaMemcpyDeviceToHost, st));
     if (grad_host != nullptr && grad_dev != nullptr)

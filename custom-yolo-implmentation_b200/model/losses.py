@@ -143,14 +143,16 @@ def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
 
 def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, gmax: int, anchors: torch.Tensor,
                strides: torch.Tensor, num_classes: int, lambda_cls: float, lambda_dfl: float, reg_max: int = 16,
-               want_grad: bool = True, want_trace: bool = False, flags: int = 0, stage_events=None):
+               want_grad: bool = True, want_trace: bool = False, flags: int = 0, stage_events=None, grid_hint="auto"):
     """One call of ``yb_loss_fwd_bwd``.  Returns ``(out_loss (8,), grad or None, trace dict)``.
 
     ``out_loss`` = [total, mean DFL, mean QFL, #matched anchors, 0, 0, in-kernel dependency timed out (never, see
     csrc/common.cuh), #GT rows with a class id outside [0, nc)] on the device.  ``trace`` (``want_trace``) holds the per-GT matched anchor / IoU and per-image
     loss terms the parity tests compare against the oracle.  ``flags``: ``_cabi.YB_LOSS_NO_PRUNE`` /
     ``YB_LOSS_SPLIT_LAUNCH`` (test / profiling aids).  ``stage_events``: three ``torch.cuda.Event(enable_timing=True)``
-    recorded around the launch(es) (bench.py's roofline leg).
+    recorded around the launch(es) (bench.py's roofline leg).  ``grid_hint``: ``"auto"`` (describe the anchors as a
+    pyramid of grids once per size: the launch then bounds every GT's nearest-centre distance from a few probe anchors and
+    prunes from its first tile on), ``None`` or a ``_cabi.TalGrid``; results never depend on it.
     """
     _cabi.require_cuda(preds, "preds")
     if preds.dim() != 3:
@@ -187,12 +189,14 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
         iou = torch.empty(max(gt_total, 1), dtype=torch.float32, device=dev)
         per_image = torch.empty(2, n, dtype=torch.float32, device=dev)
         trace = {"idx": idx[:gt_total], "iou": iou[:gt_total], "dfl_per_image": per_image[0], "cls_per_image": per_image[1]}
+    hint = _grid_hint_for(anc, st, exact=False) if isinstance(grid_hint, str) else grid_hint
     with torch.cuda.device(dev):
+        import ctypes
         rc = lib.yb_loss_fwd_bwd(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st),
                                  _cabi.ptr(gt) if gt_total else None, _cabi.ptr(gt_offsets), gt_total, gmax,
                                  float(lambda_cls), float(lambda_dfl), _cabi.ptr(grad), _cabi.ptr(out),
                                  _cabi.ptr(idx), _cabi.ptr(iou), _cabi.ptr(per_image), _cabi.ptr(ws), ws.numel(),
-                                 int(flags), ev, _cabi.stream_ptr(dev))
+                                 int(flags), ctypes.byref(hint) if hint is not None else None, ev, _cabi.stream_ptr(dev))
     _cabi.check(rc, "yb_loss_fwd_bwd")
     return out, grad, trace
 
@@ -255,11 +259,13 @@ _grid_hints = {}        # (device index, A) -> TalGrid | None (the anchors are n
 _grid_strikes = {}
 
 
-def build_grid_hint(anchors: torch.Tensor, strides: torch.Tensor):
+def build_grid_hint(anchors: torch.Tensor, strides: torch.Tensor, exact: bool = True):
     """Describe ``anchors (2, A)`` / ``strides (1, A)`` as the reference's pyramid of regular grids
     (``make_anchors``, model_utils.py:60-70: per level x fastest, ``(x0 + col, y0 + row)``, one stride per level), or
     return ``None`` when they are not one.  Pure host logic on a CPU copy; called once per anchor-set size, the
-    device re-verifies the result on every call."""
+    device re-verifies the result on every call.  ``exact=False`` accepts coordinates within one cell of the grid
+    (anchors built in bf16): good enough for ``yb_loss_fwd_bwd``'s probe role, which only
+    needs a cell NEAR each box centre; the task-aligned path verifies its hint bit for bit and takes exact ones only."""
     anc = anchors.detach().float().cpu().reshape(2, -1)
     st = strides.detach().float().cpu().reshape(-1)
     a = st.numel()
@@ -279,17 +285,20 @@ def build_grid_hint(anchors: torch.Tensor, strides: torch.Tensor):
         h = (hi - lo) // w
         col = torch.arange(w, dtype=torch.float32).repeat(h)
         row = torch.arange(h, dtype=torch.float32).repeat_interleave(w)
-        if not (torch.equal(ax, ax[0] + col) and torch.equal(ay, ay[0] + row)):
+        if exact:
+            if not (torch.equal(ax, ax[0] + col) and torch.equal(ay, ay[0] + row)):
+                return None
+        elif not ((ax - (ax[0] + col)).abs().max() <= 1.0 and (ay - (ay[0] + row)).abs().max() <= 1.0):
             return None
         hint.start[l], hint.w[l], hint.h[l] = lo, w, h
         hint.stride[l], hint.x0[l], hint.y0[l] = float(st[lo]), float(ax[0]), float(ay[0])
     return hint
 
 
-def _grid_hint_for(anc: torch.Tensor, st: torch.Tensor):
-    key = (anc.device.index, anc.shape[1])
+def _grid_hint_for(anc: torch.Tensor, st: torch.Tensor, exact: bool = True):
+    key = (anc.device.index, anc.shape[1]) if exact else (anc.device.index, anc.shape[1], "approx")
     if key not in _grid_hints:
-        _grid_hints[key] = build_grid_hint(anc, st)       # one device-to-host copy, the first time this size is seen
+        _grid_hints[key] = build_grid_hint(anc, st, exact)    # one device-to-host copy, the first time this size is seen
     return _grid_hints[key]
 
 

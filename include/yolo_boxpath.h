@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 4
+#define YB_ABI_VERSION 5
 
 typedef enum { YB_F32 = 0, YB_BF16 = 1 } yb_dtype;
 
@@ -45,6 +45,18 @@ int yb_abi_version(void);
 const char *yb_last_error(void);
 /* Kernels this library has launched in this process so far (bench.py reports the delta as gpu_launches). */
 long long yb_launch_count(void);
+
+/* The anchors described as the reference's pyramid of regular grids (make_anchors, src/utils/model_utils.py:60-70: per
+ * level x fastest, (x0 + col, y0 + row), one stride per level): level l holds anchors start[l] .. start[l] + w[l]*h[l].
+ * A HINT, never a precondition: anchors and strides stay inputs of every entry point, the kernels either verify the
+ * hint bit for bit (yb_tal_assign) or use it only where a wrong value costs speed, not correctness (yb_loss_fwd_bwd). */
+#define YB_TAL_MAX_LEVELS 8
+typedef struct {
+    int n_levels;                               /* 0: no hint */
+    int start[YB_TAL_MAX_LEVELS], w[YB_TAL_MAX_LEVELS], h[YB_TAL_MAX_LEVELS];
+    float stride[YB_TAL_MAX_LEVELS], x0[YB_TAL_MAX_LEVELS], y0[YB_TAL_MAX_LEVELS];
+} yb_tal_grid;                                  /* host struct, read during the call */
+typedef yb_tal_grid yb_anchor_grid;
 
 /* ------------------------------------------------------------------------------------------
  * Training: fused decode + nearest-centre assignment + DFL/QFL loss + backward.
@@ -68,7 +80,11 @@ long long yb_launch_count(void);
  *   out_idx      (gt_total) int32 or NULL                 matched anchor per GT  (losses.py:215)
  *   out_iou      (gt_total) fp32  or NULL                 IoU soft target per GT (losses.py:256)
  *   out_per_image (2, N) fp32 or NULL                     per-image DFL and QFL terms
- *   flags        0, or YB_LOSS_NO_PRUNE / YB_LOSS_SPLIT_LAUNCH (test and profiling aids, results identical)
+ *   flags        0, or YB_LOSS_NO_PRUNE / YB_LOSS_SPLIT_LAUNCH / YB_LOSS_FORCE_PROBE (test and profiling aids, results identical)
+ *   grid_hint    NULL, or the anchors as a pyramid of grids: lets the launch bound every GT's nearest-centre distance
+ *                up front (a few probe anchors per GT), so that the box role prunes from its first tile on; used when
+ *                gmax > 128, where the coarse pyramid levels would otherwise scan several chunks of GTs.  Results
+ *                never depend on it (tests/test_gpu_loss.py::test_tile_pruning_never_changes_the_result)
  *   stage_events NULL, or three cudaEvent_t handles of the CALLER (as void*), recorded on `stream` before the
  *                launch, after it, and (YB_LOSS_SPLIT_LAUNCH) after match_kernel (bench.py's roofline leg)
  *
@@ -84,9 +100,11 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
                     const float *gt, const int32_t *gt_offsets, int gt_total, int gmax,
                     float lambda_cls, float lambda_dfl,
                     void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou, float *out_per_image,
-                    void *workspace, size_t workspace_bytes, unsigned flags, void *const *stage_events, void *stream);
+                    void *workspace, size_t workspace_bytes, unsigned flags, const yb_anchor_grid *grid_hint,
+                    void *const *stage_events, void *stream);
 
 #define YB_LOSS_NO_PRUNE 1u      /* box role scans every (GT, tile) pair: the exactness tests compare with and without */
+#define YB_LOSS_FORCE_PROBE 4u   /* run the probe role (grid_hint) whatever gmax says: the exactness tests exercise it on small inputs */
 #define YB_LOSS_SPLIT_LAUNCH 2u  /* box, class and match roles as three launches instead of one (profiling the roles apart) */
 
 /* grad *= *scale (device scalar), in place; returns without touching memory when *scale == 1.
@@ -158,13 +176,6 @@ int yb_peer_mailbox_free(void *mailbox);
 int yb_peer_mailbox_export(void *mailbox, void *handle_out_64);
 int yb_peer_mailbox_open(const void *handle_64, void **peer_mailbox_out);
 int yb_peer_mailbox_close(void *peer_mailbox);
-
-#define YB_TAL_MAX_LEVELS 8
-typedef struct {
-    int n_levels;                               /* 0: no hint */
-    int start[YB_TAL_MAX_LEVELS], w[YB_TAL_MAX_LEVELS], h[YB_TAL_MAX_LEVELS];
-    float stride[YB_TAL_MAX_LEVELS], x0[YB_TAL_MAX_LEVELS], y0[YB_TAL_MAX_LEVELS];
-} yb_tal_grid;                                  /* host struct, read during the call */
 
 size_t yb_tal_workspace_bytes(int n_images, int n_anchors, int gt_total, int dtype, int topk);
 

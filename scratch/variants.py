@@ -32,7 +32,7 @@ def run_all():
         counts = [g.shape[0] for g in gts]
         off = torch.tensor([0] + list(itertools.accumulate(counts)), dtype=torch.int32, device=dev)
         data[cn] = dict(preds=preds.to(dev), gt=torch.cat(gts).to(dev), off=off, anc=anchors.float().to(dev), st=strides.float().to(dev),
-                        n=n, nc=nc, a=preds.shape[2], gt_total=sum(counts), gmax=max(counts), dt=1 if dt == torch.bfloat16 else 0)
+                        hint=(__import__('custom_yolo_implmentation_b200.model.losses', fromlist=['x']).build_grid_hint(*syn.anchor_grid(imgsz)) if os.environ.get('YB_NO_HINT') is None else None), n=n, nc=nc, a=preds.shape[2], gt_total=sum(counts), gmax=max(counts), dt=1 if dt == torch.bfloat16 else 0)
     for v in VARIANTS:
         so = os.path.join(OUT, f'lib_{name(v)}.so')
         if not os.path.exists(so): continue
@@ -41,7 +41,7 @@ def run_all():
         lib.yb_loss_workspace_bytes.argtypes = [ctypes.c_int] * 4
         P = ctypes.c_void_p
         lib.yb_loss_fwd_bwd.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P, P, P, ctypes.c_int, ctypes.c_int,
-                                        ctypes.c_float, ctypes.c_float, P, P, P, P, P, P, ctypes.c_size_t, ctypes.c_uint, P, P]
+                                        ctypes.c_float, ctypes.c_float, P, P, P, P, P, P, ctypes.c_size_t, ctypes.c_uint, P, P, P]
         line = [f'{name(v):28s}']
         for cn, d in data.items():
             ws = torch.empty(lib.yb_loss_workspace_bytes(d['n'], d['a'], d['gt_total'], d['dt']), dtype=torch.uint8, device=dev)
@@ -49,7 +49,7 @@ def run_all():
             st = torch.cuda.current_stream().cuda_stream
             def call():
                 rc = lib.yb_loss_fwd_bwd(d['preds'].data_ptr(), d['dt'], d['n'], d['nc'], 16, d['a'], d['anc'].data_ptr(), d['st'].data_ptr(), d['gt'].data_ptr(),
-                                         d['off'].data_ptr(), d['gt_total'], d['gmax'], 1.0, 1.5, grad.data_ptr(), out.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), 0, None, st)
+                                         d['off'].data_ptr(), d['gt_total'], d['gmax'], 1.0, 1.5, grad.data_ptr(), out.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), 0, (ctypes.byref(d['hint']) if d['hint'] is not None else None), None, st)
                 assert rc == 0, lib.yb_last_error()
             for _ in range(3): call()
             torch.cuda.synchronize()

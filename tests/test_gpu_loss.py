@@ -26,10 +26,11 @@ def run_cuda(preds, gts, anchors, strides, nc, dev, **kw):
     return loss.detach().cpu(), parts, x.grad.detach().cpu(), crit
 
 
-def run_cuda_trace(preds, gts, anchors, strides, nc, dev, want_grad=True, lambda_cls=1.0, lambda_dfl=1.5, flags=0):
+def run_cuda_trace(preds, gts, anchors, strides, nc, dev, want_grad=True, lambda_cls=1.0, lambda_dfl=1.5, flags=0,
+                   grid_hint="auto"):
     gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
     out, grad, tr = P.fused_loss(preds.to(dev), gt, off, max(counts), anchors.to(dev), strides.to(dev), nc,
-                                 lambda_cls, lambda_dfl, want_grad=want_grad, want_trace=True, flags=flags)
+                                 lambda_cls, lambda_dfl, want_grad=want_grad, want_trace=True, flags=flags, grid_hint=grid_hint)
     idx = tr["idx"].cpu().long()
     split = lambda t: list(torch.split(t, counts))
     return out.cpu(), (grad.cpu() if grad is not None else None), split(idx), split(tr["iou"].cpu()), \
@@ -401,21 +402,28 @@ def test_fused_loss_is_cuda_graph_capturable(cuda_device):
 ])
 def test_tile_pruning_never_changes_the_result(n, imgsz, gmax, dtype, seed, cuda_device):
     """The box role skips (GT, tile) pairs that cannot beat the distance already published (csrc/loss.cu,
-    assign_body).  That must be invisible: matched anchors, IoUs, loss terms and the gradient are bit-identical
-    with the pruning switched off (flag YB_LOSS_NO_PRUNE) and with the two roles launched separately
-    (YB_LOSS_SPLIT_LAUNCH), at sizes where almost every pair is pruned."""
+    assign_body) or the bound the probe role derived from a few anchors per GT (probe_gts, driven by the grid hint).
+    That must be invisible: matched anchors, IoUs, loss terms and the gradient are bit-identical with the pruning
+    switched off (flag YB_LOSS_NO_PRUNE), without the hint, with a hint that does NOT describe the anchors, and with
+    the roles launched separately (YB_LOSS_SPLIT_LAUNCH), at sizes where almost every pair is pruned."""
     from custom_yolo_implmentation_b200 import _cabi
     preds, gts, anchors, strides = syn.make_loss_inputs(n, 80, imgsz, gmax, seed, dtype=dtype)
-    ref = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device, flags=_cabi.YB_LOSS_NO_PRUNE)
-    for it in range(3):                         # what is pruned depends on CTA timing; the result must not
-        got = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device,
-                             flags=_cabi.YB_LOSS_SPLIT_LAUNCH if it == 2 else 0)
-        assert torch.equal(got[0], ref[0])
-        assert torch.equal(got[1], ref[1])
+    ref = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device, flags=_cabi.YB_LOSS_NO_PRUNE, grid_hint=None)
+    hint = P.build_grid_hint(anchors.float(), strides.float(), exact=False)      # bf16-rounded anchors are only NEAR a grid
+    assert hint is not None and hint.n_levels == 3
+    assert (P.build_grid_hint(anchors.float(), strides.float()) is None) == (dtype == torch.bfloat16)
+    wrong = _cabi.TalGrid.from_buffer_copy(hint)
+    wrong.x0[0], wrong.stride[1], wrong.w[2] = 3.25, 40.0, 7             # nonsense geometry: costs pruning, nothing else
+    force = _cabi.YB_LOSS_FORCE_PROBE                                     # the probe role whatever the number of GTs
+    for it, kw in enumerate((dict(), dict(flags=force), dict(flags=_cabi.YB_LOSS_SPLIT_LAUNCH), dict(grid_hint=None),
+                             dict(grid_hint=wrong, flags=force))):   # what is pruned depends on CTA timing; the result must not
+        got = run_cuda_trace(preds, gts, anchors, strides, 80, cuda_device, **kw)
+        assert torch.equal(got[0], ref[0]), it
+        assert torch.equal(got[1], ref[1]), it
         for a, b in zip(got[2], ref[2]):
-            assert torch.equal(a, b)
+            assert torch.equal(a, b), it
         for a, b in zip(got[3], ref[3]):
-            assert torch.equal(a, b)
+            assert torch.equal(a, b), it
 
 
 def test_fp16_head_output_goes_through_float_like_the_reference(cuda_device):

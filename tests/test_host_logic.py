@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_come_back_through_the_abi():
     lib = _cabi.lib()
     rc = lib.yb_loss_fwd_bwd(None, 0, 1, 1, 16, 4, None, None, None, None, 0, 0, 1.0, 1.5, None, None, None, None, None,
-                             None, 0, 0, None, None)
+                             None, 0, 0, None, None, None)
     assert rc == -1 and b"null pointer" in lib.yb_last_error()
     rc = lib.yb_nms(None, 1, 1, 4, 0.1, 0.5, 300, 0, None, 0, None, None, None, None, 0, None)
     assert rc == -1
