@@ -188,8 +188,10 @@ __device__ __forceinline__ float4 load_offset_box(const float *__restrict__ img,
 }
 
 // Cheap necessary condition for iou_exceeds: the boxes overlap in x and in y (four comparisons).
+// (Non-short-circuit on purpose: `&&` compiled into a chain of divergent branches in the pair loops, 17 BRA per
+// four rows; as predicate logic the test is four FSETP feeding one PLOP3.)
 __device__ __forceinline__ bool boxes_touch(const float4 &a, const float4 &b) {
-    return a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y;
+    return (a.z > b.x) & (b.z > a.x) & (a.w > b.y) & (b.w > a.y);
 }
 
 // IoU <= min(area) / max(area), so |log2(area_a) - log2(area_b)| > -log2(0.99 * thr) rules a pair out
@@ -219,7 +221,7 @@ __device__ __forceinline__ unsigned resolve_block(const float4 &bx, bool alive, 
         o.z = __shfl_sync(0xffffffffu, bx.z, partner);
         o.w = __shfl_sync(0xffffffffu, bx.w, partner);
         const float o_la = __shfl_sync(0xffffffffu, my_la, partner);
-        const bool maybe = boxes_touch(bx, o) && areas_compatible(my_la, o_la, la_bound);
+        const bool maybe = boxes_touch(bx, o) & areas_compatible(my_la, o_la, la_bound);
         if (__any_sync(0xffffffffu, maybe)) {
             if (maybe && iou_exceeds(bx, my_area, o, thr)) {
                 if (partner > lane) sup |= 1u << partner;
@@ -412,6 +414,7 @@ constexpr int kClassMaxDet = 1024;
 constexpr int kAnchorBits = 22;
 constexpr int kSelBits = 11;
 
+
 __global__ void __launch_bounds__(kClassThreads, 1)
 nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *__restrict__ count,
                  const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
@@ -577,6 +580,10 @@ nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int 
 #endif
         unsigned alive_bits = 0;
         const float la_bound = log_area_bound(thr);
+        // (Measured and not kept: for segments of up to 128 boxes, all rows against all later columns first -- ballot words
+        // of a block-upper-triangular suppression matrix in registers, no row waiting for the fate of another -- and the
+        // greedy order applied afterwards by a sweep over the words: 187 us per 64 images against 153 us for the
+        // row-by-row form below, which skips the rows and columns already suppressed.)
         for (int b = 0; b < nb; ++b) alive_bits |= (b * 32 + lane < n_c ? 1u : 0u) << b;
         for (int rb = 0; rb < nb; ++rb) {
             const int my = rb * 32 + lane;
@@ -609,11 +616,11 @@ nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int 
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int r = min(i + u, nk - 1);  // the tail repeats the last row: harmless
-                        maybe[u] = live && boxes_touch(s_rowbox[warp][r], cbox) &&
+                        maybe[u] = live & boxes_touch(s_rowbox[warp][r], cbox) &
                                    areas_compatible(s_rowla[warp][r], c_la, la_bound);
                     }
                     // most same-class pairs cannot reach the threshold: one vote skips the IoU arithmetic
-                    if (__any_sync(0xffffffffu, maybe[0] || maybe[1] || maybe[2] || maybe[3])) {
+                    if (__any_sync(0xffffffffu, maybe[0] | maybe[1] | maybe[2] | maybe[3])) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             if (maybe[u]) sup |= iou_exceeds(cbox, c_area, s_rowbox[warp][min(i + u, nk - 1)], thr);
