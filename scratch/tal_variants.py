@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 CSRC = os.path.join(ROOT, 'custom-yolo-implmentation_b200', 'csrc')
 OUT = os.path.join(ROOT, 'scratch', 'variants')
-VARIANTS = json.load(open(os.path.join(ROOT, 'scratch', 'tal_variants.json')))
+VARIANTS = json.load(open(os.environ.get('YB_VARIANTS', os.path.join(ROOT, 'scratch', 'tal_variants.json'))))
 def name(v): return v['_name'] if '_name' in v else 'base' if not v else '_'.join(f"{k[3:].lower()}{val}" for k, val in sorted(v.items()))
 def build_all():
     os.makedirs(OUT, exist_ok=True)
