@@ -353,7 +353,8 @@ def run_ours(args):
             n_bad = sum(r[2] - r[1] for r in allr)
             parity["note"] = ("exact" if n_bad == 0 else
                               f"{int(n_bad)} GT(s) on an exact float tie of the distance went to the other (equidistant) anchor")
-            bad_rank = [i for i, r in enumerate(allr) if (r[0] > 1e-5 and r[1] == r[2]) or r[0] > 2e-4 or r[2] - r[1] > 1e-3 * r[2]]
+            # (each flipped tie may move the loss by up to ~1e-4 relative: bound 1e-5 + 1e-4 per flipped GT)
+            bad_rank = [i for i, r in enumerate(allr) if r[0] > 1e-5 + 1e-4 * (r[2] - r[1]) or r[2] - r[1] > 1e-3 * r[2]]
             if bad_rank:
                 raise SystemExit(f"bench.py: PARITY FAILURE on the benchmark batch (ranks {bad_rank}): {parity} {allr}")
     if world > 1:
