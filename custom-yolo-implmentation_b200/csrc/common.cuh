@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include "../../include/yolo_boxpath.h"
@@ -32,6 +33,17 @@ void note_launch();
             return YB_ERR_ARG;           \
         }                                \
     } while (0)
+
+// An NVTX range around each entry point of the ABI (the reference wraps nothing: SURVEY.md §5 asks for the ranges a
+// timeline needs to attribute the launches to the call that issued them).  Header-only NVTX3: a no-op costing one
+// indirect call unless a tool (nsys, ncu --nvtx) is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define YB_NVTX(name) ::yb::NvtxRange nvtx_range__(name)
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }

@@ -294,6 +294,7 @@ using namespace yb;
 extern "C" int yb_dfl_decode(const void *box_logits, int dtype, int n_images, int reg_max, int n_anchors,
                              size_t image_stride, const float *anchors, const float *strides, float *out_ltrb,
                              float *out_box, int box_format, int scale_by_stride, void *stream) {
+    YB_NVTX("yb_dfl_decode");
     YB_REQUIRE(box_logits != nullptr, "yb_dfl_decode: null input");
     YB_REQUIRE(out_ltrb || out_box, "yb_dfl_decode: no output requested");
     YB_REQUIRE(!out_box || anchors, "yb_dfl_decode: anchors required for box output");
@@ -348,6 +349,7 @@ extern "C" int yb_val_decode(const void *preds, int dtype, int n_images, int nc,
                              const float *anchors, const float *strides, float conf_thres, int top_k,
                              float *out_rows, int32_t *out_count, int32_t *out_anchor, void *workspace,
                              size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_val_decode");
     YB_REQUIRE(preds && anchors && strides && out_rows && out_count && workspace, "yb_val_decode: null pointer");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && top_k > 0 && n_images <= 65535, "yb_val_decode: bad sizes");
     YB_REQUIRE(reg_max == kRegMax, "yb_val_decode: reg_max must be %d (got %d)", kRegMax, reg_max);

@@ -110,12 +110,14 @@ static int head_tail(bool gather, void *const *box_levels, void *const *cls_leve
 
 extern "C" int yb_head_gather(const void *const *box_levels, const void *const *cls_levels, const int32_t *hw_host,
                               int n_levels, int dtype, int n_images, int box_ch, int nc, void *out, void *stream) {
+    YB_NVTX("yb_head_gather");
     return yb::head_tail(true, const_cast<void *const *>(box_levels), const_cast<void *const *>(cls_levels), hw_host,
                          n_levels, dtype, n_images, box_ch, nc, out, stream);
 }
 
 extern "C" int yb_head_scatter(const void *grad, const int32_t *hw_host, int n_levels, int dtype, int n_images,
                                int box_ch, int nc, void *const *box_grads, void *const *cls_grads, void *stream) {
+    YB_NVTX("yb_head_scatter");
     return yb::head_tail(false, box_grads, cls_grads, hw_host, n_levels, dtype, n_images, box_ch, nc,
                          const_cast<void *>(grad), stream);
 }

@@ -1168,6 +1168,7 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
                                void *grad_preds, float *out_loss, int32_t *out_idx, float *out_iou,
                                float *out_per_image, void *workspace, size_t workspace_bytes, unsigned flags,
                                const yb_anchor_grid *grid_hint, void *const *stage_events, void *stream) {
+    YB_NVTX("yb_loss_fwd_bwd");
     YB_REQUIRE(preds && anchors && strides && gt_offsets && out_loss && workspace, "yb_loss_fwd_bwd: null pointer");
     YB_REQUIRE(gt_total == 0 || gt != nullptr, "yb_loss_fwd_bwd: gt is null but gt_total > 0");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && gt_total >= 0 && gmax >= 0, "yb_loss_fwd_bwd: bad sizes");
@@ -1218,6 +1219,7 @@ extern "C" int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int n
 }
 
 extern "C" int yb_scale_grad(void *grad, int dtype, size_t n_elements, const float *scale, void *stream) {
+    YB_NVTX("yb_scale_grad");
     YB_REQUIRE(grad && scale, "yb_scale_grad: null pointer");
     YB_REQUIRE(dtype == YB_F32 || dtype == YB_BF16, "yb_scale_grad: bad dtype");
     if (n_elements == 0) return YB_OK;
@@ -1237,6 +1239,7 @@ extern "C" int yb_loss_fwd_bwd_host(const void *preds_host, int dtype, int n_ima
                                     float lambda_dfl, void *preds_dev, float *gt_dev, int32_t *gt_offsets_dev,
                                     void *grad_dev, float *out_loss_dev, float *out_loss_host, void *grad_host,
                                     void *workspace, size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_loss_fwd_bwd_host");
     YB_REQUIRE(preds_host && preds_dev && gt_offsets_host && gt_offsets_dev && out_loss_dev && out_loss_host,
                "yb_loss_fwd_bwd_host: null pointer");
     YB_REQUIRE(dtype == YB_F32 || dtype == YB_BF16, "yb_loss_fwd_bwd_host: bad dtype");

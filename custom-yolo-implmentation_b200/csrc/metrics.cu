@@ -164,6 +164,7 @@ extern "C" int yb_detection_match(const float *pred_rows, int row_stride, const 
                                   const float *pred_scores, float score_threshold, const float *gt,
                                   const int32_t *gt_offsets, int gmax, int n_images, int nc, float iou_threshold,
                                   int skip_empty_targets, uint64_t *counters, void *stream) {
+    YB_NVTX("yb_detection_match");
     YB_REQUIRE(pred_count && gt_offsets && counters, "yb_detection_match: null pointer");
     YB_REQUIRE(n_images > 0 && nc > 0 && row_stride >= 0, "yb_detection_match: bad sizes");
     YB_REQUIRE(row_stride == 0 || pred_rows, "yb_detection_match: pred_rows is null");

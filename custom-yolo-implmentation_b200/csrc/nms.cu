@@ -993,6 +993,7 @@ static int run_nms(const NmsInput &in, int score_dtype, int sigmoid, int n_image
 extern "C" int yb_nms(const float *prediction, int n_images, int nc, int n_anchors, float conf_thres, double iou_thres,
                       int max_det, int agnostic, const int32_t *class_filter, int n_class_filter, float *out_rows,
                       int32_t *out_count, int32_t *out_anchor, void *workspace, size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_nms");
     YB_REQUIRE(prediction && out_rows && out_count && workspace, "yb_nms: null pointer");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && max_det > 0 && n_images <= 65535, "yb_nms: bad sizes");
     YB_REQUIRE(n_class_filter >= 0 && (n_class_filter == 0 || class_filter), "yb_nms: bad class filter");
@@ -1031,6 +1032,7 @@ extern "C" int yb_postprocess(const void *head_out, int dtype, int n_images, int
                               double iou_thres, int max_det, int agnostic, const int32_t *class_filter, int n_class_filter,
                               float *out_rows, int32_t *out_count, int32_t *out_anchor, void *workspace,
                               size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_postprocess");
     YB_REQUIRE(head_out && anchors && strides && out_rows && out_count && workspace, "yb_postprocess: null pointer");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && max_det > 0 && n_images <= 65535, "yb_postprocess: bad sizes");
     YB_REQUIRE(dtype == YB_F32 || dtype == YB_BF16, "yb_postprocess: dtype must be YB_F32 or YB_BF16");
@@ -1070,6 +1072,7 @@ extern "C" int yb_nms_multilabel(const float *prediction, int n_images, int nc, 
                                  double iou_thres, int max_det, int agnostic, const int32_t *class_filter,
                                  int n_class_filter, float *out_rows, int32_t *out_count, int32_t *out_anchor,
                                  void *workspace, size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_nms_multilabel");
     YB_REQUIRE(prediction && out_rows && out_count && workspace, "yb_nms_multilabel: null pointer");
     YB_REQUIRE(n_images > 0 && nc > 0 && n_anchors > 0 && max_det > 0 && n_images <= 65535, "yb_nms_multilabel: bad sizes");
     YB_REQUIRE((long long)n_anchors * nc < (1ll << 32), "yb_nms_multilabel: anchors x classes must fit 32 bits");

@@ -1311,6 +1311,7 @@ extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc,
                              int gt_total, const yb_tal_params *params, const yb_tal_grid *grid_hint,
                              const yb_peer_exchange *peers, float *out_stats, int32_t *out_assigned_gt,
                              float *out_target_score, void *workspace, size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_tal_assign");
     if (int rc = tal_check(preds, workspace, params, dtype, n_images, nc, reg_max, n_anchors, gt_total, "yb_tal_assign"))
         return rc;
     YB_REQUIRE(anchors && strides && gt_offsets && out_stats, "yb_tal_assign: null pointer");
@@ -1363,6 +1364,7 @@ extern "C" int yb_tal_assign(const void *preds, int dtype, int n_images, int nc,
 extern "C" int yb_tal_loss(const void *preds, int dtype, int n_images, int nc, int reg_max, int n_anchors, int gt_total,
                            const yb_tal_params *params, const float *tss_dev, const yb_peer_exchange *peers,
                            void *grad_preds, float *out_loss, void *workspace, size_t workspace_bytes, void *stream) {
+    YB_NVTX("yb_tal_loss");
     if (int rc = tal_check(preds, workspace, params, dtype, n_images, nc, reg_max, n_anchors, gt_total, "yb_tal_loss"))
         return rc;
     YB_REQUIRE((tss_dev || peers) && out_loss, "yb_tal_loss: null pointer");
