@@ -411,7 +411,7 @@ def run_ours(args):
         x_leaf.grad = None
         loss, parts = crit(x_leaf, gt_arg, anchors_d, strides_d)
         loss.backward()
-        return parts
+        return parts["total_loss"]               # read every step, as the reference's loop does after backward (train_model.py:255)
 
     packed_d = pack_gt_host(gts_h, pin_memory=False).to(dev)
     api_list_ms = time_steps(lambda: api_step(gts_d), extra_steps)
@@ -456,6 +456,7 @@ def run_ours(args):
             x.requires_grad_(True)
             loss, parts = crit(x, pg, anchors_d, strides_d)            # parts: one D2H copy of the loss scalars
             loss.backward()
+            parts["total_loss"]                                          # read every step (waits for the step's D2H copy)
         return parts
 
     e2e_steps = max(3, min(args.steps, 10))

@@ -226,6 +226,94 @@ def _raise_on_stall(flag: float, who: str):
         raise RuntimeError(f"{who}: an in-kernel dependency timed out (blocks were not dispatched in index order)")
 
 
+class LossDict(dict):
+    """The ``{"total_loss", "box_loss", "cls_loss"[, "dfl_loss"]}`` dict of Python floats that ``forward`` returns
+    (src/model/losses.py:277-281), fetched LAZILY: ``forward`` only queues one asynchronous device-to-host copy of the
+    8-float statistics vector into pinned memory, and the first read of a value waits for it.  The reference's training
+    loop reads the dict after ``loss.backward()`` and ``optimizer.step()`` (train_model.py:247-258), so the host no longer
+    stalls inside ``forward`` for the kernels to finish (the reference's three ``.item()`` calls do).  What the kernels
+    report about the inputs -- class ids outside ``[0, nc)``, on which the reference's ``scatter_`` raises -- is raised by
+    the same first read.  Every way of reading values goes through ``_fetch``; keys, ``len`` and ``in`` need no data."""
+
+    _ring = {}                          # device index -> [pinned (8,) buffers], recycled round-robin
+    _owner = {}                         # id(buffer) -> weakref to the LossDict still waiting on it
+
+    def __init__(self, stats: torch.Tensor, names, check):
+        super().__init__((k, None) for k in names)
+        self._names = tuple(names)
+        self._check = check
+        ring = LossDict._ring.setdefault(stats.device.index, {"bufs": [torch.empty(8, dtype=torch.float32).pin_memory()
+                                                                       for _ in range(8)], "next": 0})
+        buf = ring["bufs"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % len(ring["bufs"])
+        prev = LossDict._owner.get(id(buf))
+        prev = prev() if prev is not None else None
+        if prev is not None:
+            prev._fetch()                                   # an older dict nobody has read yet still owns this buffer
+        import weakref
+        LossDict._owner[id(buf)] = weakref.ref(self)
+        self._buf = buf
+        buf.copy_(stats, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(stats.device))
+
+    def _fetch(self):
+        if self._buf is None:
+            return
+        self._event.synchronize()
+        host = self._buf.tolist()
+        self._buf = self._event = None
+        for i, k in enumerate(self._names):
+            dict.__setitem__(self, k, host[i])
+        check, self._check = self._check, None
+        check(host)                                         # may raise (the values are in place either way)
+
+    def __getitem__(self, k):
+        self._fetch()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        self._fetch()
+        return dict.get(self, k, default)
+
+    def __iter__(self):                 # (also keeps dict(d) / {**d} off the raw-storage fast path)
+        return iter(self._names)
+
+    def keys(self):
+        return dict.keys(self)
+
+    def values(self):
+        self._fetch()
+        return dict.values(self)
+
+    def items(self):
+        self._fetch()
+        return dict.items(self)
+
+    def copy(self):
+        self._fetch()
+        return dict(dict.items(self))
+
+    def __eq__(self, other):
+        self._fetch()
+        if isinstance(other, LossDict):
+            other._fetch()
+        return dict.__eq__(self, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._fetch()
+        return dict.__repr__(self)
+
+    def __reduce__(self):
+        self._fetch()
+        return (dict, (dict(dict.items(self)),))
+
+
 class _FusedLoss(torch.autograd.Function):
     """Autograd bridge: forward launches the fused fwd+bwd kernels, backward hands the stored
     gradient over (scaled in place by ``grad_output`` only when that is not exactly 1)."""
@@ -418,7 +506,8 @@ class YoloDFLQFLoss(nn.Module):
 
     ``lambda_box`` is accepted and, as in the reference, never used (losses.py:88, :275).
     ``forward`` returns ``(total_loss, {"total_loss", "box_loss", "cls_loss"})`` with the dict holding
-    Python floats; they are fetched with ONE device-to-host copy instead of three ``.item()`` syncs.
+    Python floats; they are fetched with ONE asynchronous device-to-host copy that the first read of a value waits for
+    (``LossDict``), instead of three ``.item()`` syncs inside ``forward``.
     ``last_stats`` keeps the 8-float device vector [total, dfl, cls, #matched, ...] of the last call
     for ``training.distributed_setup.reduce_loss_stats``.
 
@@ -472,11 +561,13 @@ class YoloDFLQFLoss(nn.Module):
                                         (self.lambda_box, self.lambda_cls, self.lambda_dfl), self.reg_max, self.tal,
                                         need_grad, holder)
             stats = self.last_stats = holder[0]
-            host = stats.tolist()
-            _raise_on_bad_class(host[7], self.num_classes)
-            if host[6]:                             # the anchors changed under a cached grid hint (the result is still right)
-                grid_hint_rejected(preds.device.index, preds.shape[2])
-            return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2], "dfl_loss": host[3]}
+            nc, dev_index, a = self.num_classes, preds.device.index, preds.shape[2]
+
+            def check_tal(host):
+                if host[6]:                         # the anchors changed under a cached grid hint (the result is still right)
+                    grid_hint_rejected(dev_index, a)
+                _raise_on_bad_class(host[7], nc)
+            return total, LossDict(stats, ("total_loss", "box_loss", "cls_loss", "dfl_loss"), check_tal)
         if n > 0 and sum(counts) == 0:
             # the reference fails here: total_dfl is still the python float 0.0 (losses.py:271-279)
             raise AttributeError("'float' object has no attribute 'detach'")
@@ -485,10 +576,13 @@ class YoloDFLQFLoss(nn.Module):
         total = _FusedLoss.apply(preds, gt, off, max(counts), anchors, strides, self.num_classes,
                                  self.lambda_cls, self.lambda_dfl, self.reg_max, need_grad, holder)
         stats = self.last_stats = holder[0]
-        host = stats.tolist()                           # one D2H copy (the reference does three .item())
-        _raise_on_bad_class(host[7], self.num_classes)
-        _raise_on_stall(host[6], "yb_loss_fwd_bwd")
-        return total, {"total_loss": host[0], "box_loss": host[1], "cls_loss": host[2]}
+        nc = self.num_classes
+
+        def check(host):
+            _raise_on_stall(host[6], "yb_loss_fwd_bwd")
+            _raise_on_bad_class(host[7], nc)
+        # one asynchronous D2H copy, waited for by the first read of a value (the reference does three .item())
+        return total, LossDict(stats, ("total_loss", "box_loss", "cls_loss"), check)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -297,11 +297,18 @@ def test_reference_error_behaviour_is_kept(cuda_device):
     bad = [g.clone() for g in gts]
     k = next(i for i, g in enumerate(bad) if g.shape[0] > 0)
     bad[k][0, 4] = 6.0
+    # (raised by the first read of the loss dict: forward itself no longer waits for the kernels)
     with pytest.raises(RuntimeError, match="class id outside"):
-        crit(preds.to(dev), [g.to(dev) for g in bad], anchors.to(dev), strides.to(dev))
+        crit(preds.to(dev), [g.to(dev) for g in bad], anchors.to(dev), strides.to(dev))[1]["total_loss"]
     bad[k][0, 4] = -1.0
     with pytest.raises(RuntimeError, match="class id outside"):
-        P.YoloDFLQFLoss(num_classes=6, assigner="tal")(preds.to(dev), [g.to(dev) for g in bad], anchors.to(dev), strides.to(dev))
+        dict(P.YoloDFLQFLoss(num_classes=6, assigner="tal")(preds.to(dev), [g.to(dev) for g in bad], anchors.to(dev),
+                                                            strides.to(dev))[1])
+    lazy = crit(preds.to(dev), [g.to(dev) for g in gts], anchors.to(dev), strides.to(dev))[1]
+    assert isinstance(lazy, dict) and set(lazy) == {"total_loss", "box_loss", "cls_loss"} and len(lazy) == 3
+    assert "cls_loss" in lazy and isinstance(lazy["total_loss"], float) and lazy == dict(lazy) and {**lazy} == lazy.copy()
+    import json
+    assert json.loads(json.dumps(lazy)) == dict(lazy.items()) and all(isinstance(v, float) for v in lazy.values())
     loss0, parts0 = crit(preds[:0].to(dev), [], anchors.to(dev), strides.to(dev))
     assert loss0.item() == 0.0 and parts0 == {}
     x = preds.to(dev).requires_grad_(True)
