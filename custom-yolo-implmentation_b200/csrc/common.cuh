@@ -45,6 +45,17 @@ struct NvtxRange {
 };
 #define YB_NVTX(name) ::yb::NvtxRange nvtx_range__(name)
 
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -332,6 +343,22 @@ __device__ __forceinline__ void dep_wait(const unsigned int *counter, unsigned i
     atomicAdd(timeout_flag + 6, (unsigned int)((clock64() - t0) >> 10));
 #endif
 }
+
+// ---- programmatic dependent launch: the next kernel of the stream becomes resident while this one drains ----------
+// A kernel launched through launch_pdl may start before its predecessor in the stream has finished; it must call
+// pdl_wait() before it touches anything the predecessor wrote (or writes anything the predecessor reads).  The
+// predecessor calls pdl_launch_dependents() once all of ITS blocks are allowed to be joined by the successor's -- here
+// at its very start, so the successor's blocks fill the SMs its last wave leaves idle and wait there.
+// A coherent (not .nc) scalar load that the compiler may still schedule freely: for data a PREDECESSOR kernel wrote, read
+// by a kernel launched under programmatic dependent launch.  Its address must depend on something loaded after
+// pdl_wait() -- that dependence, not a memory clobber, is what keeps it behind the wait.
+__device__ __forceinline__ float ld_dependent_f32(const float *p) {
+    float r;
+    asm("ld.global.ca.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

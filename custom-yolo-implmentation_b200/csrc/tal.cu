@@ -44,6 +44,9 @@ int launch_peer_wait(const yb_peer_exchange &px, float *out2, unsigned int *time
 int check_peer(const yb_peer_exchange *px, const char *who);
 constexpr int kPeerSlotsTal = 4;                 // = kPeerSlots of csrc/peer.cu
 
+#ifndef YB_TAL_PDL                    // programmatic dependent launch between the four kernels of the step
+#define YB_TAL_PDL 1
+#endif
 constexpr int kTalThreads = 128;
 constexpr int kTalMaxK = 16;
 constexpr float kEpsCiou = 1e-7f;
@@ -333,6 +336,9 @@ tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const fl
                   float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,
                   int *__restrict__ aslot, int *__restrict__ sel_count, const TalGrid grid,
                   unsigned int *__restrict__ grid_rejected) {
+#if YB_TAL_PDL
+    pdl_launch_dependents();
+#endif
     tal_decode_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt_off, dbox, gext, ctr, akey, aslot,
                            sel_count, grid, grid_rejected);
 }
@@ -911,7 +917,11 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
               unsigned int *__restrict__ next_gt, int have_hint, float *__restrict__ out_stats, const yb_peer_exchange px) {
     __shared__ int s_aq[kTopkWarps][kTopkQueue];           // queue of inside anchors
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool regular = A.grid.n_levels > 0 && __ldg(grid_rejected) == 0u;   // uniform over the launch
+#if YB_TAL_PDL
+    pdl_launch_dependents();
+    pdl_wait();                                            // tal_decode_kernel's boxes, armed words and verdict on the hint
+#endif
+    const bool regular = A.grid.n_levels > 0 && __ldcg(grid_rejected) == 0u;   // uniform over the launch
     // (Measured and not kept: the next round's boxes requested one trip ahead of the filter -- the restructured loop cost
     // more than the hidden L2 latency gained, 180 vs 174 us for the assign phase; asking for the next unit one unit ahead:
     // no change; one batch-wide "selections done" counter for the target scores: +18 us, they then start only when the
@@ -1032,10 +1042,19 @@ __device__ __forceinline__ void vfl_bg_pair(float x0, float x1, f32x2 k2, const 
 
 template <typename T, int VW, bool WRITE_GRAD, bool VFL>
 __global__ void __launch_bounds__(kTalThreads)
-tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *__restrict__ tss_dev,
-               float lambda_cls, VflParams vp, const int *__restrict__ aslot, const float *__restrict__ fgrad,
-               const float *__restrict__ tsc, T *__restrict__ grad, float *__restrict__ part) {
+tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, const float *tss_dev, float lambda_cls,
+               VflParams vp, const int *aslot, const float *fgrad, const float *tsc, T *__restrict__ grad,
+               float *__restrict__ part) {
+    // (tss_dev, aslot, fgrad, tsc are written by the kernel before this one.  Under programmatic dependent launch a load of
+    // "read-only" data may be scheduled above pdl_wait(): the normaliser and the slot map, whose addresses are known up
+    // front, are therefore read with plain L2 loads right after the wait; fgrad and tsc are addressed THROUGH the slot
+    // map, so their loads (common.cuh::ld_dependent_f32) cannot move above it -- and unlike plain loads they may still be
+    // scheduled across the streaming stores of the row loop)
     __shared__ float s_red[kTalThreads / 32];
+#if YB_TAL_PDL
+    pdl_launch_dependents();
+    pdl_wait();                                            // the normaliser, the slot map and the per-slot terms
+#endif
     // kTalClsSplit CTAs share an anchor tile: each takes a slice of the class rows and of the box rows, so the CTAs
     // are short and the grid has several waves (one CTA per tile left a 1.6-wave grid with a long tail)
     constexpr int kTalClsSplit = tal_cls_split(kTalThreads * VW);
@@ -1045,7 +1064,7 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
     const int c_per = (nc + kTalClsSplit - 1) / kTalClsSplit, c_lo = min(split * c_per, nc), c_hi = min(c_lo + c_per, nc);
     constexpr int B_PER = (4 * kRegMax + kTalClsSplit - 1) / kTalClsSplit;
     const int b_lo = min(split * B_PER, 4 * kRegMax), b_hi = min(b_lo + B_PER, 4 * kRegMax);
-    const float inv_tss = 1.f / fmaxf(__ldg(tss_dev), 1.f);
+    const float inv_tss = 1.f / fmaxf(__ldcg(tss_dev), 1.f);
     const float kc = lambda_cls * inv_tss;
     const f32x2 k2 = pack2(kc, kc);
     float acc = 0.f;
@@ -1060,14 +1079,14 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
         float fs[VW];                                      // t / normaliser of the anchor's slot
 #pragma unroll
         for (int v = 0; v < VW; ++v) {
-            const int slot = WRITE_GRAD ? __ldg(aslot + (size_t)n * n_anchors + a0 + v) - 1 : -1;
+            const int slot = WRITE_GRAD ? __ldcg(aslot + (size_t)n * n_anchors + a0 + v) - 1 : -1;
             fo[v] = slot * (4 * kRegMax);
-            fs[v] = slot >= 0 ? __ldg(tsc + slot) * inv_tss : 0.f;
+            fs[v] = slot >= 0 ? ld_dependent_f32(tsc + slot) * inv_tss : 0.f;
         }
         auto box_row = [&](int c) {
             float vals[VW];
 #pragma unroll
-            for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? __ldg(fgrad + fo[v] + c) * fs[v] : 0.f;
+            for (int v = 0; v < VW; ++v) vals[v] = fo[v] >= 0 ? ld_dependent_f32(fgrad + fo[v] + c) * fs[v] : 0.f;
             Group<T, VW>::store(grad + img + (size_t)c * n_anchors, vals);
         };
         const size_t base = img + (size_t)4 * kRegMax * n_anchors;
@@ -1135,19 +1154,21 @@ tal_cls_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, con
 constexpr int kTalFinThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kTalFinThreads)
-tal_finalize_kernel(T *__restrict__ grad, const long long *__restrict__ fcell_off, const float4 *__restrict__ fterm,
-                    const float *__restrict__ tsc, int n_part, int n_slots, const float *__restrict__ part,
-                    const unsigned long long *__restrict__ stat_acc, const float *__restrict__ tss_dev, float lambda_box,
+tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const float4 *fterm, const float *tsc, int n_part,
+                    int n_slots, const float *part, const unsigned long long *stat_acc, const float *tss_dev, float lambda_box,
                     float lambda_cls, float lambda_dfl, int vfl, VflParams vp, double *__restrict__ cta_sums,
                     unsigned int *__restrict__ ticket, float *__restrict__ out_loss) {
     __shared__ double s[3][kTalFinThreads];
     __shared__ bool s_last;
+#if YB_TAL_PDL
+    pdl_wait();                                            // tal_cls_kernel's gradient cells and partial sums
+#endif
     const size_t i = (size_t)blockIdx.x * kTalFinThreads + threadIdx.x;
     float f_cls = 0.f, f_box = 0.f, f_dfl = 0.f;
     if (i < (size_t)n_slots) {
-        const float t = tsc[i];
+        const float t = __ldcg(tsc + i);
         if (t >= 0.f) {                                    // a foreground anchor: the slot's terms, now that t is known
-            const float4 u = fterm[i];                     // 1 - CIoU, DFL term, class logit, its sigmoid
+            const float4 u = __ldcg(fterm + i);            // 1 - CIoU, DFL term, class logit, its sigmoid
             const float z = u.z, sg = u.w;
             f_box = u.x * t;
             f_dfl = u.y * t;
@@ -1161,10 +1182,10 @@ tal_finalize_kernel(T *__restrict__ grad, const long long *__restrict__ fcell_of
             // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / normaliser, over
             // the background value the dense kernel wrote (varifocal: weighted by its own target score, a constant)
             if (grad != nullptr)
-                store_from_float(grad + fcell_off[i], lambda_cls * (sg - t) * (vfl ? t : 1.f) * (1.f / fmaxf(__ldg(tss_dev), 1.f)));
+                store_from_float(grad + __ldcg(fcell_off + i), lambda_cls * (sg - t) * (vfl ? t : 1.f) * (1.f / fmaxf(__ldcg(tss_dev), 1.f)));
         }
     }
-    s[0][threadIdx.x] = (i < (size_t)n_part ? (double)part[i] : 0.0) + (double)f_cls;
+    s[0][threadIdx.x] = (i < (size_t)n_part ? (double)__ldcg(part + i) : 0.0) + (double)f_cls;
     s[1][threadIdx.x] = (double)f_box;
     s[2][threadIdx.x] = (double)f_dfl;
     __syncthreads();
@@ -1242,7 +1263,12 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
         const int gt_ctas = (int)std::min<long long>(((long long)gt_total + kTopkWarps - 1) / kTopkWarps, 148 * YB_TOPK_MINBLOCKS);
         TalResolveArgs R;
         R.tsc = w.tsc; R.aslot = w.aslot; R.out_assigned = out_assigned; R.out_tscore = out_tscore; R.stat_acc = w.stat_acc;
+#if YB_TAL_PDL
+        YB_CUDA(launch_pdl(tal_gt_kernel<T>, dim3(gt_ctas), dim3(32 * kTopkWarps), 0, st, A, R, w.ticket + 3, w.ticket + 1,
+                           (int)(grid.n_levels > 0), out_stats, px));
+#else
         tal_gt_kernel<T><<<gt_ctas, 32 * kTopkWarps, 0, st>>>(A, R, w.ticket + 3, w.ticket + 1, grid.n_levels > 0, out_stats, px);
+#endif
         YB_LAUNCH_CHECK();
     } else {
         YB_CUDA(cudaMemsetAsync(out_stats, 0, sizeof(float) * 8, st));
@@ -1262,9 +1288,15 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
     {
         constexpr int TILE = kTalThreads * VW;
         dim3 grid(((n_anchors + TILE - 1) / TILE) * tal_cls_split(TILE), n_images);
+#if YB_TAL_PDL
+#define YB_TAL_CLS(WG, VF)                                                                                           \
+    YB_CUDA(launch_pdl(tal_cls_kernel<T, VW, WG, VF>, grid, dim3(kTalThreads), 0, st, preds, n_ch, n_anchors, nc, tss_dev, \
+                       p.lambda_cls, vp, w.aslot, w.fgrad, w.tsc, grad, w.part))
+#else
 #define YB_TAL_CLS(WG, VF)                                                                                           \
     tal_cls_kernel<T, VW, WG, VF><<<grid, kTalThreads, 0, st>>>(preds, n_ch, n_anchors, nc, tss_dev, p.lambda_cls, vp, w.aslot, \
                                                                 w.fgrad, w.tsc, grad, w.part)
+#endif
         if (grad != nullptr) { if (p.vfl) YB_TAL_CLS(true, true); else YB_TAL_CLS(true, false); }
         else { if (p.vfl) YB_TAL_CLS(false, true); else YB_TAL_CLS(false, false); }
 #undef YB_TAL_CLS
@@ -1274,9 +1306,15 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
         const int n_part = n_images * w.cls_tiles, n_slots = gt_total * p.topk;
         const int n_max = max(max(n_part, n_slots), 1);
         const int blocks = (n_max + kTalFinThreads - 1) / kTalFinThreads;
+#if YB_TAL_PDL
+        YB_CUDA(launch_pdl(tal_finalize_kernel<T>, dim3(blocks), dim3(kTalFinThreads), 0, st, grad, w.fcell_off, w.fterm, w.tsc,
+                           n_part, n_slots, w.part, w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl, (int)p.vfl, vp,
+                           w.cta_sums, w.ticket, out_loss));
+#else
         tal_finalize_kernel<T><<<blocks, kTalFinThreads, 0, st>>>(grad, w.fcell_off, w.fterm, w.tsc, n_part, n_slots, w.part,
                                                                   w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl,
                                                                   p.vfl, vp, w.cta_sums, w.ticket, out_loss);
+#endif
     }
     YB_LAUNCH_CHECK();
     return YB_OK;
