@@ -44,6 +44,9 @@ int launch_peer_wait(const yb_peer_exchange &px, float *out2, unsigned int *time
 int check_peer(const yb_peer_exchange *px, const char *who);
 constexpr int kPeerSlotsTal = 4;                 // = kPeerSlots of csrc/peer.cu
 
+#ifndef YB_TAL_DECODE_MINBLOCKS      // 0: 6 resident CTAs per SM for fp32 rows, 4 for bf16 rows (measured)
+#define YB_TAL_DECODE_MINBLOCKS 0
+#endif
 #ifndef YB_TAL_PDL                    // programmatic dependent launch between the four kernels of the step
 #define YB_TAL_PDL 1
 #endif
@@ -330,7 +333,7 @@ __device__ __forceinline__ void tal_decode_body(int n, int tile, const T *__rest
 }
 
 template <typename T, int VW>
-__global__ void __launch_bounds__(kTalThreads, VW == 8 ? 4 : 6)
+__global__ void __launch_bounds__(kTalThreads, YB_TAL_DECODE_MINBLOCKS ? YB_TAL_DECODE_MINBLOCKS : (VW == 8 ? 4 : 6))
 tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const float *__restrict__ anchors,
                   const float *__restrict__ strides, const int *__restrict__ gt_off, float4 *__restrict__ dbox,
                   float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,

@@ -28,7 +28,9 @@ out = ["# Round-2 profile summary (B200, sm_100a)", "",
        "| kernel | launches | mean µs | share |", "|---|---|---|---|"]
 for k, v in agg.items():
     m = mean(k)
-    share = "(torch / bench plumbing: host-side tensor prep, autograd scale of the API leg)"
+    share = ("(the forward-only call of the bench's parity check)" if k.startswith('yb::fused_main_kernel<float, 4, 0') else
+             "(the API leg's `loss.backward()`: returns at once, the upstream gradient is 1)" if k.startswith('yb::scale_kernel') else
+             "(torch: host-side tensor preparation of the bench, not on the path)")
     for g, f in groups.items():
         if f(k): share = f"{100 * m / totals[g]:.1f} % of {g}"
     out.append(f"| `{k}` | {len(v)} | {m:.1f} | {share} |")
