@@ -418,9 +418,9 @@ def run_ours(args):
     api_packed_ms = time_steps(lambda: api_step(packed_d), extra_steps)
     api = {"what": "YoloDFLQFLoss.forward + loss.backward, head output and GT resident on the device",
            "gt_list_of_tensors": {"ms_per_step": api_list_ms, "value": world * n / (api_list_ms * 1e-3), "unit": "images/s",
-                                  "note": "the reference's signature: 128 small device tensors packed per step (torch.cat) + loss dict D2H"},
+                                  "note": "the reference's signature: 128 small device tensors per step, gathered by one yb_gather_gt launch from a host-written table; loss dict read every step"},
            "packed_gt": {"ms_per_step": api_packed_ms, "value": world * n / (api_packed_ms * 1e-3), "unit": "images/s",
-                         "note": "PackedGT wire format (data/collate.py::collate_fn_packed) + loss dict D2H"},
+                         "note": "PackedGT wire format (data/collate.py::collate_fn_packed); loss dict read every step"},
            "kernels_only_ms_per_step": ms_per_step}
     del x_leaf
 

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "yb_postprocess_workspace_bytes": (c_size_t, [c_int, c_int]),
     "yb_postprocess": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_double,
                                c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yb_gather_gt": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "yb_xywh2xyxy": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "yb_bbox_iou": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yb_box_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p]),

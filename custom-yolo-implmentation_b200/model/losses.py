@@ -29,13 +29,82 @@ __all__ = ["YoloDFLQFLoss", "bbox_iou", "quality_focal_loss", "distribution_foca
 # ----------------------------------------------------------------------------------------------
 # host logic: GT list -> one concatenated tensor + offsets (no per-image device work, no sync)
 # ----------------------------------------------------------------------------------------------
+_pack_rings = {}        # (device index, words) -> {"bufs": [pinned int32 staging buffers], "events": [...], "next": i}
+
+
+def _pack_gt_gather(gt_boxes_list, device):
+    """Fast path of ``pack_gt``: every entry is an fp32 ``(Mi, >=5)`` tensor on ``device`` with unit column stride (what the
+    reference's loop builds, train_model.py:236).  The host writes one table -- offsets and, per image, (pointer, row pitch,
+    first row, rows) -- into a pinned staging buffer, copies it with one asynchronous H2D copy, and ``yb_gather_gt`` gathers
+    the rows in one launch: no per-image slice / cast / cat on the host.  Returns ``None`` when an entry does not qualify."""
+    n = len(gt_boxes_list)
+    words = (n + 1) + (n + 1) % 2 + 6 * n                 # offsets (padded to 8 bytes) + 24-byte table entries, in int32 words
+    ptrs, pitch, first, count = [], [], [], []
+    total = 0
+    f32, idx = torch.float32, device.index
+    for g in gt_boxes_list:                                # (kept lean: this loop IS the host cost of the list interface)
+        if not isinstance(g, torch.Tensor) or g.dtype is not f32 or not g.is_cuda or g.get_device() != idx:
+            return None
+        sh = g.shape
+        m = sh[0] if len(sh) == 2 else -1
+        if m <= 0 or sh[1] == 0:
+            if g.numel() != 0:
+                return None
+            ptrs.append(0); pitch.append(5); first.append(total); count.append(0)
+            continue
+        st = g.stride()
+        if sh[1] < 5 or st[1] != 1:
+            return None
+        ptrs.append(g.data_ptr()); pitch.append(st[0]); first.append(total); count.append(m)
+        total += m
+    key = (device.index, words)
+    ring = _pack_rings.get(key)
+    if ring is None:
+        ring = _pack_rings[key] = {"bufs": [torch.empty(words, dtype=torch.int32).pin_memory() for _ in range(4)],
+                                   "events": [None] * 4, "next": 0}
+    i = ring["next"]
+    ring["next"] = (i + 1) % 4
+    if ring["events"][i] is not None:
+        ring["events"][i].synchronize()                     # the copy that last used this staging buffer (long done)
+    stage = ring["bufs"][i]
+    host = stage.numpy()
+    t0 = (n + 1) + (n + 1) % 2
+    host[:n] = first
+    host[n] = total
+    table = host[t0:].reshape(n, 6)
+    table[:, :2].view("uint64")[:, 0] = ptrs
+    table[:, 2] = pitch
+    table[:, 3] = first
+    table[:, 4] = count
+    table[:, 5] = 0
+    dev_buf = stage.to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    ring["events"][i] = ev
+    gt = torch.empty(total, 5, dtype=torch.float32, device=device)
+    if total:
+        with torch.cuda.device(device):
+            rc = _cabi.lib().yb_gather_gt(dev_buf.data_ptr() + 4 * t0, n, _cabi.ptr(gt), _cabi.stream_ptr(device))
+        _cabi.check(rc, "yb_gather_gt")
+    return gt, dev_buf[: n + 1], count
+
+
 def pack_gt(gt_boxes_list: Sequence[torch.Tensor], device) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
     """``list[(Mi, 5)]`` -> ``(gt (sum Mi, 5) fp32, offsets (N+1,) int32, counts)`` on ``device``.
 
     The counts come from tensor *shapes*, so nothing here waits for the GPU.  Boxes are cast to
     fp32 as the reference does (``gt_boxes[:, 0:4].to(preds.dtype)`` with preds already float,
     losses.py:208); the class column is truncated toward zero inside the kernel (``.long()``, :257).
+    fp32 tensors already on ``device`` -- the reference's own calling convention -- are gathered by one kernel launch
+    (``_pack_gt_gather``); anything else (CPU tensors, other dtypes, odd strides) goes through torch ops.
     """
+    device = torch.device(device)
+    if device.type == "cuda" and len(gt_boxes_list) > 0:
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        fast = _pack_gt_gather(gt_boxes_list, device)
+        if fast is not None:
+            return fast
     counts = []
     parts = []
     for i, g in enumerate(gt_boxes_list):

@@ -107,6 +107,19 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
 #define YB_LOSS_FORCE_PROBE 4u   /* run the probe role (grid_hint) whatever gmax says: the exactness tests exercise it on small inputs */
 #define YB_LOSS_SPLIT_LAUNCH 2u  /* box, class and match roles as three launches instead of one (profiling the roles apart) */
 
+/* The reference's GT argument -- a Python list of N (Mi, 5) fp32 device tensors (src/training/train_model.py:236, read at
+ * src/model/losses.py:206-208) -- gathered into the (sum Mi, 5) buffer yb_loss_fwd_bwd / yb_tal_assign take, by ONE launch
+ * driven by a device table the caller fills with one small copy (no per-image slicing or concatenation on the host).
+ *   table_dev  n_images entries: source pointer, row pitch in floats (>= 5), first output row, number of rows */
+typedef struct {
+    const void *rows;       /* device pointer to the image's (Mi, >=5) fp32 rows; may be NULL when n_rows == 0 */
+    int32_t row_pitch;      /* floats between consecutive rows */
+    int32_t first_row;      /* where the image's rows start in out_gt (= gt_offsets[b]) */
+    int32_t n_rows;         /* Mi */
+    int32_t reserved;
+} yb_gt_source;
+int yb_gather_gt(const yb_gt_source *table_dev, int n_images, float *out_gt, void *stream);
+
 /* grad *= *scale (device scalar), in place; returns without touching memory when *scale == 1.
  * Used by the autograd bridge for `loss.backward()` under a GradScaler
  * (src/training/train_model.py:247-253). */

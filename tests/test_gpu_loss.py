@@ -433,6 +433,29 @@ def test_tile_pruning_never_changes_the_result(n, imgsz, gmax, dtype, seed, cuda
             assert torch.equal(a, b), it
 
 
+def test_gt_list_is_gathered_by_one_launch(cuda_device):
+    """The reference's GT argument is a list of small device tensors (train_model.py:236).  fp32 tensors on the device are
+    gathered by ONE yb_gather_gt launch driven by a host-written table; anything else takes the torch path.  Same wire
+    format either way, including empty images, extra columns and row-strided views."""
+    from custom_yolo_implmentation_b200 import _cabi
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    wide = torch.rand(9, 8, generator=g).to(dev)
+    gts = [torch.rand(3, 5, generator=g).to(dev), torch.zeros(0, 5, device=dev), wide[:, :6], wide[::2, 1:7],
+           torch.rand(1, 5, generator=g).to(dev), torch.zeros(0, 5, device=dev)]
+    before = _cabi.launch_count
+    gt, off, counts = P.pack_gt(gts, dev)
+    assert _cabi.launch_count - before == 1 and counts == [3, 0, 9, 5, 1, 0]
+    assert off.dtype == torch.int32 and off.tolist() == [0, 3, 3, 12, 17, 18, 18]
+    assert torch.equal(gt, torch.cat([t[:, :5] for t in gts if t.numel()], 0))
+    # not the device's fp32 tensors: CPU and fp64 entries go through torch, same result
+    before = _cabi.launch_count
+    gt2, off2, counts2 = P.pack_gt([t.cpu() for t in gts[:3]] + [t.double() for t in gts[3:]], dev)
+    assert _cabi.launch_count == before and counts2 == counts and torch.equal(off2, off) and torch.equal(gt2, gt)
+    gt3, off3, counts3 = P.pack_gt([torch.zeros(0, 5, device=dev)] * 2, dev)
+    assert gt3.shape == (0, 5) and off3.tolist() == [0, 0, 0] and counts3 == [0, 0]
+
+
 def test_fp16_head_output_goes_through_float_like_the_reference(cuda_device):
     """autocast(float16) head outputs: the module converts with .float() as the reference does (losses.py:142)
     and autograd hands an fp16 gradient back."""
