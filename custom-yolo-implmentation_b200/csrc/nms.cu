@@ -230,12 +230,16 @@ __device__ __forceinline__ unsigned resolve_block(const float4 &bx, bool alive, 
         }
     }
     unsigned kept = 0;
+    if (!__any_sync(0xffffffffu, (sup | by) != 0u)) {
+        kept = alive_mask;                                 // no pair of the block exceeds the threshold (the usual case)
+    } else {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const unsigned s_r = __shfl_sync(0xffffffffu, sup, r) | __ballot_sync(0xffffffffu, (by >> r) & 1u);
-        if ((alive_mask >> r) & 1u) {
-            kept |= 1u << r;
-            alive_mask &= ~s_r;
+        for (int r = 0; r < 32; ++r) {
+            const unsigned s_r = __shfl_sync(0xffffffffu, sup, r) | __ballot_sync(0xffffffffu, (by >> r) & 1u);
+            if ((alive_mask >> r) & 1u) {
+                kept |= 1u << r;
+                alive_mask &= ~s_r;
+            }
         }
     }
     while (__popc(kept) > room) kept &= ~(0x80000000u >> __clz(kept));   // drop the lowest-ranked keeps
