@@ -496,6 +496,7 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
         int thr = -1;                                      // bit pattern of the k-th best metric once k winners exist
         int nq = 0;                                        // queue fill (warp-uniform)
 
+        int thr_seed = -1;                                 // k-th best metric of the seed cells (below), once known
         // evaluate up to 64 anchors, two per lane (a < 0: none), in ascending order lane-major within each of the two
         auto evaluate2 = [&](const int (&a)[2]) {
             float4 pb[2];
@@ -511,7 +512,9 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
                     ov = overlap_fast(pb[u], gb, at_g, area_g);
                     m = __float_as_int(metric_fast(lg[u], ov, alpha, beta));
                 }
-                unsigned keep = __ballot_sync(0xffffffffu, m > thr);
+                // (an exact metric strictly below the seed's k-th best cannot be selected either: it never enters the list,
+                // so the list is mostly built by cheap insertions instead of REDUX rounds)
+                unsigned keep = __ballot_sync(0xffffffffu, (m > thr) & (m >= thr_seed));
                 if (keep == 0u) continue;                  // warp-uniform
                 if (__popc(keep) > 6) {
                     int vm[2] = {lane < topk ? win.m : kEmptyKey, ((keep >> lane) & 1u) ? m : kEmptyKey};
@@ -541,7 +544,6 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
         // k-th best so far (or strictly below a k-th best known from a seed of central cells) can never be selected; only the
         // survivors, compacted into the queue in ascending order, pay for the CIoU, the class logit and the merge.
         const bool can_bound = alpha >= 0.f && beta >= 0.f;
-        int thr_seed = -1;
         auto survives = [&](int a) {                       // a >= 0
             if (!can_bound) return true;
             const int ub = __float_as_int(metric_bound(iou_fast(box_row[a], gb, area_g), beta));
