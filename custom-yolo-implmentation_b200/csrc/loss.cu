@@ -72,6 +72,9 @@ namespace yb {
 #ifndef YB_MATCH_WHOLE_SECTORS
 #define YB_MATCH_WHOLE_SECTORS 1
 #endif
+#ifndef YB_BF16_SHORT_LOG             // bf16 head outputs: degree-2 log polynomial in the class role
+#define YB_BF16_SHORT_LOG 1
+#endif
 #ifndef YB_LOSS_PROBE                 // 0: ignore the grid hint (measurement aid)
 #define YB_LOSS_PROBE 1
 #endif
@@ -801,6 +804,10 @@ __device__ __forceinline__ float fast_lg2(float x) {         // MUFU.LG2
     return r;
 }
 
+// SHORT: bf16 head outputs carry 8 bits of mantissa and are held to 1e-2 relative; their log q on the polynomial branch
+// uses a degree-2 R(f) (max relative error 1.2e-4, fitted offline) instead of the degree-5 one: three packed FMAs per
+// two cells less in a kernel that is bound by instruction issue at bf16.
+template <bool SHORT>
 __device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 &acc2, float &g0, float &g1) {
     const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), mtwo = pack2(-2.f, -2.f);
     float a0, a1;
@@ -814,12 +821,19 @@ __device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 
     unpack2(q, q0, q1);
     // log q, polynomial branch: f = q - 1 is exact for q in [0.5, 1]
     const f32x2 f = add2(q, mone);
-    f32x2 r = pack2(0.3410167098045349f, 0.3410167098045349f);
-    r = fma2(r, f, pack2(-0.08926734328269958f, -0.08926734328269958f));
-    r = fma2(r, f, pack2(0.21280372142791748f, 0.21280372142791748f));
-    r = fma2(r, f, pack2(-0.249073788523674f, -0.249073788523674f));
-    r = fma2(r, f, pack2(0.33335742354393005f, 0.33335742354393005f));
-    r = fma2(r, f, pack2(-0.49999991059303284f, -0.49999991059303284f));
+    f32x2 r;
+    if (SHORT) {
+        r = pack2(-0.37099915742874146f, -0.37099915742874146f);
+        r = fma2(r, f, pack2(0.3176640272140503f, 0.3176640272140503f));
+        r = fma2(r, f, pack2(-0.5004022717475891f, -0.5004022717475891f));
+    } else {
+        r = pack2(0.3410167098045349f, 0.3410167098045349f);
+        r = fma2(r, f, pack2(-0.08926734328269958f, -0.08926734328269958f));
+        r = fma2(r, f, pack2(0.21280372142791748f, 0.21280372142791748f));
+        r = fma2(r, f, pack2(-0.249073788523674f, -0.249073788523674f));
+        r = fma2(r, f, pack2(0.33335742354393005f, 0.33335742354393005f));
+        r = fma2(r, f, pack2(-0.49999991059303284f, -0.49999991059303284f));
+    }
     float lp0, lp1;
     unpack2(fma2(mul2(f, f), r, f), lp0, lp1);                                // log(q) = f + f^2 R(f)
     // ... and the MUFU branch for the rest: skipped by the warps whose lanes all hold background logits (the usual case);
@@ -843,13 +857,14 @@ __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, f32x2 k2, 
     if constexpr (VW == 1) {
         float g1;
         f32x2 pair = pack2(0.f, 0.f);
-        qfl_bg_pair(row.get(0), row.get(0), k2, pair, g[0], g1);
+        qfl_bg_pair<YB_BF16_SHORT_LOG && sizeof(T) == 2>(row.get(0), row.get(0), k2, pair, g[0], g1);
         float lo, hi;
         unpack2(pair, lo, hi);
         acc2 = add2(acc2, pack2(lo, 0.f));                 // the second lane is a copy: count it once
     } else {
 #pragma unroll
-        for (int v = 0; v < VW; v += 2) qfl_bg_pair(row.get(v), row.get(v + 1), k2, acc2, g[v], g[v + 1]);
+        for (int v = 0; v < VW; v += 2)
+            qfl_bg_pair<YB_BF16_SHORT_LOG && sizeof(T) == 2>(row.get(v), row.get(v + 1), k2, acc2, g[v], g[v + 1]);
     }
 }
 
