@@ -129,3 +129,23 @@ def test_packed_gt_host_and_collate():
     assert images.shape == (3, 3, 4, 4) and len(targets) == 3 and packed.counts == [2, 0, 3]
     images2, targets2 = collate_fn(batch)
     assert torch.equal(images, images2) and targets2[2]["boxes"] is gts[2]
+
+
+def test_grid_hint_is_pure_host_logic():
+    """build_grid_hint describes the reference's pyramid of grids (make_anchors, model_utils.py:60-70) or returns None;
+    exact=False also takes anchors built in bf16 (159.5 rounds to 160), which only the nearest-centre path's
+    probe role may use -- it needs a cell NEAR each box centre, nothing more."""
+    from custom_yolo_implmentation_b200.model.losses import build_grid_hint
+    anchors, strides = syn.anchor_grid(1280)
+    hint = build_grid_hint(anchors, strides)
+    assert hint is not None and hint.n_levels == 3
+    assert list(hint.w)[:3] == [160, 80, 40] and list(hint.start)[:3] == [0, 25600, 32000]
+    assert list(hint.stride)[:3] == [8.0, 16.0, 32.0] and hint.x0[0] == 0.5 and hint.y0[2] == 0.5
+    ab, sb = anchors.bfloat16().float(), strides.bfloat16().float()
+    assert build_grid_hint(ab, sb) is None                          # not bit-for-bit a grid any more
+    near = build_grid_hint(ab, sb, exact=False)
+    assert near is not None and list(near.w)[:3] == [160, 80, 40]
+    perm = torch.randperm(anchors.shape[1], generator=torch.Generator().manual_seed(0))
+    assert build_grid_hint(anchors[:, perm], strides[:, perm]) is None
+    assert build_grid_hint(anchors[:, perm], strides[:, perm], exact=False) is None
+    assert build_grid_hint(anchors[:, :7], strides[:, :9]) is None  # mismatched lengths
