@@ -431,6 +431,9 @@ __device__ __forceinline__ FgFetch fg_fetch(const T *__restrict__ img, const T *
     return f;
 }
 
+#ifndef YB_TAL_FILTER                 // candidate filter: 0 off, 1 IoU-only bound, 2 IoU and the anchor's own class score
+#define YB_TAL_FILTER 2
+#endif
 #ifndef YB_TAL_SPIN_NS                // a waiting warp sleeps between polls: it must not take issue slots from the working ones
 #define YB_TAL_SPIN_NS 100
 #endif
@@ -544,10 +547,17 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
         // Cheap filter in front of the evaluation: a candidate whose plain IoU already bounds its metric at or below the
         // k-th best so far (or strictly below a k-th best known from a seed of central cells) can never be selected; only the
         // survivors, compacted into the queue in ascending order, pay for the CIoU, the class logit and the merge.
-        const bool can_bound = alpha >= 0.f && beta >= 0.f;
+        const bool can_bound = YB_TAL_FILTER && beta >= 0.f;
         auto survives = [&](int a) {                       // a >= 0
             if (!can_bound) return true;
+#if YB_TAL_FILTER == 2
+            // the metric itself with the plain IoU in place of the overlap: the class score is the anchor's own (the head's
+            // scores sit around 0.01, a bound of 1 would be ten times too loose), the CIoU penalties only lower the overlap
+            // and the metric does not fall as the overlap grows (beta >= 0)
+            const int ub = __float_as_int(metric_fast(load_as_float(cls_row + a), iou_fast(box_row[a], gb, area_g), alpha, beta) * 1.0001f);
+#else
             const int ub = __float_as_int(metric_bound(iou_fast(box_row[a], gb, area_g), beta));
+#endif
             return ub > thr && ub >= thr_seed;
         };
 
