@@ -373,7 +373,7 @@ __device__ __forceinline__ int gt_image(const int *__restrict__ gt_off, int n_im
 }
 
 constexpr int kTopkWarps = 4;
-constexpr int kTopkQueue = 96;                   // inside-anchor queue per warp: evaluated 64 at a time
+constexpr int kTopkQueue = 128;                  // inside-anchor queue per warp: evaluated 64 at a time (< 64 waiting + 64 new)
 constexpr int kEmptyKey = (int)0x80000000;       // below every metric bit pattern (metrics are >= 0)
 
 struct TopK {                                    // lane r: the r-th best so far (r < topk), or empty
@@ -548,17 +548,16 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
         // k-th best so far (or strictly below a k-th best known from a seed of central cells) can never be selected; only the
         // survivors, compacted into the queue in ascending order, pay for the CIoU, the class logit and the merge.
         const bool can_bound = YB_TAL_FILTER && beta >= 0.f;
-        auto survives = [&](int a) {                       // a >= 0
-            if (!can_bound) return true;
+        auto survives = [&](const float4 &pb, float logit) -> bool {     // the candidate's decoded box and class logit
 #if YB_TAL_FILTER == 2
             // the metric itself with the plain IoU in place of the overlap: the class score is the anchor's own (the head's
             // scores sit around 0.01, a bound of 1 would be ten times too loose), the CIoU penalties only lower the overlap
             // and the metric does not fall as the overlap grows (beta >= 0)
-            const int ub = __float_as_int(metric_fast(load_as_float(cls_row + a), iou_fast(box_row[a], gb, area_g), alpha, beta) * 1.0001f);
+            const int ub = __float_as_int(metric_fast(logit, iou_fast(pb, gb, area_g), alpha, beta) * 1.0001f);
 #else
-            const int ub = __float_as_int(metric_bound(iou_fast(box_row[a], gb, area_g), beta));
+            const int ub = __float_as_int(metric_bound(iou_fast(pb, gb, area_g), beta));
 #endif
-            return ub > thr && ub >= thr_seed;
+            return (ub > thr) & (ub >= thr_seed);
         };
 
         // lane l works out the rectangle of level l (the others fetch it by shuffle)
@@ -625,8 +624,10 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
         int gb0 = -32;                                                                      // group form
         unsigned groups = 0u;
         for (bool more = true; more;) {
-            int a = -1;
-            bool keep = false;
+            // up to two rounds of 32 candidates per trip (grid form), so that two boxes and two class logits per lane are
+            // in flight together: the filter is a chain of dependent L2 / DRAM round trips otherwise (10 us per GT)
+            int a[2] = {-1, -1};
+            bool in[2] = {false, false};
             if (regular) {
                 while (c0 >= cells) {                      // warp-uniform: on to the next level with cells inside the GT
                     if (++lvl >= n_levels) { more = false; break; }
@@ -638,12 +639,15 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
                     c0 = 0;
                 }
                 if (more) {
-                    const int c = c0 + lane;
-                    int row = (int)(((float)c + 0.5f) * inv_nx), col = c - row * nx;
-                    if (col < 0) { --row; col += nx; } else if (col >= nx) { ++row; col -= nx; }
-                    a = lst + (iy0 + row) * lw + ix0 + col;
-                    keep = c < cells && survives(a);
-                    c0 += 32;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = c0 + 32 * u + lane;
+                        int row = (int)(((float)c + 0.5f) * inv_nx), col = c - row * nx;
+                        if (col < 0) { --row; col += nx; } else if (col >= nx) { ++row; col -= nx; }
+                        a[u] = lst + (iy0 + row) * lw + ix0 + col;
+                        in[u] = c < cells;
+                    }
+                    c0 += 64;
                 }
             } else {
                 while (groups == 0u) {                     // warp-uniform: lane l looks at the centre extent of group gb0 + l
@@ -654,29 +658,39 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
                     groups = __ballot_sync(0xffffffffu, gb.x < ext.z && gb.z > ext.x && gb.y < ext.w && gb.w > ext.y);
                 }
                 if (more) {
-                    a = ((gb0 + (__ffs(groups) - 1)) << 5) + lane;
+                    a[0] = ((gb0 + (__ffs(groups) - 1)) << 5) + lane;
                     groups &= groups - 1;
-                    bool in = false;
-                    if (a < n_anchors) {
-                        const float2 c = ctr[a];
-                        in = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
+                    if (a[0] < n_anchors) {
+                        const float2 c = ctr[a[0]];
+                        in[0] = fminf(fminf(c.x - gb.x, c.y - gb.y), fminf(gb.z - c.x, gb.w - c.y)) > kEpsIn;
                     }
-                    keep = in && survives(a);
                 }
             }
-            // append the kept anchors in lane order; evaluate 64 at a time (and what is left once the enumeration ends)
-            const unsigned mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a;
-            nq += __popc(mask);
+            // the cheap filter on both rounds (loads first), then append the kept anchors in round / lane order
+            float4 fb[2];
+            float fl[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (in[u] && can_bound) { fb[u] = box_row[a[u]]; fl[u] = YB_TAL_FILTER == 2 ? load_as_float(cls_row + a[u]) : 0.f; }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                bool keep = in[u];
+                if (keep && can_bound) keep = survives(fb[u], fl[u]);
+                const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                if (keep) aq[nq + __popc(mask & ((1u << lane) - 1u))] = a[u];
+                nq += __popc(mask);
+            }
             __syncwarp();
+            // evaluate 64 at a time (and what is left once the enumeration ends)
             while (nq >= 64 || (!more && nq > 0)) {        // warp-uniform
                 const int cnt = min(nq, 64);
                 const int a2[2] = {lane < cnt ? aq[lane] : -1, lane + 32 < cnt ? aq[lane + 32] : -1};
                 evaluate2(a2);
-                const int rest = nq - cnt;                 // < 32
-                const int keep_a = lane < rest ? aq[64 + lane] : 0;
+                const int rest = nq - cnt;                 // < 64
+                const int k0 = lane < rest ? aq[64 + lane] : 0, k1 = lane + 32 < rest ? aq[96 + lane] : 0;
                 __syncwarp();
-                if (lane < rest) aq[lane] = keep_a;
+                if (lane < rest) aq[lane] = k0;
+                if (lane + 32 < rest) aq[32 + lane] = k1;
                 nq = rest;
                 __syncwarp();
             }
