@@ -612,7 +612,9 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
                     const unsigned eq = __ballot_sync(0xffffffffu, v == kth);
                     if (lane == __ffs(eq) - 1) v = kEmptyKey;
                 }
-                thr_seed = kth == kEmptyKey ? -1 : kth;
+                // (a hair below the k-th best seed: the seeds are evaluated by another copy of the metric arithmetic than the
+                // candidates, and the last bit of the two may differ -- the seed itself must never fall below its own mark)
+                thr_seed = kth == kEmptyKey ? -1 : __float_as_int(__int_as_float(kth) * 0.9999f);
             }
         }
         // One loop for both forms of the enumeration, so that the evaluation below exists ONCE in the kernel (one copy of
