@@ -434,6 +434,9 @@ __device__ __forceinline__ FgFetch fg_fetch(const T *__restrict__ img, const T *
 #ifndef YB_TAL_FILTER                 // candidate filter: 0 off, 1 IoU-only bound, 2 IoU and the anchor's own class score
 #define YB_TAL_FILTER 2
 #endif
+#ifndef YB_TAL_FENCE_ALL
+#define YB_TAL_FENCE_ALL 0
+#endif
 #ifndef YB_TAL_SPIN_NS                // a waiting warp sleeps between polls: it must not take issue slots from the working ones
 #define YB_TAL_SPIN_NS 100
 #endif
@@ -706,9 +709,19 @@ __device__ __forceinline__ void tal_gt_body(const TalGtArgs<T> &A, int g, int n,
             atomicMax(akey + (size_t)n * n_anchors + win.a,
                       ((unsigned long long)__float_as_uint(win.o) << 32) | (unsigned int)(~(unsigned int)g_local));
         }
+#if YB_TAL_FENCE_ALL
         __threadfence();                                   // the list before the word that announces it
         __syncwarp();
         if (lane == 0) *reinterpret_cast<volatile int *>(sel_count + g) = (n << 8) | n_sel;
+#else
+        // the list before the word that announces it: the lanes' stores are ordered before lane 0's fence by the warp
+        // barrier, and the fence is cumulative
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            *reinterpret_cast<volatile int *>(sel_count + g) = (n << 8) | n_sel;
+        }
+#endif
     }
 }
 
