@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libyolo_boxpath.so")
 ABI_VERSION = 5
 YB_F32, YB_BF16 = 0, 1
-YB_LOSS_NO_PRUNE, YB_LOSS_SPLIT_LAUNCH, YB_LOSS_FORCE_PROBE = 1, 2, 4
+YB_LOSS_NO_PRUNE, YB_LOSS_SPLIT_LAUNCH, YB_LOSS_FORCE_PROBE, YB_LOSS_WS_CLEAN = 1, 2, 4, 8
+YB_LOSS_NO_PDL = 16
 
 _lib = None
 _lock = threading.Lock()
@@ -84,7 +85,10 @@ EXPORTS = tuple(_SIGNATURES)
 class TalParams(ctypes.Structure):
     """``yb_tal_params`` of include/yolo_boxpath.h."""
     _fields_ = [("topk", c_int), ("alpha", c_float), ("beta", c_float), ("lambda_box", c_float), ("lambda_cls", c_float),
-                ("lambda_dfl", c_float), ("vfl", c_int), ("vfl_alpha", c_float), ("vfl_gamma", c_float)]
+                ("lambda_dfl", c_float), ("vfl", c_int), ("vfl_alpha", c_float), ("vfl_gamma", c_float), ("flags", ctypes.c_uint)]
+
+
+YB_TAL_WS_CLEAN = 1
 
 
 TAL_MAX_LEVELS = 8

@@ -78,6 +78,9 @@ namespace yb {
 #ifndef YB_LOSS_PROBE                 // 0: ignore the grid hint (measurement aid)
 #define YB_LOSS_PROBE 1
 #endif
+#ifndef YB_LOSS_PDL                   // 1: the launch may become resident behind its predecessor's last wave (programmatic dependent launch)
+#define YB_LOSS_PDL 1
+#endif
 #ifndef YB_PROBE_MIN_GT               // the probe role runs when an image can hold more GTs than this (gmax)
 #define YB_PROBE_MIN_GT 128
 #endif
@@ -159,7 +162,7 @@ __device__ __forceinline__ void assign_body(int n, int tile, const T *__restrict
     const size_t img = (size_t)n * n_ch * n_anchors;
     const int g_begin = gt_off[n];
     const int m_img = gt_off[n + 1] - g_begin;
-    if (tile == 0)                                         // GT -> image table for match_kernel
+    if (tile == 0 && gt_img != nullptr)                    // GT -> image table for match_kernel (not needed by the match role)
         for (int m = threadIdx.x; m < m_img; m += kAssignThreads) gt_img[g_begin + m] = n;
 
     if (a0 < n_anchors) {
@@ -561,12 +564,6 @@ __device__ __forceinline__ GtTerms gt_terms(const AnchorTerms &a, float z_cls, f
 
 constexpr int kMatchThreads = 128;
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 // One HALF-warp per GT; all 32 lanes of a warp call this together (the two halves may serve different images).
 // `m` is the GT's index within image n (of m_img > 0 GTs starting at row g_begin); an idle half (live == false) walks
 // through the same shuffles on the image's last GT and writes nothing.
@@ -941,6 +938,11 @@ cls_loss_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, int nc, fl
 // they run UNDER the streaming roles -- 250 / 244 / 240 us per step for a lag of 1 / 4 / all machine-loads of CTAs: the
 // scattered sector reads and writes of the match role cost the same DRAM time wherever they run, and more when they
 // break into the streams' open rows.
+// zeros over `n` 64-bit words by one CTA of kAssignThreads threads (the arrays of the workspace are 64-byte aligned and padded)
+__device__ __forceinline__ void wipe_words(unsigned long long *p, size_t n) {
+    for (size_t i = threadIdx.x; i < n; i += kAssignThreads) p[i] = 0ull;
+}
+
 struct FusedPlan {
     int n_tiles, coarse, skew;     // coarse < 0: pruning (and the coarse-first order) off
     int match_ctas;                // match CTAs per image (0: no GT in the whole batch); < 0: match_kernel is launched separately
@@ -948,6 +950,7 @@ struct FusedPlan {
     int whole_sectors;             // gradient rows may be patched with whole 32-byte sectors (match_gt)
     int probe_ctas;                // CTAs of the probe role at the head of the grid (0: no grid hint)
     int gt_total;
+    int self_clean;                // YB_LOSS_WS_CLEAN: the reducer leaves every workspace word the launch touched at zero again
 };
 #ifndef YB_FUSED_MINBLOCKS           // measured on B200: 6 resident CTAs/SM is best for fp32 rows, 5 for bf16 rows
 #define YB_FUSED_MINBLOCKS 0
@@ -962,6 +965,10 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
                   unsigned int *flags, unsigned int *done, int *__restrict__ out_idx, float *__restrict__ out_iou,
                   float *__restrict__ out_loss, float *__restrict__ out_per_image) {
     static_assert(kAssignThreads == kClsThreads && kAssignThreads == kMatchThreads, "roles share one block shape");
+#if YB_LOSS_PDL
+    pdl_launch_dependents();
+    pdl_wait();
+#endif
     constexpr int ROLES = 1 + YB_CLS_CSPLIT;
     const int n_tiles = plan.n_tiles, skew = plan.skew;
     const bool prune = plan.coarse >= 0;                   // coarse < 0: YB_LOSS_NO_PRUNE (exactness tests)
@@ -979,6 +986,10 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         if (id < plan.probe_ctas) {                        // probe role: the grid's first CTAs, 8 GTs each
             probe_gts<T>(preds, gt, id * (kAssignThreads / 16), plan.gt_total, gt_off, n_images, n_ch, n_anchors, anchors, strides,
                          grid, bound);
+            if (plan.self_clean) {                         // the reducer may only wipe `bound` once nobody writes it any more
+                __syncthreads();
+                if (threadIdx.x == 0) dep_signal(flags + 4);
+            }
             return;
         }
         id -= plan.probe_ctas;
@@ -1007,8 +1018,20 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     if (reducer) {
         for (int b = threadIdx.x; b < n_images; b += kAssignThreads)
             dep_wait(done + b, tile_ctas + (unsigned int)plan.match_ctas, flags + 3);
+        // (self-cleaning) `bound` may only be wiped once no probe CTA can write it any more
+        if (plan.self_clean && plan.probe_ctas > 0 && threadIdx.x == 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3);
         __syncthreads();
         final_reduce(n_images, n_anchors, gt_off, acc, flags, lambda_cls, lambda_dfl, out_loss, out_per_image);
+        if (plan.self_clean) {
+            // Every other CTA of the launch that touches the workspace has counted itself off: put back the zeros the next
+            // call expects (the words this launch used, no more), so that the step needs no memset node in front of it.
+            __syncthreads();                               // ... and final_reduce has read the sums and the flags
+            wipe_words(reinterpret_cast<unsigned long long *>(flags), 8);
+            wipe_words(reinterpret_cast<unsigned long long *>(done), ((size_t)n_images + 1) / 2);
+            wipe_words(acc, (size_t)n_images * kAccPerImage);
+            wipe_words(best, (size_t)plan.gt_total);
+            if (plan.probe_ctas > 0) wipe_words(reinterpret_cast<unsigned long long *>(bound), ((size_t)plan.gt_total + 1) / 2);
+        }
         return;
     }
     int image;
@@ -1040,7 +1063,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         }
         if (role == 0)
             assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best,
-                               plan.probe_ctas > 0 ? bound : nullptr, gt_img, WRITE_GRAD ? grad : nullptr, prune);
+                               plan.probe_ctas > 0 ? bound : nullptr, chained ? nullptr : gt_img, WRITE_GRAD ? grad : nullptr, prune);
         else
             cls_body<T, VW, WRITE_GRAD>(image, tile, n_tiles, role - 1, YB_CLS_CSPLIT, preds, n_ch, n_anchors, nc, k_cls, grad,
                                         acc, flags);
@@ -1095,7 +1118,10 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
     // whole-sector patches of the gradient rows need 32-byte aligned rows (match_gt)
     const int whole_sectors = YB_MATCH_WHOLE_SECTORS && grad != nullptr && n_anchors % (32 / (int)sizeof(T)) == 0 &&
                               (reinterpret_cast<uintptr_t>(grad) & 31u) == 0;
-    YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
+    // YB_LOSS_WS_CLEAN: the caller vouches that the workspace is all zero -- as this entry point leaves it when it is called
+    // with the flag (fused launch only): no memset node in front of the step
+    const bool ws_clean = (flags & YB_LOSS_WS_CLEAN) && !(flags & YB_LOSS_SPLIT_LAUNCH) && !YB_MATCH_SEPARATE;
+    if (!ws_clean) YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
     if (int rc = stage_mark(stage_events, 0, st)) return rc;
     if (!(flags & YB_LOSS_SPLIT_LAUNCH)) {
         // Block order: first the last quarter of the tiles of every image -- the coarse pyramid levels (P4 + P5
@@ -1117,6 +1143,7 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         if (YB_MATCH_SEPARATE) plan.match_ctas = -1;
         plan.whole_sectors = whole_sectors;
         plan.gt_total = gt_total;
+        plan.self_clean = ws_clean ? 1 : 0;
         // the probe role pays once the coarse tiles would otherwise scan more than one chunk of GTs per image (measured:
         // cfg5, <= 300 GT per image, 188 -> 170 us; cfg2, <= 100 GT per image, 241 -> 252 us with it)
         plan.probe_ctas = (YB_LOSS_PROBE && grid.n_levels > 0 && gt_total > 0 && !(flags & YB_LOSS_NO_PRUNE) &&
@@ -1125,14 +1152,21 @@ static int launch_loss(const T *preds, int n_images, int nc, int n_anchors, cons
         const long long blocks = (long long)n_tiles * (1 + cls_split) * n_images + plan.skew + plan.probe_ctas +
                                  (plan.match_ctas < 0 ? 0 : (long long)plan.match_ctas * n_images + 1);
         YB_REQUIRE(blocks < (1ll << 31), "yb_loss_fwd_bwd: too many tiles for one launch");
-        if (grad != nullptr)
-            fused_main_kernel<T, VW, true><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, plan, grid, anchors, strides, gt, gt_off, w.best, w.bound, w.gt_img, k_cls, k_dfl_num,
-                lambda_cls, lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
-        else
-            fused_main_kernel<T, VW, false><<<(unsigned)blocks, kAssignThreads, 0, st>>>(
-                preds, n_images, n_ch, n_anchors, nc, plan, grid, anchors, strides, gt, gt_off, w.best, w.bound, w.gt_img, k_cls, k_dfl_num,
-                lambda_cls, lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
+        // a programmatic dependent launch: the grid may become resident while its predecessor in the stream drains (it waits
+        // at its top for that kernel's completion); YB_LOSS_NO_PDL: a plain launch
+        auto launch = [&](auto kernel) -> cudaError_t {
+            if (YB_LOSS_PDL && !(flags & YB_LOSS_NO_PDL))
+                return launch_pdl(kernel, dim3((unsigned)blocks), dim3(kAssignThreads), 0, st, preds, n_images, n_ch, n_anchors, nc, plan,
+                                  grid, anchors, strides, gt, gt_off, w.best, w.bound, w.gt_img, k_cls, k_dfl_num, lambda_cls, lambda_dfl,
+                                  grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss, out_per_image);
+            kernel<<<(unsigned)blocks, kAssignThreads, 0, st>>>(preds, n_images, n_ch, n_anchors, nc, plan, grid, anchors, strides, gt,
+                                                                 gt_off, w.best, w.bound, w.gt_img, k_cls, k_dfl_num, lambda_cls,
+                                                                 lambda_dfl, grad, w.acc, w.ticket, w.done, out_idx, out_iou, out_loss,
+                                                                 out_per_image);
+            return cudaSuccess;
+        };
+        if (grad != nullptr) YB_CUDA(launch(fused_main_kernel<T, VW, true>));
+        else YB_CUDA(launch(fused_main_kernel<T, VW, false>));
         YB_LAUNCH_CHECK();
         if (int rc = stage_mark(stage_events, 1, st)) return rc;
         if (plan.match_ctas < 0) {

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const T *__restrict__ score, size_t score_stride, int nc, int n_anchors, float conf,
                 const int *__restrict__ filter, int n_filter, int *__restrict__ count, int *__restrict__ cls_out,
                 unsigned long long *__restrict__ keys, int a_pad) {
+    pdl_launch_dependents();                               // the class-parallel kernel's CTAs move in behind this grid's last wave
     const int n = blockIdx.y;
     const int a0 = (blockIdx.x * kScanThreads + threadIdx.x) * VW;
     const int lane = threadIdx.x & 31;
@@ -246,7 +247,7 @@ __device__ __forceinline__ unsigned resolve_block(const float4 &bx, bool alive, 
     return kept;
 }
 
-__device__ __forceinline__ int cls_n_of(const int *__restrict__ cls, int n, int n_anchors, int a) {
+__device__ __forceinline__ int cls_n_of(const int *cls, int n, int n_anchors, int a) {
     return cls[(size_t)n * n_anchors + a];
 }
 
@@ -271,8 +272,9 @@ __device__ __forceinline__ void emit_row(float *__restrict__ out_rows, int *__re
 // MULTI (multi_label): a key's low word is anchor * nc + class instead of the anchor.
 template <bool REG, bool MULTI>
 __global__ void __launch_bounds__(kSortThreads, 1)
-nms_sweep_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *__restrict__ count,
-                 const int *__restrict__ mode, const int *__restrict__ cls, unsigned long long *__restrict__ keys, int a_pad,
+nms_sweep_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *count,
+                 const int *mode, const int *cls, unsigned long long *keys, int a_pad,   // written by the predecessor kernels: no
+                 // `const __restrict__` (a read-only load may be scheduled above pdl_wait())
                  float4 *__restrict__ sbox, int sbox_stride, float thr, int max_det, int agnostic, float *__restrict__ out_rows,
                  int *__restrict__ out_count, int *__restrict__ out_anchor) {
     __shared__ float4 s_row[32];
@@ -282,6 +284,7 @@ nms_sweep_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int 
 
     const int n = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();                                            // launched under programmatic dependent launch behind the kernel that wrote `mode`
     if (!MULTI && mode[n] != 0) return;                    // finished by the class-parallel kernel
     const int n_cand = min(min(count[n], a_pad), kMaxNms);
     auto anchor_of = [&](unsigned id) { return MULTI ? (int)(id / (unsigned)nc) : (int)id; };
@@ -420,8 +423,9 @@ constexpr int kSelBits = 11;
 
 
 __global__ void __launch_bounds__(kClassThreads, 1)
-nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *__restrict__ count,
-                 const int *__restrict__ cls, const unsigned long long *__restrict__ keys, int a_pad,
+nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int n_anchors, const int *count,
+                 const int *cls, const unsigned long long *keys, int a_pad,   // nms_scan_kernel's output: no `const __restrict__`
+                 // (a read-only load may be scheduled above pdl_wait())
                  unsigned long long *__restrict__ keys2, unsigned char *__restrict__ alive_g,
                  unsigned *__restrict__ tick, unsigned *__restrict__ range, float thr, int max_det,
                  int *__restrict__ mode, float *__restrict__ out_rows, int *__restrict__ out_count,
@@ -442,6 +446,8 @@ nms_class_kernel(const float *__restrict__ pred, size_t box_stride, int nc, int 
     // gridDim.x CTAs share an image: CTA `part` owns the classes c with c % gridDim.x == part
     const int img = blockIdx.y, part = blockIdx.x, n_part = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();                                            // nms_scan_kernel's counts, classes and keys
     const int n = count[img];
     if (n == 0) {
         if (tid == 0 && part == 0) { out_count[img] = 0; mode[img] = 1; }
@@ -972,23 +978,23 @@ static int run_nms(const NmsInput &in, int score_dtype, int sigmoid, int n_image
         YB_CUDA(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         // CTAs per image: enough to put every SM to work on small batches
         const int split = n_images >= 96 ? 1 : (n_images >= 48 ? 2 : (n_images >= 24 ? 4 : 8));
-        nms_class_kernel<<<dim3(split, n_images), kClassThreads, csmem, st>>>(
-            in.box, in.box_stride, nc, n_anchors, w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det,
-            w.mode, out_rows, out_count, out_anchor);
+        YB_CUDA(launch_pdl(nms_class_kernel, dim3(split, n_images), dim3(kClassThreads), csmem, st, in.box, in.box_stride, nc, n_anchors,
+                           w.count, w.cls, w.keys, w.a_pad, w.keys2, w.alive_g, w.tick, w.range, thr, max_det, w.mode, out_rows,
+                           out_count, out_anchor));
         YB_LAUNCH_CHECK();
     }
     // generic path for whatever the class-parallel kernel left (mode == 0)
     const size_t smem = sizeof(unsigned long long) * (size_t)min(w.a_pad, kSortTile);
     if (n_anchors <= kRegCols * kSortThreads) {
         YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_sweep_kernel<true, false><<<n_images, kSortThreads, smem, st>>>(in.box, in.box_stride, nc, n_anchors, w.count, w.mode, w.cls,
-                                                                            w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
-                                                                            agnostic, out_rows, out_count, out_anchor);
+        YB_CUDA(launch_pdl(nms_sweep_kernel<true, false>, dim3(n_images), dim3(kSortThreads), smem, st, in.box, in.box_stride, nc, n_anchors,
+                           w.count, w.mode, w.cls, w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det, agnostic, out_rows, out_count,
+                           out_anchor));
     } else {
         YB_CUDA(cudaFuncSetAttribute(nms_sweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_sweep_kernel<false, false><<<n_images, kSortThreads, smem, st>>>(in.box, in.box_stride, nc, n_anchors, w.count, w.mode, w.cls,
-                                                                             w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det,
-                                                                             agnostic, out_rows, out_count, out_anchor);
+        YB_CUDA(launch_pdl(nms_sweep_kernel<false, false>, dim3(n_images), dim3(kSortThreads), smem, st, in.box, in.box_stride, nc, n_anchors,
+                           w.count, w.mode, w.cls, w.keys, w.a_pad, w.sbox, n_anchors, thr, max_det, agnostic, out_rows, out_count,
+                           out_anchor));
     }
     YB_LAUNCH_CHECK();
     return YB_OK;

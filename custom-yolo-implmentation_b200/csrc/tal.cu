@@ -341,6 +341,8 @@ tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const fl
                   unsigned int *__restrict__ grid_rejected) {
 #if YB_TAL_PDL
     pdl_launch_dependents();
+    pdl_wait();                                            // behind the previous step's tal_finalize_kernel (YB_TAL_WS_CLEAN): its wiped counters,
+                                                           // and the workspace arrays that step's kernels still read
 #endif
     tal_decode_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt_off, dbox, gext, ctr, akey, aslot,
                            sel_count, grid, grid_rejected);
@@ -1200,47 +1202,53 @@ constexpr int kTalFinThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kTalFinThreads)
 tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const float4 *fterm, const float *tsc, int n_part,
-                    int n_slots, const float *part, const unsigned long long *stat_acc, const float *tss_dev, float lambda_box,
+                    int n_slots, const float *part, unsigned long long *stat_acc, const float *tss_dev, float lambda_box,
                     float lambda_cls, float lambda_dfl, int vfl, VflParams vp, double *__restrict__ cta_sums,
-                    unsigned int *__restrict__ ticket, float *__restrict__ out_loss) {
-    __shared__ double s[3][kTalFinThreads];
+                    unsigned int *__restrict__ ticket, int wipe, float *__restrict__ out_loss) {
+    __shared__ double s[3][kTalFinThreads / 32];
     __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #if YB_TAL_PDL
+    pdl_launch_dependents();                               // the next step's tal_decode_kernel may move in behind this grid
     pdl_wait();                                            // tal_cls_kernel's gradient cells and partial sums
 #endif
     const size_t i = (size_t)blockIdx.x * kTalFinThreads + threadIdx.x;
     float f_cls = 0.f, f_box = 0.f, f_dfl = 0.f;
-    if (i < (size_t)n_slots) {
-        const float t = __ldcg(tsc + i);
-        if (t >= 0.f) {                                    // a foreground anchor: the slot's terms, now that t is known
-            const float4 u = __ldcg(fterm + i);            // 1 - CIoU, DFL term, class logit, its sigmoid
-            const float z = u.z, sg = u.w;
-            f_box = u.x * t;
-            f_dfl = u.y * t;
-            if (vfl) {
-                // the dense pass counted this cell as background (w_bg * softplus); it is t * BCE(x, t) instead
-                const float sp = fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
-                f_cls = t * (sp - t * z) - vfl_bg_weight(sg, vp) * sp;
-            } else {
-                f_cls = -t * z;                            // BCE(x, t) - BCE(x, 0)
-            }
-            // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / normaliser, over
-            // the background value the dense kernel wrote (varifocal: weighted by its own target score, a constant)
-            if (grad != nullptr)
-                store_from_float(grad + __ldcg(fcell_off + i), lambda_cls * (sg - t) * (vfl ? t : 1.f) * (1.f / fmaxf(__ldcg(tss_dev), 1.f)));
+    // every load of the slot is issued at once (one round trip, not a chain of three behind the t >= 0 test)
+    const bool slot = i < (size_t)n_slots;
+    const float t = slot ? __ldcg(tsc + i) : -1.f;
+    const float4 u = slot ? __ldcg(fterm + i) : make_float4(0.f, 0.f, 0.f, 0.f);   // 1 - CIoU, DFL term, class logit, its sigmoid
+    const long long cell = slot ? __ldcg(fcell_off + i) : 0ll;
+    const float p_i = i < (size_t)n_part ? __ldcg(part + i) : 0.f;
+    const float inv_tss = 1.f / fmaxf(__ldcg(tss_dev), 1.f);
+    if (t >= 0.f) {                                        // a foreground anchor: the slot's terms, now that t is known
+        const float z = u.z, sg = u.w;
+        f_box = u.x * t;
+        f_dfl = u.y * t;
+        if (vfl) {
+            // the dense pass counted this cell as background (w_bg * softplus); it is t * BCE(x, t) instead
+            const float sp = fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+            f_cls = t * (sp - t * z) - vfl_bg_weight(sg, vp) * sp;
+        } else {
+            f_cls = -t * z;                                // BCE(x, t) - BCE(x, 0)
         }
+        // the anchor's one positive class cell: BCE(x, t) = softplus(x) - t x  ->  (sigmoid(x) - t) / normaliser, over
+        // the background value the dense kernel wrote (varifocal: weighted by its own target score, a constant)
+        if (grad != nullptr) store_from_float(grad + cell, lambda_cls * (sg - t) * (vfl ? t : 1.f) * inv_tss);
     }
-    s[0][threadIdx.x] = (i < (size_t)n_part ? (double)__ldcg(part + i) : 0.0) + (double)f_cls;
-    s[1][threadIdx.x] = (double)f_box;
-    s[2][threadIdx.x] = (double)f_dfl;
+    // fixed-shape trees: butterfly inside each warp, then the warps in index order
+    double v[3] = {(double)p_i + (double)f_cls, (double)f_box, (double)f_dfl};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = warp_sum_d(v[k]);
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) s[k][warp] = v[k];
     __syncthreads();
-    for (int o = kTalFinThreads / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-            for (int k = 0; k < 3; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 3; ++k) cta_sums[(size_t)blockIdx.x * 3 + k] = s[k][0];
+        for (int k = 0; k < 3; ++k) {
+            double a = 0.0;
+            for (int w = 0; w < kTalFinThreads / 32; ++w) a += s[k][w];
+            cta_sums[(size_t)blockIdx.x * 3 + k] = a;
+        }
         __threadfence();
         s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
@@ -1250,13 +1258,14 @@ tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const floa
     double acc[3] = {0.0, 0.0, 0.0};
     for (int b = threadIdx.x; b < (int)gridDim.x; b += kTalFinThreads)
         for (int k = 0; k < 3; ++k) acc[k] += __ldcg(cta_sums + (size_t)b * 3 + k);
-    for (int k = 0; k < 3; ++k) s[k][threadIdx.x] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] = warp_sum_d(acc[k]);
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) s[k][warp] = acc[k];
     __syncthreads();
-    for (int o = kTalFinThreads / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-            for (int k = 0; k < 3; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
-        __syncthreads();
-    }
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 3; ++k)
+            for (int w = 1; w < kTalFinThreads / 32; ++w) s[k][0] += s[k][w];
     if (threadIdx.x == 0) {
         const double tss = fmax((double)tss_dev[0], 1.0);
         const float l_cls = (float)(s[0][0] / tss), l_box = (float)(s[1][0] / tss), l_dfl = (float)(s[2][0] / tss);
@@ -1268,8 +1277,17 @@ tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const floa
         out_loss[5] = (float)__ldcg(stat_acc + 2 * kTalStatAcc);   // foreground anchors (counted by tal_fg_kernel)
         out_loss[6] = (float)ticket[3];                    // 1: yb_tal_assign was given a grid hint that does not describe the anchors
         out_loss[7] = (float)ticket[2];                    // GT rows whose class id lies outside [0, nc) (counted by yb_tal_assign)
-        *ticket = 0u;                                      // re-armed for the next yb_tal_loss on this workspace
     }
+    // ticket[0] is re-armed for a second yb_tal_loss on the same assignment.  YB_TAL_WS_CLEAN: the step's last reader of the
+    // counters puts ALL their zeros back, so that a workspace that started out zeroed stays valid for the next
+    // yb_tal_assign without a memset node.
+    __syncthreads();
+    if (!wipe) {
+        if (threadIdx.x == 0) *ticket = 0u;
+        return;
+    }
+    for (int w = threadIdx.x; w < 8 + 2 * kTalStatAcc + 1; w += kTalFinThreads)
+        (w < 8 ? reinterpret_cast<unsigned long long *>(ticket) + w : stat_acc + (w - 8))[0] = 0ull;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1288,7 +1306,9 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
                              int32_t *out_assigned, float *out_tscore, const TalWorkspace &w, cudaStream_t st) {
     const int n_ch = 4 * kRegMax + nc;
     // the counters (tickets, statistics, per-GT unit counts) here; the per-anchor arrays by tal_decode_kernel
-    YB_CUDA(cudaMemsetAsync(w.ticket, 0, gt_total == 0 ? w.zero_bytes : w.small_zero_bytes, st));
+    // (YB_TAL_WS_CLEAN: the caller vouches that the counters are zero, as the previous step's tal_finalize_kernel left them)
+    if (gt_total == 0) YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.zero_bytes, st));
+    else if (!(p.flags & YB_TAL_WS_CLEAN)) YB_CUDA(cudaMemsetAsync(w.ticket, 0, w.small_zero_bytes, st));
     if (out_assigned) YB_CUDA(cudaMemsetAsync(out_assigned, 0xff, sizeof(int32_t) * (size_t)n_images * n_anchors, st));
     if (out_tscore) YB_CUDA(cudaMemsetAsync(out_tscore, 0, sizeof(float) * (size_t)n_images * n_anchors, st));
     if (gt_total > 0) {
@@ -1301,8 +1321,13 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
         A.dbox = w.dbox; A.gext = w.gext; A.ctr = w.ctr; A.grid = grid;
         A.sel = w.sel; A.sel_count = w.sel_count; A.akey = w.akey; A.fterm = w.fterm; A.fgrad = w.fgrad; A.fcell_off = w.fcell_off;
         A.bad_cls = w.ticket + 2;
+#if YB_TAL_PDL
+        YB_CUDA(launch_pdl(tal_decode_kernel<T, VW>, dim3(n_tiles, n_images), dim3(kTalThreads), 0, st, preds, n_ch, n_anchors, anchors,
+                           strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3));
+#else
         tal_decode_kernel<T, VW><<<dim3(n_tiles, n_images), kTalThreads, 0, st>>>(
             preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3);
+#endif
         YB_LAUNCH_CHECK();
         // warps draw GTs from a counter
         const int gt_ctas = (int)std::min<long long>(((long long)gt_total + kTopkWarps - 1) / kTopkWarps, 148 * YB_TOPK_MINBLOCKS);
@@ -1354,11 +1379,12 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
 #if YB_TAL_PDL
         YB_CUDA(launch_pdl(tal_finalize_kernel<T>, dim3(blocks), dim3(kTalFinThreads), 0, st, grad, w.fcell_off, w.fterm, w.tsc,
                            n_part, n_slots, w.part, w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl, (int)p.vfl, vp,
-                           w.cta_sums, w.ticket, out_loss));
+                           w.cta_sums, w.ticket, (int)((p.flags & YB_TAL_WS_CLEAN) != 0), out_loss));
 #else
         tal_finalize_kernel<T><<<blocks, kTalFinThreads, 0, st>>>(grad, w.fcell_off, w.fterm, w.tsc, n_part, n_slots, w.part,
                                                                   w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl,
-                                                                  p.vfl, vp, w.cta_sums, w.ticket, out_loss);
+                                                                  p.vfl, vp, w.cta_sums, w.ticket,
+                                                                  (int)((p.flags & YB_TAL_WS_CLEAN) != 0), out_loss);
 #endif
     }
     YB_LAUNCH_CHECK();

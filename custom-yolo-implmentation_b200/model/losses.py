@@ -185,6 +185,21 @@ def _stream_workspace(n_bytes: int, device) -> torch.Tensor:
     return buf
 
 
+_clean_ws_cache = {}
+
+
+def _clean_workspace(n_bytes: int, device, tag: str) -> torch.Tensor:
+    """A scratch buffer per (device, stream, entry point) that the kernels keep ZEROED between calls: allocated as zeros
+    (on the current stream, so ordered before its first use) and handed only to an entry point that wipes what it used
+    before its last kernel ends (``YB_LOSS_WS_CLEAN`` / ``YB_TAL_WS_CLEAN``) -- the step then needs no memset node."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _clean_ws_cache.get(key)
+    if buf is None or buf.numel() < n_bytes:
+        buf = torch.zeros(max(n_bytes, 1 << 16), dtype=torch.uint8, device=device)
+        _clean_ws_cache[key] = buf
+    return buf
+
+
 def _as_offsets(gt: torch.Tensor, gt_offsets: torch.Tensor, n: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
     """The GT wire format as the kernels read it: ``gt (sum Mi, 5)`` fp32 and ``offsets (N+1,)`` int32, contiguous, on
     ``device``.  A CPU (pinned) ``PackedGT`` straight from ``collate_fn_packed`` is moved, not dereferenced as a device
@@ -241,7 +256,11 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
     gt, gt_offsets = _as_offsets(gt, gt_offsets, n, dev)
     gt_total = int(gt.shape[0])
     lib = _cabi.lib()
-    ws = _stream_workspace(lib.yb_loss_workspace_bytes(n, a, gt_total, dt), dev)
+    if int(flags) & _cabi.YB_LOSS_SPLIT_LAUNCH:                 # the profiling split leaves its counters behind
+        ws = _stream_workspace(lib.yb_loss_workspace_bytes(n, a, gt_total, dt), dev)
+    else:
+        ws = _clean_workspace(lib.yb_loss_workspace_bytes(n, a, gt_total, dt), dev, "loss")
+        flags = int(flags) | _cabi.YB_LOSS_WS_CLEAN
     ev = None
     if stage_events is not None:
         import ctypes
@@ -292,6 +311,7 @@ def _raise_on_stall(flag: float, who: str):
     # a consumer CTA of the fused launch gave up waiting for its producers (csrc/common.cuh::dep_wait): the block
     # dispatch order the launch relies on did not hold -- fail loudly, the loss of that call is NaN
     if flag:
+        _clean_ws_cache.clear()                     # what the stalled launch left in its workspace is unknown
         raise RuntimeError(f"{who}: an in-kernel dependency timed out (blocks were not dispatched in index order)")
 
 
@@ -503,7 +523,7 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     gt, gt_offsets = _as_offsets(gt, gt_offsets, n, dev)
     gt_total = int(gt.shape[0])
     lib = _cabi.lib()
-    ws = _stream_workspace(lib.yb_tal_workspace_bytes(n, a, gt_total, dt, topk), dev)
+    ws = _clean_workspace(lib.yb_tal_workspace_bytes(n, a, gt_total, dt, topk), dev, "tal")
     stats = torch.empty(8, dtype=torch.float32, device=dev)
     asg = tsc = None
     if want_trace:
@@ -518,7 +538,7 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     px = exchange.next_step() if (exchange is not None and sync_normalizer) else None
     px_ref = ctypes.byref(px) if px is not None else None
     params = _cabi.TalParams(int(topk), float(alpha), float(beta), float(lambda_box), float(lambda_cls), float(lambda_dfl),
-                             int(cls_loss == "vfl"), float(vfl_alpha), float(vfl_gamma))
+                             int(cls_loss == "vfl"), float(vfl_alpha), float(vfl_gamma), _cabi.YB_TAL_WS_CLEAN)
     with torch.cuda.device(dev):
         rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
                                _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params),

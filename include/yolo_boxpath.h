@@ -106,6 +106,12 @@ int yb_loss_fwd_bwd(const void *preds, int dtype, int n_images, int nc, int reg_
 #define YB_LOSS_NO_PRUNE 1u      /* box role scans every (GT, tile) pair: the exactness tests compare with and without */
 #define YB_LOSS_FORCE_PROBE 4u   /* run the probe role (grid_hint) whatever gmax says: the exactness tests exercise it on small inputs */
 #define YB_LOSS_SPLIT_LAUNCH 2u  /* box, class and match roles as three launches instead of one (profiling the roles apart) */
+#define YB_LOSS_NO_PDL 16u       /* plain launch instead of a programmatic dependent launch */
+#define YB_LOSS_WS_CLEAN 8u      /* the caller vouches that the whole workspace is zero: no memset node in front of the launch.
+                                    A call made with this flag leaves the workspace all zero again when its launch completes
+                                    (its last CTA wipes the words the launch used), so a buffer that was zeroed once and is
+                                    only ever handed to yb_loss_fwd_bwd with this flag stays valid from step to step, whatever
+                                    the batch shape.  Not after a call that reported a stalled dependency (out_loss[6]). */
 
 /* The reference's GT argument -- a Python list of N (Mi, 5) fp32 device tensors (src/training/train_model.py:236, read at
  * src/model/losses.py:206-208) -- gathered into the (sum Mi, 5) buffer yb_loss_fwd_bwd / yb_tal_assign take, by ONE launch
@@ -160,6 +166,10 @@ typedef struct {
     int vfl;                                    /* 0: plain BCE class term; 1: varifocal weighting (north_star "VFL-BCE"): */
     float vfl_alpha, vfl_gamma;                 /*    weight = vfl_alpha * sigmoid(x)^vfl_gamma on background cells
                                                       (differentiated), = the target score on the positive cell */
+    unsigned flags;                             /* 0, or YB_TAL_WS_CLEAN: the caller vouches that the first 2 KB of the workspace are
+                                                   zero -- true for a buffer that was zeroed once and has only seen complete
+                                                   yb_tal_assign + yb_tal_loss pairs since (yb_tal_loss's last kernel wipes the
+                                                   step's counters): no memset node in front of the step */
 } yb_tal_params;                                /* host struct, read during the call; pass the SAME values to both calls */
 
 /* Optional hint: the anchors as a pyramid of regular grids, what the reference's make_anchors produces
@@ -176,6 +186,7 @@ typedef struct {
  *   yb_peer_mailbox_alloc -> own mailbox;  yb_peer_mailbox_export -> 64-byte CUDA IPC handle to send to the other ranks;
  *   yb_peer_mailbox_open(handle of rank r) -> mailbox[r] as mapped in this process;  mailbox[rank] = the own one.
  * `seq` must be the same on all ranks for one step, start at 1 and increase by 1 per step. */
+#define YB_TAL_WS_CLEAN 1u
 #define YB_PEER_MAX_WORLD 16
 #define YB_PEER_HANDLE_BYTES 64
 typedef struct {
