@@ -804,20 +804,23 @@ __device__ __forceinline__ float fast_lg2(float x) {         // MUFU.LG2
 // SHORT: bf16 head outputs carry 8 bits of mantissa and are held to 1e-2 relative; their log q on the polynomial branch
 // uses a degree-2 R(f) (max relative error 1.2e-4, fitted offline) instead of the degree-5 one: three packed FMAs per
 // two cells less in a kernel that is bound by instruction issue at bf16.
+struct QflPair {                                              // two cells between the two halves of qfl_bg_group
+    f32x2 p, q, lq;
+};
+
 template <bool SHORT>
-__device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 &acc2, float &g0, float &g1) {
-    const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f), mtwo = pack2(-2.f, -2.f);
+__device__ __forceinline__ QflPair qfl_bg_front(float x0, float x1) {
+    const f32x2 one = pack2(1.f, 1.f), mone = pack2(-1.f, -1.f);
     float a0, a1;
     unpack2(mul2(pack2(x0, x1), pack2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
     const f32x2 u = add2(pack2(fast_ex2(a0), fast_ex2(a1)), one);            // 1 + exp(-x)
     float u0, u1;
     unpack2(u, u0, u1);
-    const f32x2 p = pack2(fast_rcp(u0), fast_rcp(u1));
-    const f32x2 q = fma2(p, mone, one);                                       // fl(1 - p), as the reference
-    float q0, q1;
-    unpack2(q, q0, q1);
+    QflPair c;
+    c.p = pack2(fast_rcp(u0), fast_rcp(u1));
+    c.q = fma2(c.p, mone, one);                                               // fl(1 - p), as the reference
     // log q, polynomial branch: f = q - 1 is exact for q in [0.5, 1]
-    const f32x2 f = add2(q, mone);
+    const f32x2 f = add2(c.q, mone);
     f32x2 r;
     if (SHORT) {
         r = pack2(-0.37099915742874146f, -0.37099915742874146f);
@@ -831,37 +834,69 @@ __device__ __forceinline__ void qfl_bg_pair(float x0, float x1, f32x2 k2, f32x2 
         r = fma2(r, f, pack2(0.33335742354393005f, 0.33335742354393005f));
         r = fma2(r, f, pack2(-0.49999991059303284f, -0.49999991059303284f));
     }
-    float lp0, lp1;
-    unpack2(fma2(mul2(f, f), r, f), lp0, lp1);                                // log(q) = f + f^2 R(f)
-    // ... and the MUFU branch for the rest: skipped by the warps whose lanes all hold background logits (the usual case);
-    // when taken it costs two MUFU.LG2 and a handful of selects, not a function call
-    if (!(fminf(q0, q1) >= kFastQ)) {
-        const float lm0 = fast_lg2(q0 + kEpsLog) * 0.6931471805599453f, lm1 = fast_lg2(q1 + kEpsLog) * 0.6931471805599453f;
-        lp0 = q0 >= kFastQ ? lp0 : lm0;
-        lp1 = q1 >= kFastQ ? lp1 : lm1;
-    }
-    const f32x2 lq = pack2(lp0, lp1);
-    const f32x2 p2 = mul2(p, p);
-    acc2 = fma2(p2, lq, acc2);
-    const f32x2 g = mul2(mul2(p2, k2), fma2(mul2(q, mtwo), lq, p));           // k p^2 (p - 2 q log q)
-    unpack2(g, g0, g1);
-    g0 = q0 == 0.f ? 0.f : g0;                                                // sigmoid'(x) = p q = 0: no gradient (NaN stays NaN)
-    g1 = q1 == 0.f ? 0.f : g1;
+    c.lq = fma2(mul2(f, f), r, f);                                            // log(q) = f + f^2 R(f)
+    return c;
 }
 
+// the cells the polynomial does not cover (q < 0.7071: logit above -0.88): MUFU.LG2; and q == 0 (logit above ~16.6), where
+// sigmoid'(x) = p q = 0: the reference's gradient vanishes while its loss term p^2 log(1e-12) stays -- that term is added
+// here and the cell's p zeroed, which zeroes both of its later products (NaN stays NaN: no comparison below holds for it)
+__device__ __forceinline__ void qfl_bg_fix(QflPair &c, f32x2 &acc2) {
+    float q0, q1, l0, l1, p0, p1;
+    unpack2(c.q, q0, q1);
+    unpack2(c.lq, l0, l1);
+    unpack2(c.p, p0, p1);
+    const float lm0 = fast_lg2(q0 + kEpsLog) * 0.6931471805599453f, lm1 = fast_lg2(q1 + kEpsLog) * 0.6931471805599453f;
+    l0 = q0 >= kFastQ ? l0 : lm0;
+    l1 = q1 >= kFastQ ? l1 : lm1;
+    const float t0 = q0 == 0.f ? p0 * p0 * lm0 : 0.f, t1 = q1 == 0.f ? p1 * p1 * lm1 : 0.f;
+    acc2 = add2(acc2, pack2(t0, t1));
+    p0 = q0 == 0.f ? 0.f : p0;
+    p1 = q1 == 0.f ? 0.f : p1;
+    c.lq = pack2(l0, l1);
+    c.p = pack2(p0, p1);
+}
+
+__device__ __forceinline__ void qfl_bg_back(const QflPair &c, f32x2 k2, f32x2 &acc2, float &g0, float &g1) {
+    const f32x2 mtwo = pack2(-2.f, -2.f);
+    const f32x2 p2 = mul2(c.p, c.p);
+    acc2 = fma2(p2, c.lq, acc2);
+    unpack2(mul2(mul2(p2, k2), fma2(mul2(c.q, mtwo), c.lq, c.p)), g0, g1);    // k p^2 (p - 2 q log q)
+}
+
+// One row of a thread's anchors.  The polynomial serves every cell first; ONE test per row (the smallest q of the row, a
+// per-lane branch the background never takes) sends the row through qfl_bg_fix -- per pair of cells that test cost a
+// compare, a branch with its convergence barrier and two selects for q == 0, a fifth of the class role's instructions.
 template <typename T, int VW>
 __device__ __forceinline__ void qfl_bg_group(const Group<T, VW> &row, f32x2 k2, f32x2 &acc2, float (&g)[VW]) {
+    constexpr bool SHORT = YB_BF16_SHORT_LOG && sizeof(T) == 2;
     if constexpr (VW == 1) {
         float g1;
         f32x2 pair = pack2(0.f, 0.f);
-        qfl_bg_pair<YB_BF16_SHORT_LOG && sizeof(T) == 2>(row.get(0), row.get(0), k2, pair, g[0], g1);
+        QflPair c = qfl_bg_front<SHORT>(row.get(0), row.get(0));
+        float q0, q1;
+        unpack2(c.q, q0, q1);
+        if (!(q0 >= kFastQ)) qfl_bg_fix(c, pair);
+        qfl_bg_back(c, k2, pair, g[0], g1);
         float lo, hi;
         unpack2(pair, lo, hi);
         acc2 = add2(acc2, pack2(lo, 0.f));                 // the second lane is a copy: count it once
     } else {
+        QflPair c[VW / 2];
+        float qmin = __int_as_float(0x7f800000);
 #pragma unroll
-        for (int v = 0; v < VW; v += 2)
-            qfl_bg_pair<YB_BF16_SHORT_LOG && sizeof(T) == 2>(row.get(v), row.get(v + 1), k2, acc2, g[v], g[v + 1]);
+        for (int v = 0; v < VW; v += 2) {
+            c[v / 2] = qfl_bg_front<SHORT>(row.get(v), row.get(v + 1));
+            float q0, q1;
+            unpack2(c[v / 2].q, q0, q1);
+            qmin = fminf(qmin, fminf(q0, q1));             // (a NaN q drops out of the minimum: its cell stays NaN either way)
+        }
+        if (qmin < kFastQ) {
+#pragma unroll
+            for (int v = 0; v < VW; v += 2) qfl_bg_fix(c[v / 2], acc2);
+        }
+#pragma unroll
+        for (int v = 0; v < VW; v += 2) qfl_bg_back(c[v / 2], k2, acc2, g[v], g[v + 1]);
     }
 }
 
@@ -952,6 +987,24 @@ struct FusedPlan {
     int gt_total;
     int self_clean;                // YB_LOSS_WS_CLEAN: the reducer leaves every workspace word the launch touched at zero again
 };
+#ifdef YB_LOSS_TRACE                 // measurement aid (scratch/trace_loss.py): when and where every CTA of the launch ran
+__device__ ulonglong4 g_trace[1 << 16];
+struct TraceScope {
+    unsigned long long t0;
+    int role;
+    __device__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+    __device__ TraceScope() : t0(now()), role(-1) {}
+    __device__ ~TraceScope() {
+        unsigned int sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        if (threadIdx.x == 0 && blockIdx.x < (1u << 16)) g_trace[blockIdx.x] = make_ulonglong4(t0, now(), sm, (unsigned long long)(role + 1));
+    }
+};
+extern "C" int yb_trace_dump(void *dst) { return (int)cudaMemcpyFromSymbol(dst, g_trace, sizeof(g_trace)); }
+#define YB_TRACE_ROLE(r) trace_scope.role = (r)
+#else
+#define YB_TRACE_ROLE(r)
+#endif
 #ifndef YB_FUSED_MINBLOCKS           // measured on B200: 6 resident CTAs/SM is best for fp32 rows, 5 for bf16 rows
 #define YB_FUSED_MINBLOCKS 0
 #endif
@@ -969,6 +1022,9 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     pdl_launch_dependents();
     pdl_wait();
 #endif
+#ifdef YB_LOSS_TRACE
+    TraceScope trace_scope;
+#endif
     constexpr int ROLES = 1 + YB_CLS_CSPLIT;
     const int n_tiles = plan.n_tiles, skew = plan.skew;
     const bool prune = plan.coarse >= 0;                   // coarse < 0: YB_LOSS_NO_PRUNE (exactness tests)
@@ -984,6 +1040,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     {
         int id = blockIdx.x;
         if (id < plan.probe_ctas) {                        // probe role: the grid's first CTAs, 8 GTs each
+            YB_TRACE_ROLE(10);
             probe_gts<T>(preds, gt, id * (kAssignThreads / 16), plan.gt_total, gt_off, n_images, n_ch, n_anchors, anchors, strides,
                          grid, bound);
             if (plan.self_clean) {                         // the reducer may only wipe `bound` once nobody writes it any more
@@ -1016,6 +1073,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         }
     }
     if (reducer) {
+        YB_TRACE_ROLE(12);
         for (int b = threadIdx.x; b < n_images; b += kAssignThreads)
             dep_wait(done + b, tile_ctas + (unsigned int)plan.match_ctas, flags + 3);
         // (self-cleaning) `bound` may only be wiped once no probe CTA can write it any more
@@ -1036,6 +1094,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     }
     int image;
     if (match_image >= 0) {
+        YB_TRACE_ROLE(11);
         image = match_image;
         const int g_begin = __ldg(gt_off + image), m_img = __ldg(gt_off + image + 1) - g_begin;
         if (m_img > 0) {                                    // uniform per CTA
@@ -1061,6 +1120,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
             image = gf / fine;
             tile = gf - image * fine;
         }
+        YB_TRACE_ROLE(role == 0 ? (tile >= n_tiles - coarse ? 1 : 0) : 2);
         if (role == 0)
             assign_body<T, VW>(image, tile, preds, n_ch, n_anchors, anchors, strides, gt, gt_off, best,
                                plan.probe_ctas > 0 ? bound : nullptr, chained ? nullptr : gt_img, WRITE_GRAD ? grad : nullptr, prune);

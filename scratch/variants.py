@@ -44,12 +44,12 @@ def run_all():
                                         ctypes.c_float, ctypes.c_float, P, P, P, P, P, P, ctypes.c_size_t, ctypes.c_uint, P, P, P]
         line = [f'{name(v):28s}']
         for cn, d in data.items():
-            ws = torch.empty(lib.yb_loss_workspace_bytes(d['n'], d['a'], d['gt_total'], d['dt']), dtype=torch.uint8, device=dev)
+            ws = torch.zeros(lib.yb_loss_workspace_bytes(d['n'], d['a'], d['gt_total'], d['dt']), dtype=torch.uint8, device=dev)
             grad = torch.empty_like(d['preds']); out = torch.empty(8, device=dev)
             st = torch.cuda.current_stream().cuda_stream
             def call():
                 rc = lib.yb_loss_fwd_bwd(d['preds'].data_ptr(), d['dt'], d['n'], d['nc'], 16, d['a'], d['anc'].data_ptr(), d['st'].data_ptr(), d['gt'].data_ptr(),
-                                         d['off'].data_ptr(), d['gt_total'], d['gmax'], 1.0, 1.5, grad.data_ptr(), out.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), 0, (ctypes.byref(d['hint']) if d['hint'] is not None else None), None, st)
+                                         d['off'].data_ptr(), d['gt_total'], d['gmax'], 1.0, 1.5, grad.data_ptr(), out.data_ptr(), None, None, None, ws.data_ptr(), ws.numel(), 8, (ctypes.byref(d['hint']) if d['hint'] is not None else None), None, st)
                 assert rc == 0, lib.yb_last_error()
             for _ in range(3): call()
             torch.cuda.synchronize()
