@@ -81,6 +81,9 @@ namespace yb {
 #ifndef YB_LOSS_PDL                   // 1: the launch may become resident behind its predecessor's last wave (programmatic dependent launch)
 #define YB_LOSS_PDL 1
 #endif
+#ifndef YB_PROBE_LEVELS               // the probe role looks at the GT's home cell on the k finest levels (0: on every level)
+#define YB_PROBE_LEVELS 1
+#endif
 #ifndef YB_PROBE_MIN_GT               // the probe role runs when an image can hold more GTs than this (gmax)
 #define YB_PROBE_MIN_GT 128
 #endif
@@ -451,23 +454,27 @@ __device__ __forceinline__ void probe_gts(const T *__restrict__ preds, const flo
     const int n = lo;
     const float gx = __ldg(gt + (size_t)g * 5), gy = __ldg(gt + (size_t)g * 5 + 1);
     float best_d = __int_as_float(0x7f800000);
-    for (int l0 = 0; l0 < grid.n_levels; l0 += 4) {        // the gathers of four levels fly together
+    // Only the YB_PROBE_LEVELS finest levels are probed (0: all).  Each probed anchor costs 64 scattered 32-byte sectors, every
+    // GT probes at the head of the launch -- a burst of random DRAM accesses during which nothing streams -- and the finest
+    // level's home cell nearly always holds the smallest distance (cfg5: 163.4 -> 157.5 us with one level, 158.5 with two)
+    const int n_levels = YB_PROBE_LEVELS > 0 ? min(grid.n_levels, YB_PROBE_LEVELS) : grid.n_levels;
+    for (int l0 = 0; l0 < n_levels; l0 += 4) {             // the gathers of four levels fly together
         float z[4][4];
         int a[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int l = min(l0 + u, grid.n_levels - 1);  // the tail repeats the last level: harmless
+            const int l = min(l0 + u, n_levels - 1);       // (the tail repeats the last level's index and loads nothing)
             const float s = grid.stride[l];
             const int col = min(max((int)floorf(gx / s - grid.x0[l] + 0.5f), 0), grid.w[l] - 1);
             const int row = min(max((int)floorf(gy / s - grid.y0[l] + 0.5f), 0), grid.h[l] - 1);
             a[u] = min(max(grid.start[l] + row * grid.w[l] + col, 0), n_anchors - 1);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                z[u][k] = load_as_float(preds + ((size_t)n * n_ch + k * kRegMax + bin) * n_anchors + a[u]);
+                z[u][k] = l0 + u < n_levels ? load_as_float(preds + ((size_t)n * n_ch + k * kRegMax + bin) * n_anchors + a[u]) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (l0 + u >= grid.n_levels) break;            // warp-uniform
+            if (l0 + u >= n_levels) break;                 // warp-uniform
             AnchorTerms at;
 #pragma unroll
             for (int k = 0; k < 4; ++k) at.z[k] = z[u][k];
@@ -1079,7 +1086,13 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         // (self-cleaning) `bound` may only be wiped once no probe CTA can write it any more
         if (plan.self_clean && plan.probe_ctas > 0 && threadIdx.x == 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3);
         __syncthreads();
+#ifdef YB_LOSS_TRACE
+        const unsigned long long t_waited = TraceScope::now();
+#endif
         final_reduce(n_images, n_anchors, gt_off, acc, flags, lambda_cls, lambda_dfl, out_loss, out_per_image);
+#ifdef YB_LOSS_TRACE
+        if (threadIdx.x == 0) g_trace[(1 << 16) - 1] = make_ulonglong4(t_waited, TraceScope::now(), 0ull, 99ull);
+#endif
         if (plan.self_clean) {
             // Every other CTA of the launch that touches the workspace has counted itself off: put back the zeros the next
             // call expects (the words this launch used, no more), so that the step needs no memset node in front of it.

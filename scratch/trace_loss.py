@@ -41,10 +41,12 @@ for cn, (n, nc, imgsz, gmax, dt) in {'cfg2': (128, 80, 640, 100, torch.float32),
     torch.cuda.synchronize()
     buf = np.zeros((1 << 16, 4), dtype=np.uint64)
     assert lib.yb_trace_dump(buf.ctypes.data) == 0
+    red = buf[-1].copy(); buf = buf[:-1]
     buf = buf[buf[:, 3] > 0]
+    buf = buf[buf[:, 1] + np.uint64(2_000_000) > buf[:, 1].max()]      # this launch only (entries of larger earlier grids linger)
     t0 = buf[:, 0].min(); t1 = buf[:, 1].max()
     s = (buf[:, 0] - t0).astype(np.float64) / 1e3; e = (buf[:, 1] - t0).astype(np.float64) / 1e3; role = buf[:, 3].astype(int)
-    print(f'== {cn}: {len(buf)} CTAs, span {float(t1 - t0) / 1e3:.1f} us')
+    print(f'== {cn}: {len(buf)} CTAs, span {float(t1 - t0) / 1e3:.1f} us; reducer: waited until {(float(red[0]) - float(t0)) / 1e3:.1f}, reduced by {(float(red[1]) - float(t0)) / 1e3:.1f}')
     for r in sorted(set(role)):
         m = role == r
         d = e[m] - s[m]
