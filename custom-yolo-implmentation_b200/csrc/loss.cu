@@ -1083,7 +1083,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         YB_TRACE_ROLE(12);
         for (int b = threadIdx.x; b < n_images; b += kAssignThreads)
             dep_wait(done + b, tile_ctas + (unsigned int)plan.match_ctas, flags + 3);
-        // (self-cleaning) `bound` may only be wiped once no probe CTA can write it any more
+        // (self-cleaning) the probe CTAs' counter may only be wiped once they have all counted themselves off
         if (plan.self_clean && plan.probe_ctas > 0 && threadIdx.x == 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3);
         __syncthreads();
 #ifdef YB_LOSS_TRACE
@@ -1100,8 +1100,6 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
             wipe_words(reinterpret_cast<unsigned long long *>(flags), 8);
             wipe_words(reinterpret_cast<unsigned long long *>(done), ((size_t)n_images + 1) / 2);
             wipe_words(acc, (size_t)n_images * kAccPerImage);
-            wipe_words(best, (size_t)plan.gt_total);
-            if (plan.probe_ctas > 0) wipe_words(reinterpret_cast<unsigned long long *>(bound), ((size_t)plan.gt_total + 1) / 2);
         }
         return;
     }
@@ -1143,6 +1141,26 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     }
     if (!chained) return;
     __syncthreads();
+    if (match_image >= 0 && plan.self_clean) {
+        // (self-cleaning) the image's last match CTA to finish wipes the image's keys and bounds: every other CTA that reads
+        // or writes them has counted itself off (the probe CTAs on their own counter); the reducer no longer looks at them
+        __shared__ bool s_last_of_image;
+        if (threadIdx.x == 0) {
+            // (before this CTA counts itself off: afterwards the reducer may wipe the probes' counter at any time)
+            if (plan.probe_ctas > 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3);
+            __threadfence();
+            s_last_of_image = atomicAdd(done + image, 1u) + 1u == tile_ctas + (unsigned int)plan.match_ctas;
+        }
+        __syncthreads();
+        if (s_last_of_image) {
+            const int g_begin = __ldg(gt_off + image), m_img = __ldg(gt_off + image + 1) - g_begin;
+            for (int m = threadIdx.x; m < m_img; m += kAssignThreads) {
+                best[g_begin + m] = 0ull;
+                if (plan.probe_ctas > 0) bound[g_begin + m] = 0u;
+            }
+        }
+        return;
+    }
     if (threadIdx.x == 0) dep_signal(done + image);
 }
 

@@ -469,3 +469,46 @@ def test_fp16_head_output_goes_through_float_like_the_reference(cuda_device):
     ora = L.loss_forward_backward(x16.float(), gts, anchors, strides, 6)
     assert abs(loss.item() - ora.total.item()) <= F32_RTOL * abs(ora.total.item())
     assert_grad_close(x.grad.cpu(), ora.grad.half(), 2e-3)          # one fp16 rounding of the gradient
+
+
+@pytest.mark.gpu
+def test_workspace_is_left_zeroed_between_calls(cuda_device):
+    """No memset node in front of the step (YB_LOSS_WS_CLEAN / YB_TAL_WS_CLEAN): the launch's last CTAs wipe every
+    workspace word the launch used, so a buffer that starts out zeroed serves call after call, whatever the batch
+    shape.  Checked directly: after calls of very different shapes (probe role on and off, images without boxes, a
+    forward-only call, a GT-free batch, the task-aligned pair) every byte the kernels own is zero again, and a call
+    repeated after all of them reproduces its first result bit for bit."""
+    from custom_yolo_implmentation_b200 import _cabi
+    dev = cuda_device
+
+    def owned_is_zero(tag):
+        torch.cuda.synchronize(dev)
+        bufs = [b for k, b in P._clean_ws_cache.items() if k[2] == tag and k[0] == dev.index]
+        assert bufs
+        # the fused loss owns its whole buffer; the task-aligned pair promises its counters (the first 2 KB)
+        return all(int((b if tag == "loss" else b[:2048]).count_nonzero()) == 0 for b in bufs)
+
+    cases = [(3, 640, 60, torch.float32, 71, 0), (2, 1280, 300, torch.bfloat16, 72, 0),
+             (2, 256, 40, torch.float32, 73, _cabi.YB_LOSS_FORCE_PROBE), (5, 320, 7, torch.float32, 74, 0)]
+    first = None
+    for rep in range(2):
+        for n, imgsz, gmax, dtype, seed, flags in cases:
+            preds, gts, anchors, strides = syn.make_loss_inputs(n, 80, imgsz, gmax, seed, dtype=dtype)
+            gts[0] = gts[0][:0]                                              # an image without boxes
+            got = run_cuda_trace(preds, gts, anchors, strides, 80, dev, flags=flags, want_grad=(seed != 74))
+            assert owned_is_zero("loss"), (rep, seed)
+            if seed == 71:
+                if first is None:
+                    first = got
+                else:
+                    assert torch.equal(got[0], first[0]) and torch.equal(got[1], first[1])
+        # a batch without any box: the forward-only kernels, no match role
+        preds, gts, anchors, strides = syn.make_loss_inputs(2, 80, 320, 5, 75)
+        gt, off, counts = P.pack_gt([g[:0].to(dev) for g in gts], dev)
+        P.fused_loss(preds.to(dev), gt, off, 0, anchors.to(dev), strides.to(dev), 80, 1.0, 1.5)
+        assert owned_is_zero("loss"), rep
+        # the task-aligned pair
+        preds, gts, anchors, strides = syn.make_loss_inputs(2, 80, 320, 20, 76 + rep)
+        gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
+        P.fused_tal_loss(preds.to(dev), gt, off, anchors.to(dev), strides.to(dev), 80, 1.5, 1.0, 1.5)
+        assert owned_is_zero("tal"), rep
