@@ -334,8 +334,15 @@ def run_ours(args):
             rel = max(abs(host[k].item() - float(z[key][rank])) / abs(float(z[key][rank]))
                       for k, key in enumerate(("total_loss", "box_loss", "cls_loss")))
             idx_ref = torch.from_numpy(z["idx"][rank, : int(sum(counts))].astype("int64"))
-            agree = int((tr["idx"].cpu().long() == idx_ref).sum())
-            res = torch.tensor([rel, float(agree), float(sum(counts))], dtype=torch.float64, device=dev)
+            same = tr["idx"].cpu().long() == idx_ref
+            agree = int(same.sum())
+            # What a flipped exact tie may move: the GT goes to the other (equidistant) anchor and its own DFL term changes
+            # -- at most ~24 (four sides, cross-entropy over 16 bins of O(1) logits) against a mean of ~3.3 per side -- with the
+            # weight 1 / (4 M N) of a GT in an image of M boxes: 24 / (4 * 3.3 * N * M) = 1.5e-2 / M at N = 128, relative.
+            img_of_gt = torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts))
+            m_of_gt = torch.tensor(counts, dtype=torch.float64)[img_of_gt]
+            allow = 1e-5 + float((1.5e-2 * (128.0 / n) / m_of_gt[~same]).sum())
+            res = torch.tensor([rel, float(agree), float(sum(counts)), allow], dtype=torch.float64, device=dev)
             if world > 1:
                 allr = [torch.zeros_like(res) for _ in range(world)]
                 dist.all_gather(allr, res)
@@ -345,16 +352,17 @@ def run_ours(args):
             parity = {"against": "the unmodified reference's loss scalars and matched anchors for each rank's batch "
                                  "(tests/golden/loss_cfg3_ranks.npz, generated by tests/golden/make_golden.py)",
                       "ranks_checked": len(allr), "loss_rel_err_max": max(r[0] for r in allr),
+                      "loss_rel_err_per_rank": [r[0] for r in allr], "loss_rel_err_allowed_per_rank": [r[3] for r in allr],
                       "matched_anchors_identical": f"{int(sum(r[1] for r in allr))}/{int(sum(r[2] for r in allr))}"}
             # A GT whose two nearest predicted centres lie at the SAME float distance is decided by the last ulp of
             # the decode (rank 0's batch has four such exact ties; the reference's own CPU and CUDA runs differ on
             # them, see cuda_eager_baseline.matched_anchors_cuda_vs_cpu).  Ranks with every anchor identical must
-            # meet 1e-5 on the loss; a flipped tie moves one GT's terms (a few 1e-5 of the loss) and nothing else.
+            # meet 1e-5 on the loss; a flipped tie moves one GT's terms and nothing else.
             n_bad = sum(r[2] - r[1] for r in allr)
             parity["note"] = ("exact" if n_bad == 0 else
                               f"{int(n_bad)} GT(s) on an exact float tie of the distance went to the other (equidistant) anchor")
-            # (each flipped tie may move the loss by up to ~1e-4 relative: bound 1e-5 + 1e-4 per flipped GT)
-            bad_rank = [i for i, r in enumerate(allr) if r[0] > 1e-5 + 1e-4 * (r[2] - r[1]) or r[2] - r[1] > 1e-3 * r[2]]
+            # (bound per rank: 1e-5, plus 1.5e-2 / M for every flipped GT of an image with M boxes -- computed above, r[3])
+            bad_rank = [i for i, r in enumerate(allr) if r[0] > r[3] or r[2] - r[1] > 1e-3 * r[2]]
             if bad_rank:
                 raise SystemExit(f"bench.py: PARITY FAILURE on the benchmark batch (ranks {bad_rank}): {parity} {allr}")
     if world > 1:
