@@ -36,8 +36,11 @@ namespace yb {
 #ifndef YB_CLS_THREADS
 #define YB_CLS_THREADS 128
 #endif
-#ifndef YB_CLS_UNROLL
+#ifndef YB_CLS_UNROLL                 // class rows in flight per thread, bf16 rows (measured at cfg5: 4 -> 157.3 us, 5 -> 161.0, 8 -> 182.8)
 #define YB_CLS_UNROLL 4
+#endif
+#ifndef YB_CLS_UNROLL_F32             // ... fp32 rows: a class CTA's 20 rows as 4 batches of 5 instead of 5 of 4 (cfg2: 234.9 -> 232.9 us;
+#define YB_CLS_UNROLL_F32 5           // 8 spills at 80 registers: 248.5)
 #endif
 #ifndef YB_CLS_CSPLIT
 #define YB_CLS_CSPLIT 4
@@ -921,7 +924,7 @@ __device__ __forceinline__ void cls_body(int n, int tile, int n_tiles, int split
     if (a0 < n_anchors && nc > 0) {
         const size_t base = ((size_t)n * n_ch + 4 * kRegMax + c_lo) * n_anchors + a0;
         const f32x2 k2 = pack2(k_cls, k_cls);
-        constexpr int U = YB_CLS_UNROLL;
+        constexpr int U = sizeof(T) == 4 ? YB_CLS_UNROLL_F32 : YB_CLS_UNROLL;
         // software pipeline: the next U rows are in flight while the current U are evaluated
         Group<T, VW> cur[U];
 #pragma unroll

@@ -42,12 +42,12 @@ def run_all():
         lib.yb_tal_assign.argtypes = [Pp, I, I, I, I, I, Pp, Pp, Pp, Pp, I, Pp, Pp, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
         lib.yb_tal_loss.argtypes = [Pp, I, I, I, I, I, I, Pp, Pp, Pp, Pp, Pp, Pp, ctypes.c_size_t, Pp]
         lib.yb_last_error.restype = ctypes.c_char_p
-        prm = _cabi.TalParams(10, 0.5, 6.0, 1.5, 1.0, 1.5, 0, 0.75, 2.0)
+        prm = _cabi.TalParams(10, 0.5, 6.0, 1.5, 1.0, 1.5, 0, 0.75, 2.0, 1)
         line = [f'{name(v):24s}']
         for cn, (x, gt, off, a, s, code) in data.items():
             n, c, A = x.shape; G = gt.shape[0]
             hint = P.build_grid_hint(a, s) if os.environ.get('YB_NO_HINT') is None else None
-            ws = torch.empty(lib.yb_tal_workspace_bytes(n, A, G, code, 10), dtype=torch.uint8, device=dev)
+            ws = torch.zeros(lib.yb_tal_workspace_bytes(n, A, G, code, 10), dtype=torch.uint8, device=dev)
             stats = torch.empty(8, device=dev); out = torch.empty(8, device=dev); grad = torch.empty_like(x)
             st = torch.cuda.current_stream().cuda_stream
             def assign():
