@@ -69,6 +69,7 @@ struct TalWorkspace {
     // zeroed by yb_tal_assign's first kernels (the counters by a memset, the per-anchor arrays by tal_decode_kernel)
     unsigned int *ticket;               // [0] finalize ticket, [1] / [7] / [8] next unit of tal_gt_kernel's three kinds of work, [9] units resolved, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived
     unsigned long long *stat_acc;       // [kTalStatAcc] fixed-point sums of the target scores, [kTalStatAcc] foreground counts, [1] total #foreground
+    unsigned int *img_done;             // [N]  tal_decode_kernel CTAs that have finished with the image (tal_gt_kernel starts on an image behind this count)
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
     int *aslot;                         // [N * A]  1 + (g * topk + r) of the GT slot that owns the anchor (0 = background)
     // plain scratch
@@ -101,6 +102,8 @@ static TalWorkspace carve_tal(void *base, int n_images, int n_anchors, int gt_to
     off += 64;
     w.stat_acc = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (2 * kTalStatAcc + 1), 64);
+    w.img_done = reinterpret_cast<unsigned int *>(p + off);
+    off += round_up(sizeof(unsigned int) * (size_t)n_images, 64);
     w.small_zero_bytes = off;
     w.akey = reinterpret_cast<unsigned long long *>(p + off);
     off += round_up(sizeof(unsigned long long) * (size_t)n_images * n_anchors, 64);
@@ -338,14 +341,20 @@ tal_decode_kernel(const T *__restrict__ preds, int n_ch, int n_anchors, const fl
                   const float *__restrict__ strides, const int *__restrict__ gt_off, float4 *__restrict__ dbox,
                   float4 *__restrict__ gext, float2 *__restrict__ ctr, unsigned long long *__restrict__ akey,
                   int *__restrict__ aslot, int *__restrict__ sel_count, const TalGrid grid,
-                  unsigned int *__restrict__ grid_rejected) {
+                  unsigned int *__restrict__ grid_rejected, unsigned int *__restrict__ img_done) {
 #if YB_TAL_PDL
-    pdl_launch_dependents();
     pdl_wait();                                            // behind the previous step's tal_finalize_kernel (YB_TAL_WS_CLEAN): its wiped counters,
                                                            // and the workspace arrays that step's kernels still read
+    // ... and only then may tal_gt_kernel's CTAs move in: they do NOT wait for this grid to complete but for the per-image
+    // counts below, so nothing of the previous step may still be in flight when the first of them starts.  By the time
+    // every CTA of this grid has passed this line, every CTA of this grid is resident or done: a waiting successor can
+    // never keep a producer out of the machine.
+    pdl_launch_dependents();
 #endif
     tal_decode_body<T, VW>(blockIdx.y, blockIdx.x, preds, n_ch, n_anchors, anchors, strides, gt_off, dbox, gext, ctr, akey, aslot,
                            sel_count, grid, grid_rejected);
+    __syncthreads();
+    if (threadIdx.x == 0) dep_signal(img_done + blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -960,15 +969,25 @@ __device__ __forceinline__ void tal_gt_resolve(const TalGtArgs<T> &A, const TalR
 // the resident slots the streaming role needs to keep HBM busy, and a per-image GT queue balances worse than a global one.
 template <typename T>
 __global__ void __launch_bounds__(32 * kTopkWarps, YB_TOPK_MINBLOCKS)
-tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *__restrict__ grid_rejected,
-              unsigned int *__restrict__ next_gt, int have_hint, float *__restrict__ out_stats, const yb_peer_exchange px) {
+tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *grid_rejected,
+              unsigned int *__restrict__ next_gt, int have_hint, float *__restrict__ out_stats, const yb_peer_exchange px,
+              const unsigned int *img_done, int decode_tiles) {
     __shared__ int s_aq[kTopkWarps][kTopkQueue];           // queue of inside anchors
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #if YB_TAL_PDL
     pdl_launch_dependents();
-    pdl_wait();                                            // tal_decode_kernel's boxes, armed words and verdict on the hint
 #endif
+    // No wait for tal_decode_kernel as a whole: its last wave fills only part of the machine (2 176 CTAs on 888 slots at
+    // cfg2), and these CTAs move into the rest and start on the images that are already decoded -- a warp waits for the
+    // decode CTAs of the image it is about to read (boxes, armed keys and "published" words), image 0 first (the anchor
+    // centres, their extents and the verdict on the grid hint are written by image 0's CTAs).  The acquire of dep_wait
+    // orders the warp's reads behind the producers' release; the units further down read behind the per-GT / per-unit
+    // acquires that chain back to it.  griddepcontrol.wait at the END of the kernel keeps the stream's completion order
+    // (tal_cls_kernel waits for THIS grid only).
+    if (lane == 0) dep_wait(img_done, (unsigned int)decode_tiles, next_gt + 9);
+    __syncwarp();
     const bool regular = A.grid.n_levels > 0 && __ldcg(grid_rejected) == 0u;   // uniform over the launch
+    int n_ready = 0;                                       // the image this warp last waited for (GTs come in image order)
     // (Measured and not kept: the next round's boxes requested one trip ahead of the filter -- the restructured loop cost
     // more than the hidden L2 latency gained, 180 vs 174 us for the assign phase; asking for the next unit one unit ahead:
     // no change; one batch-wide "selections done" counter for the target scores: +18 us, they then start only when the
@@ -985,6 +1004,11 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= A.gt_total) break;
         const int n = gt_image(A.gt_off, A.n_images, g);
+        if (n != n_ready) {
+            if (lane == 0) dep_wait(img_done + n, (unsigned int)decode_tiles, next_gt + 9);
+            __syncwarp();
+            n_ready = n;
+        }
         tal_gt_body<T>(A, g, n, g - __ldg(A.gt_off + n), regular, s_aq[warp]);
     }
     for (;;) {
@@ -1011,6 +1035,9 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
             tal_publish_stats(R.stat_acc, grid_rejected, have_hint, out_stats, px);
         }
     }
+#if YB_TAL_PDL
+    pdl_wait();                                            // (returns at once: every image this grid read was complete)
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1204,7 +1231,8 @@ __global__ void __launch_bounds__(kTalFinThreads)
 tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const float4 *fterm, const float *tsc, int n_part,
                     int n_slots, const float *part, unsigned long long *stat_acc, const float *tss_dev, float lambda_box,
                     float lambda_cls, float lambda_dfl, int vfl, VflParams vp, double *__restrict__ cta_sums,
-                    unsigned int *__restrict__ ticket, int wipe, float *__restrict__ out_loss) {
+                    unsigned int *__restrict__ ticket, int wipe, unsigned int *__restrict__ img_done, int n_images,
+                    float *__restrict__ out_loss) {
     __shared__ double s[3][kTalFinThreads / 32];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1288,6 +1316,7 @@ tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const floa
     }
     for (int w = threadIdx.x; w < 8 + 2 * kTalStatAcc + 1; w += kTalFinThreads)
         (w < 8 ? reinterpret_cast<unsigned long long *>(ticket) + w : stat_acc + (w - 8))[0] = 0ull;
+    for (int b = threadIdx.x; b < n_images; b += kTalFinThreads) img_done[b] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1323,10 +1352,11 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
         A.bad_cls = w.ticket + 2;
 #if YB_TAL_PDL
         YB_CUDA(launch_pdl(tal_decode_kernel<T, VW>, dim3(n_tiles, n_images), dim3(kTalThreads), 0, st, preds, n_ch, n_anchors, anchors,
-                           strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3));
+                           strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3, w.img_done));
 #else
         tal_decode_kernel<T, VW><<<dim3(n_tiles, n_images), kTalThreads, 0, st>>>(
-            preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3);
+            preds, n_ch, n_anchors, anchors, strides, gt_off, w.dbox, w.gext, w.ctr, w.akey, w.aslot, w.sel_count, grid, w.ticket + 3,
+            w.img_done);
 #endif
         YB_LAUNCH_CHECK();
         // warps draw GTs from a counter
@@ -1335,9 +1365,10 @@ static int launch_tal_assign(const T *preds, int n_images, int nc, int n_anchors
         R.tsc = w.tsc; R.aslot = w.aslot; R.out_assigned = out_assigned; R.out_tscore = out_tscore; R.stat_acc = w.stat_acc;
 #if YB_TAL_PDL
         YB_CUDA(launch_pdl(tal_gt_kernel<T>, dim3(gt_ctas), dim3(32 * kTopkWarps), 0, st, A, R, w.ticket + 3, w.ticket + 1,
-                           (int)(grid.n_levels > 0), out_stats, px));
+                           (int)(grid.n_levels > 0), out_stats, px, w.img_done, n_tiles));
 #else
-        tal_gt_kernel<T><<<gt_ctas, 32 * kTopkWarps, 0, st>>>(A, R, w.ticket + 3, w.ticket + 1, grid.n_levels > 0, out_stats, px);
+        tal_gt_kernel<T><<<gt_ctas, 32 * kTopkWarps, 0, st>>>(A, R, w.ticket + 3, w.ticket + 1, grid.n_levels > 0, out_stats, px,
+                                                              w.img_done, n_tiles);
 #endif
         YB_LAUNCH_CHECK();
     } else {
@@ -1379,12 +1410,12 @@ static int launch_tal_loss(const T *preds, int n_images, int nc, int n_anchors, 
 #if YB_TAL_PDL
         YB_CUDA(launch_pdl(tal_finalize_kernel<T>, dim3(blocks), dim3(kTalFinThreads), 0, st, grad, w.fcell_off, w.fterm, w.tsc,
                            n_part, n_slots, w.part, w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl, (int)p.vfl, vp,
-                           w.cta_sums, w.ticket, (int)((p.flags & YB_TAL_WS_CLEAN) != 0), out_loss));
+                           w.cta_sums, w.ticket, (int)((p.flags & YB_TAL_WS_CLEAN) != 0), w.img_done, n_images, out_loss));
 #else
         tal_finalize_kernel<T><<<blocks, kTalFinThreads, 0, st>>>(grad, w.fcell_off, w.fterm, w.tsc, n_part, n_slots, w.part,
                                                                   w.stat_acc, tss_dev, p.lambda_box, p.lambda_cls, p.lambda_dfl,
                                                                   p.vfl, vp, w.cta_sums, w.ticket,
-                                                                  (int)((p.flags & YB_TAL_WS_CLEAN) != 0), out_loss);
+                                                                  (int)((p.flags & YB_TAL_WS_CLEAN) != 0), w.img_done, n_images, out_loss);
 #endif
     }
     YB_LAUNCH_CHECK();

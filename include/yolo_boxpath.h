@@ -166,7 +166,7 @@ typedef struct {
     int vfl;                                    /* 0: plain BCE class term; 1: varifocal weighting (north_star "VFL-BCE"): */
     float vfl_alpha, vfl_gamma;                 /*    weight = vfl_alpha * sigmoid(x)^vfl_gamma on background cells
                                                       (differentiated), = the target score on the positive cell */
-    unsigned flags;                             /* 0, or YB_TAL_WS_CLEAN: the caller vouches that the first 1152 bytes of the workspace (the counters) are
+    unsigned flags;                             /* 0, or YB_TAL_WS_CLEAN: the caller vouches that the first 1152 + 4 * n_images (rounded up to 64) bytes of the workspace (the counters) are
                                                    zero -- true for a buffer that was zeroed once and has only seen complete
                                                    yb_tal_assign + yb_tal_loss pairs since (yb_tal_loss's last kernel wipes the
                                                    step's counters): no memset node in front of the step */

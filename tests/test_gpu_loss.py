@@ -485,8 +485,9 @@ def test_workspace_is_left_zeroed_between_calls(cuda_device):
         torch.cuda.synchronize(dev)
         bufs = [b for k, b in P._clean_ws_cache.items() if k[2] == tag and k[0] == dev.index]
         assert bufs
-        # the fused loss owns its whole buffer; the task-aligned pair promises its counters (the first 1152 bytes)
-        return all(int((b if tag == "loss" else b[:1152]).count_nonzero()) == 0 for b in bufs)
+        # the fused loss owns its whole buffer; the task-aligned pair promises its counters (1152 bytes + 4 per image,
+        # rounded up to 64: two images here)
+        return all(int((b if tag == "loss" else b[:1152 + 64]).count_nonzero()) == 0 for b in bufs)
 
     cases = [(3, 640, 60, torch.float32, 71, 0), (2, 1280, 300, torch.bfloat16, 72, 0),
              (2, 256, 40, torch.float32, 73, _cabi.YB_LOSS_FORCE_PROBE), (5, 320, 7, torch.float32, 74, 0)]
