@@ -200,6 +200,23 @@ def _clean_workspace(n_bytes: int, device, tag: str) -> torch.Tensor:
     return buf
 
 
+class _keeps_workspace_clean:
+    """``with _keeps_workspace_clean(device, tag): ...`` around the calls that use a clean workspace: if anything raises in
+    between (an ABI error, a failing collective between ``yb_tal_assign`` and ``yb_tal_loss``), what the kernels left in the
+    buffer is unknown -- forget it, the next call zeroes a fresh one."""
+
+    def __init__(self, device, tag: str):
+        self.key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is not None:
+            _clean_ws_cache.pop(self.key, None)
+        return False
+
+
 def _as_offsets(gt: torch.Tensor, gt_offsets: torch.Tensor, n: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
     """The GT wire format as the kernels read it: ``gt (sum Mi, 5)`` fp32 and ``offsets (N+1,)`` int32, contiguous, on
     ``device``.  A CPU (pinned) ``PackedGT`` straight from ``collate_fn_packed`` is moved, not dereferenced as a device
@@ -278,14 +295,14 @@ def fused_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tensor, 
         per_image = torch.empty(2, n, dtype=torch.float32, device=dev)
         trace = {"idx": idx[:gt_total], "iou": iou[:gt_total], "dfl_per_image": per_image[0], "cls_per_image": per_image[1]}
     hint = _grid_hint_for(anc, st, exact=False) if isinstance(grid_hint, str) else grid_hint
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _keeps_workspace_clean(dev, "loss"):
         import ctypes
         rc = lib.yb_loss_fwd_bwd(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st),
                                  _cabi.ptr(gt) if gt_total else None, _cabi.ptr(gt_offsets), gt_total, gmax,
                                  float(lambda_cls), float(lambda_dfl), _cabi.ptr(grad), _cabi.ptr(out),
                                  _cabi.ptr(idx), _cabi.ptr(iou), _cabi.ptr(per_image), _cabi.ptr(ws), ws.numel(),
                                  int(flags), ctypes.byref(hint) if hint is not None else None, ev, _cabi.stream_ptr(dev))
-    _cabi.check(rc, "yb_loss_fwd_bwd")
+        _cabi.check(rc, "yb_loss_fwd_bwd")
     return out, grad, trace
 
 
@@ -539,29 +556,30 @@ def fused_tal_loss(preds: torch.Tensor, gt: torch.Tensor, gt_offsets: torch.Tens
     px_ref = ctypes.byref(px) if px is not None else None
     params = _cabi.TalParams(int(topk), float(alpha), float(beta), float(lambda_box), float(lambda_cls), float(lambda_dfl),
                              int(cls_loss == "vfl"), float(vfl_alpha), float(vfl_gamma), _cabi.YB_TAL_WS_CLEAN)
-    with torch.cuda.device(dev):
-        rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
-                               _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params),
-                               ctypes.byref(hint) if hint is not None else None, px_ref, _cabi.ptr(stats),
-                               _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
-    _cabi.check(rc, "yb_tal_assign")
-    tss = stats[:1]
-    if px is None and sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
-            and torch.distributed.get_world_size() > 1:
-        # [sum of target scores, #foreground] -> mean over the ranks, in place: one collective, no extra kernels.
-        # Nothing of the step is left to overlap it with: everything that does not need the normaliser has already run.
-        if torch.distributed.get_backend() == "nccl":
-            torch.distributed.all_reduce(stats[:2], op=torch.distributed.ReduceOp.AVG)
-        else:                                                   # gloo has no AVG
-            torch.distributed.all_reduce(stats[:2])
-            stats[:2] /= torch.distributed.get_world_size()
+    with _keeps_workspace_clean(dev, "tal"):       # an exception between the two calls leaves the counters armed
+        with torch.cuda.device(dev):
+            rc = lib.yb_tal_assign(_cabi.ptr(x), dt, n, num_classes, reg_max, a, _cabi.ptr(anc), _cabi.ptr(st), gt_ptr,
+                                   _cabi.ptr(gt_offsets), gt_total, ctypes.byref(params),
+                                   ctypes.byref(hint) if hint is not None else None, px_ref, _cabi.ptr(stats),
+                                   _cabi.ptr(asg), _cabi.ptr(tsc), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
+        _cabi.check(rc, "yb_tal_assign")
         tss = stats[:1]
-    grad = torch.empty_like(x) if want_grad else None
-    out = torch.empty(8, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        rc = lib.yb_tal_loss(_cabi.ptr(x), dt, n, num_classes, reg_max, a, gt_total, ctypes.byref(params), _cabi.ptr(tss),
-                             px_ref, _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
-    _cabi.check(rc, "yb_tal_loss")
+        if px is None and sync_normalizer and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            # [sum of target scores, #foreground] -> mean over the ranks, in place: one collective, no extra kernels.
+            # Nothing of the step is left to overlap it with: everything that does not need the normaliser has already run.
+            if torch.distributed.get_backend() == "nccl":
+                torch.distributed.all_reduce(stats[:2], op=torch.distributed.ReduceOp.AVG)
+            else:                                                   # gloo has no AVG
+                torch.distributed.all_reduce(stats[:2])
+                stats[:2] /= torch.distributed.get_world_size()
+            tss = stats[:1]
+        grad = torch.empty_like(x) if want_grad else None
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.yb_tal_loss(_cabi.ptr(x), dt, n, num_classes, reg_max, a, gt_total, ctypes.byref(params), _cabi.ptr(tss),
+                                 px_ref, _cabi.ptr(grad), _cabi.ptr(out), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr(dev))
+        _cabi.check(rc, "yb_tal_loss")
     trace = {"assigned_gt": asg, "target_score": tsc, "stats": stats} if want_trace else {}
     return out, grad, trace
 

@@ -161,3 +161,27 @@ def test_tal_full_size_properties(cuda_device):
         a = asg[b]
         cnt = torch.bincount(a[a >= 0], minlength=max(gts[b].shape[0], 1))
         assert int(cnt.max()) <= 10 if cnt.numel() else True
+
+
+def test_an_exception_between_the_two_calls_does_not_poison_the_workspace(cuda_device, monkeypatch):
+    """yb_tal_assign arms the step's counters and yb_tal_loss's last kernel wipes them (YB_TAL_WS_CLEAN: no memset in front
+    of the next step).  If something raises in between -- here right after yb_tal_assign's kernels were queued, so that
+    yb_tal_loss never runs and the counters stay armed -- the buffer is forgotten and the next call starts from a freshly
+    zeroed one: same result as before the failure, bit for bit."""
+    from custom_yolo_implmentation_b200 import _cabi
+    preds, gts, anchors, strides = syn.make_loss_inputs(3, 80, 320, 30, 91)
+    ref = run_cuda(preds, gts, anchors, strides, 80, cuda_device)
+    real_check = _cabi.check
+
+    def failing_check(rc, who):
+        if who == "yb_tal_assign":
+            raise RuntimeError("injected failure")
+        return real_check(rc, who)
+
+    monkeypatch.setattr(_cabi, "check", failing_check)
+    with pytest.raises(RuntimeError, match="injected"):
+        run_cuda(preds, gts, anchors, strides, 80, cuda_device)
+    monkeypatch.setattr(_cabi, "check", real_check)
+    got = run_cuda(preds, gts, anchors, strides, 80, cuda_device)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
