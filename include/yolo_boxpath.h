@@ -80,7 +80,8 @@ typedef yb_tal_grid yb_anchor_grid;
  *   out_idx      (gt_total) int32 or NULL                 matched anchor per GT  (losses.py:215)
  *   out_iou      (gt_total) fp32  or NULL                 IoU soft target per GT (losses.py:256)
  *   out_per_image (2, N) fp32 or NULL                     per-image DFL and QFL terms
- *   flags        0, or YB_LOSS_NO_PRUNE / YB_LOSS_SPLIT_LAUNCH / YB_LOSS_FORCE_PROBE (test and profiling aids, results identical)
+ *   flags        0, or YB_LOSS_NO_PRUNE / YB_LOSS_SPLIT_LAUNCH / YB_LOSS_FORCE_PROBE / YB_LOSS_NO_PDL (test and profiling aids,
+ *                results identical), YB_LOSS_WS_CLEAN (the caller keeps the workspace zeroed: no memset node, see below)
  *   grid_hint    NULL, or the anchors as a pyramid of grids: lets the launch bound every GT's nearest-centre distance
  *                up front (a few probe anchors per GT), so that the box role prunes from its first tile on; used when
  *                gmax > 128, where the coarse pyramid levels would otherwise scan several chunks of GTs.  Results
