@@ -315,6 +315,9 @@ __device__ __forceinline__ f32x2 log1p_neg_small2(f32x2 f) {
 // no deadlock.  That dispatch order is an observation, not a documented guarantee, hence the bounded poll: a consumer
 // that waits longer than ~2 s raises *timeout_flag (reported through the entry point's out_loss and raised by the host
 // side) and carries on, so a violated assumption shows up as an error, never as a hang.
+#ifndef YB_DEP_MAX_SLEEP_NS            // longest sleep between two polls of a waiting consumer
+#define YB_DEP_MAX_SLEEP_NS 1024
+#endif
 __device__ __forceinline__ void dep_signal(unsigned int *counter) {      // ONE thread, after a __syncthreads()
 #ifndef YB_DEP_NOFENCE                                     // (measurement aid: what the fence costs)
     __threadfence();                                      // the CTA's writes (ordered before by the barrier) are visible first
@@ -326,13 +329,14 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void dep_wait(const unsigned int *counter, unsigned int target, unsigned int *timeout_flag) {
+__device__ __forceinline__ void dep_wait(const unsigned int *counter, unsigned int target, unsigned int *timeout_flag,
+                                         unsigned int max_sleep_ns = YB_DEP_MAX_SLEEP_NS) {
     if (ld_acquire_u32(counter) >= target) return;
     const long long t0 = clock64();
     unsigned int ns = 64;
     while (ld_acquire_u32(counter) < target) {
         __nanosleep(ns);
-        ns = min(ns * 2u, 1024u);
+        ns = min(ns * 2u, max_sleep_ns);
         if (clock64() - t0 > (4ll << 30)) {               // ~2 s at 2 GHz
             atomicOr(timeout_flag, 1u);
             return;

@@ -90,6 +90,10 @@ namespace yb {
 #ifndef YB_PROBE_MIN_GT               // the probe role runs when an image can hold more GTs than this (gmax)
 #define YB_PROBE_MIN_GT 128
 #endif
+#ifndef YB_LOSS_POLL_NS               // longest sleep between two polls of a waiting match CTA / the reducer: the launch ENDS on these
+#define YB_LOSS_POLL_NS 256           // waits (cfg2 233.2 -> 232.1 us, cfg5 158.5 -> 156.5 against 1024 ns)
+#endif
+constexpr unsigned int kLossPollNs = YB_LOSS_POLL_NS;
 constexpr int kScanUnroll = YB_SCAN_UNROLL;
 constexpr int kAssignThreads = YB_ASSIGN_THREADS;
 constexpr int kClsThreads = YB_CLS_THREADS;
@@ -1085,9 +1089,9 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
     if (reducer) {
         YB_TRACE_ROLE(12);
         for (int b = threadIdx.x; b < n_images; b += kAssignThreads)
-            dep_wait(done + b, tile_ctas + (unsigned int)plan.match_ctas, flags + 3);
+            dep_wait(done + b, tile_ctas + (unsigned int)plan.match_ctas, flags + 3, kLossPollNs);
         // (self-cleaning) the probe CTAs' counter may only be wiped once they have all counted themselves off
-        if (plan.self_clean && plan.probe_ctas > 0 && threadIdx.x == 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3);
+        if (plan.self_clean && plan.probe_ctas > 0 && threadIdx.x == 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3, kLossPollNs);
         __syncthreads();
 #ifdef YB_LOSS_TRACE
         const unsigned long long t_waited = TraceScope::now();
@@ -1112,7 +1116,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         image = match_image;
         const int g_begin = __ldg(gt_off + image), m_img = __ldg(gt_off + image + 1) - g_begin;
         if (m_img > 0) {                                    // uniform per CTA
-            if (threadIdx.x == 0) dep_wait(done + image, tile_ctas, flags + 3);
+            if (threadIdx.x == 0) dep_wait(done + image, tile_ctas, flags + 3, kLossPollNs);
             __syncthreads();
             // 8 GTs (half-warps) per pass; CTA j of the image takes passes j, j + match_ctas, ...
             for (int base = match_j * (kMatchThreads / 16); base < m_img; base += plan.match_ctas * (kMatchThreads / 16)) {
@@ -1150,7 +1154,7 @@ fused_main_kernel(const T *__restrict__ preds, int n_images, int n_ch, int n_anc
         __shared__ bool s_last_of_image;
         if (threadIdx.x == 0) {
             // (before this CTA counts itself off: afterwards the reducer may wipe the probes' counter at any time)
-            if (plan.probe_ctas > 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3);
+            if (plan.probe_ctas > 0) dep_wait(flags + 4, (unsigned int)plan.probe_ctas, flags + 3, kLossPollNs);
             __threadfence();
             s_last_of_image = atomicAdd(done + image, 1u) + 1u == tile_ctas + (unsigned int)plan.match_ctas;
         }
