@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libyolo_boxpath.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 YB_F32, YB_BF16 = 0, 1
 YB_LOSS_NO_PRUNE, YB_LOSS_SPLIT_LAUNCH, YB_LOSS_FORCE_PROBE, YB_LOSS_WS_CLEAN = 1, 2, 4, 8
 YB_LOSS_NO_PDL = 16
@@ -28,6 +28,7 @@ _lock = threading.Lock()
 _SIGNATURES = {
     "yb_abi_version": (c_int, []),
     "yb_last_error": (ctypes.c_char_p, []),
+    "yb_struct_size": (c_size_t, [c_int]),
     "yb_launch_count": (ctypes.c_longlong, []),
     "yb_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "yb_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -29,3 +29,12 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" int yb_abi_version(void) { return YB_ABI_VERSION; }
 extern "C" const char *yb_last_error(void) { return yb::g_err; }
 extern "C" long long yb_launch_count(void) { return yb::g_launches.load(std::memory_order_relaxed); }
+extern "C" size_t yb_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(yb_tal_params);
+        case 1: return sizeof(yb_tal_grid);
+        case 2: return sizeof(yb_peer_exchange);
+        case 3: return sizeof(yb_gt_source);
+        default: return 0;
+    }
+}

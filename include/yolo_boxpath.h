@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 5
+#define YB_ABI_VERSION 6
 
 typedef enum { YB_F32 = 0, YB_BF16 = 1 } yb_dtype;
 
@@ -45,6 +45,10 @@ int yb_abi_version(void);
 const char *yb_last_error(void);
 /* Kernels this library has launched in this process so far (bench.py reports the delta as gpu_launches). */
 long long yb_launch_count(void);
+/* sizeof() of this header's host structs as the library was built with them -- which: 0 yb_tal_params, 1 yb_tal_grid
+ * (= yb_anchor_grid), 2 yb_peer_exchange, 3 yb_gt_source; 0 for anything else.  A foreign-language binding checks its own
+ * struct layouts against these before the first call (tests/test_host_logic.py does for the ctypes mirror). */
+size_t yb_struct_size(int which);
 
 /* The anchors described as the reference's pyramid of regular grids (make_anchors, src/utils/model_utils.py:60-70: per
  * level x fastest, (x0 + col, y0 + row), one stride per level): level l holds anchors start[l] .. start[l] + w[l]*h[l].

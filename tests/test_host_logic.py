@@ -35,6 +35,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.yb_loss_workspace_bytes(0, 8400, 0, 0) == 0
 
 
+def test_ctypes_struct_layouts_match_the_library():
+    """The host structs cross the boundary by pointer: the ctypes mirror must have the library's sizes (a stale or
+    re-ordered field would corrupt arguments silently) and the hand-packed GT table its 24-byte entries."""
+    import ctypes
+    lib = _cabi.lib()
+    assert lib.yb_struct_size(0) == ctypes.sizeof(_cabi.TalParams)
+    assert lib.yb_struct_size(1) == ctypes.sizeof(_cabi.TalGrid)
+    assert lib.yb_struct_size(2) == ctypes.sizeof(_cabi.PeerExchangeStruct)
+    assert lib.yb_struct_size(3) == 24                  # model/losses.py::_pack_gt_gather writes these by hand
+    assert lib.yb_struct_size(99) == 0
+    assert _cabi.TalParams.flags.offset == ctypes.sizeof(_cabi.TalParams) - 4
+
+
 def test_argument_errors_come_back_through_the_abi():
     lib = _cabi.lib()
     rc = lib.yb_loss_fwd_bwd(None, 0, 1, 1, 16, 4, None, None, None, None, 0, 0, 1.0, 1.5, None, None, None, None, None,
