@@ -185,3 +185,33 @@ def test_an_exception_between_the_two_calls_does_not_poison_the_workspace(cuda_d
     got = run_cuda(preds, gts, anchors, strides, 80, cuda_device)
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+def test_tal_step_is_cuda_graph_capturable(cuda_device):
+    """Both ABI calls of the task-aligned step -- four kernels chained by programmatic dependent launch, the per-GT kernel
+    starting behind per-image counts of the decode kernel, the last kernel wiping the step's counters -- captured in a CUDA
+    graph and replayed: same results as the eager calls, replay after replay, and on new data in the captured buffer."""
+    dev = cuda_device
+    preds, gts, anchors, strides = syn.make_loss_inputs(4, 80, 640, 40, 97)
+    x = preds.to(dev)
+    gt, off, counts = P.pack_gt([g.to(dev) for g in gts], dev)
+    a, s = anchors.to(dev), strides.to(dev)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            ref_out, ref_grad, _ = P.fused_tal_loss(x, gt, off, a, s, 80, 1.5, 1.0, 1.5)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            out, grad, _ = P.fused_tal_loss(x, gt, off, a, s, 80, 1.5, 1.0, 1.5)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        out.zero_(); grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref_out) and torch.equal(grad, ref_grad)
+    x.add_(0.25)
+    graph.replay()
+    torch.cuda.synchronize()
+    chk_out, chk_grad, _ = P.fused_tal_loss(x, gt, off, a, s, 80, 1.5, 1.0, 1.5)
+    assert torch.equal(out, chk_out) and torch.equal(grad, chk_grad)
