@@ -103,10 +103,13 @@ constexpr int kAccCls = 16;           // class-role sub-accumulators per image (
 constexpr int kAccDfl = 16, kAccDcls = 17, kAccWin = 18, kAccPerImage = 20;
 constexpr double kFixScale = 4294967296.0;   // 2^32
 
+// The marked arrays must be zero when a call starts: memset by the entry point, or -- YB_LOSS_WS_CLEAN -- left zero by the
+// previous call, whose last CTAs wipe every word the launch used (the image's last match CTA the image's keys and bounds,
+// the reducer the rest).
 struct LossWorkspace {
-    unsigned int *ticket;          // [16] [0] match_kernel ticket, [1] non-finite partial seen, [2] class ids out of range, } zeroed
-                                   //      [3] a consumer CTA timed out (common.cuh::dep_wait)                               } every
-    unsigned int *done;            // [N] CTAs of fused_main_kernel that have finished with the image                        } call
+    unsigned int *ticket;          // [16] [0] match_kernel ticket, [1] non-finite partial seen, [2] class ids out of range, } zero
+                                   //      [3] a consumer CTA timed out (common.cuh::dep_wait), [4] probe CTAs done          } at the
+    unsigned int *done;            // [N] CTAs of fused_main_kernel that have finished with the image                        } start
     unsigned long long *acc;       // [N * kAccPerImage] fixed-point sums: 16 x class part, DFL, QFL cell correction, winners }
     unsigned long long *best;      // [gt_total] inverted (distance, anchor) keys                                           }
     unsigned int *bound;           // [gt_total] bits of an upper bound of the GT's nearest-centre distance (0 = none yet)   }

@@ -66,10 +66,11 @@ __host__ __device__ constexpr int tal_cls_split(int tile) { return tile >= 1024 
 #define YB_TAL_CLS_UNROLL 4
 #endif
 struct TalWorkspace {
-    // zeroed by yb_tal_assign's first kernels (the counters by a memset, the per-anchor arrays by tal_decode_kernel)
-    unsigned int *ticket;               // [0] finalize ticket, [1] / [7] / [8] next unit of tal_gt_kernel's three kinds of work, [9] units resolved, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived
+    // the counters: zero when yb_tal_assign starts -- memset there, or (YB_TAL_WS_CLEAN) wiped by the previous step's tal_finalize_kernel
+    unsigned int *ticket;               // [0] finalize ticket, [1] / [7] / [8] next unit of tal_gt_kernel's three kinds of work, [9] units resolved, [2] GT rows with a class id outside [0, nc), [3] grid hint rejected, [4] a peer's entry never arrived, [10] a wait on img_done timed out
     unsigned long long *stat_acc;       // [kTalStatAcc] fixed-point sums of the target scores, [kTalStatAcc] foreground counts, [1] total #foreground
     unsigned int *img_done;             // [N]  tal_decode_kernel CTAs that have finished with the image (tal_gt_kernel starts on an image behind this count)
+    // armed (zeroed) by tal_decode_kernel, every call
     unsigned long long *akey;           // [N * A]  (overlap bits << 32) | ~gt_local   (0 = nobody)
     int *aslot;                         // [N * A]  1 + (g * topk + r) of the GT slot that owns the anchor (0 = background)
     // plain scratch
