@@ -1298,7 +1298,9 @@ tal_finalize_kernel(T *__restrict__ grad, const long long *fcell_off, const floa
     if (threadIdx.x == 0) {
         const double tss = fmax((double)tss_dev[0], 1.0);
         const float l_cls = (float)(s[0][0] / tss), l_box = (float)(s[1][0] / tss), l_dfl = (float)(s[2][0] / tss);
-        out_loss[0] = lambda_box * l_box + lambda_cls * l_cls + lambda_dfl * l_dfl;
+        // (ticket[10]: a warp of tal_gt_kernel gave up waiting for an image's decode CTAs -- cannot happen, every producer is
+        // resident before the first consumer exists; if it ever did, the loss is NaN, not silently wrong)
+        out_loss[0] = ticket[10] != 0u ? __int_as_float(0x7fc00000) : lambda_box * l_box + lambda_cls * l_cls + lambda_dfl * l_dfl;
         out_loss[1] = l_box;
         out_loss[2] = l_cls;
         out_loss[3] = l_dfl;
