@@ -968,6 +968,15 @@ __device__ __forceinline__ void tal_gt_resolve(const TalGtArgs<T> &A, const TalR
 // (common.cuh), GT CTAs of image i placed `lag` CTAs behind the image's decode CTAs: 255 / 244 / 225 / 216 us for the
 // assign phase at a lag of 100 / 300 / 1000 / all CTAs against 206 us for the two launches -- the long-lived GT CTAs take
 // the resident slots the streaming role needs to keep HBM busy, and a per-image GT queue balances worse than a global one.
+#ifdef YB_TAL_TRACE                   // measurement aid (scratch/trace_tal.py): when every warp of tal_gt_kernel passed its phases
+__device__ ulonglong4 g_tal_trace[1 << 13];
+__device__ unsigned long long g_tal_trace2[1 << 13];
+__device__ __forceinline__ unsigned long long tal_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+extern "C" int yb_tal_trace_dump(void *dst, void *dst2) {
+    int rc = (int)cudaMemcpyFromSymbol(dst, g_tal_trace, sizeof(g_tal_trace));
+    return rc ? rc : (int)cudaMemcpyFromSymbol(dst2, g_tal_trace2, sizeof(g_tal_trace2));
+}
+#endif
 template <typename T>
 __global__ void __launch_bounds__(32 * kTopkWarps, YB_TOPK_MINBLOCKS)
 tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *grid_rejected,
@@ -985,6 +994,9 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
     // orders the warp's reads behind the producers' release; the units further down read behind the per-GT / per-unit
     // acquires that chain back to it.  griddepcontrol.wait at the END of the kernel keeps the stream's completion order
     // (tal_cls_kernel waits for THIS grid only).
+#ifdef YB_TAL_TRACE
+    const unsigned long long tr0 = tal_now();
+#endif
     if (lane == 0) dep_wait(img_done, (unsigned int)decode_tiles, next_gt + 9);
     __syncwarp();
     const bool regular = A.grid.n_levels > 0 && __ldcg(grid_rejected) == 0u;   // uniform over the launch
@@ -999,6 +1011,10 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
     // last unit publishes the rank's statistics.  (Measured and not kept: the warp that finishes an image's last GT
     // resolving that image, one lane per GT: a release fence per GT and a serial tail per image, 216 us against 185 us
     // for the assign phase; the target scores as a launch of their own: 10 us more.)
+    // (Measured and not kept: the large GTs first -- a pass over the draws that only takes GTs with >= 600 anchors inside, then
+    // the rest.  The slowest selection ends at 80 us instead of 89, but the second round of draws (an atomic and a dependent
+    // load per skipped GT) delays every warp: selections done at 48 us instead of 42 for the median warp, kernel 103 us
+    // instead of 97, step 313 vs 307 us; scratch/trace_tal.py prints the phase times per warp.)
     for (;;) {
         int g = 0;
         if (lane == 0) g = (int)atomicAdd(next_gt, 1u);
@@ -1012,6 +1028,9 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
         }
         tal_gt_body<T>(A, g, n, g - __ldg(A.gt_off + n), regular, s_aq[warp]);
     }
+#ifdef YB_TAL_TRACE
+    const unsigned long long tr1 = tal_now();
+#endif
     for (;;) {
         int g = 0;
         if (lane == 0) g = (int)atomicAdd(next_gt + 6, 1u);     // ticket[7]
@@ -1019,6 +1038,9 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
         if (g >= A.gt_total) break;
         tal_gt_terms<T>(A, g);
     }
+#ifdef YB_TAL_TRACE
+    const unsigned long long tr2 = tal_now();
+#endif
     const int n_units = (A.gt_total + 1) >> 1;
     for (;;) {
         int u = 0;
@@ -1036,8 +1058,16 @@ tal_gt_kernel(const TalGtArgs<T> A, const TalResolveArgs R, const unsigned int *
             tal_publish_stats(R.stat_acc, grid_rejected, have_hint, out_stats, px);
         }
     }
+#ifdef YB_TAL_TRACE
+    if (lane == 0 && blockIdx.x * kTopkWarps + warp < (1 << 13)) {
+        g_tal_trace[blockIdx.x * kTopkWarps + warp] = make_ulonglong4(tr0, tr1, tr2, tal_now());
+    }
+#endif
 #if YB_TAL_PDL
     pdl_wait();                                            // (returns at once: every image this grid read was complete)
+#endif
+#ifdef YB_TAL_TRACE
+    if (lane == 0 && blockIdx.x * kTopkWarps + warp < (1 << 13)) g_tal_trace2[blockIdx.x * kTopkWarps + warp] = tal_now();
 #endif
 }
 
